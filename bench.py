@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""Benchmark of the Sub-GC hot path (BASELINE.json metric: captions/sec, 36-node sub-graphs, 20-token decode).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode greedy|topk|beam]
+
+One step = one pass of the whole path (fusion -> GCN -> sGPN -> NMS -> prepare -> 20-token decode) over one batch of
+128 synthetic images per GPU (BASELINE config 2: 128 images x 36 nodes x 2048-d, one full 36-node sub-graph kept per
+image, greedy decode).  N > 1: launched by torchrun, every rank decodes its own 128 images (weak scaling, no
+data-path collective; NCCL only carries the barrier and the max-over-ranks time).
+
+Prints ONE JSON line on rank 0:
+  value        whole-job captions/s with inputs resident in HBM (CUDA-event timed, max over ranks)
+  e2e          same metric through the public model API from pinned HOST buffers, H2D + D2H inside the timed region
+  roofline     decode loop (subgc_decode_sample): algorithmic bytes per launch / CUDA-event duration vs measured HBM peak
+  cpu_baseline the oracle port of the reference algorithm (torch CPU ops) on this box's host cores, same workload
+`--impl reference` times that CPU path alone (the reference itself is pure PyTorch; oracle/ restates it and is pinned to
+it by tests/golden — the one place besides tests/smoke where bench.py executes oracle/).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "sub-gc_b200"))
+
+import torch  # noqa: E402
+
+from subgc import synth  # noqa: E402
+from subgc.config import Dims, make_opt  # noqa: E402
+
+IMAGES_PER_GPU = 128
+SEED = 2019  # test.py:21 of the reference
+METRIC = "captions/sec (36-node sub-graphs, 20-token decode)"
+
+# algorithmic work of the decode loop, fp32 storage (SURVEY §8d / BASELINE.md §4)
+W_BYTES = 4 * (4000 * 3000 + 4000 * 1000 + 4000 * 2000 + 4000 * 1000 + 512 * 1000 + 9488 * 1000) \
+    + 4 * (8000 + 8000 + 512 + 9488)                       # LSTM + h2att + logit weights and biases: 152.1 MB
+ROW_BYTES = 4 * (36 * 1000 + 36 * 512 + 8 * 1000 + 1000 + 1000)  # att + p_att + state r/w + fc + embed row: 257.7 KB
+ROW_FLOPS = 76.13e6
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), float(j.get("bf16_tflops_sustained", j.get("bf16_tflops", 1590.0))), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop_flag, self.th = index, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def start(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.th:
+            self.th.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_inputs(d, rank):
+    data = synth.make_test_inputs(d, SEED + rank, n_images=IMAGES_PER_GPU, per_half=1, ragged=False, ragged_edges=False)
+    return data
+
+
+def cpu_reference(d, sd, data, mode, steps, warmup, threads):
+    """The reference algorithm on host cores (oracle port), whole workload per step.  Returns captions/s, ms/step."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import subgc_oracle as O
+    torch.set_num_threads(threads)
+    kw = dict(use_nms=True, iou_thres=0.75, max_subgraphs=1)
+    if mode == "topk":
+        kw.update(topk=True, temp=0.6, k=3)
+    elif mode == "beam":
+        kw.update(beam_size=5)
+    n = None
+    with torch.no_grad():
+        for _ in range(warmup):
+            n = O.sample(sd, d, data, **kw)["seq"].shape[0]
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            n = O.sample(sd, d, data, **kw)["seq"].shape[0]
+        dt = time.perf_counter() - t0
+    return n * steps / dt, dt / steps * 1e3, n
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="greedy", choices=["greedy", "topk", "beam"])
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    d = Dims()
+    config = {"workload": f"BASELINE config 2: {IMAGES_PER_GPU} images/GPU x 36 nodes x 2048-d, 64 edges, 1 full sub-graph kept per image "
+                          f"(NMS 0.75/max 1), {args.mode} 20-token decode, V=9487",
+              "images_per_gpu": IMAGES_PER_GPU, "rows_per_gpu": IMAGES_PER_GPU, "decode": args.mode, "weights": "random init (synthetic), fp32",
+              "l2": "per-step working set (280 MB weights + 83 MB inputs + activations) exceeds the 126 MB L2; no explicit flush"}
+    cores = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sd = synth.make_state_dict(d, SEED)
+        data = make_inputs(d, 0)
+        val, ms, n = cpu_reference(d, sd, data, args.mode, max(args.steps, 1), args.warmup, cores)
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "captions/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": "captions/s", "cores": cores, "kind": "port",
+                                 "sample": f"whole workload: {n} captions per step (oracle port of the reference's PyTorch path, "
+                                           f"torch {torch.__version__} CPU, {cores} threads)"},
+                "e2e": {"value": val, "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the product path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from subgc import _lib
+    from subgc.model import setup
+
+    sd = synth.make_state_dict(d, SEED)
+    model = setup(make_opt(d, test_LSTM=1, gpn_nms_thres=0.75, gpn_max_subg=1, use_topk_sampling=1 if args.mode == "topk" else 0))
+    model.load_state_dict(sd)
+    model.to(dev).eval()
+    data = make_inputs(d, rank)
+    names = [k for k in synth.SAMPLE_ARG_ORDER]
+    host = {k: (data[k].pin_memory() if data[k] is not None else None) for k in names}
+    resident = {k: (host[k].to(dev) if host[k] is not None else None) for k in names}
+    opt = {"beam_size": 5 if args.mode == "beam" else 1}
+    if args.mode == "topk":
+        opt["seed"] = SEED
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host.values() if t is not None)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        return model(*[resident[k] for k in names], opt=opt, mode="sample")
+
+    def step_e2e():
+        args_dev = [host[k].to(dev, non_blocking=True) if host[k] is not None else None for k in names]
+        out = model(*args_dev, opt=opt, mode="sample")
+        res = [t.to("cpu", non_blocking=True) if t.is_cuda else t for t in out]
+        torch.cuda.synchronize()
+        return res
+
+    L = _lib.lib()
+    with torch.no_grad():
+        for _ in range(warmup):
+            out = step_resident()
+        n_rows = out[0].shape[0]
+        assert n_rows == IMAGES_PER_GPU, n_rows
+        # ---- timed region 1: device-resident inputs -----------------------------------------------------------------
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        barrier()
+        if sampler:
+            sampler.start()
+        model.stage_events = []
+        launches0 = L.subgc_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            out = step_resident()
+        e1.record()
+        barrier()
+        launches = L.subgc_launch_count() - launches0
+        ms_total = e0.elapsed_time(e1)
+        stage_ms = {}
+        for name, a, b in model.stage_events:
+            stage_ms[name] = stage_ms.get(name, 0.0) + a.elapsed_time(b)
+        model.stage_events = None
+        # ---- timed region 2: end to end from pinned host memory -----------------------------------------------------
+        for _ in range(2):
+            res = step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            res = step_e2e()
+        f1.record()
+        barrier()
+        e2e_ms_total = f0.elapsed_time(f1)
+        d2h_bytes = sum(t.numel() * t.element_size() for t in res)
+        clocks = sampler.stop() if sampler else None
+
+    times = torch.tensor([ms_total, e2e_ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms_total = float(times[0]), float(times[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    steps_exec = int(model.last_steps.item()) if model.last_steps is not None else d.seq_length + 1
+    total_caps = n_rows * world * args.steps
+    value = total_caps / (ms_total * 1e-3)
+    e2e_value = total_caps / (e2e_ms_total * 1e-3)
+    hbm_peak, tf_peak, peak_kind = load_peaks()
+    line = {"metric": METRIC, "value": value, "unit": "captions/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "captions/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "ms_per_step": e2e_ms_total / args.steps},
+            "gpu_launches": int(launches), "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
+            "decode_steps_executed": steps_exec}
+    if args.mode != "beam" and "decode" in stage_ms:
+        t_dec = stage_ms["decode"] / args.steps * 1e-3           # one launch of the decode loop (subgc_decode_sample)
+        algo_steps = d.seq_length                                 # 20 algorithmic steps per caption
+        algo_bytes = algo_steps * (W_BYTES + n_rows * ROW_BYTES)
+        achieved = algo_bytes / t_dec / 1e9
+        line["roofline"] = {"bound": "hbm", "kernel": "decode loop (subgc_decode_sample: 20 x [att-LSTM, attention, lang-LSTM, logit, select])",
+                            "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                            "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
+                            "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": t_dec * 1e3,
+                            "tensor_equiv": {"achieved_tflops": algo_steps * n_rows * ROW_FLOPS / t_dec / 1e12, "peak_tflops": tf_peak,
+                                             "note": "fp32 FMA path: tensor pipe unused in this round"}}
+    if not args.no_cpu_baseline:
+        cval, cms, cn = cpu_reference(d, sd, data, args.mode, args.cpu_steps, 1, cores)
+        line["cpu_baseline"] = {"value": cval, "unit": "captions/s", "cores": cores, "kind": "port", "ms_per_step": cms,
+                                "sample": f"whole workload ({cn} captions per step), {args.cpu_steps} steps after 1 warm-up; oracle port of the "
+                                          f"reference's PyTorch path on {cores} host threads"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

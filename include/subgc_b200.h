@@ -1,0 +1,240 @@
+/*
+ * subgc_b200 — C ABI of the B200-native Sub-GC hot path (sm_100a).
+ *
+ * The reference (YiwuZhong/Sub-GC) is pure Python/PyTorch and has no FFI; the boundary it exposes is the
+ * nn.Module surface `models.setup(opt)` -> `AttModel.forward(mode=...)` (reference models/__init__.py:43-59,
+ * models/CaptionModel.py:21-26) and `LossWrapper` (models/loss_wrapper.py:7-27).  This header is the native layer a
+ * replacement of that path binds to (ctypes in `sub-gc_b200/subgc/_lib.py`; SURVEY.md §8b lists the contract):
+ *
+ *   - every entry point is `extern "C"`, returns int (0 = ok, non-zero = SUBGC_E_*; text via subgc_last_error()),
+ *   - takes raw DEVICE pointers + explicit sizes + a cudaStream_t, never allocates, frees or synchronises,
+ *   - keeps no global mutable state (thread-local error string only), so DataParallel-style threads and
+ *     one-process-per-GPU both work, and every call can be captured into a CUDA graph by the caller,
+ *   - scratch memory is caller-provided; size it with the matching *_workspace_bytes() query.
+ *
+ * All floating-point tensors are fp32 row-major; index tensors are int64 exactly as the reference loaders emit
+ * them (dataloaders/dataloader.py:194-206, dataloaders/dataloader_test.py:191-203).
+ * Each function names the reference code it replaces (file:line relative to the reference root).
+ */
+#ifndef SUBGC_B200_H
+#define SUBGC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SUBGC_ABI_VERSION 1
+#define SUBGC_MAX_GCN_LAYERS 8
+
+typedef void* subgc_stream_t; /* cudaStream_t */
+
+enum {
+    SUBGC_OK = 0,
+    SUBGC_E_INVALID = 1,   /* bad argument (null pointer, size, unsupported option) */
+    SUBGC_E_WORKSPACE = 2, /* workspace too small */
+    SUBGC_E_CUDA = 3,      /* a CUDA runtime call / launch failed */
+    SUBGC_E_UNSUPPORTED = 4
+};
+
+/* Dimensions: the `opt` attributes AttModel.__init__ reads (models/AttModel.py:44-69). */
+typedef struct subgc_dims {
+    int32_t vocab1;       /* vocab_size + 1 (logit rows)            */
+    int32_t enc;          /* input_encoding_size X                  */
+    int32_t rnn;          /* rnn_size H                             */
+    int32_t att_hid;      /* att_hid_size AH (also sGPN hidden)     */
+    int32_t fc_feat;      /* fc_feat_size                           */
+    int32_t att_feat;     /* att_feat_size A (== 2*gcn)             */
+    int32_t gcn;          /* gcn_dim L                              */
+    int32_t low_rank;     /* GCN unit low-rank width R (512)        */
+    int32_t embed;        /* embed_dim E                            */
+    int32_t obj_classes;  /* C (1599)                               */
+    int32_t pred_classes; /* P (21)                                 */
+    int32_t gcn_layers;
+    int32_t gcn_residual;
+    int32_t pred_emb_type;
+    int32_t seq_length;   /* T                                      */
+    int32_t obj_num;      /* N (37)                                 */
+    int32_t rel_num;      /* K (65)                                 */
+} subgc_dims;
+
+typedef struct subgc_linear {
+    const float* w; /* [out, in] as nn.Linear stores it */
+    const float* b; /* [out] */
+} subgc_linear;
+
+/* Device pointers to the reference state_dict tensors, un-repacked (key names in comments). */
+typedef struct subgc_weights {
+    subgc_linear obj_v_proj;                           /* obj_v_proj.{weight[L,A],bias}                         */
+    const float* sg_obj_embed;                         /* sg_obj_embed.weight [C,E]                             */
+    subgc_linear obj_emb_proj;                         /* obj_emb_proj [L,E]                                    */
+    const float* sg_pred_embed;                        /* sg_pred_embed.weight [P,E]                            */
+    subgc_linear pred_emb_prj;                         /* pred_emb_prj [L,E]                                    */
+    subgc_linear gcn_lft[SUBGC_MAX_GCN_LAYERS][4];     /* gcn_backbone.gcn.l.gcn_collect.collect_units.u.fc_lft [R,L] */
+    subgc_linear gcn_rgt[SUBGC_MAX_GCN_LAYERS][4];     /* ...fc_rgt [L,R]                                       */
+    subgc_linear gpn_fc0;                              /* gpn_layer.gpn_fc.0 [AH,2L]                            */
+    subgc_linear gpn_fc3;                              /* gpn_layer.gpn_fc.3 [1,AH]                             */
+    subgc_linear read_out0;                            /* gpn_layer.read_out_proj.0 [AH,2L]                     */
+    subgc_linear read_out1;                            /* gpn_layer.read_out_proj.1 [2L,AH]                     */
+    subgc_linear logit;                                /* logit [V1,H]                                          */
+    const float* embed;                                /* embed.0.weight [V1,X]                                 */
+    subgc_linear fc_embed0;                            /* fc_embed.0 [FC,A]                                     */
+    subgc_linear fc_embed2;                            /* fc_embed.2 [H,FC]                                     */
+    subgc_linear att_embed;                            /* att_embed.0 [H,L]                                     */
+    subgc_linear ctx2att;                              /* ctx2att [AH,H]                                        */
+    subgc_linear h2att;                                /* core.attention.h2att [AH,H]                           */
+    subgc_linear alpha_net;                            /* core.attention.alpha_net [1,AH]                       */
+    const float* att_w_ih; const float* att_w_hh;      /* core.att_lstm.weight_ih [4H,X+2H], weight_hh [4H,H]   */
+    const float* att_b_ih; const float* att_b_hh;
+    const float* lang_w_ih; const float* lang_w_hh;    /* core.lang_lstm.weight_ih [4H,2H], weight_hh [4H,H]    */
+    const float* lang_b_ih; const float* lang_b_hh;
+} subgc_weights;
+
+/* How sub-graph s of a flat list maps onto the loader tensors gpn_obj_ind / att_masks [rows,2,per_half,N].
+ *   order 0 (training, models/lib/gpn.py:157-170): s = (half*rows + row)*per_half + g      (positives first)
+ *   order 1 (inference, models/lib/gpn.py:86-94):  s = (image*2 + half)*per_half + g, row = image*seq_per_img
+ * image(s) = row / seq_per_img.  n_sub = 2*rows*per_half (order 0) or 2*(rows/seq_per_img)*per_half (order 1). */
+typedef struct subgc_subgraph_layout {
+    int32_t rows;        /* leading dim of the loader tensors (5B)  */
+    int32_t per_half;    /* G (training) or M (inference)           */
+    int32_t seq_per_img; /* 5                                       */
+    int32_t order;       /* 0 training, 1 inference                 */
+} subgc_subgraph_layout;
+
+const char* subgc_last_error(void);
+int subgc_version(void);
+/* kernels launched so far by the calling thread through this library (instrumentation for bench.py's gpu_launches) */
+unsigned long long subgc_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Building block: C[M,N] = act((A[gather] . W^T + bias + addend) / div), the nn.Linear contraction every stage
+ * of the path is made of (exported for unit tests; fp32 FMA accumulation).
+ * ------------------------------------------------------------------------------------------------------- */
+size_t subgc_linear_workspace_bytes(int M, int N, int K);
+int subgc_linear_forward(int M, int N, int K, const float* A, int lda, const int64_t* a_gather /*nullable*/,
+                         const float* W, int ldw, const float* bias /*nullable*/, int relu, float* C, int ldc,
+                         void* ws, size_t ws_bytes, subgc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Encoder.
+ * subgc_fuse_nodes  replaces AttModel.feat_fusion (models/AttModel.py:370-387):
+ *    x0[b,n] = relu(W_v att[b,n] + b_v + W_e E_obj[1+argmax(obj_dist[b,n,1:])] + b_e)
+ *    p0[b,k] = W_p E_pred[cls(pred_dist[b,k])] + b_p          (skipped when p0 == NULL)
+ * subgc_gcn_forward replaces gcn_backbone.forward/make_map (models/lib/gcn_backbone.py:29-67),
+ *    _GraphConvolutionLayer.forward (models/lib/graph_conv.py:15-34) and _Collection_Unit.forward
+ *    (models/lib/graph_conv_unit.py:28-36) with an edge-list gather / segment-mean instead of the dense
+ *    adjacency bmm.  Outputs are NOT tiled x5 (gcn_backbone.py:50-51): consumers index image = row/5.
+ *    x_pred == NULL skips every unit whose result cannot reach x_obj (for Sub-GC: half of them).
+ * ------------------------------------------------------------------------------------------------------- */
+size_t subgc_encoder_workspace_bytes(const subgc_dims* d, int n_images);
+int subgc_fuse_nodes(const subgc_dims* d, const subgc_weights* w, int n_images, const float* att_feats,
+                     const float* obj_dist, const float* pred_dist, float* x0, float* p0 /*nullable*/,
+                     void* ws, size_t ws_bytes, subgc_stream_t stream);
+int subgc_gcn_forward(const subgc_dims* d, const subgc_weights* w, int n_images, const float* x0,
+                      const float* p0 /*nullable iff not needed*/, const int64_t* rel_ind, float* x_obj,
+                      float* x_pred /*nullable*/, void* ws, size_t ws_bytes, subgc_stream_t stream);
+/* 1 if p0 (the predicate embedding) influences x_obj / x_pred for this configuration, else 0. */
+int subgc_gcn_needs_pred(const subgc_dims* d, int want_x_pred);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * sGPN.  subgc_sgpn_forward replaces gpn_layer.extract_subgraph_feats + graph_pooling + gpn_fc + sigmoid
+ * (models/lib/gpn.py:50-57,152-185) for the n_sub sub-graphs described by `lay`:
+ *    read_out[s] = [max_n F ‖ sum_n F / len],  F = rows of x_obj[image(s)] listed in gpn_obj_ind, zero beyond len
+ *    score[s]    = sigmoid(w2 . relu(W1 read_out[s] + b1) + b2)          (eval-mode: no dropout)
+ *    sub_len[s]  = number of ones in att_masks (the loader's pooling matrix is diag(first len ones))
+ *    bce_loss    = mean BCE(score, 1 for the first half of the list, 0 for the second)   (nullable)
+ * ------------------------------------------------------------------------------------------------------- */
+size_t subgc_sgpn_workspace_bytes(const subgc_dims* d, int n_sub);
+int subgc_sgpn_forward(const subgc_dims* d, const subgc_weights* w, const subgc_subgraph_layout* lay,
+                       const float* x_obj, const int64_t* gpn_obj_ind, const float* att_masks, float* read_out,
+                       float* score, int32_t* sub_len, float* bce_loss /*nullable*/, void* ws, size_t ws_bytes,
+                       subgc_stream_t stream);
+
+/* Training-mode selection (models/lib/gpn.py:64-81): for each sentence row pick argmax_first over its per_half
+ * positive scores.  sel[row] = flat sub-graph id; stats[0] = n rows, stats[1] = max length of the picks. */
+int subgc_sgpn_select_train(const subgc_subgraph_layout* lay, const float* score, const int32_t* sub_len,
+                            int32_t* sel, int32_t* stats, subgc_stream_t stream);
+
+/* Inference-mode NMS, per image (models/lib/gpn.py:108-150): greedy suppression in descending score order
+ * (ties: higher index first) of sub-graphs whose node-set IoU with a kept one exceeds iou_thres (compared in
+ * double like the reference), at most max_subgraphs survivors per image, emitted in ascending original index.
+ * use_nms == 0 keeps everything (gpn.py:97).  Outputs: sel [n_sub] flat ids of kept sub-graphs, images in order,
+ * compacted; keep_ind [n_sub] the per-image index of each kept one; stats[0] = total kept, stats[1] = max length
+ * among kept, stats[2 + i] = kept count of image i. */
+size_t subgc_nms_workspace_bytes(int n_images, int per_image);
+int subgc_subgraph_nms(const subgc_dims* d, const subgc_subgraph_layout* lay, const float* score,
+                       const int32_t* sub_len, const int64_t* gpn_obj_ind, const float* att_masks, int use_nms,
+                       double iou_thres, int max_subgraphs, int32_t* sel, int64_t* keep_ind, int32_t* stats,
+                       void* ws, size_t ws_bytes, subgc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Decoder feature preparation: replaces gpn read_out_proj (models/lib/gpn.py:79,95), AttModel.clip_att /
+ * _prepare_feature / pack_wrapper (models/AttModel.py:16-36,348-368) for the n_rows selected sub-graphs `sel`:
+ *    g_fc  = W_b(W_a read_out[sel] + b_a) + b_b                      [n_rows, 2L]   (reference `fc_feats`)
+ *    fc    = relu(W2 relu(W1 g_fc + b1) + b2)                        [n_rows, H]
+ *    att   = relu(W_a x_obj[image, ids[n]] + b_a) for n < len else 0 [n_rows, len_max, H]
+ *    p_att = W_c att + b_c                                           [n_rows, len_max, AH]
+ *    masks = att_masks[sel, :len_max]                                [n_rows, len_max]
+ * ------------------------------------------------------------------------------------------------------- */
+size_t subgc_prepare_workspace_bytes(const subgc_dims* d, int n_rows, int len_max);
+int subgc_prepare_forward(const subgc_dims* d, const subgc_weights* w, const subgc_subgraph_layout* lay,
+                          int n_rows, int len_max, const int32_t* sel, const float* x_obj,
+                          const int64_t* gpn_obj_ind, const float* att_masks, const float* read_out,
+                          float* g_fc, float* fc, float* att, float* p_att, float* masks, void* ws,
+                          size_t ws_bytes, subgc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Decoder.  One step = AttModel.get_logprobs_state (models/AttModel.py:328-341) = embed+ReLU, TopDownCore.forward
+ * (:400-431: att-LSTM, Attention.forward :445-471, lang-LSTM) and logit + log_softmax.
+ * rows_per_ctx > 1 lets consecutive rows share one (att, p_att, masks, fc) entry (beam search: the beams of a
+ * sub-graph).  State tensors are [2, n_rows, H] (index 0 attention LSTM, 1 language LSTM), in/out distinct.
+ * ------------------------------------------------------------------------------------------------------- */
+size_t subgc_decode_workspace_bytes(const subgc_dims* d, int n_rows, int len_max);
+int subgc_decode_step(const subgc_dims* d, const subgc_weights* w, int n_rows, int len_max, int rows_per_ctx,
+                      const int64_t* it, const float* fc, const float* att, const float* p_att,
+                      const float* masks, const float* h_in, const float* c_in, float* h_out, float* c_out,
+                      float* logprobs /*[n_rows,V1]*/, float* att_weights /*nullable [n_rows,len_max]*/,
+                      void* ws, size_t ws_bytes, subgc_stream_t stream);
+
+/* Whole greedy / top-k loop of AttModel._sample (models/AttModel.py:278-326): T+1 decoder steps, finish masks and
+ * the all-finished early exit evaluated on the device (no host sync).
+ *   mode 0: greedy argmax (first index on ties).
+ *   mode 1: top-k sampling: q = log_softmax(logp / temp); keep the k largest; draw from softmax(kept) by
+ *           inverse CDF over the kept tokens in descending order using uniforms[t*n_rows + r] if given, else a
+ *           Philox4x32-10 stream keyed by (seed, offset, t, r); seqLogprobs holds q[token] (un-renormalised).
+ * Outputs: seq [n_rows,T] int64, seq_logprobs [n_rows,T], att_weights (nullable) [n_rows,T+1,len_max],
+ * steps_done[0] = decoder steps executed (<= T+1).  Columns after an early exit stay zero. */
+int subgc_decode_sample(const subgc_dims* d, const subgc_weights* w, int n_rows, int len_max, int mode,
+                        float temp, int top_k, uint64_t seed, uint64_t offset, const float* uniforms /*nullable*/,
+                        const float* fc, const float* att, const float* p_att, const float* masks,
+                        int64_t* seq, float* seq_logprobs, float* att_weights /*nullable*/,
+                        int32_t* steps_done, void* ws, size_t ws_bytes, subgc_stream_t stream);
+
+/* Teacher-forced decoding of AttModel._forward (models/AttModel.py:150-177, sampling_prob == 0, eval mode): step i
+ * is fed tokens[:, i]; outputs[:, i] = log-probs; from the first column i >= 1 that is entirely zero on, the loop
+ * stops and the remaining outputs stay zero (AttModel.py:170-171), evaluated on the device.
+ * tokens [n_rows, ld_tok] int64 (labels), outputs [n_rows, n_steps, V1]. */
+size_t subgc_teacher_workspace_bytes(const subgc_dims* d, int n_rows, int n_steps);
+int subgc_decode_teacher(const subgc_dims* d, const subgc_weights* w, int n_rows, int len_max, int n_steps,
+                         const int64_t* tokens, int ld_tok, const float* fc, const float* att, const float* p_att,
+                         const float* masks, float* outputs, void* ws, size_t ws_bytes, subgc_stream_t stream);
+
+/* Batched beam search: AttModel._sample_sentences + CaptionModel.beam_search with group_size 1
+ * (models/AttModel.py:208-234, models/CaptionModel.py:43-94,97-176) for n_sub sub-graphs at once, beam_size rows
+ * each.  length_penalty: 0 none, 1 wu_alpha, 2 avg (misc/utils.py:242-266).
+ * Outputs (per sub-graph, the reference's `done_beams` list in its final order, best first):
+ *   done_seq [n_sub, beam, T] int64, done_logps [n_sub, beam, T], done_p [n_sub, beam] (double),
+ *   done_unaug_p [n_sub, beam] (double), done_count [n_sub]. */
+size_t subgc_beam_workspace_bytes(const subgc_dims* d, int n_sub, int beam_size, int len_max);
+int subgc_decode_beam(const subgc_dims* d, const subgc_weights* w, int n_sub, int len_max, int beam_size,
+                      int length_penalty, double lp_alpha, int decoding_constraint, const float* fc,
+                      const float* att, const float* p_att, const float* masks, int64_t* done_seq,
+                      float* done_logps, double* done_p, double* done_unaug_p, int32_t* done_count, void* ws,
+                      size_t ws_bytes, subgc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUBGC_B200_H */

@@ -1,0 +1,209 @@
+// Internal helpers shared by the subgc_b200 translation units (not part of the C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "subgc_b200.h"
+
+namespace subgc {
+
+void set_error(const char* fmt, ...);
+void count_launch();  // per-thread tally of kernels launched through this library (subgc_launch_count)
+
+#define SUBGC_CHECK_ARG(cond, ...)                 \
+    do {                                           \
+        if (!(cond)) {                             \
+            subgc::set_error(__VA_ARGS__);         \
+            return SUBGC_E_INVALID;                \
+        }                                          \
+    } while (0)
+
+#define SUBGC_CUDA(expr)                                                                      \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            subgc::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return SUBGC_E_CUDA;                                                              \
+        }                                                                                     \
+    } while (0)
+
+#define SUBGC_LAUNCH_CHECK()                                                                  \
+    do {                                                                                      \
+        subgc::count_launch();                                                                \
+        cudaError_t e__ = cudaGetLastError();                                                 \
+        if (e__ != cudaSuccess) {                                                             \
+            subgc::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return SUBGC_E_CUDA;                                                              \
+        }                                                                                     \
+    } while (0)
+
+#define SUBGC_TRY(expr)            \
+    do {                           \
+        int rc__ = (expr);         \
+        if (rc__ != SUBGC_OK) return rc__; \
+    } while (0)
+
+constexpr int kNumSMs = 148;  // B200
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Bump allocator over the caller-provided workspace.
+struct Workspace {
+    char* base;
+    size_t size;
+    size_t used;
+    Workspace(void* p, size_t n) : base(static_cast<char*>(p)), size(n), used(0) {}
+    template <typename T>
+    T* take(size_t count) {
+        size_t off = align_up(used, 256);
+        size_t bytes = count * sizeof(T);
+        if (base == nullptr || off + bytes > size) {
+            used = size + 1;  // poison
+            return nullptr;
+        }
+        used = off + bytes;
+        return reinterpret_cast<T*>(base + off);
+    }
+    bool ok() const { return used <= size; }
+    size_t remaining() const { size_t off = align_up(used, 256); return off >= size ? 0 : size - off; }
+    void* cursor() { return base + align_up(used, 256); }
+};
+
+// ---- GEMM building block -----------------------------------------------------------------------------
+// C[M,N] = epilogue( sum over segments  A_seg[M,K_seg] . W_seg[N,K_seg]^T ).  Segments let the decoder contract
+// the concatenated LSTM input [h_lang | fc | relu(E[it])] (+ h_att through weight_hh) straight from the caller's
+// tensors and the reference's un-repacked weight_ih / weight_hh, with no concat buffer.
+struct GemmSeg {
+    const float* A;          // [rows, K] row-major, leading dim lda
+    const float* W;          // [N, K] row-major (nn.Linear layout), leading dim ldw
+    const long long* gather; // optional: A row index per output row (e.g. token ids into the embedding table)
+    int lda, ldw, K;
+    int a_row_div;           // A row = m / a_row_div (rows shared by consecutive outputs; 1 = identity)
+    int relu_a;              // apply ReLU to A elements on load (embed + ReLU)
+    const int* gather32;     // optional 32-bit variant of `gather` (sub-graph selections)
+};
+
+inline GemmSeg make_seg(const float* A, int lda, const float* W, int ldw, int K) {
+    GemmSeg s;
+    s.A = A; s.W = W; s.gather = nullptr; s.lda = lda; s.ldw = ldw; s.K = K; s.a_row_div = 1; s.relu_a = 0; s.gather32 = nullptr;
+    return s;
+}
+
+struct GemmEpilogue {
+    const float* bias = nullptr;    // [N]
+    const float* bias2 = nullptr;   // [N] second bias (LSTM b_ih + b_hh)
+    const float* addend = nullptr;  // optional [*, ld_add] rows added before activation
+    const long long* add_gather = nullptr;  // addend row index per output row (nullptr: row m)
+    const int* add_gather32 = nullptr;
+    int ld_add = 0;
+    float div = 0.f;                // != 0: divide by it (GCN mean with count 1: 1 + 1e-7 in fp32)
+    int relu = 0;
+    // rows are grouped in blocks of `group` rows; row (g, j) is valid iff j < group_len[g]; invalid rows are
+    // written as exact zeros (pack_padded_sequence semantics).  group_sel maps block -> index into group_len.
+    const int* group_len = nullptr;
+    const int* group_sel = nullptr;
+    int group = 0;
+};
+
+struct GemmProblem {
+    int M = 0, N = 0;
+    int nseg = 0;
+    GemmSeg seg[4];
+    GemmEpilogue epi;
+    float* C = nullptr;
+    int ldc = 0;
+    const int* active = nullptr;  // optional device flag: kernel exits immediately when *active == 0
+};
+
+size_t gemm_workspace_bytes(int M, int N, int Ktotal);
+// Launches the contraction (+ split-K reduction when used).  ws may be null when gemm_workspace_bytes == 0.
+int launch_gemm(const GemmProblem& p, void* ws, size_t ws_bytes, cudaStream_t stream);
+// raw_part != nullptr: leave the per-split partial sums [splits][M][N] there (the consumer reduces them in z order)
+// and report the split count through *out_splits; no epilogue is applied.
+int launch_gemm_ex(const GemmProblem& p, float* raw_part, size_t raw_part_elems, int* out_splits, void* ws, size_t ws_bytes,
+                   cudaStream_t stream);
+// upper bound of splits * M * N floats for launch_gemm_ex raw partials
+size_t gemm_partial_elems(int M, int N, int Ktotal);
+
+// ---- device helpers ------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float block_sum(float v, float* red /*[32]*/) {
+    // all threads of the block must call; returns the total to every thread (fixed reduction order)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int i = 0; i < nw; ++i) t += red[i];
+    return t;
+}
+__device__ __forceinline__ float block_max(float v, float* red /*[32]*/) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    float t = red[0];
+    for (int i = 1; i < nw; ++i) t = fmaxf(t, red[i]);
+    return t;
+}
+// (value, index) arg-max with first-index tie-break, the semantics of torch.max(dim) the reference relies on.
+__device__ __forceinline__ void argmax_combine(float& v, int& i, float ov, int oi) {
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+}
+__device__ __forceinline__ void warp_argmax(float& v, int& i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        int oi = __shfl_xor_sync(0xffffffffu, i, o);
+        argmax_combine(v, i, ov, oi);
+    }
+}
+__device__ __forceinline__ void block_argmax(float& v, int& i, float* redv /*[32]*/, int* redi /*[32]*/) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    warp_argmax(v, i);
+    __syncthreads();
+    if (lane == 0) { redv[wid] = v; redi[wid] = i; }
+    __syncthreads();
+    v = redv[0]; i = redi[0];
+    for (int w = 1; w < nw; ++w) argmax_combine(v, i, redv[w], redi[w]);
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+#endif
+
+// locate sub-graph s in the loader tensors [rows, 2, per_half, N]: returns the flat (row*2+half)*per_half+g.
+__host__ __device__ inline int subgraph_slot(const subgc_subgraph_layout& l, int s, int* image) {
+    int half, row, g;
+    if (l.order == 0) {
+        g = s % l.per_half;
+        int t = s / l.per_half;
+        row = t % l.rows;
+        half = t / l.rows;
+    } else {
+        g = s % l.per_half;
+        int t = s / l.per_half;
+        half = t % 2;
+        row = (t / 2) * l.seq_per_img;
+    }
+    if (image) *image = row / l.seq_per_img;
+    return (row * 2 + half) * l.per_half + g;
+}
+inline int subgraph_count(const subgc_subgraph_layout& l) {
+    return l.order == 0 ? 2 * l.rows * l.per_half : 2 * (l.rows / l.seq_per_img) * l.per_half;
+}
+
+}  // namespace subgc

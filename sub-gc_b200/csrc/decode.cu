@@ -1,0 +1,684 @@
+// Top-down attention-LSTM decoder: one step, the greedy / top-k sampling loop and batched beam search.
+//
+//   subgc_decode_step   <- AttModel.get_logprobs_state            (reference models/AttModel.py:328-341)
+//                          TopDownCore.forward                    (reference models/AttModel.py:400-431)
+//                          Attention.forward                      (reference models/AttModel.py:445-471)
+//   subgc_decode_sample <- AttModel._sample, beam_size == 1       (reference models/AttModel.py:278-326)
+//   subgc_decode_beam   <- AttModel._sample_sentences             (reference models/AttModel.py:208-234)
+//                          CaptionModel.beam_search / beam_step   (reference models/CaptionModel.py:43-94,97-176)
+//
+// One decoder step is: att-LSTM gates (one contraction over the un-concatenated [h_lang | fc | relu(E[it])] and
+// h_att segments) -> LSTM cell -> h2att -> fused attention (tanh / alpha / softmax / mask / renormalise / context,
+// warp-shuffle reductions) -> lang-LSTM gates -> LSTM cell -> logit.  The loops keep token feedback, finish masks,
+// the all-finished early exit and (for beam search) candidate ranking, history / state re-ordering and the
+// done-beam lists on the device: no host synchronisation anywhere, the whole loop is graph-capturable.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace subgc {
+
+// ---- pointwise LSTM cell (torch.nn.LSTMCell gate order i, f, g, o) --------------------------------------------
+__global__ void __launch_bounds__(256) lstm_cell_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev,
+                                                        const long long* __restrict__ parent, float* __restrict__ h_out,
+                                                        float* __restrict__ c_out, int S, int H, const int* __restrict__ active) {
+    if (active != nullptr && *active == 0) return;
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= S * H) return;
+    int r = idx / H, j = idx - r * H;
+    const float* g = gates + (size_t)r * 4 * H;
+    long long pr = parent ? parent[r] : r;
+    float gi = g[j], gf = g[H + j], gg = g[2 * H + j], go = g[3 * H + j];
+    float c = sigmoidf_(gf) * c_prev[(size_t)pr * H + j] + sigmoidf_(gi) * tanhf(gg);
+    c_out[idx] = c;
+    h_out[idx] = sigmoidf_(go) * tanhf(c);
+}
+
+// ---- fused attention: one block per decode row -------------------------------------------------------------------
+// e_n = w . tanh(p_att[n] + atth) + b ; alpha = softmax_n(e) ; alpha *= mask ; alpha /= sum(alpha) ; ctx = sum_n alpha_n att[n]
+__global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ atth, const float* __restrict__ p_att,
+                                                        const float* __restrict__ att, const float* __restrict__ masks,
+                                                        const float* __restrict__ alpha_w, const float* __restrict__ alpha_b,
+                                                        float* __restrict__ ctx, float* __restrict__ att_w, int att_w_stride, int len_max, int H,
+                                                        int AH, int rows_per_ctx, const int* __restrict__ active) {
+    if (active != nullptr && *active == 0) return;
+    extern __shared__ float s_att[];  // [AH] atth | [AH] alpha_w | [len_max] e
+    float* s_h = s_att;
+    float* s_w = s_att + AH;
+    float* s_e = s_att + 2 * AH;
+    const int r = blockIdx.x, cr = r / rows_per_ctx;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int j = threadIdx.x; j < AH; j += blockDim.x) {
+        s_h[j] = atth[(size_t)r * AH + j];
+        s_w[j] = __ldg(alpha_w + j);
+    }
+    __syncthreads();
+    const float* pa = p_att + (size_t)cr * len_max * AH;
+    for (int n = wid; n < len_max; n += nw) {
+        float a = 0.f;
+        for (int j = lane; j < AH; j += 32) a = fmaf(s_w[j], tanhf(__ldg(pa + (size_t)n * AH + j) + s_h[j]), a);
+        a = warp_sum(a);
+        if (lane == 0) s_e[n] = a + __ldg(alpha_b);
+    }
+    __syncthreads();
+    if (wid == 0) {  // len_max <= 64: one warp finishes the softmax / mask / renormalise
+        float m = -INFINITY;
+        for (int n = lane; n < len_max; n += 32) m = fmaxf(m, s_e[n]);
+        m = warp_max(m);
+        float sum = 0.f;
+        for (int n = lane; n < len_max; n += 32) sum += expf(s_e[n] - m);
+        sum = warp_sum(sum);
+        float msum = 0.f;
+        for (int n = lane; n < len_max; n += 32) {
+            float wv = expf(s_e[n] - m) / sum;
+            wv = wv * __ldg(masks + (size_t)cr * len_max + n);
+            s_e[n] = wv;
+            msum += wv;
+        }
+        msum = warp_sum(msum);
+        for (int n = lane; n < len_max; n += 32) {
+            float wv = s_e[n] / msum;
+            s_e[n] = wv;
+            if (att_w) att_w[(size_t)r * att_w_stride + n] = wv;
+        }
+    }
+    __syncthreads();
+    const float* af = att + (size_t)cr * len_max * H;
+    for (int j = threadIdx.x; j < H; j += blockDim.x) {
+        float a = 0.f;
+        for (int n = 0; n < len_max; ++n) a = fmaf(s_e[n], __ldg(af + (size_t)n * H + j), a);
+        ctx[(size_t)r * H + j] = a;
+    }
+}
+
+// ---- row-wise log_softmax (materialised log-probs: get_logprobs_state API and beam search) ----------------------
+__global__ void __launch_bounds__(256) log_softmax_kernel(const float* __restrict__ logits, float* __restrict__ logp, int V1,
+                                                          size_t out_stride, const int* __restrict__ active) {
+    if (active != nullptr && *active == 0) return;
+    __shared__ float red[32];
+    const float* x = logits + (size_t)blockIdx.x * V1;
+    float m = -INFINITY;
+    for (int j = threadIdx.x; j < V1; j += blockDim.x) m = fmaxf(m, x[j]);
+    m = block_max(m, red);
+    float s = 0.f;
+    for (int j = threadIdx.x; j < V1; j += blockDim.x) s += expf(x[j] - m);
+    s = block_sum(s, red);
+    const float lz = logf(s);
+    for (int j = threadIdx.x; j < V1; j += blockDim.x) logp[(size_t)blockIdx.x * out_stride + j] = (x[j] - m) - lz;
+}
+
+// ---- greedy / top-k selection + finish bookkeeping: one block per row ------------------------------------------
+struct Philox {
+    static __device__ __forceinline__ void round(unsigned (&c)[4], unsigned k0, unsigned k1) {
+        unsigned hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        unsigned hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        unsigned n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    }
+    // Philox4x32-10 keyed by `seed`, counter (offset, t, r); returns a uniform in [0, 1)
+    static __device__ float uniform(unsigned long long seed, unsigned long long offset, unsigned t, unsigned r) {
+        unsigned c[4] = {(unsigned)offset, (unsigned)(offset >> 32), t, r};
+        unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+        for (int i = 0; i < 10; ++i) {
+            round(c, k0, k1);
+            k0 += 0x9E3779B9u;
+            k1 += 0xBB67AE85u;
+        }
+        return (float)(c[0] >> 8) * (1.0f / 16777216.0f);
+    }
+};
+
+constexpr int kMaxTopK = 16;
+
+struct SelectArgs {
+    const float* logits;   // [S, V1]
+    int V1, T, t, S;
+    int mode;              // 0 greedy, 1 top-k sampling
+    float temp;
+    int top_k;
+    unsigned long long seed, offset;
+    const float* uniforms; // nullable [T, S]
+    long long* it;         // [S] token fed to the next step
+    int* unfinished;       // [S]
+    long long* seq;        // [S, T]
+    float* seq_lp;         // [S, T]
+    int* count;            // [T + 1] unfinished rows after step t (count[t] doubles as the `active` flag of step t+1)
+    const int* active;
+};
+
+__global__ void __launch_bounds__(256) select_kernel(const SelectArgs a) {
+    if (a.active != nullptr && *a.active == 0) return;
+    __shared__ float redv[32];
+    __shared__ int redi[32];
+    __shared__ float s_topv[kMaxTopK];
+    __shared__ int s_topi[kMaxTopK];
+    const int r = blockIdx.x;
+    const float* x = a.logits + (size_t)r * a.V1;
+    // max (first index) and log-sum-exp of the logits
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int j = threadIdx.x; j < a.V1; j += blockDim.x) {
+        float v = x[j];
+        if (v > bv || bi == 0x7fffffff) { bv = v; bi = j; }
+    }
+    block_argmax(bv, bi, redv, redi);
+    const float m = bv;
+    float s = 0.f;
+    for (int j = threadIdx.x; j < a.V1; j += blockDim.x) s += expf(x[j] - m);
+    s = block_sum(s, redv);
+    const float lz = logf(s);
+    int tok;
+    float lp;
+    if (a.mode == 0) {
+        tok = bi;
+        lp = (m - m) - lz;  // log_softmax value at the arg-max
+    } else {
+        // q = log_softmax(logp / temp) (AttModel.py:296), logp = (x - m) - lz
+        const float ym = ((m - m) - lz) / a.temp;
+        float s2 = 0.f;
+        for (int j = threadIdx.x; j < a.V1; j += blockDim.x) s2 += expf(((x[j] - m) - lz) / a.temp - ym);
+        s2 = block_sum(s2, redv);
+        const float lz2 = logf(s2);
+        const int k = a.top_k;
+        for (int c = 0; c < k; ++c) {  // k rounds of arg-max with exclusion (descending q, lower index first on ties)
+            float cv = -INFINITY;
+            int ci = 0x7fffffff;
+            for (int j = threadIdx.x; j < a.V1; j += blockDim.x) {
+                bool taken = false;
+                for (int e = 0; e < c; ++e) taken |= (s_topi[e] == j);
+                if (taken) continue;
+                float q = (((x[j] - m) - lz) / a.temp - ym) - lz2;
+                if (q > cv || ci == 0x7fffffff) { cv = q; ci = j; }
+            }
+            block_argmax(cv, ci, redv, redi);
+            if (threadIdx.x == 0) { s_topv[c] = cv; s_topi[c] = ci; }
+            __syncthreads();
+        }
+        // Categorical over the kept tokens: inverse CDF in descending-probability order
+        float u = a.uniforms ? a.uniforms[(size_t)a.t * a.S + r] : Philox::uniform(a.seed, a.offset, (unsigned)a.t, (unsigned)r);
+        float den = 0.f;
+        for (int c = 0; c < k; ++c) den += expf(s_topv[c] - s_topv[0]);
+        float cdf = 0.f;
+        int pos = 0;
+        for (int c = 0; c < k; ++c) {
+            cdf += expf(s_topv[c] - s_topv[0]) / den;
+            if (u >= cdf) pos = c + 1;
+        }
+        if (pos > k - 1) pos = k - 1;
+        tok = s_topi[pos];
+        lp = s_topv[pos];
+    }
+    if (threadIdx.x == 0) {
+        int unf = (a.t == 0 ? 1 : a.unfinished[r]) && (tok > 0);
+        long long it = unf ? tok : 0;
+        a.it[r] = it;
+        a.unfinished[r] = unf;
+        a.seq[(size_t)r * a.T + a.t] = it;
+        a.seq_lp[(size_t)r * a.T + a.t] = lp;
+        if (unf) atomicAdd(a.count + a.t, 1);
+    }
+}
+
+__global__ void steps_done_kernel(const int* __restrict__ count, int T, int* __restrict__ steps_done) {
+    int steps = T + 1;
+    for (int t = 0; t < T; ++t)
+        if (count[t] == 0) { steps = t + 1; break; }
+    steps_done[0] = steps;
+}
+
+// teacher forcing: tok[i][r] = tokens[r, i]; flag[i] = 1 while no earlier column i >= 1 was all-zero (AttModel.py:170-171)
+__global__ void __launch_bounds__(256) teacher_columns_kernel(const long long* __restrict__ tokens, int ld_tok, int S, int n_steps,
+                                                              long long* __restrict__ tok_cols, int* __restrict__ flags) {
+    __shared__ int s_any;
+    int alive = 1;
+    for (int i = 0; i < n_steps; ++i) {
+        if (threadIdx.x == 0) s_any = 0;
+        __syncthreads();
+        int any = 0;
+        for (int r = threadIdx.x; r < S; r += blockDim.x) {
+            long long v = tokens[(size_t)r * ld_tok + i];
+            tok_cols[(size_t)i * S + r] = v;
+            any |= (v != 0);
+        }
+        if (any) atomicOr(&s_any, 1);
+        __syncthreads();
+        if (i >= 1 && s_any == 0) alive = 0;
+        if (threadIdx.x == 0) flags[i] = alive;
+        __syncthreads();
+    }
+}
+
+// ---- one decoder step ---------------------------------------------------------------------------------------------
+struct StepScratch {
+    float* gates;   // [S, 4H]
+    float* atth;    // [S, AH]
+    float* ctx;     // [S, H]
+    void* gemm_ws;
+    size_t gemm_ws_bytes;
+};
+
+static size_t step_gemm_ws_bytes(const subgc_dims* d, int S) {
+    size_t g = gemm_workspace_bytes(S, 4 * d->rnn, d->enc + 3 * d->rnn);
+    size_t t = gemm_workspace_bytes(S, 4 * d->rnn, 3 * d->rnn);
+    if (t > g) g = t;
+    t = gemm_workspace_bytes(S, d->att_hid, d->rnn);
+    if (t > g) g = t;
+    t = gemm_workspace_bytes(S, d->vocab1, d->rnn);
+    if (t > g) g = t;
+    return align_up(g, 256);
+}
+
+static size_t step_scratch_bytes(const subgc_dims* d, int S) {
+    return align_up((size_t)S * 4 * d->rnn * 4, 256) + align_up((size_t)S * d->att_hid * 4, 256) + align_up((size_t)S * d->rnn * 4, 256) +
+           step_gemm_ws_bytes(d, S) + 256;
+}
+
+static bool take_step_scratch(const subgc_dims* d, int S, Workspace& ws, StepScratch& sc) {
+    sc.gates = ws.take<float>((size_t)S * 4 * d->rnn);
+    sc.atth = ws.take<float>((size_t)S * d->att_hid);
+    sc.ctx = ws.take<float>((size_t)S * d->rnn);
+    sc.gemm_ws_bytes = step_gemm_ws_bytes(d, S);
+    sc.gemm_ws = ws.take<char>(sc.gemm_ws_bytes);
+    return ws.ok();
+}
+
+// upto: 0 = whole step (logits written), 1 = stop after the attention (the reference's discarded last step, only
+// its attention weights are observable).  parent (nullable) re-maps the previous-state rows (beam re-ordering).
+static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int len_max, int rows_per_ctx, const long long* it,
+                       const long long* parent, const float* fc, const float* att, const float* p_att, const float* masks,
+                       const float* h_in, const float* c_in, float* h_out, float* c_out, float* logits, float* att_w, int att_w_stride,
+                       const StepScratch& sc, const int* active, int upto, cudaStream_t st) {
+    const int H = d->rnn, X = d->enc, AH = d->att_hid, V1 = d->vocab1;
+    const size_t SH = (size_t)S * H;
+    GemmProblem p;
+    // attention LSTM: gates = W_ih [h_lang | fc | relu(E[it])] + b_ih + W_hh h_att + b_hh   (AttModel.py:410-413)
+    p.M = S; p.N = 4 * H; p.nseg = 4;
+    p.seg[0] = make_seg(h_in + SH, H, w->att_w_ih, X + 2 * H, H);
+    p.seg[0].gather = parent;
+    p.seg[1] = make_seg(fc, H, w->att_w_ih + H, X + 2 * H, H);
+    p.seg[1].a_row_div = rows_per_ctx;
+    p.seg[2] = make_seg(w->embed, X, w->att_w_ih + 2 * H, X + 2 * H, X);
+    p.seg[2].gather = it;
+    p.seg[2].relu_a = 1;
+    p.seg[3] = make_seg(h_in, H, w->att_w_hh, H, H);
+    p.seg[3].gather = parent;
+    p.epi.bias = w->att_b_ih; p.epi.bias2 = w->att_b_hh;
+    p.C = sc.gates; p.ldc = 4 * H;
+    p.active = active;
+    SUBGC_TRY(launch_gemm(p, sc.gemm_ws, sc.gemm_ws_bytes, st));
+    const int pw_blocks = (int)((SH + 255) / 256);
+    lstm_cell_kernel<<<pw_blocks, 256, 0, st>>>(sc.gates, c_in, parent, h_out, c_out, S, H, active);
+    SUBGC_LAUNCH_CHECK();
+    // attention (AttModel.py:445-471)
+    p = GemmProblem();
+    p.M = S; p.N = AH; p.nseg = 1;
+    p.seg[0] = make_seg(h_out, H, w->h2att.w, H, H);
+    p.epi.bias = w->h2att.b;
+    p.C = sc.atth; p.ldc = AH;
+    p.active = active;
+    SUBGC_TRY(launch_gemm(p, sc.gemm_ws, sc.gemm_ws_bytes, st));
+    size_t smem = (size_t)(2 * AH + len_max) * sizeof(float);
+    attention_kernel<<<S, 256, smem, st>>>(sc.atth, p_att, att, masks, w->alpha_net.w, w->alpha_net.b, sc.ctx, att_w, att_w_stride, len_max, H,
+                                           AH, rows_per_ctx, active);
+    SUBGC_LAUNCH_CHECK();
+    if (upto == 1) return SUBGC_OK;
+    // language LSTM on [ctx | h_att] (AttModel.py:421-423)
+    p = GemmProblem();
+    p.M = S; p.N = 4 * H; p.nseg = 3;
+    p.seg[0] = make_seg(sc.ctx, H, w->lang_w_ih, 2 * H, H);
+    p.seg[1] = make_seg(h_out, H, w->lang_w_ih + H, 2 * H, H);
+    p.seg[2] = make_seg(h_in + SH, H, w->lang_w_hh, H, H);
+    p.seg[2].gather = parent;
+    p.epi.bias = w->lang_b_ih; p.epi.bias2 = w->lang_b_hh;
+    p.C = sc.gates; p.ldc = 4 * H;
+    p.active = active;
+    SUBGC_TRY(launch_gemm(p, sc.gemm_ws, sc.gemm_ws_bytes, st));
+    lstm_cell_kernel<<<pw_blocks, 256, 0, st>>>(sc.gates, c_in + SH, parent, h_out + SH, c_out + SH, S, H, active);
+    SUBGC_LAUNCH_CHECK();
+    // logit (AttModel.py:336,340); eval mode: dropout is the identity
+    p = GemmProblem();
+    p.M = S; p.N = V1; p.nseg = 1;
+    p.seg[0] = make_seg(h_out + SH, H, w->logit.w, H, H);
+    p.epi.bias = w->logit.b;
+    p.C = logits; p.ldc = V1;
+    p.active = active;
+    SUBGC_TRY(launch_gemm(p, sc.gemm_ws, sc.gemm_ws_bytes, st));
+    return SUBGC_OK;
+}
+
+static int check_decode_args(const subgc_dims* d, const subgc_weights* w, int S, int len_max, const char* who) {
+    SUBGC_CHECK_ARG(d && w, "%s: null dims/weights", who);
+    SUBGC_CHECK_ARG(d->rnn > 0 && d->enc > 0 && d->att_hid > 0 && d->vocab1 > 1 && d->seq_length > 0, "%s: bad decoder dims", who);
+    SUBGC_CHECK_ARG(S > 0 && len_max > 0 && len_max <= 64, "%s: bad n_rows/len_max (%d, %d)", who, S, len_max);
+    SUBGC_CHECK_ARG((size_t)(2 * d->att_hid + len_max) * 4 <= 48 * 1024, "%s: att_hid too large for the attention kernel", who);
+    return SUBGC_OK;
+}
+
+// ---- beam search step: one block per sub-graph -------------------------------------------------------------------
+constexpr int kMaxBeam = 8;
+
+struct BeamArgs {
+    const float* logits;     // [n_sub*b, V1]
+    int V1, T, t, b;
+    int length_penalty;      // 0 none, 1 wu, 2 avg
+    double lp_alpha;
+    int decoding_constraint;
+    int* seq_prev; int* seq_next;       // [n_sub, b, T] histories (ping-pong)
+    float* lp_prev; float* lp_next;     // [n_sub, b, T]
+    float* sum;                         // [n_sub, b] cumulative scores
+    long long* it;                      // [n_sub*b] next input tokens
+    long long* parent;                  // [n_sub*b] state row each new beam continues
+    long long* done_seq; float* done_logps; double* done_p; double* done_unaug_p; int* done_count;  // outputs
+    int* done_total;                    // [n_sub] appended so far
+};
+
+__global__ void __launch_bounds__(256) beam_step_kernel(const BeamArgs a) {
+    __shared__ float redv[32];
+    __shared__ int redi[32];
+    __shared__ float s_ys[kMaxBeam][kMaxBeam];
+    __shared__ int s_ix[kMaxBeam][kMaxBeam];
+    __shared__ int s_q[kMaxBeam], s_tok[kMaxBeam];
+    __shared__ float s_p[kMaxBeam], s_r[kMaxBeam];
+    const int sg = blockIdx.x, b = a.b, t = a.t, T = a.T, V1 = a.V1;
+    const int rows = (t == 0) ? 1 : b;
+    const int* seq_prev = a.seq_prev + (size_t)sg * b * T;
+    int* seq_next = a.seq_next + (size_t)sg * b * T;
+    const float* lp_prev = a.lp_prev + (size_t)sg * b * T;
+    float* lp_next = a.lp_next + (size_t)sg * b * T;
+    for (int q = 0; q < rows; ++q) {
+        const float* x = a.logits + ((size_t)sg * b + q) * V1;
+        float m = -INFINITY;
+        for (int j = threadIdx.x; j < V1; j += blockDim.x) m = fmaxf(m, x[j]);
+        m = block_max(m, redv);
+        float s = 0.f;
+        for (int j = threadIdx.x; j < V1; j += blockDim.x) s += expf(x[j] - m);
+        s = block_sum(s, redv);
+        const float lz = logf(s);
+        const int banned = (a.decoding_constraint && t > 0) ? seq_prev[q * T + t - 1] : -1;
+        for (int c = 0; c < b; ++c) {
+            float cv = -INFINITY;
+            int ci = 0x7fffffff;
+            for (int j = threadIdx.x; j < V1; j += blockDim.x) {
+                bool taken = false;
+                for (int e = 0; e < c; ++e) taken |= (s_ix[q][e] == j);
+                if (taken) continue;
+                float v = (x[j] - m) - lz;
+                if (j == banned) v = -INFINITY;
+                if (j == V1 - 1) v = v - 1000.f;  // UNK suppression (CaptionModel.py:131)
+                if (v > cv || ci == 0x7fffffff) { cv = v; ci = j; }
+            }
+            block_argmax(cv, ci, redv, redi);
+            if (threadIdx.x == 0) { s_ys[q][c] = cv; s_ix[q][c] = ci; }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) {
+        // candidates c-major / q-minor, stable descending sort by p = fl32(sum[q] + ys[q][c]) (CaptionModel.py:61-69)
+        float cp[kMaxBeam * kMaxBeam];
+        unsigned char cq[kMaxBeam * kMaxBeam], cc[kMaxBeam * kMaxBeam];
+        int n = 0;
+        for (int c = 0; c < b; ++c)
+            for (int q = 0; q < rows; ++q) {
+                float p = a.sum[sg * b + q] + s_ys[q][c];
+                int pos = n;
+                while (pos > 0 && cp[pos - 1] < p) { cp[pos] = cp[pos - 1]; cq[pos] = cq[pos - 1]; cc[pos] = cc[pos - 1]; --pos; }
+                cp[pos] = p; cq[pos] = (unsigned char)q; cc[pos] = (unsigned char)c;
+                ++n;
+            }
+        for (int v = 0; v < b; ++v) {
+            s_q[v] = cq[v]; s_tok[v] = s_ix[cq[v]][cc[v]]; s_p[v] = cp[v]; s_r[v] = s_ys[cq[v]][cc[v]];
+        }
+    }
+    __syncthreads();
+    // fork histories (beam v continues beam s_q[v]) and append the new token
+    for (int idx = threadIdx.x; idx < b * T; idx += blockDim.x) {
+        int v = idx / T, i = idx - v * T;
+        int sv = 0;
+        float lv = 0.f;
+        if (i < t) { sv = seq_prev[s_q[v] * T + i]; lv = lp_prev[s_q[v] * T + i]; }
+        else if (i == t) { sv = s_tok[v]; lv = s_r[v]; }
+        seq_next[idx] = sv;
+        lp_next[idx] = lv;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int v = 0; v < b; ++v) {
+            a.sum[sg * b + v] = s_p[v];
+            a.it[sg * b + v] = s_tok[v];
+            a.parent[sg * b + v] = (long long)sg * b + s_q[v];
+        }
+        for (int v = 0; v < b; ++v) {
+            if (s_tok[v] == 0 || t == T - 1) {  // finished beam -> done list (CaptionModel.py:149-162)
+                double p = (double)a.sum[sg * b + v];
+                const int len = t + 1;
+                if (a.length_penalty == 1) p = p / (pow(5.0 + (double)len, a.lp_alpha) / pow(6.0, a.lp_alpha));
+                else if (a.length_penalty == 2) p = p / (double)len;
+                float un = 0.f;
+                for (int i = 0; i < T; ++i) un += lp_next[v * T + i];
+                // stable insertion into the descending-p list, truncated to b entries
+                int cnt = a.done_total[sg] < b ? a.done_total[sg] : b;
+                int pos = cnt;
+                while (pos > 0 && a.done_p[sg * b + pos - 1] < p) --pos;
+                if (pos < b) {
+                    int last = cnt < b ? cnt : b - 1;
+                    for (int e = last; e > pos; --e) {
+                        for (int i = 0; i < T; ++i) {
+                            a.done_seq[((size_t)sg * b + e) * T + i] = a.done_seq[((size_t)sg * b + e - 1) * T + i];
+                            a.done_logps[((size_t)sg * b + e) * T + i] = a.done_logps[((size_t)sg * b + e - 1) * T + i];
+                        }
+                        a.done_p[sg * b + e] = a.done_p[sg * b + e - 1];
+                        a.done_unaug_p[sg * b + e] = a.done_unaug_p[sg * b + e - 1];
+                    }
+                    for (int i = 0; i < T; ++i) {
+                        a.done_seq[((size_t)sg * b + pos) * T + i] = seq_next[v * T + i];
+                        a.done_logps[((size_t)sg * b + pos) * T + i] = lp_next[v * T + i];
+                    }
+                    a.done_p[sg * b + pos] = p;
+                    a.done_unaug_p[sg * b + pos] = (double)un;
+                }
+                a.done_total[sg] += 1;
+                a.done_count[sg] = a.done_total[sg] < b ? a.done_total[sg] : b;
+                a.sum[sg * b + v] = -1000.f;  // don't continue beams from finished sequences
+            }
+        }
+    }
+}
+
+}  // namespace subgc
+
+using namespace subgc;
+
+extern "C" size_t subgc_decode_workspace_bytes(const subgc_dims* d, int n_rows, int len_max) {
+    if (!d || n_rows <= 0) return 0;
+    (void)len_max;
+    const size_t S = n_rows, H = d->rnn;
+    size_t b = step_scratch_bytes(d, n_rows);
+    b += 4 * align_up(2 * S * H * 4, 256);                 // h / c ping-pong
+    b += align_up(S * d->vocab1 * 4, 256);                 // logits
+    b += align_up(S * 8, 256) + align_up(S * 4, 256);      // it, unfinished
+    b += align_up((size_t)(d->seq_length + 2) * 4, 256);   // count
+    return b + 1024;
+}
+
+extern "C" int subgc_decode_step(const subgc_dims* d, const subgc_weights* w, int n_rows, int len_max, int rows_per_ctx, const int64_t* it,
+                                 const float* fc, const float* att, const float* p_att, const float* masks, const float* h_in,
+                                 const float* c_in, float* h_out, float* c_out, float* logprobs, float* att_weights, void* ws_,
+                                 size_t ws_bytes, subgc_stream_t stream) {
+    SUBGC_TRY(check_decode_args(d, w, n_rows, len_max, "subgc_decode_step"));
+    SUBGC_CHECK_ARG(it && fc && att && p_att && masks && h_in && c_in && h_out && c_out && logprobs, "subgc_decode_step: null argument");
+    SUBGC_CHECK_ARG(rows_per_ctx >= 1 && n_rows % rows_per_ctx == 0, "subgc_decode_step: n_rows must be a multiple of rows_per_ctx");
+    SUBGC_CHECK_ARG(h_in != h_out && c_in != c_out, "subgc_decode_step: state in/out must be distinct buffers");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Workspace ws(ws_, ws_bytes);
+    StepScratch sc;
+    bool ok = take_step_scratch(d, n_rows, ws, sc);
+    float* logits = ws.take<float>((size_t)n_rows * d->vocab1);
+    if (!ok || !ws.ok()) { set_error("subgc_decode_step: workspace too small"); return SUBGC_E_WORKSPACE; }
+    SUBGC_TRY(launch_step(d, w, n_rows, len_max, rows_per_ctx, reinterpret_cast<const long long*>(it), nullptr, fc, att, p_att, masks, h_in,
+                          c_in, h_out, c_out, logits, att_weights, len_max, sc, nullptr, 0, st));
+    log_softmax_kernel<<<n_rows, 256, 0, st>>>(logits, logprobs, d->vocab1, (size_t)d->vocab1, nullptr);
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}
+
+extern "C" int subgc_decode_sample(const subgc_dims* d, const subgc_weights* w, int n_rows, int len_max, int mode, float temp, int top_k,
+                                   uint64_t seed, uint64_t offset, const float* uniforms, const float* fc, const float* att,
+                                   const float* p_att, const float* masks, int64_t* seq, float* seq_logprobs, float* att_weights,
+                                   int32_t* steps_done, void* ws_, size_t ws_bytes, subgc_stream_t stream) {
+    SUBGC_TRY(check_decode_args(d, w, n_rows, len_max, "subgc_decode_sample"));
+    SUBGC_CHECK_ARG(fc && att && p_att && masks && seq && seq_logprobs && steps_done, "subgc_decode_sample: null argument");
+    SUBGC_CHECK_ARG(mode == 0 || mode == 1, "subgc_decode_sample: mode must be 0 (greedy) or 1 (top-k)");
+    SUBGC_CHECK_ARG(mode == 0 || (top_k >= 1 && top_k <= kMaxTopK && top_k <= d->vocab1 && temp > 0.f),
+                    "subgc_decode_sample: top_k must be in [1, %d] and temp > 0", kMaxTopK);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int S = n_rows, H = d->rnn, T = d->seq_length, V1 = d->vocab1;
+    Workspace ws(ws_, ws_bytes);
+    StepScratch sc;
+    bool ok = take_step_scratch(d, S, ws, sc);
+    float* hbuf[2] = {ws.take<float>(2 * (size_t)S * H), ws.take<float>(2 * (size_t)S * H)};
+    float* cbuf[2] = {ws.take<float>(2 * (size_t)S * H), ws.take<float>(2 * (size_t)S * H)};
+    float* logits = ws.take<float>((size_t)S * V1);
+    long long* it = ws.take<long long>(S);
+    int* unfinished = ws.take<int>(S);
+    int* count = ws.take<int>(T + 2);
+    if (!ok || !ws.ok()) { set_error("subgc_decode_sample: workspace too small"); return SUBGC_E_WORKSPACE; }
+    SUBGC_CUDA(cudaMemsetAsync(hbuf[0], 0, 2 * (size_t)S * H * 4, st));   // init_hidden (AttModel.py:343-346)
+    SUBGC_CUDA(cudaMemsetAsync(cbuf[0], 0, 2 * (size_t)S * H * 4, st));
+    SUBGC_CUDA(cudaMemsetAsync(it, 0, (size_t)S * 8, st));                // <bos>
+    SUBGC_CUDA(cudaMemsetAsync(count, 0, (size_t)(T + 2) * 4, st));
+    SUBGC_CUDA(cudaMemsetAsync(seq, 0, (size_t)S * T * 8, st));
+    SUBGC_CUDA(cudaMemsetAsync(seq_logprobs, 0, (size_t)S * T * 4, st));
+    if (att_weights) SUBGC_CUDA(cudaMemsetAsync(att_weights, 0, (size_t)S * (T + 1) * len_max * 4, st));
+    for (int t = 0; t <= T; ++t) {
+        const int* active = (t == 0) ? nullptr : count + (t - 1);
+        const int in = t & 1, out = in ^ 1;
+        float* aw = att_weights ? att_weights + (size_t)t * len_max : nullptr;
+        if (t == T) {
+            // the reference runs this step and discards its log-probs (AttModel.py:292-293); only the attention
+            // weights are observable, so the step stops there (and is skipped entirely when they are not requested)
+            if (att_weights)
+                SUBGC_TRY(launch_step(d, w, S, len_max, 1, it, nullptr, fc, att, p_att, masks, hbuf[in], cbuf[in], hbuf[out], cbuf[out], logits,
+                                      aw, (T + 1) * len_max, sc, active, 1, st));
+            break;
+        }
+        SUBGC_TRY(launch_step(d, w, S, len_max, 1, it, nullptr, fc, att, p_att, masks, hbuf[in], cbuf[in], hbuf[out], cbuf[out], logits, aw,
+                              (T + 1) * len_max, sc, active, 0, st));
+        SelectArgs a;
+        a.logits = logits; a.V1 = V1; a.T = T; a.t = t; a.S = S; a.mode = mode; a.temp = temp; a.top_k = top_k; a.seed = seed;
+        a.offset = offset; a.uniforms = uniforms; a.it = it; a.unfinished = unfinished; a.seq = reinterpret_cast<long long*>(seq);
+        a.seq_lp = seq_logprobs; a.count = count; a.active = active;
+        select_kernel<<<S, 256, 0, st>>>(a);
+        SUBGC_LAUNCH_CHECK();
+    }
+    steps_done_kernel<<<1, 1, 0, st>>>(count, T, steps_done);
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}
+
+extern "C" size_t subgc_teacher_workspace_bytes(const subgc_dims* d, int n_rows, int n_steps) {
+    if (!d || n_rows <= 0 || n_steps <= 0) return 0;
+    return subgc_decode_workspace_bytes(d, n_rows, 0) + align_up((size_t)n_rows * n_steps * 8, 256) + align_up((size_t)n_steps * 4, 256) + 512;
+}
+
+extern "C" int subgc_decode_teacher(const subgc_dims* d, const subgc_weights* w, int n_rows, int len_max, int n_steps, const int64_t* tokens,
+                                    int ld_tok, const float* fc, const float* att, const float* p_att, const float* masks, float* outputs,
+                                    void* ws_, size_t ws_bytes, subgc_stream_t stream) {
+    SUBGC_TRY(check_decode_args(d, w, n_rows, len_max, "subgc_decode_teacher"));
+    SUBGC_CHECK_ARG(tokens && fc && att && p_att && masks && outputs && n_steps > 0 && ld_tok >= n_steps, "subgc_decode_teacher: bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int S = n_rows, H = d->rnn, V1 = d->vocab1;
+    Workspace ws(ws_, ws_bytes);
+    StepScratch sc;
+    bool ok = take_step_scratch(d, S, ws, sc);
+    float* hbuf[2] = {ws.take<float>(2 * (size_t)S * H), ws.take<float>(2 * (size_t)S * H)};
+    float* cbuf[2] = {ws.take<float>(2 * (size_t)S * H), ws.take<float>(2 * (size_t)S * H)};
+    float* logits = ws.take<float>((size_t)S * V1);
+    long long* tok_cols = ws.take<long long>((size_t)S * n_steps);
+    int* flags = ws.take<int>(n_steps);
+    if (!ok || !ws.ok()) { set_error("subgc_decode_teacher: workspace too small"); return SUBGC_E_WORKSPACE; }
+    SUBGC_CUDA(cudaMemsetAsync(hbuf[0], 0, 2 * (size_t)S * H * 4, st));
+    SUBGC_CUDA(cudaMemsetAsync(cbuf[0], 0, 2 * (size_t)S * H * 4, st));
+    SUBGC_CUDA(cudaMemsetAsync(outputs, 0, (size_t)S * n_steps * V1 * 4, st));  // steps after the early break stay zero
+    teacher_columns_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const long long*>(tokens), ld_tok, S, n_steps, tok_cols, flags);
+    SUBGC_LAUNCH_CHECK();
+    for (int i = 0; i < n_steps; ++i) {
+        const int in = i & 1, out = in ^ 1;
+        SUBGC_TRY(launch_step(d, w, S, len_max, 1, tok_cols + (size_t)i * S, nullptr, fc, att, p_att, masks, hbuf[in], cbuf[in], hbuf[out],
+                              cbuf[out], logits, nullptr, 0, sc, flags + i, 0, st));
+        log_softmax_kernel<<<S, 256, 0, st>>>(logits, outputs + (size_t)i * V1, V1, (size_t)n_steps * V1, flags + i);
+        SUBGC_LAUNCH_CHECK();
+    }
+    return SUBGC_OK;
+}
+
+extern "C" size_t subgc_beam_workspace_bytes(const subgc_dims* d, int n_sub, int beam_size, int len_max) {
+    if (!d || n_sub <= 0 || beam_size <= 0) return 0;
+    (void)len_max;
+    const size_t S = (size_t)n_sub * beam_size, H = d->rnn, T = d->seq_length;
+    size_t b = step_scratch_bytes(d, (int)S);
+    b += 4 * align_up(2 * S * H * 4, 256);
+    b += align_up(S * d->vocab1 * 4, 256);
+    b += 2 * align_up(S * 8, 256);                          // it, parent
+    b += 4 * align_up(S * T * 4, 256);                      // histories
+    b += align_up(S * 4, 256) + align_up((size_t)n_sub * 4, 256);
+    return b + 1024;
+}
+
+extern "C" int subgc_decode_beam(const subgc_dims* d, const subgc_weights* w, int n_sub, int len_max, int beam_size, int length_penalty,
+                                 double lp_alpha, int decoding_constraint, const float* fc, const float* att, const float* p_att,
+                                 const float* masks, int64_t* done_seq, float* done_logps, double* done_p, double* done_unaug_p,
+                                 int32_t* done_count, void* ws_, size_t ws_bytes, subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(beam_size >= 1 && beam_size <= kMaxBeam, "subgc_decode_beam: beam_size must be in [1, %d]", kMaxBeam);
+    SUBGC_CHECK_ARG(n_sub > 0, "subgc_decode_beam: n_sub must be positive");
+    SUBGC_TRY(check_decode_args(d, w, n_sub * beam_size, len_max, "subgc_decode_beam"));
+    SUBGC_CHECK_ARG(fc && att && p_att && masks && done_seq && done_logps && done_p && done_unaug_p && done_count,
+                    "subgc_decode_beam: null argument");
+    SUBGC_CHECK_ARG(length_penalty >= 0 && length_penalty <= 2, "subgc_decode_beam: unknown length penalty %d", length_penalty);
+    SUBGC_CHECK_ARG(beam_size <= d->vocab1, "subgc_decode_beam: beam_size exceeds the vocabulary");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int b = beam_size, S = n_sub * b, H = d->rnn, T = d->seq_length, V1 = d->vocab1;
+    Workspace ws(ws_, ws_bytes);
+    StepScratch sc;
+    bool ok = take_step_scratch(d, S, ws, sc);
+    float* hbuf[2] = {ws.take<float>(2 * (size_t)S * H), ws.take<float>(2 * (size_t)S * H)};
+    float* cbuf[2] = {ws.take<float>(2 * (size_t)S * H), ws.take<float>(2 * (size_t)S * H)};
+    float* logits = ws.take<float>((size_t)S * V1);
+    long long* it = ws.take<long long>(S);
+    long long* parent = ws.take<long long>(S);
+    int* seqb[2] = {ws.take<int>((size_t)S * T), ws.take<int>((size_t)S * T)};
+    float* lpb[2] = {ws.take<float>((size_t)S * T), ws.take<float>((size_t)S * T)};
+    float* sum = ws.take<float>(S);
+    int* done_total = ws.take<int>(n_sub);
+    if (!ok || !ws.ok()) { set_error("subgc_decode_beam: workspace too small"); return SUBGC_E_WORKSPACE; }
+    SUBGC_CUDA(cudaMemsetAsync(hbuf[0], 0, 2 * (size_t)S * H * 4, st));
+    SUBGC_CUDA(cudaMemsetAsync(cbuf[0], 0, 2 * (size_t)S * H * 4, st));
+    SUBGC_CUDA(cudaMemsetAsync(it, 0, (size_t)S * 8, st));
+    SUBGC_CUDA(cudaMemsetAsync(seqb[0], 0, (size_t)S * T * 4, st));
+    SUBGC_CUDA(cudaMemsetAsync(lpb[0], 0, (size_t)S * T * 4, st));
+    SUBGC_CUDA(cudaMemsetAsync(sum, 0, (size_t)S * 4, st));
+    SUBGC_CUDA(cudaMemsetAsync(done_total, 0, (size_t)n_sub * 4, st));
+    SUBGC_CUDA(cudaMemsetAsync(done_count, 0, (size_t)n_sub * 4, st));
+    SUBGC_CUDA(cudaMemsetAsync(done_seq, 0, (size_t)S * T * 8, st));
+    SUBGC_CUDA(cudaMemsetAsync(done_logps, 0, (size_t)S * T * 4, st));
+    SUBGC_CUDA(cudaMemsetAsync(done_p, 0, (size_t)S * 8, st));
+    SUBGC_CUDA(cudaMemsetAsync(done_unaug_p, 0, (size_t)S * 8, st));
+    // <bos> step on b identical rows per sub-graph (AttModel.py:216-227)
+    SUBGC_TRY(launch_step(d, w, S, len_max, b, it, nullptr, fc, att, p_att, masks, hbuf[0], cbuf[0], hbuf[1], cbuf[1], logits, nullptr, 0, sc,
+                          nullptr, 0, st));
+    for (int t = 0; t < T; ++t) {
+        BeamArgs a;
+        a.logits = logits; a.V1 = V1; a.T = T; a.t = t; a.b = b; a.length_penalty = length_penalty; a.lp_alpha = lp_alpha;
+        a.decoding_constraint = decoding_constraint;
+        a.seq_prev = seqb[t & 1]; a.seq_next = seqb[(t & 1) ^ 1]; a.lp_prev = lpb[t & 1]; a.lp_next = lpb[(t & 1) ^ 1];
+        a.sum = sum; a.it = it; a.parent = parent;
+        a.done_seq = reinterpret_cast<long long*>(done_seq); a.done_logps = done_logps; a.done_p = done_p; a.done_unaug_p = done_unaug_p;
+        a.done_count = done_count; a.done_total = done_total;
+        beam_step_kernel<<<n_sub, 256, 0, st>>>(a);
+        SUBGC_LAUNCH_CHECK();
+        if (t == T - 1) break;  // the reference's final get_logprobs_state result is never read (CaptionModel.py:170-171)
+        const int in = (t + 1) & 1, out = in ^ 1;
+        SUBGC_TRY(launch_step(d, w, S, len_max, b, it, parent, fc, att, p_att, masks, hbuf[in], cbuf[in], hbuf[out], cbuf[out], logits, nullptr, 0,
+                              sc, nullptr, 0, st));
+    }
+    return SUBGC_OK;
+}

@@ -1,0 +1,247 @@
+// Encoder of the Sub-GC path: feature fusion and GCN message passing over ragged per-image scene graphs.
+//
+//   subgc_fuse_nodes   <- AttModel.feat_fusion                     (reference models/AttModel.py:370-387)
+//   subgc_gcn_forward  <- gcn_backbone.forward / make_map          (reference models/lib/gcn_backbone.py:29-67)
+//                         _GraphConvolutionLayer.forward           (reference models/lib/graph_conv.py:15-34)
+//                         _Collection_Unit.forward                 (reference models/lib/graph_conv_unit.py:28-36)
+//
+// The reference materialises a dense 0/1 adjacency [B,N,K,2] and multiplies with it (bmm).  Each edge has exactly one
+// subject and one object, so  adj^T . msg  is a row gather (edge <- node) and  adj . msg  is a segment sum over the
+// edges incident to a node, taken here in ascending edge order (the order of the dense product).  The mean divisor
+// is the fp32 value (count + 1e-7) the reference divides by.  Units whose result cannot reach a requested output are
+// skipped (for Sub-GC's 2 layers / residual 2 that is half of them, SURVEY headline fact 2).
+#include "common.cuh"
+
+namespace subgc {
+
+// cls[row] = off + argmax_first(dist[row, off:])   (torch.max first-index tie-break), one warp per row
+__global__ void __launch_bounds__(256) class_argmax_kernel(const float* __restrict__ dist, int rows, int C, int off,
+                                                           long long* __restrict__ cls) {
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const float* p = dist + (size_t)row * C;
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int j = off + lane; j < C; j += 32) {
+        float v = __ldg(p + j);
+        if (v > bv || bi == 0x7fffffff) { bv = v; bi = j; }  // strictly greater keeps the first index within a lane
+    }
+    warp_argmax(bv, bi);
+    if (lane == 0) cls[row] = (bi == 0x7fffffff) ? off : bi;
+}
+
+// p_new[b,k,:] = 0.5 * ( relu(M2[b, s_k, :] / (1+1e-7)) + relu(M3[b, o_k, :] / (1+1e-7)) ) (+ residual)
+__global__ void __launch_bounds__(256) gcn_edge_update_kernel(const float* __restrict__ m_subj, const float* __restrict__ m_obj,
+                                                              const long long* __restrict__ rel_ind, const float* __restrict__ res,
+                                                              float* __restrict__ out, int B, int N, int K, int L) {
+    const int bk = blockIdx.x;  // b*K + k
+    const int b = bk / K;
+    const long long s = rel_ind[(size_t)bk * 2], o = rel_ind[(size_t)bk * 2 + 1];
+    const float d = 1.f + 1e-7f;
+    const float* ms = m_subj + ((size_t)b * N + s) * L;
+    const float* mo = m_obj + ((size_t)b * N + o) * L;
+    for (int c = threadIdx.x; c < L; c += blockDim.x) {
+        float v = 0.5f * (fmaxf(__ldg(ms + c) / d, 0.f) + fmaxf(__ldg(mo + c) / d, 0.f));
+        if (res) v += __ldg(res + (size_t)bk * L + c);
+        out[(size_t)bk * L + c] = v;
+    }
+}
+
+// x_new[b,n,:] = 0.5 * ( relu(sum_{k: s_k = n} M0[b,k,:] / (cnt_s + 1e-7)) + relu(sum_{k: o_k = n} M1[b,k,:] / (cnt_o + 1e-7)) )
+__global__ void __launch_bounds__(256) gcn_node_update_kernel(const float* __restrict__ m_subj, const float* __restrict__ m_obj,
+                                                              const long long* __restrict__ rel_ind, const float* __restrict__ res,
+                                                              float* __restrict__ out, int B, int N, int K, int L) {
+    extern __shared__ int s_list[];  // [2][K] edge lists of this node
+    __shared__ int s_cnt[2];
+    const int bn = blockIdx.x;
+    const int b = bn / N, n = bn - b * N;
+    if (threadIdx.x == 0) {  // K is small (65): a serial scan keeps the ascending edge order
+        int cs = 0, co = 0;
+        for (int k = 0; k < K; ++k) {
+            long long s = rel_ind[((size_t)b * K + k) * 2], o = rel_ind[((size_t)b * K + k) * 2 + 1];
+            if (s == n) s_list[cs++] = k;
+            if (o == n) s_list[K + co++] = k;
+        }
+        s_cnt[0] = cs; s_cnt[1] = co;
+    }
+    __syncthreads();
+    const int cs = s_cnt[0], co = s_cnt[1];
+    const float ds = (float)cs + 1e-7f, dob = (float)co + 1e-7f;
+    const float* ms = m_subj + (size_t)b * K * L;
+    const float* mo = m_obj + (size_t)b * K * L;
+    for (int c = threadIdx.x; c < L; c += blockDim.x) {
+        float a0 = 0.f, a1 = 0.f;
+        for (int i = 0; i < cs; ++i) a0 += __ldg(ms + (size_t)s_list[i] * L + c);
+        for (int i = 0; i < co; ++i) a1 += __ldg(mo + (size_t)s_list[K + i] * L + c);
+        float v = (fmaxf(a0 / ds, 0.f) + fmaxf(a1 / dob, 0.f)) * 0.5f;
+        if (res) v += __ldg(res + (size_t)bn * L + c);
+        out[(size_t)bn * L + c] = v;
+    }
+}
+
+static int check_dims(const subgc_dims* d) {
+    SUBGC_CHECK_ARG(d != nullptr, "dims is null");
+    SUBGC_CHECK_ARG(d->gcn > 0 && d->low_rank > 0 && d->att_feat > 0 && d->embed > 0 && d->obj_num > 1 && d->rel_num > 0 &&
+                        d->obj_classes > 1 && d->pred_classes > 1,
+                    "bad encoder dims");
+    SUBGC_CHECK_ARG(d->gcn_layers >= 0 && d->gcn_layers <= SUBGC_MAX_GCN_LAYERS && d->gcn_residual >= 1, "bad gcn_layers/gcn_residual");
+    return SUBGC_OK;
+}
+
+// which layer inputs are live: need_x[l] / need_p[l] = the node / edge stream entering layer l (l == layers: outputs)
+static void gcn_liveness(const subgc_dims* d, int want_x_pred, bool* need_x, bool* need_p) {
+    const int Ln = d->gcn_layers, R = d->gcn_residual;
+    for (int l = 0; l <= Ln; ++l) need_x[l] = need_p[l] = false;
+    need_x[Ln] = true;
+    need_p[Ln] = want_x_pred != 0;
+    for (int l = Ln; l >= 1; --l) {
+        if (need_x[l]) {
+            need_p[l - 1] = true;                  // units 0,1 read the edge stream
+            if (l % R == 0) need_x[l - R] = true;  // residual anchor
+        }
+        if (need_p[l]) {
+            need_x[l - 1] = true;                  // units 2,3 read the node stream
+            if (l % R == 0) need_p[l - R] = true;
+        }
+    }
+}
+
+static size_t gcn_ws_bytes(const subgc_dims* d, int B) {
+    const size_t rows = (size_t)B * (d->obj_num > d->rel_num ? d->obj_num : d->rel_num);
+    size_t b = 0;
+    b += align_up(rows * d->low_rank * 4, 256);          // T
+    b += 2 * align_up(rows * d->gcn * 4, 256);           // two message buffers
+    b += (size_t)d->gcn_layers * (align_up((size_t)B * d->obj_num * d->gcn * 4, 256) + align_up((size_t)B * d->rel_num * d->gcn * 4, 256));
+    size_t g1 = gemm_workspace_bytes((int)rows, d->low_rank, d->gcn), g2 = gemm_workspace_bytes((int)rows, d->gcn, d->low_rank);
+    b += align_up(g1 > g2 ? g1 : g2, 256) + 1024;
+    return b;
+}
+
+static size_t fuse_ws_bytes(const subgc_dims* d, int B) {
+    size_t b = 0;
+    b += align_up((size_t)B * d->obj_num * 8, 256) + align_up((size_t)B * d->rel_num * 8, 256);
+    size_t g1 = gemm_workspace_bytes(B * d->obj_num, d->gcn, d->att_feat + d->embed), g2 = gemm_workspace_bytes(B * d->rel_num, d->gcn, d->embed);
+    b += align_up(g1 > g2 ? g1 : g2, 256) + 1024;
+    return b;
+}
+
+static int linear(const float* A, int M, int K, const subgc_linear& lin, int N, float* C, Workspace& ws, cudaStream_t st) {
+    GemmProblem p;
+    p.M = M; p.N = N; p.nseg = 1;
+    p.seg[0] = make_seg(A, K, lin.w, K, K);
+    p.epi.bias = lin.b;
+    p.C = C; p.ldc = N;
+    return launch_gemm(p, ws.cursor(), ws.remaining(), st);
+}
+
+}  // namespace subgc
+
+using namespace subgc;
+
+extern "C" size_t subgc_encoder_workspace_bytes(const subgc_dims* d, int n_images) {
+    if (!d || n_images <= 0) return 0;
+    size_t a = fuse_ws_bytes(d, n_images), b = gcn_ws_bytes(d, n_images);
+    return a > b ? a : b;
+}
+
+extern "C" int subgc_gcn_needs_pred(const subgc_dims* d, int want_x_pred) {
+    if (!d || d->gcn_layers < 0 || d->gcn_layers > SUBGC_MAX_GCN_LAYERS || d->gcn_residual < 1) return 1;
+    bool nx[SUBGC_MAX_GCN_LAYERS + 1], np[SUBGC_MAX_GCN_LAYERS + 1];
+    gcn_liveness(d, want_x_pred, nx, np);
+    return np[0] ? 1 : 0;
+}
+
+extern "C" int subgc_fuse_nodes(const subgc_dims* d, const subgc_weights* w, int n_images, const float* att_feats, const float* obj_dist,
+                                const float* pred_dist, float* x0, float* p0, void* ws_, size_t ws_bytes, subgc_stream_t stream) {
+    SUBGC_TRY(check_dims(d));
+    SUBGC_CHECK_ARG(w && att_feats && obj_dist && x0 && n_images > 0, "subgc_fuse_nodes: null argument");
+    SUBGC_CHECK_ARG(p0 == nullptr || pred_dist != nullptr, "subgc_fuse_nodes: p0 requested without pred_dist");
+    SUBGC_CHECK_ARG(d->pred_emb_type == 1 || d->pred_emb_type == 2, "subgc_fuse_nodes: pred_emb_type must be 1 or 2");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Workspace ws(ws_, ws_bytes);
+    const int rows_n = n_images * d->obj_num, rows_k = n_images * d->rel_num;
+    long long* cls = ws.take<long long>(rows_n);
+    long long* pcls = ws.take<long long>(rows_k);
+    if (!ws.ok()) { set_error("subgc_fuse_nodes: workspace too small"); return SUBGC_E_WORKSPACE; }
+    class_argmax_kernel<<<(rows_n + 7) / 8, 256, 0, st>>>(obj_dist, rows_n, d->obj_classes, 1, cls);
+    SUBGC_LAUNCH_CHECK();
+    {
+        GemmProblem p;
+        p.M = rows_n; p.N = d->gcn; p.nseg = 2;
+        p.seg[0] = make_seg(att_feats, d->att_feat, w->obj_v_proj.w, d->att_feat, d->att_feat);
+        p.seg[1] = make_seg(w->sg_obj_embed, d->embed, w->obj_emb_proj.w, d->embed, d->embed);
+        p.seg[1].gather = cls;
+        p.epi.bias = w->obj_v_proj.b;
+        p.epi.bias2 = w->obj_emb_proj.b;
+        p.epi.relu = 1;
+        p.C = x0; p.ldc = d->gcn;
+        SUBGC_TRY(launch_gemm(p, ws.cursor(), ws.remaining(), st));
+    }
+    if (p0) {
+        class_argmax_kernel<<<(rows_k + 7) / 8, 256, 0, st>>>(pred_dist, rows_k, d->pred_classes, d->pred_emb_type == 1 ? 1 : 0, pcls);
+        SUBGC_LAUNCH_CHECK();
+        GemmProblem p;
+        p.M = rows_k; p.N = d->gcn; p.nseg = 1;
+        p.seg[0] = make_seg(w->sg_pred_embed, d->embed, w->pred_emb_prj.w, d->embed, d->embed);
+        p.seg[0].gather = pcls;
+        p.epi.bias = w->pred_emb_prj.b;
+        p.C = p0; p.ldc = d->gcn;
+        SUBGC_TRY(launch_gemm(p, ws.cursor(), ws.remaining(), st));
+    }
+    return SUBGC_OK;
+}
+
+extern "C" int subgc_gcn_forward(const subgc_dims* d, const subgc_weights* w, int n_images, const float* x0, const float* p0,
+                                 const int64_t* rel_ind, float* x_obj, float* x_pred, void* ws_, size_t ws_bytes, subgc_stream_t stream) {
+    SUBGC_TRY(check_dims(d));
+    SUBGC_CHECK_ARG(w && x0 && rel_ind && x_obj && n_images > 0, "subgc_gcn_forward: null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int B = n_images, N = d->obj_num, K = d->rel_num, L = d->gcn, R = d->low_rank, Ln = d->gcn_layers;
+    bool need_x[SUBGC_MAX_GCN_LAYERS + 1], need_p[SUBGC_MAX_GCN_LAYERS + 1];
+    gcn_liveness(d, x_pred != nullptr, need_x, need_p);
+    SUBGC_CHECK_ARG(!need_p[0] || p0 != nullptr, "subgc_gcn_forward: this configuration needs the predicate embedding p0");
+    const size_t xn = (size_t)B * N * L, pn = (size_t)B * K * L;
+    if (Ln == 0) {
+        SUBGC_CUDA(cudaMemcpyAsync(x_obj, x0, xn * 4, cudaMemcpyDeviceToDevice, st));
+        if (x_pred) SUBGC_CUDA(cudaMemcpyAsync(x_pred, p0, pn * 4, cudaMemcpyDeviceToDevice, st));
+        return SUBGC_OK;
+    }
+    Workspace ws(ws_, ws_bytes);
+    const size_t rows_max = (size_t)B * (N > K ? N : K);
+    float* T = ws.take<float>(rows_max * R);
+    float* Ma = ws.take<float>(rows_max * L);
+    float* Mb = ws.take<float>(rows_max * L);
+    const float* x = x0;
+    const float* p = p0;
+    const float* x_res = x0;
+    const float* p_res = p0;
+    const long long* rel = reinterpret_cast<const long long*>(rel_ind);
+    for (int l = 0; l < Ln; ++l) {
+        const bool last = (l == Ln - 1), boundary = ((l + 1) % d->gcn_residual == 0);
+        float* x_next = nullptr;
+        float* p_next = nullptr;
+        if (need_x[l + 1]) x_next = last ? x_obj : ws.take<float>(xn);
+        if (need_p[l + 1]) p_next = last ? x_pred : ws.take<float>(pn);
+        if (!ws.ok() || !T || !Ma || !Mb) { set_error("subgc_gcn_forward: workspace too small"); return SUBGC_E_WORKSPACE; }
+        if (p_next) {  // units 2,3: edge <- node (graph_conv.py:29-33)
+            SUBGC_TRY(linear(x, B * N, L, w->gcn_lft[l][2], R, T, ws, st));
+            SUBGC_TRY(linear(T, B * N, R, w->gcn_rgt[l][2], L, Ma, ws, st));
+            SUBGC_TRY(linear(x, B * N, L, w->gcn_lft[l][3], R, T, ws, st));
+            SUBGC_TRY(linear(T, B * N, R, w->gcn_rgt[l][3], L, Mb, ws, st));
+            gcn_edge_update_kernel<<<B * K, 256, 0, st>>>(Ma, Mb, rel, boundary ? p_res : nullptr, p_next, B, N, K, L);
+            SUBGC_LAUNCH_CHECK();
+        }
+        if (x_next) {  // units 0,1: node <- edges (graph_conv.py:22-26)
+            SUBGC_TRY(linear(p, B * K, L, w->gcn_lft[l][0], R, T, ws, st));
+            SUBGC_TRY(linear(T, B * K, R, w->gcn_rgt[l][0], L, Ma, ws, st));
+            SUBGC_TRY(linear(p, B * K, L, w->gcn_lft[l][1], R, T, ws, st));
+            SUBGC_TRY(linear(T, B * K, R, w->gcn_rgt[l][1], L, Mb, ws, st));
+            gcn_node_update_kernel<<<B * N, 256, 2 * K * sizeof(int), st>>>(Ma, Mb, rel, boundary ? x_res : nullptr, x_next, B, N, K, L);
+            SUBGC_LAUNCH_CHECK();
+        }
+        x = x_next; p = p_next;
+        if (boundary) { x_res = x; p_res = p; }
+    }
+    return SUBGC_OK;
+}

@@ -1,0 +1,109 @@
+"""ctypes binding of the C ABI declared in include/subgc_b200.h (libsubgc_b200.so, built by `subgc.build`).
+
+There is no CPU fallback: `lib()` raises if the shared library is missing or cannot be loaded, and every wrapper
+raises `SubgcError` with the library's own message on a non-zero return code.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsubgc_b200.so")
+MAX_GCN_LAYERS = 8
+
+c_fp = C.c_void_p  # device pointers travel as plain integers
+
+
+class SubgcError(RuntimeError):
+    pass
+
+
+class Dims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("vocab1", "enc", "rnn", "att_hid", "fc_feat", "att_feat", "gcn", "low_rank", "embed",
+                                         "obj_classes", "pred_classes", "gcn_layers", "gcn_residual", "pred_emb_type",
+                                         "seq_length", "obj_num", "rel_num")]
+
+
+class Linear(C.Structure):
+    _fields_ = [("w", c_fp), ("b", c_fp)]
+
+
+class Weights(C.Structure):
+    _fields_ = [
+        ("obj_v_proj", Linear), ("sg_obj_embed", c_fp), ("obj_emb_proj", Linear), ("sg_pred_embed", c_fp),
+        ("pred_emb_prj", Linear), ("gcn_lft", (Linear * 4) * MAX_GCN_LAYERS), ("gcn_rgt", (Linear * 4) * MAX_GCN_LAYERS),
+        ("gpn_fc0", Linear), ("gpn_fc3", Linear), ("read_out0", Linear), ("read_out1", Linear), ("logit", Linear),
+        ("embed", c_fp), ("fc_embed0", Linear), ("fc_embed2", Linear), ("att_embed", Linear), ("ctx2att", Linear),
+        ("h2att", Linear), ("alpha_net", Linear),
+        ("att_w_ih", c_fp), ("att_w_hh", c_fp), ("att_b_ih", c_fp), ("att_b_hh", c_fp),
+        ("lang_w_ih", c_fp), ("lang_w_hh", c_fp), ("lang_b_ih", c_fp), ("lang_b_hh", c_fp),
+    ]
+
+
+class Layout(C.Structure):
+    _fields_ = [("rows", C.c_int32), ("per_half", C.c_int32), ("seq_per_img", C.c_int32), ("order", C.c_int32)]
+
+
+_P = C.POINTER
+_i, _sz, _f, _d, _u64 = C.c_int, C.c_size_t, C.c_float, C.c_double, C.c_uint64
+
+# name -> (restype, argtypes); mirrors include/subgc_b200.h one to one
+SIGNATURES = {
+    "subgc_last_error": (C.c_char_p, []),
+    "subgc_version": (_i, []),
+    "subgc_launch_count": (C.c_ulonglong, []),
+    "subgc_linear_workspace_bytes": (_sz, [_i, _i, _i]),
+    "subgc_linear_forward": (_i, [_i, _i, _i, c_fp, _i, c_fp, c_fp, _i, c_fp, _i, c_fp, _i, c_fp, _sz, c_fp]),
+    "subgc_encoder_workspace_bytes": (_sz, [_P(Dims), _i]),
+    "subgc_fuse_nodes": (_i, [_P(Dims), _P(Weights), _i, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, _sz, c_fp]),
+    "subgc_gcn_forward": (_i, [_P(Dims), _P(Weights), _i, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, _sz, c_fp]),
+    "subgc_gcn_needs_pred": (_i, [_P(Dims), _i]),
+    "subgc_sgpn_workspace_bytes": (_sz, [_P(Dims), _i]),
+    "subgc_sgpn_forward": (_i, [_P(Dims), _P(Weights), _P(Layout), c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, _sz, c_fp]),
+    "subgc_sgpn_select_train": (_i, [_P(Layout), c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "subgc_nms_workspace_bytes": (_sz, [_i, _i]),
+    "subgc_subgraph_nms": (_i, [_P(Dims), _P(Layout), c_fp, c_fp, c_fp, c_fp, _i, _d, _i, c_fp, c_fp, c_fp, c_fp, _sz, c_fp]),
+    "subgc_prepare_workspace_bytes": (_sz, [_P(Dims), _i, _i]),
+    "subgc_prepare_forward": (_i, [_P(Dims), _P(Weights), _P(Layout), _i, _i, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp,
+                                   c_fp, c_fp, c_fp, _sz, c_fp]),
+    "subgc_decode_workspace_bytes": (_sz, [_P(Dims), _i, _i]),
+    "subgc_decode_step": (_i, [_P(Dims), _P(Weights), _i, _i, _i, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp,
+                               c_fp, _sz, c_fp]),
+    "subgc_decode_sample": (_i, [_P(Dims), _P(Weights), _i, _i, _i, _f, _i, _u64, _u64, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp,
+                                 c_fp, c_fp, c_fp, _sz, c_fp]),
+    "subgc_teacher_workspace_bytes": (_sz, [_P(Dims), _i, _i]),
+    "subgc_decode_teacher": (_i, [_P(Dims), _P(Weights), _i, _i, _i, c_fp, _i, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, _sz, c_fp]),
+    "subgc_beam_workspace_bytes": (_sz, [_P(Dims), _i, _i, _i]),
+    "subgc_decode_beam": (_i, [_P(Dims), _P(Weights), _i, _i, _i, _i, _d, _i, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp,
+                               c_fp, _sz, c_fp]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libsubgc_b200.so (once).  Raises if it has not been built — the product path never falls back."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise SubgcError(f"{LIB_PATH} not found: build it with `python -m subgc.build` "
+                             "(or __graft_entry__.build()); there is no CPU fallback")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().subgc_last_error()
+        raise SubgcError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()

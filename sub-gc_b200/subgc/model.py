@@ -1,0 +1,452 @@
+"""Host-side mirror of the reference model API for the Sub-GC hot path.
+
+`setup(opt)` -> `TopDownModel` keeps the surface of reference models/__init__.py:43-59 / models/AttModel.py /
+models/CaptionModel.py: constructor from `opt`, identical `state_dict` keys and shapes (a reference checkpoint loads
+with `load_state_dict`), `model(*tensors, mode='forward'|'sample', opt={...})` with the reference's positional
+signatures and return tuples, `get_logprobs_state`, `init_hidden`, and the attributes the drivers touch
+(`gpn`, `ss_prob`, `done_beams`, `seq_length`, `vocab_size`).  The modules below only *hold* parameters under the
+reference's names — all arithmetic runs in the CUDA kernels behind the C ABI (include/subgc_b200.h); there is no
+torch / CPU fallback and calls fail loudly when the library or a CUDA device is missing.
+
+One extension over the reference: `mode='sample'` accepts B >= 1 images per call (the reference asserts B == 1,
+models/lib/gpn.py:84); images are encoded / scored / NMS-ed independently and decoded as one batch, and the image
+of every returned row is in `model.last_image_of_row`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import check, lib, ptr
+from .config import Dims, dims_from_opt
+
+
+def _holder(**mods):
+    m = nn.Module()
+    for k, v in mods.items():
+        m.add_module(k, v)
+    return m
+
+
+class _CollectionUnit(nn.Module):
+    """Parameter holder for _Collection_Unit (reference models/lib/graph_conv_unit.py:5-26)."""
+
+    def __init__(self, dim, low_rank):
+        super().__init__()
+        self.fc_lft = nn.Linear(dim, low_rank)
+        self.fc_rgt = nn.Linear(low_rank, dim)
+        for lin in (self.fc_lft, self.fc_rgt):  # normal_init(m, 0, 0.001) with zero bias
+            nn.init.normal_(lin.weight, 0.0, 0.001)
+            nn.init.zeros_(lin.bias)
+
+
+def _gcn_backbone(layers, dim, low_rank):
+    gcn = nn.ModuleList()
+    for _ in range(layers):
+        gcn.append(_holder(gcn_collect=_holder(collect_units=nn.ModuleList([_CollectionUnit(dim, low_rank) for _ in range(4)]))))
+    return _holder(gcn=gcn)
+
+
+class Workspace:
+    """Grow-only device scratch buffer handed to the C ABI (which never allocates)."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, nbytes, device):
+        nbytes = int(nbytes) + 256
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        return self.buf
+
+
+class TopDownModel(nn.Module):
+    """Drop-in for reference `TopDownModel(AttModel(CaptionModel))`, Sub-GC configuration."""
+
+    def __init__(self, opt):
+        super().__init__()
+        self.dims: Dims = dims_from_opt(opt)
+        d = self.dims
+        self.vocab_size = d.vocab
+        self.input_encoding_size = d.enc
+        self.rnn_size = d.rnn
+        self.num_layers = 2
+        self.drop_prob_lm = getattr(opt, "drop_prob_lm", 0.5)
+        self.seq_length = d.seq_length
+        self.fc_feat_size = d.fc_feat
+        self.att_feat_size = d.att_feat
+        self.att_hid_size = d.att_hid
+        self.ss_prob = getattr(opt, "sampling_prob", 0.0)
+        self.gpn = True
+        self.GCN_dim = d.gcn
+        self.test_LSTM = getattr(opt, "test_LSTM", 0) != 0
+        self.topk_sampling = getattr(opt, "use_topk_sampling", 0) != 0
+        self.topk_temp = getattr(opt, "topk_temp", 0.6)
+        self.the_k = getattr(opt, "the_k", 3)
+        self.sct = getattr(opt, "sct", 0) != 0
+        self.seq_per_img = getattr(opt, "seq_per_img", 5)
+        if getattr(opt, "use_gt_subg", 0) != 0:
+            raise NotImplementedError("use_gt_subg (Sup. SCT model) is outside the Sub-GC hot path")
+
+        # parameter holders, named exactly like the reference modules (state_dict contract)
+        self.obj_v_proj = nn.Linear(d.att_feat, d.gcn)
+        self.sg_obj_embed = nn.Embedding(d.obj_classes, d.embed)   # GloVe-initialised in the reference; a checkpoint overwrites it
+        self.obj_emb_proj = nn.Linear(d.embed, d.gcn)
+        self.sg_pred_embed = nn.Embedding(d.pred_classes, d.embed)
+        self.pred_emb_prj = nn.Linear(d.embed, d.gcn)
+        self.gcn_backbone = _gcn_backbone(d.gcn_layers, d.gcn, d.low_rank)
+        gpn = nn.Module()
+        gpn.gpn_fc = nn.Sequential(nn.Linear(2 * d.gcn, d.att_hid), nn.ReLU(inplace=True), nn.Dropout(0.5), nn.Linear(d.att_hid, 1))
+        gpn.read_out_proj = nn.Sequential(nn.Linear(2 * d.gcn, d.att_hid), nn.Linear(d.att_hid, 2 * d.gcn))
+        for lin in (gpn.gpn_fc[0], gpn.gpn_fc[3], gpn.read_out_proj[0], gpn.read_out_proj[1]):
+            nn.init.zeros_(lin.bias)
+        gpn.use_nms = not self.sct
+        gpn.iou_thres = getattr(opt, "gpn_nms_thres", 0.75)
+        gpn.max_subgraphs = getattr(opt, "gpn_max_subg", 1)
+        gpn.test_LSTM = self.test_LSTM
+        self.gpn_layer = gpn
+        self.logit = nn.Linear(d.rnn, d.v1)
+        self.embed = nn.Sequential(nn.Embedding(d.v1, d.enc), nn.ReLU(), nn.Dropout(self.drop_prob_lm))
+        self.fc_embed = nn.Sequential(nn.Linear(d.att_feat, d.fc_feat), nn.ReLU(), nn.Linear(d.fc_feat, d.rnn), nn.ReLU(),
+                                      nn.Dropout(self.drop_prob_lm))
+        self.att_embed = nn.Sequential(nn.Linear(d.gcn, d.rnn), nn.ReLU(), nn.Dropout(self.drop_prob_lm))
+        self.ctx2att = nn.Linear(d.rnn, d.att_hid)
+        self.core = _holder(attention=_holder(h2att=nn.Linear(d.rnn, d.att_hid), alpha_net=nn.Linear(d.att_hid, 1)),
+                            att_lstm=nn.LSTMCell(d.enc + 2 * d.rnn, d.rnn), lang_lstm=nn.LSTMCell(2 * d.rnn, d.rnn))
+
+        self.done_beams = []
+        self.last_gpn_loss = None
+        self.last_image_of_row = None
+        self.last_steps = None
+        self._ws = Workspace()
+        self._wcache = None
+        self.stage_events = None  # set to [] to collect (name, start_event, end_event) per stage (bench / profiling)
+        self._cdims = _lib.Dims(d.v1, d.enc, d.rnn, d.att_hid, d.fc_feat, d.att_feat, d.gcn, d.low_rank, d.embed, d.obj_classes,
+                                d.pred_classes, d.gcn_layers, d.gcn_residual, d.pred_emb_type, d.seq_length, d.obj_num, d.rel_num)
+
+    # ------------------------------------------------------------------------------------------------------------
+    # plumbing
+    # ------------------------------------------------------------------------------------------------------------
+    def forward(self, *args, **kwargs):
+        """Reference models/CaptionModel.py:21-26."""
+        mode = kwargs.get("mode", "forward")
+        if "mode" in kwargs:
+            del kwargs["mode"]
+        return getattr(self, "_" + mode)(*args, **kwargs)
+
+    def init_hidden(self, bsz):
+        """Reference models/AttModel.py:343-346."""
+        w = self.logit.weight
+        return (w.new_zeros(self.num_layers, bsz, self.rnn_size), w.new_zeros(self.num_layers, bsz, self.rnn_size))
+
+    def _weights(self):
+        """subgc_weights over the live parameter storage (rebuilt when a tensor moved, e.g. after .cuda() / load)."""
+        params = dict(self.named_parameters())
+        key = tuple(p.data_ptr() for p in params.values())
+        if self._wcache is not None and self._wcache[0] == key:
+            return self._wcache[1]
+        for n, p in params.items():
+            if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
+                raise _lib.SubgcError(f"parameter {n} must be a contiguous fp32 CUDA tensor (got {p.dtype} on {p.device}); "
+                                      "the Sub-GC path has no CPU implementation")
+        g = lambda n: params[n].data_ptr()
+        lin = lambda n: _lib.Linear(g(n + ".weight"), g(n + ".bias"))
+        w = _lib.Weights()
+        w.obj_v_proj = lin("obj_v_proj"); w.sg_obj_embed = g("sg_obj_embed.weight"); w.obj_emb_proj = lin("obj_emb_proj")
+        w.sg_pred_embed = g("sg_pred_embed.weight"); w.pred_emb_prj = lin("pred_emb_prj")
+        for l in range(self.dims.gcn_layers):
+            for u in range(4):
+                pre = f"gcn_backbone.gcn.{l}.gcn_collect.collect_units.{u}."
+                w.gcn_lft[l][u] = lin(pre + "fc_lft")
+                w.gcn_rgt[l][u] = lin(pre + "fc_rgt")
+        w.gpn_fc0 = lin("gpn_layer.gpn_fc.0"); w.gpn_fc3 = lin("gpn_layer.gpn_fc.3")
+        w.read_out0 = lin("gpn_layer.read_out_proj.0"); w.read_out1 = lin("gpn_layer.read_out_proj.1")
+        w.logit = lin("logit"); w.embed = g("embed.0.weight")
+        w.fc_embed0 = lin("fc_embed.0"); w.fc_embed2 = lin("fc_embed.2"); w.att_embed = lin("att_embed.0"); w.ctx2att = lin("ctx2att")
+        w.h2att = lin("core.attention.h2att"); w.alpha_net = lin("core.attention.alpha_net")
+        w.att_w_ih = g("core.att_lstm.weight_ih"); w.att_w_hh = g("core.att_lstm.weight_hh")
+        w.att_b_ih = g("core.att_lstm.bias_ih"); w.att_b_hh = g("core.att_lstm.bias_hh")
+        w.lang_w_ih = g("core.lang_lstm.weight_ih"); w.lang_w_hh = g("core.lang_lstm.weight_hh")
+        w.lang_b_ih = g("core.lang_lstm.bias_ih"); w.lang_b_hh = g("core.lang_lstm.bias_hh")
+        self._wcache = (key, w)
+        return w
+
+    @staticmethod
+    def _stream():
+        return torch.cuda.current_stream().cuda_stream
+
+    def _mark(self, name=None):
+        """Stage timing hook: _mark() opens a region on the current stream, _mark(name) closes it."""
+        if self.stage_events is None:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        if name is None:
+            self._open_ev = ev
+        else:
+            self.stage_events.append((name, self._open_ev, ev))
+            self._open_ev = ev
+
+    def _f32(self, t):
+        return t.contiguous().float() if (t.dtype != torch.float32 or not t.is_contiguous()) else t
+
+    def _i64(self, t):
+        return t.contiguous().long() if (t.dtype != torch.int64 or not t.is_contiguous()) else t
+
+    def _check_device(self, *tensors):
+        dev = self.logit.weight.device
+        if dev.type != "cuda":
+            raise _lib.SubgcError("the model must live on a CUDA device (model.cuda()); there is no CPU path")
+        for t in tensors:
+            if t is not None and t.device != dev:
+                raise _lib.SubgcError(f"input tensor on {t.device}, model on {dev}")
+        return dev
+
+    # ------------------------------------------------------------------------------------------------------------
+    # stages (each one is one C-ABI call)
+    # ------------------------------------------------------------------------------------------------------------
+    def encode(self, att_feats, obj_dist, pred_dist, rel_ind, want_x_pred=False):
+        """feat_fusion + gcn_backbone (reference models/AttModel.py:370-387, models/lib/gcn_backbone.py:29-53) WITHOUT the x5
+        replication.  Returns x_obj [B,N,L] (and x_pred [B,K,L] when asked)."""
+        dev = self._check_device(att_feats, obj_dist, pred_dist, rel_ind)
+        L, d, w, cd = lib(), self.dims, self._weights(), self._cdims
+        att_feats, obj_dist, rel_ind = self._f32(att_feats), self._f32(obj_dist), self._i64(rel_ind)
+        B = att_feats.shape[0]
+        need_pred = bool(L.subgc_gcn_needs_pred(C.byref(cd), int(want_x_pred)))
+        x0 = torch.empty(B, d.obj_num, d.gcn, device=dev)
+        p0 = torch.empty(B, d.rel_num, d.gcn, device=dev) if need_pred else None
+        x_obj = torch.empty_like(x0)
+        x_pred = torch.empty(B, d.rel_num, d.gcn, device=dev) if want_x_pred else None
+        wsb = L.subgc_encoder_workspace_bytes(C.byref(cd), B)
+        ws = self._ws.get(wsb, dev)
+        st = self._stream()
+        pd = self._f32(pred_dist) if need_pred else None
+        check(L.subgc_fuse_nodes(C.byref(cd), C.byref(w), B, ptr(att_feats), ptr(obj_dist), ptr(pd), ptr(x0), ptr(p0), ptr(ws),
+                                 ws.numel(), st), "subgc_fuse_nodes")
+        check(L.subgc_gcn_forward(C.byref(cd), C.byref(w), B, ptr(x0), ptr(p0), ptr(rel_ind), ptr(x_obj), ptr(x_pred), ptr(ws),
+                                  ws.numel(), st), "subgc_gcn_forward")
+        self._x0 = x0
+        return (x_obj, x_pred) if want_x_pred else x_obj
+
+    def _sgpn(self, x_obj, gpn_obj_ind, att_masks, order):
+        dev = x_obj.device
+        L, w, cd = lib(), self._weights(), self._cdims
+        rows, _, per_half, _ = gpn_obj_ind.shape
+        lay = _lib.Layout(rows, per_half, self.seq_per_img, order)
+        n_sub = 2 * rows * per_half if order == 0 else 2 * (rows // self.seq_per_img) * per_half
+        read_out = torch.empty(n_sub, 2 * self.dims.gcn, device=dev)
+        score = torch.empty(n_sub, device=dev)
+        sub_len = torch.empty(n_sub, dtype=torch.int32, device=dev)
+        loss = torch.empty(1, device=dev)
+        ws = self._ws.get(L.subgc_sgpn_workspace_bytes(C.byref(cd), n_sub), dev)
+        check(L.subgc_sgpn_forward(C.byref(cd), C.byref(w), C.byref(lay), ptr(x_obj), ptr(gpn_obj_ind), ptr(att_masks), ptr(read_out),
+                                   ptr(score), ptr(sub_len), ptr(loss), ptr(ws), ws.numel(), self._stream()), "subgc_sgpn_forward")
+        return lay, n_sub, read_out, score, sub_len, loss
+
+    def _prepare(self, lay, n_rows, len_max, sel, x_obj, gpn_obj_ind, att_masks, read_out):
+        dev = x_obj.device
+        L, d, w, cd = lib(), self.dims, self._weights(), self._cdims
+        g_fc = torch.empty(n_rows, 2 * d.gcn, device=dev)
+        fc = torch.empty(n_rows, d.rnn, device=dev)
+        att = torch.empty(n_rows, len_max, d.rnn, device=dev)
+        p_att = torch.empty(n_rows, len_max, d.att_hid, device=dev)
+        masks = torch.empty(n_rows, len_max, device=dev)
+        ws = self._ws.get(L.subgc_prepare_workspace_bytes(C.byref(cd), n_rows, len_max), dev)
+        check(L.subgc_prepare_forward(C.byref(cd), C.byref(w), C.byref(lay), n_rows, len_max, ptr(sel), ptr(x_obj), ptr(gpn_obj_ind),
+                                      ptr(att_masks), ptr(read_out), ptr(g_fc), ptr(fc), ptr(att), ptr(p_att), ptr(masks), ptr(ws),
+                                      ws.numel(), self._stream()), "subgc_prepare_forward")
+        return g_fc, fc, att, p_att, masks
+
+    def _front(self, att_feats, att_masks, obj_dist, rel_ind, pred_dist, gpn_obj_ind):
+        """Encoder + sGPN + NMS + feature preparation for inference.  One host read-back (kept count, clip length) —
+        the reference synchronises at the same two places (NMS on the host, clip_att's .max())."""
+        dev = self._check_device(att_feats, att_masks, obj_dist, rel_ind, gpn_obj_ind)
+        L, cd = lib(), self._cdims
+        gpn_obj_ind, att_masks = self._i64(gpn_obj_ind), self._f32(att_masks)
+        self._mark()
+        x_obj = self.encode(att_feats, obj_dist, pred_dist, rel_ind)
+        self._mark("encode")
+        lay, n_sub, read_out, score, sub_len, loss = self._sgpn(x_obj, gpn_obj_ind, att_masks, order=1)
+        n_images = lay.rows // self.seq_per_img
+        P = 2 * lay.per_half
+        sel = torch.empty(n_sub, dtype=torch.int32, device=dev)
+        keep = torch.empty(n_sub, dtype=torch.int64, device=dev)
+        stats = torch.empty(2 + n_images, dtype=torch.int32, device=dev)
+        ws = self._ws.get(L.subgc_nms_workspace_bytes(n_images, P), dev)
+        g = self.gpn_layer
+        check(L.subgc_subgraph_nms(C.byref(cd), C.byref(lay), ptr(score), ptr(sub_len), ptr(gpn_obj_ind), ptr(att_masks), int(bool(g.use_nms)),
+                                   float(g.iou_thres), int(g.max_subgraphs), ptr(sel), ptr(keep), ptr(stats), ptr(ws), ws.numel(),
+                                   self._stream()), "subgc_subgraph_nms")
+        self._mark("sgpn_nms")
+        stats_h = stats.cpu()
+        n_rows, len_max = int(stats_h[0]), int(stats_h[1])
+        sel = sel[:n_rows]
+        keep = keep[:n_rows]
+        self._mark()
+        prep = self._prepare(lay, n_rows, len_max, sel, x_obj, gpn_obj_ind, att_masks, read_out)
+        self._mark("prepare")
+        sel_l = sel.long()
+        self.last_gpn_loss = loss[0]
+        self.last_image_of_row = torch.div(sel_l, P, rounding_mode="floor")
+        self.last_x_obj = x_obj
+        self.last_all_scores = score
+        # the reference returns a float arange when NMS is off (models/lib/gpn.py:97) and int64 indices otherwise (:136)
+        keep_ind = keep if g.use_nms else keep.to(score.dtype)
+        return prep, score[sel_l], keep_ind, n_rows, len_max
+
+    # ------------------------------------------------------------------------------------------------------------
+    # reference entry points
+    # ------------------------------------------------------------------------------------------------------------
+    def _sample(self, fc_feats, att_feats, att_masks=None, trip_pred=None, obj_dist=None, obj_box=None, rel_ind=None, pred_fmap=None,
+                pred_dist=None, gpn_obj_ind=None, gpn_pred_ind=None, gpn_nrel_ind=None, gpn_pool_mtx=None, opt={}):
+        """Reference models/AttModel.py:236-326 (greedy / top-k) and :179-234 (beam).  Returns
+        (seq, seqLogprobs, subgraph_score, keep_ind[, att2_weights])."""
+        if not self.test_LSTM:
+            raise _lib.SubgcError("mode='sample' needs a model built with opt.test_LSTM=1 (as test.py does)")
+        beam_size = opt.get("beam_size", 1)
+        return_att = opt.get("return_att", 0) == 1
+        if not opt.get("sample_max", 1) and not self.topk_sampling and beam_size == 1:
+            raise NotImplementedError("sample_max=0 leaves `it` undefined in the reference (AttModel.py:304-307)")
+        (g_fc, fc, att, p_att, masks), sub_score, keep_ind, n_rows, len_max = self._front(att_feats, att_masks, obj_dist, rel_ind,
+                                                                                          pred_dist, gpn_obj_ind)
+        if beam_size > 1:
+            seq, lps = self._beam(fc, att, p_att, masks, n_rows, len_max, opt)
+            return seq, lps, sub_score, keep_ind
+        dev = fc.device
+        L, w, cd, T = lib(), self._weights(), self._cdims, self.seq_length
+        seq = torch.empty(n_rows, T, dtype=torch.int64, device=dev)
+        lps = torch.empty(n_rows, T, device=dev)
+        attw = torch.empty(n_rows, T + 1, len_max, device=dev) if return_att else None
+        steps = torch.empty(1, dtype=torch.int32, device=dev)
+        ws = self._ws.get(L.subgc_decode_workspace_bytes(C.byref(cd), n_rows, len_max), dev)
+        uniforms = opt.get("topk_uniforms", None)
+        if uniforms is not None:
+            uniforms = self._f32(uniforms.to(dev))
+            assert uniforms.shape == (T, n_rows), "topk_uniforms must be [seq_length, rows]"
+        seed = int(opt.get("seed", torch.initial_seed())) & (2 ** 64 - 1)
+        offset = int(opt.get("seed_offset", 0))
+        check(L.subgc_decode_sample(C.byref(cd), C.byref(w), n_rows, len_max, 1 if self.topk_sampling else 0, float(self.topk_temp),
+                                    int(self.the_k), seed, offset, ptr(uniforms), ptr(fc), ptr(att), ptr(p_att), ptr(masks), ptr(seq),
+                                    ptr(lps), ptr(attw), ptr(steps), ptr(ws), ws.numel(), self._stream()), "subgc_decode_sample")
+        self._mark("decode")
+        self.last_steps = steps
+        if return_att:
+            return seq, lps, sub_score, keep_ind, attw[:, :int(steps.item())]
+        return seq, lps, sub_score, keep_ind
+
+    def _beam(self, fc, att, p_att, masks, n_sub, len_max, opt):
+        """Batched replacement of the per-sub-graph beam loop (reference models/AttModel.py:208-234)."""
+        if opt.get("group_size", 1) != 1:
+            raise NotImplementedError("diverse beam search (group_size > 1) is not part of the Sub-GC configurations")
+        dev = fc.device
+        L, w, cd, T = lib(), self._weights(), self._cdims, self.seq_length
+        b = int(opt.get("beam_size", 10))
+        pen = opt.get("length_penalty", "")
+        kind, alpha = 0, 0.0
+        if pen:
+            name, a = pen.split("_")
+            kind, alpha = {"wu": 1, "avg": 2}[name], float(a)
+        done_seq = torch.empty(n_sub, b, T, dtype=torch.int64, device=dev)
+        done_lps = torch.empty(n_sub, b, T, device=dev)
+        done_p = torch.empty(n_sub, b, dtype=torch.float64, device=dev)
+        done_up = torch.empty(n_sub, b, dtype=torch.float64, device=dev)
+        done_cnt = torch.empty(n_sub, dtype=torch.int32, device=dev)
+        ws = self._ws.get(L.subgc_beam_workspace_bytes(C.byref(cd), n_sub, b, len_max), dev)
+        check(L.subgc_decode_beam(C.byref(cd), C.byref(w), n_sub, len_max, b, kind, alpha, int(opt.get("decoding_constraint", 0)), ptr(fc),
+                                  ptr(att), ptr(p_att), ptr(masks), ptr(done_seq), ptr(done_lps), ptr(done_p), ptr(done_up), ptr(done_cnt),
+                                  ptr(ws), ws.numel(), self._stream()), "subgc_decode_beam")
+        self._mark("decode")
+        # the reference hands back CPU tensors and python lists here (AttModel.py:212-213,229-231)
+        seq_h, lps_h, p_h, up_h, cnt_h = done_seq.cpu(), done_lps.cpu(), done_p.cpu(), done_up.cpu(), done_cnt.cpu()
+        self.done_beams = [[dict(seq=seq_h[k, j], logps=lps_h[k, j], unaug_p=float(up_h[k, j]), p=float(p_h[k, j]))
+                            for j in range(int(cnt_h[k]))] for k in range(n_sub)]
+        return seq_h[:, 0].contiguous(), lps_h[:, 0].contiguous()
+
+    def get_logprobs_state(self, it, fc_feats, att_feats, p_att_feats, att_masks, state, sg_emb=None, p_sg_emb=None, return_att=False):
+        """Reference models/AttModel.py:328-341 (eval mode).  `fc_feats` may have fewer rows than `it` when consecutive
+        rows share a context (beam search)."""
+        dev = self._check_device(it, fc_feats, att_feats, p_att_feats, att_masks)
+        L, w, cd = lib(), self._weights(), self._cdims
+        S, n_ctx, len_max = it.shape[0], fc_feats.shape[0], att_feats.shape[1]
+        h_in, c_in = self._f32(state[0]), self._f32(state[1])
+        h_out, c_out = torch.empty_like(h_in), torch.empty_like(c_in)
+        logp = torch.empty(S, self.dims.v1, device=dev)
+        attw = torch.empty(S, len_max, device=dev) if return_att else None
+        ws = self._ws.get(L.subgc_decode_workspace_bytes(C.byref(cd), S, len_max), dev)
+        check(L.subgc_decode_step(C.byref(cd), C.byref(w), S, len_max, S // n_ctx, ptr(self._i64(it)), ptr(self._f32(fc_feats)),
+                                  ptr(self._f32(att_feats)), ptr(self._f32(p_att_feats)), ptr(self._f32(att_masks)), ptr(h_in), ptr(c_in),
+                                  ptr(h_out), ptr(c_out), ptr(logp), ptr(attw), ptr(ws), ws.numel(), self._stream()), "subgc_decode_step")
+        if return_att:
+            return logp, (h_out, c_out), attw
+        return logp, (h_out, c_out)
+
+    def _forward(self, fc_feats, att_feats, seq, att_masks=None, trip_pred=None, obj_dist=None, obj_box=None, rel_ind=None,
+                 pred_fmap=None, pred_dist=None, gpn_obj_ind=None, gpn_pred_ind=None, gpn_nrel_ind=None, gpn_pool_mtx=None):
+        """Reference models/AttModel.py:122-177, evaluation semantics (no dropout, no scheduled sampling): returns
+        (outputs [5B, T', V+1] log-probs, gpn_loss, subgraph_score [2*5B*G, 1])."""
+        if self.training:
+            raise NotImplementedError("training-mode forward (dropout + autograd) is not implemented by the CUDA path yet; "
+                                      "call model.eval() (validation loss, eval_utils.py:73-86)")
+        dev = self._check_device(att_feats, seq, att_masks, obj_dist, rel_ind, gpn_obj_ind)
+        L, w, cd = lib(), self._weights(), self._cdims
+        gpn_obj_ind, att_masks, seq = self._i64(gpn_obj_ind), self._f32(att_masks), self._i64(seq)
+        x_obj = self.encode(att_feats, obj_dist, pred_dist, rel_ind)
+        lay, n_sub, read_out, score, sub_len, loss = self._sgpn(x_obj, gpn_obj_ind, att_masks, order=0)
+        rows = lay.rows
+        sel = torch.empty(rows, dtype=torch.int32, device=dev)
+        stats = torch.empty(2, dtype=torch.int32, device=dev)
+        check(L.subgc_sgpn_select_train(C.byref(lay), ptr(score), ptr(sub_len), ptr(sel), ptr(stats), self._stream()),
+              "subgc_sgpn_select_train")
+        len_max = int(stats.cpu()[1])
+        g_fc, fc, att, p_att, masks = self._prepare(lay, rows, len_max, sel, x_obj, gpn_obj_ind, att_masks, read_out)
+        n_steps = seq.shape[1] - 1
+        outputs = torch.empty(rows, n_steps, self.dims.v1, device=dev)
+        ws = self._ws.get(L.subgc_teacher_workspace_bytes(C.byref(cd), rows, n_steps), dev)
+        check(L.subgc_decode_teacher(C.byref(cd), C.byref(w), rows, len_max, n_steps, ptr(seq), seq.shape[1], ptr(fc), ptr(att), ptr(p_att),
+                                     ptr(masks), ptr(outputs), ptr(ws), ws.numel(), self._stream()), "subgc_decode_teacher")
+        self.last_sel = sel
+        return outputs, loss[0], score.view(-1, 1)
+
+
+class LanguageModelCriterion(nn.Module):
+    """Reference misc/utils.py:111-124."""
+
+    def forward(self, input, target, mask):
+        target = target[:, :input.size(1)]
+        mask = mask[:, :input.size(1)]
+        output = -input.gather(2, target.unsqueeze(2)).squeeze(2) * mask
+        return torch.sum(output) / torch.sum(mask)
+
+
+class LossWrapper(nn.Module):
+    """Reference models/loss_wrapper.py:7-27."""
+
+    def __init__(self, model, opt):
+        super().__init__()
+        self.opt = opt
+        self.model = model
+        self.crit = LanguageModelCriterion()
+
+    def forward(self, fc_feats, att_feats, labels, masks, att_masks, gts, gt_indices, trip_pred, obj_dist, obj_box, rel_ind, pred_fmap,
+                pred_dist, gpn_obj_ind, gpn_pred_ind, gpn_nrel_ind, gpn_pool_mtx):
+        lang_output, gpn_loss, _ = self.model(fc_feats, att_feats, labels, att_masks, trip_pred, obj_dist, obj_box, rel_ind, pred_fmap,
+                                              pred_dist, gpn_obj_ind, gpn_pred_ind, gpn_nrel_ind, gpn_pool_mtx)
+        lang_loss = self.crit(lang_output, labels[:, 1:], masks[:, 1:]) if lang_output is not None else None
+        return {"gpn_loss": gpn_loss, "lang_loss": lang_loss}
+
+
+def setup(opt):
+    """Reference models/__init__.py:43-59."""
+    import os
+    if opt.caption_model != "topdown":
+        raise Exception("Caption model not supported: {}".format(opt.caption_model))
+    model = TopDownModel(opt)
+    if vars(opt).get("start_from", None) is not None:
+        assert os.path.isdir(opt.start_from), " %s must be a a path" % opt.start_from
+        assert os.path.isfile(os.path.join(opt.start_from, "infos_" + opt.id + ".pkl")), \
+            "infos.pkl file does not exist in path %s" % opt.start_from
+        model.load_state_dict(torch.load(os.path.join(opt.start_from, "model.pth")))
+    return model

@@ -1,0 +1,92 @@
+"""CPU-only checks of the host side: the C-ABI library builds, loads and exports exactly what include/subgc_b200.h
+declares; the module keeps the reference's state_dict contract; and the product path refuses to run without CUDA
+(no CPU fallback).  No compute entry point is called here."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from subgc import _lib, synth
+from subgc.build import build
+from subgc.config import SMALL, Dims, dims_from_opt, make_opt
+from subgc.model import LossWrapper, TopDownModel, setup
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def libpath():
+    return build()
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "subgc_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return set(re.findall(r"\b(subgc_[a-z0-9_]+)\s*\(", text))
+
+
+def test_header_and_binding_declare_the_same_symbols():
+    assert header_symbols() == set(_lib.SIGNATURES)
+
+
+def test_library_exports_every_declared_symbol(libpath):
+    handle = ctypes.CDLL(libpath)
+    for name in header_symbols():
+        assert hasattr(handle, name), name
+    handle.subgc_version.restype = ctypes.c_int
+    assert handle.subgc_version() == 1
+
+
+def test_struct_layouts_match_the_header():
+    assert ctypes.sizeof(_lib.Dims) == 17 * 4
+    assert ctypes.sizeof(_lib.Linear) == 16
+    n_linear = 3 + 2 * 4 * _lib.MAX_GCN_LAYERS + 5 + 6
+    assert ctypes.sizeof(_lib.Weights) == 16 * n_linear + 8 * (3 + 8)
+    assert ctypes.sizeof(_lib.Layout) == 16
+
+
+@pytest.mark.parametrize("d", [SMALL, Dims()])
+def test_state_dict_contract(d):
+    m = setup(make_opt(d, test_LSTM=1))
+    sd = m.state_dict()
+    want = synth.param_shapes(d)
+    assert list(sd.keys()) == list(want.keys())
+    for k, shape in want.items():
+        assert tuple(sd[k].shape) == tuple(shape), k
+    if d is not SMALL:
+        assert sum(v.numel() for v in sd.values()) == 70048210  # SURVEY headline fact
+    m.load_state_dict(synth.make_state_dict(d, 1), strict=True)
+
+
+def test_reference_attributes_and_dispatch():
+    m = setup(make_opt(SMALL, test_LSTM=1, gpn_nms_thres=0.5, gpn_max_subg=7, use_topk_sampling=1, the_k=4, topk_temp=0.7))
+    assert isinstance(m, TopDownModel)
+    assert m.gpn and m.seq_length == SMALL.seq_length and m.vocab_size == SMALL.vocab and m.num_layers == 2
+    assert m.gpn_layer.iou_thres == 0.5 and m.gpn_layer.max_subgraphs == 7 and m.gpn_layer.use_nms
+    assert m.topk_sampling and m.the_k == 4 and m.topk_temp == 0.7
+    m.ss_prob = 0.25  # train.py:131 writes it
+    h, c = m.init_hidden(3)
+    assert h.shape == (2, 3, SMALL.rnn) and float(h.abs().sum()) == 0
+    lw = LossWrapper(m, None)
+    assert hasattr(lw, "crit")
+    with pytest.raises(Exception):
+        setup(make_opt(SMALL, caption_model="fc"))
+
+
+def test_no_cpu_fallback():
+    d = SMALL
+    m = setup(make_opt(d, test_LSTM=1)).eval()
+    data = synth.make_test_inputs(d, 1)
+    with pytest.raises(_lib.SubgcError):
+        m(*synth.sample_args(data), opt={"beam_size": 1}, mode="sample")
+    with pytest.raises(_lib.SubgcError):
+        m.get_logprobs_state(torch.zeros(2, dtype=torch.long), torch.zeros(2, d.rnn), torch.zeros(2, 3, d.rnn),
+                             torch.zeros(2, 3, d.att_hid), torch.ones(2, 3), m.init_hidden(2))
+
+
+def test_unsupported_variants_are_rejected():
+    for over in (dict(use_gpn=0), dict(noun_fuse=0), dict(gcn_bn=1), dict(use_bn=1)):
+        with pytest.raises(NotImplementedError):
+            dims_from_opt(make_opt(Dims(), **over))
