@@ -236,14 +236,25 @@ static int count_tiles(const GemmProblem& p) {
     return t;
 }
 
+// Upper bounds independent of how K is cut into segments (each segment rounds its tile count up separately).
+static int max_splits(int M, int N) {
+    long long tiles64 = (long long)((M + 63) / 64) * ((N + 63) / 64);
+    long long tiles128 = (long long)((M + 127) / 128) * ((N + 127) / 128);
+    long long tiles = tiles64 < tiles128 ? tiles64 : tiles128;  // whichever tile shape the plan picks, it has >= this many CTAs
+    if (tiles >= kTargetCtas) return 1;
+    long long s = kTargetCtas / tiles;
+    return (int)(s > 32 ? 32 : s);
+}
+
 size_t gemm_workspace_bytes(int M, int N, int Ktotal) {
-    GemmPlan pl = plan_gemm(M, N, (Ktotal + BK - 1) / BK + 4);
-    return pl.splits > 1 ? align_up((size_t)pl.splits * M * N * sizeof(float), 256) : 0;
+    (void)Ktotal;
+    int s = max_splits(M, N);
+    return s > 1 ? align_up((size_t)s * M * N * sizeof(float), 256) : 0;
 }
 
 size_t gemm_partial_elems(int M, int N, int Ktotal) {
-    GemmPlan pl = plan_gemm(M, N, (Ktotal + BK - 1) / BK + 4);
-    return (size_t)pl.splits * M * N;
+    (void)Ktotal;
+    return (size_t)max_splits(M, N) * M * N;
 }
 
 static bool vec_ok(const GemmProblem& p) {
