@@ -125,6 +125,10 @@ int launch_gemm(const GemmProblem& p, void* ws, size_t ws_bytes, cudaStream_t st
 // and report the split count through *out_splits; no epilogue is applied.
 int launch_gemm_ex(const GemmProblem& p, float* raw_part, size_t raw_part_elems, int* out_splits, void* ws, size_t ws_bytes,
                    cudaStream_t stream);
+// tensor-core (tcgen05, split-precision TF32) variant of the same contraction, umma_gemm.cu
+bool tc_eligible(const GemmProblem& p);
+size_t tc_workspace_bytes(int M, int N, int Ktotal);
+int launch_gemm_tc(const GemmProblem& p, void* ws, size_t ws_bytes, cudaStream_t stream);
 // upper bound of splits * M * N floats for launch_gemm_ex raw partials
 size_t gemm_partial_elems(int M, int N, int Ktotal);
 

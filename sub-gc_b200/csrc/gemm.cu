@@ -247,9 +247,10 @@ static int max_splits(int M, int N) {
 }
 
 size_t gemm_workspace_bytes(int M, int N, int Ktotal) {
-    (void)Ktotal;
     int s = max_splits(M, N);
-    return s > 1 ? align_up((size_t)s * M * N * sizeof(float), 256) : 0;
+    size_t simt = s > 1 ? align_up((size_t)s * M * N * sizeof(float), 256) : 0;
+    size_t tc = tc_workspace_bytes(M, N, Ktotal);
+    return simt > tc ? simt : tc;
 }
 
 size_t gemm_partial_elems(int M, int N, int Ktotal) {
@@ -323,7 +324,18 @@ int launch_gemm_ex(const GemmProblem& p, float* raw_part, size_t raw_part_elems,
     return SUBGC_OK;
 }
 
+void launch_splitk_reduce(const GemmProblem& p, const float* part, int splits, cudaStream_t stream) {
+    size_t total = (size_t)p.M * p.N;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(p, part, splits);
+}
+
 int launch_gemm(const GemmProblem& p, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    if (p.M > 0 && tc_eligible(p)) {
+        SUBGC_CHECK_ARG(p.N > 0 && p.C != nullptr && p.ldc >= p.N, "gemm: bad output");
+        return launch_gemm_tc(p, ws, ws_bytes, stream);
+    }
     return launch_gemm_ex(p, nullptr, 0, nullptr, ws, ws_bytes, stream);
 }
 
