@@ -128,7 +128,10 @@ int launch_gemm_ex(const GemmProblem& p, float* raw_part, size_t raw_part_elems,
 // tensor-core (tcgen05, split-precision TF32) variant of the same contraction, umma_gemm.cu
 bool tc_eligible(const GemmProblem& p);
 size_t tc_workspace_bytes(int M, int N, int Ktotal);
-int launch_gemm_tc(const GemmProblem& p, void* ws, size_t ws_bytes, cudaStream_t stream);
+struct RawPartials { const float* part; int splits; };  // [splits][M][N] partial sums, to be added in z order
+int launch_gemm_tc(const GemmProblem& p, void* ws, size_t ws_bytes, cudaStream_t stream, RawPartials* raw = nullptr);
+// contraction without epilogue: the partial sums stay in `ws` for a consumer kernel that reduces them itself
+int launch_gemm_raw(const GemmProblem& p, void* ws, size_t ws_bytes, cudaStream_t stream, RawPartials* raw);
 // upper bound of splits * M * N floats for launch_gemm_ex raw partials
 size_t gemm_partial_elems(int M, int N, int Ktotal);
 

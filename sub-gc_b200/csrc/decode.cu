@@ -18,50 +18,88 @@
 
 namespace subgc {
 
-// ---- pointwise LSTM cell (torch.nn.LSTMCell gate order i, f, g, o) --------------------------------------------
-__global__ void __launch_bounds__(256) lstm_cell_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev,
-                                                        const long long* __restrict__ parent, float* __restrict__ h_out,
-                                                        float* __restrict__ c_out, int S, int H, const int* __restrict__ active) {
+// ---- split-K reduction + biases + LSTM cell (torch.nn.LSTMCell gate order i, f, g, o) ---------------------------
+// gates[r, g*H + j] = sum_z part[z][r][g*H + j] + b_ih + b_hh (z ascending: deterministic); c' = s(f) c + s(i) tanh(g); h' = s(o) tanh(c')
+__global__ void __launch_bounds__(256) lstm_reduce_cell_kernel(const float* __restrict__ part, int splits, const float* __restrict__ b_ih,
+                                                               const float* __restrict__ b_hh, const float* __restrict__ c_prev,
+                                                               const long long* __restrict__ parent, float* __restrict__ h_out,
+                                                               float* __restrict__ c_out, int S, int H, const int* __restrict__ active) {
     if (active != nullptr && *active == 0) return;
+    const size_t zs = (size_t)S * 4 * H;
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= S * H) return;
     int r = idx / H, j = idx - r * H;
-    const float* g = gates + (size_t)r * 4 * H;
+    const float* g = part + (size_t)r * 4 * H + j;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int z = 0; z < splits; ++z) {  // one hidden unit per thread keeps ~128 K threads in flight; 16 independent loads each
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] += g[(size_t)z * zs + (size_t)q * H];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] = (acc[q] + __ldg(b_ih + q * H + j)) + __ldg(b_hh + q * H + j);
     long long pr = parent ? parent[r] : r;
-    float gi = g[j], gf = g[H + j], gg = g[2 * H + j], go = g[3 * H + j];
-    float c = sigmoidf_(gf) * c_prev[(size_t)pr * H + j] + sigmoidf_(gi) * tanhf(gg);
+    float c = sigmoidf_(acc[1]) * c_prev[(size_t)pr * H + j] + sigmoidf_(acc[0]) * tanhf(acc[2]);
     c_out[idx] = c;
-    h_out[idx] = sigmoidf_(go) * tanhf(c);
+    h_out[idx] = sigmoidf_(acc[3]) * tanhf(c);
 }
 
 // ---- fused attention: one block per decode row -------------------------------------------------------------------
-// e_n = w . tanh(p_att[n] + atth) + b ; alpha = softmax_n(e) ; alpha *= mask ; alpha /= sum(alpha) ; ctx = sum_n alpha_n att[n]
-__global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ atth, const float* __restrict__ p_att,
-                                                        const float* __restrict__ att, const float* __restrict__ masks,
-                                                        const float* __restrict__ alpha_w, const float* __restrict__ alpha_b,
-                                                        float* __restrict__ ctx, float* __restrict__ att_w, int att_w_stride, int len_max, int H,
-                                                        int AH, int rows_per_ctx, const int* __restrict__ active) {
+// atth = sum_z part[z][r] + b_h (h2att split-K partials reduced here); e_n = w . tanh(p_att[n] + atth) + b ;
+// alpha = softmax_n(e) ; alpha *= mask ; alpha /= sum(alpha) ; ctx = sum_n alpha_n att[n]
+constexpr int kAttThreads = 1024;  // one block per row; the row is latency-bound (28 MB of att / p_att per step over 128 rows), so every
+                                   // warp slot of the SM is used to keep loads in flight
+
+__global__ void __launch_bounds__(kAttThreads) attention_kernel(const float* __restrict__ atth_part, int splits, const float* __restrict__ h2att_b,
+                                                                const float* __restrict__ p_att, const float* __restrict__ att,
+                                                                const float* __restrict__ masks, const float* __restrict__ alpha_w,
+                                                                const float* __restrict__ alpha_b, float* __restrict__ ctx, float* __restrict__ att_w,
+                                                                int att_w_stride, int S, int len_max, int H, int AH, int rows_per_ctx,
+                                                                const int* __restrict__ active) {
     if (active != nullptr && *active == 0) return;
-    extern __shared__ float s_att[];  // [AH] atth | [AH] alpha_w | [len_max] e
+    extern __shared__ float s_att[];  // [AH] atth | [AH] alpha_w | [64] e | [4][H] context partials
     float* s_h = s_att;
     float* s_w = s_att + AH;
     float* s_e = s_att + 2 * AH;
+    float* s_c = s_att + 2 * AH + 64;
     const int r = blockIdx.x, cr = r / rows_per_ctx;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (int j = threadIdx.x; j < AH; j += blockDim.x) {
-        s_h[j] = atth[(size_t)r * AH + j];
+        float a = 0.f;
+        for (int z = 0; z < splits; ++z) a += atth_part[((size_t)z * S + r) * AH + j];
+        s_h[j] = a + __ldg(h2att_b + j);
         s_w[j] = __ldg(alpha_w + j);
     }
     __syncthreads();
     const float* pa = p_att + (size_t)cr * len_max * AH;
-    for (int n = wid; n < len_max; n += nw) {
-        float a = 0.f;
-        for (int j = lane; j < AH; j += 32) a = fmaf(s_w[j], tanhf(__ldg(pa + (size_t)n * AH + j) + s_h[j]), a);
-        a = warp_sum(a);
-        if (lane == 0) s_e[n] = a + __ldg(alpha_b);
+    if ((AH & 3) == 0) {
+        const int AH4 = AH >> 2;
+        const float4* h4 = reinterpret_cast<const float4*>(s_h);
+        const float4* w4 = reinterpret_cast<const float4*>(s_w);
+        for (int n = wid; n < len_max; n += nw) {
+            const float4* pr = reinterpret_cast<const float4*>(pa + (size_t)n * AH);
+            float a = 0.f;
+#pragma unroll 4
+            for (int j4 = lane; j4 < AH4; j4 += 32) {
+                const float4 v = __ldg(pr + j4), hh = h4[j4], ww = w4[j4];
+                a = fmaf(ww.x, tanhf(v.x + hh.x), a);
+                a = fmaf(ww.y, tanhf(v.y + hh.y), a);
+                a = fmaf(ww.z, tanhf(v.z + hh.z), a);
+                a = fmaf(ww.w, tanhf(v.w + hh.w), a);
+            }
+            a = warp_sum(a);
+            if (lane == 0) s_e[n] = a + __ldg(alpha_b);
+        }
+    } else {
+        for (int n = wid; n < len_max; n += nw) {
+            float a = 0.f;
+            for (int j = lane; j < AH; j += 32) a = fmaf(s_w[j], tanhf(__ldg(pa + (size_t)n * AH + j) + s_h[j]), a);
+            a = warp_sum(a);
+            if (lane == 0) s_e[n] = a + __ldg(alpha_b);
+        }
     }
     __syncthreads();
-    if (wid == 0) {  // len_max <= 64: one warp finishes the softmax / mask / renormalise
+    if (wid == 0) {  // len_max <= 64: one warp finishes the softmax / mask / renormalise (two-stage, as the reference)
         float m = -INFINITY;
         for (int n = lane; n < len_max; n += 32) m = fmaxf(m, s_e[n]);
         m = warp_max(m);
@@ -83,12 +121,30 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
         }
     }
     __syncthreads();
+    // context: four thread groups take interleaved node subsets (n = g, g+4, ...), partials combined in fixed order
     const float* af = att + (size_t)cr * len_max * H;
-    for (int j = threadIdx.x; j < H; j += blockDim.x) {
-        float a = 0.f;
-        for (int n = 0; n < len_max; ++n) a = fmaf(s_e[n], __ldg(af + (size_t)n * H + j), a);
-        ctx[(size_t)r * H + j] = a;
+    const int grp = threadIdx.x >> 8, tg = threadIdx.x & 255;
+    if ((H & 3) == 0) {
+        const int H4 = H >> 2;
+        for (int j4 = tg; j4 < H4; j4 += 256) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 9
+            for (int n = grp; n < len_max; n += 4) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(af + (size_t)n * H) + j4);
+                const float wv = s_e[n];
+                a.x = fmaf(wv, v.x, a.x); a.y = fmaf(wv, v.y, a.y); a.z = fmaf(wv, v.z, a.z); a.w = fmaf(wv, v.w, a.w);
+            }
+            reinterpret_cast<float4*>(s_c + (size_t)grp * H)[j4] = a;
+        }
+    } else {
+        for (int j = tg; j < H; j += 256) {
+            float a = 0.f;
+            for (int n = grp; n < len_max; n += 4) a = fmaf(s_e[n], __ldg(af + (size_t)n * H + j), a);
+            s_c[(size_t)grp * H + j] = a;
+        }
     }
+    __syncthreads();
+    for (int j = threadIdx.x; j < H; j += blockDim.x) ctx[(size_t)r * H + j] = ((s_c[j] + s_c[H + j]) + s_c[2 * H + j]) + s_c[3 * H + j];
 }
 
 // ---- row-wise log_softmax (materialised log-probs: get_logprobs_state API and beam search) ----------------------
@@ -131,7 +187,9 @@ struct Philox {
 constexpr int kMaxTopK = 16;
 
 struct SelectArgs {
-    const float* logits;   // [S, V1]
+    const float* logits;   // [S, V1] materialised logits, or (splits > 0) split-K partials [splits][S][V1] without bias
+    int splits;
+    const float* bias;     // logit bias, added here when reading partials
     int V1, T, t, S;
     int mode;              // 0 greedy, 1 top-k sampling
     float temp;
@@ -146,14 +204,39 @@ struct SelectArgs {
     const int* active;
 };
 
-__global__ void __launch_bounds__(256) select_kernel(const SelectArgs a) {
+constexpr int kSelectThreads = 1024;  // one block per row: the row is latency-bound, so use every warp slot of the SM
+
+__global__ void __launch_bounds__(kSelectThreads) select_kernel(const SelectArgs a) {
     if (a.active != nullptr && *a.active == 0) return;
     __shared__ float redv[32];
     __shared__ int redi[32];
     __shared__ float s_topv[kMaxTopK];
     __shared__ int s_topi[kMaxTopK];
+    extern __shared__ float s_row[];  // [V1] the logit row (reduced from the partials)
     const int r = blockIdx.x;
-    const float* x = a.logits + (size_t)r * a.V1;
+    if (a.splits > 0) {
+        const size_t zs = (size_t)a.S * a.V1;
+        const float* p0 = a.logits + (size_t)r * a.V1;
+        for (int j0 = threadIdx.x; j0 < a.V1; j0 += 4 * blockDim.x) {  // 4 columns x splits independent loads in flight
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int z = 0; z < a.splits; ++z) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + u * blockDim.x;
+                    if (j < a.V1) v[u] += p0[(size_t)z * zs + j];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + u * blockDim.x;
+                if (j < a.V1) s_row[j] = v[u] + __ldg(a.bias + j);
+            }
+        }
+    } else {
+        for (int j = threadIdx.x; j < a.V1; j += blockDim.x) s_row[j] = a.logits[(size_t)r * a.V1 + j];
+    }
+    __syncthreads();
+    const float* x = s_row;
     // max (first index) and log-sum-exp of the logits
     float bv = -INFINITY;
     int bi = 0x7fffffff;
@@ -282,15 +365,19 @@ static bool take_step_scratch(const subgc_dims* d, int S, Workspace& ws, StepScr
     return ws.ok();
 }
 
-// upto: 0 = whole step (logits written), 1 = stop after the attention (the reference's discarded last step, only
-// its attention weights are observable).  parent (nullable) re-maps the previous-state rows (beam re-ordering).
+// upto: 0 = whole step, 1 = stop after the attention (the reference's discarded last step, only its attention
+// weights are observable).  parent (nullable) re-maps the previous-state rows (beam re-ordering).
+// raw_logits != nullptr: the logit contraction leaves its split-K partials (no bias) for a fused consumer
+// (select_kernel); otherwise `logits` [S, V1] is materialised with the bias applied.
 static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int len_max, int rows_per_ctx, const long long* it,
                        const long long* parent, const float* fc, const float* att, const float* p_att, const float* masks,
-                       const float* h_in, const float* c_in, float* h_out, float* c_out, float* logits, float* att_w, int att_w_stride,
-                       const StepScratch& sc, const int* active, int upto, cudaStream_t st) {
+                       const float* h_in, const float* c_in, float* h_out, float* c_out, float* logits, RawPartials* raw_logits, float* att_w,
+                       int att_w_stride, const StepScratch& sc, const int* active, int upto, cudaStream_t st) {
     const int H = d->rnn, X = d->enc, AH = d->att_hid, V1 = d->vocab1;
     const size_t SH = (size_t)S * H;
+    const int pw_blocks = (int)((SH + 255) / 256);
     GemmProblem p;
+    RawPartials rp;
     // attention LSTM: gates = W_ih [h_lang | fc | relu(E[it])] + b_ih + W_hh h_att + b_hh   (AttModel.py:410-413)
     p.M = S; p.N = 4 * H; p.nseg = 4;
     p.seg[0] = make_seg(h_in + SH, H, w->att_w_ih, X + 2 * H, H);
@@ -302,24 +389,19 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
     p.seg[2].relu_a = 1;
     p.seg[3] = make_seg(h_in, H, w->att_w_hh, H, H);
     p.seg[3].gather = parent;
-    p.epi.bias = w->att_b_ih; p.epi.bias2 = w->att_b_hh;
-    p.C = sc.gates; p.ldc = 4 * H;
     p.active = active;
-    SUBGC_TRY(launch_gemm(p, sc.gemm_ws, sc.gemm_ws_bytes, st));
-    const int pw_blocks = (int)((SH + 255) / 256);
-    lstm_cell_kernel<<<pw_blocks, 256, 0, st>>>(sc.gates, c_in, parent, h_out, c_out, S, H, active);
+    SUBGC_TRY(launch_gemm_raw(p, sc.gemm_ws, sc.gemm_ws_bytes, st, &rp));
+    lstm_reduce_cell_kernel<<<pw_blocks, 256, 0, st>>>(rp.part, rp.splits, w->att_b_ih, w->att_b_hh, c_in, parent, h_out, c_out, S, H, active);
     SUBGC_LAUNCH_CHECK();
-    // attention (AttModel.py:445-471)
+    // attention (AttModel.py:445-471); the h2att partials are reduced inside the attention kernel
     p = GemmProblem();
     p.M = S; p.N = AH; p.nseg = 1;
     p.seg[0] = make_seg(h_out, H, w->h2att.w, H, H);
-    p.epi.bias = w->h2att.b;
-    p.C = sc.atth; p.ldc = AH;
     p.active = active;
-    SUBGC_TRY(launch_gemm(p, sc.gemm_ws, sc.gemm_ws_bytes, st));
-    size_t smem = (size_t)(2 * AH + len_max) * sizeof(float);
-    attention_kernel<<<S, 256, smem, st>>>(sc.atth, p_att, att, masks, w->alpha_net.w, w->alpha_net.b, sc.ctx, att_w, att_w_stride, len_max, H,
-                                           AH, rows_per_ctx, active);
+    SUBGC_TRY(launch_gemm_raw(p, sc.gemm_ws, sc.gemm_ws_bytes, st, &rp));
+    size_t smem = (size_t)(2 * AH + 64 + 4 * H) * sizeof(float);
+    attention_kernel<<<S, kAttThreads, smem, st>>>(rp.part, rp.splits, w->h2att.b, p_att, att, masks, w->alpha_net.w, w->alpha_net.b, sc.ctx, att_w,
+                                           att_w_stride, S, len_max, H, AH, rows_per_ctx, active);
     SUBGC_LAUNCH_CHECK();
     if (upto == 1) return SUBGC_OK;
     // language LSTM on [ctx | h_att] (AttModel.py:421-423)
@@ -329,28 +411,27 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
     p.seg[1] = make_seg(h_out, H, w->lang_w_ih + H, 2 * H, H);
     p.seg[2] = make_seg(h_in + SH, H, w->lang_w_hh, H, H);
     p.seg[2].gather = parent;
-    p.epi.bias = w->lang_b_ih; p.epi.bias2 = w->lang_b_hh;
-    p.C = sc.gates; p.ldc = 4 * H;
     p.active = active;
-    SUBGC_TRY(launch_gemm(p, sc.gemm_ws, sc.gemm_ws_bytes, st));
-    lstm_cell_kernel<<<pw_blocks, 256, 0, st>>>(sc.gates, c_in + SH, parent, h_out + SH, c_out + SH, S, H, active);
+    SUBGC_TRY(launch_gemm_raw(p, sc.gemm_ws, sc.gemm_ws_bytes, st, &rp));
+    lstm_reduce_cell_kernel<<<pw_blocks, 256, 0, st>>>(rp.part, rp.splits, w->lang_b_ih, w->lang_b_hh, c_in + SH, parent, h_out + SH,
+                                                       c_out + SH, S, H, active);
     SUBGC_LAUNCH_CHECK();
     // logit (AttModel.py:336,340); eval mode: dropout is the identity
     p = GemmProblem();
     p.M = S; p.N = V1; p.nseg = 1;
     p.seg[0] = make_seg(h_out + SH, H, w->logit.w, H, H);
+    p.active = active;
+    if (raw_logits) return launch_gemm_raw(p, sc.gemm_ws, sc.gemm_ws_bytes, st, raw_logits);
     p.epi.bias = w->logit.b;
     p.C = logits; p.ldc = V1;
-    p.active = active;
-    SUBGC_TRY(launch_gemm(p, sc.gemm_ws, sc.gemm_ws_bytes, st));
-    return SUBGC_OK;
+    return launch_gemm(p, sc.gemm_ws, sc.gemm_ws_bytes, st);
 }
 
 static int check_decode_args(const subgc_dims* d, const subgc_weights* w, int S, int len_max, const char* who) {
     SUBGC_CHECK_ARG(d && w, "%s: null dims/weights", who);
     SUBGC_CHECK_ARG(d->rnn > 0 && d->enc > 0 && d->att_hid > 0 && d->vocab1 > 1 && d->seq_length > 0, "%s: bad decoder dims", who);
     SUBGC_CHECK_ARG(S > 0 && len_max > 0 && len_max <= 64, "%s: bad n_rows/len_max (%d, %d)", who, S, len_max);
-    SUBGC_CHECK_ARG((size_t)(2 * d->att_hid + len_max) * 4 <= 48 * 1024, "%s: att_hid too large for the attention kernel", who);
+    SUBGC_CHECK_ARG((size_t)(2 * d->att_hid + 64 + 4 * d->rnn) * 4 <= 48 * 1024, "%s: att_hid / rnn_size too large for the attention kernel", who);
     return SUBGC_OK;
 }
 
@@ -515,7 +596,7 @@ extern "C" int subgc_decode_step(const subgc_dims* d, const subgc_weights* w, in
     float* logits = ws.take<float>((size_t)n_rows * d->vocab1);
     if (!ok || !ws.ok()) { set_error("subgc_decode_step: workspace too small"); return SUBGC_E_WORKSPACE; }
     SUBGC_TRY(launch_step(d, w, n_rows, len_max, rows_per_ctx, reinterpret_cast<const long long*>(it), nullptr, fc, att, p_att, masks, h_in,
-                          c_in, h_out, c_out, logits, att_weights, len_max, sc, nullptr, 0, st));
+                          c_in, h_out, c_out, logits, nullptr, att_weights, len_max, sc, nullptr, 0, st));
     log_softmax_kernel<<<n_rows, 256, 0, st>>>(logits, logprobs, d->vocab1, (size_t)d->vocab1, nullptr);
     SUBGC_LAUNCH_CHECK();
     return SUBGC_OK;
@@ -549,6 +630,10 @@ extern "C" int subgc_decode_sample(const subgc_dims* d, const subgc_weights* w, 
     SUBGC_CUDA(cudaMemsetAsync(seq, 0, (size_t)S * T * 8, st));
     SUBGC_CUDA(cudaMemsetAsync(seq_logprobs, 0, (size_t)S * T * 4, st));
     if (att_weights) SUBGC_CUDA(cudaMemsetAsync(att_weights, 0, (size_t)S * (T + 1) * len_max * 4, st));
+    if ((size_t)V1 * sizeof(float) > 48 * 1024) {
+        SUBGC_CHECK_ARG((size_t)V1 * sizeof(float) <= 200 * 1024, "subgc_decode_sample: vocabulary too large for the selection kernel");
+        SUBGC_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(V1 * sizeof(float))));
+    }
     for (int t = 0; t <= T; ++t) {
         const int* active = (t == 0) ? nullptr : count + (t - 1);
         const int in = t & 1, out = in ^ 1;
@@ -558,16 +643,17 @@ extern "C" int subgc_decode_sample(const subgc_dims* d, const subgc_weights* w, 
             // weights are observable, so the step stops there (and is skipped entirely when they are not requested)
             if (att_weights)
                 SUBGC_TRY(launch_step(d, w, S, len_max, 1, it, nullptr, fc, att, p_att, masks, hbuf[in], cbuf[in], hbuf[out], cbuf[out], logits,
-                                      aw, (T + 1) * len_max, sc, active, 1, st));
+                                      nullptr, aw, (T + 1) * len_max, sc, active, 1, st));
             break;
         }
-        SUBGC_TRY(launch_step(d, w, S, len_max, 1, it, nullptr, fc, att, p_att, masks, hbuf[in], cbuf[in], hbuf[out], cbuf[out], logits, aw,
+        RawPartials rl;
+        SUBGC_TRY(launch_step(d, w, S, len_max, 1, it, nullptr, fc, att, p_att, masks, hbuf[in], cbuf[in], hbuf[out], cbuf[out], logits, &rl, aw,
                               (T + 1) * len_max, sc, active, 0, st));
         SelectArgs a;
-        a.logits = logits; a.V1 = V1; a.T = T; a.t = t; a.S = S; a.mode = mode; a.temp = temp; a.top_k = top_k; a.seed = seed;
+        a.logits = rl.part; a.splits = rl.splits; a.bias = w->logit.b; a.V1 = V1; a.T = T; a.t = t; a.S = S; a.mode = mode; a.temp = temp; a.top_k = top_k; a.seed = seed;
         a.offset = offset; a.uniforms = uniforms; a.it = it; a.unfinished = unfinished; a.seq = reinterpret_cast<long long*>(seq);
         a.seq_lp = seq_logprobs; a.count = count; a.active = active;
-        select_kernel<<<S, 256, 0, st>>>(a);
+        select_kernel<<<S, kSelectThreads, (size_t)V1 * sizeof(float), st>>>(a);
         SUBGC_LAUNCH_CHECK();
     }
     steps_done_kernel<<<1, 1, 0, st>>>(count, T, steps_done);
@@ -604,7 +690,7 @@ extern "C" int subgc_decode_teacher(const subgc_dims* d, const subgc_weights* w,
     for (int i = 0; i < n_steps; ++i) {
         const int in = i & 1, out = in ^ 1;
         SUBGC_TRY(launch_step(d, w, S, len_max, 1, tok_cols + (size_t)i * S, nullptr, fc, att, p_att, masks, hbuf[in], cbuf[in], hbuf[out],
-                              cbuf[out], logits, nullptr, 0, sc, flags + i, 0, st));
+                              cbuf[out], logits, nullptr, nullptr, 0, sc, flags + i, 0, st));
         log_softmax_kernel<<<S, 256, 0, st>>>(logits, outputs + (size_t)i * V1, V1, (size_t)n_steps * V1, flags + i);
         SUBGC_LAUNCH_CHECK();
     }
@@ -663,8 +749,8 @@ extern "C" int subgc_decode_beam(const subgc_dims* d, const subgc_weights* w, in
     SUBGC_CUDA(cudaMemsetAsync(done_p, 0, (size_t)S * 8, st));
     SUBGC_CUDA(cudaMemsetAsync(done_unaug_p, 0, (size_t)S * 8, st));
     // <bos> step on b identical rows per sub-graph (AttModel.py:216-227)
-    SUBGC_TRY(launch_step(d, w, S, len_max, b, it, nullptr, fc, att, p_att, masks, hbuf[0], cbuf[0], hbuf[1], cbuf[1], logits, nullptr, 0, sc,
-                          nullptr, 0, st));
+    SUBGC_TRY(launch_step(d, w, S, len_max, b, it, nullptr, fc, att, p_att, masks, hbuf[0], cbuf[0], hbuf[1], cbuf[1], logits, nullptr, nullptr,
+                          0, sc, nullptr, 0, st));
     for (int t = 0; t < T; ++t) {
         BeamArgs a;
         a.logits = logits; a.V1 = V1; a.T = T; a.t = t; a.b = b; a.length_penalty = length_penalty; a.lp_alpha = lp_alpha;
@@ -677,8 +763,8 @@ extern "C" int subgc_decode_beam(const subgc_dims* d, const subgc_weights* w, in
         SUBGC_LAUNCH_CHECK();
         if (t == T - 1) break;  // the reference's final get_logprobs_state result is never read (CaptionModel.py:170-171)
         const int in = (t + 1) & 1, out = in ^ 1;
-        SUBGC_TRY(launch_step(d, w, S, len_max, b, it, parent, fc, att, p_att, masks, hbuf[in], cbuf[in], hbuf[out], cbuf[out], logits, nullptr, 0,
-                              sc, nullptr, 0, st));
+        SUBGC_TRY(launch_step(d, w, S, len_max, b, it, parent, fc, att, p_att, masks, hbuf[in], cbuf[in], hbuf[out], cbuf[out], logits, nullptr,
+                              nullptr, 0, sc, nullptr, 0, st));
     }
     return SUBGC_OK;
 }

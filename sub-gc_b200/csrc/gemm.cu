@@ -331,6 +331,16 @@ void launch_splitk_reduce(const GemmProblem& p, const float* part, int splits, c
     splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(p, part, splits);
 }
 
+int launch_gemm_raw(const GemmProblem& p, void* ws, size_t ws_bytes, cudaStream_t stream, RawPartials* raw) {
+    SUBGC_CHECK_ARG(p.M > 0 && raw != nullptr, "gemm(raw): bad arguments");
+    if (tc_eligible(p)) return launch_gemm_tc(p, ws, ws_bytes, stream, raw);
+    int splits = 1;
+    SUBGC_TRY(launch_gemm_ex(p, static_cast<float*>(ws), ws_bytes / sizeof(float), &splits, nullptr, 0, stream));
+    raw->part = static_cast<const float*>(ws);
+    raw->splits = splits;
+    return SUBGC_OK;
+}
+
 int launch_gemm(const GemmProblem& p, void* ws, size_t ws_bytes, cudaStream_t stream) {
     if (p.M > 0 && tc_eligible(p)) {
         SUBGC_CHECK_ARG(p.N > 0 && p.C != nullptr && p.ldc >= p.N, "gemm: bad output");

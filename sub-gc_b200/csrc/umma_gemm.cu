@@ -39,17 +39,34 @@ constexpr int TC_STAGE_BYTES = 2 * TC_W_BYTES + 2 * TC_X_BYTES;   // Whi | Wlo |
 constexpr int TC_TX_BYTES = TC_W_BYTES + 2 * TC_X_BYTES;          // bytes TMA lands per stage
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int TC_MAX_SEG = 4;
+constexpr bool TC_L2_PREFETCH = false;  // measured on B200: no gain in steady state (the loop is shared-memory-bandwidth
+                                        // bound) and the burst of prefetches delays the first demand tile by ~3 us
+constexpr int TC_PF_KB = 8;       // weights are requested into L2 in chunks of 8 k-blocks (128 columns = 512 contiguous bytes per row),
+                                  // two chunks ahead of the smem ring: long row runs for the DRAM pages, latency cover without smem
+constexpr int TC_MAX_CHAIN = 32;  // k-blocks (512 columns) accumulated in TMEM before an fp32 round-to-nearest combine
 
 struct TcParams {
     CUtensorMap tm_xhi, tm_xlo;
     CUtensorMap tm_w[TC_MAX_SEG];
+    CUtensorMap tm_wpf[TC_MAX_SEG];  // same tensors, box 128 columns x 256 rows: L2 prefetch of 512-byte row runs (DRAM page locality)
     int seg_kb_end[TC_MAX_SEG];  // cumulative k-block count at the end of each segment
     int nseg;
     int M, N;
     int kb_total, kb_per_split;
     float* part;                 // [splits][M][N]
     const int* active;
+    int raw_hi;                  // 1 (default): the raw fp32 weight tile is the "hi" operand -- the tensor core reads only the tf32
+                                 // bits, i.e. truncates (measured: same error as an explicit split) -- and only lo = w - trunc(w) is
+                                 // written; 0 (SUBGC_TC_REWRITE_HI=1): hi = rn_tf32(w) is rewritten in place as well
+    long long* trace;            // debug (SUBGC_TC_TRACE=1): per-role clock64 stamps of CTA (0,0,0); nullptr in normal operation
 };
+constexpr int TC_TRACE_SLOTS = 64;  // k-blocks traced per role
+
+#define TC_STAMP(role, i)                                                                                      \
+    do {                                                                                                       \
+        if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (i) < TC_TRACE_SLOTS) \
+            p.trace[(role) * TC_TRACE_SLOTS + (i)] = clock64();                                                \
+    } while (0)
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -78,6 +95,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
                  "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
                  : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 __device__ __forceinline__ uint32_t to_tf32(float v) {
     uint32_t r;
@@ -132,33 +156,56 @@ __global__ void __launch_bounds__(TC_THREADS, 1) umma_gemm_kernel(const __grid_c
         mbar_init(bar_base + 96, 1);               // accumulator ready
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {  // TMEM: 256 fp32 accumulator columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
+    if (warp == 0) {  // TMEM: two 256-column fp32 accumulators (main hi*hi chain | cross terms), i.e. all 512 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = *tmem_slot;
+    if (threadIdx.x == 0) TC_STAMP(0, 0);
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            int seg = 0;
+            prefetch_tensormap(&p.tm_xhi);
+            prefetch_tensormap(&p.tm_xlo);
+            for (int sgi = 0; sgi < p.nseg; ++sgi) prefetch_tensormap(&p.tm_w[sgi]);
+            // weight k-block -> (segment, column) lookup; `pseg` trails the L2 prefetch cursor, `seg` the smem ring
+            int seg = 0, pseg = 0;
             while (seg < p.nseg - 1 && kb_begin >= p.seg_kb_end[seg]) ++seg;
+            pseg = seg;
+            auto prefetch_chunk = [&](int kb0) {  // k-blocks [kb0, kb0 + TC_PF_KB), split at segment boundaries
+                int kb = kb0;
+                const int kend = min(kb0 + TC_PF_KB, kb_end);
+                while (kb < kend) {
+                    while (pseg < p.nseg - 1 && kb >= p.seg_kb_end[pseg]) ++pseg;
+                    const int k0 = pseg == 0 ? 0 : p.seg_kb_end[pseg - 1];
+                    tma_prefetch_l2_2d(&p.tm_wpf[pseg], (kb - k0) * TC_BK, n0);
+                    kb = min(kend, p.seg_kb_end[pseg]);
+                }
+            };
+            if (TC_L2_PREFETCH) {
+                prefetch_chunk(kb_begin);
+                prefetch_chunk(kb_begin + TC_PF_KB);
+            }
             for (int i = 0; i < nkb; ++i) {
                 const int kb = kb_begin + i;
+                if (TC_L2_PREFETCH && (i % TC_PF_KB) == 0 && i + 2 * TC_PF_KB < nkb) prefetch_chunk(kb + 2 * TC_PF_KB);
                 while (seg < p.nseg - 1 && kb >= p.seg_kb_end[seg]) ++seg;
                 const int seg_kb0 = seg == 0 ? 0 : p.seg_kb_end[seg - 1];
                 const int s = i % TC_STAGES;
                 const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
                 mbar_wait(bar_base + 64 + 8 * s, ph ^ 1u);
+                TC_STAMP(1, i);
                 const uint32_t st = base + s * TC_STAGE_BYTES;
                 const uint32_t full = bar_base + 8 * s;
                 mbar_arrive_expect_tx(full, TC_TX_BYTES);
                 tma_load_2d(st, &p.tm_w[seg], full, (kb - seg_kb0) * TC_BK, n0);
                 tma_load_2d(st + 2 * TC_W_BYTES, &p.tm_xhi, full, kb * TC_BK, m0);
                 tma_load_2d(st + 2 * TC_W_BYTES + TC_X_BYTES, &p.tm_xlo, full, kb * TC_BK, m0);
+                TC_STAMP(2, i);
             }
         }
     } else if (warp == 1) {
@@ -171,6 +218,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) umma_gemm_kernel(const __grid_c
             mbar_wait(bar_base + 32 + 8 * s, ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
+                TC_STAMP(5, i);
                 const uint32_t st = base + s * TC_STAGE_BYTES;
 #pragma unroll
                 for (int ks = 0; ks < TC_BK / 8; ++ks) {
@@ -178,12 +226,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) umma_gemm_kernel(const __grid_c
                     const uint64_t wlo = umma_desc_sw64(st + TC_W_BYTES + ks * 32);
                     const uint64_t xhi = umma_desc_sw64(st + 2 * TC_W_BYTES + ks * 32);
                     const uint64_t xlo = umma_desc_sw64(st + 2 * TC_W_BYTES + TC_X_BYTES + ks * 32);
-                    umma_tf32(tmem_d, xhi, whi, idesc, (i > 0 || ks > 0) ? 1u : 0u);
-                    umma_tf32(tmem_d, xlo, whi, idesc, 1u);
-                    umma_tf32(tmem_d, xhi, wlo, idesc, 1u);
+                    // The tensor core truncates its fp32 accumulator on every add, a bias that grows with the chain length.
+                    // The two cross terms (2^-11 of the main term) therefore get their own accumulator: the main chain
+                    // sees one add per K-step instead of three, and the cross chain's truncation is 2^-11 smaller.
+                    const uint32_t acc = (i > 0 || ks > 0) ? 1u : 0u;
+                    umma_tf32(tmem_d, xhi, whi, idesc, acc);
+                    umma_tf32(tmem_d + TC_BN, xlo, whi, idesc, acc);
+                    umma_tf32(tmem_d + TC_BN, xhi, wlo, idesc, 1u);
                 }
                 umma_commit(bar_base + 64 + 8 * s);              // stage free once these MMAs have read it
                 if (i == nkb - 1) umma_commit(bar_base + 96);    // accumulator complete
+                TC_STAMP(6, i);
             }
             __syncwarp();
         }
@@ -194,61 +247,96 @@ __global__ void __launch_bounds__(TC_THREADS, 1) umma_gemm_kernel(const __grid_c
             const int s = i % TC_STAGES;
             const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
             mbar_wait(bar_base + 8 * s, ph);
+            if (t == 0) TC_STAMP(3, i);
             float4* whi = reinterpret_cast<float4*>(gbase + s * TC_STAGE_BYTES);
             float4* wlo = reinterpret_cast<float4*>(gbase + s * TC_STAGE_BYTES + TC_W_BYTES);
 #pragma unroll
             for (int j = 0; j < TC_W_BYTES / 16 / 128; ++j) {
                 const int idx = t + 128 * j;
-                float4 v = whi[idx];
+                const float4 v = whi[idx];
+                // hi = v rounded to tf32 (integer round-half-up on the 13 dropped bits: 2 ALU ops, finite inputs), lo = v - hi is
+                // exact in fp32; the tensor core reads only the tf32 bits of lo (a 2^-22 relative residual)
                 float4 h, l;
-                h.x = __uint_as_float(to_tf32(v.x)); h.y = __uint_as_float(to_tf32(v.y));
-                h.z = __uint_as_float(to_tf32(v.z)); h.w = __uint_as_float(to_tf32(v.w));
-                l.x = __uint_as_float(to_tf32(v.x - h.x)); l.y = __uint_as_float(to_tf32(v.y - h.y));
-                l.z = __uint_as_float(to_tf32(v.z - h.z)); l.w = __uint_as_float(to_tf32(v.w - h.w));
-                whi[idx] = h;
+                h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xffffe000u);
+                h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xffffe000u);
+                h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xffffe000u);
+                h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xffffe000u);
+                l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+                if (p.raw_hi) {
+                    l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+                    l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+                    l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+                    l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+                } else {
+                    whi[idx] = h;
+                }
                 wlo[idx] = l;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to tcgen05.mma
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_base + 32 + 8 * s);
+            if (t == 0) TC_STAMP(4, i);
         }
         // epilogue: TMEM lanes of this warp = 32 * (warp % 4)
         mbar_wait(bar_base + 96, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (t == 0) TC_STAMP(0, 1);
         const int q = warp & 3;
-        float* scratch = reinterpret_cast<float*>(gbase) + (warp - 2) * (32 * 33);  // stage memory is idle now
-        float* out = p.part + (size_t)blockIdx.z * p.M * p.N;
+        const int row = m0 + q * 32 + lane;            // TMEM lane == output row
+        float* out = p.part + (size_t)blockIdx.z * p.M * p.N + (size_t)row * p.N;
+        const bool vec = ((p.N & 3) == 0);
+#define TC_TMEM_LD32(R, ADDR)                                                                                                             \
+    asm volatile(                                                                                                                        \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, " \
+        "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                                                            \
+        : "=r"(R[0]), "=r"(R[1]), "=r"(R[2]), "=r"(R[3]), "=r"(R[4]), "=r"(R[5]), "=r"(R[6]), "=r"(R[7]), "=r"(R[8]), "=r"(R[9]),        \
+          "=r"(R[10]), "=r"(R[11]), "=r"(R[12]), "=r"(R[13]), "=r"(R[14]), "=r"(R[15]), "=r"(R[16]), "=r"(R[17]), "=r"(R[18]),           \
+          "=r"(R[19]), "=r"(R[20]), "=r"(R[21]), "=r"(R[22]), "=r"(R[23]), "=r"(R[24]), "=r"(R[25]), "=r"(R[26]), "=r"(R[27]),           \
+          "=r"(R[28]), "=r"(R[29]), "=r"(R[30]), "=r"(R[31])                                                                             \
+        : "r"(ADDR))
+        const uint32_t tlane = tmem_d + ((uint32_t)(q * 32) << 16);
+        const int nchunks = min(TC_BN / 32, (p.N - n0 + 31) / 32);
+        uint32_t ra[32], rb[32], na[32], nb[32];
+        TC_TMEM_LD32(ra, tlane);
+        TC_TMEM_LD32(rb, tlane + TC_BN);
 #pragma unroll 1
-        for (int c = 0; c < TC_BN / 32; ++c) {
-            if (n0 + c * 32 >= p.N) break;
-            uint32_t r[32];
-            const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
-                "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-                  "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-                  "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-                  "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr));
+        for (int c = 0; c < nchunks; ++c) {
+            const int col0 = n0 + c * 32;
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = __uint_as_float(r[j]);
-            __syncwarp();
-            const int col = n0 + c * 32 + lane;
-#pragma unroll 4
-            for (int rr = 0; rr < 32; ++rr) {
-                const int row = m0 + q * 32 + rr;
-                if (row < p.M && col < p.N) out[(size_t)row * p.N + col] = scratch[rr * 33 + lane];
+            if (c + 1 < nchunks) {  // next chunk's TMEM reads overlap this chunk's global stores
+                TC_TMEM_LD32(na, tlane + (uint32_t)((c + 1) * 32));
+                TC_TMEM_LD32(nb, tlane + TC_BN + (uint32_t)((c + 1) * 32));
             }
-            __syncwarp();
+            if (row < p.M) {
+                if (vec && col0 + 32 <= p.N) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 v;
+                        v.x = __uint_as_float(ra[j]) + __uint_as_float(rb[j]);
+                        v.y = __uint_as_float(ra[j + 1]) + __uint_as_float(rb[j + 1]);
+                        v.z = __uint_as_float(ra[j + 2]) + __uint_as_float(rb[j + 2]);
+                        v.w = __uint_as_float(ra[j + 3]) + __uint_as_float(rb[j + 3]);
+                        *reinterpret_cast<float4*>(out + col0 + j) = v;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < p.N) out[col0 + j] = __uint_as_float(ra[j]) + __uint_as_float(rb[j]);
+                }
+            }
+            if (c + 1 < nchunks) {
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { ra[j] = na[j]; rb[j] = nb[j]; }
+            }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (t == 0) TC_STAMP(0, 2);
     }
     __syncthreads();
     if (warp == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(256) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512) : "memory");
     }
 }
 
@@ -308,30 +396,34 @@ static EncodeTiledFn encode_fn() {
 }
 
 // 2-D fp32 tensor map: inner dim `cols` (contiguous), outer dim `rows` with `ld` floats between rows; box 16 x box_rows
-static bool make_map(CUtensorMap* out, const float* base, int rows, int cols, long long ld, int box_rows) {
+static bool make_map(CUtensorMap* out, const float* base, int rows, int cols, long long ld, int box_rows, int box_cols = TC_BK) {
     struct Key {
-        const void* base; int rows, cols; long long ld; int box;
-        bool operator==(const Key& o) const { return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box == o.box; }
+        const void* base; int rows, cols; long long ld; int box, boxc;
+        bool operator==(const Key& o) const {
+            return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box == o.box && boxc == o.boxc;
+        }
     };
     struct Hash {
         size_t operator()(const Key& k) const {
             size_t h = reinterpret_cast<size_t>(k.base);
-            h = h * 1000003u ^ (size_t)k.rows; h = h * 1000003u ^ (size_t)k.cols; h = h * 1000003u ^ (size_t)k.ld; h = h * 1000003u ^ (size_t)k.box;
+            h = h * 1000003u ^ (size_t)k.rows; h = h * 1000003u ^ (size_t)k.cols; h = h * 1000003u ^ (size_t)k.ld; h = h * 1000003u ^ (size_t)k.box; h = h * 1000003u ^ (size_t)k.boxc;
             return h;
         }
     };
     static thread_local std::unordered_map<Key, CUtensorMap, Hash> cache;  // encoding is pure: same key -> same descriptor
-    Key key{base, rows, cols, ld, box_rows};
+    Key key{base, rows, cols, ld, box_rows, box_cols};
     auto it = cache.find(key);
     if (it != cache.end()) { *out = it->second; return true; }
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    const bool tile = box_cols == TC_BK;  // smem tiles are 64-byte swizzled; the wide box is only ever used for L2 prefetch
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    tile ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    tile ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return false;
     if (cache.size() > 512) cache.clear();
     cache.emplace(key, *out);
@@ -374,6 +466,7 @@ static TcPlan tc_plan(int M, int N, const int* segK, int nseg) {
     if (splits > 32) splits = 32;
     if (splits < 1) splits = 1;
     pl.kb_per_split = (pl.kb_total + splits - 1) / splits;
+    if (pl.kb_per_split > TC_MAX_CHAIN) pl.kb_per_split = TC_MAX_CHAIN;  // bound the truncating accumulation chain
     pl.splits = (pl.kb_total + pl.kb_per_split - 1) / pl.kb_per_split;
     pl.Mpad = pl.m_tiles * TC_BM;
     pl.Kpad = pl.kb_total * TC_BK;
@@ -386,13 +479,16 @@ size_t tc_workspace_bytes(int M, int N, int Ktotal) {
     int splits = kNumSMs / (m_tiles * n_tiles);
     if (splits > 32) splits = 32;
     if (splits < 1) splits = 1;
+    const int by_chain = (Ktotal / TC_BK + TC_MAX_SEG + TC_MAX_CHAIN - 1) / TC_MAX_CHAIN + 1;
+    if (splits < by_chain) splits = by_chain;
     const size_t Kpad = (size_t)Ktotal + TC_MAX_SEG * TC_BK;
     return 2 * align_up((size_t)m_tiles * TC_BM * Kpad * 4, 256) + align_up((size_t)splits * M * N * 4, 256) + 512;
 }
 
 void launch_splitk_reduce(const GemmProblem& p, const float* part, int splits, cudaStream_t stream);
 
-int launch_gemm_tc(const GemmProblem& p, void* ws_, size_t ws_bytes, cudaStream_t stream) {
+// raw != nullptr: leave the split-K partials [splits][M][N] (no epilogue) for a fused consumer and report where they are
+int launch_gemm_tc(const GemmProblem& p, void* ws_, size_t ws_bytes, cudaStream_t stream, RawPartials* raw) {
     int segK[TC_MAX_SEG];
     for (int s = 0; s < p.nseg; ++s) segK[s] = p.seg[s].K;
     const TcPlan pl = tc_plan(p.M, p.N, segK, p.nseg);
@@ -419,8 +515,12 @@ int launch_gemm_tc(const GemmProblem& p, void* ws_, size_t ws_bytes, cudaStream_
             set_error("gemm(tc): cuTensorMapEncodeTiled failed for weight segment %d", s);
             return SUBGC_E_CUDA;
         }
+        if (!make_map(&tp.tm_wpf[s], p.seg[s].W, p.N, p.seg[s].K, p.seg[s].ldw, TC_BN, TC_PF_KB * TC_BK)) {
+            set_error("gemm(tc): cuTensorMapEncodeTiled failed for the prefetch map of weight segment %d", s);
+            return SUBGC_E_CUDA;
+        }
     }
-    for (int s = p.nseg; s < TC_MAX_SEG; ++s) { tp.seg_kb_end[s] = kb; tp.tm_w[s] = tp.tm_w[0]; }
+    for (int s = p.nseg; s < TC_MAX_SEG; ++s) { tp.seg_kb_end[s] = kb; tp.tm_w[s] = tp.tm_w[0]; tp.tm_wpf[s] = tp.tm_wpf[0]; }
     pa.seg_col0[p.nseg] = col;
     if (!make_map(&tp.tm_xhi, xhi, pl.Mpad, pl.Kpad, pl.Kpad, TC_BM) || !make_map(&tp.tm_xlo, xlo, pl.Mpad, pl.Kpad, pl.Kpad, TC_BM)) {
         set_error("gemm(tc): cuTensorMapEncodeTiled failed for the activation tiles");
@@ -438,8 +538,38 @@ int launch_gemm_tc(const GemmProblem& p, void* ws_, size_t ws_bytes, cudaStream_
         attr_set = true;
     }
     dim3 grid(pl.n_tiles, pl.m_tiles, pl.splits);
+    static const bool trace_on = getenv("SUBGC_TC_TRACE") != nullptr;  // debugging aid only: allocates and synchronises
+    static long long* trace_buf = nullptr;
+    static const bool raw_hi = getenv("SUBGC_TC_REWRITE_HI") == nullptr;
+    tp.raw_hi = raw_hi ? 1 : 0;
+    tp.trace = nullptr;
+    if (trace_on) {
+        if (!trace_buf) cudaMalloc(&trace_buf, 8 * TC_TRACE_SLOTS * sizeof(long long));
+        cudaMemsetAsync(trace_buf, 0, 8 * TC_TRACE_SLOTS * sizeof(long long), stream);
+        tp.trace = trace_buf;
+    }
     umma_gemm_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(tp);
     SUBGC_LAUNCH_CHECK();
+    if (trace_on) {
+        static int dumps = 0;
+        long long h[8 * TC_TRACE_SLOTS];
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
+        if (dumps++ < 40) {
+            const long long t0 = h[0];
+            fprintf(stderr, "[tc-trace] M=%d N=%d kb=%d per_split=%d grid=(%d,%d,%d): acc_ready=%lld epi_done=%lld\n", p.M, p.N, pl.kb_total,
+                    pl.kb_per_split, pl.n_tiles, pl.m_tiles, pl.splits, h[1] - t0, h[2] - t0);
+            for (int i = 0; i < pl.kb_per_split && i < TC_TRACE_SLOTS; ++i)
+                fprintf(stderr, "[tc-trace]  kb %2d: prod_wait %6lld prod_issued %6lld | xf_start %6lld xf_done %6lld | mma_start %6lld mma_issued %6lld\n", i,
+                        h[1 * TC_TRACE_SLOTS + i] - t0, h[2 * TC_TRACE_SLOTS + i] - t0, h[3 * TC_TRACE_SLOTS + i] - t0, h[4 * TC_TRACE_SLOTS + i] - t0,
+                        h[5 * TC_TRACE_SLOTS + i] - t0, h[6 * TC_TRACE_SLOTS + i] - t0);
+        }
+    }
+    if (raw) {
+        raw->part = part;
+        raw->splits = pl.splits;
+        return SUBGC_OK;
+    }
     launch_splitk_reduce(p, part, pl.splits, stream);
     SUBGC_LAUNCH_CHECK();
     return SUBGC_OK;

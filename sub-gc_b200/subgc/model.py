@@ -15,6 +15,7 @@ of every returned row is in `model.last_image_of_row`.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 import torch.nn as nn
@@ -61,6 +62,39 @@ class Workspace:
         if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
             self.buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
         return self.buf
+
+
+class _DecodePlan:
+    """Static buffers + captured CUDA graph of one decode shape.  The decode loops issue ~250 dependent launches;
+    replaying them as a graph removes the per-launch CPU cost and most of the inter-kernel gaps.  The C ABI never
+    allocates or synchronises, so a call is capturable as is; every pointer it receives lives in this object."""
+
+    def __init__(self, dev, d, n_rows, len_max):
+        self.fc = torch.empty(n_rows, d.rnn, device=dev)
+        self.g_fc = torch.empty(n_rows, 2 * d.gcn, device=dev)
+        self.att = torch.empty(n_rows, len_max, d.rnn, device=dev)
+        self.p_att = torch.empty(n_rows, len_max, d.att_hid, device=dev)
+        self.masks = torch.empty(n_rows, len_max, device=dev)
+        self.graph = None
+        self.calls = 0
+        self.out = {}
+
+    def run(self, launch, use_graph):
+        """launch() enqueues the C call on the current stream.  First call: eager (also sets kernel attributes);
+        second call: capture; afterwards: replay."""
+        self.calls += 1
+        if not use_graph:
+            launch()
+        elif self.graph is not None:
+            self.graph.replay()
+        elif self.calls == 1:
+            launch()
+        else:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                launch()
+            self.graph = g
+            g.replay()
 
 
 class TopDownModel(nn.Module):
@@ -124,6 +158,8 @@ class TopDownModel(nn.Module):
         self._ws = Workspace()
         self._wcache = None
         self.stage_events = None  # set to [] to collect (name, start_event, end_event) per stage (bench / profiling)
+        self.use_graphs = os.environ.get("SUBGC_NO_GRAPH", "0") != "1"
+        self._plans = {}
         self._cdims = _lib.Dims(d.v1, d.enc, d.rnn, d.att_hid, d.fc_feat, d.att_feat, d.gcn, d.low_rank, d.embed, d.obj_classes,
                                 d.pred_classes, d.gcn_layers, d.gcn_residual, d.pred_emb_type, d.seq_length, d.obj_num, d.rel_num)
 
@@ -172,6 +208,7 @@ class TopDownModel(nn.Module):
         w.lang_w_ih = g("core.lang_lstm.weight_ih"); w.lang_w_hh = g("core.lang_lstm.weight_hh")
         w.lang_b_ih = g("core.lang_lstm.bias_ih"); w.lang_b_hh = g("core.lang_lstm.bias_hh")
         self._wcache = (key, w)
+        self._plans.clear()  # captured graphs hold the old parameter addresses
         return w
 
     @staticmethod
@@ -246,21 +283,29 @@ class TopDownModel(nn.Module):
                                    ptr(score), ptr(sub_len), ptr(loss), ptr(ws), ws.numel(), self._stream()), "subgc_sgpn_forward")
         return lay, n_sub, read_out, score, sub_len, loss
 
-    def _prepare(self, lay, n_rows, len_max, sel, x_obj, gpn_obj_ind, att_masks, read_out):
+    def _plan(self, dev, n_rows, len_max, kind):
+        """Decode plan (static buffers + graph) for a shape; a handful of shapes are kept."""
+        key = (dev.index, n_rows, len_max, kind)
+        plan = self._plans.get(key)
+        if plan is None:
+            if len(self._plans) >= 8:
+                self._plans.pop(next(iter(self._plans)))
+            plan = self._plans[key] = _DecodePlan(dev, self.dims, n_rows, len_max)
+        return plan
+
+    def _prepare(self, lay, n_rows, len_max, sel, x_obj, gpn_obj_ind, att_masks, read_out, plan=None):
         dev = x_obj.device
         L, d, w, cd = lib(), self.dims, self._weights(), self._cdims
-        g_fc = torch.empty(n_rows, 2 * d.gcn, device=dev)
-        fc = torch.empty(n_rows, d.rnn, device=dev)
-        att = torch.empty(n_rows, len_max, d.rnn, device=dev)
-        p_att = torch.empty(n_rows, len_max, d.att_hid, device=dev)
-        masks = torch.empty(n_rows, len_max, device=dev)
+        if plan is None:
+            plan = _DecodePlan(dev, d, n_rows, len_max)
+        g_fc, fc, att, p_att, masks = plan.g_fc, plan.fc, plan.att, plan.p_att, plan.masks
         ws = self._ws.get(L.subgc_prepare_workspace_bytes(C.byref(cd), n_rows, len_max), dev)
         check(L.subgc_prepare_forward(C.byref(cd), C.byref(w), C.byref(lay), n_rows, len_max, ptr(sel), ptr(x_obj), ptr(gpn_obj_ind),
                                       ptr(att_masks), ptr(read_out), ptr(g_fc), ptr(fc), ptr(att), ptr(p_att), ptr(masks), ptr(ws),
                                       ws.numel(), self._stream()), "subgc_prepare_forward")
         return g_fc, fc, att, p_att, masks
 
-    def _front(self, att_feats, att_masks, obj_dist, rel_ind, pred_dist, gpn_obj_ind):
+    def _front(self, att_feats, att_masks, obj_dist, rel_ind, pred_dist, gpn_obj_ind, plan_kind=None):
         """Encoder + sGPN + NMS + feature preparation for inference.  One host read-back (kept count, clip length) —
         the reference synchronises at the same two places (NMS on the host, clip_att's .max())."""
         dev = self._check_device(att_feats, att_masks, obj_dist, rel_ind, gpn_obj_ind)
@@ -286,7 +331,8 @@ class TopDownModel(nn.Module):
         sel = sel[:n_rows]
         keep = keep[:n_rows]
         self._mark()
-        prep = self._prepare(lay, n_rows, len_max, sel, x_obj, gpn_obj_ind, att_masks, read_out)
+        self._cur_plan = self._plan(dev, n_rows, len_max, plan_kind) if plan_kind is not None else None
+        prep = self._prepare(lay, n_rows, len_max, sel, x_obj, gpn_obj_ind, att_masks, read_out, self._cur_plan)
         self._mark("prepare")
         sel_l = sel.long()
         self.last_gpn_loss = loss[0]
@@ -310,34 +356,53 @@ class TopDownModel(nn.Module):
         return_att = opt.get("return_att", 0) == 1
         if not opt.get("sample_max", 1) and not self.topk_sampling and beam_size == 1:
             raise NotImplementedError("sample_max=0 leaves `it` undefined in the reference (AttModel.py:304-307)")
+        uniforms = opt.get("topk_uniforms", None)
+        kind = ("beam", beam_size, opt.get("length_penalty", ""), int(opt.get("decoding_constraint", 0))) if beam_size > 1 else \
+            ("sample", bool(self.topk_sampling), float(self.topk_temp), int(self.the_k), return_att)
         (g_fc, fc, att, p_att, masks), sub_score, keep_ind, n_rows, len_max = self._front(att_feats, att_masks, obj_dist, rel_ind,
-                                                                                          pred_dist, gpn_obj_ind)
+                                                                                          pred_dist, gpn_obj_ind, plan_kind=kind)
+        plan = self._cur_plan
         if beam_size > 1:
-            seq, lps = self._beam(fc, att, p_att, masks, n_rows, len_max, opt)
+            seq, lps = self._beam(fc, att, p_att, masks, n_rows, len_max, opt, plan)
             return seq, lps, sub_score, keep_ind
         dev = fc.device
         L, w, cd, T = lib(), self._weights(), self._cdims, self.seq_length
-        seq = torch.empty(n_rows, T, dtype=torch.int64, device=dev)
-        lps = torch.empty(n_rows, T, device=dev)
-        attw = torch.empty(n_rows, T + 1, len_max, device=dev) if return_att else None
-        steps = torch.empty(1, dtype=torch.int32, device=dev)
-        ws = self._ws.get(L.subgc_decode_workspace_bytes(C.byref(cd), n_rows, len_max), dev)
-        uniforms = opt.get("topk_uniforms", None)
-        if uniforms is not None:
-            uniforms = self._f32(uniforms.to(dev))
-            assert uniforms.shape == (T, n_rows), "topk_uniforms must be [seq_length, rows]"
-        seed = int(opt.get("seed", torch.initial_seed())) & (2 ** 64 - 1)
-        offset = int(opt.get("seed_offset", 0))
-        check(L.subgc_decode_sample(C.byref(cd), C.byref(w), n_rows, len_max, 1 if self.topk_sampling else 0, float(self.topk_temp),
-                                    int(self.the_k), seed, offset, ptr(uniforms), ptr(fc), ptr(att), ptr(p_att), ptr(masks), ptr(seq),
-                                    ptr(lps), ptr(attw), ptr(steps), ptr(ws), ws.numel(), self._stream()), "subgc_decode_sample")
+        o = plan.out
+        if not o:
+            o["seq"] = torch.empty(n_rows, T, dtype=torch.int64, device=dev)
+            o["lps"] = torch.empty(n_rows, T, device=dev)
+            o["attw"] = torch.empty(n_rows, T + 1, len_max, device=dev) if return_att else None
+            o["steps"] = torch.empty(1, dtype=torch.int32, device=dev)
+            o["uniforms"] = torch.empty(T, n_rows, device=dev) if self.topk_sampling else None
+            o["ws"] = torch.empty(L.subgc_decode_workspace_bytes(C.byref(cd), n_rows, len_max) + 256, dtype=torch.uint8, device=dev)
+        if self.topk_sampling:
+            # uniforms come from torch's generator (torch.manual_seed / opt['seed'] control them); the kernel maps them to
+            # tokens by inverse CDF over the k kept candidates.  (The C ABI also has its own Philox stream: uniforms = NULL.)
+            if uniforms is not None:
+                assert tuple(uniforms.shape) == (T, n_rows), "topk_uniforms must be [seq_length, rows]"
+                o["uniforms"].copy_(uniforms.to(dev, dtype=torch.float32))
+            elif "seed" in opt:
+                gen = torch.Generator(device=dev)
+                gen.manual_seed(int(opt["seed"]))
+                o["uniforms"].copy_(torch.rand(T, n_rows, device=dev, generator=gen))
+            else:
+                o["uniforms"].uniform_()
+        st_args = (C.byref(cd), C.byref(w), n_rows, len_max, 1 if self.topk_sampling else 0, float(self.topk_temp), int(self.the_k), 0, 0,
+                   ptr(o["uniforms"]), ptr(fc), ptr(att), ptr(p_att), ptr(masks), ptr(o["seq"]), ptr(o["lps"]), ptr(o["attw"]),
+                   ptr(o["steps"]), ptr(o["ws"]), o["ws"].numel())
+
+        def launch():
+            check(L.subgc_decode_sample(*st_args, self._stream()), "subgc_decode_sample")
+
+        plan.run(launch, self.use_graphs)
         self._mark("decode")
-        self.last_steps = steps
+        self.last_steps = o["steps"]
+        seq, lps = o["seq"].clone(), o["lps"].clone()
         if return_att:
-            return seq, lps, sub_score, keep_ind, attw[:, :int(steps.item())]
+            return seq, lps, sub_score, keep_ind, o["attw"][:, :int(o["steps"].item())].clone()
         return seq, lps, sub_score, keep_ind
 
-    def _beam(self, fc, att, p_att, masks, n_sub, len_max, opt):
+    def _beam(self, fc, att, p_att, masks, n_sub, len_max, opt, plan):
         """Batched replacement of the per-sub-graph beam loop (reference models/AttModel.py:208-234)."""
         if opt.get("group_size", 1) != 1:
             raise NotImplementedError("diverse beam search (group_size > 1) is not part of the Sub-GC configurations")
@@ -349,18 +414,25 @@ class TopDownModel(nn.Module):
         if pen:
             name, a = pen.split("_")
             kind, alpha = {"wu": 1, "avg": 2}[name], float(a)
-        done_seq = torch.empty(n_sub, b, T, dtype=torch.int64, device=dev)
-        done_lps = torch.empty(n_sub, b, T, device=dev)
-        done_p = torch.empty(n_sub, b, dtype=torch.float64, device=dev)
-        done_up = torch.empty(n_sub, b, dtype=torch.float64, device=dev)
-        done_cnt = torch.empty(n_sub, dtype=torch.int32, device=dev)
-        ws = self._ws.get(L.subgc_beam_workspace_bytes(C.byref(cd), n_sub, b, len_max), dev)
-        check(L.subgc_decode_beam(C.byref(cd), C.byref(w), n_sub, len_max, b, kind, alpha, int(opt.get("decoding_constraint", 0)), ptr(fc),
-                                  ptr(att), ptr(p_att), ptr(masks), ptr(done_seq), ptr(done_lps), ptr(done_p), ptr(done_up), ptr(done_cnt),
-                                  ptr(ws), ws.numel(), self._stream()), "subgc_decode_beam")
+        o = plan.out
+        if not o:
+            o["seq"] = torch.empty(n_sub, b, T, dtype=torch.int64, device=dev)
+            o["lps"] = torch.empty(n_sub, b, T, device=dev)
+            o["p"] = torch.empty(n_sub, b, dtype=torch.float64, device=dev)
+            o["up"] = torch.empty(n_sub, b, dtype=torch.float64, device=dev)
+            o["cnt"] = torch.empty(n_sub, dtype=torch.int32, device=dev)
+            o["ws"] = torch.empty(L.subgc_beam_workspace_bytes(C.byref(cd), n_sub, b, len_max) + 256, dtype=torch.uint8, device=dev)
+        st_args = (C.byref(cd), C.byref(w), n_sub, len_max, b, kind, alpha, int(opt.get("decoding_constraint", 0)), ptr(fc), ptr(att),
+                   ptr(p_att), ptr(masks), ptr(o["seq"]), ptr(o["lps"]), ptr(o["p"]), ptr(o["up"]), ptr(o["cnt"]), ptr(o["ws"]),
+                   o["ws"].numel())
+
+        def launch():
+            check(L.subgc_decode_beam(*st_args, self._stream()), "subgc_decode_beam")
+
+        plan.run(launch, self.use_graphs)
         self._mark("decode")
         # the reference hands back CPU tensors and python lists here (AttModel.py:212-213,229-231)
-        seq_h, lps_h, p_h, up_h, cnt_h = done_seq.cpu(), done_lps.cpu(), done_p.cpu(), done_up.cpu(), done_cnt.cpu()
+        seq_h, lps_h, p_h, up_h, cnt_h = o["seq"].cpu(), o["lps"].cpu(), o["p"].cpu(), o["up"].cpu(), o["cnt"].cpu()
         self.done_beams = [[dict(seq=seq_h[k, j], logps=lps_h[k, j], unaug_p=float(up_h[k, j]), p=float(p_h[k, j]))
                             for j in range(int(cnt_h[k]))] for k in range(n_sub)]
         return seq_h[:, 0].contiguous(), lps_h[:, 0].contiguous()
