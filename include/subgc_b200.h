@@ -234,6 +234,67 @@ int subgc_decode_beam(const subgc_dims* d, const subgc_weights* w, int n_sub, in
                       float* done_logps, double* done_p, double* done_unaug_p, int32_t* done_count, void* ws,
                       size_t ws_bytes, subgc_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Training building blocks (train-mode forward pieces and the backward halves).  The host side composes them
+ * into AttModel._forward + LossWrapper + backward (models/AttModel.py:122-177, models/loss_wrapper.py:14-27,
+ * misc/utils.py:111-124); see sub-gc_b200/subgc/train.py for the exact sequence.
+ * ------------------------------------------------------------------------------------------------------- */
+/* C[M,N] (+)= act(A[gather] . W^T + bias): nn.Linear forward; with swapped / transposed operands the two backward
+ * products dX = dY . W and dW += dY^T . X (operands are K-major: materialise transposes with subgc_transpose). */
+size_t subgc_gemm_nt_workspace_bytes(int M, int N, int K);
+int subgc_gemm_nt(int M, int N, int K, const float* A, int lda, const int64_t* a_gather /*nullable*/, const float* W,
+                  int ldw, const float* bias /*nullable*/, int relu, int accumulate, float* C, int ldc, void* ws,
+                  size_t ws_bytes, subgc_stream_t stream);
+int subgc_transpose(int rows, int cols, const float* in, int ld_in, float* out, int ld_out, subgc_stream_t stream);
+int subgc_colsum(int rows, int cols, const float* in, int ld, float* out, int accumulate, subgc_stream_t stream);
+/* op: 0 out=a*b, 1 out=a+b, 2 out=(a>0?b:0) (ReLU backward, a = forward output), 3 out=a*scalar, 4 out=a */
+int subgc_ew(int op, size_t n, const float* a, const float* b /*nullable*/, float* out, float scalar, subgc_stream_t stream);
+/* mask[i] = (u_i >= p) ? 1/(1-p) : 0 with Philox4x32-10 uniforms keyed by (seed, offset, i): nn.Dropout(p) */
+int subgc_dropout_mask(size_t n, float p, uint64_t seed, uint64_t offset, float* mask, subgc_stream_t stream);
+int subgc_gather_rows(int n_rows, int cols, const float* src, int ld_src, const int64_t* idx, float* out, int relu,
+                      subgc_stream_t stream);
+/* op 0: relu, 1: sigmoid */
+int subgc_unary(int op, size_t n, const float* a, float* out, subgc_stream_t stream);
+int subgc_scatter_add_rows(int n_rows, int cols, const float* src, int ld_src, const int64_t* idx, float* dst, int ld_dst,
+                           subgc_stream_t stream);
+/* nn.LSTMCell pointwise part; `gates` (pre-activation incl. biases) is overwritten by the activations (i,f,g,o) */
+int subgc_lstm_cell_train_fwd(int S, int H, float* gates, const float* c_prev, float* h_out, float* c_out,
+                              subgc_stream_t stream);
+int subgc_lstm_cell_bwd(int S, int H, const float* act, const float* c_prev, const float* c_new, const float* dh,
+                        const float* dc_in /*nullable*/, float* dgates, float* dc_prev, subgc_stream_t stream);
+/* Attention.forward (models/AttModel.py:445-471) keeping the pre-mask softmax `sm` and the final weights `alpha` */
+int subgc_attention_train_fwd(int S, int len, int H, int AH, const float* atth, const float* p_att, const float* att,
+                              const float* masks, const float* alpha_w, const float* alpha_b, float* ctx, float* alpha,
+                              float* sm, subgc_stream_t stream);
+/* d_att and d_p_att are accumulated (+=); d_atth [S,AH] and d_w_rows [S,AH] (per-row partials of alpha_net.weight's
+ * gradient) are overwritten */
+int subgc_attention_bwd(int S, int len, int H, int AH, const float* atth, const float* p_att, const float* att,
+                        const float* masks, const float* alpha_w, const float* alpha, const float* sm, const float* dctx,
+                        float* d_att, float* d_p_att, float* d_atth, float* d_w_rows, subgc_stream_t stream);
+int subgc_log_softmax_fwd(int rows, int V1, const float* logits, float* logp, size_t ld_out, subgc_stream_t stream);
+int subgc_log_softmax_bwd(int rows, int V1, const float* logp, const float* dlogp, size_t ld, float* dlogits,
+                          subgc_stream_t stream);
+int subgc_class_argmax(int rows, int n_classes, int skip_first, const float* dist, int64_t* cls, subgc_stream_t stream);
+int subgc_sgpn_pool(const subgc_dims* d, const subgc_subgraph_layout* lay, const float* x_obj, const int64_t* gpn_obj_ind,
+                    const float* att_masks, float* read_out, int32_t* sub_len, subgc_stream_t stream);
+int subgc_sgpn_bce(const subgc_subgraph_layout* lay, const float* score, float* loss, subgc_stream_t stream);
+int subgc_sgpn_pool_bwd(const subgc_dims* d, const subgc_subgraph_layout* lay, const float* x_obj,
+                        const int64_t* gpn_obj_ind, const int32_t* sub_len, const float* d_read_out, float* d_x_obj,
+                        subgc_stream_t stream);
+int subgc_bce_sigmoid_bwd(const subgc_subgraph_layout* lay, const float* score, float scale, float* dz,
+                          subgc_stream_t stream);
+int subgc_prepare_index(const subgc_dims* d, const subgc_subgraph_layout* lay, int n_rows, int len_max, const int32_t* sel,
+                        const int64_t* gpn_obj_ind, const float* att_masks, int64_t* node_row, float* masks,
+                        int32_t* row_len, subgc_stream_t stream);
+int subgc_gcn_edge_fwd(int B, int N, int K, int L, const float* m_subj, const float* m_obj, const int64_t* rel_ind,
+                       const float* res /*nullable*/, float* out, subgc_stream_t stream);
+int subgc_gcn_node_train_fwd(int B, int N, int K, int L, const float* m_subj, const float* m_obj, const int64_t* rel_ind,
+                             const float* res /*nullable*/, float* out, float* y0, float* y1, subgc_stream_t stream);
+int subgc_gcn_node_bwd(int B, int N, int K, int L, const float* dx, const float* y0, const float* y1,
+                       const int64_t* rel_ind, float* dm_subj, float* dm_obj, subgc_stream_t stream);
+int subgc_gcn_edge_bwd(int B, int N, int K, int L, const float* dp, const float* m_subj, const float* m_obj,
+                       const int64_t* rel_ind, float* dm_subj, float* dm_obj, subgc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

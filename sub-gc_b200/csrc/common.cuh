@@ -101,6 +101,7 @@ struct GemmEpilogue {
     int ld_add = 0;
     float div = 0.f;                // != 0: divide by it (GCN mean with count 1: 1 + 1e-7 in fp32)
     int relu = 0;
+    int accumulate = 0;             // C += result (weight-gradient accumulation); applied last
     // rows are grouped in blocks of `group` rows; row (g, j) is valid iff j < group_len[g]; invalid rows are
     // written as exact zeros (pack_padded_sequence semantics).  group_sel maps block -> index into group_len.
     const int* group_len = nullptr;

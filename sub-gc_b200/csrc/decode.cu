@@ -569,6 +569,13 @@ __global__ void __launch_bounds__(256) beam_step_kernel(const BeamArgs a) {
 
 using namespace subgc;
 
+extern "C" int subgc_log_softmax_fwd(int rows, int V1, const float* logits, float* logp, size_t ld_out, subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(logits && logp && rows > 0 && V1 > 0 && ld_out >= (size_t)V1, "subgc_log_softmax_fwd: bad arguments");
+    log_softmax_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, logp, V1, ld_out, nullptr);
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}
+
 extern "C" size_t subgc_decode_workspace_bytes(const subgc_dims* d, int n_rows, int len_max) {
     if (!d || n_rows <= 0) return 0;
     (void)len_max;

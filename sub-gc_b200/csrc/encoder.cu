@@ -245,3 +245,20 @@ extern "C" int subgc_gcn_forward(const subgc_dims* d, const subgc_weights* w, in
     }
     return SUBGC_OK;
 }
+
+extern "C" int subgc_class_argmax(int rows, int n_classes, int skip_first, const float* dist, int64_t* cls, subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(dist && cls && rows > 0 && n_classes > skip_first, "subgc_class_argmax: bad arguments");
+    class_argmax_kernel<<<(rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(dist, rows, n_classes, skip_first ? 1 : 0,
+                                                                                      reinterpret_cast<long long*>(cls));
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}
+
+extern "C" int subgc_gcn_edge_fwd(int B, int N, int K, int L, const float* m_subj, const float* m_obj, const int64_t* rel_ind, const float* res,
+                                  float* out, subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(m_subj && m_obj && rel_ind && out && B > 0, "subgc_gcn_edge_fwd: bad arguments");
+    gcn_edge_update_kernel<<<B * K, 256, 0, static_cast<cudaStream_t>(stream)>>>(m_subj, m_obj, reinterpret_cast<const long long*>(rel_ind), res, out,
+                                                                               B, N, K, L);
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}

@@ -180,6 +180,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tn_kernel(const GemmKern
                     if (n + j < p.N) v[j] = epilogue_apply(p.epi, v[j], m, n + j);
             }
             float* dst = out + (size_t)m * ldo + n;
+            if (!raw && p.epi.accumulate) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (n + j < p.N) v[j] += dst[j];
+            }
             if (n + 3 < p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
                 *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
             } else {
@@ -199,7 +204,9 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmProblem p,
         int m = (int)(idx / p.N), n = (int)(idx - (size_t)m * p.N);
         float v = 0.f;
         for (int z = 0; z < splits; ++z) v += part[(size_t)z * total + idx];
-        p.C[(size_t)m * p.ldc + n] = epilogue_apply(p.epi, v, m, n);
+        v = epilogue_apply(p.epi, v, m, n);
+        if (p.epi.accumulate) v += p.C[(size_t)m * p.ldc + n];
+        p.C[(size_t)m * p.ldc + n] = v;
     }
 }
 

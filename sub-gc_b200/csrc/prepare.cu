@@ -117,3 +117,16 @@ extern "C" int subgc_prepare_forward(const subgc_dims* d, const subgc_weights* w
     SUBGC_TRY(launch_gemm(p, ws.cursor(), ws.remaining(), st));
     return SUBGC_OK;
 }
+
+extern "C" int subgc_prepare_index(const subgc_dims* d, const subgc_subgraph_layout* lay, int n_rows, int len_max, const int32_t* sel,
+                                   const int64_t* gpn_obj_ind, const float* att_masks, int64_t* node_row, float* masks, int32_t* row_len,
+                                   subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(d && lay && sel && gpn_obj_ind && att_masks && node_row && masks && row_len && n_rows > 0 && len_max > 0,
+                    "subgc_prepare_index: bad arguments");
+    const int rows = n_rows * len_max;
+    prepare_index_kernel<<<(rows + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        *lay, sel, n_rows, len_max, d->obj_num, reinterpret_cast<const long long*>(gpn_obj_ind), att_masks, reinterpret_cast<long long*>(node_row),
+        masks, row_len);
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}

@@ -281,3 +281,22 @@ extern "C" int subgc_subgraph_nms(const subgc_dims* d, const subgc_subgraph_layo
     SUBGC_LAUNCH_CHECK();
     return SUBGC_OK;
 }
+
+extern "C" int subgc_sgpn_pool(const subgc_dims* d, const subgc_subgraph_layout* lay, const float* x_obj, const int64_t* gpn_obj_ind,
+                               const float* att_masks, float* read_out, int32_t* sub_len, subgc_stream_t stream) {
+    SUBGC_TRY(check_layout(lay));
+    SUBGC_CHECK_ARG(d && x_obj && gpn_obj_ind && att_masks && read_out && sub_len, "subgc_sgpn_pool: null argument");
+    const int n_sub = subgraph_count(*lay);
+    sgpn_pool_kernel<<<n_sub, 256, d->obj_num * sizeof(int), static_cast<cudaStream_t>(stream)>>>(
+        *lay, x_obj, reinterpret_cast<const long long*>(gpn_obj_ind), att_masks, read_out, sub_len, d->obj_num, d->gcn);
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}
+
+extern "C" int subgc_sgpn_bce(const subgc_subgraph_layout* lay, const float* score, float* loss, subgc_stream_t stream) {
+    SUBGC_TRY(check_layout(lay));
+    SUBGC_CHECK_ARG(score && loss, "subgc_sgpn_bce: null argument");
+    sgpn_bce_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(*lay, score, subgraph_count(*lay), loss);
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}

@@ -1,0 +1,571 @@
+// Training-side building blocks of the Sub-GC path: the backward halves of the decoder / sGPN / GCN stages and the
+// train-mode (dropout, saved activations) variants of the forward kernels.  The host side (subgc/train.py) composes
+// them into AttModel._forward + LossWrapper + backward (reference models/AttModel.py:122-177, models/loss_wrapper.py:14-27,
+// misc/utils.py:111-124); every contraction goes through the same GEMM block as inference (C = A . W^T, operands
+// K-major — transposed operands are materialised with subgc_transpose so that the tensor-core path applies).
+#include "common.cuh"
+
+namespace subgc {
+
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, int rows, int cols, int ld_in, float* __restrict__ out,
+                                                        int ld_out) {
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int i = ty; i < 32; i += 8) {
+        int r = r0 + i, c = c0 + tx;
+        if (r < rows && c < cols) tile[i][tx] = in[(size_t)r * ld_in + c];
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        int c = c0 + i, r = r0 + tx;
+        if (r < rows && c < cols) out[(size_t)c * ld_out + r] = tile[tx][i];
+    }
+}
+
+// out[c] (+)= sum_r in[r, c]; one block per 32 columns, fixed summation order
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ in, int rows, int cols, int ld, float* __restrict__ out,
+                                                     int accumulate) {
+    __shared__ float red[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    float a = 0.f;
+    if (c < cols)
+        for (int r = ty; r < rows; r += 8) a += in[(size_t)r * ld + c];
+    red[ty][tx] = a;
+    __syncthreads();
+    if (ty == 0 && c < cols) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += red[i][tx];
+        out[c] = accumulate ? out[c] + t : t;
+    }
+}
+
+// generic element-wise ops (grid-stride)
+enum { EW_MUL = 0, EW_ADD = 1, EW_RELU_BWD = 2, EW_SCALE = 3, EW_COPY = 4 };
+__global__ void __launch_bounds__(256) ew_kernel(int op, size_t n, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                                                 float scalar) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float v;
+        switch (op) {
+            case EW_MUL: v = a[i] * b[i]; break;
+            case EW_ADD: v = a[i] + b[i]; break;
+            case EW_RELU_BWD: v = a[i] > 0.f ? b[i] : 0.f; break;  // a = forward output, b = upstream gradient
+            case EW_SCALE: v = a[i] * scalar; break;
+            default: v = a[i]; break;
+        }
+        out[i] = v;
+    }
+}
+
+// Philox4x32-10 dropout mask: mask[i] = (u >= p) ? 1/(1-p) : 0, keyed by (seed, offset, i)
+__device__ __forceinline__ void philox_round(unsigned (&c)[4], unsigned k0, unsigned k1) {
+    unsigned hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    unsigned hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    unsigned n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+__global__ void __launch_bounds__(256) dropout_mask_kernel(size_t n, float p, unsigned long long seed, unsigned long long offset,
+                                                           float* __restrict__ mask) {
+    const float keep = 1.f / (1.f - p);
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q * 4 < n; q += (size_t)gridDim.x * blockDim.x) {
+        unsigned c[4] = {(unsigned)q, (unsigned)(q >> 32), (unsigned)offset, (unsigned)(offset >> 32)};
+        unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+        for (int i = 0; i < 10; ++i) { philox_round(c, k0, k1); k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+        for (int j = 0; j < 4; ++j) {
+            size_t i = q * 4 + j;
+            if (i < n) mask[i] = ((float)(c[j] >> 8) * (1.0f / 16777216.0f) >= p) ? keep : 0.f;
+        }
+    }
+}
+
+// dst[idx[r], :] += src[r, :]   (embedding / node-feature gradient; atomics: order-independent up to fp32 rounding)
+__global__ void __launch_bounds__(256) scatter_add_rows_kernel(const float* __restrict__ src, const long long* __restrict__ idx, int n_rows,
+                                                               int cols, int ld_src, float* __restrict__ dst, int ld_dst) {
+    const int r = blockIdx.x;
+    if (r >= n_rows) return;
+    float* d = dst + (size_t)idx[r] * ld_dst;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) atomicAdd(d + c, src[(size_t)r * ld_src + c]);
+}
+
+// LSTM cell, training flavour: gates (pre-activation, biases included) are overwritten with their activations
+// (i, f, o: sigmoid; g: tanh), which is what the backward pass needs.
+__global__ void __launch_bounds__(256) lstm_cell_train_fwd_kernel(float* __restrict__ gates, const float* __restrict__ c_prev,
+                                                                  float* __restrict__ h_out, float* __restrict__ c_out, int S, int H) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= S * H) return;
+    int r = idx / H, j = idx - r * H;
+    float* g = gates + (size_t)r * 4 * H;
+    float i = sigmoidf_(g[j]), f = sigmoidf_(g[H + j]), gg = tanhf(g[2 * H + j]), o = sigmoidf_(g[3 * H + j]);
+    float c = f * c_prev[idx] + i * gg;
+    g[j] = i; g[H + j] = f; g[2 * H + j] = gg; g[3 * H + j] = o;
+    c_out[idx] = c;
+    h_out[idx] = o * tanhf(c);
+}
+
+// dgates (pre-activation) and dc_prev from dh, dc (nullable), the saved activations and cell states
+__global__ void __launch_bounds__(256) lstm_cell_bwd_kernel(const float* __restrict__ act, const float* __restrict__ c_prev,
+                                                            const float* __restrict__ c_new, const float* __restrict__ dh,
+                                                            const float* __restrict__ dc_in, float* __restrict__ dgates,
+                                                            float* __restrict__ dc_prev, int S, int H) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= S * H) return;
+    int r = idx / H, j = idx - r * H;
+    const float* a = act + (size_t)r * 4 * H;
+    float i = a[j], f = a[H + j], g = a[2 * H + j], o = a[3 * H + j];
+    float tc = tanhf(c_new[idx]);
+    float dhv = dh[idx];
+    float dc = dhv * o * (1.f - tc * tc) + (dc_in ? dc_in[idx] : 0.f);
+    float* dg = dgates + (size_t)r * 4 * H;
+    dg[j] = dc * g * i * (1.f - i);
+    dg[H + j] = dc * c_prev[idx] * f * (1.f - f);
+    dg[2 * H + j] = dc * i * (1.f - g * g);
+    dg[3 * H + j] = dhv * tc * o * (1.f - o);
+    dc_prev[idx] = dc * f;
+}
+
+// Attention forward, training flavour: also stores the pre-mask softmax `sm` [S, len] next to alpha.
+__global__ void __launch_bounds__(256) attention_train_fwd_kernel(const float* __restrict__ atth, const float* __restrict__ p_att,
+                                                                  const float* __restrict__ att, const float* __restrict__ masks,
+                                                                  const float* __restrict__ alpha_w, const float* __restrict__ alpha_b,
+                                                                  float* __restrict__ ctx, float* __restrict__ alpha, float* __restrict__ sm,
+                                                                  int len, int H, int AH) {
+    extern __shared__ float s_a[];  // [AH] atth | [AH] w | [len] e
+    float* s_h = s_a; float* s_w = s_a + AH; float* s_e = s_a + 2 * AH;
+    const int r = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int j = threadIdx.x; j < AH; j += blockDim.x) { s_h[j] = atth[(size_t)r * AH + j]; s_w[j] = alpha_w[j]; }
+    __syncthreads();
+    const float* pa = p_att + (size_t)r * len * AH;
+    for (int n = wid; n < len; n += nw) {
+        float a = 0.f;
+        for (int j = lane; j < AH; j += 32) a = fmaf(s_w[j], tanhf(pa[(size_t)n * AH + j] + s_h[j]), a);
+        a = warp_sum(a);
+        if (lane == 0) s_e[n] = a + alpha_b[0];
+    }
+    __syncthreads();
+    if (wid == 0) {
+        float m = -INFINITY;
+        for (int n = lane; n < len; n += 32) m = fmaxf(m, s_e[n]);
+        m = warp_max(m);
+        float sum = 0.f;
+        for (int n = lane; n < len; n += 32) sum += expf(s_e[n] - m);
+        sum = warp_sum(sum);
+        float msum = 0.f;
+        for (int n = lane; n < len; n += 32) {
+            float sv = expf(s_e[n] - m) / sum;
+            sm[(size_t)r * len + n] = sv;
+            float wv = sv * masks[(size_t)r * len + n];
+            s_e[n] = wv;
+            msum += wv;
+        }
+        msum = warp_sum(msum);
+        for (int n = lane; n < len; n += 32) {
+            float wv = s_e[n] / msum;
+            s_e[n] = wv;
+            alpha[(size_t)r * len + n] = wv;
+        }
+    }
+    __syncthreads();
+    const float* af = att + (size_t)r * len * H;
+    for (int j = threadIdx.x; j < H; j += blockDim.x) {
+        float a = 0.f;
+        for (int n = 0; n < len; ++n) a = fmaf(s_e[n], af[(size_t)n * H + j], a);
+        ctx[(size_t)r * H + j] = a;
+    }
+}
+
+// Attention backward for one row per block.
+//   d_alpha_n = dctx . att_n ; d_w_n = (d_alpha_n - sum_k alpha_k d_alpha_k) / Z ; d_s_n = d_w_n m_n ; d_e_n = s_n (d_s_n - sum_k s_k d_s_k)
+//   d_att_n += alpha_n dctx ; u_nj = tanh(p_att_nj + atth_j) ; d_pre_nj = d_e_n w_j (1 - u^2) ; d_p_att_nj += d_pre_nj ;
+//   d_atth_j = sum_n d_pre_nj ; d_w_row_j = sum_n d_e_n u_nj  (per-row partial of alpha_net.weight's gradient)
+__global__ void __launch_bounds__(256) attention_bwd_kernel(const float* __restrict__ atth, const float* __restrict__ p_att,
+                                                            const float* __restrict__ att, const float* __restrict__ masks,
+                                                            const float* __restrict__ alpha_w, const float* __restrict__ alpha,
+                                                            const float* __restrict__ sm, const float* __restrict__ dctx,
+                                                            float* __restrict__ d_att, float* __restrict__ d_p_att, float* __restrict__ d_atth,
+                                                            float* __restrict__ d_w_rows, int len, int H, int AH) {
+    extern __shared__ float s_b[];  // [len] d_e | [len] alpha | [32] red
+    float* s_de = s_b; float* s_al = s_b + len; float* red = s_b + 2 * len;
+    const int r = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const float* af = att + (size_t)r * len * H;
+    const float* dc = dctx + (size_t)r * H;
+    for (int n = wid; n < len; n += nw) {  // d_alpha_n
+        float a = 0.f;
+        for (int j = lane; j < H; j += 32) a = fmaf(dc[j], af[(size_t)n * H + j], a);
+        a = warp_sum(a);
+        if (lane == 0) { s_de[n] = a; s_al[n] = alpha[(size_t)r * len + n]; }
+    }
+    __syncthreads();
+    if (wid == 0) {
+        float z = 0.f, dot = 0.f;
+        for (int n = lane; n < len; n += 32) {
+            z += sm[(size_t)r * len + n] * masks[(size_t)r * len + n];
+            dot += s_al[n] * s_de[n];
+        }
+        z = warp_sum(z); dot = warp_sum(dot);
+        float dot2 = 0.f;
+        for (int n = lane; n < len; n += 32) {
+            float ds = (s_de[n] - dot) / z * masks[(size_t)r * len + n];
+            s_de[n] = ds;
+            dot2 += sm[(size_t)r * len + n] * ds;
+        }
+        dot2 = warp_sum(dot2);
+        for (int n = lane; n < len; n += 32) s_de[n] = sm[(size_t)r * len + n] * (s_de[n] - dot2);
+    }
+    __syncthreads();
+    float* da = d_att + (size_t)r * len * H;
+    for (int idx = threadIdx.x; idx < len * H; idx += blockDim.x) {
+        int n = idx / H, j = idx - n * H;
+        da[idx] += s_al[n] * dc[j];
+    }
+    const float* pa = p_att + (size_t)r * len * AH;
+    float* dpa = d_p_att + (size_t)r * len * AH;
+    for (int j = threadIdx.x; j < AH; j += blockDim.x) {
+        const float hj = atth[(size_t)r * AH + j], wj = alpha_w[j];
+        float dh = 0.f, dw = 0.f;
+        for (int n = 0; n < len; ++n) {
+            float u = tanhf(pa[(size_t)n * AH + j] + hj);
+            float dpre = s_de[n] * wj * (1.f - u * u);
+            dpa[(size_t)n * AH + j] += dpre;
+            dh += dpre;
+            dw = fmaf(s_de[n], u, dw);
+        }
+        d_atth[(size_t)r * AH + j] = dh;
+        d_w_rows[(size_t)r * AH + j] = dw;
+    }
+    (void)red;
+}
+
+// dlogits = dlogp - exp(logp) * rowsum(dlogp)
+__global__ void __launch_bounds__(256) log_softmax_bwd_kernel(const float* __restrict__ logp, const float* __restrict__ dlogp, size_t ld,
+                                                              float* __restrict__ dlogits, int V1) {
+    __shared__ float red[32];
+    const float* lp = logp + (size_t)blockIdx.x * ld;
+    const float* dl = dlogp + (size_t)blockIdx.x * ld;
+    float s = 0.f;
+    for (int j = threadIdx.x; j < V1; j += blockDim.x) s += dl[j];
+    s = block_sum(s, red);
+    for (int j = threadIdx.x; j < V1; j += blockDim.x) dlogits[(size_t)blockIdx.x * V1 + j] = dl[j] - expf(lp[j]) * s;
+}
+
+// sGPN pooling backward: read_out = [max over rows | mean over rows]; d_x_obj[image, ids[n], c] += ...
+__global__ void __launch_bounds__(256) sgpn_pool_bwd_kernel(const subgc_subgraph_layout lay, const float* __restrict__ x_obj,
+                                                            const long long* __restrict__ obj_ind, const int* __restrict__ sub_len,
+                                                            const float* __restrict__ d_read, float* __restrict__ d_x_obj, int N, int L) {
+    extern __shared__ int s_ids[];
+    const int s = blockIdx.x;
+    int image;
+    const int slot = subgraph_slot(lay, s, &image);
+    for (int n = threadIdx.x; n < N; n += blockDim.x) s_ids[n] = (int)obj_ind[(size_t)slot * N + n];
+    __syncthreads();
+    const int len = sub_len[s];
+    const float* xi = x_obj + (size_t)image * N * L;
+    float* dxi = d_x_obj + (size_t)image * N * L;
+    const float inv = 1.f / (float)len;
+    for (int c = threadIdx.x; c < L; c += blockDim.x) {
+        float best = -INFINITY;
+        int bn = -1;
+        for (int n = 0; n < len; ++n) {
+            float v = xi[(size_t)s_ids[n] * L + c];
+            if (v > best) { best = v; bn = n; }
+        }
+        const float dmax = d_read[(size_t)s * 2 * L + c], dmean = d_read[(size_t)s * 2 * L + L + c] * inv;
+        const bool pad_wins = (len < N) && (0.f > best);  // a zero padding row holds the max: no gradient reaches x_obj
+        for (int n = 0; n < len; ++n) {
+            float g = dmean + ((n == bn && !pad_wins) ? dmax : 0.f);
+            atomicAdd(dxi + (size_t)s_ids[n] * L + c, g);
+        }
+    }
+}
+
+// GCN, training flavour of the node update: also stores the two branch outputs y0 = relu(S0/d0), y1 = relu(S1/d1)
+__global__ void __launch_bounds__(256) gcn_node_train_fwd_kernel(const float* __restrict__ m_subj, const float* __restrict__ m_obj,
+                                                                 const long long* __restrict__ rel_ind, const float* __restrict__ res,
+                                                                 float* __restrict__ out, float* __restrict__ y0, float* __restrict__ y1, int N,
+                                                                 int K, int L) {
+    extern __shared__ int s_list[];
+    __shared__ int s_cnt[2];
+    const int bn = blockIdx.x, b = bn / N, n = bn - b * N;
+    if (threadIdx.x == 0) {
+        int cs = 0, co = 0;
+        for (int k = 0; k < K; ++k) {
+            long long s = rel_ind[((size_t)b * K + k) * 2], o = rel_ind[((size_t)b * K + k) * 2 + 1];
+            if (s == n) s_list[cs++] = k;
+            if (o == n) s_list[K + co++] = k;
+        }
+        s_cnt[0] = cs; s_cnt[1] = co;
+    }
+    __syncthreads();
+    const int cs = s_cnt[0], co = s_cnt[1];
+    const float ds = (float)cs + 1e-7f, dob = (float)co + 1e-7f;
+    const float* ms = m_subj + (size_t)b * K * L;
+    const float* mo = m_obj + (size_t)b * K * L;
+    for (int c = threadIdx.x; c < L; c += blockDim.x) {
+        float a0 = 0.f, a1 = 0.f;
+        for (int i = 0; i < cs; ++i) a0 += ms[(size_t)s_list[i] * L + c];
+        for (int i = 0; i < co; ++i) a1 += mo[(size_t)s_list[K + i] * L + c];
+        float v0 = fmaxf(a0 / ds, 0.f), v1 = fmaxf(a1 / dob, 0.f);
+        y0[(size_t)bn * L + c] = v0;
+        y1[(size_t)bn * L + c] = v1;
+        float v = (v0 + v1) * 0.5f;
+        if (res) v += res[(size_t)bn * L + c];
+        out[(size_t)bn * L + c] = v;
+    }
+}
+
+// backward of the node update w.r.t. the per-edge messages: dM0[b,k] = 0.5 dx[b,s_k] 1[y0[b,s_k] > 0] / (cnt_s(s_k) + 1e-7), same for M1 / o_k
+__global__ void __launch_bounds__(256) gcn_node_bwd_kernel(const float* __restrict__ dx, const float* __restrict__ y0, const float* __restrict__ y1,
+                                                           const long long* __restrict__ rel_ind, float* __restrict__ dm_subj,
+                                                           float* __restrict__ dm_obj, int N, int K, int L) {
+    __shared__ float s_d[2];
+    const int bk = blockIdx.x, b = bk / K;
+    const long long s = rel_ind[(size_t)bk * 2], o = rel_ind[(size_t)bk * 2 + 1];
+    if (threadIdx.x == 0) {
+        int cs = 0, co = 0;
+        for (int k = 0; k < K; ++k) {
+            cs += rel_ind[((size_t)b * K + k) * 2] == s;
+            co += rel_ind[((size_t)b * K + k) * 2 + 1] == o;
+        }
+        s_d[0] = (float)cs + 1e-7f; s_d[1] = (float)co + 1e-7f;
+    }
+    __syncthreads();
+    const float ds = s_d[0], dob = s_d[1];
+    const size_t rs = ((size_t)b * N + s) * L, ro = ((size_t)b * N + o) * L;
+    for (int c = threadIdx.x; c < L; c += blockDim.x) {
+        dm_subj[(size_t)bk * L + c] = (y0[rs + c] > 0.f) ? 0.5f * dx[rs + c] / ds : 0.f;
+        dm_obj[(size_t)bk * L + c] = (y1[ro + c] > 0.f) ? 0.5f * dx[ro + c] / dob : 0.f;
+    }
+}
+
+// backward of the edge update w.r.t. the per-node messages: dM2[b,n] = (0.5/(1+1e-7)) 1[M2[b,n] > 0] sum_{k: s_k = n} dp[b,k], same for M3 / o_k
+__global__ void __launch_bounds__(256) gcn_edge_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ m_subj, const float* __restrict__ m_obj,
+                                                           const long long* __restrict__ rel_ind, float* __restrict__ dm_subj,
+                                                           float* __restrict__ dm_obj, int N, int K, int L) {
+    extern __shared__ int s_list[];
+    __shared__ int s_cnt[2];
+    const int bn = blockIdx.x, b = bn / N, n = bn - b * N;
+    if (threadIdx.x == 0) {
+        int cs = 0, co = 0;
+        for (int k = 0; k < K; ++k) {
+            long long s = rel_ind[((size_t)b * K + k) * 2], o = rel_ind[((size_t)b * K + k) * 2 + 1];
+            if (s == n) s_list[cs++] = k;
+            if (o == n) s_list[K + co++] = k;
+        }
+        s_cnt[0] = cs; s_cnt[1] = co;
+    }
+    __syncthreads();
+    const int cs = s_cnt[0], co = s_cnt[1];
+    const float d = 1.f + 1e-7f;
+    const float* dpb = dp + (size_t)b * K * L;
+    for (int c = threadIdx.x; c < L; c += blockDim.x) {
+        float a0 = 0.f, a1 = 0.f;
+        for (int i = 0; i < cs; ++i) a0 += dpb[(size_t)s_list[i] * L + c];
+        for (int i = 0; i < co; ++i) a1 += dpb[(size_t)s_list[K + i] * L + c];
+        dm_subj[(size_t)bn * L + c] = (m_subj[(size_t)bn * L + c] > 0.f) ? 0.5f * a0 / d : 0.f;
+        dm_obj[(size_t)bn * L + c] = (m_obj[(size_t)bn * L + c] > 0.f) ? 0.5f * a1 / d : 0.f;
+    }
+}
+
+// d_z = (p - t) * scale for BCE(sigmoid(z)); t = 1 for half 0 sub-graphs, 0 for half 1
+__global__ void __launch_bounds__(256) bce_sigmoid_bwd_kernel(const subgc_subgraph_layout lay, const float* __restrict__ score, int n_sub,
+                                                              float scale, float* __restrict__ dz) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_sub) return;
+    int half = (lay.order == 0) ? (s / lay.per_half) / lay.rows : (s / lay.per_half) % 2;
+    dz[s] = (score[s] - (half == 0 ? 1.f : 0.f)) * scale;
+}
+
+static int ew_blocks(size_t n) {
+    size_t b = (n + 255) / 256;
+    return (int)(b > (size_t)kNumSMs * 16 ? (size_t)kNumSMs * 16 : (b ? b : 1));
+}
+
+}  // namespace subgc
+
+using namespace subgc;
+#define ST static_cast<cudaStream_t>(stream)
+
+extern "C" size_t subgc_gemm_nt_workspace_bytes(int M, int N, int K) { return gemm_workspace_bytes(M, N, K) + 256; }
+
+extern "C" int subgc_gemm_nt(int M, int N, int K, const float* A, int lda, const int64_t* a_gather, const float* W, int ldw, const float* bias,
+                             int relu, int accumulate, float* C, int ldc, void* ws, size_t ws_bytes, subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(A && W && C && M >= 0 && N > 0 && K > 0, "subgc_gemm_nt: bad arguments");
+    GemmProblem p;
+    p.M = M; p.N = N; p.nseg = 1;
+    p.seg[0] = make_seg(A, lda, W, ldw, K);
+    p.seg[0].gather = reinterpret_cast<const long long*>(a_gather);
+    p.epi.bias = bias; p.epi.relu = relu; p.epi.accumulate = accumulate;
+    p.C = C; p.ldc = ldc;
+    return launch_gemm(p, ws, ws_bytes, ST);
+}
+
+extern "C" int subgc_transpose(int rows, int cols, const float* in, int ld_in, float* out, int ld_out, subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(in && out && rows > 0 && cols > 0, "subgc_transpose: bad arguments");
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+    transpose_kernel<<<grid, 256, 0, ST>>>(in, rows, cols, ld_in, out, ld_out);
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}
+
+extern "C" int subgc_colsum(int rows, int cols, const float* in, int ld, float* out, int accumulate, subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(in && out && rows >= 0 && cols > 0, "subgc_colsum: bad arguments");
+    colsum_kernel<<<(cols + 31) / 32, 256, 0, ST>>>(in, rows, cols, ld, out, accumulate);
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}
+
+extern "C" int subgc_ew(int op, size_t n, const float* a, const float* b, float* out, float scalar, subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(a && out && op >= 0 && op <= 4, "subgc_ew: bad arguments");
+    if (n == 0) return SUBGC_OK;
+    ew_kernel<<<ew_blocks(n), 256, 0, ST>>>(op, n, a, b, out, scalar);
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}
+
+extern "C" int subgc_dropout_mask(size_t n, float p, uint64_t seed, uint64_t offset, float* mask, subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(mask && p >= 0.f && p < 1.f, "subgc_dropout_mask: bad arguments");
+    if (n == 0) return SUBGC_OK;
+    dropout_mask_kernel<<<ew_blocks((n + 3) / 4), 256, 0, ST>>>(n, p, seed, offset, mask);
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}
+
+extern "C" int subgc_scatter_add_rows(int n_rows, int cols, const float* src, int ld_src, const int64_t* idx, float* dst, int ld_dst,
+                                      subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(src && idx && dst && cols > 0, "subgc_scatter_add_rows: bad arguments");
+    if (n_rows <= 0) return SUBGC_OK;
+    scatter_add_rows_kernel<<<n_rows, 256, 0, ST>>>(src, reinterpret_cast<const long long*>(idx), n_rows, cols, ld_src, dst, ld_dst);
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}
+
+extern "C" int subgc_lstm_cell_train_fwd(int S, int H, float* gates, const float* c_prev, float* h_out, float* c_out, subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(gates && c_prev && h_out && c_out && S > 0 && H > 0, "subgc_lstm_cell_train_fwd: bad arguments");
+    lstm_cell_train_fwd_kernel<<<(S * H + 255) / 256, 256, 0, ST>>>(gates, c_prev, h_out, c_out, S, H);
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}
+
+extern "C" int subgc_lstm_cell_bwd(int S, int H, const float* act, const float* c_prev, const float* c_new, const float* dh, const float* dc_in,
+                                   float* dgates, float* dc_prev, subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(act && c_prev && c_new && dh && dgates && dc_prev && S > 0 && H > 0, "subgc_lstm_cell_bwd: bad arguments");
+    lstm_cell_bwd_kernel<<<(S * H + 255) / 256, 256, 0, ST>>>(act, c_prev, c_new, dh, dc_in, dgates, dc_prev, S, H);
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}
+
+extern "C" int subgc_attention_train_fwd(int S, int len, int H, int AH, const float* atth, const float* p_att, const float* att,
+                                         const float* masks, const float* alpha_w, const float* alpha_b, float* ctx, float* alpha, float* sm,
+                                         subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(atth && p_att && att && masks && alpha_w && alpha_b && ctx && alpha && sm && S > 0 && len > 0 && len <= 64,
+                    "subgc_attention_train_fwd: bad arguments");
+    attention_train_fwd_kernel<<<S, 256, (size_t)(2 * AH + len) * 4, ST>>>(atth, p_att, att, masks, alpha_w, alpha_b, ctx, alpha, sm, len, H, AH);
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}
+
+extern "C" int subgc_attention_bwd(int S, int len, int H, int AH, const float* atth, const float* p_att, const float* att, const float* masks,
+                                   const float* alpha_w, const float* alpha, const float* sm, const float* dctx, float* d_att, float* d_p_att,
+                                   float* d_atth, float* d_w_rows, subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(atth && p_att && att && masks && alpha_w && alpha && sm && dctx && d_att && d_p_att && d_atth && d_w_rows && S > 0 &&
+                        len > 0 && len <= 64,
+                    "subgc_attention_bwd: bad arguments");
+    attention_bwd_kernel<<<S, 256, (size_t)(2 * len + 32) * 4, ST>>>(atth, p_att, att, masks, alpha_w, alpha, sm, dctx, d_att, d_p_att, d_atth,
+                                                                      d_w_rows, len, H, AH);
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}
+
+extern "C" int subgc_log_softmax_fwd(int rows, int V1, const float* logits, float* logp, size_t ld_out, subgc_stream_t stream);
+
+extern "C" int subgc_log_softmax_bwd(int rows, int V1, const float* logp, const float* dlogp, size_t ld, float* dlogits, subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(logp && dlogp && dlogits && rows > 0 && V1 > 0, "subgc_log_softmax_bwd: bad arguments");
+    log_softmax_bwd_kernel<<<rows, 256, 0, ST>>>(logp, dlogp, ld, dlogits, V1);
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}
+
+extern "C" int subgc_sgpn_pool_bwd(const subgc_dims* d, const subgc_subgraph_layout* lay, const float* x_obj, const int64_t* gpn_obj_ind,
+                                   const int32_t* sub_len, const float* d_read_out, float* d_x_obj, subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(d && lay && x_obj && gpn_obj_ind && sub_len && d_read_out && d_x_obj, "subgc_sgpn_pool_bwd: null argument");
+    const int n_sub = subgraph_count(*lay);
+    sgpn_pool_bwd_kernel<<<n_sub, 256, d->obj_num * sizeof(int), ST>>>(*lay, x_obj, reinterpret_cast<const long long*>(gpn_obj_ind), sub_len,
+                                                                      d_read_out, d_x_obj, d->obj_num, d->gcn);
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}
+
+extern "C" int subgc_gcn_node_train_fwd(int B, int N, int K, int L, const float* m_subj, const float* m_obj, const int64_t* rel_ind,
+                                        const float* res, float* out, float* y0, float* y1, subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(m_subj && m_obj && rel_ind && out && y0 && y1 && B > 0, "subgc_gcn_node_train_fwd: bad arguments");
+    gcn_node_train_fwd_kernel<<<B * N, 256, 2 * K * sizeof(int), ST>>>(m_subj, m_obj, reinterpret_cast<const long long*>(rel_ind), res, out, y0, y1,
+                                                                      N, K, L);
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}
+
+extern "C" int subgc_gcn_node_bwd(int B, int N, int K, int L, const float* dx, const float* y0, const float* y1, const int64_t* rel_ind,
+                                  float* dm_subj, float* dm_obj, subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(dx && y0 && y1 && rel_ind && dm_subj && dm_obj && B > 0, "subgc_gcn_node_bwd: bad arguments");
+    gcn_node_bwd_kernel<<<B * K, 256, 0, ST>>>(dx, y0, y1, reinterpret_cast<const long long*>(rel_ind), dm_subj, dm_obj, N, K, L);
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}
+
+extern "C" int subgc_gcn_edge_fwd(int B, int N, int K, int L, const float* m_subj, const float* m_obj, const int64_t* rel_ind, const float* res,
+                                  float* out, subgc_stream_t stream);
+
+extern "C" int subgc_gcn_edge_bwd(int B, int N, int K, int L, const float* dp, const float* m_subj, const float* m_obj, const int64_t* rel_ind,
+                                  float* dm_subj, float* dm_obj, subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(dp && m_subj && m_obj && rel_ind && dm_subj && dm_obj && B > 0, "subgc_gcn_edge_bwd: bad arguments");
+    gcn_edge_bwd_kernel<<<B * N, 256, 2 * K * sizeof(int), ST>>>(dp, m_subj, m_obj, reinterpret_cast<const long long*>(rel_ind), dm_subj, dm_obj, N, K,
+                                                                L);
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}
+
+extern "C" int subgc_bce_sigmoid_bwd(const subgc_subgraph_layout* lay, const float* score, float scale, float* dz, subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(lay && score && dz, "subgc_bce_sigmoid_bwd: null argument");
+    const int n_sub = subgraph_count(*lay);
+    bce_sigmoid_bwd_kernel<<<(n_sub + 255) / 256, 256, 0, ST>>>(*lay, score, n_sub, scale, dz);
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}
+
+namespace subgc {
+// out[r, :] = act(src[idx[r], :])
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, const long long* __restrict__ idx, int n_rows, int cols,
+                                                          int ld_src, float* __restrict__ out, int relu) {
+    const int r = blockIdx.x;
+    if (r >= n_rows) return;
+    const float* s = src + (size_t)idx[r] * ld_src;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+        float v = s[c];
+        out[(size_t)r * cols + c] = relu ? fmaxf(v, 0.f) : v;
+    }
+}
+__global__ void __launch_bounds__(256) ew2_kernel(int op, size_t n, const float* __restrict__ a, float* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float v = a[i];
+        out[i] = op == 0 ? fmaxf(v, 0.f) : sigmoidf_(v);
+    }
+}
+}  // namespace subgc
+
+extern "C" int subgc_gather_rows(int n_rows, int cols, const float* src, int ld_src, const int64_t* idx, float* out, int relu,
+                                 subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(src && idx && out && cols > 0, "subgc_gather_rows: bad arguments");
+    if (n_rows <= 0) return SUBGC_OK;
+    gather_rows_kernel<<<n_rows, 256, 0, ST>>>(src, reinterpret_cast<const long long*>(idx), n_rows, cols, ld_src, out, relu);
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}
+
+/* op 0: relu, 1: sigmoid */
+extern "C" int subgc_unary(int op, size_t n, const float* a, float* out, subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(a && out && (op == 0 || op == 1), "subgc_unary: bad arguments");
+    if (n == 0) return SUBGC_OK;
+    ew2_kernel<<<ew_blocks(n), 256, 0, ST>>>(op, n, a, out);
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}

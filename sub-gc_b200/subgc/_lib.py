@@ -77,6 +77,32 @@ SIGNATURES = {
     "subgc_beam_workspace_bytes": (_sz, [_P(Dims), _i, _i, _i]),
     "subgc_decode_beam": (_i, [_P(Dims), _P(Weights), _i, _i, _i, _i, _d, _i, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp,
                                c_fp, _sz, c_fp]),
+    # training building blocks
+    "subgc_gemm_nt_workspace_bytes": (_sz, [_i, _i, _i]),
+    "subgc_gemm_nt": (_i, [_i, _i, _i, c_fp, _i, c_fp, c_fp, _i, c_fp, _i, _i, c_fp, _i, c_fp, _sz, c_fp]),
+    "subgc_transpose": (_i, [_i, _i, c_fp, _i, c_fp, _i, c_fp]),
+    "subgc_colsum": (_i, [_i, _i, c_fp, _i, c_fp, _i, c_fp]),
+    "subgc_ew": (_i, [_i, _sz, c_fp, c_fp, c_fp, _f, c_fp]),
+    "subgc_dropout_mask": (_i, [_sz, _f, _u64, _u64, c_fp, c_fp]),
+    "subgc_gather_rows": (_i, [_i, _i, c_fp, _i, c_fp, c_fp, _i, c_fp]),
+    "subgc_unary": (_i, [_i, _sz, c_fp, c_fp, c_fp]),
+    "subgc_scatter_add_rows": (_i, [_i, _i, c_fp, _i, c_fp, c_fp, _i, c_fp]),
+    "subgc_lstm_cell_train_fwd": (_i, [_i, _i, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "subgc_lstm_cell_bwd": (_i, [_i, _i, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "subgc_attention_train_fwd": (_i, [_i, _i, _i, _i, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "subgc_attention_bwd": (_i, [_i, _i, _i, _i, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "subgc_log_softmax_fwd": (_i, [_i, _i, c_fp, c_fp, _sz, c_fp]),
+    "subgc_log_softmax_bwd": (_i, [_i, _i, c_fp, c_fp, _sz, c_fp, c_fp]),
+    "subgc_class_argmax": (_i, [_i, _i, _i, c_fp, c_fp, c_fp]),
+    "subgc_sgpn_pool": (_i, [_P(Dims), _P(Layout), c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "subgc_sgpn_bce": (_i, [_P(Layout), c_fp, c_fp, c_fp]),
+    "subgc_sgpn_pool_bwd": (_i, [_P(Dims), _P(Layout), c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "subgc_bce_sigmoid_bwd": (_i, [_P(Layout), c_fp, _f, c_fp, c_fp]),
+    "subgc_prepare_index": (_i, [_P(Dims), _P(Layout), _i, _i, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "subgc_gcn_edge_fwd": (_i, [_i, _i, _i, _i, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "subgc_gcn_node_train_fwd": (_i, [_i, _i, _i, _i, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "subgc_gcn_node_bwd": (_i, [_i, _i, _i, _i, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "subgc_gcn_edge_bwd": (_i, [_i, _i, _i, _i, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
 }
 
 _lib = None

@@ -97,6 +97,31 @@ class _DecodePlan:
             g.replay()
 
 
+class _TrainStep(torch.autograd.Function):
+    """Autograd hook-up of the CUDA training step: forward = subgc.train.forward (saves activations), backward =
+    subgc.train.backward (hand-written gradients of all parameters).  Inputs after `names` are the parameters, in order."""
+
+    @staticmethod
+    def forward(ctx, model, data, drop, names, *params):
+        from . import train
+        P = dict(zip(names, (p.detach() for p in params)))
+        ops = model._train_ops()
+        outputs, gpn_loss, score, saved = train.forward(ops, P, model._weights(), model.dims, data, drop, model.seq_per_img)
+        ctx.pack = (model, ops, P, saved, names)
+        ctx.mark_non_differentiable(score)
+        return outputs, gpn_loss[0], score
+
+    @staticmethod
+    def backward(ctx, d_outputs, d_gpn_loss, _d_score):
+        from . import train
+        model, ops, P, saved, names = ctx.pack
+        if d_outputs is None:
+            d_outputs = torch.zeros_like(saved["outputs"])
+        dg = 0.0 if d_gpn_loss is None else float(d_gpn_loss)
+        G = train.backward(ops, P, model.dims, saved, d_outputs.contiguous(), dg)
+        return (None, None, None, None) + tuple(G.get(n) for n in names)
+
+
 class TopDownModel(nn.Module):
     """Drop-in for reference `TopDownModel(AttModel(CaptionModel))`, Sub-GC configuration."""
 
@@ -158,6 +183,9 @@ class TopDownModel(nn.Module):
         self._ws = Workspace()
         self._wcache = None
         self.stage_events = None  # set to [] to collect (name, start_event, end_event) per stage (bench / profiling)
+        self.dropout_enabled = True   # tests switch it off: Philox masks cannot match torch's RNG stream (SURVEY §7 hard part 5)
+        self.force_train_path = False  # run the autograd-capable path in eval mode too (gradient parity tests)
+        self._tops = None
         self.use_graphs = os.environ.get("SUBGC_NO_GRAPH", "0") != "1"
         self._plans = {}
         self._cdims = _lib.Dims(d.v1, d.enc, d.rnn, d.att_hid, d.fc_feat, d.att_feat, d.gcn, d.low_rank, d.embed, d.obj_classes,
@@ -210,6 +238,12 @@ class TopDownModel(nn.Module):
         self._wcache = (key, w)
         self._plans.clear()  # captured graphs hold the old parameter addresses
         return w
+
+    def _train_ops(self):
+        from .train import CudaOps
+        if self._tops is None:
+            self._tops = CudaOps(self._cdims, self.seq_per_img)
+        return self._tops
 
     @staticmethod
     def _stream():
@@ -459,10 +493,9 @@ class TopDownModel(nn.Module):
                  pred_fmap=None, pred_dist=None, gpn_obj_ind=None, gpn_pred_ind=None, gpn_nrel_ind=None, gpn_pool_mtx=None):
         """Reference models/AttModel.py:122-177, evaluation semantics (no dropout, no scheduled sampling): returns
         (outputs [5B, T', V+1] log-probs, gpn_loss, subgraph_score [2*5B*G, 1])."""
-        if self.training:
-            raise NotImplementedError("training-mode forward (dropout + autograd) is not implemented by the CUDA path yet; "
-                                      "call model.eval() (validation loss, eval_utils.py:73-86)")
         dev = self._check_device(att_feats, seq, att_masks, obj_dist, rel_ind, gpn_obj_ind)
+        if self.training or (torch.is_grad_enabled() and self.force_train_path):
+            return self._forward_train(att_feats, seq, att_masks, obj_dist, rel_ind, gpn_obj_ind)
         L, w, cd = lib(), self._weights(), self._cdims
         gpn_obj_ind, att_masks, seq = self._i64(gpn_obj_ind), self._f32(att_masks), self._i64(seq)
         x_obj = self.encode(att_feats, obj_dist, pred_dist, rel_ind)
@@ -481,6 +514,23 @@ class TopDownModel(nn.Module):
                                      ptr(masks), ptr(outputs), ptr(ws), ws.numel(), self._stream()), "subgc_decode_teacher")
         self.last_sel = sel
         return outputs, loss[0], score.view(-1, 1)
+
+
+def _forward_train(self, att_feats, seq, att_masks, obj_dist, rel_ind, gpn_obj_ind):
+    """Training-mode AttModel._forward: CUDA forward with dropout + saved activations, gradients through _TrainStep."""
+    if self.ss_prob > 0:
+        raise NotImplementedError("scheduled sampling (ss_prob > 0) is not implemented by the CUDA training path (SURVEY §8f n4)")
+    data = dict(att_feats=self._f32(att_feats), obj_dist=self._f32(obj_dist), rel_ind=self._i64(rel_ind), labels=self._i64(seq),
+                att_masks=self._f32(att_masks), gpn_obj_ind=self._i64(gpn_obj_ind))
+    drop = None
+    if self.training and self.dropout_enabled and self.drop_prob_lm > 0:
+        drop = dict(p=float(self.drop_prob_lm), seed=int(torch.randint(0, 2 ** 31 - 1, (1,)).item()))
+    names, params = zip(*self.named_parameters())
+    outputs, gpn_loss, score = _TrainStep.apply(self, data, drop, names, *params)
+    return outputs, gpn_loss, score
+
+
+TopDownModel._forward_train = _forward_train
 
 
 class LanguageModelCriterion(nn.Module):
