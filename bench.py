@@ -120,13 +120,68 @@ def cpu_reference(d, sd, data, mode, steps, warmup, threads):
     return n * steps / dt, dt / steps * 1e3, n
 
 
+def bench_train(args, d, dev, rank, world, warmup):
+    """BASELINE config 5 (secondary line): Sub_GC_Kar training step = LossWrapper forward + backward (dropout on) + gradient
+    all-reduce (NCCL) on `--train-images` images per GPU (5 sentences each, 17 teacher-forced steps).  No optimiser step."""
+    import torch.distributed as dist
+    from subgc import parallel
+    from subgc.model import LossWrapper, setup
+    sd = synth.make_state_dict(d, SEED)
+    model = setup(make_opt(d))
+    model.load_state_dict(sd)
+    model.to(dev).train()
+    lw = LossWrapper(model, None)
+    data = synth.make_train_inputs(d, SEED + rank, n_images=args.train_images, gpn_batch=2, ragged=True, ragged_edges=True)
+    data = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in data.items()}
+    call = (data["fc_feats"], data["att_feats"], data["labels"], data["masks"], data["att_masks"], None, None, None, data["obj_dist"], None,
+            data["rel_ind"], None, data["pred_dist"], data["gpn_obj_ind"], data["gpn_pred_ind"], data["gpn_nrel_ind"], data["gpn_pool_mtx"])
+    params = list(model.parameters())
+
+    def step():
+        for p in params:
+            p.grad = None
+        out = lw(*call)
+        (out["lang_loss"] + out["gpn_loss"]).backward()
+        parallel.allreduce_gradients(params, world)
+        return out
+
+    for _ in range(warmup):
+        out = step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms = float(t[0]) / args.steps
+        sent = args.train_images * 5 * world
+        print(json.dumps({"metric": "training sentences/sec (Sub_GC_Kar step: forward + LanguageModelCriterion + backward + grad all-reduce)",
+                          "value": sent / (ms * 1e-3), "unit": "sentences/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+                          "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": f"BASELINE config 5: {args.train_images} images/GPU ({args.train_images * 5} sentences), 17 "
+                                                 "teacher-forced steps, dropout 0.5, grads all-reduced (280 MB fp32), no optimiser step"},
+                          "lang_loss": float(out["lang_loss"]), "gpn_loss": float(out["gpn_loss"])}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="greedy", choices=["greedy", "topk", "beam"])
+    ap.add_argument("--mode", default="greedy", choices=["greedy", "topk", "beam", "train"])
+    ap.add_argument("--train-images", type=int, default=32, help="images per GPU for --mode train (BASELINE config 5: 256 / 8 GPUs)")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -165,6 +220,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     from subgc import _lib
     from subgc.model import setup
+    if args.mode == "train":
+        return bench_train(args, d, dev, rank, world, warmup)
 
     sd = synth.make_state_dict(d, SEED)
     model = setup(make_opt(d, test_LSTM=1, gpn_nms_thres=0.75, gpn_max_subg=1, use_topk_sampling=1 if args.mode == "topk" else 0))

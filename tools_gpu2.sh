@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+nvidia-smi -L | head -4
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/ddp_check.py 2>&1 | tail -5
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-330
+timeout 300 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-330
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --mode train --steps 3 --warmup 2 2>&1 | tail -1 | cut -c1-600
+timeout 300 python bench.py --mode train --steps 3 --warmup 2 2>&1 | tail -1 | cut -c1-400
