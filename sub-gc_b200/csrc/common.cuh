@@ -191,6 +191,26 @@ __device__ __forceinline__ void block_argmax(float& v, int& i, float* redv /*[32
     for (int w = 1; w < nw; ++w) argmax_combine(v, i, redv[w], redi[w]);
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// bias / addend / divide / ReLU / zero-padding part of the contraction epilogue (accumulate-into-C is applied by the caller)
+__device__ __forceinline__ float epilogue_apply(const GemmEpilogue& e, float v, int m, int n) {
+    if (e.bias) v += __ldg(e.bias + n);
+    if (e.bias2) v += __ldg(e.bias2 + n);
+    if (e.addend) {
+        long long r = e.add_gather ? e.add_gather[m] : (e.add_gather32 ? (long long)e.add_gather32[m] : (long long)m);
+        v += __ldg(e.addend + r * e.ld_add + n);
+    }
+    // division by 1 is exact; never hand the compiler a speculative x / 0 (it if-converts the branch and every element
+    // then takes the slow-path division subroutine: measured 12x slower epilogues)
+    v = v / (e.div != 0.f ? e.div : 1.f);
+    if (e.relu) v = fmaxf(v, 0.f);
+    if (e.group) {
+        int g = m / e.group, j = m - g * e.group;
+        int len = e.group_len[e.group_sel ? e.group_sel[g] : g];
+        if (j >= len) v = 0.f;
+    }
+    return v;
+}
+
 #endif
 
 // locate sub-graph s in the loader tensors [rows, 2, per_half, N]: returns the flat (row*2+half)*per_half+g.

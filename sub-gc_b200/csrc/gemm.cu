@@ -26,23 +26,6 @@ struct GemmKernelArgs {
     float* part;          // != nullptr: raw partial sums [splits][M][N]
 };
 
-__device__ __forceinline__ float epilogue_apply(const GemmEpilogue& e, float v, int m, int n) {
-    if (e.bias) v += __ldg(e.bias + n);
-    if (e.bias2) v += __ldg(e.bias2 + n);
-    if (e.addend) {
-        long long r = e.add_gather ? e.add_gather[m] : (e.add_gather32 ? (long long)e.add_gather32[m] : (long long)m);
-        v += __ldg(e.addend + r * e.ld_add + n);
-    }
-    if (e.div != 0.f) v = v / e.div;
-    if (e.relu) v = fmaxf(v, 0.f);
-    if (e.group) {
-        int g = m / e.group, j = m - g * e.group;
-        int len = e.group_len[e.group_sel ? e.group_sel[g] : g];
-        if (j >= len) v = 0.f;
-    }
-    return v;
-}
-
 template <int ROWS, bool VEC>
 __device__ __forceinline__ void load_tile(float4 (&reg)[ROWS / 64], const float* base, int ld, int K, int k0, int row0,
                                           int row_limit, const long long* gather, const int* gather32, int row_div, bool relu, int tid) {
@@ -196,10 +179,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tn_kernel(const GemmKern
     }
 }
 
-// Fixed-order reduction of split-K partials followed by the epilogue.
+// Fixed-order reduction of split-K partials followed by the epilogue (z ascending: deterministic).
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmProblem p, const float* __restrict__ part, int splits) {
     if (p.active != nullptr && *p.active == 0) return;
-    size_t total = (size_t)p.M * p.N;
+    const size_t total = (size_t)p.M * p.N;
+    if ((p.N & 3) == 0 && (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0) {
+        const int n4 = p.N >> 2;
+        const size_t quads = total >> 2;
+        for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += (size_t)gridDim.x * blockDim.x) {
+            const int m = (int)(q / n4), n = (int)(q - (size_t)m * n4) << 2;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+            for (int z = 0; z < splits; ++z) {
+                const float4 t = *reinterpret_cast<const float4*>(part + (size_t)z * total + (q << 2));
+                v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+            }
+            v.x = epilogue_apply(p.epi, v.x, m, n); v.y = epilogue_apply(p.epi, v.y, m, n + 1);
+            v.z = epilogue_apply(p.epi, v.z, m, n + 2); v.w = epilogue_apply(p.epi, v.w, m, n + 3);
+            float4* dst = reinterpret_cast<float4*>(p.C + (size_t)m * p.ldc + n);
+            if (p.epi.accumulate) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+            *dst = v;
+        }
+        return;
+    }
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         int m = (int)(idx / p.N), n = (int)(idx - (size_t)m * p.N);
         float v = 0.f;
@@ -333,8 +335,10 @@ int launch_gemm_ex(const GemmProblem& p, float* raw_part, size_t raw_part_elems,
 
 void launch_splitk_reduce(const GemmProblem& p, const float* part, int splits, cudaStream_t stream) {
     size_t total = (size_t)p.M * p.N;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    size_t work = ((p.N & 3) == 0) ? total / 4 : total;
+    int blocks = (int)((work + 255) / 256);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    if (blocks < 1) blocks = 1;
     splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(p, part, splits);
 }
 

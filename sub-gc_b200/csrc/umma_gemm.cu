@@ -43,7 +43,7 @@ constexpr bool TC_L2_PREFETCH = false;  // measured on B200: no gain in steady s
                                         // bound) and the burst of prefetches delays the first demand tile by ~3 us
 constexpr int TC_PF_KB = 8;       // weights are requested into L2 in chunks of 8 k-blocks (128 columns = 512 contiguous bytes per row),
                                   // two chunks ahead of the smem ring: long row runs for the DRAM pages, latency cover without smem
-constexpr int TC_MAX_CHAIN = 32;  // k-blocks (512 columns) accumulated in TMEM before an fp32 round-to-nearest combine
+constexpr int TC_MAX_CHAIN = 64;  // k-blocks (1024 columns) accumulated in TMEM before an fp32 round-to-nearest combine
 
 struct TcParams {
     CUtensorMap tm_xhi, tm_xlo;
@@ -54,10 +54,15 @@ struct TcParams {
     int M, N;
     int kb_total, kb_per_split;
     float* part;                 // [splits][M][N]
+    int direct;                  // single split: apply the epilogue here and write C (no partial round trip)
+    GemmEpilogue epi;
+    float* C;
+    int ldc;
     const int* active;
     int raw_hi;                  // 1 (default): the raw fp32 weight tile is the "hi" operand -- the tensor core reads only the tf32
                                  // bits, i.e. truncates (measured: same error as an explicit split) -- and only lo = w - trunc(w) is
                                  // written; 0 (SUBGC_TC_REWRITE_HI=1): hi = rn_tf32(w) is rewritten in place as well
+    int epi_mode;                // debug (SUBGC_TC_EPI=1: TMEM loads only, 2: stores only)
     long long* trace;            // debug (SUBGC_TC_TRACE=1): per-role clock64 stamps of CTA (0,0,0); nullptr in normal operation
 };
 constexpr int TC_TRACE_SLOTS = 64;  // k-blocks traced per role
@@ -303,11 +308,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) umma_gemm_kernel(const __grid_c
         for (int c = 0; c < nchunks; ++c) {
             const int col0 = n0 + c * 32;
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (c + 1 < nchunks) {  // next chunk's TMEM reads overlap this chunk's global stores
+            if (t == 0) TC_STAMP(7, 2 * c);
+            if (c + 1 < nchunks && p.epi_mode != 2) {  // next chunk's TMEM reads overlap this chunk's global stores
                 TC_TMEM_LD32(na, tlane + (uint32_t)((c + 1) * 32));
                 TC_TMEM_LD32(nb, tlane + TC_BN + (uint32_t)((c + 1) * 32));
             }
-            if (row < p.M) {
+            if (row < p.M && p.direct) {
+                // epilogue in place for the simple cases (+ bias + bias2, ReLU, += C); anything with a divisor, addend or
+                // zero-padding goes through the partial buffer + reduce kernel.  Four warps do this for the whole tile: keep it lean.
+                float* crow = p.C + (size_t)row * p.ldc;
+                const bool vecc = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (col0 + 32 <= p.N);
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    // the (row-invariant) bias / addend values of 8 columns are fetched first, as independent loads under uniform
+                    // conditions: one dependent load->add chain per element would cost ~200 cycles each
+                    float b1[8], b2[8], v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { b1[u] = 0.f; b2[u] = 0.f; }
+                    if (p.epi.bias) {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) b1[u] = __ldg(p.epi.bias + min(col0 + j + u, p.N - 1));
+                    }
+                    if (p.epi.bias2) {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) b2[u] = __ldg(p.epi.bias2 + min(col0 + j + u, p.N - 1));
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        float t = __uint_as_float(ra[j + u]) + __uint_as_float(rb[j + u]);
+                        if (p.epi.bias) t += b1[u];
+                        if (p.epi.bias2) t += b2[u];
+                        v[u] = p.epi.relu ? fmaxf(t, 0.f) : t;
+                    }
+                    if (vecc) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            float4* dst = reinterpret_cast<float4*>(crow + col0 + j + 4 * h);
+                            float4 o = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
+                            if (p.epi.accumulate) { const float4 t = *dst; o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+                            *dst = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            if (col0 + j + u < p.N) crow[col0 + j + u] = p.epi.accumulate ? v[u] + crow[col0 + j + u] : v[u];
+                    }
+                }
+            } else if (row < p.M && p.epi_mode != 1) {
                 if (vec && col0 + 32 <= p.N) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
@@ -324,6 +371,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) umma_gemm_kernel(const __grid_c
                         if (col0 + j < p.N) out[col0 + j] = __uint_as_float(ra[j]) + __uint_as_float(rb[j]);
                 }
             }
+            if (t == 0) TC_STAMP(7, 2 * c + 1);
             if (c + 1 < nchunks) {
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
@@ -495,7 +543,8 @@ int launch_gemm_tc(const GemmProblem& p, void* ws_, size_t ws_bytes, cudaStream_
     Workspace ws(ws_, ws_bytes);
     float* xhi = ws.take<float>((size_t)pl.Mpad * pl.Kpad);
     float* xlo = ws.take<float>((size_t)pl.Mpad * pl.Kpad);
-    float* part = ws.take<float>((size_t)pl.splits * p.M * p.N);
+    const bool direct = (pl.splits == 1 && raw == nullptr && p.epi.div == 0.f && p.epi.addend == nullptr && p.epi.group == 0);
+    float* part = direct ? nullptr : ws.take<float>((size_t)pl.splits * p.M * p.N);
     if (!ws.ok()) {
         set_error("gemm(tc): workspace too small (%zu bytes given)", ws_bytes);
         return SUBGC_E_WORKSPACE;
@@ -527,6 +576,7 @@ int launch_gemm_tc(const GemmProblem& p, void* ws_, size_t ws_bytes, cudaStream_
         return SUBGC_E_CUDA;
     }
     tp.nseg = p.nseg; tp.M = p.M; tp.N = p.N; tp.kb_total = pl.kb_total; tp.kb_per_split = pl.kb_per_split; tp.part = part; tp.active = p.active;
+    tp.direct = direct ? 1 : 0; tp.epi = p.epi; tp.C = p.C; tp.ldc = p.ldc;
     size_t quads = (size_t)pl.Mpad * (pl.Kpad >> 2);
     int pblocks = (int)((quads + 255) / 256);
     if (pblocks > kNumSMs * 8) pblocks = kNumSMs * 8;
@@ -542,6 +592,8 @@ int launch_gemm_tc(const GemmProblem& p, void* ws_, size_t ws_bytes, cudaStream_
     static long long* trace_buf = nullptr;
     static const bool raw_hi = getenv("SUBGC_TC_REWRITE_HI") == nullptr;
     tp.raw_hi = raw_hi ? 1 : 0;
+    static const int epi_mode = getenv("SUBGC_TC_EPI") ? atoi(getenv("SUBGC_TC_EPI")) : 0;
+    tp.epi_mode = epi_mode;
     tp.trace = nullptr;
     if (trace_on) {
         if (!trace_buf) cudaMalloc(&trace_buf, 8 * TC_TRACE_SLOTS * sizeof(long long));
@@ -559,12 +611,16 @@ int launch_gemm_tc(const GemmProblem& p, void* ws_, size_t ws_bytes, cudaStream_
             const long long t0 = h[0];
             fprintf(stderr, "[tc-trace] M=%d N=%d kb=%d per_split=%d grid=(%d,%d,%d): acc_ready=%lld epi_done=%lld\n", p.M, p.N, pl.kb_total,
                     pl.kb_per_split, pl.n_tiles, pl.m_tiles, pl.splits, h[1] - t0, h[2] - t0);
+            fprintf(stderr, "[tc-trace]  epilogue chunk (start, stored):");
+            for (int c = 0; c < 8; ++c) fprintf(stderr, " (%lld, %lld)", h[7 * TC_TRACE_SLOTS + 2 * c] - t0, h[7 * TC_TRACE_SLOTS + 2 * c + 1] - t0);
+            fprintf(stderr, "\n");
             for (int i = 0; i < pl.kb_per_split && i < TC_TRACE_SLOTS; ++i)
                 fprintf(stderr, "[tc-trace]  kb %2d: prod_wait %6lld prod_issued %6lld | xf_start %6lld xf_done %6lld | mma_start %6lld mma_issued %6lld\n", i,
                         h[1 * TC_TRACE_SLOTS + i] - t0, h[2 * TC_TRACE_SLOTS + i] - t0, h[3 * TC_TRACE_SLOTS + i] - t0, h[4 * TC_TRACE_SLOTS + i] - t0,
                         h[5 * TC_TRACE_SLOTS + i] - t0, h[6 * TC_TRACE_SLOTS + i] - t0);
         }
     }
+    if (direct) return SUBGC_OK;
     if (raw) {
         raw->part = part;
         raw->splits = pl.splits;
