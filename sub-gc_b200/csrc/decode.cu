@@ -202,6 +202,9 @@ struct SelectArgs {
     float* seq_lp;         // [S, T]
     int* count;            // [T + 1] unfinished rows after step t (count[t] doubles as the `active` flag of step t+1)
     const int* active;
+    const float* embed;    // [V1, X] word embedding; the next step's input row relu(E[it]) is written to xt [S, X] here
+    float* xt;
+    int X;
 };
 
 constexpr int kSelectThreads = 1024;  // one block per row: the row is latency-bound, so use every warp slot of the SM
@@ -291,6 +294,7 @@ __global__ void __launch_bounds__(kSelectThreads) select_kernel(const SelectArgs
         tok = s_topi[pos];
         lp = s_topv[pos];
     }
+    __shared__ int s_it;
     if (threadIdx.x == 0) {
         int unf = (a.t == 0 ? 1 : a.unfinished[r]) && (tok > 0);
         long long it = unf ? tok : 0;
@@ -299,6 +303,12 @@ __global__ void __launch_bounds__(kSelectThreads) select_kernel(const SelectArgs
         a.seq[(size_t)r * a.T + a.t] = it;
         a.seq_lp[(size_t)r * a.T + a.t] = lp;
         if (unf) atomicAdd(a.count + a.t, 1);
+        s_it = (int)it;
+    }
+    if (a.xt != nullptr) {  // embed + ReLU of the token fed to the next step (AttModel.py:332), fused here
+        __syncthreads();
+        const float* e = a.embed + (size_t)s_it * a.X;
+        for (int j = threadIdx.x; j < a.X; j += blockDim.x) a.xt[(size_t)r * a.X + j] = fmaxf(__ldg(e + j), 0.f);
     }
 }
 
@@ -369,7 +379,7 @@ static bool take_step_scratch(const subgc_dims* d, int S, Workspace& ws, StepScr
 // weights are observable).  parent (nullable) re-maps the previous-state rows (beam re-ordering).
 // raw_logits != nullptr: the logit contraction leaves its split-K partials (no bias) for a fused consumer
 // (select_kernel); otherwise `logits` [S, V1] is materialised with the bias applied.
-static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int len_max, int rows_per_ctx, const long long* it,
+static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int len_max, int rows_per_ctx, const long long* it, const float* xt,
                        const long long* parent, const float* fc, const float* att, const float* p_att, const float* masks,
                        const float* h_in, const float* c_in, float* h_out, float* c_out, float* logits, RawPartials* raw_logits, float* att_w,
                        int att_w_stride, const StepScratch& sc, const int* active, int upto, cudaStream_t st) {
@@ -384,9 +394,13 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
     p.seg[0].gather = parent;
     p.seg[1] = make_seg(fc, H, w->att_w_ih + H, X + 2 * H, H);
     p.seg[1].a_row_div = rows_per_ctx;
-    p.seg[2] = make_seg(w->embed, X, w->att_w_ih + 2 * H, X + 2 * H, X);
-    p.seg[2].gather = it;
-    p.seg[2].relu_a = 1;
+    if (xt) {  // relu(E[it]) already materialised by the previous step's selection kernel
+        p.seg[2] = make_seg(xt, X, w->att_w_ih + 2 * H, X + 2 * H, X);
+    } else {
+        p.seg[2] = make_seg(w->embed, X, w->att_w_ih + 2 * H, X + 2 * H, X);
+        p.seg[2].gather = it;
+        p.seg[2].relu_a = 1;
+    }
     p.seg[3] = make_seg(h_in, H, w->att_w_hh, H, H);
     p.seg[3].gather = parent;
     p.active = active;
@@ -583,7 +597,7 @@ extern "C" size_t subgc_decode_workspace_bytes(const subgc_dims* d, int n_rows, 
     size_t b = step_scratch_bytes(d, n_rows);
     b += 4 * align_up(2 * S * H * 4, 256);                 // h / c ping-pong
     b += align_up(S * d->vocab1 * 4, 256);                 // logits
-    b += align_up(S * 8, 256) + align_up(S * 4, 256);      // it, unfinished
+    b += align_up(S * 8, 256) + align_up(S * 4, 256) + align_up(S * d->enc * 4, 256);  // it, unfinished, xt
     b += align_up((size_t)(d->seq_length + 2) * 4, 256);   // count
     return b + 1024;
 }
@@ -602,7 +616,7 @@ extern "C" int subgc_decode_step(const subgc_dims* d, const subgc_weights* w, in
     bool ok = take_step_scratch(d, n_rows, ws, sc);
     float* logits = ws.take<float>((size_t)n_rows * d->vocab1);
     if (!ok || !ws.ok()) { set_error("subgc_decode_step: workspace too small"); return SUBGC_E_WORKSPACE; }
-    SUBGC_TRY(launch_step(d, w, n_rows, len_max, rows_per_ctx, reinterpret_cast<const long long*>(it), nullptr, fc, att, p_att, masks, h_in,
+    SUBGC_TRY(launch_step(d, w, n_rows, len_max, rows_per_ctx, reinterpret_cast<const long long*>(it), nullptr, nullptr, fc, att, p_att, masks, h_in,
                           c_in, h_out, c_out, logits, nullptr, att_weights, len_max, sc, nullptr, 0, st));
     log_softmax_kernel<<<n_rows, 256, 0, st>>>(logits, logprobs, d->vocab1, (size_t)d->vocab1, nullptr);
     SUBGC_LAUNCH_CHECK();
@@ -629,6 +643,7 @@ extern "C" int subgc_decode_sample(const subgc_dims* d, const subgc_weights* w, 
     long long* it = ws.take<long long>(S);
     int* unfinished = ws.take<int>(S);
     int* count = ws.take<int>(T + 2);
+    float* xt = ws.take<float>((size_t)S * d->enc);
     if (!ok || !ws.ok()) { set_error("subgc_decode_sample: workspace too small"); return SUBGC_E_WORKSPACE; }
     SUBGC_CUDA(cudaMemsetAsync(hbuf[0], 0, 2 * (size_t)S * H * 4, st));   // init_hidden (AttModel.py:343-346)
     SUBGC_CUDA(cudaMemsetAsync(cbuf[0], 0, 2 * (size_t)S * H * 4, st));
@@ -649,17 +664,18 @@ extern "C" int subgc_decode_sample(const subgc_dims* d, const subgc_weights* w, 
             // the reference runs this step and discards its log-probs (AttModel.py:292-293); only the attention
             // weights are observable, so the step stops there (and is skipped entirely when they are not requested)
             if (att_weights)
-                SUBGC_TRY(launch_step(d, w, S, len_max, 1, it, nullptr, fc, att, p_att, masks, hbuf[in], cbuf[in], hbuf[out], cbuf[out], logits,
+                SUBGC_TRY(launch_step(d, w, S, len_max, 1, it, t > 0 ? xt : nullptr, nullptr, fc, att, p_att, masks, hbuf[in], cbuf[in], hbuf[out], cbuf[out], logits,
                                       nullptr, aw, (T + 1) * len_max, sc, active, 1, st));
             break;
         }
         RawPartials rl;
-        SUBGC_TRY(launch_step(d, w, S, len_max, 1, it, nullptr, fc, att, p_att, masks, hbuf[in], cbuf[in], hbuf[out], cbuf[out], logits, &rl, aw,
+        SUBGC_TRY(launch_step(d, w, S, len_max, 1, it, t > 0 ? xt : nullptr, nullptr, fc, att, p_att, masks, hbuf[in], cbuf[in], hbuf[out], cbuf[out], logits, &rl, aw,
                               (T + 1) * len_max, sc, active, 0, st));
         SelectArgs a;
         a.logits = rl.part; a.splits = rl.splits; a.bias = w->logit.b; a.V1 = V1; a.T = T; a.t = t; a.S = S; a.mode = mode; a.temp = temp; a.top_k = top_k; a.seed = seed;
         a.offset = offset; a.uniforms = uniforms; a.it = it; a.unfinished = unfinished; a.seq = reinterpret_cast<long long*>(seq);
         a.seq_lp = seq_logprobs; a.count = count; a.active = active;
+        a.embed = w->embed; a.xt = xt; a.X = d->enc;
         select_kernel<<<S, kSelectThreads, (size_t)V1 * sizeof(float), st>>>(a);
         SUBGC_LAUNCH_CHECK();
     }
@@ -696,7 +712,7 @@ extern "C" int subgc_decode_teacher(const subgc_dims* d, const subgc_weights* w,
     SUBGC_LAUNCH_CHECK();
     for (int i = 0; i < n_steps; ++i) {
         const int in = i & 1, out = in ^ 1;
-        SUBGC_TRY(launch_step(d, w, S, len_max, 1, tok_cols + (size_t)i * S, nullptr, fc, att, p_att, masks, hbuf[in], cbuf[in], hbuf[out],
+        SUBGC_TRY(launch_step(d, w, S, len_max, 1, tok_cols + (size_t)i * S, nullptr, nullptr, fc, att, p_att, masks, hbuf[in], cbuf[in], hbuf[out],
                               cbuf[out], logits, nullptr, nullptr, 0, sc, flags + i, 0, st));
         log_softmax_kernel<<<S, 256, 0, st>>>(logits, outputs + (size_t)i * V1, V1, (size_t)n_steps * V1, flags + i);
         SUBGC_LAUNCH_CHECK();
@@ -756,7 +772,7 @@ extern "C" int subgc_decode_beam(const subgc_dims* d, const subgc_weights* w, in
     SUBGC_CUDA(cudaMemsetAsync(done_p, 0, (size_t)S * 8, st));
     SUBGC_CUDA(cudaMemsetAsync(done_unaug_p, 0, (size_t)S * 8, st));
     // <bos> step on b identical rows per sub-graph (AttModel.py:216-227)
-    SUBGC_TRY(launch_step(d, w, S, len_max, b, it, nullptr, fc, att, p_att, masks, hbuf[0], cbuf[0], hbuf[1], cbuf[1], logits, nullptr, nullptr,
+    SUBGC_TRY(launch_step(d, w, S, len_max, b, it, nullptr, nullptr, fc, att, p_att, masks, hbuf[0], cbuf[0], hbuf[1], cbuf[1], logits, nullptr, nullptr,
                           0, sc, nullptr, 0, st));
     for (int t = 0; t < T; ++t) {
         BeamArgs a;
@@ -770,7 +786,7 @@ extern "C" int subgc_decode_beam(const subgc_dims* d, const subgc_weights* w, in
         SUBGC_LAUNCH_CHECK();
         if (t == T - 1) break;  // the reference's final get_logprobs_state result is never read (CaptionModel.py:170-171)
         const int in = (t + 1) & 1, out = in ^ 1;
-        SUBGC_TRY(launch_step(d, w, S, len_max, b, it, parent, fc, att, p_att, masks, hbuf[in], cbuf[in], hbuf[out], cbuf[out], logits, nullptr,
+        SUBGC_TRY(launch_step(d, w, S, len_max, b, it, nullptr, parent, fc, att, p_att, masks, hbuf[in], cbuf[in], hbuf[out], cbuf[out], logits, nullptr,
                               nullptr, 0, sc, nullptr, 0, st));
     }
     return SUBGC_OK;

@@ -8,16 +8,17 @@
 //
 // Dataflow of one CTA (192 threads = 6 warps, 1 CTA / SM, persistent over its k-range):
 //   warp 0      TMA producer: per k-block (16 fp32 = one 64-byte swizzled row) loads the raw fp32 weight tile
-//               W[256 x 16] straight from the reference's un-repacked nn.Linear / LSTMCell tensor, plus the
-//               pre-split activation tiles Xhi / Xlo [128 x 16]            (cp.async.bulk.tensor, mbarrier tx)
-//   warps 2-5   transform: split the weight tile in shared memory (hi in place, lo to a second buffer),
-//               fence.proxy.async, signal the MMA warp; after the main loop they are the epilogue warps
+//               W[256 x 16] straight from the reference's un-repacked nn.Linear / LSTMCell tensor and the raw fp32
+//               activation tile X[128 x 16] of the K segment it belongs to   (cp.async.bulk.tensor, mbarrier tx)
+//   warps 2-5   transform: write lo = v - trunc_tf32(v) of both tiles to second buffers (the raw tiles serve as
+//               "hi": the tensor core reads only their tf32 bits), fence.proxy.async, signal the MMA warp; after
+//               the main loop they are the epilogue warps
 //   warp 1      one elected thread issues 3 x 2 tcgen05.mma.kind::tf32 (M=128, N=256, K=8) per k-block into a
 //               256-column TMEM accumulator, tcgen05.commit frees the stage / publishes the accumulator
 //   epilogue    tcgen05.ld 32x32b.x32 -> registers -> per-warp smem transpose -> coalesced 128-byte row stores of
 //               the split-K partial [z][M][N]; the reduction + epilogue kernel is shared with the SIMT block.
-// Activations are packed once per GEMM by pack_split_kernel (gather / shared rows / ReLU-on-load / concat of the K
-// segments, zero padding to 16 columns per segment and 128 rows) so that one 2-D tensor map describes them.
+// K segments (the un-concatenated LSTM inputs) are separate tensor maps on both sides, so plain activations are read
+// in place; only segments that need a row gather / shared rows / ReLU-on-load are materialised first (gather_seg_kernel).
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -35,8 +36,8 @@ constexpr int TC_STAGES = 4;
 constexpr int TC_THREADS = 192;
 constexpr int TC_W_BYTES = TC_BN * TC_BK * 4;                     // 16 KB
 constexpr int TC_X_BYTES = TC_BM * TC_BK * 4;                     // 8 KB
-constexpr int TC_STAGE_BYTES = 2 * TC_W_BYTES + 2 * TC_X_BYTES;   // Whi | Wlo | Xhi | Xlo = 48 KB
-constexpr int TC_TX_BYTES = TC_W_BYTES + 2 * TC_X_BYTES;          // bytes TMA lands per stage
+constexpr int TC_STAGE_BYTES = 2 * TC_W_BYTES + 2 * TC_X_BYTES;   // W raw | W lo | X raw | X lo = 48 KB
+constexpr int TC_TX_BYTES = TC_W_BYTES + TC_X_BYTES;              // bytes TMA lands per stage
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int TC_MAX_SEG = 4;
 constexpr bool TC_L2_PREFETCH = false;  // measured on B200: no gain in steady state (the loop is shared-memory-bandwidth
@@ -46,7 +47,7 @@ constexpr int TC_PF_KB = 8;       // weights are requested into L2 in chunks of 
 constexpr int TC_MAX_CHAIN = 64;  // k-blocks (1024 columns) accumulated in TMEM before an fp32 round-to-nearest combine
 
 struct TcParams {
-    CUtensorMap tm_xhi, tm_xlo;
+    CUtensorMap tm_x[TC_MAX_SEG];
     CUtensorMap tm_w[TC_MAX_SEG];
     CUtensorMap tm_wpf[TC_MAX_SEG];  // same tensors, box 128 columns x 256 rows: L2 prefetch of 512-byte row runs (DRAM page locality)
     int seg_kb_end[TC_MAX_SEG];  // cumulative k-block count at the end of each segment
@@ -174,9 +175,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) umma_gemm_kernel(const __grid_c
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            prefetch_tensormap(&p.tm_xhi);
-            prefetch_tensormap(&p.tm_xlo);
-            for (int sgi = 0; sgi < p.nseg; ++sgi) prefetch_tensormap(&p.tm_w[sgi]);
+            for (int sgi = 0; sgi < p.nseg; ++sgi) { prefetch_tensormap(&p.tm_w[sgi]); prefetch_tensormap(&p.tm_x[sgi]); }
             // weight k-block -> (segment, column) lookup; `pseg` trails the L2 prefetch cursor, `seg` the smem ring
             int seg = 0, pseg = 0;
             while (seg < p.nseg - 1 && kb_begin >= p.seg_kb_end[seg]) ++seg;
@@ -208,8 +207,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) umma_gemm_kernel(const __grid_c
                 const uint32_t full = bar_base + 8 * s;
                 mbar_arrive_expect_tx(full, TC_TX_BYTES);
                 tma_load_2d(st, &p.tm_w[seg], full, (kb - seg_kb0) * TC_BK, n0);
-                tma_load_2d(st + 2 * TC_W_BYTES, &p.tm_xhi, full, kb * TC_BK, m0);
-                tma_load_2d(st + 2 * TC_W_BYTES + TC_X_BYTES, &p.tm_xlo, full, kb * TC_BK, m0);
+                tma_load_2d(st + 2 * TC_W_BYTES, &p.tm_x[seg], full, (kb - seg_kb0) * TC_BK, m0);
                 TC_STAMP(2, i);
             }
         }
@@ -276,6 +274,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) umma_gemm_kernel(const __grid_c
                     whi[idx] = h;
                 }
                 wlo[idx] = l;
+            }
+            {
+                const float4* xr = reinterpret_cast<const float4*>(gbase + s * TC_STAGE_BYTES + 2 * TC_W_BYTES);
+                float4* xl = reinterpret_cast<float4*>(gbase + s * TC_STAGE_BYTES + 2 * TC_W_BYTES + TC_X_BYTES);
+#pragma unroll
+                for (int j = 0; j < TC_X_BYTES / 16 / 128; ++j) {
+                    const int idx = t + 128 * j;
+                    const float4 v = xr[idx];
+                    float4 l;
+                    l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+                    l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+                    l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+                    l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+                    xl[idx] = l;
+                }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to tcgen05.mma
             __syncwarp();
@@ -388,41 +401,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) umma_gemm_kernel(const __grid_c
     }
 }
 
-// ---- activation packing: concat segments, gather, ReLU-on-load, zero pad, hi/lo split ----------------------------------
-struct PackArgs {
-    GemmSeg seg[TC_MAX_SEG];
-    int seg_col0[TC_MAX_SEG + 1];  // first packed column of each segment (multiples of 16); [nseg] = Kpad
-    int nseg, M, Mpad, Kpad;
-    float* xhi;
-    float* xlo;
-    const int* active;
-};
-
-__global__ void __launch_bounds__(256) pack_split_kernel(const PackArgs a) {
-    if (a.active != nullptr && *a.active == 0) return;
-    const int kq = a.Kpad >> 2;
-    const size_t total = (size_t)a.Mpad * kq;
+// ---- materialisation of a K segment whose rows are gathered / shared / ReLU-ed on load --------------------------------------
+__global__ void __launch_bounds__(256) gather_seg_kernel(const GemmSeg g, int M, int Kp, float* __restrict__ out, const int* __restrict__ active) {
+    if (active != nullptr && *active == 0) return;
+    const int kq = Kp >> 2;
+    const size_t total = (size_t)M * kq;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const int m = (int)(idx / kq), c = (int)(idx - (size_t)m * kq) << 2;
-        int s = 0;
-        while (s < a.nseg - 1 && c >= a.seg_col0[s + 1]) ++s;
-        const GemmSeg& g = a.seg[s];
-        const int k = c - a.seg_col0[s];
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (m < a.M && k < g.K) {
-            long long src = g.gather ? g.gather[m] : (g.gather32 ? (long long)g.gather32[m] : (long long)(m / g.a_row_div));
-            const float* ptr = g.A + src * g.lda + k;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (k + j < g.K) v[j] = g.relu_a ? fmaxf(__ldg(ptr + j), 0.f) : __ldg(ptr + j);
-        }
-        float4 h, l;
-        h.x = __uint_as_float(to_tf32(v[0])); h.y = __uint_as_float(to_tf32(v[1]));
-        h.z = __uint_as_float(to_tf32(v[2])); h.w = __uint_as_float(to_tf32(v[3]));
-        l.x = __uint_as_float(to_tf32(v[0] - h.x)); l.y = __uint_as_float(to_tf32(v[1] - h.y));
-        l.z = __uint_as_float(to_tf32(v[2] - h.z)); l.w = __uint_as_float(to_tf32(v[3] - h.w));
-        reinterpret_cast<float4*>(a.xhi)[idx] = h;
-        reinterpret_cast<float4*>(a.xlo)[idx] = l;
+        const int m = (int)(idx / kq), k = (int)(idx - (size_t)m * kq) << 2;
+        const long long src = g.gather ? g.gather[m] : (g.gather32 ? (long long)g.gather32[m] : (long long)(m / g.a_row_div));
+        const float* ptr = g.A + src * g.lda + k;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < g.K) v.x = __ldg(ptr);
+        if (k + 1 < g.K) v.y = __ldg(ptr + 1);
+        if (k + 2 < g.K) v.z = __ldg(ptr + 2);
+        if (k + 3 < g.K) v.w = __ldg(ptr + 3);
+        if (g.relu_a) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        reinterpret_cast<float4*>(out)[idx] = v;
     }
 }
 
@@ -529,8 +523,8 @@ size_t tc_workspace_bytes(int M, int N, int Ktotal) {
     if (splits < 1) splits = 1;
     const int by_chain = (Ktotal / TC_BK + TC_MAX_SEG + TC_MAX_CHAIN - 1) / TC_MAX_CHAIN + 1;
     if (splits < by_chain) splits = by_chain;
-    const size_t Kpad = (size_t)Ktotal + TC_MAX_SEG * TC_BK;
-    return 2 * align_up((size_t)m_tiles * TC_BM * Kpad * 4, 256) + align_up((size_t)splits * M * N * 4, 256) + 512;
+    const size_t Kpad = (size_t)Ktotal + TC_MAX_SEG * 4;
+    return align_up((size_t)M * Kpad * 4, 256) + TC_MAX_SEG * 256 + align_up((size_t)splits * M * N * 4, 256) + 512;
 }
 
 void launch_splitk_reduce(const GemmProblem& p, const float* part, int splits, cudaStream_t stream);
@@ -541,47 +535,52 @@ int launch_gemm_tc(const GemmProblem& p, void* ws_, size_t ws_bytes, cudaStream_
     for (int s = 0; s < p.nseg; ++s) segK[s] = p.seg[s].K;
     const TcPlan pl = tc_plan(p.M, p.N, segK, p.nseg);
     Workspace ws(ws_, ws_bytes);
-    float* xhi = ws.take<float>((size_t)pl.Mpad * pl.Kpad);
-    float* xlo = ws.take<float>((size_t)pl.Mpad * pl.Kpad);
     const bool direct = (pl.splits == 1 && raw == nullptr && p.epi.div == 0.f && p.epi.addend == nullptr && p.epi.group == 0);
     float* part = direct ? nullptr : ws.take<float>((size_t)pl.splits * p.M * p.N);
+    TcParams tp;
+    int kb = 0;
+    for (int s = 0; s < p.nseg; ++s) {
+        const GemmSeg& g = p.seg[s];
+        const int nkb = (g.K + TC_BK - 1) / TC_BK;
+        kb += nkb;
+        tp.seg_kb_end[s] = kb;
+        if (!make_map(&tp.tm_w[s], g.W, p.N, g.K, g.ldw, TC_BN)) {
+            set_error("gemm(tc): cuTensorMapEncodeTiled failed for weight segment %d", s);
+            return SUBGC_E_CUDA;
+        }
+        if (TC_L2_PREFETCH && !make_map(&tp.tm_wpf[s], g.W, p.N, g.K, g.ldw, TC_BN, TC_PF_KB * TC_BK)) {
+            set_error("gemm(tc): cuTensorMapEncodeTiled failed for the prefetch map of weight segment %d", s);
+            return SUBGC_E_CUDA;
+        }
+        const float* xa = g.A;
+        long long xld = g.lda;
+        const bool plain = g.gather == nullptr && g.gather32 == nullptr && g.a_row_div == 1 && g.relu_a == 0 && (g.lda & 3) == 0 &&
+                           (reinterpret_cast<uintptr_t>(g.A) & 15) == 0;
+        if (!plain) {  // gathered / shared / ReLU-ed rows: materialise this segment once, [M, K rounded up to 4]
+            const int Kp = (g.K + 3) & ~3;
+            float* tmp = ws.take<float>((size_t)p.M * Kp);
+            if (!ws.ok()) break;
+            size_t quads = (size_t)p.M * (Kp >> 2);
+            int gb = (int)((quads + 255) / 256);
+            if (gb > kNumSMs * 8) gb = kNumSMs * 8;
+            gather_seg_kernel<<<gb, 256, 0, stream>>>(g, p.M, Kp, tmp, p.active);
+            SUBGC_LAUNCH_CHECK();
+            xa = tmp;
+            xld = Kp;
+        }
+        if (!make_map(&tp.tm_x[s], xa, p.M, g.K, xld, TC_BM)) {
+            set_error("gemm(tc): cuTensorMapEncodeTiled failed for activation segment %d", s);
+            return SUBGC_E_CUDA;
+        }
+    }
     if (!ws.ok()) {
         set_error("gemm(tc): workspace too small (%zu bytes given)", ws_bytes);
         return SUBGC_E_WORKSPACE;
     }
-    PackArgs pa;
-    pa.nseg = p.nseg; pa.M = p.M; pa.Mpad = pl.Mpad; pa.Kpad = pl.Kpad; pa.xhi = xhi; pa.xlo = xlo; pa.active = p.active;
-    TcParams tp;
-    int col = 0, kb = 0;
-    for (int s = 0; s < p.nseg; ++s) {
-        pa.seg[s] = p.seg[s];
-        pa.seg_col0[s] = col;
-        const int nkb = (p.seg[s].K + TC_BK - 1) / TC_BK;
-        col += nkb * TC_BK;
-        kb += nkb;
-        tp.seg_kb_end[s] = kb;
-        if (!make_map(&tp.tm_w[s], p.seg[s].W, p.N, p.seg[s].K, p.seg[s].ldw, TC_BN)) {
-            set_error("gemm(tc): cuTensorMapEncodeTiled failed for weight segment %d", s);
-            return SUBGC_E_CUDA;
-        }
-        if (!make_map(&tp.tm_wpf[s], p.seg[s].W, p.N, p.seg[s].K, p.seg[s].ldw, TC_BN, TC_PF_KB * TC_BK)) {
-            set_error("gemm(tc): cuTensorMapEncodeTiled failed for the prefetch map of weight segment %d", s);
-            return SUBGC_E_CUDA;
-        }
-    }
-    for (int s = p.nseg; s < TC_MAX_SEG; ++s) { tp.seg_kb_end[s] = kb; tp.tm_w[s] = tp.tm_w[0]; tp.tm_wpf[s] = tp.tm_wpf[0]; }
-    pa.seg_col0[p.nseg] = col;
-    if (!make_map(&tp.tm_xhi, xhi, pl.Mpad, pl.Kpad, pl.Kpad, TC_BM) || !make_map(&tp.tm_xlo, xlo, pl.Mpad, pl.Kpad, pl.Kpad, TC_BM)) {
-        set_error("gemm(tc): cuTensorMapEncodeTiled failed for the activation tiles");
-        return SUBGC_E_CUDA;
-    }
+    for (int s = p.nseg; s < TC_MAX_SEG; ++s) { tp.seg_kb_end[s] = kb; tp.tm_w[s] = tp.tm_w[0]; tp.tm_x[s] = tp.tm_x[0]; tp.tm_wpf[s] = tp.tm_w[0]; }
+    if (!TC_L2_PREFETCH) for (int s = 0; s < p.nseg; ++s) tp.tm_wpf[s] = tp.tm_w[s];
     tp.nseg = p.nseg; tp.M = p.M; tp.N = p.N; tp.kb_total = pl.kb_total; tp.kb_per_split = pl.kb_per_split; tp.part = part; tp.active = p.active;
     tp.direct = direct ? 1 : 0; tp.epi = p.epi; tp.C = p.C; tp.ldc = p.ldc;
-    size_t quads = (size_t)pl.Mpad * (pl.Kpad >> 2);
-    int pblocks = (int)((quads + 255) / 256);
-    if (pblocks > kNumSMs * 8) pblocks = kNumSMs * 8;
-    pack_split_kernel<<<pblocks, 256, 0, stream>>>(pa);
-    SUBGC_LAUNCH_CHECK();
     static bool attr_set = false;
     if (!attr_set) {
         SUBGC_CUDA(cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
