@@ -244,9 +244,24 @@ def main():
     def step_resident():
         return model(*[resident[k] for k in names], opt=opt, mode="sample")
 
-    def step_e2e():
-        args_dev = [host[k].to(dev, non_blocking=True) if host[k] is not None else None for k in names]
-        out = model(*args_dev, opt=opt, mode="sample")
+    # end to end: every step's inputs start in pinned HOST memory and its results end in host memory.  The H2D copy of step
+    # i+1 is issued on a copy stream while step i computes (two device-side input sets); the timed region contains all of it.
+    copy_stream = torch.cuda.Stream(device=dev)
+    dev_in = [{k: (torch.empty_like(resident[k]) if resident[k] is not None else None) for k in names} for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            for k in names:
+                if host[k] is not None:
+                    dev_in[i % 2][k].copy_(host[k], non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
+    def step_e2e(i, last):
+        if not last:
+            prefetch(i + 1)
+        torch.cuda.current_stream().wait_event(ready[i % 2])
+        out = model(*[dev_in[i % 2][k] for k in names], opt=opt, mode="sample")
         res = [t.to("cpu", non_blocking=True) if t.is_cuda else t for t in out]
         torch.cuda.synchronize()
         return res
@@ -277,17 +292,16 @@ def main():
             stage_ms[name] = stage_ms.get(name, 0.0) + a.elapsed_time(b)
         model.stage_events = None
         # ---- timed region 2: end to end from pinned host memory -----------------------------------------------------
-        for _ in range(2):
-            res = step_e2e()
+        prefetch(0)
+        for i in range(2):
+            res = step_e2e(i, i == 1)
         barrier()
-        t0 = time.perf_counter()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for _ in range(args.steps):
-            res = step_e2e()
-        f1.record()
+        t_wall0 = time.perf_counter()
+        prefetch(2)                                            # all K host->device copies happen inside the timed region
+        for i in range(2, 2 + args.steps):
+            res = step_e2e(i, i == 1 + args.steps)
+        e2e_ms_total = (time.perf_counter() - t_wall0) * 1e3   # host wall clock: every step ends with a device synchronisation
         barrier()
-        e2e_ms_total = f0.elapsed_time(f1)
         d2h_bytes = sum(t.numel() * t.element_size() for t in res)
         clocks = sampler.stop() if sampler else None
 
@@ -318,7 +332,10 @@ def main():
         algo_bytes = algo_steps * (W_BYTES + n_rows * ROW_BYTES)
         achieved = algo_bytes / t_dec / 1e9
         line["roofline"] = {"bound": "hbm", "kernel": "decode loop (subgc_decode_sample: 20 x [att-LSTM, attention, lang-LSTM, logit, select])",
-                            "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                            "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                            "traffic": 4.85e9 if args.mode == "greedy" else None,
+                            "traffic_note": "sum of dram__bytes_read+write over the 160 launches of one decode loop from profiles/r01_ncu_decode_tc.md "
+                                            "(cold-cache replay: the 1.0 GB of split-K partial reads hit L2 in the live run)",
                             "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
                             "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": t_dec * 1e3,
                             "tensor_equiv": {"achieved_tflops": algo_steps * n_rows * ROW_FLOPS / t_dec / 1e12, "peak_tflops": tf_peak,

@@ -63,6 +63,7 @@ struct TcParams {
     int raw_hi;                  // 1 (default): the raw fp32 weight tile is the "hi" operand -- the tensor core reads only the tf32
                                  // bits, i.e. truncates (measured: same error as an explicit split) -- and only lo = w - trunc(w) is
                                  // written; 0 (SUBGC_TC_REWRITE_HI=1): hi = rn_tf32(w) is rewritten in place as well
+    int collect;                 // A-operand collector reuse for the X-hi tile (SUBGC_TC_NOCOLLECT=1 disables)
     int epi_mode;                // debug (SUBGC_TC_EPI=1: TMEM loads only, 2: stores only)
     long long* trace;            // debug (SUBGC_TC_TRACE=1): per-role clock64 stamps of CTA (0,0,0); nullptr in normal operation
 };
@@ -130,6 +131,28 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// same MMA with the A-operand collector hint: `fill` keeps the A tile in the tensor core's collector buffer, `lastuse` reuses it
+// (the X-hi tile feeds two consecutive MMAs: it is then read from shared memory once instead of twice)
+__device__ __forceinline__ void umma_tf32_afill(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32.collector::a::fill [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32_alast(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32.collector::a::lastuse [%0], %1, %2, %3, p;\n\t"
         "}\n" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
@@ -233,9 +256,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) umma_gemm_kernel(const __grid_c
                     // The two cross terms (2^-11 of the main term) therefore get their own accumulator: the main chain
                     // sees one add per K-step instead of three, and the cross chain's truncation is 2^-11 smaller.
                     const uint32_t acc = (i > 0 || ks > 0) ? 1u : 0u;
-                    umma_tf32(tmem_d, xhi, whi, idesc, acc);
-                    umma_tf32(tmem_d + TC_BN, xlo, whi, idesc, acc);
-                    umma_tf32(tmem_d + TC_BN, xhi, wlo, idesc, 1u);
+                    if (p.collect) {
+                        umma_tf32_afill(tmem_d, xhi, whi, idesc, acc);
+                        umma_tf32_alast(tmem_d + TC_BN, xhi, wlo, idesc, acc);
+                        umma_tf32(tmem_d + TC_BN, xlo, whi, idesc, 1u);
+                    } else {
+                        umma_tf32(tmem_d, xhi, whi, idesc, acc);
+                        umma_tf32(tmem_d + TC_BN, xlo, whi, idesc, acc);
+                        umma_tf32(tmem_d + TC_BN, xhi, wlo, idesc, 1u);
+                    }
                 }
                 umma_commit(bar_base + 64 + 8 * s);              // stage free once these MMAs have read it
                 if (i == nkb - 1) umma_commit(bar_base + 96);    // accumulator complete
@@ -593,6 +622,8 @@ int launch_gemm_tc(const GemmProblem& p, void* ws_, size_t ws_bytes, cudaStream_
     tp.raw_hi = raw_hi ? 1 : 0;
     static const int epi_mode = getenv("SUBGC_TC_EPI") ? atoi(getenv("SUBGC_TC_EPI")) : 0;
     tp.epi_mode = epi_mode;
+    static const bool collect = getenv("SUBGC_TC_NOCOLLECT") == nullptr;
+    tp.collect = collect ? 1 : 0;
     tp.trace = nullptr;
     if (trace_on) {
         if (!trace_buf) cudaMalloc(&trace_buf, 8 * TC_TRACE_SLOTS * sizeof(long long));

@@ -1,9 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_r01_tc.json 2> gpurun_out/bench_err.log
-tail -1 gpurun_out/bench_r01_tc.json | cut -c1-250
-SUBGC_NO_GRAPH=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_tc.csv \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
-SUBGC_NO_GRAPH=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"umma_gemm|attention_kernel|select_kernel|lstm_reduce" -s 60 -c 8 -f -o gpurun_out/prof_tc \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
-ls -la gpurun_out/*.ncu-rep
+timeout 180 python tools/gemm_check.py 2>&1 | grep "N=4000 K=4000\|N=1024\|N=9488"
+SUBGC_TC_NOCOLLECT=1 timeout 180 python tools/gemm_check.py 2>&1 | grep "N=4000 K=4000\|N=1024\|N=9488"
+timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider 2>&1 | tail -40 > gpurun_out/pytest_gpu.log
+grep -E "^(FAILED|ERROR)|passed|failed|rror" gpurun_out/pytest_gpu.log | head
+timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench.log 2>&1
+grep -o '"value": [0-9.]*' gpurun_out/bench.log | head -3; grep -o '"stage_ms_per_step[^}]*}' gpurun_out/bench.log; grep -o '"e2e": {[^}]*}' gpurun_out/bench.log
+SUBGC_TC_NOCOLLECT=1 timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>&1 | grep -o '"stage_ms_per_step[^}]*}'
