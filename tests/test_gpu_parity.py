@@ -281,3 +281,76 @@ def test_full_size_batch_properties():
     assert np.array_equal(t2n(seq[:2]), t2n(ref["seq"]))
     assert rel_err(t2n(lps[:2]), t2n(ref["seqLogprobs"])) <= RTOL
     assert rel_err(t2n(score[:2]), t2n(ref["subgraph_score"])) <= RTOL
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# decoding options and edge cases (oracle on fresh inputs)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("pen,constraint,beam", [("avg_0.0", 0, 2), ("wu_0.7", 1, 3), ("", 1, 4)])
+def test_beam_options_match_oracle(pen, constraint, beam):
+    d = SMALL
+    sd = synth.make_state_dict(d, 17, logit_gain=8.0, lstm_gain=3.0, eos_bias=0.6)
+    data = synth.make_test_inputs(d, 17, n_images=2, per_half=2, ragged=True, ragged_edges=True)
+    model = make_model(d, sd, gpn_nms_thres=0.9, gpn_max_subg=4)
+    with torch.no_grad():
+        ref = O.sample(sd, d, data, use_nms=True, iou_thres=0.9, max_subgraphs=4)
+        fc, att, p_att, masks = ref["p_fc"], ref["p_att"], ref["pp_att"], ref["p_masks"]
+        want = [O.beam_search_one(sd, d, fc[s:s + 1], att[s:s + 1], p_att[s:s + 1], masks[s:s + 1], beam, pen, constraint)
+                for s in range(fc.shape[0])]
+        seq, lps, _, _ = model(*synth.sample_args(to_dev(data)), opt={"beam_size": beam, "length_penalty": pen,
+                                                                     "decoding_constraint": constraint}, mode="sample")
+    assert len(model.done_beams) == len(want)
+    for got, exp in zip(model.done_beams, want):
+        assert len(got) == len(exp)
+        for a, b in zip(got, exp):
+            assert np.array_equal(t2n(a["seq"]), t2n(b["seq"]))
+            assert rel_err(t2n(a["logps"]), t2n(b["logps"])) <= RTOL
+            assert abs(a["p"] - b["p"]) <= 1e-5 * max(1.0, abs(b["p"]))
+    assert np.array_equal(t2n(seq), np.stack([t2n(w[0]["seq"]) for w in want]))
+
+
+def test_single_node_subgraphs_and_single_image():
+    """Shortest possible inputs: one image, sub-graphs of 3..36 nodes clipped by NMS to one survivor, and a graph with 2 edges."""
+    d = SMALL
+    sd = synth.make_state_dict(d, 23, logit_gain=8.0, lstm_gain=3.0)
+    data = synth.make_test_inputs(d, 23, n_images=1, per_half=1, ragged=True, ragged_edges=True)
+    # shrink the first sub-graph to a single node
+    data["gpn_obj_ind"][:, 0, 0, 1:] = d.obj_num - 1
+    data["att_masks"][:, 0, 0, 1:] = 0
+    data["gpn_pool_mtx"][:, 0, 0] = 0
+    data["gpn_pool_mtx"][:, 0, 0, 0, 0] = 1
+    model = make_model(d, sd, gpn_nms_thres=0.99, gpn_max_subg=2)
+    with torch.no_grad():
+        ref = O.sample(sd, d, data, use_nms=True, iou_thres=0.99, max_subgraphs=2, return_att=True)
+        seq, lps, score, keep, attw = model(*synth.sample_args(to_dev(data)), opt={"beam_size": 1, "return_att": 1}, mode="sample")
+    assert np.array_equal(t2n(keep), t2n(ref["keep_ind"])) and np.array_equal(t2n(seq), t2n(ref["seq"]))
+    assert rel_err(t2n(lps), t2n(ref["seqLogprobs"])) <= RTOL and rel_err(t2n(attw), t2n(ref["att_weights"])) <= RTOL
+    assert rel_err(t2n(score), t2n(ref["subgraph_score"])) <= RTOL
+
+
+def test_early_exit_when_every_caption_finishes():
+    """eos_bias large: all rows emit token 0 at some step; the loop must stop exactly where the reference stops."""
+    d = SMALL
+    sd = synth.make_state_dict(d, 29, logit_gain=2.0, eos_bias=6.0)
+    data = synth.make_test_inputs(d, 29, n_images=2, per_half=2, ragged=True)
+    model = make_model(d, sd, gpn_nms_thres=0.9, gpn_max_subg=4)
+    with torch.no_grad():
+        ref = O.sample(sd, d, data, use_nms=True, iou_thres=0.9, max_subgraphs=4, return_att=True)
+        seq, lps, _, _, attw = model(*synth.sample_args(to_dev(data)), opt={"beam_size": 1, "return_att": 1}, mode="sample")
+    assert ref["att_weights"].shape[1] < d.seq_length + 1            # the oracle really stopped early
+    assert tuple(attw.shape) == tuple(ref["att_weights"].shape)
+    assert np.array_equal(t2n(seq), t2n(ref["seq"])) and rel_err(t2n(lps), t2n(ref["seqLogprobs"])) <= RTOL
+    assert int(model.last_steps.item()) == ref["att_weights"].shape[1]
+
+
+def test_topk_k1_equals_greedy_tokens():
+    d = SMALL
+    sd = synth.make_state_dict(d, 31, logit_gain=8.0, lstm_gain=3.0)
+    data = to_dev(synth.make_test_inputs(d, 31, n_images=2, per_half=2, ragged=True))
+    model = make_model(d, sd, gpn_nms_thres=0.9, gpn_max_subg=4)
+    with torch.no_grad():
+        seq_g, _, _, _ = model(*synth.sample_args(data), opt={"beam_size": 1}, mode="sample")
+        model.topk_sampling, model.the_k, model.topk_temp = True, 1, 0.6
+        seq_k, lps_k, _, _ = model(*synth.sample_args(data), opt={"beam_size": 1}, mode="sample")
+        model.topk_sampling = False
+    assert torch.equal(seq_g, seq_k) and (lps_k <= 0).all()
