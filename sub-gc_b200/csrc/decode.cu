@@ -12,9 +12,13 @@
 // warp-shuffle reductions) -> lang-LSTM gates -> LSTM cell -> logit.  The loops keep token feedback, finish masks,
 // the all-finished early exit and (for beam search) candidate ranking, history / state re-ordering and the
 // done-beam lists on the device: no host synchronisation anywhere, the whole loop is graph-capturable.
+#include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace subgc {
 
@@ -23,7 +27,10 @@ namespace subgc {
 __global__ void __launch_bounds__(256) lstm_reduce_cell_kernel(const float* __restrict__ part, int splits, const float* __restrict__ b_ih,
                                                                const float* __restrict__ b_hh, const float* __restrict__ c_prev,
                                                                const long long* __restrict__ parent, float* __restrict__ h_out,
-                                                               float* __restrict__ c_out, int S, int H, const int* __restrict__ active) {
+                                                               float* __restrict__ c_out, int S, int H, const int* __restrict__ active,
+                                                               const float* __restrict__ addend, int add_div) {
+    // addend != nullptr: a pre-computed [S / add_div, 4H] term (the step-invariant fc segment with both biases folded in)
+    // replaces b_ih + b_hh
     if (active != nullptr && *active == 0) return;
     const size_t zs = (size_t)S * 4 * H;
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -36,8 +43,14 @@ __global__ void __launch_bounds__(256) lstm_reduce_cell_kernel(const float* __re
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[q] += g[(size_t)z * zs + (size_t)q * H];
     }
+    if (addend) {
+        const float* a = addend + (size_t)(r / add_div) * 4 * H + j;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) acc[q] = (acc[q] + __ldg(b_ih + q * H + j)) + __ldg(b_hh + q * H + j);
+        for (int q = 0; q < 4; ++q) acc[q] += a[(size_t)q * H];
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] = (acc[q] + __ldg(b_ih + q * H + j)) + __ldg(b_hh + q * H + j);
+    }
     long long pr = parent ? parent[r] : r;
     float c = sigmoidf_(acc[1]) * c_prev[(size_t)pr * H + j] + sigmoidf_(acc[0]) * tanhf(acc[2]);
     c_out[idx] = c;
@@ -50,27 +63,13 @@ __global__ void __launch_bounds__(256) lstm_reduce_cell_kernel(const float* __re
 constexpr int kAttThreads = 1024;  // one block per row; the row is latency-bound (28 MB of att / p_att per step over 128 rows), so every
                                    // warp slot of the SM is used to keep loads in flight
 
-__global__ void __launch_bounds__(kAttThreads) attention_kernel(const float* __restrict__ atth_part, int splits, const float* __restrict__ h2att_b,
-                                                                const float* __restrict__ p_att, const float* __restrict__ att,
-                                                                const float* __restrict__ masks, const float* __restrict__ alpha_w,
-                                                                const float* __restrict__ alpha_b, float* __restrict__ ctx, float* __restrict__ att_w,
-                                                                int att_w_stride, int S, int len_max, int H, int AH, int rows_per_ctx,
-                                                                const int* __restrict__ active) {
-    if (active != nullptr && *active == 0) return;
-    extern __shared__ float s_att[];  // [AH] atth | [AH] alpha_w | [64] e | [4][H] context partials
-    float* s_h = s_att;
-    float* s_w = s_att + AH;
-    float* s_e = s_att + 2 * AH;
-    float* s_c = s_att + 2 * AH + 64;
-    const int r = blockIdx.x, cr = r / rows_per_ctx;
+// body shared by attention_kernel and the fused att-phase kernel: expects s_h (atth of this row) and s_w (alpha_net weight)
+// filled and synchronised
+__device__ __forceinline__ void attention_row_body(float* s_h, float* s_w, float* s_e, float* s_c, int r, int cr, const float* __restrict__ p_att,
+                                                   const float* __restrict__ att, const float* __restrict__ masks,
+                                                   const float* __restrict__ alpha_b, float* __restrict__ ctx, float* __restrict__ att_w,
+                                                   int att_w_stride, int len_max, int H, int AH) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int j = threadIdx.x; j < AH; j += blockDim.x) {
-        float a = 0.f;
-        for (int z = 0; z < splits; ++z) a += atth_part[((size_t)z * S + r) * AH + j];
-        s_h[j] = a + __ldg(h2att_b + j);
-        s_w[j] = __ldg(alpha_w + j);
-    }
-    __syncthreads();
     const float* pa = p_att + (size_t)cr * len_max * AH;
     if ((AH & 3) == 0) {
         const int AH4 = AH >> 2;
@@ -145,6 +144,134 @@ __global__ void __launch_bounds__(kAttThreads) attention_kernel(const float* __r
     }
     __syncthreads();
     for (int j = threadIdx.x; j < H; j += blockDim.x) ctx[(size_t)r * H + j] = ((s_c[j] + s_c[H + j]) + s_c[2 * H + j]) + s_c[3 * H + j];
+}
+
+__global__ void __launch_bounds__(kAttThreads) attention_kernel(const float* __restrict__ atth_part, int splits, const float* __restrict__ h2att_b,
+                                                                const float* __restrict__ p_att, const float* __restrict__ att,
+                                                                const float* __restrict__ masks, const float* __restrict__ alpha_w,
+                                                                const float* __restrict__ alpha_b, float* __restrict__ ctx, float* __restrict__ att_w,
+                                                                int att_w_stride, int S, int len_max, int H, int AH, int rows_per_ctx,
+                                                                const int* __restrict__ active) {
+    if (active != nullptr && *active == 0) return;
+    extern __shared__ float s_att[];  // [AH] atth | [AH] alpha_w | [64] e | [4][H] context partials
+    float* s_h = s_att;
+    float* s_w = s_att + AH;
+    float* s_e = s_att + 2 * AH;
+    float* s_c = s_att + 2 * AH + 64;
+    const int r = blockIdx.x, cr = r / rows_per_ctx;
+    for (int j = threadIdx.x; j < AH; j += blockDim.x) {
+        float a = 0.f;
+        for (int z = 0; z < splits; ++z) a += atth_part[((size_t)z * S + r) * AH + j];
+        s_h[j] = a + __ldg(h2att_b + j);
+        s_w[j] = __ldg(alpha_w + j);
+    }
+    __syncthreads();
+    attention_row_body(s_h, s_w, s_e, s_c, r, cr, p_att, att, masks, alpha_b, ctx, att_w, att_w_stride, len_max, H, AH);
+}
+
+// ---- fused attention phase of a decode step: one cooperative kernel instead of cell + h2att GEMM + attention ---------------
+// The three stages are tiny but strictly dependent (att-LSTM cell -> W_h h_att -> attention); as separate kernels they cost
+// three launch / fill / tail latencies (~40 us).  Here block r (one per decode row, all co-resident: cooperative launch)
+//   1. reduces the att-LSTM split-K partials of row r and applies the LSTM cell              -> h_att[r], c_att[r]
+//   -- grid barrier --
+//   2. computes atth[:, cols_r] = h_att . W_h[cols_r]^T + b_h for its slice of <= 4 output columns (all rows; W_h rows in smem)
+//   -- grid barrier --
+//   3. runs the attention of row r (tanh / alpha / softmax / mask / renormalise / context)     -> ctx[r]
+struct AttPhaseArgs {
+    const float* part; int splits;               // att-LSTM gate partials [splits][S][4H]
+    const float* b_ih; const float* b_hh;        // used when fc_pre == nullptr
+    const float* fc_pre;                         // [S, 4H] hoisted fc segment + biases (nullable)
+    const float* c_prev; float* h_out; float* c_out;   // layer-0 state rows [S, H]
+    const float* w_h; const float* b_h;          // h2att [AH, H], [AH]
+    float* atth;                                 // [S, AH] scratch
+    const float* p_att; const float* att; const float* masks; const float* alpha_w; const float* alpha_b;
+    float* ctx; float* att_w; int att_w_stride;
+    int S, len_max, H, AH, cols_per_block;
+    const int* active;
+};
+
+__global__ void __launch_bounds__(kAttThreads, 1) att_phase_kernel(const AttPhaseArgs a) {
+    if (a.active != nullptr && *a.active == 0) return;   // uniform across the grid: nobody reaches the barriers
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ float s_att[];  // [AH] atth | [AH] alpha_w | [64] e | [4][H] context partials (stage 2: W_h rows)
+    float* s_h = s_att;
+    float* s_w = s_att + a.AH;
+    float* s_e = s_att + 2 * a.AH;
+    float* s_c = s_att + 2 * a.AH + 64;
+    const int r = blockIdx.x, H = a.H, AH = a.AH, S = a.S;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    // The row's attention operands (p_att 74 KB, att 144 KB) do not depend on this step: ask for them in L2 now, they are
+    // evicted by the weight streams between steps and stage 3 is otherwise a chain of DRAM-latency rounds.
+    {
+        const char* pa = reinterpret_cast<const char*>(a.p_att + (size_t)r * a.len_max * AH);
+        const char* af = reinterpret_cast<const char*>(a.att + (size_t)r * a.len_max * H);
+        const size_t nb_p = (size_t)a.len_max * AH * 4, nb_a = (size_t)a.len_max * H * 4;
+        for (size_t o = (size_t)threadIdx.x * 128; o < nb_p; o += (size_t)blockDim.x * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + o));
+        for (size_t o = (size_t)threadIdx.x * 128; o < nb_a; o += (size_t)blockDim.x * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(af + o));
+    }
+    // ---- 1. split-K reduce + biases + LSTM cell of row r
+    {
+        const size_t zs = (size_t)S * 4 * H;
+        for (int j = threadIdx.x; j < H; j += blockDim.x) {
+            const float* g = a.part + (size_t)r * 4 * H + j;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 9
+            for (int z = 0; z < a.splits; ++z) {   // all splits' loads in flight at once
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[q] += g[(size_t)z * zs + (size_t)q * H];
+            }
+            if (a.fc_pre) {
+                const float* ad = a.fc_pre + (size_t)r * 4 * H + j;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[q] += ad[(size_t)q * H];
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[q] = (acc[q] + __ldg(a.b_ih + q * H + j)) + __ldg(a.b_hh + q * H + j);
+            }
+            const float c = sigmoidf_(acc[1]) * a.c_prev[(size_t)r * H + j] + sigmoidf_(acc[0]) * tanhf(acc[2]);
+            a.c_out[(size_t)r * H + j] = c;
+            a.h_out[(size_t)r * H + j] = sigmoidf_(acc[3]) * tanhf(c);
+        }
+    }
+    grid.sync();
+    // ---- 2. h2att for this block's column slice, all rows
+    {
+        const int c0 = r * a.cols_per_block;
+        const int nc = max(0, min(a.cols_per_block, AH - c0));
+        for (int idx = threadIdx.x; idx < nc * H; idx += blockDim.x) s_c[idx] = __ldg(a.w_h + (size_t)c0 * H + idx);
+        __syncthreads();
+        if (nc > 0) {
+            for (int row = wid; row < S; row += nw) {
+                const float* hr = a.h_out + (size_t)row * H;   // written in stage 1 by block `row` (plain loads: not the read-only path)
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int k0 = lane; k0 < H; k0 += 32 * 8) {   // 8 independent loads in flight per lane (the loop is latency-bound)
+                    float hv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) hv[u] = (k0 + 32 * u < H) ? hr[k0 + 32 * u] : 0.f;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int k = min(k0 + 32 * u, H - 1);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            if (c < nc) acc[c] = fmaf(hv[u], s_c[c * H + k], acc[c]);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float v = warp_sum(acc[c]);
+                    if (lane == 0 && c < nc) a.atth[(size_t)row * AH + c0 + c] = v + __ldg(a.b_h + c0 + c);
+                }
+            }
+        }
+    }
+    grid.sync();
+    // ---- 3. attention of row r
+    for (int j = threadIdx.x; j < AH; j += blockDim.x) {
+        s_h[j] = a.atth[(size_t)r * AH + j];
+        s_w[j] = __ldg(a.alpha_w + j);
+    }
+    __syncthreads();
+    attention_row_body(s_h, s_w, s_e, s_c, r, r, a.p_att, a.att, a.masks, a.alpha_b, a.ctx, a.att_w, a.att_w_stride, a.len_max, H, AH);
 }
 
 // ---- row-wise log_softmax (materialised log-probs: get_logprobs_state API and beam search) ----------------------
@@ -375,6 +502,28 @@ static bool take_step_scratch(const subgc_dims* d, int S, Workspace& ws, StepScr
     return ws.ok();
 }
 
+// Ablation aid (timing experiments only, results are wrong when set): SUBGC_SKIP = bitmask of decode-step kernels NOT to launch:
+// 1 att-LSTM GEMM, 2 att cell / fused att phase, 4 h2att GEMM, 8 attention, 16 lang GEMM, 32 lang cell, 64 logit GEMM, 128 select
+static int skip_mask() {
+    static int m = -1;
+    if (m < 0) { const char* e = getenv("SUBGC_SKIP"); m = e ? atoi(e) : 0; }
+    return m;
+}
+
+// The fused att-phase kernel needs every block co-resident (grid barriers): one 1024-thread block per SM.
+static bool att_phase_fusable(int S, int cols_per_block, size_t smem) {
+    static int mode = -1, sms = 0, coop = 0;
+    if (mode < 0) {
+        const char* e = getenv("SUBGC_NO_FUSED_ATT");
+        mode = (e && e[0] == '1') ? 0 : 1;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    }
+    return mode == 1 && coop && S <= sms && cols_per_block <= 4 && smem <= 48 * 1024;
+}
+
 // upto: 0 = whole step, 1 = stop after the attention (the reference's discarded last step, only its attention
 // weights are observable).  parent (nullable) re-maps the previous-state rows (beam re-ordering).
 // raw_logits != nullptr: the logit contraction leaves its split-K partials (no bias) for a fused consumer
@@ -382,41 +531,65 @@ static bool take_step_scratch(const subgc_dims* d, int S, Workspace& ws, StepScr
 static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int len_max, int rows_per_ctx, const long long* it, const float* xt,
                        const long long* parent, const float* fc, const float* att, const float* p_att, const float* masks,
                        const float* h_in, const float* c_in, float* h_out, float* c_out, float* logits, RawPartials* raw_logits, float* att_w,
-                       int att_w_stride, const StepScratch& sc, const int* active, int upto, cudaStream_t st) {
+                       int att_w_stride, const StepScratch& sc, const int* active, int upto, cudaStream_t st, const float* fc_pre = nullptr) {
+    // fc_pre != nullptr: W_ih[:, H:2H] fc + b_ih + b_hh was computed once for the whole loop (launch_fc_pre): the fc segment
+    // (a quarter of the att-LSTM weights) is not streamed again at every step
     const int H = d->rnn, X = d->enc, AH = d->att_hid, V1 = d->vocab1;
     const size_t SH = (size_t)S * H;
     const int pw_blocks = (int)((SH + 255) / 256);
     GemmProblem p;
     RawPartials rp;
     // attention LSTM: gates = W_ih [h_lang | fc | relu(E[it])] + b_ih + W_hh h_att + b_hh   (AttModel.py:410-413)
-    p.M = S; p.N = 4 * H; p.nseg = 4;
-    p.seg[0] = make_seg(h_in + SH, H, w->att_w_ih, X + 2 * H, H);
-    p.seg[0].gather = parent;
-    p.seg[1] = make_seg(fc, H, w->att_w_ih + H, X + 2 * H, H);
-    p.seg[1].a_row_div = rows_per_ctx;
-    if (xt) {  // relu(E[it]) already materialised by the previous step's selection kernel
-        p.seg[2] = make_seg(xt, X, w->att_w_ih + 2 * H, X + 2 * H, X);
-    } else {
-        p.seg[2] = make_seg(w->embed, X, w->att_w_ih + 2 * H, X + 2 * H, X);
-        p.seg[2].gather = it;
-        p.seg[2].relu_a = 1;
+    p.M = S; p.N = 4 * H;
+    int ns = 0;
+    p.seg[ns] = make_seg(h_in + SH, H, w->att_w_ih, X + 2 * H, H);
+    p.seg[ns++].gather = parent;
+    if (!fc_pre) {
+        p.seg[ns] = make_seg(fc, H, w->att_w_ih + H, X + 2 * H, H);
+        p.seg[ns++].a_row_div = rows_per_ctx;
     }
-    p.seg[3] = make_seg(h_in, H, w->att_w_hh, H, H);
-    p.seg[3].gather = parent;
+    if (xt) {  // relu(E[it]) already materialised by the previous step's selection kernel
+        p.seg[ns++] = make_seg(xt, X, w->att_w_ih + 2 * H, X + 2 * H, X);
+    } else {
+        p.seg[ns] = make_seg(w->embed, X, w->att_w_ih + 2 * H, X + 2 * H, X);
+        p.seg[ns].gather = it;
+        p.seg[ns++].relu_a = 1;
+    }
+    p.seg[ns] = make_seg(h_in, H, w->att_w_hh, H, H);
+    p.seg[ns++].gather = parent;
+    p.nseg = ns;
     p.active = active;
-    SUBGC_TRY(launch_gemm_raw(p, sc.gemm_ws, sc.gemm_ws_bytes, st, &rp));
-    lstm_reduce_cell_kernel<<<pw_blocks, 256, 0, st>>>(rp.part, rp.splits, w->att_b_ih, w->att_b_hh, c_in, parent, h_out, c_out, S, H, active);
-    SUBGC_LAUNCH_CHECK();
-    // attention (AttModel.py:445-471); the h2att partials are reduced inside the attention kernel
-    p = GemmProblem();
-    p.M = S; p.N = AH; p.nseg = 1;
-    p.seg[0] = make_seg(h_out, H, w->h2att.w, H, H);
-    p.active = active;
-    SUBGC_TRY(launch_gemm_raw(p, sc.gemm_ws, sc.gemm_ws_bytes, st, &rp));
+    const int skip = skip_mask();
+    rp.part = static_cast<const float*>(sc.gemm_ws); rp.splits = 1;
+    if (!(skip & 1)) SUBGC_TRY(launch_gemm_raw(p, sc.gemm_ws, sc.gemm_ws_bytes, st, &rp));
     size_t smem = (size_t)(2 * AH + 64 + 4 * H) * sizeof(float);
-    attention_kernel<<<S, kAttThreads, smem, st>>>(rp.part, rp.splits, w->h2att.b, p_att, att, masks, w->alpha_net.w, w->alpha_net.b, sc.ctx, att_w,
-                                           att_w_stride, S, len_max, H, AH, rows_per_ctx, active);
-    SUBGC_LAUNCH_CHECK();
+    const int cpb = (AH + S - 1) / S;
+    if (att_phase_fusable(S, cpb, smem) && parent == nullptr && rows_per_ctx == 1) {
+        // cell + h2att + attention as one cooperative kernel (one block per row, two grid barriers)
+        AttPhaseArgs fa;
+        fa.part = rp.part; fa.splits = rp.splits; fa.b_ih = w->att_b_ih; fa.b_hh = w->att_b_hh; fa.fc_pre = fc_pre; fa.c_prev = c_in;
+        fa.h_out = h_out; fa.c_out = c_out; fa.w_h = w->h2att.w; fa.b_h = w->h2att.b; fa.atth = sc.atth; fa.p_att = p_att; fa.att = att;
+        fa.masks = masks; fa.alpha_w = w->alpha_net.w; fa.alpha_b = w->alpha_net.b; fa.ctx = sc.ctx; fa.att_w = att_w;
+        fa.att_w_stride = att_w_stride; fa.S = S; fa.len_max = len_max; fa.H = H; fa.AH = AH; fa.cols_per_block = cpb; fa.active = active;
+        void* kargs[] = {&fa};
+        if (!(skip & 2)) {
+            SUBGC_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(att_phase_kernel), dim3(S), dim3(kAttThreads), kargs, smem, st));
+            count_launch();
+        }
+    } else {
+        if (!(skip & 2)) lstm_reduce_cell_kernel<<<pw_blocks, 256, 0, st>>>(rp.part, rp.splits, w->att_b_ih, w->att_b_hh, c_in, parent, h_out, c_out, S,
+                                                                            H, active, fc_pre, rows_per_ctx);
+        SUBGC_LAUNCH_CHECK();
+        // attention (AttModel.py:445-471); the h2att partials are reduced inside the attention kernel
+        p = GemmProblem();
+        p.M = S; p.N = AH; p.nseg = 1;
+        p.seg[0] = make_seg(h_out, H, w->h2att.w, H, H);
+        p.active = active;
+        if (!(skip & 4)) SUBGC_TRY(launch_gemm_raw(p, sc.gemm_ws, sc.gemm_ws_bytes, st, &rp));
+        if (!(skip & 8)) attention_kernel<<<S, kAttThreads, smem, st>>>(rp.part, rp.splits, w->h2att.b, p_att, att, masks, w->alpha_net.w, w->alpha_net.b,
+                                                                        sc.ctx, att_w, att_w_stride, S, len_max, H, AH, rows_per_ctx, active);
+        SUBGC_LAUNCH_CHECK();
+    }
     if (upto == 1) return SUBGC_OK;
     // language LSTM on [ctx | h_att] (AttModel.py:421-423)
     p = GemmProblem();
@@ -426,18 +599,32 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
     p.seg[2] = make_seg(h_in + SH, H, w->lang_w_hh, H, H);
     p.seg[2].gather = parent;
     p.active = active;
-    SUBGC_TRY(launch_gemm_raw(p, sc.gemm_ws, sc.gemm_ws_bytes, st, &rp));
-    lstm_reduce_cell_kernel<<<pw_blocks, 256, 0, st>>>(rp.part, rp.splits, w->lang_b_ih, w->lang_b_hh, c_in + SH, parent, h_out + SH,
-                                                       c_out + SH, S, H, active);
+    if (!(skip & 16)) SUBGC_TRY(launch_gemm_raw(p, sc.gemm_ws, sc.gemm_ws_bytes, st, &rp));
+    if (!(skip & 32)) lstm_reduce_cell_kernel<<<pw_blocks, 256, 0, st>>>(rp.part, rp.splits, w->lang_b_ih, w->lang_b_hh, c_in + SH, parent, h_out + SH,
+                                                                         c_out + SH, S, H, active, nullptr, 1);
     SUBGC_LAUNCH_CHECK();
     // logit (AttModel.py:336,340); eval mode: dropout is the identity
     p = GemmProblem();
     p.M = S; p.N = V1; p.nseg = 1;
     p.seg[0] = make_seg(h_out + SH, H, w->logit.w, H, H);
     p.active = active;
-    if (raw_logits) return launch_gemm_raw(p, sc.gemm_ws, sc.gemm_ws_bytes, st, raw_logits);
+    if (raw_logits) {
+        raw_logits->part = static_cast<const float*>(sc.gemm_ws); raw_logits->splits = 1;
+        return (skip & 64) ? SUBGC_OK : launch_gemm_raw(p, sc.gemm_ws, sc.gemm_ws_bytes, st, raw_logits);
+    }
     p.epi.bias = w->logit.b;
     p.C = logits; p.ldc = V1;
+    return launch_gemm(p, sc.gemm_ws, sc.gemm_ws_bytes, st);
+}
+
+// fc_pre[c, :] = W_ih[:, H:2H] fc[c] + b_ih + b_hh for every context row c (step-invariant part of the att-LSTM gates)
+static int launch_fc_pre(const subgc_dims* d, const subgc_weights* w, int n_ctx, const float* fc, const StepScratch& sc, cudaStream_t st) {
+    const int H = d->rnn, X = d->enc;
+    GemmProblem p;
+    p.M = n_ctx; p.N = 4 * H; p.nseg = 1;
+    p.seg[0] = make_seg(fc, H, w->att_w_ih + H, X + 2 * H, H);
+    p.epi.bias = w->att_b_ih; p.epi.bias2 = w->att_b_hh;
+    p.C = sc.gates; p.ldc = 4 * H;
     return launch_gemm(p, sc.gemm_ws, sc.gemm_ws_bytes, st);
 }
 
@@ -656,6 +843,7 @@ extern "C" int subgc_decode_sample(const subgc_dims* d, const subgc_weights* w, 
         SUBGC_CHECK_ARG((size_t)V1 * sizeof(float) <= 200 * 1024, "subgc_decode_sample: vocabulary too large for the selection kernel");
         SUBGC_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(V1 * sizeof(float))));
     }
+    SUBGC_TRY(launch_fc_pre(d, w, S, fc, sc, st));
     for (int t = 0; t <= T; ++t) {
         const int* active = (t == 0) ? nullptr : count + (t - 1);
         const int in = t & 1, out = in ^ 1;
@@ -665,18 +853,18 @@ extern "C" int subgc_decode_sample(const subgc_dims* d, const subgc_weights* w, 
             // weights are observable, so the step stops there (and is skipped entirely when they are not requested)
             if (att_weights)
                 SUBGC_TRY(launch_step(d, w, S, len_max, 1, it, t > 0 ? xt : nullptr, nullptr, fc, att, p_att, masks, hbuf[in], cbuf[in], hbuf[out], cbuf[out], logits,
-                                      nullptr, aw, (T + 1) * len_max, sc, active, 1, st));
+                                      nullptr, aw, (T + 1) * len_max, sc, active, 1, st, sc.gates));
             break;
         }
         RawPartials rl;
         SUBGC_TRY(launch_step(d, w, S, len_max, 1, it, t > 0 ? xt : nullptr, nullptr, fc, att, p_att, masks, hbuf[in], cbuf[in], hbuf[out], cbuf[out], logits, &rl, aw,
-                              (T + 1) * len_max, sc, active, 0, st));
+                              (T + 1) * len_max, sc, active, 0, st, sc.gates));
         SelectArgs a;
         a.logits = rl.part; a.splits = rl.splits; a.bias = w->logit.b; a.V1 = V1; a.T = T; a.t = t; a.S = S; a.mode = mode; a.temp = temp; a.top_k = top_k; a.seed = seed;
         a.offset = offset; a.uniforms = uniforms; a.it = it; a.unfinished = unfinished; a.seq = reinterpret_cast<long long*>(seq);
         a.seq_lp = seq_logprobs; a.count = count; a.active = active;
         a.embed = w->embed; a.xt = xt; a.X = d->enc;
-        select_kernel<<<S, kSelectThreads, (size_t)V1 * sizeof(float), st>>>(a);
+        if (!(skip_mask() & 128)) select_kernel<<<S, kSelectThreads, (size_t)V1 * sizeof(float), st>>>(a);
         SUBGC_LAUNCH_CHECK();
     }
     steps_done_kernel<<<1, 1, 0, st>>>(count, T, steps_done);
@@ -710,10 +898,11 @@ extern "C" int subgc_decode_teacher(const subgc_dims* d, const subgc_weights* w,
     SUBGC_CUDA(cudaMemsetAsync(outputs, 0, (size_t)S * n_steps * V1 * 4, st));  // steps after the early break stay zero
     teacher_columns_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const long long*>(tokens), ld_tok, S, n_steps, tok_cols, flags);
     SUBGC_LAUNCH_CHECK();
+    SUBGC_TRY(launch_fc_pre(d, w, S, fc, sc, st));
     for (int i = 0; i < n_steps; ++i) {
         const int in = i & 1, out = in ^ 1;
         SUBGC_TRY(launch_step(d, w, S, len_max, 1, tok_cols + (size_t)i * S, nullptr, nullptr, fc, att, p_att, masks, hbuf[in], cbuf[in], hbuf[out],
-                              cbuf[out], logits, nullptr, nullptr, 0, sc, flags + i, 0, st));
+                              cbuf[out], logits, nullptr, nullptr, 0, sc, flags + i, 0, st, sc.gates));
         log_softmax_kernel<<<S, 256, 0, st>>>(logits, outputs + (size_t)i * V1, V1, (size_t)n_steps * V1, flags + i);
         SUBGC_LAUNCH_CHECK();
     }
@@ -772,8 +961,9 @@ extern "C" int subgc_decode_beam(const subgc_dims* d, const subgc_weights* w, in
     SUBGC_CUDA(cudaMemsetAsync(done_p, 0, (size_t)S * 8, st));
     SUBGC_CUDA(cudaMemsetAsync(done_unaug_p, 0, (size_t)S * 8, st));
     // <bos> step on b identical rows per sub-graph (AttModel.py:216-227)
+    SUBGC_TRY(launch_fc_pre(d, w, n_sub, fc, sc, st));
     SUBGC_TRY(launch_step(d, w, S, len_max, b, it, nullptr, nullptr, fc, att, p_att, masks, hbuf[0], cbuf[0], hbuf[1], cbuf[1], logits, nullptr, nullptr,
-                          0, sc, nullptr, 0, st));
+                          0, sc, nullptr, 0, st, sc.gates));
     for (int t = 0; t < T; ++t) {
         BeamArgs a;
         a.logits = logits; a.V1 = V1; a.T = T; a.t = t; a.b = b; a.length_penalty = length_penalty; a.lp_alpha = lp_alpha;
@@ -787,7 +977,7 @@ extern "C" int subgc_decode_beam(const subgc_dims* d, const subgc_weights* w, in
         if (t == T - 1) break;  // the reference's final get_logprobs_state result is never read (CaptionModel.py:170-171)
         const int in = (t + 1) & 1, out = in ^ 1;
         SUBGC_TRY(launch_step(d, w, S, len_max, b, it, nullptr, parent, fc, att, p_att, masks, hbuf[in], cbuf[in], hbuf[out], cbuf[out], logits, nullptr,
-                              nullptr, 0, sc, nullptr, 0, st));
+                              nullptr, 0, sc, nullptr, 0, st, sc.gates));
     }
     return SUBGC_OK;
 }
