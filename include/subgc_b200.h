@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SUBGC_ABI_VERSION 1
+#define SUBGC_ABI_VERSION 2
 #define SUBGC_MAX_GCN_LAYERS 8
 
 typedef void* subgc_stream_t; /* cudaStream_t */
@@ -65,6 +65,17 @@ typedef struct subgc_linear {
     const float* b; /* [out] */
 } subgc_linear;
 
+/* Split-fp16 copy of one weight matrix for the tensor cores (subgc_pack_weight): w[r,c] = hi[r,c] + lo[r,c] * 2^-11 with
+ * hi, lo IEEE fp16, i.e. the same 4 bytes per weight as the fp32 tensor it mirrors and 22 of its 24 mantissa bits.
+ * The fp32 tensor stays the source of truth (and the lookup key): contractions whose weight pointer falls inside
+ * [w, w + rows*cols) read the packed copy instead; weights without one take the fp32 (split-TF32) path. */
+typedef struct subgc_packed {
+    const float* w;      /* the fp32 [rows, cols] contiguous tensor this was packed from */
+    const uint16_t* hi;  /* [rows, ld16] fp16 */
+    const uint16_t* lo;  /* [rows, ld16] fp16, scaled by 2^11 */
+    int32_t rows, cols, ld16;
+} subgc_packed;
+
 /* Device pointers to the reference state_dict tensors, un-repacked (key names in comments). */
 typedef struct subgc_weights {
     subgc_linear obj_v_proj;                           /* obj_v_proj.{weight[L,A],bias}                         */
@@ -90,6 +101,8 @@ typedef struct subgc_weights {
     const float* att_b_ih; const float* att_b_hh;
     const float* lang_w_ih; const float* lang_w_hh;    /* core.lang_lstm.weight_ih [4H,2H], weight_hh [4H,H]    */
     const float* lang_b_ih; const float* lang_b_hh;
+    const subgc_packed* packs;                         /* HOST array of packed copies (nullable)                 */
+    int32_t n_packs;
 } subgc_weights;
 
 /* How sub-graph s of a flat list maps onto the loader tensors gpn_obj_ind / att_masks [rows,2,per_half,N].
@@ -108,6 +121,14 @@ int subgc_version(void);
 /* kernels launched so far by the calling thread through this library (instrumentation for bench.py's gpu_launches) */
 unsigned long long subgc_launch_count(void);
 
+/* Packs an fp32 weight matrix [rows, cols] (leading dim ldw) into the split-fp16 form of subgc_packed; ld16 =
+ * subgc_pack_ld(cols) (cols rounded up to 8), each output array holds rows * ld16 fp16 values.  `overflow` (device,
+ * nullable) is OR-ed with 1 when a weight does not fit fp16 (|w| > 65504): such a tensor must not be registered.
+ * Replaces nothing in the reference: nn.Linear / nn.LSTMCell keep fp32 weights (models/AttModel.py:393-398). */
+int subgc_pack_ld(int cols);
+int subgc_pack_weight(int rows, int cols, const float* w, int ldw, uint16_t* hi, uint16_t* lo, int32_t* overflow,
+                      subgc_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Building block: C[M,N] = act((A[gather] . W^T + bias + addend) / div), the nn.Linear contraction every stage
  * of the path is made of (exported for unit tests; fp32 FMA accumulation).
@@ -116,6 +137,10 @@ size_t subgc_linear_workspace_bytes(int M, int N, int K);
 int subgc_linear_forward(int M, int N, int K, const float* A, int lda, const int64_t* a_gather /*nullable*/,
                          const float* W, int ldw, const float* bias /*nullable*/, int relu, float* C, int ldc,
                          void* ws, size_t ws_bytes, subgc_stream_t stream);
+/* Same contraction with the weight given as a packed copy (pk->w must be the [N,K] tensor itself): split-fp16 tensor-core path. */
+int subgc_linear_packed_forward(int M, int N, int K, const float* A, int lda, const int64_t* a_gather /*nullable*/,
+                                const subgc_packed* pk, const float* bias /*nullable*/, int relu, float* C, int ldc,
+                                void* ws, size_t ws_bytes, subgc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Encoder.

@@ -1,6 +1,7 @@
 // Internal helpers shared by the subgc_b200 translation units (not part of the C ABI).
 #pragma once
 
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -84,12 +85,21 @@ struct GemmSeg {
     int a_row_div;           // A row = m / a_row_div (rows shared by consecutive outputs; 1 = identity)
     int relu_a;              // apply ReLU to A elements on load (embed + ReLU)
     const int* gather32;     // optional 32-bit variant of `gather` (sub-graph selections)
+    // split-fp16 operands of the h3 tensor-core path (h3_gemm.cu): v = hi + lo * 2^-11, both fp16.  W16_* come from a packed copy
+    // of the weight tensor (subgc_pack_weight, resolved by resolve_packs); A16_* are optional pre-split activations written by
+    // the producer kernel (rows 1:1 with the output rows), otherwise the launcher splits A itself.
+    const unsigned short* W16_hi = nullptr;
+    const unsigned short* W16_lo = nullptr;
+    int ldw16 = 0;
+    const unsigned short* A16_hi = nullptr;
+    const unsigned short* A16_lo = nullptr;
+    int lda16 = 0;
 };
 
 inline GemmSeg make_seg(const float* A, int lda, const float* W, int ldw, int K) {
     GemmSeg s;
     s.A = A; s.W = W; s.gather = nullptr; s.lda = lda; s.ldw = ldw; s.K = K; s.a_row_div = 1; s.relu_a = 0; s.gather32 = nullptr;
-    return s;
+    return s;  // the split-fp16 fields default to null
 }
 
 struct GemmEpilogue {
@@ -117,6 +127,7 @@ struct GemmProblem {
     float* C = nullptr;
     int ldc = 0;
     const int* active = nullptr;  // optional device flag: kernel exits immediately when *active == 0
+    const subgc_weights* wts = nullptr;  // when set, segments whose weight has a packed copy there take the split-fp16 path
 };
 
 size_t gemm_workspace_bytes(int M, int N, int Ktotal);
@@ -131,6 +142,12 @@ bool tc_eligible(const GemmProblem& p);
 size_t tc_workspace_bytes(int M, int N, int Ktotal);
 struct RawPartials { const float* part; int splits; };  // [splits][M][N] partial sums, to be added in z order
 int launch_gemm_tc(const GemmProblem& p, void* ws, size_t ws_bytes, cudaStream_t stream, RawPartials* raw = nullptr);
+// tensor-core (tcgen05, split-fp16 "h3") variant for weights that have a packed copy, h3_gemm.cu
+bool h3_eligible(const GemmProblem& p);
+int launch_gemm_h3(const GemmProblem& p, void* ws, size_t ws_bytes, cudaStream_t stream, RawPartials* raw = nullptr);
+// fills W16_hi / W16_lo of every segment whose weight pointer lies inside a packed tensor of `w` (no-op without packs)
+void resolve_packs(GemmProblem& p, const subgc_weights* w);
+void* tc_encode_fn();  // cuTensorMapEncodeTiled through the runtime's driver entry point (nullptr when unavailable)
 // contraction without epilogue: the partial sums stay in `ws` for a consumer kernel that reduces them itself
 int launch_gemm_raw(const GemmProblem& p, void* ws, size_t ws_bytes, cudaStream_t stream, RawPartials* raw);
 // upper bound of splits * M * N floats for launch_gemm_ex raw partials
@@ -191,6 +208,24 @@ __device__ __forceinline__ void block_argmax(float& v, int& i, float* redv /*[32
     for (int w = 1; w < nw; ++w) argmax_combine(v, i, redv[w], redi[w]);
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// fp32 -> split fp16 (h3 operands): v = hi + lo * 2^-11.  Values beyond the fp16 range saturate and raise ovf.
+constexpr float kH3LoScale = 2048.f;
+constexpr float kH3LoInv = 1.f / 2048.f;
+__device__ __forceinline__ void split_f16(float v, unsigned short& hi, unsigned short& lo, int& ovf) {
+    const float c = fminf(fmaxf(v, -65504.f), 65504.f);
+    if (!(c == v)) ovf = 1;                      // out of range or NaN
+    const __half h = __float2half_rn(c);
+    const float r = (c - __half2float(h)) * kH3LoScale;   // exact in fp32
+    hi = __half_as_ushort(h);
+    lo = __half_as_ushort(__float2half_rn(r));
+}
+__device__ __forceinline__ void split_f16_store(float v, unsigned short* hi, unsigned short* lo, size_t idx) {
+    int ovf = 0;
+    unsigned short h, l;
+    split_f16(v, h, l, ovf);
+    hi[idx] = h;
+    lo[idx] = l;
+}
 // bias / addend / divide / ReLU / zero-padding part of the contraction epilogue (accumulate-into-C is applied by the caller)
 __device__ __forceinline__ float epilogue_apply(const GemmEpilogue& e, float v, int m, int n) {
     if (e.bias) v += __ldg(e.bias + n);

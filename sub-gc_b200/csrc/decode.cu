@@ -28,7 +28,9 @@ __global__ void __launch_bounds__(256) lstm_reduce_cell_kernel(const float* __re
                                                                const float* __restrict__ b_hh, const float* __restrict__ c_prev,
                                                                const long long* __restrict__ parent, float* __restrict__ h_out,
                                                                float* __restrict__ c_out, int S, int H, const int* __restrict__ active,
-                                                               const float* __restrict__ addend, int add_div) {
+                                                               const float* __restrict__ addend, int add_div,
+                                                               unsigned short* __restrict__ h16_hi, unsigned short* __restrict__ h16_lo, int Hp) {
+    // h16_hi / h16_lo (nullable, [S, Hp]): the split-fp16 copy of h' the next contractions read as their activation operand
     // addend != nullptr: a pre-computed [S / add_div, 4H] term (the step-invariant fc segment with both biases folded in)
     // replaces b_ih + b_hh
     if (active != nullptr && *active == 0) return;
@@ -54,7 +56,9 @@ __global__ void __launch_bounds__(256) lstm_reduce_cell_kernel(const float* __re
     long long pr = parent ? parent[r] : r;
     float c = sigmoidf_(acc[1]) * c_prev[(size_t)pr * H + j] + sigmoidf_(acc[0]) * tanhf(acc[2]);
     c_out[idx] = c;
-    h_out[idx] = sigmoidf_(acc[3]) * tanhf(c);
+    const float hv = sigmoidf_(acc[3]) * tanhf(c);
+    h_out[idx] = hv;
+    if (h16_hi) split_f16_store(hv, h16_hi, h16_lo, (size_t)r * Hp + j);
 }
 
 // ---- fused attention: one block per decode row -------------------------------------------------------------------
@@ -68,7 +72,8 @@ constexpr int kAttThreads = 1024;  // one block per row; the row is latency-boun
 __device__ __forceinline__ void attention_row_body(float* s_h, float* s_w, float* s_e, float* s_c, int r, int cr, const float* __restrict__ p_att,
                                                    const float* __restrict__ att, const float* __restrict__ masks,
                                                    const float* __restrict__ alpha_b, float* __restrict__ ctx, float* __restrict__ att_w,
-                                                   int att_w_stride, int len_max, int H, int AH) {
+                                                   int att_w_stride, int len_max, int H, int AH, unsigned short* __restrict__ c16_hi,
+                                                   unsigned short* __restrict__ c16_lo, int Hp) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const float* pa = p_att + (size_t)cr * len_max * AH;
     if ((AH & 3) == 0) {
@@ -143,7 +148,11 @@ __device__ __forceinline__ void attention_row_body(float* s_h, float* s_w, float
         }
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < H; j += blockDim.x) ctx[(size_t)r * H + j] = ((s_c[j] + s_c[H + j]) + s_c[2 * H + j]) + s_c[3 * H + j];
+    for (int j = threadIdx.x; j < H; j += blockDim.x) {
+        const float cv = ((s_c[j] + s_c[H + j]) + s_c[2 * H + j]) + s_c[3 * H + j];
+        ctx[(size_t)r * H + j] = cv;
+        if (c16_hi) split_f16_store(cv, c16_hi, c16_lo, (size_t)r * Hp + j);
+    }
 }
 
 __global__ void __launch_bounds__(kAttThreads) attention_kernel(const float* __restrict__ atth_part, int splits, const float* __restrict__ h2att_b,
@@ -151,7 +160,8 @@ __global__ void __launch_bounds__(kAttThreads) attention_kernel(const float* __r
                                                                 const float* __restrict__ masks, const float* __restrict__ alpha_w,
                                                                 const float* __restrict__ alpha_b, float* __restrict__ ctx, float* __restrict__ att_w,
                                                                 int att_w_stride, int S, int len_max, int H, int AH, int rows_per_ctx,
-                                                                const int* __restrict__ active) {
+                                                                const int* __restrict__ active, unsigned short* __restrict__ c16_hi,
+                                                                unsigned short* __restrict__ c16_lo, int Hp) {
     if (active != nullptr && *active == 0) return;
     extern __shared__ float s_att[];  // [AH] atth | [AH] alpha_w | [64] e | [4][H] context partials
     float* s_h = s_att;
@@ -166,7 +176,7 @@ __global__ void __launch_bounds__(kAttThreads) attention_kernel(const float* __r
         s_w[j] = __ldg(alpha_w + j);
     }
     __syncthreads();
-    attention_row_body(s_h, s_w, s_e, s_c, r, cr, p_att, att, masks, alpha_b, ctx, att_w, att_w_stride, len_max, H, AH);
+    attention_row_body(s_h, s_w, s_e, s_c, r, cr, p_att, att, masks, alpha_b, ctx, att_w, att_w_stride, len_max, H, AH, c16_hi, c16_lo, Hp);
 }
 
 // ---- fused attention phase of a decode step: one cooperative kernel instead of cell + h2att GEMM + attention ---------------
@@ -188,6 +198,8 @@ struct AttPhaseArgs {
     float* ctx; float* att_w; int att_w_stride;
     int S, len_max, H, AH, cols_per_block;
     const int* active;
+    unsigned short *h16_hi, *h16_lo, *c16_hi, *c16_lo;   // nullable split-fp16 copies of h_att / ctx, [S, Hp]
+    int Hp;
 };
 
 __global__ void __launch_bounds__(kAttThreads, 1) att_phase_kernel(const AttPhaseArgs a) {
@@ -230,7 +242,9 @@ __global__ void __launch_bounds__(kAttThreads, 1) att_phase_kernel(const AttPhas
             }
             const float c = sigmoidf_(acc[1]) * a.c_prev[(size_t)r * H + j] + sigmoidf_(acc[0]) * tanhf(acc[2]);
             a.c_out[(size_t)r * H + j] = c;
-            a.h_out[(size_t)r * H + j] = sigmoidf_(acc[3]) * tanhf(c);
+            const float hv = sigmoidf_(acc[3]) * tanhf(c);
+            a.h_out[(size_t)r * H + j] = hv;
+            if (a.h16_hi) split_f16_store(hv, a.h16_hi, a.h16_lo, (size_t)r * a.Hp + j);
         }
     }
     grid.sync();
@@ -271,7 +285,8 @@ __global__ void __launch_bounds__(kAttThreads, 1) att_phase_kernel(const AttPhas
         s_w[j] = __ldg(a.alpha_w + j);
     }
     __syncthreads();
-    attention_row_body(s_h, s_w, s_e, s_c, r, r, a.p_att, a.att, a.masks, a.alpha_b, a.ctx, a.att_w, a.att_w_stride, a.len_max, H, AH);
+    attention_row_body(s_h, s_w, s_e, s_c, r, r, a.p_att, a.att, a.masks, a.alpha_b, a.ctx, a.att_w, a.att_w_stride, a.len_max, H, AH, a.c16_hi,
+                       a.c16_lo, a.Hp);
 }
 
 // ---- row-wise log_softmax (materialised log-probs: get_logprobs_state API and beam search) ----------------------
@@ -332,6 +347,8 @@ struct SelectArgs {
     const float* embed;    // [V1, X] word embedding; the next step's input row relu(E[it]) is written to xt [S, X] here
     float* xt;
     int X;
+    unsigned short *xt16_hi, *xt16_lo;   // nullable split-fp16 copy of xt, [S, Xp]
+    int Xp;
 };
 
 constexpr int kSelectThreads = 1024;  // one block per row: the row is latency-bound, so use every warp slot of the SM
@@ -435,7 +452,11 @@ __global__ void __launch_bounds__(kSelectThreads) select_kernel(const SelectArgs
     if (a.xt != nullptr) {  // embed + ReLU of the token fed to the next step (AttModel.py:332), fused here
         __syncthreads();
         const float* e = a.embed + (size_t)s_it * a.X;
-        for (int j = threadIdx.x; j < a.X; j += blockDim.x) a.xt[(size_t)r * a.X + j] = fmaxf(__ldg(e + j), 0.f);
+        for (int j = threadIdx.x; j < a.X; j += blockDim.x) {
+            const float xv = fmaxf(__ldg(e + j), 0.f);
+            a.xt[(size_t)r * a.X + j] = xv;
+            if (a.xt16_hi) split_f16_store(xv, a.xt16_hi, a.xt16_lo, (size_t)r * a.Xp + j);
+        }
     }
 }
 
@@ -528,34 +549,53 @@ static bool att_phase_fusable(int S, int cols_per_block, size_t smem) {
 // weights are observable).  parent (nullable) re-maps the previous-state rows (beam re-ordering).
 // raw_logits != nullptr: the logit contraction leaves its split-K partials (no bias) for a fused consumer
 // (select_kernel); otherwise `logits` [S, V1] is materialised with the bias applied.
+// Split-fp16 copies of the step's activations, written by the kernels that produce them (cells, attention, selection) so that the
+// h3 contractions read them through TMA without a conversion pass.  Row-identity only: unused when rows are re-mapped (beam search).
+struct Step16 {
+    unsigned short *hin_hi = nullptr, *hin_lo = nullptr;     // [2, S, Hp] previous state
+    unsigned short *hout_hi = nullptr, *hout_lo = nullptr;   // [2, S, Hp] new state
+    unsigned short *ctx_hi = nullptr, *ctx_lo = nullptr;     // [S, Hp]
+    unsigned short *xt_hi = nullptr, *xt_lo = nullptr;       // [S, Xp] relu(E[it]) of the token fed to this step (valid when xt != nullptr)
+    int Hp = 0, Xp = 0;
+};
+static void set_a16(GemmSeg& g, const unsigned short* hi, const unsigned short* lo, int ld) { g.A16_hi = hi; g.A16_lo = lo; g.lda16 = ld; }
+
 static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int len_max, int rows_per_ctx, const long long* it, const float* xt,
                        const long long* parent, const float* fc, const float* att, const float* p_att, const float* masks,
                        const float* h_in, const float* c_in, float* h_out, float* c_out, float* logits, RawPartials* raw_logits, float* att_w,
-                       int att_w_stride, const StepScratch& sc, const int* active, int upto, cudaStream_t st, const float* fc_pre = nullptr) {
+                       int att_w_stride, const StepScratch& sc, const int* active, int upto, cudaStream_t st, const float* fc_pre = nullptr,
+                       const Step16* h16 = nullptr) {
     // fc_pre != nullptr: W_ih[:, H:2H] fc + b_ih + b_hh was computed once for the whole loop (launch_fc_pre): the fc segment
     // (a quarter of the att-LSTM weights) is not streamed again at every step
     const int H = d->rnn, X = d->enc, AH = d->att_hid, V1 = d->vocab1;
     const size_t SH = (size_t)S * H;
     const int pw_blocks = (int)((SH + 255) / 256);
     GemmProblem p;
+    p.wts = w;
     RawPartials rp;
     // attention LSTM: gates = W_ih [h_lang | fc | relu(E[it])] + b_ih + W_hh h_att + b_hh   (AttModel.py:410-413)
     p.M = S; p.N = 4 * H;
     int ns = 0;
+    const bool use16 = h16 != nullptr && parent == nullptr && h16->hin_hi != nullptr;
+    const size_t SHp = use16 ? (size_t)S * h16->Hp : 0;
     p.seg[ns] = make_seg(h_in + SH, H, w->att_w_ih, X + 2 * H, H);
+    if (use16) set_a16(p.seg[ns], h16->hin_hi + SHp, h16->hin_lo + SHp, h16->Hp);
     p.seg[ns++].gather = parent;
     if (!fc_pre) {
         p.seg[ns] = make_seg(fc, H, w->att_w_ih + H, X + 2 * H, H);
         p.seg[ns++].a_row_div = rows_per_ctx;
     }
     if (xt) {  // relu(E[it]) already materialised by the previous step's selection kernel
-        p.seg[ns++] = make_seg(xt, X, w->att_w_ih + 2 * H, X + 2 * H, X);
+        p.seg[ns] = make_seg(xt, X, w->att_w_ih + 2 * H, X + 2 * H, X);
+        if (use16 && h16->xt_hi) set_a16(p.seg[ns], h16->xt_hi, h16->xt_lo, h16->Xp);
+        ++ns;
     } else {
         p.seg[ns] = make_seg(w->embed, X, w->att_w_ih + 2 * H, X + 2 * H, X);
         p.seg[ns].gather = it;
         p.seg[ns++].relu_a = 1;
     }
     p.seg[ns] = make_seg(h_in, H, w->att_w_hh, H, H);
+    if (use16) set_a16(p.seg[ns], h16->hin_hi, h16->hin_lo, h16->Hp);
     p.seg[ns++].gather = parent;
     p.nseg = ns;
     p.active = active;
@@ -571,6 +611,8 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
         fa.h_out = h_out; fa.c_out = c_out; fa.w_h = w->h2att.w; fa.b_h = w->h2att.b; fa.atth = sc.atth; fa.p_att = p_att; fa.att = att;
         fa.masks = masks; fa.alpha_w = w->alpha_net.w; fa.alpha_b = w->alpha_net.b; fa.ctx = sc.ctx; fa.att_w = att_w;
         fa.att_w_stride = att_w_stride; fa.S = S; fa.len_max = len_max; fa.H = H; fa.AH = AH; fa.cols_per_block = cpb; fa.active = active;
+        fa.h16_hi = use16 ? h16->hout_hi : nullptr; fa.h16_lo = use16 ? h16->hout_lo : nullptr;
+        fa.c16_hi = use16 ? h16->ctx_hi : nullptr; fa.c16_lo = use16 ? h16->ctx_lo : nullptr; fa.Hp = use16 ? h16->Hp : 0;
         void* kargs[] = {&fa};
         if (!(skip & 2)) {
             SUBGC_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(att_phase_kernel), dim3(S), dim3(kAttThreads), kargs, smem, st));
@@ -578,35 +620,45 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
         }
     } else {
         if (!(skip & 2)) lstm_reduce_cell_kernel<<<pw_blocks, 256, 0, st>>>(rp.part, rp.splits, w->att_b_ih, w->att_b_hh, c_in, parent, h_out, c_out, S,
-                                                                            H, active, fc_pre, rows_per_ctx);
+                                                                            H, active, fc_pre, rows_per_ctx, use16 ? h16->hout_hi : nullptr,
+                                                                            use16 ? h16->hout_lo : nullptr, use16 ? h16->Hp : 0);
         SUBGC_LAUNCH_CHECK();
         // attention (AttModel.py:445-471); the h2att partials are reduced inside the attention kernel
-        p = GemmProblem();
+        p = GemmProblem(); p.wts = w;
         p.M = S; p.N = AH; p.nseg = 1;
         p.seg[0] = make_seg(h_out, H, w->h2att.w, H, H);
+        if (use16) set_a16(p.seg[0], h16->hout_hi, h16->hout_lo, h16->Hp);
         p.active = active;
         if (!(skip & 4)) SUBGC_TRY(launch_gemm_raw(p, sc.gemm_ws, sc.gemm_ws_bytes, st, &rp));
         if (!(skip & 8)) attention_kernel<<<S, kAttThreads, smem, st>>>(rp.part, rp.splits, w->h2att.b, p_att, att, masks, w->alpha_net.w, w->alpha_net.b,
-                                                                        sc.ctx, att_w, att_w_stride, S, len_max, H, AH, rows_per_ctx, active);
+                                                                        sc.ctx, att_w, att_w_stride, S, len_max, H, AH, rows_per_ctx, active,
+                                                                        use16 ? h16->ctx_hi : nullptr, use16 ? h16->ctx_lo : nullptr, use16 ? h16->Hp : 0);
         SUBGC_LAUNCH_CHECK();
     }
     if (upto == 1) return SUBGC_OK;
     // language LSTM on [ctx | h_att] (AttModel.py:421-423)
-    p = GemmProblem();
+    p = GemmProblem(); p.wts = w;
     p.M = S; p.N = 4 * H; p.nseg = 3;
     p.seg[0] = make_seg(sc.ctx, H, w->lang_w_ih, 2 * H, H);
     p.seg[1] = make_seg(h_out, H, w->lang_w_ih + H, 2 * H, H);
     p.seg[2] = make_seg(h_in + SH, H, w->lang_w_hh, H, H);
     p.seg[2].gather = parent;
+    if (use16) {
+        set_a16(p.seg[0], h16->ctx_hi, h16->ctx_lo, h16->Hp);
+        set_a16(p.seg[1], h16->hout_hi, h16->hout_lo, h16->Hp);
+        set_a16(p.seg[2], h16->hin_hi + SHp, h16->hin_lo + SHp, h16->Hp);
+    }
     p.active = active;
     if (!(skip & 16)) SUBGC_TRY(launch_gemm_raw(p, sc.gemm_ws, sc.gemm_ws_bytes, st, &rp));
     if (!(skip & 32)) lstm_reduce_cell_kernel<<<pw_blocks, 256, 0, st>>>(rp.part, rp.splits, w->lang_b_ih, w->lang_b_hh, c_in + SH, parent, h_out + SH,
-                                                                         c_out + SH, S, H, active, nullptr, 1);
+                                                                         c_out + SH, S, H, active, nullptr, 1, use16 ? h16->hout_hi + SHp : nullptr,
+                                                                         use16 ? h16->hout_lo + SHp : nullptr, use16 ? h16->Hp : 0);
     SUBGC_LAUNCH_CHECK();
     // logit (AttModel.py:336,340); eval mode: dropout is the identity
-    p = GemmProblem();
+    p = GemmProblem(); p.wts = w;
     p.M = S; p.N = V1; p.nseg = 1;
     p.seg[0] = make_seg(h_out + SH, H, w->logit.w, H, H);
+    if (use16) set_a16(p.seg[0], h16->hout_hi + SHp, h16->hout_lo + SHp, h16->Hp);
     p.active = active;
     if (raw_logits) {
         raw_logits->part = static_cast<const float*>(sc.gemm_ws); raw_logits->splits = 1;
@@ -617,10 +669,41 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
     return launch_gemm(p, sc.gemm_ws, sc.gemm_ws_bytes, st);
 }
 
+// ping-pong storage of the split-fp16 activation copies of a decode loop
+struct Step16Bufs {
+    unsigned short* h[2][2];   // [ping-pong][hi | lo] -> [2, S, Hp]
+    unsigned short* ctx[2];    // [hi | lo] -> [S, Hp]
+    unsigned short* xt[2];     // [hi | lo] -> [S, Xp]
+    int Hp, Xp;
+};
+static size_t step16_bytes(const subgc_dims* d, int S) {
+    const size_t Hp = (d->rnn + 7) & ~7, Xp = (d->enc + 7) & ~7;
+    return 4 * align_up(2 * (size_t)S * Hp * 2, 256) + 2 * align_up((size_t)S * Hp * 2, 256) + 2 * align_up((size_t)S * Xp * 2, 256) + 256;
+}
+static bool take_step16(const subgc_dims* d, int S, Workspace& ws, Step16Bufs& b) {
+    b.Hp = (d->rnn + 7) & ~7; b.Xp = (d->enc + 7) & ~7;
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j) b.h[i][j] = ws.take<unsigned short>(2 * (size_t)S * b.Hp);
+    for (int j = 0; j < 2; ++j) b.ctx[j] = ws.take<unsigned short>((size_t)S * b.Hp);
+    for (int j = 0; j < 2; ++j) b.xt[j] = ws.take<unsigned short>((size_t)S * b.Xp);
+    return ws.ok();
+}
+static Step16 step16_of(const Step16Bufs& b, int in, int out, bool has_xt) {
+    Step16 s;
+    s.hin_hi = b.h[in][0]; s.hin_lo = b.h[in][1]; s.hout_hi = b.h[out][0]; s.hout_lo = b.h[out][1];
+    s.ctx_hi = b.ctx[0]; s.ctx_lo = b.ctx[1];
+    s.xt_hi = has_xt ? b.xt[0] : nullptr; s.xt_lo = has_xt ? b.xt[1] : nullptr;
+    s.Hp = b.Hp; s.Xp = b.Xp;
+    return s;
+}
+// the split copies only pay off when the contractions take the h3 path (packed LSTM / logit weights present)
+static bool use_step16(const subgc_weights* w) { return w->packs != nullptr && w->n_packs > 0 && getenv("SUBGC_NO_STEP16") == nullptr; }
+
 // fc_pre[c, :] = W_ih[:, H:2H] fc[c] + b_ih + b_hh for every context row c (step-invariant part of the att-LSTM gates)
 static int launch_fc_pre(const subgc_dims* d, const subgc_weights* w, int n_ctx, const float* fc, const StepScratch& sc, cudaStream_t st) {
     const int H = d->rnn, X = d->enc;
     GemmProblem p;
+    p.wts = w;
     p.M = n_ctx; p.N = 4 * H; p.nseg = 1;
     p.seg[0] = make_seg(fc, H, w->att_w_ih + H, X + 2 * H, H);
     p.epi.bias = w->att_b_ih; p.epi.bias2 = w->att_b_hh;
@@ -786,6 +869,7 @@ extern "C" size_t subgc_decode_workspace_bytes(const subgc_dims* d, int n_rows, 
     b += align_up(S * d->vocab1 * 4, 256);                 // logits
     b += align_up(S * 8, 256) + align_up(S * 4, 256) + align_up(S * d->enc * 4, 256);  // it, unfinished, xt
     b += align_up((size_t)(d->seq_length + 2) * 4, 256);   // count
+    b += step16_bytes(d, n_rows);                          // split-fp16 activation copies
     return b + 1024;
 }
 
@@ -831,7 +915,14 @@ extern "C" int subgc_decode_sample(const subgc_dims* d, const subgc_weights* w, 
     int* unfinished = ws.take<int>(S);
     int* count = ws.take<int>(T + 2);
     float* xt = ws.take<float>((size_t)S * d->enc);
+    Step16Bufs b16;
+    const bool s16 = use_step16(w);
+    if (s16) ok = take_step16(d, S, ws, b16) && ok;
     if (!ok || !ws.ok()) { set_error("subgc_decode_sample: workspace too small"); return SUBGC_E_WORKSPACE; }
+    if (s16) {
+        SUBGC_CUDA(cudaMemsetAsync(b16.h[0][0], 0, 2 * (size_t)S * b16.Hp * 2, st));   // fp16 zeros: split copy of the zero state
+        SUBGC_CUDA(cudaMemsetAsync(b16.h[0][1], 0, 2 * (size_t)S * b16.Hp * 2, st));
+    }
     SUBGC_CUDA(cudaMemsetAsync(hbuf[0], 0, 2 * (size_t)S * H * 4, st));   // init_hidden (AttModel.py:343-346)
     SUBGC_CUDA(cudaMemsetAsync(cbuf[0], 0, 2 * (size_t)S * H * 4, st));
     SUBGC_CUDA(cudaMemsetAsync(it, 0, (size_t)S * 8, st));                // <bos>
@@ -848,22 +939,25 @@ extern "C" int subgc_decode_sample(const subgc_dims* d, const subgc_weights* w, 
         const int* active = (t == 0) ? nullptr : count + (t - 1);
         const int in = t & 1, out = in ^ 1;
         float* aw = att_weights ? att_weights + (size_t)t * len_max : nullptr;
+        const Step16 h16v = s16 ? step16_of(b16, in, out, t > 0) : Step16();
+        const Step16* h16 = s16 ? &h16v : nullptr;
         if (t == T) {
             // the reference runs this step and discards its log-probs (AttModel.py:292-293); only the attention
             // weights are observable, so the step stops there (and is skipped entirely when they are not requested)
             if (att_weights)
                 SUBGC_TRY(launch_step(d, w, S, len_max, 1, it, t > 0 ? xt : nullptr, nullptr, fc, att, p_att, masks, hbuf[in], cbuf[in], hbuf[out], cbuf[out], logits,
-                                      nullptr, aw, (T + 1) * len_max, sc, active, 1, st, sc.gates));
+                                      nullptr, aw, (T + 1) * len_max, sc, active, 1, st, sc.gates, h16));
             break;
         }
         RawPartials rl;
         SUBGC_TRY(launch_step(d, w, S, len_max, 1, it, t > 0 ? xt : nullptr, nullptr, fc, att, p_att, masks, hbuf[in], cbuf[in], hbuf[out], cbuf[out], logits, &rl, aw,
-                              (T + 1) * len_max, sc, active, 0, st, sc.gates));
+                              (T + 1) * len_max, sc, active, 0, st, sc.gates, h16));
         SelectArgs a;
         a.logits = rl.part; a.splits = rl.splits; a.bias = w->logit.b; a.V1 = V1; a.T = T; a.t = t; a.S = S; a.mode = mode; a.temp = temp; a.top_k = top_k; a.seed = seed;
         a.offset = offset; a.uniforms = uniforms; a.it = it; a.unfinished = unfinished; a.seq = reinterpret_cast<long long*>(seq);
         a.seq_lp = seq_logprobs; a.count = count; a.active = active;
         a.embed = w->embed; a.xt = xt; a.X = d->enc;
+        a.xt16_hi = s16 ? b16.xt[0] : nullptr; a.xt16_lo = s16 ? b16.xt[1] : nullptr; a.Xp = s16 ? b16.Xp : 0;
         if (!(skip_mask() & 128)) select_kernel<<<S, kSelectThreads, (size_t)V1 * sizeof(float), st>>>(a);
         SUBGC_LAUNCH_CHECK();
     }

@@ -126,8 +126,9 @@ static size_t fuse_ws_bytes(const subgc_dims* d, int B) {
     return b;
 }
 
-static int linear(const float* A, int M, int K, const subgc_linear& lin, int N, float* C, Workspace& ws, cudaStream_t st) {
+static int linear(const subgc_weights* w, const float* A, int M, int K, const subgc_linear& lin, int N, float* C, Workspace& ws, cudaStream_t st) {
     GemmProblem p;
+    p.wts = w;
     p.M = M; p.N = N; p.nseg = 1;
     p.seg[0] = make_seg(A, K, lin.w, K, K);
     p.epi.bias = lin.b;
@@ -168,6 +169,7 @@ extern "C" int subgc_fuse_nodes(const subgc_dims* d, const subgc_weights* w, int
     SUBGC_LAUNCH_CHECK();
     {
         GemmProblem p;
+        p.wts = w;
         p.M = rows_n; p.N = d->gcn; p.nseg = 2;
         p.seg[0] = make_seg(att_feats, d->att_feat, w->obj_v_proj.w, d->att_feat, d->att_feat);
         p.seg[1] = make_seg(w->sg_obj_embed, d->embed, w->obj_emb_proj.w, d->embed, d->embed);
@@ -182,6 +184,7 @@ extern "C" int subgc_fuse_nodes(const subgc_dims* d, const subgc_weights* w, int
         class_argmax_kernel<<<(rows_k + 7) / 8, 256, 0, st>>>(pred_dist, rows_k, d->pred_classes, d->pred_emb_type == 1 ? 1 : 0, pcls);
         SUBGC_LAUNCH_CHECK();
         GemmProblem p;
+        p.wts = w;
         p.M = rows_k; p.N = d->gcn; p.nseg = 1;
         p.seg[0] = make_seg(w->sg_pred_embed, d->embed, w->pred_emb_prj.w, d->embed, d->embed);
         p.seg[0].gather = pcls;
@@ -225,18 +228,18 @@ extern "C" int subgc_gcn_forward(const subgc_dims* d, const subgc_weights* w, in
         if (need_p[l + 1]) p_next = last ? x_pred : ws.take<float>(pn);
         if (!ws.ok() || !T || !Ma || !Mb) { set_error("subgc_gcn_forward: workspace too small"); return SUBGC_E_WORKSPACE; }
         if (p_next) {  // units 2,3: edge <- node (graph_conv.py:29-33)
-            SUBGC_TRY(linear(x, B * N, L, w->gcn_lft[l][2], R, T, ws, st));
-            SUBGC_TRY(linear(T, B * N, R, w->gcn_rgt[l][2], L, Ma, ws, st));
-            SUBGC_TRY(linear(x, B * N, L, w->gcn_lft[l][3], R, T, ws, st));
-            SUBGC_TRY(linear(T, B * N, R, w->gcn_rgt[l][3], L, Mb, ws, st));
+            SUBGC_TRY(linear(w, x, B * N, L, w->gcn_lft[l][2], R, T, ws, st));
+            SUBGC_TRY(linear(w, T, B * N, R, w->gcn_rgt[l][2], L, Ma, ws, st));
+            SUBGC_TRY(linear(w, x, B * N, L, w->gcn_lft[l][3], R, T, ws, st));
+            SUBGC_TRY(linear(w, T, B * N, R, w->gcn_rgt[l][3], L, Mb, ws, st));
             gcn_edge_update_kernel<<<B * K, 256, 0, st>>>(Ma, Mb, rel, boundary ? p_res : nullptr, p_next, B, N, K, L);
             SUBGC_LAUNCH_CHECK();
         }
         if (x_next) {  // units 0,1: node <- edges (graph_conv.py:22-26)
-            SUBGC_TRY(linear(p, B * K, L, w->gcn_lft[l][0], R, T, ws, st));
-            SUBGC_TRY(linear(T, B * K, R, w->gcn_rgt[l][0], L, Ma, ws, st));
-            SUBGC_TRY(linear(p, B * K, L, w->gcn_lft[l][1], R, T, ws, st));
-            SUBGC_TRY(linear(T, B * K, R, w->gcn_rgt[l][1], L, Mb, ws, st));
+            SUBGC_TRY(linear(w, p, B * K, L, w->gcn_lft[l][0], R, T, ws, st));
+            SUBGC_TRY(linear(w, T, B * K, R, w->gcn_rgt[l][0], L, Ma, ws, st));
+            SUBGC_TRY(linear(w, p, B * K, L, w->gcn_lft[l][1], R, T, ws, st));
+            SUBGC_TRY(linear(w, T, B * K, R, w->gcn_rgt[l][1], L, Mb, ws, st));
             gcn_node_update_kernel<<<B * N, 256, 2 * K * sizeof(int), st>>>(Ma, Mb, rel, boundary ? x_res : nullptr, x_next, B, N, K, L);
             SUBGC_LAUNCH_CHECK();
         }

@@ -344,6 +344,13 @@ void launch_splitk_reduce(const GemmProblem& p, const float* part, int splits, c
 
 int launch_gemm_raw(const GemmProblem& p, void* ws, size_t ws_bytes, cudaStream_t stream, RawPartials* raw) {
     SUBGC_CHECK_ARG(p.M > 0 && raw != nullptr, "gemm(raw): bad arguments");
+    if (p.wts) {
+        GemmProblem q = p;
+        q.wts = nullptr;
+        resolve_packs(q, p.wts);
+        return launch_gemm_raw(q, ws, ws_bytes, stream, raw);
+    }
+    if (h3_eligible(p)) return launch_gemm_h3(p, ws, ws_bytes, stream, raw);
     if (tc_eligible(p)) return launch_gemm_tc(p, ws, ws_bytes, stream, raw);
     int splits = 1;
     SUBGC_TRY(launch_gemm_ex(p, static_cast<float*>(ws), ws_bytes / sizeof(float), &splits, nullptr, 0, stream));
@@ -353,6 +360,16 @@ int launch_gemm_raw(const GemmProblem& p, void* ws, size_t ws_bytes, cudaStream_
 }
 
 int launch_gemm(const GemmProblem& p, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    if (p.wts) {
+        GemmProblem q = p;
+        q.wts = nullptr;
+        resolve_packs(q, p.wts);
+        return launch_gemm(q, ws, ws_bytes, stream);
+    }
+    if (p.M > 0 && h3_eligible(p)) {
+        SUBGC_CHECK_ARG(p.N > 0 && p.C != nullptr && p.ldc >= p.N, "gemm: bad output");
+        return launch_gemm_h3(p, ws, ws_bytes, stream);
+    }
     if (p.M > 0 && tc_eligible(p)) {
         SUBGC_CHECK_ARG(p.N > 0 && p.C != nullptr && p.ldc >= p.N, "gemm: bad output");
         return launch_gemm_tc(p, ws, ws_bytes, stream);
@@ -372,7 +389,8 @@ extern "C" int subgc_linear_forward(int M, int N, int K, const float* A, int lda
     SUBGC_CHECK_ARG(A && W && C && M >= 0 && N > 0 && K > 0, "subgc_linear_forward: bad arguments");
     GemmProblem p;
     p.M = M; p.N = N; p.nseg = 1;
-    p.seg[0] = GemmSeg{A, W, reinterpret_cast<const long long*>(a_gather), lda, ldw, K, 1, 0, nullptr};
+    p.seg[0] = make_seg(A, lda, W, ldw, K);
+    p.seg[0].gather = reinterpret_cast<const long long*>(a_gather);
     p.epi.bias = bias;
     p.epi.relu = relu;
     p.C = C; p.ldc = ldc;

@@ -1,0 +1,505 @@
+// "h3": the contraction block on tcgen05 with split-fp16 operands, for weights that carry a packed copy (subgc_packed).
+//
+//   C[M,N] = epi( sum_seg X_seg[M,K] . W_seg[N,K]^T ),   v = hi + lo * 2^-11,  hi = rn_f16(v),  lo = rn_f16((v - hi) * 2^11)
+//   X.W^T  = Xhi.Whi^T  +  2^-11 (Xhi.Wlo^T + Xlo.Whi^T)          (the dropped lo.lo term is 2^-22 relative)
+//
+// Why this form instead of the split-TF32 kernel (umma_gemm.cu): the decode step streams 136 MB of weights per token and is
+// HBM-bound on paper, but splitting fp32 tiles into hi/lo inside the kernel moves every weight tile through shared memory six
+// times and runs three TF32 MMAs, which measured at 31 % of the HBM roofline.  hi/lo in fp16 are exactly the 4 bytes per weight
+// of the fp32 tensor (same algorithmic HBM bytes), need no in-kernel transform (TMA lands MMA-ready tiles) and kind::f16 runs
+// at twice the TF32 rate; 22 mantissa bits per operand and fp32 accumulation keep the result at the fp32 noise floor
+// (tools/gemm_check.py).  Activations are split by their producer kernel (decode loop) or by split_rows_kernel here.
+//
+// One CTA (192 threads, 1 per SM) computes a 128 x 256 tile over its k-range:
+//   warp 0     TMA producer: per k-block (32 fp16 = one 64-byte swizzled row) four tiles  Whi | Wlo [256 x 32], Xhi | Xlo [128 x 32]
+//   warp 1     one thread issues 2 x 3 tcgen05.mma.kind::f16 (M=128, N=256, K=16) per k-block: main chain -> TMEM columns [0,256),
+//              the two cross terms -> columns [256,512) (separate chains: the accumulator truncation of the main chain is not
+//              multiplied by three adds per step, and the cross sum is scaled by 2^-11 once, exactly, in the epilogue)
+//   warps 2-5  epilogue: tcgen05.ld -> main + cross * 2^-11 -> split-K partial [z][M][N] or the in-place epilogue (single split)
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace subgc {
+
+constexpr int H3_BM = 128;
+constexpr int H3_BN = 256;
+constexpr int H3_BK = 32;   // fp16 elements per k-block (64-byte rows)
+constexpr int H3_STAGES = 4;
+constexpr int H3_THREADS = 192;
+constexpr int H3_W_BYTES = H3_BN * H3_BK * 2;                    // 16 KB
+constexpr int H3_X_BYTES = H3_BM * H3_BK * 2;                    // 8 KB
+constexpr int H3_STAGE_BYTES = 2 * H3_W_BYTES + 2 * H3_X_BYTES;  // Whi | Wlo | Xhi | Xlo = 48 KB
+constexpr int H3_SMEM_BYTES = H3_STAGES * H3_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int H3_MAX_SEG = 4;
+constexpr int H3_MAX_CHAIN = 64;   // k-blocks (128 MMA accumulation steps) per TMEM chain before the fp32 combine of split-K
+constexpr float H3_LO_INV = kH3LoInv;
+
+struct H3Params {
+    CUtensorMap tm_xh[H3_MAX_SEG], tm_xl[H3_MAX_SEG], tm_wh[H3_MAX_SEG], tm_wl[H3_MAX_SEG];
+    int seg_kb_end[H3_MAX_SEG];
+    int nseg;
+    int M, N;
+    int kb_total, kb_per_split;
+    float* part;   // [splits][M][N]
+    int direct;    // single split: apply the epilogue here and write C
+    GemmEpilogue epi;
+    float* C;
+    int ldc;
+    const int* active;
+    CUtensorMap tm_part;   // [splits, M, N] fp32 partials, box 32 x 32 x 1, 128-byte swizzle (valid when tma_part)
+    int tma_part;          // 1: the partial tiles leave through shared memory + TMA stores (full 128-byte lines) instead of per-thread rows
+};
+
+__global__ void __launch_bounds__(H3_THREADS, 1) h3_gemm_kernel(const __grid_constant__ H3Params p) {
+    if (p.active != nullptr && *p.active == 0) return;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bar_base = base + H3_STAGES * H3_STAGE_BYTES;
+    // barriers: full[s] @ +0, empty[s] @ +32, accum @ +64, tmem slot @ +72
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + H3_STAGES * H3_STAGE_BYTES + 72);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * H3_BN, m0 = blockIdx.y * H3_BM;
+    const int kb_begin = blockIdx.z * p.kb_per_split;
+    const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
+    const int nkb = kb_end - kb_begin;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < H3_STAGES; ++s) {
+            mbar_init(bar_base + 8 * s, 1);        // full: producer arrive + tx bytes
+            mbar_init(bar_base + 32 + 8 * s, 1);   // empty: tcgen05.commit
+        }
+        mbar_init(bar_base + 64, 1);               // accumulator ready
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int sgi = 0; sgi < p.nseg; ++sgi) {
+                prefetch_tensormap(&p.tm_wh[sgi]); prefetch_tensormap(&p.tm_wl[sgi]);
+                prefetch_tensormap(&p.tm_xh[sgi]); prefetch_tensormap(&p.tm_xl[sgi]);
+            }
+            int seg = 0;
+            for (int i = 0; i < nkb; ++i) {
+                const int kb = kb_begin + i;
+                while (seg < p.nseg - 1 && kb >= p.seg_kb_end[seg]) ++seg;
+                const int seg_kb0 = seg == 0 ? 0 : p.seg_kb_end[seg - 1];
+                const int s = i % H3_STAGES;
+                const uint32_t ph = (uint32_t)(i / H3_STAGES) & 1u;
+                mbar_wait(bar_base + 32 + 8 * s, ph ^ 1u);
+                const uint32_t st = base + s * H3_STAGE_BYTES;
+                const uint32_t full = bar_base + 8 * s;
+                const int kc = (kb - seg_kb0) * H3_BK;
+                mbar_arrive_expect_tx(full, H3_STAGE_BYTES);
+                tma_load_2d(st, &p.tm_wh[seg], full, kc, n0);
+                tma_load_2d(st + H3_W_BYTES, &p.tm_wl[seg], full, kc, n0);
+                tma_load_2d(st + 2 * H3_W_BYTES, &p.tm_xh[seg], full, kc, m0);
+                tma_load_2d(st + 2 * H3_W_BYTES + H3_X_BYTES, &p.tm_xl[seg], full, kc, m0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        // instruction descriptor: D fp32, A/B fp16, both K-major, N=256, M=128
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(H3_BN >> 3) << 17) | ((uint32_t)(H3_BM >> 4) << 24);
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % H3_STAGES;
+            const uint32_t ph = (uint32_t)(i / H3_STAGES) & 1u;
+            mbar_wait(bar_base + 8 * s, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t st = base + s * H3_STAGE_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < H3_BK / 16; ++ks) {
+                    const uint64_t whi = umma_desc_sw64(st + ks * 32);
+                    const uint64_t wlo = umma_desc_sw64(st + H3_W_BYTES + ks * 32);
+                    const uint64_t xhi = umma_desc_sw64(st + 2 * H3_W_BYTES + ks * 32);
+                    const uint64_t xlo = umma_desc_sw64(st + 2 * H3_W_BYTES + H3_X_BYTES + ks * 32);
+                    const uint32_t acc = (i > 0 || ks > 0) ? 1u : 0u;
+                    umma_f16_afill(tmem_d, xhi, whi, idesc, acc);
+                    umma_f16_alast(tmem_d + H3_BN, xhi, wlo, idesc, acc);
+                    umma_f16(tmem_d + H3_BN, xlo, whi, idesc, 1u);
+                }
+                umma_commit(bar_base + 32 + 8 * s);              // stage free once these MMAs have read it
+                if (i == nkb - 1) umma_commit(bar_base + 64);    // accumulator complete
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== epilogue warps (2..5): TMEM lanes of this warp = 32 * (warp % 4) =====
+        const int t = threadIdx.x - 64;
+        mbar_wait(bar_base + 64, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;
+        const int row = m0 + q * 32 + lane;            // TMEM lane == output row
+        float* out = p.part + (size_t)blockIdx.z * p.M * p.N + (size_t)row * p.N;
+        const bool vec = ((p.N & 3) == 0);
+        const uint32_t tlane = tmem_d + ((uint32_t)(q * 32) << 16);
+        const int nchunks = min(H3_BN / 32, (p.N - n0 + 31) / 32);
+        uint32_t ra[32], rb[32], na[32], nb[32];
+        SUBGC_TMEM_LD32(ra, tlane);
+        SUBGC_TMEM_LD32(rb, tlane + H3_BN);
+        (void)t;
+        // staging tiles of the TMA-store path live in the pipeline stages (idle by now: every MMA has retired): 2 x 4 KB per warp
+        const uint32_t sbuf = base + (uint32_t)q * 8192u;
+        const bool tma_out = !p.direct && p.tma_part && (m0 + q * 32 < p.M);
+#pragma unroll 1
+        for (int c = 0; c < nchunks; ++c) {
+            const int col0 = n0 + c * 32;
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (c + 1 < nchunks) {  // next chunk's TMEM reads overlap this chunk's global stores
+                SUBGC_TMEM_LD32(na, tlane + (uint32_t)((c + 1) * 32));
+                SUBGC_TMEM_LD32(nb, tlane + H3_BN + (uint32_t)((c + 1) * 32));
+            }
+            if (!p.direct && p.tma_part) {
+                if (tma_out) {
+                    const uint32_t buf = sbuf + (uint32_t)(c & 1) * 4096u;
+                    if (c >= 2) {  // the store that read this buffer two chunks ago must have drained it
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {  // 16-byte chunk j of row `lane` sits at chunk j ^ (lane & 7): conflict-free, and what SWIZZLE_128B expects
+                        const uint32_t addr = buf + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
+                        const float v0 = fmaf(__uint_as_float(rb[4 * j]), H3_LO_INV, __uint_as_float(ra[4 * j]));
+                        const float v1 = fmaf(__uint_as_float(rb[4 * j + 1]), H3_LO_INV, __uint_as_float(ra[4 * j + 1]));
+                        const float v2 = fmaf(__uint_as_float(rb[4 * j + 2]), H3_LO_INV, __uint_as_float(ra[4 * j + 2]));
+                        const float v3 = fmaf(__uint_as_float(rb[4 * j + 3]), H3_LO_INV, __uint_as_float(ra[4 * j + 3]));
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                                         reinterpret_cast<uint64_t>(&p.tm_part)),
+                                     "r"(buf), "r"(col0), "r"(m0 + q * 32), "r"((int)blockIdx.z)
+                                     : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+            } else if (row < p.M && p.direct) {
+                float* crow = p.C + (size_t)row * p.ldc;
+                const bool vecc = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (col0 + 32 <= p.N);
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    float b1[8], b2[8], v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { b1[u] = 0.f; b2[u] = 0.f; }
+                    if (p.epi.bias) {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) b1[u] = __ldg(p.epi.bias + min(col0 + j + u, p.N - 1));
+                    }
+                    if (p.epi.bias2) {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) b2[u] = __ldg(p.epi.bias2 + min(col0 + j + u, p.N - 1));
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        float tv = fmaf(__uint_as_float(rb[j + u]), H3_LO_INV, __uint_as_float(ra[j + u]));
+                        if (p.epi.bias) tv += b1[u];
+                        if (p.epi.bias2) tv += b2[u];
+                        v[u] = p.epi.relu ? fmaxf(tv, 0.f) : tv;
+                    }
+                    if (vecc) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            float4* dst = reinterpret_cast<float4*>(crow + col0 + j + 4 * h);
+                            float4 o = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
+                            if (p.epi.accumulate) { const float4 tt = *dst; o.x += tt.x; o.y += tt.y; o.z += tt.z; o.w += tt.w; }
+                            *dst = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            if (col0 + j + u < p.N) crow[col0 + j + u] = p.epi.accumulate ? v[u] + crow[col0 + j + u] : v[u];
+                    }
+                }
+            } else if (row < p.M) {
+                if (vec && col0 + 32 <= p.N) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 v;
+                        v.x = fmaf(__uint_as_float(rb[j]), H3_LO_INV, __uint_as_float(ra[j]));
+                        v.y = fmaf(__uint_as_float(rb[j + 1]), H3_LO_INV, __uint_as_float(ra[j + 1]));
+                        v.z = fmaf(__uint_as_float(rb[j + 2]), H3_LO_INV, __uint_as_float(ra[j + 2]));
+                        v.w = fmaf(__uint_as_float(rb[j + 3]), H3_LO_INV, __uint_as_float(ra[j + 3]));
+                        *reinterpret_cast<float4*>(out + col0 + j) = v;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < p.N) out[col0 + j] = fmaf(__uint_as_float(rb[j]), H3_LO_INV, __uint_as_float(ra[j]));
+                }
+            }
+            if (c + 1 < nchunks) {
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { ra[j] = na[j]; rb[j] = nb[j]; }
+            }
+        }
+        if (tma_out && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before the CTA retires
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512) : "memory");
+    }
+}
+
+// ---- fp32 -> (hi, lo) fp16 (split_f16, common.cuh) ------------------------------------------------------------------
+// weights: [rows, cols] fp32 (ld ldw) -> hi / lo [rows, ld16], tail columns zero
+__global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, int rows, int cols, int ldw, unsigned short* __restrict__ hi,
+                                                          unsigned short* __restrict__ lo, int ld16, int* __restrict__ overflow) {
+    const size_t total = (size_t)rows * ld16;
+    int ovf = 0;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(idx / ld16), c = (int)(idx - (size_t)r * ld16);
+        unsigned short h = 0, l = 0;
+        if (c < cols) split_f16(w[(size_t)r * ldw + c], h, l, ovf);
+        hi[idx] = h;
+        lo[idx] = l;
+    }
+    if (ovf && overflow) atomicOr(overflow, 1);
+}
+
+// activations of one K segment (row gather / shared rows / ReLU-on-load applied) -> hi / lo [M, Kp]
+__global__ void __launch_bounds__(256) split_rows_kernel(const GemmSeg g, int M, int Kp, unsigned short* __restrict__ hi, unsigned short* __restrict__ lo,
+                                                         const int* __restrict__ active, int* __restrict__ overflow) {
+    if (active != nullptr && *active == 0) return;
+    const int kq = Kp >> 2;
+    const size_t total = (size_t)M * kq;
+    int ovf = 0;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int m = (int)(idx / kq), k = (int)(idx - (size_t)m * kq) << 2;
+        const long long src = g.gather ? g.gather[m] : (g.gather32 ? (long long)g.gather32[m] : (long long)(m / g.a_row_div));
+        const float* ptr = g.A + src * g.lda + k;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (k + 3 < g.K && ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0)) {
+            const float4 t = *reinterpret_cast<const float4*>(ptr);
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (k + u < g.K) v[u] = ptr[u];
+        }
+        unsigned short h[4], l[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (g.relu_a) v[u] = fmaxf(v[u], 0.f);
+            split_f16(v[u], h[u], l[u], ovf);
+        }
+        reinterpret_cast<uint2*>(hi)[idx] = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+        reinterpret_cast<uint2*>(lo)[idx] = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+    }
+    if (ovf && overflow) atomicOr(overflow, 1);
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2-D fp16 tensor map: inner dim `cols` (contiguous), outer dim `rows`, `ld` elements between rows; box 32 x box_rows, 64-byte swizzle
+static bool make_map16(CUtensorMap* out, const unsigned short* base, int rows, int cols, long long ld, int box_rows) {
+    EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(tc_encode_fn());
+    if (!fn) return false;
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)H3_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<unsigned short*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// 3-D fp32 map of the split-K partials [splits, M, N]: box 32 columns x 32 rows x 1 split, 128-byte swizzle
+static bool make_map_part(CUtensorMap* out, float* part, int splits, int M, int N) {
+    EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(tc_encode_fn());
+    if (!fn) return false;
+    cuuint64_t gdim[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)splits};
+    cuuint64_t gstride[2] = {(cuuint64_t)N * 4, (cuuint64_t)M * N * 4};
+    cuuint32_t box[3] = {32, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, part, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+static int h3_mode() {  // SUBGC_H3=0 ignores packed weights (A/B runs against the split-TF32 path)
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("SUBGC_H3");
+        mode = (e && e[0] == '0') ? 0 : 1;
+    }
+    return mode;
+}
+
+bool h3_eligible(const GemmProblem& p) {
+    if (!h3_mode()) return false;
+    if (p.M < 1 || p.N < 64 || p.nseg < 1 || p.nseg > H3_MAX_SEG) return false;
+    long long ktot = 0;
+    for (int s = 0; s < p.nseg; ++s) {
+        const GemmSeg& g = p.seg[s];
+        if (!g.W16_hi || !g.W16_lo || (g.ldw16 & 7) || (reinterpret_cast<uintptr_t>(g.W16_hi) & 15) || (reinterpret_cast<uintptr_t>(g.W16_lo) & 15))
+            return false;
+        if (g.A16_hi && ((g.lda16 & 7) || (reinterpret_cast<uintptr_t>(g.A16_hi) & 15) || (reinterpret_cast<uintptr_t>(g.A16_lo) & 15) || !g.A16_lo))
+            return false;
+        ktot += g.K;
+    }
+    return ktot >= 64;
+}
+
+void resolve_packs(GemmProblem& p, const subgc_weights* w) {
+    if (!w || !w->packs || w->n_packs <= 0 || !h3_mode()) return;
+    for (int s = 0; s < p.nseg; ++s) {
+        GemmSeg& g = p.seg[s];
+        if (g.W16_hi) continue;
+        for (int i = 0; i < w->n_packs; ++i) {
+            const subgc_packed& pk = w->packs[i];
+            if (!pk.w || g.W < pk.w || g.W >= pk.w + (size_t)pk.rows * pk.cols || g.ldw != pk.cols) continue;
+            const size_t off = (size_t)(g.W - pk.w);
+            const size_t r = off / pk.cols, c = off - r * pk.cols;
+            if (c + g.K > (size_t)pk.cols || (c & 7)) break;
+            g.W16_hi = pk.hi + r * pk.ld16 + c;
+            g.W16_lo = pk.lo + r * pk.ld16 + c;
+            g.ldw16 = pk.ld16;
+            break;
+        }
+    }
+}
+
+struct H3Plan { int m_tiles, n_tiles, kb_total, splits, kb_per_split; };
+
+static H3Plan h3_plan(int M, int N, const int* segK, int nseg) {
+    H3Plan pl;
+    pl.m_tiles = (M + H3_BM - 1) / H3_BM;
+    pl.n_tiles = (N + H3_BN - 1) / H3_BN;
+    pl.kb_total = 0;
+    for (int s = 0; s < nseg; ++s) pl.kb_total += (segK[s] + H3_BK - 1) / H3_BK;
+    const int tiles = pl.m_tiles * pl.n_tiles;
+    int splits = kNumSMs / tiles;
+    const int by_k = pl.kb_total / 4;  // at least 4 k-blocks (128 columns) per split
+    if (splits > by_k) splits = by_k;
+    if (splits > 32) splits = 32;
+    if (splits < 1) splits = 1;
+    pl.kb_per_split = (pl.kb_total + splits - 1) / splits;
+    if (pl.kb_per_split > H3_MAX_CHAIN) pl.kb_per_split = H3_MAX_CHAIN;
+    pl.splits = (pl.kb_total + pl.kb_per_split - 1) / pl.kb_per_split;
+    return pl;
+}
+
+void launch_splitk_reduce(const GemmProblem& p, const float* part, int splits, cudaStream_t stream);
+
+// Workspace: within tc_workspace_bytes(M, N, Ktotal) (split activations take M * Kp * 4 bytes per segment like the fp32 copies there,
+// and the split count is never larger because a k-block covers twice the columns).
+int launch_gemm_h3(const GemmProblem& p, void* ws_, size_t ws_bytes, cudaStream_t stream, RawPartials* raw) {
+    int segK[H3_MAX_SEG];
+    for (int s = 0; s < p.nseg; ++s) segK[s] = p.seg[s].K;
+    const H3Plan pl = h3_plan(p.M, p.N, segK, p.nseg);
+    Workspace ws(ws_, ws_bytes);
+    const bool direct = (pl.splits == 1 && raw == nullptr && p.epi.div == 0.f && p.epi.addend == nullptr && p.epi.group == 0);
+    float* part = direct ? nullptr : ws.take<float>((size_t)pl.splits * p.M * p.N);
+    H3Params hp;
+    int kb = 0;
+    for (int s = 0; s < p.nseg; ++s) {
+        const GemmSeg& g = p.seg[s];
+        kb += (g.K + H3_BK - 1) / H3_BK;
+        hp.seg_kb_end[s] = kb;
+        if (!make_map16(&hp.tm_wh[s], g.W16_hi, p.N, g.K, g.ldw16, H3_BN) || !make_map16(&hp.tm_wl[s], g.W16_lo, p.N, g.K, g.ldw16, H3_BN)) {
+            set_error("gemm(h3): cuTensorMapEncodeTiled failed for weight segment %d", s);
+            return SUBGC_E_CUDA;
+        }
+        const unsigned short *xh = g.A16_hi, *xl = g.A16_lo;
+        long long xld = g.lda16;
+        if (!xh) {  // no pre-split copy from the producer: split (and gather / ReLU) this segment here, [M, K rounded up to 8]
+            const int Kp = (g.K + 7) & ~7;
+            unsigned short* th = ws.take<unsigned short>((size_t)p.M * Kp);
+            unsigned short* tl = ws.take<unsigned short>((size_t)p.M * Kp);
+            if (!ws.ok()) break;
+            const size_t quads = (size_t)p.M * (Kp >> 2);
+            int gb = (int)((quads + 255) / 256);
+            if (gb > kNumSMs * 8) gb = kNumSMs * 8;
+            split_rows_kernel<<<gb, 256, 0, stream>>>(g, p.M, Kp, th, tl, p.active, nullptr);
+            SUBGC_LAUNCH_CHECK();
+            xh = th; xl = tl; xld = Kp;
+        }
+        if (!make_map16(&hp.tm_xh[s], xh, p.M, g.K, xld, H3_BM) || !make_map16(&hp.tm_xl[s], xl, p.M, g.K, xld, H3_BM)) {
+            set_error("gemm(h3): cuTensorMapEncodeTiled failed for activation segment %d", s);
+            return SUBGC_E_CUDA;
+        }
+    }
+    if (!ws.ok()) {
+        set_error("gemm(h3): workspace too small (%zu bytes given)", ws_bytes);
+        return SUBGC_E_WORKSPACE;
+    }
+    for (int s = p.nseg; s < H3_MAX_SEG; ++s) {
+        hp.seg_kb_end[s] = kb; hp.tm_wh[s] = hp.tm_wh[0]; hp.tm_wl[s] = hp.tm_wl[0]; hp.tm_xh[s] = hp.tm_xh[0]; hp.tm_xl[s] = hp.tm_xl[0];
+    }
+    hp.nseg = p.nseg; hp.M = p.M; hp.N = p.N; hp.kb_total = pl.kb_total; hp.kb_per_split = pl.kb_per_split; hp.part = part; hp.active = p.active;
+    hp.direct = direct ? 1 : 0; hp.epi = p.epi; hp.C = p.C; hp.ldc = p.ldc;
+    static const bool tma_store = getenv("SUBGC_H3_NO_TMA_STORE") == nullptr;
+    hp.tma_part = 0;
+    hp.tm_part = hp.tm_wh[0];
+    if (!direct && tma_store && (p.N & 3) == 0 && make_map_part(&hp.tm_part, part, pl.splits, p.M, p.N)) hp.tma_part = 1;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SUBGC_CUDA(cudaFuncSetAttribute(h3_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H3_SMEM_BYTES));
+        attr_set = true;
+    }
+    dim3 grid(pl.n_tiles, pl.m_tiles, pl.splits);
+    h3_gemm_kernel<<<grid, H3_THREADS, H3_SMEM_BYTES, stream>>>(hp);
+    SUBGC_LAUNCH_CHECK();
+    if (direct) return SUBGC_OK;
+    if (raw) {
+        raw->part = part;
+        raw->splits = pl.splits;
+        return SUBGC_OK;
+    }
+    launch_splitk_reduce(p, part, pl.splits, stream);
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}
+
+}  // namespace subgc
+
+using namespace subgc;
+
+extern "C" int subgc_pack_ld(int cols) { return (cols + 7) & ~7; }
+
+extern "C" int subgc_pack_weight(int rows, int cols, const float* w, int ldw, uint16_t* hi, uint16_t* lo, int32_t* overflow, subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(rows > 0 && cols > 0 && w && hi && lo && ldw >= cols, "subgc_pack_weight: bad arguments");
+    const int ld16 = subgc_pack_ld(cols);
+    const size_t total = (size_t)rows * ld16;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    pack_weight_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, rows, cols, ldw, hi, lo, ld16, overflow);
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}
+
+extern "C" int subgc_linear_packed_forward(int M, int N, int K, const float* A, int lda, const int64_t* a_gather, const subgc_packed* pk,
+                                           const float* bias, int relu, float* C, int ldc, void* ws, size_t ws_bytes, subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(A && pk && pk->w && pk->hi && pk->lo && C && M >= 0 && N > 0 && K > 0, "subgc_linear_packed_forward: bad arguments");
+    SUBGC_CHECK_ARG(pk->rows == N && pk->cols == K && pk->ld16 == subgc_pack_ld(K), "subgc_linear_packed_forward: pack does not match [N, K]");
+    GemmProblem p;
+    p.M = M; p.N = N; p.nseg = 1;
+    p.seg[0] = make_seg(A, lda, pk->w, K, K);
+    p.seg[0].gather = reinterpret_cast<const long long*>(a_gather);
+    p.seg[0].W16_hi = pk->hi; p.seg[0].W16_lo = pk->lo; p.seg[0].ldw16 = pk->ld16;
+    p.epi.bias = bias;
+    p.epi.relu = relu;
+    p.C = C; p.ldc = ldc;
+    return launch_gemm(p, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}

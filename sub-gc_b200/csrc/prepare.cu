@@ -72,35 +72,36 @@ extern "C" int subgc_prepare_forward(const subgc_dims* d, const subgc_weights* w
                                                              att_masks, node_row, masks, row_len);
     SUBGC_LAUNCH_CHECK();
     GemmProblem p;
+    p.wts = w;
     // read_out_proj: 2L -> AH -> 2L (no activation)
-    p = GemmProblem();
+    p = GemmProblem(); p.wts = w;
     p.M = n_rows; p.N = AH; p.nseg = 1;
     p.seg[0] = make_seg(read_out, 2 * L, w->read_out0.w, 2 * L, 2 * L);
     p.seg[0].gather32 = sel;
     p.epi.bias = w->read_out0.b;
     p.C = hid; p.ldc = AH;
     SUBGC_TRY(launch_gemm(p, ws.cursor(), ws.remaining(), st));
-    p = GemmProblem();
+    p = GemmProblem(); p.wts = w;
     p.M = n_rows; p.N = 2 * L; p.nseg = 1;
     p.seg[0] = make_seg(hid, AH, w->read_out1.w, AH, AH);
     p.epi.bias = w->read_out1.b;
     p.C = g_fc; p.ldc = 2 * L;
     SUBGC_TRY(launch_gemm(p, ws.cursor(), ws.remaining(), st));
     // fc_embed: relu(W2 relu(W1 g_fc + b1) + b2)
-    p = GemmProblem();
+    p = GemmProblem(); p.wts = w;
     p.M = n_rows; p.N = FC; p.nseg = 1;
     p.seg[0] = make_seg(g_fc, 2 * L, w->fc_embed0.w, d->att_feat, d->att_feat);
     p.epi.bias = w->fc_embed0.b; p.epi.relu = 1;
     p.C = fch; p.ldc = FC;
     SUBGC_TRY(launch_gemm(p, ws.cursor(), ws.remaining(), st));
-    p = GemmProblem();
+    p = GemmProblem(); p.wts = w;
     p.M = n_rows; p.N = H; p.nseg = 1;
     p.seg[0] = make_seg(fch, FC, w->fc_embed2.w, FC, FC);
     p.epi.bias = w->fc_embed2.b; p.epi.relu = 1;
     p.C = fc; p.ldc = H;
     SUBGC_TRY(launch_gemm(p, ws.cursor(), ws.remaining(), st));
     // att_embed on valid rows (pads exactly zero), straight from x_obj through the node index
-    p = GemmProblem();
+    p = GemmProblem(); p.wts = w;
     p.M = rows; p.N = H; p.nseg = 1;
     p.seg[0] = make_seg(x_obj, L, w->att_embed.w, L, L);
     p.seg[0].gather = node_row;
@@ -109,7 +110,7 @@ extern "C" int subgc_prepare_forward(const subgc_dims* d, const subgc_weights* w
     p.C = att; p.ldc = H;
     SUBGC_TRY(launch_gemm(p, ws.cursor(), ws.remaining(), st));
     // ctx2att on every row up to len_max (padded rows give the bias)
-    p = GemmProblem();
+    p = GemmProblem(); p.wts = w;
     p.M = rows; p.N = AH; p.nseg = 1;
     p.seg[0] = make_seg(att, H, w->ctx2att.w, H, H);
     p.epi.bias = w->ctx2att.b;

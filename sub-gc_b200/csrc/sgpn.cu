@@ -226,6 +226,7 @@ extern "C" int subgc_sgpn_forward(const subgc_dims* d, const subgc_weights* w, c
                                                           sub_len, N, L);
     SUBGC_LAUNCH_CHECK();
     GemmProblem p;
+    p.wts = w;
     p.M = n_sub; p.N = AH; p.nseg = 1;
     p.seg[0] = make_seg(read_out, 2 * L, w->gpn_fc0.w, 2 * L, 2 * L);
     p.epi.bias = w->gpn_fc0.b;

@@ -1,0 +1,122 @@
+// tcgen05 / TMA / mbarrier PTX wrappers shared by the tensor-core contraction kernels (umma_gemm.cu, h3_gemm.cu).
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+
+namespace subgc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+// K-major, 64-byte swizzle, rows of 64 bytes: 8-row groups are 512 bytes apart (SBO), LBO unused for swizzled K-major
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);   // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                          // leading byte offset (16-byte units), bits [16,30)
+    d |= (uint64_t)(512 >> 4) << 32;                 // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell), bits [46,48)
+    d |= (uint64_t)4 << 61;                          // layout type SWIZZLE_64B, bits [61,64)
+    return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// same MMA with the A-operand collector hint: `fill` keeps the A tile in the tensor core's collector buffer, `lastuse` reuses it
+// (the X-hi tile feeds two consecutive MMAs: it is then read from shared memory once instead of twice)
+__device__ __forceinline__ void umma_tf32_afill(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32.collector::a::fill [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32_alast(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32.collector::a::lastuse [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+
+// kind::f16 (fp16 operands, fp32 accumulation in TMEM), K = 16 per instruction; COLL is the A-collector hint
+// ("" | ".collector::a::fill" | ".collector::a::lastuse")
+#define SUBGC_DEF_UMMA_F16(NAME, COLL)                                                                                          \
+    __device__ __forceinline__ void NAME(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) { \
+        asm volatile(                                                                                                          \
+            "{\n\t"                                                                                                            \
+            ".reg .pred p;\n\t"                                                                                                \
+            "setp.ne.b32 p, %4, 0;\n\t"                                                                                        \
+            "tcgen05.mma.cta_group::1.kind::f16" COLL " [%0], %1, %2, %3, p;\n\t"                                              \
+            "}\n" ::"r"(tmem_d),                                                                                               \
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)                                                                \
+            : "memory");                                                                                                       \
+    }
+SUBGC_DEF_UMMA_F16(umma_f16, "")
+SUBGC_DEF_UMMA_F16(umma_f16_afill, ".collector::a::fill")
+SUBGC_DEF_UMMA_F16(umma_f16_alast, ".collector::a::lastuse")
+
+// 32 lanes x 32 consecutive fp32 columns of TMEM -> 32 registers per thread (lane = row)
+#define SUBGC_TMEM_LD32(R, ADDR)                                                                                                         \
+    asm volatile(                                                                                                                        \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, " \
+        "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                                                            \
+        : "=r"(R[0]), "=r"(R[1]), "=r"(R[2]), "=r"(R[3]), "=r"(R[4]), "=r"(R[5]), "=r"(R[6]), "=r"(R[7]), "=r"(R[8]), "=r"(R[9]),        \
+          "=r"(R[10]), "=r"(R[11]), "=r"(R[12]), "=r"(R[13]), "=r"(R[14]), "=r"(R[15]), "=r"(R[16]), "=r"(R[17]), "=r"(R[18]),           \
+          "=r"(R[19]), "=r"(R[20]), "=r"(R[21]), "=r"(R[22]), "=r"(R[23]), "=r"(R[24]), "=r"(R[25]), "=r"(R[26]), "=r"(R[27]),           \
+          "=r"(R[28]), "=r"(R[29]), "=r"(R[30]), "=r"(R[31])                                                                             \
+        : "r"(ADDR))
+
+}  // namespace subgc

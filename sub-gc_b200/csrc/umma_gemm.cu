@@ -26,6 +26,7 @@
 #include <unordered_map>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace subgc {
 
@@ -74,92 +75,6 @@ constexpr int TC_TRACE_SLOTS = 64;  // k-blocks traced per role
         if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (i) < TC_TRACE_SLOTS) \
             p.trace[(role) * TC_TRACE_SLOTS + (i)] = clock64();                                                \
     } while (0)
-
-// ---- PTX wrappers -------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t"
-        "}\n" ::"r"(bar), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-                 "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1)
-                 : "memory");
-}
-__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-__device__ __forceinline__ uint32_t to_tf32(float v) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-    return r;
-}
-// K-major, 64-byte swizzle, rows of 64 bytes: 8-row groups are 512 bytes apart (SBO), LBO unused for swizzled K-major
-__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);   // start address, bits [0,14)
-    d |= (uint64_t)1 << 16;                          // leading byte offset (16-byte units), bits [16,30)
-    d |= (uint64_t)(512 >> 4) << 32;                 // stride byte offset, bits [32,46)
-    d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell), bits [46,48)
-    d |= (uint64_t)4 << 61;                          // layout type SWIZZLE_64B, bits [61,64)
-    return d;
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// same MMA with the A-operand collector hint: `fill` keeps the A tile in the tensor core's collector buffer, `lastuse` reuses it
-// (the X-hi tile feeds two consecutive MMAs: it is then read from shared memory once instead of twice)
-__device__ __forceinline__ void umma_tf32_afill(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32.collector::a::fill [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_tf32_alast(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32.collector::a::lastuse [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
 
 // ---- main kernel ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1) umma_gemm_kernel(const __grid_constant__ TcParams p) {
@@ -453,6 +368,8 @@ __global__ void __launch_bounds__(256) gather_seg_kernel(const GemmSeg g, int M,
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+static EncodeTiledFn encode_fn();
+void* tc_encode_fn() { return reinterpret_cast<void*>(encode_fn()); }
 static EncodeTiledFn encode_fn() {
     static EncodeTiledFn fn = nullptr;
     static std::once_flag once;
@@ -552,8 +469,8 @@ size_t tc_workspace_bytes(int M, int N, int Ktotal) {
     if (splits < 1) splits = 1;
     const int by_chain = (Ktotal / TC_BK + TC_MAX_SEG + TC_MAX_CHAIN - 1) / TC_MAX_CHAIN + 1;
     if (splits < by_chain) splits = by_chain;
-    const size_t Kpad = (size_t)Ktotal + TC_MAX_SEG * 4;
-    return align_up((size_t)M * Kpad * 4, 256) + TC_MAX_SEG * 256 + align_up((size_t)splits * M * N * 4, 256) + 512;
+    const size_t Kpad = (size_t)Ktotal + TC_MAX_SEG * 8;   // per-segment padding of the materialised / split activation copies
+    return align_up((size_t)M * Kpad * 4, 256) + 2 * TC_MAX_SEG * 256 + align_up((size_t)splits * M * N * 4, 256) + 1024;
 }
 
 void launch_splitk_reduce(const GemmProblem& p, const float* part, int splits, cudaStream_t stream);

@@ -29,6 +29,10 @@ class Linear(C.Structure):
     _fields_ = [("w", c_fp), ("b", c_fp)]
 
 
+class Packed(C.Structure):
+    _fields_ = [("w", c_fp), ("hi", c_fp), ("lo", c_fp), ("rows", C.c_int32), ("cols", C.c_int32), ("ld16", C.c_int32)]
+
+
 class Weights(C.Structure):
     _fields_ = [
         ("obj_v_proj", Linear), ("sg_obj_embed", c_fp), ("obj_emb_proj", Linear), ("sg_pred_embed", c_fp),
@@ -38,6 +42,7 @@ class Weights(C.Structure):
         ("h2att", Linear), ("alpha_net", Linear),
         ("att_w_ih", c_fp), ("att_w_hh", c_fp), ("att_b_ih", c_fp), ("att_b_hh", c_fp),
         ("lang_w_ih", c_fp), ("lang_w_hh", c_fp), ("lang_b_ih", c_fp), ("lang_b_hh", c_fp),
+        ("packs", C.POINTER(Packed)), ("n_packs", C.c_int32),
     ]
 
 
@@ -53,6 +58,9 @@ SIGNATURES = {
     "subgc_last_error": (C.c_char_p, []),
     "subgc_version": (_i, []),
     "subgc_launch_count": (C.c_ulonglong, []),
+    "subgc_pack_ld": (_i, [_i]),
+    "subgc_pack_weight": (_i, [_i, _i, c_fp, _i, c_fp, c_fp, c_fp, c_fp]),
+    "subgc_linear_packed_forward": (_i, [_i, _i, _i, c_fp, _i, c_fp, _P(Packed), c_fp, _i, c_fp, _i, c_fp, _sz, c_fp]),
     "subgc_linear_workspace_bytes": (_sz, [_i, _i, _i]),
     "subgc_linear_forward": (_i, [_i, _i, _i, c_fp, _i, c_fp, c_fp, _i, c_fp, _i, c_fp, _i, c_fp, _sz, c_fp]),
     "subgc_encoder_workspace_bytes": (_sz, [_P(Dims), _i]),

@@ -20,7 +20,7 @@ import os
 import torch
 import torch.nn as nn
 
-from . import _lib
+from . import _lib, packing
 from ._lib import check, lib, ptr
 from .config import Dims, dims_from_opt
 
@@ -182,6 +182,9 @@ class TopDownModel(nn.Module):
         self.last_steps = None
         self._ws = Workspace()
         self._wcache = None
+        self._packs = packing.PackCache()
+        self._pack_key = None
+        self.use_packed = True   # inference contractions read split-fp16 copies of the weights (subgc.packing)
         self.stage_events = None  # set to [] to collect (name, start_event, end_event) per stage (bench / profiling)
         self.dropout_enabled = True   # tests switch it off: Philox masks cannot match torch's RNG stream (SURVEY §7 hard part 5)
         self.force_train_path = False  # run the autograd-capable path in eval mode too (gradient parity tests)
@@ -211,7 +214,9 @@ class TopDownModel(nn.Module):
         params = dict(self.named_parameters())
         key = tuple(p.data_ptr() for p in params.values())
         if self._wcache is not None and self._wcache[0] == key:
-            return self._wcache[1]
+            w = self._wcache[1]
+            self._attach_packs(w, params)
+            return w
         for n, p in params.items():
             if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
                 raise _lib.SubgcError(f"parameter {n} must be a contiguous fp32 CUDA tensor (got {p.dtype} on {p.device}); "
@@ -237,7 +242,28 @@ class TopDownModel(nn.Module):
         w.lang_b_ih = g("core.lang_lstm.bias_ih"); w.lang_b_hh = g("core.lang_lstm.bias_hh")
         self._wcache = (key, w)
         self._plans.clear()  # captured graphs hold the old parameter addresses
+        self._pack_key = None
+        self._attach_packs(w, params)
         return w
+
+    # weight matrices that are the W operand of a contraction on the inference path (embedding tables are A operands)
+    _PACK_SKIP = ("sg_obj_embed.weight", "sg_pred_embed.weight", "embed.0.weight")
+
+    def _attach_packs(self, w, params):
+        """Inference only: split-fp16 copies of the weight matrices for the tensor cores (subgc.packing), refreshed when a
+        parameter was updated in place; training steps read the fp32 parameters directly."""
+        use = (not self.training) and self.use_packed and os.environ.get("SUBGC_H3", "1") != "0"
+        if not use:
+            if w.n_packs:
+                w.packs, w.n_packs = None, 0
+                self._plans.clear()
+            return
+        named = {n: p for n, p in params.items() if p.dim() == 2 and p.shape[0] >= 64 and n not in self._PACK_SKIP}
+        arr, cnt = self._packs.build(named)
+        if self._pack_key != self._packs.array_key or not w.n_packs:
+            w.packs, w.n_packs = arr, cnt
+            self._pack_key = self._packs.array_key
+            self._plans.clear()  # captured graphs hold the old packed-copy addresses
 
     def _train_ops(self):
         from .train import CudaOps
