@@ -120,6 +120,8 @@ const char* subgc_last_error(void);
 int subgc_version(void);
 /* kernels launched so far by the calling thread through this library (instrumentation for bench.py's gpu_launches) */
 unsigned long long subgc_launch_count(void);
+/* debugging aid (env SUBGC_ATT_TRACE=1, synchronises): per-block stage time stamps [n_blocks][8] of the last fused att-phase launch */
+int subgc_debug_att_trace(unsigned long long* host_out, int n_blocks);
 
 /* Packs an fp32 weight matrix [rows, cols] (leading dim ldw) into the split-fp16 form of subgc_packed; ld16 =
  * subgc_pack_ld(cols) (cols rounded up to 8), each output array holds rows * ld16 fp16 values.  `overflow` (device,

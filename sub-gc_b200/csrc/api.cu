@@ -1,5 +1,6 @@
 // Error reporting and version of the subgc_b200 C ABI.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -13,6 +14,11 @@ void set_error(const char* fmt, ...) {
 }
 static thread_local unsigned long long g_launches = 0;
 void count_launch() { ++g_launches; }
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("SUBGC_NO_PDL"); on = (e && e[0] == '1') ? 0 : 1; }
+    return on == 1;
+}
 }  // namespace subgc
 
 extern "C" const char* subgc_last_error(void) { return subgc::g_err; }

@@ -153,6 +153,29 @@ int launch_gemm_raw(const GemmProblem& p, void* ws, size_t ws_bytes, cudaStream_
 // upper bound of splits * M * N floats for launch_gemm_ex raw partials
 size_t gemm_partial_elems(int M, int N, int Ktotal);
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
+// The decode loop is a chain of ~6 dependent kernels per token, each of them short: launch latency, grid drain and kernel
+// prologues are a third of the step.  Kernels launched through launch_pdl may start while their predecessor in the stream is
+// still running (as soon as every block of it has passed pdl_trigger()); they do their input-independent prologue (barrier /
+// TMEM set-up, weight-tile prefetch) and then block in pdl_wait() until the predecessor has completed and its writes are
+// visible.  RULE: a kernel launched with launch_pdl must call pdl_wait() before it reads anything another kernel wrote and
+// before it writes anything another kernel may still read.  Without the launch attribute both instructions are no-ops.
+bool pdl_enabled();  // SUBGC_NO_PDL=1 switches the attribute off (plain stream order)
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // ---- device helpers ------------------------------------------------------------------------------------
 #ifdef __CUDACC__
 __device__ __forceinline__ float warp_sum(float v) {

@@ -33,6 +33,8 @@ __global__ void __launch_bounds__(256) lstm_reduce_cell_kernel(const float* __re
     // h16_hi / h16_lo (nullable, [S, Hp]): the split-fp16 copy of h' the next contractions read as their activation operand
     // addend != nullptr: a pre-computed [S / add_div, 4H] term (the step-invariant fc segment with both biases folded in)
     // replaces b_ih + b_hh
+    pdl_trigger();
+    pdl_wait();
     if (active != nullptr && *active == 0) return;
     const size_t zs = (size_t)S * 4 * H;
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -40,8 +42,8 @@ __global__ void __launch_bounds__(256) lstm_reduce_cell_kernel(const float* __re
     int r = idx / H, j = idx - r * H;
     const float* g = part + (size_t)r * 4 * H + j;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-    for (int z = 0; z < splits; ++z) {  // one hidden unit per thread keeps ~128 K threads in flight; 16 independent loads each
+#pragma unroll 9
+    for (int z = 0; z < splits; ++z) {  // one hidden unit per thread keeps ~128 K threads in flight; all 4 x splits loads independent
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[q] += g[(size_t)z * zs + (size_t)q * H];
     }
@@ -162,6 +164,16 @@ __global__ void __launch_bounds__(kAttThreads) attention_kernel(const float* __r
                                                                 int att_w_stride, int S, int len_max, int H, int AH, int rows_per_ctx,
                                                                 const int* __restrict__ active, unsigned short* __restrict__ c16_hi,
                                                                 unsigned short* __restrict__ c16_lo, int Hp) {
+    pdl_trigger();
+    {   // the row's attention operands do not depend on this step: request them into L2 while the predecessor kernels still run
+        const int cr0 = blockIdx.x / rows_per_ctx;
+        const char* pa = reinterpret_cast<const char*>(p_att + (size_t)cr0 * len_max * AH);
+        const char* af = reinterpret_cast<const char*>(att + (size_t)cr0 * len_max * H);
+        const size_t nb_p = (size_t)len_max * AH * 4, nb_a = (size_t)len_max * H * 4;
+        for (size_t o = (size_t)threadIdx.x * 128; o < nb_p; o += (size_t)blockDim.x * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + o));
+        for (size_t o = (size_t)threadIdx.x * 128; o < nb_a; o += (size_t)blockDim.x * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(af + o));
+    }
+    pdl_wait();
     if (active != nullptr && *active == 0) return;
     extern __shared__ float s_att[];  // [AH] atth | [AH] alpha_w | [64] e | [4][H] context partials
     float* s_h = s_att;
@@ -179,51 +191,68 @@ __global__ void __launch_bounds__(kAttThreads) attention_kernel(const float* __r
     attention_row_body(s_h, s_w, s_e, s_c, r, cr, p_att, att, masks, alpha_b, ctx, att_w, att_w_stride, len_max, H, AH, c16_hi, c16_lo, Hp);
 }
 
-// ---- fused attention phase of a decode step: one cooperative kernel instead of cell + h2att GEMM + attention ---------------
+// ---- fused attention phase of a decode step: one cluster kernel instead of cell + h2att GEMM + attention --------------------
 // The three stages are tiny but strictly dependent (att-LSTM cell -> W_h h_att -> attention); as separate kernels they cost
-// three launch / fill / tail latencies (~40 us).  Here block r (one per decode row, all co-resident: cooperative launch)
-//   1. reduces the att-LSTM split-K partials of row r and applies the LSTM cell              -> h_att[r], c_att[r]
-//   -- grid barrier --
-//   2. computes atth[:, cols_r] = h_att . W_h[cols_r]^T + b_h for its slice of <= 4 output columns (all rows; W_h rows in smem)
-//   -- grid barrier --
-//   3. runs the attention of row r (tanh / alpha / softmax / mask / renormalise / context)     -> ctx[r]
+// three launch / fill / tail latencies.  Here block r (one per decode row) belongs to a cluster of 8 consecutive rows and
+//   1. reduces the att-LSTM split-K partials of row r and applies the LSTM cell                  -> h_att[r], c_att[r]
+//   -- cluster barrier --
+//   2. computes atth[rows of the cluster, its 1/8 slice of the AH columns] (W_h slice streamed once from L2, the 8 h rows in
+//      shared memory) and writes each value into the shared memory of the block that owns the row (DSMEM)
+//   -- cluster barrier --
+//   3. runs the attention of row r (tanh / alpha / softmax / mask / renormalise / context)         -> ctx[r]
+constexpr int kAttCluster = 8;
 struct AttPhaseArgs {
     const float* part; int splits;               // att-LSTM gate partials [splits][S][4H]
     const float* b_ih; const float* b_hh;        // used when fc_pre == nullptr
-    const float* fc_pre;                         // [S, 4H] hoisted fc segment + biases (nullable)
+    const float* fc_pre;                         // [S / rows_per_ctx, 4H] hoisted fc segment + biases (nullable)
     const float* c_prev; float* h_out; float* c_out;   // layer-0 state rows [S, H]
+    const long long* parent;                     // nullable: previous-state row of each row (beam re-ordering)
     const float* w_h; const float* b_h;          // h2att [AH, H], [AH]
-    float* atth;                                 // [S, AH] scratch
     const float* p_att; const float* att; const float* masks; const float* alpha_w; const float* alpha_b;
     float* ctx; float* att_w; int att_w_stride;
-    int S, len_max, H, AH, cols_per_block;
+    int S, len_max, H, AH, cols_per_block, rows_per_ctx;
     const int* active;
     unsigned short *h16_hi, *h16_lo, *c16_hi, *c16_lo;   // nullable split-fp16 copies of h_att / ctx, [S, Hp]
     int Hp;
+    unsigned long long* trace;   // debug (SUBGC_ATT_TRACE=1): [grid][8] globaltimer stamps per block; nullptr in normal operation
 };
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define ATT_STAMP(i) do { if (a.trace != nullptr && threadIdx.x == 0) a.trace[(size_t)blockIdx.x * 8 + (i)] = gtime(); } while (0)
 
 __global__ void __launch_bounds__(kAttThreads, 1) att_phase_kernel(const AttPhaseArgs a) {
-    if (a.active != nullptr && *a.active == 0) return;   // uniform across the grid: nobody reaches the barriers
-    cg::grid_group grid = cg::this_grid();
-    extern __shared__ float s_att[];  // [AH] atth | [AH] alpha_w | [64] e | [4][H] context partials (stage 2: W_h rows)
+    pdl_trigger();
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ float s_att[];  // [AH] atth | [AH] alpha_w | [64] e | [8][H] h rows of the cluster (stage 2) / [4][H] context partials
     float* s_h = s_att;
     float* s_w = s_att + a.AH;
     float* s_e = s_att + 2 * a.AH;
     float* s_c = s_att + 2 * a.AH + 64;
     const int r = blockIdx.x, H = a.H, AH = a.AH, S = a.S;
+    const bool valid = r < S;
+    const int crank = (int)cluster.block_rank();
+    const int row0 = r - crank;
+    const int cr = r / a.rows_per_ctx;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    ATT_STAMP(0);
     // The row's attention operands (p_att 74 KB, att 144 KB) do not depend on this step: ask for them in L2 now, they are
     // evicted by the weight streams between steps and stage 3 is otherwise a chain of DRAM-latency rounds.
-    {
-        const char* pa = reinterpret_cast<const char*>(a.p_att + (size_t)r * a.len_max * AH);
-        const char* af = reinterpret_cast<const char*>(a.att + (size_t)r * a.len_max * H);
+    if (valid) {
+        const char* pa = reinterpret_cast<const char*>(a.p_att + (size_t)cr * a.len_max * AH);
+        const char* af = reinterpret_cast<const char*>(a.att + (size_t)cr * a.len_max * H);
         const size_t nb_p = (size_t)a.len_max * AH * 4, nb_a = (size_t)a.len_max * H * 4;
         for (size_t o = (size_t)threadIdx.x * 128; o < nb_p; o += (size_t)blockDim.x * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + o));
         for (size_t o = (size_t)threadIdx.x * 128; o < nb_a; o += (size_t)blockDim.x * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(af + o));
     }
+    pdl_wait();
+    if (a.active != nullptr && *a.active == 0) return;   // uniform across the grid: nobody reaches the barriers
     // ---- 1. split-K reduce + biases + LSTM cell of row r
-    {
+    if (valid) {
         const size_t zs = (size_t)S * 4 * H;
+        const long long pr = a.parent ? a.parent[r] : r;
         for (int j = threadIdx.x; j < H; j += blockDim.x) {
             const float* g = a.part + (size_t)r * 4 * H + j;
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -233,65 +262,102 @@ __global__ void __launch_bounds__(kAttThreads, 1) att_phase_kernel(const AttPhas
                 for (int q = 0; q < 4; ++q) acc[q] += g[(size_t)z * zs + (size_t)q * H];
             }
             if (a.fc_pre) {
-                const float* ad = a.fc_pre + (size_t)r * 4 * H + j;
+                const float* ad = a.fc_pre + (size_t)cr * 4 * H + j;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) acc[q] += ad[(size_t)q * H];
             } else {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) acc[q] = (acc[q] + __ldg(a.b_ih + q * H + j)) + __ldg(a.b_hh + q * H + j);
             }
-            const float c = sigmoidf_(acc[1]) * a.c_prev[(size_t)r * H + j] + sigmoidf_(acc[0]) * tanhf(acc[2]);
+            const float c = sigmoidf_(acc[1]) * a.c_prev[(size_t)pr * H + j] + sigmoidf_(acc[0]) * tanhf(acc[2]);
             a.c_out[(size_t)r * H + j] = c;
             const float hv = sigmoidf_(acc[3]) * tanhf(c);
             a.h_out[(size_t)r * H + j] = hv;
             if (a.h16_hi) split_f16_store(hv, a.h16_hi, a.h16_lo, (size_t)r * a.Hp + j);
         }
     }
-    grid.sync();
-    // ---- 2. h2att for this block's column slice, all rows
+    ATT_STAMP(1);
+    cluster.sync();
+    ATT_STAMP(2);
+    // ---- 2. h2att: this block's column slice for the rows of the cluster
     {
-        const int c0 = r * a.cols_per_block;
-        const int nc = max(0, min(a.cols_per_block, AH - c0));
-        for (int idx = threadIdx.x; idx < nc * H; idx += blockDim.x) s_c[idx] = __ldg(a.w_h + (size_t)c0 * H + idx);
+        const int nrows = max(0, min(kAttCluster, S - row0));
+        const float* hsrc = a.h_out + (size_t)row0 * H;   // the cluster's rows are consecutive: one contiguous run, written in stage 1
+        for (int idx = threadIdx.x; idx < nrows * H; idx += blockDim.x) s_c[idx] = __ldcg(hsrc + idx);
+        for (int idx = nrows * H + threadIdx.x; idx < kAttCluster * H; idx += blockDim.x) s_c[idx] = 0.f;
         __syncthreads();
-        if (nc > 0) {
-            for (int row = wid; row < S; row += nw) {
-                const float* hr = a.h_out + (size_t)row * H;   // written in stage 1 by block `row` (plain loads: not the read-only path)
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                for (int k0 = lane; k0 < H; k0 += 32 * 8) {   // 8 independent loads in flight per lane (the loop is latency-bound)
-                    float hv[8];
+        const int c0 = crank * a.cols_per_block;
+        const int nc = max(0, min(a.cols_per_block, AH - c0));
+        for (int cp = wid * 2; cp < nc; cp += nw * 2) {
+            const int colA = c0 + cp, colB = min(c0 + cp + 1, AH - 1);
+            const bool hasB = cp + 1 < nc;
+            const float* wa = a.w_h + (size_t)colA * H;
+            const float* wb = a.w_h + (size_t)colB * H;
+            float accA[kAttCluster], accB[kAttCluster];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) hv[u] = (k0 + 32 * u < H) ? hr[k0 + 32 * u] : 0.f;
+            for (int i = 0; i < kAttCluster; ++i) { accA[i] = 0.f; accB[i] = 0.f; }
+            if ((H & 3) == 0) {
+                // The stage is instruction-bound (65 MFMA over the grid), so every shared-memory read feeds 8 FMAs: a lane owns 4
+                // consecutive k (one 16-byte weight load per column, one 16-byte read per h row)
+                const int H4 = H >> 2;
+                const float4* wa4 = reinterpret_cast<const float4*>(wa);
+                const float4* wb4 = reinterpret_cast<const float4*>(wb);
+                float4 a0 = lane < H4 ? __ldg(wa4 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 b0 = lane < H4 ? __ldg(wb4 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int q0 = lane; q0 < H4; q0 += 32) {   // the next quad of both columns is requested before this one is consumed
+                    const int q1 = q0 + 32;
+                    const float4 an = q1 < H4 ? __ldg(wa4 + q1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 bn = q1 < H4 ? __ldg(wb4 + q1) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int k = min(k0 + 32 * u, H - 1);
+                    for (int i = 0; i < kAttCluster; ++i) {
+                        const float4 h0 = reinterpret_cast<const float4*>(s_c + i * H)[q0];
+                        accA[i] = fmaf(a0.x, h0.x, accA[i]); accA[i] = fmaf(a0.y, h0.y, accA[i]);
+                        accA[i] = fmaf(a0.z, h0.z, accA[i]); accA[i] = fmaf(a0.w, h0.w, accA[i]);
+                        accB[i] = fmaf(b0.x, h0.x, accB[i]); accB[i] = fmaf(b0.y, h0.y, accB[i]);
+                        accB[i] = fmaf(b0.z, h0.z, accB[i]); accB[i] = fmaf(b0.w, h0.w, accB[i]);
+                    }
+                    a0 = an; b0 = bn;
+                }
+            } else {
+                for (int k = lane; k < H; k += 32) {
+                    const float va = __ldg(wa + k), vb = __ldg(wb + k);
 #pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            if (c < nc) acc[c] = fmaf(hv[u], s_c[c * H + k], acc[c]);
+                    for (int i = 0; i < kAttCluster; ++i) {
+                        const float hv = s_c[i * H + k];
+                        accA[i] = fmaf(va, hv, accA[i]);
+                        accB[i] = fmaf(vb, hv, accB[i]);
                     }
                 }
+            }
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const float v = warp_sum(acc[c]);
-                    if (lane == 0 && c < nc) a.atth[(size_t)row * AH + c0 + c] = v + __ldg(a.b_h + c0 + c);
+            for (int i = 0; i < kAttCluster; ++i) {
+                const float sa = warp_sum(accA[i]), sb = warp_sum(accB[i]);
+                if (lane == 0 && i < nrows) {
+                    float* peer = cluster.map_shared_rank(s_h, i);   // atth row of the block that owns row (row0 + i)
+                    peer[colA] = sa + __ldg(a.b_h + colA);
+                    if (hasB) peer[colB] = sb + __ldg(a.b_h + colB);
                 }
             }
         }
     }
-    grid.sync();
+    ATT_STAMP(3);
+    cluster.sync();
+    ATT_STAMP(4);
+    if (!valid) return;
     // ---- 3. attention of row r
-    for (int j = threadIdx.x; j < AH; j += blockDim.x) {
-        s_h[j] = a.atth[(size_t)r * AH + j];
-        s_w[j] = __ldg(a.alpha_w + j);
-    }
+    for (int j = threadIdx.x; j < AH; j += blockDim.x) s_w[j] = __ldg(a.alpha_w + j);
     __syncthreads();
-    attention_row_body(s_h, s_w, s_e, s_c, r, r, a.p_att, a.att, a.masks, a.alpha_b, a.ctx, a.att_w, a.att_w_stride, a.len_max, H, AH, a.c16_hi,
+    attention_row_body(s_h, s_w, s_e, s_c, r, cr, a.p_att, a.att, a.masks, a.alpha_b, a.ctx, a.att_w, a.att_w_stride, a.len_max, H, AH, a.c16_hi,
                        a.c16_lo, a.Hp);
+    __syncthreads();
+    ATT_STAMP(5);
 }
 
 // ---- row-wise log_softmax (materialised log-probs: get_logprobs_state API and beam search) ----------------------
 __global__ void __launch_bounds__(256) log_softmax_kernel(const float* __restrict__ logits, float* __restrict__ logp, int V1,
                                                           size_t out_stride, const int* __restrict__ active) {
+    pdl_trigger();
+    pdl_wait();
     if (active != nullptr && *active == 0) return;
     __shared__ float red[32];
     const float* x = logits + (size_t)blockIdx.x * V1;
@@ -354,6 +420,8 @@ struct SelectArgs {
 constexpr int kSelectThreads = 1024;  // one block per row: the row is latency-bound, so use every warp slot of the SM
 
 __global__ void __launch_bounds__(kSelectThreads) select_kernel(const SelectArgs a) {
+    pdl_trigger();
+    pdl_wait();
     if (a.active != nullptr && *a.active == 0) return;
     __shared__ float redv[32];
     __shared__ int redi[32];
@@ -531,18 +599,28 @@ static int skip_mask() {
     return m;
 }
 
-// The fused att-phase kernel needs every block co-resident (grid barriers): one 1024-thread block per SM.
-static bool att_phase_fusable(int S, int cols_per_block, size_t smem) {
-    static int mode = -1, sms = 0, coop = 0;
+// debugging aid (SUBGC_ATT_TRACE=1): per-block stage time stamps of the most recent att-phase launch, read back by subgc_debug_att_trace
+static unsigned long long* att_trace_buffer() {
+    static unsigned long long* buf = nullptr;
+    static int on = -1;
+    if (on < 0) {
+        on = getenv("SUBGC_ATT_TRACE") != nullptr ? 1 : 0;
+        if (on) { cudaMalloc(&buf, 1024 * 8 * sizeof(unsigned long long)); cudaMemset(buf, 0, 1024 * 8 * sizeof(unsigned long long)); }
+    }
+    return buf;
+}
+
+// The fused att-phase kernel runs as clusters of 8 row-blocks (distributed shared memory carries the h2att results).
+static bool att_phase_fusable(size_t smem) {
+    static int mode = -1, clus = 0;
     if (mode < 0) {
-        const char* e = getenv("SUBGC_NO_FUSED_ATT");
-        mode = (e && e[0] == '1') ? 0 : 1;
+        const char* e = getenv("SUBGC_FUSED_ATT");   // opt-in: measured slower than the three separate kernels under PDL
+        mode = (e && e[0] == '1') ? 1 : 0;
         int dev = 0;
         cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&clus, cudaDevAttrClusterLaunch, dev);
     }
-    return mode == 1 && coop && S <= sms && cols_per_block <= 4 && smem <= 48 * 1024;
+    return mode == 1 && clus && smem <= 48 * 1024;
 }
 
 // upto: 0 = whole step, 1 = stop after the attention (the reference's discarded last step, only its attention
@@ -603,23 +681,35 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
     rp.part = static_cast<const float*>(sc.gemm_ws); rp.splits = 1;
     if (!(skip & 1)) SUBGC_TRY(launch_gemm_raw(p, sc.gemm_ws, sc.gemm_ws_bytes, st, &rp));
     size_t smem = (size_t)(2 * AH + 64 + 4 * H) * sizeof(float);
-    const int cpb = (AH + S - 1) / S;
-    if (att_phase_fusable(S, cpb, smem) && parent == nullptr && rows_per_ctx == 1) {
-        // cell + h2att + attention as one cooperative kernel (one block per row, two grid barriers)
+    const size_t smem_fused = (size_t)(2 * AH + 64 + kAttCluster * H) * sizeof(float);
+    if (att_phase_fusable(smem_fused)) {
+        // cell + h2att + attention as one kernel (one block per row, clusters of 8 rows, two cluster barriers)
         AttPhaseArgs fa;
         fa.part = rp.part; fa.splits = rp.splits; fa.b_ih = w->att_b_ih; fa.b_hh = w->att_b_hh; fa.fc_pre = fc_pre; fa.c_prev = c_in;
-        fa.h_out = h_out; fa.c_out = c_out; fa.w_h = w->h2att.w; fa.b_h = w->h2att.b; fa.atth = sc.atth; fa.p_att = p_att; fa.att = att;
+        fa.h_out = h_out; fa.c_out = c_out; fa.parent = parent; fa.w_h = w->h2att.w; fa.b_h = w->h2att.b; fa.p_att = p_att; fa.att = att;
         fa.masks = masks; fa.alpha_w = w->alpha_net.w; fa.alpha_b = w->alpha_net.b; fa.ctx = sc.ctx; fa.att_w = att_w;
-        fa.att_w_stride = att_w_stride; fa.S = S; fa.len_max = len_max; fa.H = H; fa.AH = AH; fa.cols_per_block = cpb; fa.active = active;
+        fa.att_w_stride = att_w_stride; fa.S = S; fa.len_max = len_max; fa.H = H; fa.AH = AH;
+        fa.cols_per_block = (AH + kAttCluster - 1) / kAttCluster; fa.rows_per_ctx = rows_per_ctx; fa.active = active;
         fa.h16_hi = use16 ? h16->hout_hi : nullptr; fa.h16_lo = use16 ? h16->hout_lo : nullptr;
         fa.c16_hi = use16 ? h16->ctx_hi : nullptr; fa.c16_lo = use16 ? h16->ctx_lo : nullptr; fa.Hp = use16 ? h16->Hp : 0;
-        void* kargs[] = {&fa};
+        fa.trace = att_trace_buffer();
         if (!(skip & 2)) {
-            SUBGC_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(att_phase_kernel), dim3(S), dim3(kAttThreads), kargs, smem, st));
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((S + kAttCluster - 1) / kAttCluster * kAttCluster);
+            cfg.blockDim = dim3(kAttThreads);
+            cfg.dynamicSmemBytes = smem_fused;
+            cfg.stream = st;
+            cudaLaunchAttribute at[2];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = kAttCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+            cfg.attrs = at; cfg.numAttrs = 2;
+            SUBGC_CUDA(cudaLaunchKernelEx(&cfg, att_phase_kernel, fa));
             count_launch();
         }
     } else {
-        if (!(skip & 2)) lstm_reduce_cell_kernel<<<pw_blocks, 256, 0, st>>>(rp.part, rp.splits, w->att_b_ih, w->att_b_hh, c_in, parent, h_out, c_out, S,
+        if (!(skip & 2)) launch_pdl(lstm_reduce_cell_kernel, dim3(pw_blocks), dim3(256), (size_t)0, st, rp.part, rp.splits, w->att_b_ih, w->att_b_hh, c_in, parent, h_out, c_out, S,
                                                                             H, active, fc_pre, rows_per_ctx, use16 ? h16->hout_hi : nullptr,
                                                                             use16 ? h16->hout_lo : nullptr, use16 ? h16->Hp : 0);
         SUBGC_LAUNCH_CHECK();
@@ -630,7 +720,7 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
         if (use16) set_a16(p.seg[0], h16->hout_hi, h16->hout_lo, h16->Hp);
         p.active = active;
         if (!(skip & 4)) SUBGC_TRY(launch_gemm_raw(p, sc.gemm_ws, sc.gemm_ws_bytes, st, &rp));
-        if (!(skip & 8)) attention_kernel<<<S, kAttThreads, smem, st>>>(rp.part, rp.splits, w->h2att.b, p_att, att, masks, w->alpha_net.w, w->alpha_net.b,
+        if (!(skip & 8)) launch_pdl(attention_kernel, dim3(S), dim3(kAttThreads), smem, st, rp.part, rp.splits, w->h2att.b, p_att, att, masks, w->alpha_net.w, w->alpha_net.b,
                                                                         sc.ctx, att_w, att_w_stride, S, len_max, H, AH, rows_per_ctx, active,
                                                                         use16 ? h16->ctx_hi : nullptr, use16 ? h16->ctx_lo : nullptr, use16 ? h16->Hp : 0);
         SUBGC_LAUNCH_CHECK();
@@ -650,7 +740,7 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
     }
     p.active = active;
     if (!(skip & 16)) SUBGC_TRY(launch_gemm_raw(p, sc.gemm_ws, sc.gemm_ws_bytes, st, &rp));
-    if (!(skip & 32)) lstm_reduce_cell_kernel<<<pw_blocks, 256, 0, st>>>(rp.part, rp.splits, w->lang_b_ih, w->lang_b_hh, c_in + SH, parent, h_out + SH,
+    if (!(skip & 32)) launch_pdl(lstm_reduce_cell_kernel, dim3(pw_blocks), dim3(256), (size_t)0, st, rp.part, rp.splits, w->lang_b_ih, w->lang_b_hh, c_in + SH, parent, h_out + SH,
                                                                          c_out + SH, S, H, active, nullptr, 1, use16 ? h16->hout_hi + SHp : nullptr,
                                                                          use16 ? h16->hout_lo + SHp : nullptr, use16 ? h16->Hp : 0);
     SUBGC_LAUNCH_CHECK();
@@ -744,6 +834,8 @@ __global__ void __launch_bounds__(256) beam_step_kernel(const BeamArgs a) {
     __shared__ int s_ix[kMaxBeam][kMaxBeam];
     __shared__ int s_q[kMaxBeam], s_tok[kMaxBeam];
     __shared__ float s_p[kMaxBeam], s_r[kMaxBeam];
+    pdl_trigger();
+    pdl_wait();
     const int sg = blockIdx.x, b = a.b, t = a.t, T = a.T, V1 = a.V1;
     const int rows = (t == 0) ? 1 : b;
     const int* seq_prev = a.seq_prev + (size_t)sg * b * T;
@@ -853,9 +945,16 @@ __global__ void __launch_bounds__(256) beam_step_kernel(const BeamArgs a) {
 
 using namespace subgc;
 
+extern "C" int subgc_debug_att_trace(unsigned long long* host_out, int n_blocks) {
+    unsigned long long* buf = att_trace_buffer();
+    if (!buf || !host_out || n_blocks > 1024) return SUBGC_E_INVALID;
+    cudaDeviceSynchronize();
+    return cudaMemcpy(host_out, buf, (size_t)n_blocks * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess ? SUBGC_OK : SUBGC_E_CUDA;
+}
+
 extern "C" int subgc_log_softmax_fwd(int rows, int V1, const float* logits, float* logp, size_t ld_out, subgc_stream_t stream) {
     SUBGC_CHECK_ARG(logits && logp && rows > 0 && V1 > 0 && ld_out >= (size_t)V1, "subgc_log_softmax_fwd: bad arguments");
-    log_softmax_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, logp, V1, ld_out, nullptr);
+    launch_pdl(log_softmax_kernel, dim3(rows), dim3(256), (size_t)0, static_cast<cudaStream_t>(stream), logits, logp, V1, ld_out, (const int*)nullptr);
     SUBGC_LAUNCH_CHECK();
     return SUBGC_OK;
 }
@@ -889,7 +988,7 @@ extern "C" int subgc_decode_step(const subgc_dims* d, const subgc_weights* w, in
     if (!ok || !ws.ok()) { set_error("subgc_decode_step: workspace too small"); return SUBGC_E_WORKSPACE; }
     SUBGC_TRY(launch_step(d, w, n_rows, len_max, rows_per_ctx, reinterpret_cast<const long long*>(it), nullptr, nullptr, fc, att, p_att, masks, h_in,
                           c_in, h_out, c_out, logits, nullptr, att_weights, len_max, sc, nullptr, 0, st));
-    log_softmax_kernel<<<n_rows, 256, 0, st>>>(logits, logprobs, d->vocab1, (size_t)d->vocab1, nullptr);
+    launch_pdl(log_softmax_kernel, dim3(n_rows), dim3(256), (size_t)0, st, (const float*)logits, logprobs, (int)d->vocab1, (size_t)d->vocab1, (const int*)nullptr);
     SUBGC_LAUNCH_CHECK();
     return SUBGC_OK;
 }
@@ -958,7 +1057,7 @@ extern "C" int subgc_decode_sample(const subgc_dims* d, const subgc_weights* w, 
         a.seq_lp = seq_logprobs; a.count = count; a.active = active;
         a.embed = w->embed; a.xt = xt; a.X = d->enc;
         a.xt16_hi = s16 ? b16.xt[0] : nullptr; a.xt16_lo = s16 ? b16.xt[1] : nullptr; a.Xp = s16 ? b16.Xp : 0;
-        if (!(skip_mask() & 128)) select_kernel<<<S, kSelectThreads, (size_t)V1 * sizeof(float), st>>>(a);
+        if (!(skip_mask() & 128)) launch_pdl(select_kernel, dim3(S), dim3(kSelectThreads), (size_t)V1 * sizeof(float), st, a);
         SUBGC_LAUNCH_CHECK();
     }
     steps_done_kernel<<<1, 1, 0, st>>>(count, T, steps_done);
@@ -997,7 +1096,7 @@ extern "C" int subgc_decode_teacher(const subgc_dims* d, const subgc_weights* w,
         const int in = i & 1, out = in ^ 1;
         SUBGC_TRY(launch_step(d, w, S, len_max, 1, tok_cols + (size_t)i * S, nullptr, nullptr, fc, att, p_att, masks, hbuf[in], cbuf[in], hbuf[out],
                               cbuf[out], logits, nullptr, nullptr, 0, sc, flags + i, 0, st, sc.gates));
-        log_softmax_kernel<<<S, 256, 0, st>>>(logits, outputs + (size_t)i * V1, V1, (size_t)n_steps * V1, flags + i);
+        launch_pdl(log_softmax_kernel, dim3(S), dim3(256), (size_t)0, st, (const float*)logits, outputs + (size_t)i * V1, V1, (size_t)n_steps * V1, (const int*)(flags + i));
         SUBGC_LAUNCH_CHECK();
     }
     return SUBGC_OK;
@@ -1066,7 +1165,7 @@ extern "C" int subgc_decode_beam(const subgc_dims* d, const subgc_weights* w, in
         a.sum = sum; a.it = it; a.parent = parent;
         a.done_seq = reinterpret_cast<long long*>(done_seq); a.done_logps = done_logps; a.done_p = done_p; a.done_unaug_p = done_unaug_p;
         a.done_count = done_count; a.done_total = done_total;
-        beam_step_kernel<<<n_sub, 256, 0, st>>>(a);
+        launch_pdl(beam_step_kernel, dim3(n_sub), dim3(256), (size_t)0, st, a);
         SUBGC_LAUNCH_CHECK();
         if (t == T - 1) break;  // the reference's final get_logprobs_state result is never read (CaptionModel.py:170-171)
         const int in = (t + 1) & 1, out = in ^ 1;

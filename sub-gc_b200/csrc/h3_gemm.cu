@@ -55,7 +55,6 @@ struct H3Params {
 };
 
 __global__ void __launch_bounds__(H3_THREADS, 1) h3_gemm_kernel(const __grid_constant__ H3Params p) {
-    if (p.active != nullptr && *p.active == 0) return;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -70,7 +69,7 @@ __global__ void __launch_bounds__(H3_THREADS, 1) h3_gemm_kernel(const __grid_con
 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < H3_STAGES; ++s) {
-            mbar_init(bar_base + 8 * s, 1);        // full: producer arrive + tx bytes
+            mbar_init(bar_base + 8 * s, 2);        // full: two producer arrivals (weight tiles, activation tiles) + their tx bytes
             mbar_init(bar_base + 32 + 8 * s, 1);   // empty: tcgen05.commit
         }
         mbar_init(bar_base + 64, 1);               // accumulator ready
@@ -84,30 +83,53 @@ __global__ void __launch_bounds__(H3_THREADS, 1) h3_gemm_kernel(const __grid_con
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = *tmem_slot;
+    pdl_trigger();   // the next kernel of the stream may start its own prologue
 
-    if (warp == 0) {
+    // ---- producer helpers: the weight tiles of a k-block do not depend on the preceding kernel, the activation tiles do
+    int seg_w = 0, seg_x = 0;
+    auto issue_w = [&](int i) {
+        const int kb = kb_begin + i;
+        while (seg_w < p.nseg - 1 && kb >= p.seg_kb_end[seg_w]) ++seg_w;
+        const int kc = (kb - (seg_w == 0 ? 0 : p.seg_kb_end[seg_w - 1])) * H3_BK;
+        const int s = i % H3_STAGES;
+        const uint32_t st = base + s * H3_STAGE_BYTES, full = bar_base + 8 * s;
+        mbar_arrive_expect_tx(full, 2 * H3_W_BYTES);
+        tma_load_2d(st, &p.tm_wh[seg_w], full, kc, n0);
+        tma_load_2d(st + H3_W_BYTES, &p.tm_wl[seg_w], full, kc, n0);
+    };
+    auto issue_x = [&](int i) {
+        const int kb = kb_begin + i;
+        while (seg_x < p.nseg - 1 && kb >= p.seg_kb_end[seg_x]) ++seg_x;
+        const int kc = (kb - (seg_x == 0 ? 0 : p.seg_kb_end[seg_x - 1])) * H3_BK;
+        const int s = i % H3_STAGES;
+        const uint32_t st = base + s * H3_STAGE_BYTES, full = bar_base + 8 * s;
+        mbar_arrive_expect_tx(full, 2 * H3_X_BYTES);
+        tma_load_2d(st + 2 * H3_W_BYTES, &p.tm_xh[seg_x], full, kc, m0);
+        tma_load_2d(st + 2 * H3_W_BYTES + H3_X_BYTES, &p.tm_xl[seg_x], full, kc, m0);
+    };
+    const bool producer = (warp == 0 && lane == 0);
+    const int pre = min(nkb, H3_STAGES);
+    if (producer) {   // fill the weight half of the ring while the predecessor kernel is still running
+        for (int sgi = 0; sgi < p.nseg; ++sgi) { prefetch_tensormap(&p.tm_wh[sgi]); prefetch_tensormap(&p.tm_wl[sgi]); }
+        for (int i = 0; i < pre; ++i) issue_w(i);
+        for (int sgi = 0; sgi < p.nseg; ++sgi) { prefetch_tensormap(&p.tm_xh[sgi]); prefetch_tensormap(&p.tm_xl[sgi]); }
+    }
+    pdl_wait();      // from here on the activations / flags written by earlier kernels are visible
+    const bool act = (p.active == nullptr) || (*p.active != 0);
+    if (!act) {
+        if (producer)   // drain the prefetched weight tiles before the CTA retires
+            for (int i = 0; i < pre; ++i) { mbar_arrive(bar_base + 8 * i); mbar_wait(bar_base + 8 * i, 0); }
+    } else if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            for (int sgi = 0; sgi < p.nseg; ++sgi) {
-                prefetch_tensormap(&p.tm_wh[sgi]); prefetch_tensormap(&p.tm_wl[sgi]);
-                prefetch_tensormap(&p.tm_xh[sgi]); prefetch_tensormap(&p.tm_xl[sgi]);
-            }
-            int seg = 0;
             for (int i = 0; i < nkb; ++i) {
-                const int kb = kb_begin + i;
-                while (seg < p.nseg - 1 && kb >= p.seg_kb_end[seg]) ++seg;
-                const int seg_kb0 = seg == 0 ? 0 : p.seg_kb_end[seg - 1];
                 const int s = i % H3_STAGES;
-                const uint32_t ph = (uint32_t)(i / H3_STAGES) & 1u;
-                mbar_wait(bar_base + 32 + 8 * s, ph ^ 1u);
-                const uint32_t st = base + s * H3_STAGE_BYTES;
-                const uint32_t full = bar_base + 8 * s;
-                const int kc = (kb - seg_kb0) * H3_BK;
-                mbar_arrive_expect_tx(full, H3_STAGE_BYTES);
-                tma_load_2d(st, &p.tm_wh[seg], full, kc, n0);
-                tma_load_2d(st + H3_W_BYTES, &p.tm_wl[seg], full, kc, n0);
-                tma_load_2d(st + 2 * H3_W_BYTES, &p.tm_xh[seg], full, kc, m0);
-                tma_load_2d(st + 2 * H3_W_BYTES + H3_X_BYTES, &p.tm_xl[seg], full, kc, m0);
+                if (i >= pre) {
+                    const uint32_t ph = (uint32_t)(i / H3_STAGES) & 1u;
+                    mbar_wait(bar_base + 32 + 8 * s, ph ^ 1u);
+                    issue_w(i);
+                }
+                issue_x(i);
             }
         }
     } else if (warp == 1) {
@@ -278,6 +300,8 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restric
 // activations of one K segment (row gather / shared rows / ReLU-on-load applied) -> hi / lo [M, Kp]
 __global__ void __launch_bounds__(256) split_rows_kernel(const GemmSeg g, int M, int Kp, unsigned short* __restrict__ hi, unsigned short* __restrict__ lo,
                                                          const int* __restrict__ active, int* __restrict__ overflow) {
+    pdl_trigger();
+    pdl_wait();
     if (active != nullptr && *active == 0) return;
     const int kq = Kp >> 2;
     const size_t total = (size_t)M * kq;
@@ -431,7 +455,7 @@ int launch_gemm_h3(const GemmProblem& p, void* ws_, size_t ws_bytes, cudaStream_
             const size_t quads = (size_t)p.M * (Kp >> 2);
             int gb = (int)((quads + 255) / 256);
             if (gb > kNumSMs * 8) gb = kNumSMs * 8;
-            split_rows_kernel<<<gb, 256, 0, stream>>>(g, p.M, Kp, th, tl, p.active, nullptr);
+            SUBGC_CUDA(launch_pdl(split_rows_kernel, dim3(gb), dim3(256), (size_t)0, stream, g, p.M, Kp, th, tl, p.active, (int*)nullptr));
             SUBGC_LAUNCH_CHECK();
             xh = th; xl = tl; xld = Kp;
         }
@@ -459,7 +483,7 @@ int launch_gemm_h3(const GemmProblem& p, void* ws_, size_t ws_bytes, cudaStream_
         attr_set = true;
     }
     dim3 grid(pl.n_tiles, pl.m_tiles, pl.splits);
-    h3_gemm_kernel<<<grid, H3_THREADS, H3_SMEM_BYTES, stream>>>(hp);
+    SUBGC_CUDA(launch_pdl(h3_gemm_kernel, grid, dim3(H3_THREADS), (size_t)H3_SMEM_BYTES, stream, hp));
     SUBGC_LAUNCH_CHECK();
     if (direct) return SUBGC_OK;
     if (raw) {
