@@ -65,15 +65,22 @@ typedef struct subgc_linear {
     const float* b; /* [out] */
 } subgc_linear;
 
-/* Split-fp16 copy of one weight matrix for the tensor cores (subgc_pack_weight): w[r,c] = hi[r,c] + lo[r,c] * 2^-11 with
- * hi, lo IEEE fp16, i.e. the same 4 bytes per weight as the fp32 tensor it mirrors and 22 of its 24 mantissa bits.
- * The fp32 tensor stays the source of truth (and the lookup key): contractions whose weight pointer falls inside
- * [w, w + rows*cols) read the packed copy instead; weights without one take the fp32 (split-TF32) path. */
+/* Split-fp16 copy of one weight matrix for the tensor cores (subgc_pack_weight): w[r,c] = hi + lo * 2^-11 with hi, lo IEEE
+ * fp16, i.e. the same 4 bytes per weight as the fp32 tensor it mirrors and 22 of its 24 mantissa bits.  Layout: k-block-major
+ * [kb][rows][32] -- for a block of 32 consecutive columns all rows are contiguous (64 bytes each), so the [tile rows x 32] tile a
+ * CTA streams per step is ONE contiguous run in HBM (DRAM page locality; a row-major layout gives 64-byte pieces 2-12 KB apart,
+ * measured at < 50 % of the HBM rate).  The columns may be cut into K segments (the un-concatenated LSTM inputs
+ * [h_lang | fc | x_t]): every segment starts on a k-block boundary and is zero-padded to a multiple of 32 columns.
+ * The fp32 tensor stays the source of truth (and the lookup key): contractions whose weight operand is exactly one segment of
+ * `w` read the packed copy instead; anything else takes the fp32 (split-TF32) path. */
+#define SUBGC_PACK_MAX_SEG 4
 typedef struct subgc_packed {
     const float* w;      /* the fp32 [rows, cols] contiguous tensor this was packed from */
-    const uint16_t* hi;  /* [rows, ld16] fp16 */
-    const uint16_t* lo;  /* [rows, ld16] fp16, scaled by 2^11 */
-    int32_t rows, cols, ld16;
+    const uint16_t* hi;  /* [kb_total][rows][32] fp16 */
+    const uint16_t* lo;  /* same shape, scaled by 2^11 */
+    int32_t rows, cols;
+    int32_t n_seg;                           /* 1..SUBGC_PACK_MAX_SEG */
+    int32_t seg_col[SUBGC_PACK_MAX_SEG + 1]; /* 0 = seg_col[0] < ... < seg_col[n_seg] = cols */
 } subgc_packed;
 
 /* Device pointers to the reference state_dict tensors, un-repacked (key names in comments). */
@@ -122,14 +129,18 @@ int subgc_version(void);
 unsigned long long subgc_launch_count(void);
 /* debugging aid (env SUBGC_ATT_TRACE=1, synchronises): per-block stage time stamps [n_blocks][8] of the last fused att-phase launch */
 int subgc_debug_att_trace(unsigned long long* host_out, int n_blocks);
+/* debugging aid (env SUBGC_TRACE=1, synchronises): globaltimer stamps of the decode-loop launches, per launch
+ * [first block start, last block end, first block past its dependency wait, last block past it].
+ * op 0 restart slot numbering, op 1 reset stamps, op 2 copy out up to n slots (stamps [n][4], kernel ids [n]); returns slots used */
+int subgc_debug_trace(int op, unsigned long long* stamps, int* ids, int n);
 
-/* Packs an fp32 weight matrix [rows, cols] (leading dim ldw) into the split-fp16 form of subgc_packed; ld16 =
- * subgc_pack_ld(cols) (cols rounded up to 8), each output array holds rows * ld16 fp16 values.  `overflow` (device,
+/* Packs an fp32 weight matrix [rows, cols] (leading dim ldw) into the split-fp16 form of subgc_packed, columns cut at
+ * seg_col[0..n_seg].  Each output array holds subgc_pack_elems(rows, n_seg, seg_col) fp16 values.  `overflow` (device,
  * nullable) is OR-ed with 1 when a weight does not fit fp16 (|w| > 65504): such a tensor must not be registered.
  * Replaces nothing in the reference: nn.Linear / nn.LSTMCell keep fp32 weights (models/AttModel.py:393-398). */
-int subgc_pack_ld(int cols);
-int subgc_pack_weight(int rows, int cols, const float* w, int ldw, uint16_t* hi, uint16_t* lo, int32_t* overflow,
-                      subgc_stream_t stream);
+size_t subgc_pack_elems(int rows, int n_seg, const int32_t* seg_col);
+int subgc_pack_weight(int rows, int cols, const float* w, int ldw, int n_seg, const int32_t* seg_col, uint16_t* hi,
+                      uint16_t* lo, int32_t* overflow, subgc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Building block: C[M,N] = act((A[gather] . W^T + bias + addend) / div), the nn.Linear contraction every stage

@@ -88,9 +88,9 @@ struct GemmSeg {
     // split-fp16 operands of the h3 tensor-core path (h3_gemm.cu): v = hi + lo * 2^-11, both fp16.  W16_* come from a packed copy
     // of the weight tensor (subgc_pack_weight, resolved by resolve_packs); A16_* are optional pre-split activations written by
     // the producer kernel (rows 1:1 with the output rows), otherwise the launcher splits A itself.
-    const unsigned short* W16_hi = nullptr;
+    const unsigned short* W16_hi = nullptr;   // first k-block plane of this segment, [kb][w16_rows][32] (k-block-major)
     const unsigned short* W16_lo = nullptr;
-    int ldw16 = 0;
+    int w16_rows = 0;                         // rows per k-block plane of the packed tensor
     const unsigned short* A16_hi = nullptr;
     const unsigned short* A16_lo = nullptr;
     int lda16 = 0;
@@ -173,6 +173,30 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = at; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
+// ---- timeline tracing (debug, SUBGC_TRACE=1): [first block start, last block end] of every launch of the decode loop ----------
+struct TraceSlot { unsigned long long* buf; int seq; };   // buf == nullptr in normal operation
+TraceSlot next_trace_slot(int kernel_id);                  // host: hands out consecutive slots (api.cu)
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void trace_begin(const TraceSlot& t) {
+    if (t.buf != nullptr && threadIdx.x == 0) atomicMin(&t.buf[4 * t.seq], globaltimer_ns());
+}
+__device__ __forceinline__ void trace_end(const TraceSlot& t) {
+    if (t.buf != nullptr && threadIdx.x == 0) atomicMax(&t.buf[4 * t.seq + 1], globaltimer_ns());
+}
+__device__ __forceinline__ void trace_released(const TraceSlot& t) {   // right after pdl_wait(): [first, last] block released
+    if (t.buf != nullptr && threadIdx.x == 0) {
+        const unsigned long long now = globaltimer_ns();
+        atomicMin(&t.buf[4 * t.seq + 2], now);
+        atomicMax(&t.buf[4 * t.seq + 3], now);
+    }
 }
 #endif
 

@@ -29,16 +29,19 @@ __global__ void __launch_bounds__(256) lstm_reduce_cell_kernel(const float* __re
                                                                const long long* __restrict__ parent, float* __restrict__ h_out,
                                                                float* __restrict__ c_out, int S, int H, const int* __restrict__ active,
                                                                const float* __restrict__ addend, int add_div,
-                                                               unsigned short* __restrict__ h16_hi, unsigned short* __restrict__ h16_lo, int Hp) {
+                                                               unsigned short* __restrict__ h16_hi, unsigned short* __restrict__ h16_lo, int Hp,
+                                                               TraceSlot trace) {
     // h16_hi / h16_lo (nullable, [S, Hp]): the split-fp16 copy of h' the next contractions read as their activation operand
     // addend != nullptr: a pre-computed [S / add_div, 4H] term (the step-invariant fc segment with both biases folded in)
     // replaces b_ih + b_hh
+    trace_begin(trace);
     pdl_trigger();
     pdl_wait();
+    trace_released(trace);
     if (active != nullptr && *active == 0) return;
     const size_t zs = (size_t)S * 4 * H;
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= S * H) return;
+    if (idx >= S * H) { trace_end(trace); return; }
     int r = idx / H, j = idx - r * H;
     const float* g = part + (size_t)r * 4 * H + j;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -61,6 +64,7 @@ __global__ void __launch_bounds__(256) lstm_reduce_cell_kernel(const float* __re
     const float hv = sigmoidf_(acc[3]) * tanhf(c);
     h_out[idx] = hv;
     if (h16_hi) split_f16_store(hv, h16_hi, h16_lo, (size_t)r * Hp + j);
+    trace_end(trace);
 }
 
 // ---- fused attention: one block per decode row -------------------------------------------------------------------
@@ -163,7 +167,8 @@ __global__ void __launch_bounds__(kAttThreads) attention_kernel(const float* __r
                                                                 const float* __restrict__ alpha_b, float* __restrict__ ctx, float* __restrict__ att_w,
                                                                 int att_w_stride, int S, int len_max, int H, int AH, int rows_per_ctx,
                                                                 const int* __restrict__ active, unsigned short* __restrict__ c16_hi,
-                                                                unsigned short* __restrict__ c16_lo, int Hp) {
+                                                                unsigned short* __restrict__ c16_lo, int Hp, TraceSlot trace) {
+    trace_begin(trace);
     pdl_trigger();
     {   // the row's attention operands do not depend on this step: request them into L2 while the predecessor kernels still run
         const int cr0 = blockIdx.x / rows_per_ctx;
@@ -174,6 +179,7 @@ __global__ void __launch_bounds__(kAttThreads) attention_kernel(const float* __r
         for (size_t o = (size_t)threadIdx.x * 128; o < nb_a; o += (size_t)blockDim.x * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(af + o));
     }
     pdl_wait();
+    trace_released(trace);
     if (active != nullptr && *active == 0) return;
     extern __shared__ float s_att[];  // [AH] atth | [AH] alpha_w | [64] e | [4][H] context partials
     float* s_h = s_att;
@@ -189,6 +195,7 @@ __global__ void __launch_bounds__(kAttThreads) attention_kernel(const float* __r
     }
     __syncthreads();
     attention_row_body(s_h, s_w, s_e, s_c, r, cr, p_att, att, masks, alpha_b, ctx, att_w, att_w_stride, len_max, H, AH, c16_hi, c16_lo, Hp);
+    trace_end(trace);
 }
 
 // ---- fused attention phase of a decode step: one cluster kernel instead of cell + h2att GEMM + attention --------------------
@@ -415,13 +422,16 @@ struct SelectArgs {
     int X;
     unsigned short *xt16_hi, *xt16_lo;   // nullable split-fp16 copy of xt, [S, Xp]
     int Xp;
+    TraceSlot trace;
 };
 
 constexpr int kSelectThreads = 1024;  // one block per row: the row is latency-bound, so use every warp slot of the SM
 
 __global__ void __launch_bounds__(kSelectThreads) select_kernel(const SelectArgs a) {
+    trace_begin(a.trace);
     pdl_trigger();
     pdl_wait();
+    trace_released(a.trace);
     if (a.active != nullptr && *a.active == 0) return;
     __shared__ float redv[32];
     __shared__ int redi[32];
@@ -526,6 +536,7 @@ __global__ void __launch_bounds__(kSelectThreads) select_kernel(const SelectArgs
             if (a.xt16_hi) split_f16_store(xv, a.xt16_hi, a.xt16_lo, (size_t)r * a.Xp + j);
         }
     }
+    trace_end(a.trace);
 }
 
 __global__ void steps_done_kernel(const int* __restrict__ count, int T, int* __restrict__ steps_done) {
@@ -711,7 +722,7 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
     } else {
         if (!(skip & 2)) launch_pdl(lstm_reduce_cell_kernel, dim3(pw_blocks), dim3(256), (size_t)0, st, rp.part, rp.splits, w->att_b_ih, w->att_b_hh, c_in, parent, h_out, c_out, S,
                                                                             H, active, fc_pre, rows_per_ctx, use16 ? h16->hout_hi : nullptr,
-                                                                            use16 ? h16->hout_lo : nullptr, use16 ? h16->Hp : 0);
+                                                                            use16 ? h16->hout_lo : nullptr, use16 ? h16->Hp : 0, next_trace_slot(2));
         SUBGC_LAUNCH_CHECK();
         // attention (AttModel.py:445-471); the h2att partials are reduced inside the attention kernel
         p = GemmProblem(); p.wts = w;
@@ -722,7 +733,7 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
         if (!(skip & 4)) SUBGC_TRY(launch_gemm_raw(p, sc.gemm_ws, sc.gemm_ws_bytes, st, &rp));
         if (!(skip & 8)) launch_pdl(attention_kernel, dim3(S), dim3(kAttThreads), smem, st, rp.part, rp.splits, w->h2att.b, p_att, att, masks, w->alpha_net.w, w->alpha_net.b,
                                                                         sc.ctx, att_w, att_w_stride, S, len_max, H, AH, rows_per_ctx, active,
-                                                                        use16 ? h16->ctx_hi : nullptr, use16 ? h16->ctx_lo : nullptr, use16 ? h16->Hp : 0);
+                                                                        use16 ? h16->ctx_hi : nullptr, use16 ? h16->ctx_lo : nullptr, use16 ? h16->Hp : 0, next_trace_slot(3));
         SUBGC_LAUNCH_CHECK();
     }
     if (upto == 1) return SUBGC_OK;
@@ -742,7 +753,7 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
     if (!(skip & 16)) SUBGC_TRY(launch_gemm_raw(p, sc.gemm_ws, sc.gemm_ws_bytes, st, &rp));
     if (!(skip & 32)) launch_pdl(lstm_reduce_cell_kernel, dim3(pw_blocks), dim3(256), (size_t)0, st, rp.part, rp.splits, w->lang_b_ih, w->lang_b_hh, c_in + SH, parent, h_out + SH,
                                                                          c_out + SH, S, H, active, nullptr, 1, use16 ? h16->hout_hi + SHp : nullptr,
-                                                                         use16 ? h16->hout_lo + SHp : nullptr, use16 ? h16->Hp : 0);
+                                                                         use16 ? h16->hout_lo + SHp : nullptr, use16 ? h16->Hp : 0, next_trace_slot(2));
     SUBGC_LAUNCH_CHECK();
     // logit (AttModel.py:336,340); eval mode: dropout is the identity
     p = GemmProblem(); p.wts = w;
@@ -1057,6 +1068,7 @@ extern "C" int subgc_decode_sample(const subgc_dims* d, const subgc_weights* w, 
         a.seq_lp = seq_logprobs; a.count = count; a.active = active;
         a.embed = w->embed; a.xt = xt; a.X = d->enc;
         a.xt16_hi = s16 ? b16.xt[0] : nullptr; a.xt16_lo = s16 ? b16.xt[1] : nullptr; a.Xp = s16 ? b16.Xp : 0;
+        a.trace = next_trace_slot(4);
         if (!(skip_mask() & 128)) launch_pdl(select_kernel, dim3(S), dim3(kSelectThreads), (size_t)V1 * sizeof(float), st, a);
         SUBGC_LAUNCH_CHECK();
     }

@@ -11,8 +11,8 @@
 // (tools/gemm_check.py).  Activations are split by their producer kernel (decode loop) or by split_rows_kernel here.
 //
 // One CTA (192 threads, 1 per SM) computes a 128 x 256 tile over its k-range:
-//   warp 0     TMA producer: per k-block (32 fp16 = one 64-byte swizzled row) four tiles  Whi | Wlo [256 x 32], Xhi | Xlo [128 x 32]
-//   warp 1     one thread issues 2 x 3 tcgen05.mma.kind::f16 (M=128, N=256, K=16) per k-block: main chain -> TMEM columns [0,256),
+//   warp 0     TMA producer: per k-block (32 fp16 = one 128-byte swizzled row) four tiles  Whi | Wlo [bn x 64], Xhi | Xlo [128 x 64]
+//   warp 1     one thread issues 4 x 3 tcgen05.mma.kind::f16 (M=128, N=bn, K=16) per k-block: main chain -> TMEM columns [0,256),
 //              the two cross terms -> columns [256,512) (separate chains: the accumulator truncation of the main chain is not
 //              multiplied by three adds per step, and the cross sum is scaled by 2^-11 once, exactly, in the epilogue)
 //   warps 2-5  epilogue: tcgen05.ld -> main + cross * 2^-11 -> split-K partial [z][M][N] or the in-place epilogue (single split)
@@ -26,16 +26,15 @@
 namespace subgc {
 
 constexpr int H3_BM = 128;
-constexpr int H3_BN = 256;
-constexpr int H3_BK = 32;   // fp16 elements per k-block (64-byte rows)
-constexpr int H3_STAGES = 4;
+constexpr int H3_BN_MAX = 256;
+constexpr int H3_BK = 64;   // fp16 elements per k-block: 128-byte rows (TMA issues one request per box row: 64-byte rows measured request-bound)
+constexpr int H3_MAX_STAGES = 8;
 constexpr int H3_THREADS = 192;
-constexpr int H3_W_BYTES = H3_BN * H3_BK * 2;                    // 16 KB
-constexpr int H3_X_BYTES = H3_BM * H3_BK * 2;                    // 8 KB
-constexpr int H3_STAGE_BYTES = 2 * H3_W_BYTES + 2 * H3_X_BYTES;  // Whi | Wlo | Xhi | Xlo = 48 KB
-constexpr int H3_SMEM_BYTES = H3_STAGES * H3_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int H3_X_BYTES = H3_BM * H3_BK * 2;                    // 16 KB
+constexpr int H3_SMEM_EXTRA = 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int H3_SMEM_BUDGET = 196 * 1024;   // pipeline bytes: leaves ~30 KB of the SM's shared memory for a co-resident consumer kernel (PDL)
 constexpr int H3_MAX_SEG = 4;
-constexpr int H3_MAX_CHAIN = 64;   // k-blocks (128 MMA accumulation steps) per TMEM chain before the fp32 combine of split-K
+constexpr int H3_MAX_CHAIN = 32;   // k-blocks (128 MMA accumulation steps) per TMEM chain before the fp32 combine of split-K
 constexpr float H3_LO_INV = kH3LoInv;
 
 struct H3Params {
@@ -43,6 +42,8 @@ struct H3Params {
     int seg_kb_end[H3_MAX_SEG];
     int nseg;
     int M, N;
+    int bn;        // tile width (multiple of 32, <= 256): the weight tiles are [bn x 32]
+    int stages;    // ring depth (<= 8)
     int kb_total, kb_per_split;
     float* part;   // [splits][M][N]
     int direct;    // single split: apply the epilogue here and write C
@@ -52,31 +53,38 @@ struct H3Params {
     const int* active;
     CUtensorMap tm_part;   // [splits, M, N] fp32 partials, box 32 x 32 x 1, 128-byte swizzle (valid when tma_part)
     int tma_part;          // 1: the partial tiles leave through shared memory + TMA stores (full 128-byte lines) instead of per-thread rows
+    TraceSlot trace;
 };
 
 __global__ void __launch_bounds__(H3_THREADS, 1) h3_gemm_kernel(const __grid_constant__ H3Params p) {
     extern __shared__ uint8_t smem_raw[];
+    trace_begin(p.trace);
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t bar_base = base + H3_STAGES * H3_STAGE_BYTES;
-    // barriers: full[s] @ +0, empty[s] @ +32, accum @ +64, tmem slot @ +72
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + H3_STAGES * H3_STAGE_BYTES + 72);
+    const int bn = p.bn, stages = p.stages;
+    const uint32_t w_bytes = (uint32_t)bn * H3_BK * 2;                 // one weight tile (hi or lo)
+    const uint32_t stage_bytes = 2 * w_bytes + 2 * H3_X_BYTES;         // Whi | Wlo | Xhi | Xlo
+    const uint32_t bar_base = base + (uint32_t)stages * stage_bytes;
+    // barriers: full[s] @ +0, empty[s] @ +64, accum @ +128, tmem slot @ +136
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + (size_t)stages * stage_bytes + 136);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * H3_BN, m0 = blockIdx.y * H3_BM;
+    const int n0 = blockIdx.x * bn, m0 = blockIdx.y * H3_BM;
     const int kb_begin = blockIdx.z * p.kb_per_split;
     const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
     const int nkb = kb_end - kb_begin;
+    const uint32_t tmem_cols = bn <= 128 ? 256u : 512u;   // main chain | cross chain
+    const uint32_t cross = tmem_cols >> 1;
 
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < H3_STAGES; ++s) {
+        for (int s = 0; s < stages; ++s) {
             mbar_init(bar_base + 8 * s, 2);        // full: two producer arrivals (weight tiles, activation tiles) + their tx bytes
-            mbar_init(bar_base + 32 + 8 * s, 1);   // empty: tcgen05.commit
+            mbar_init(bar_base + 64 + 8 * s, 1);   // empty: tcgen05.commit
         }
-        mbar_init(bar_base + 64, 1);               // accumulator ready
+        mbar_init(bar_base + 128, 1);              // accumulator ready
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -91,30 +99,31 @@ __global__ void __launch_bounds__(H3_THREADS, 1) h3_gemm_kernel(const __grid_con
         const int kb = kb_begin + i;
         while (seg_w < p.nseg - 1 && kb >= p.seg_kb_end[seg_w]) ++seg_w;
         const int kc = (kb - (seg_w == 0 ? 0 : p.seg_kb_end[seg_w - 1])) * H3_BK;
-        const int s = i % H3_STAGES;
-        const uint32_t st = base + s * H3_STAGE_BYTES, full = bar_base + 8 * s;
-        mbar_arrive_expect_tx(full, 2 * H3_W_BYTES);
-        tma_load_2d(st, &p.tm_wh[seg_w], full, kc, n0);
-        tma_load_2d(st + H3_W_BYTES, &p.tm_wl[seg_w], full, kc, n0);
+        const int s = i % stages;
+        const uint32_t st = base + s * stage_bytes, full = bar_base + 8 * s;
+        mbar_arrive_expect_tx(full, 2 * w_bytes);
+        tma_load_3d(st, &p.tm_wh[seg_w], full, 0, n0, kc / H3_BK);           // packed weights are k-block-major: one contiguous run
+        tma_load_3d(st + w_bytes, &p.tm_wl[seg_w], full, 0, n0, kc / H3_BK);
     };
     auto issue_x = [&](int i) {
         const int kb = kb_begin + i;
         while (seg_x < p.nseg - 1 && kb >= p.seg_kb_end[seg_x]) ++seg_x;
         const int kc = (kb - (seg_x == 0 ? 0 : p.seg_kb_end[seg_x - 1])) * H3_BK;
-        const int s = i % H3_STAGES;
-        const uint32_t st = base + s * H3_STAGE_BYTES, full = bar_base + 8 * s;
+        const int s = i % stages;
+        const uint32_t st = base + s * stage_bytes, full = bar_base + 8 * s;
         mbar_arrive_expect_tx(full, 2 * H3_X_BYTES);
-        tma_load_2d(st + 2 * H3_W_BYTES, &p.tm_xh[seg_x], full, kc, m0);
-        tma_load_2d(st + 2 * H3_W_BYTES + H3_X_BYTES, &p.tm_xl[seg_x], full, kc, m0);
+        tma_load_2d(st + 2 * w_bytes, &p.tm_xh[seg_x], full, kc, m0);
+        tma_load_2d(st + 2 * w_bytes + H3_X_BYTES, &p.tm_xl[seg_x], full, kc, m0);
     };
     const bool producer = (warp == 0 && lane == 0);
-    const int pre = min(nkb, H3_STAGES);
+    const int pre = min(nkb, stages);
     if (producer) {   // fill the weight half of the ring while the predecessor kernel is still running
         for (int sgi = 0; sgi < p.nseg; ++sgi) { prefetch_tensormap(&p.tm_wh[sgi]); prefetch_tensormap(&p.tm_wl[sgi]); }
         for (int i = 0; i < pre; ++i) issue_w(i);
         for (int sgi = 0; sgi < p.nseg; ++sgi) { prefetch_tensormap(&p.tm_xh[sgi]); prefetch_tensormap(&p.tm_xl[sgi]); }
     }
     pdl_wait();      // from here on the activations / flags written by earlier kernels are visible
+    trace_released(p.trace);
     const bool act = (p.active == nullptr) || (*p.active != 0);
     if (!act) {
         if (producer)   // drain the prefetched weight tiles before the CTA retires
@@ -123,10 +132,10 @@ __global__ void __launch_bounds__(H3_THREADS, 1) h3_gemm_kernel(const __grid_con
         // ===== TMA producer =====
         if (lane == 0) {
             for (int i = 0; i < nkb; ++i) {
-                const int s = i % H3_STAGES;
+                const int s = i % stages;
                 if (i >= pre) {
-                    const uint32_t ph = (uint32_t)(i / H3_STAGES) & 1u;
-                    mbar_wait(bar_base + 32 + 8 * s, ph ^ 1u);
+                    const uint32_t ph = (uint32_t)(i / stages) & 1u;
+                    mbar_wait(bar_base + 64 + 8 * s, ph ^ 1u);
                     issue_w(i);
                 }
                 issue_x(i);
@@ -134,57 +143,51 @@ __global__ void __launch_bounds__(H3_THREADS, 1) h3_gemm_kernel(const __grid_con
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        // instruction descriptor: D fp32, A/B fp16, both K-major, N=256, M=128
-        const uint32_t idesc = (1u << 4) | ((uint32_t)(H3_BN >> 3) << 17) | ((uint32_t)(H3_BM >> 4) << 24);
+        // instruction descriptor: D fp32, A/B fp16, both K-major, N=bn, M=128
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(H3_BM >> 4) << 24);
         for (int i = 0; i < nkb; ++i) {
-            const int s = i % H3_STAGES;
-            const uint32_t ph = (uint32_t)(i / H3_STAGES) & 1u;
+            const int s = i % stages;
+            const uint32_t ph = (uint32_t)(i / stages) & 1u;
             mbar_wait(bar_base + 8 * s, ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
-                const uint32_t st = base + s * H3_STAGE_BYTES;
+                const uint32_t st = base + s * stage_bytes;
 #pragma unroll
                 for (int ks = 0; ks < H3_BK / 16; ++ks) {
-                    const uint64_t whi = umma_desc_sw64(st + ks * 32);
-                    const uint64_t wlo = umma_desc_sw64(st + H3_W_BYTES + ks * 32);
-                    const uint64_t xhi = umma_desc_sw64(st + 2 * H3_W_BYTES + ks * 32);
-                    const uint64_t xlo = umma_desc_sw64(st + 2 * H3_W_BYTES + H3_X_BYTES + ks * 32);
+                    const uint64_t whi = umma_desc_sw128(st + ks * 32);
+                    const uint64_t wlo = umma_desc_sw128(st + w_bytes + ks * 32);
+                    const uint64_t xhi = umma_desc_sw128(st + 2 * w_bytes + ks * 32);
+                    const uint64_t xlo = umma_desc_sw128(st + 2 * w_bytes + H3_X_BYTES + ks * 32);
                     const uint32_t acc = (i > 0 || ks > 0) ? 1u : 0u;
                     umma_f16_afill(tmem_d, xhi, whi, idesc, acc);
-                    umma_f16_alast(tmem_d + H3_BN, xhi, wlo, idesc, acc);
-                    umma_f16(tmem_d + H3_BN, xlo, whi, idesc, 1u);
+                    umma_f16_alast(tmem_d + cross, xhi, wlo, idesc, acc);
+                    umma_f16(tmem_d + cross, xlo, whi, idesc, 1u);
                 }
-                umma_commit(bar_base + 32 + 8 * s);              // stage free once these MMAs have read it
-                if (i == nkb - 1) umma_commit(bar_base + 64);    // accumulator complete
+                umma_commit(bar_base + 64 + 8 * s);              // stage free once these MMAs have read it
+                if (i == nkb - 1) umma_commit(bar_base + 128);   // accumulator complete
             }
             __syncwarp();
         }
     } else {
         // ===== epilogue warps (2..5): TMEM lanes of this warp = 32 * (warp % 4) =====
-        const int t = threadIdx.x - 64;
-        mbar_wait(bar_base + 64, 0);
+        mbar_wait(bar_base + 128, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3;
         const int row = m0 + q * 32 + lane;            // TMEM lane == output row
         float* out = p.part + (size_t)blockIdx.z * p.M * p.N + (size_t)row * p.N;
         const bool vec = ((p.N & 3) == 0);
         const uint32_t tlane = tmem_d + ((uint32_t)(q * 32) << 16);
-        const int nchunks = min(H3_BN / 32, (p.N - n0 + 31) / 32);
-        uint32_t ra[32], rb[32], na[32], nb[32];
-        SUBGC_TMEM_LD32(ra, tlane);
-        SUBGC_TMEM_LD32(rb, tlane + H3_BN);
-        (void)t;
+        const int nchunks = min(bn / 32, (p.N - n0 + 31) / 32);
+        uint32_t ra[32], rb[32];
         // staging tiles of the TMA-store path live in the pipeline stages (idle by now: every MMA has retired): 2 x 4 KB per warp
         const uint32_t sbuf = base + (uint32_t)q * 8192u;
         const bool tma_out = !p.direct && p.tma_part && (m0 + q * 32 < p.M);
 #pragma unroll 1
         for (int c = 0; c < nchunks; ++c) {
             const int col0 = n0 + c * 32;
+            SUBGC_TMEM_LD32(ra, tlane + (uint32_t)(c * 32));
+            SUBGC_TMEM_LD32(rb, tlane + cross + (uint32_t)(c * 32));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (c + 1 < nchunks) {  // next chunk's TMEM reads overlap this chunk's global stores
-                SUBGC_TMEM_LD32(na, tlane + (uint32_t)((c + 1) * 32));
-                SUBGC_TMEM_LD32(nb, tlane + H3_BN + (uint32_t)((c + 1) * 32));
-            }
             if (!p.direct && p.tma_part) {
                 if (tma_out) {
                     const uint32_t buf = sbuf + (uint32_t)(c & 1) * 4096u;
@@ -265,36 +268,50 @@ __global__ void __launch_bounds__(H3_THREADS, 1) h3_gemm_kernel(const __grid_con
                         if (col0 + j < p.N) out[col0 + j] = fmaf(__uint_as_float(rb[j]), H3_LO_INV, __uint_as_float(ra[j]));
                 }
             }
-            if (c + 1 < nchunks) {
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                for (int j = 0; j < 32; ++j) { ra[j] = na[j]; rb[j] = nb[j]; }
-            }
         }
         if (tma_out && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before the CTA retires
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();
+    trace_end(p.trace);
     if (warp == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
     }
 }
 
 // ---- fp32 -> (hi, lo) fp16 (split_f16, common.cuh) ------------------------------------------------------------------
-// weights: [rows, cols] fp32 (ld ldw) -> hi / lo [rows, ld16], tail columns zero
-__global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, int rows, int cols, int ldw, unsigned short* __restrict__ hi,
-                                                          unsigned short* __restrict__ lo, int ld16, int* __restrict__ overflow) {
-    const size_t total = (size_t)rows * ld16;
+// weights: [rows, cols] fp32 (ld ldw) -> hi / lo [kb][rows][32] (k-block-major, segments padded to 32 columns with zeros)
+struct PackSegs { int n_seg; int col[SUBGC_PACK_MAX_SEG + 1]; int kb[SUBGC_PACK_MAX_SEG + 1]; };
+__global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, int rows, int ldw, const PackSegs sg,
+                                                          unsigned short* __restrict__ hi, unsigned short* __restrict__ lo, int* __restrict__ overflow) {
+    const size_t total = (size_t)sg.kb[sg.n_seg] * rows * H3_BK;
     int ovf = 0;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const int r = (int)(idx / ld16), c = (int)(idx - (size_t)r * ld16);
+        const int j = (int)(idx % H3_BK);
+        const size_t t = idx / H3_BK;
+        const int r = (int)(t % rows), kb = (int)(t / rows);
+        int s = 0;
+        while (s < sg.n_seg - 1 && kb >= sg.kb[s + 1]) ++s;
+        const int c = sg.col[s] + (kb - sg.kb[s]) * H3_BK + j;
         unsigned short h = 0, l = 0;
-        if (c < cols) split_f16(w[(size_t)r * ldw + c], h, l, ovf);
+        if (c < sg.col[s + 1]) split_f16(w[(size_t)r * ldw + c], h, l, ovf);
         hi[idx] = h;
         lo[idx] = l;
     }
     if (ovf && overflow) atomicOr(overflow, 1);
+}
+static bool make_pack_segs(int cols, int n_seg, const int32_t* seg_col, PackSegs& sg) {
+    if (n_seg < 1 || n_seg > SUBGC_PACK_MAX_SEG || !seg_col || seg_col[0] != 0 || seg_col[n_seg] != cols) return false;
+    sg.n_seg = n_seg;
+    sg.kb[0] = 0;
+    for (int s = 0; s < n_seg; ++s) {
+        if (seg_col[s + 1] <= seg_col[s]) return false;
+        sg.col[s] = seg_col[s];
+        sg.kb[s + 1] = sg.kb[s] + (seg_col[s + 1] - seg_col[s] + H3_BK - 1) / H3_BK;
+    }
+    sg.col[n_seg] = cols;
+    return true;
 }
 
 // activations of one K segment (row gather / shared rows / ReLU-on-load applied) -> hi / lo [M, Kp]
@@ -336,6 +353,19 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // 2-D fp16 tensor map: inner dim `cols` (contiguous), outer dim `rows`, `ld` elements between rows; box 32 x box_rows, 64-byte swizzle
+// 3-D fp16 map of a packed weight segment [nkb][plane_rows][32]: box 32 x box_rows x 1, 64-byte swizzle; `rows` valid rows from `base`
+static bool make_map_w16(CUtensorMap* out, const unsigned short* base, int rows, int plane_rows, int nkb, int box_rows) {
+    EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(tc_encode_fn());
+    if (!fn) return false;
+    cuuint64_t gdim[3] = {(cuuint64_t)H3_BK, (cuuint64_t)rows, (cuuint64_t)nkb};
+    cuuint64_t gstride[2] = {(cuuint64_t)H3_BK * 2, (cuuint64_t)plane_rows * H3_BK * 2};
+    cuuint32_t box[3] = {(cuuint32_t)H3_BK, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<unsigned short*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 static bool make_map16(CUtensorMap* out, const unsigned short* base, int rows, int cols, long long ld, int box_rows) {
     EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(tc_encode_fn());
     if (!fn) return false;
@@ -344,7 +374,7 @@ static bool make_map16(CUtensorMap* out, const unsigned short* base, int rows, i
     cuuint32_t box[2] = {(cuuint32_t)H3_BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<unsigned short*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
 
@@ -376,7 +406,7 @@ bool h3_eligible(const GemmProblem& p) {
     long long ktot = 0;
     for (int s = 0; s < p.nseg; ++s) {
         const GemmSeg& g = p.seg[s];
-        if (!g.W16_hi || !g.W16_lo || (g.ldw16 & 7) || (reinterpret_cast<uintptr_t>(g.W16_hi) & 15) || (reinterpret_cast<uintptr_t>(g.W16_lo) & 15))
+        if (!g.W16_hi || !g.W16_lo || g.w16_rows < p.N || (reinterpret_cast<uintptr_t>(g.W16_hi) & 15) || (reinterpret_cast<uintptr_t>(g.W16_lo) & 15))
             return false;
         if (g.A16_hi && ((g.lda16 & 7) || (reinterpret_cast<uintptr_t>(g.A16_hi) & 15) || (reinterpret_cast<uintptr_t>(g.A16_lo) & 15) || !g.A16_lo))
             return false;
@@ -395,33 +425,66 @@ void resolve_packs(GemmProblem& p, const subgc_weights* w) {
             if (!pk.w || g.W < pk.w || g.W >= pk.w + (size_t)pk.rows * pk.cols || g.ldw != pk.cols) continue;
             const size_t off = (size_t)(g.W - pk.w);
             const size_t r = off / pk.cols, c = off - r * pk.cols;
-            if (c + g.K > (size_t)pk.cols || (c & 7)) break;
-            g.W16_hi = pk.hi + r * pk.ld16 + c;
-            g.W16_lo = pk.lo + r * pk.ld16 + c;
-            g.ldw16 = pk.ld16;
+            int kb0 = 0, found = -1;   // the operand must be exactly one packed K segment (from its first column, over its full width)
+            for (int q = 0; q < pk.n_seg; ++q) {
+                if ((size_t)pk.seg_col[q] == c && pk.seg_col[q + 1] - pk.seg_col[q] == g.K) { found = q; break; }
+                kb0 += (pk.seg_col[q + 1] - pk.seg_col[q] + H3_BK - 1) / H3_BK;
+            }
+            if (found < 0 || r + (size_t)p.N > (size_t)pk.rows) break;
+            g.W16_hi = pk.hi + ((size_t)kb0 * pk.rows + r) * H3_BK;
+            g.W16_lo = pk.lo + ((size_t)kb0 * pk.rows + r) * H3_BK;
+            g.w16_rows = pk.rows;
             break;
         }
     }
 }
 
-struct H3Plan { int m_tiles, n_tiles, kb_total, splits, kb_per_split; };
+struct H3Plan { int m_tiles, n_tiles, kb_total, splits, kb_per_split, bn, stages; };
 
+// Tile width and split count.  One CTA streams bn weight rows over its k-range; narrow tiles leave more n-tiles, i.e. fewer
+// k-splits and proportionally less split-K partial traffic (the consumers' read volume), but re-read the activation tile more
+// often.  A small cost model (cycles per CTA: HBM share vs shared-memory traffic per k-block, plus the partial-tile epilogue,
+// times the number of waves) picks among {256, 224, 192, 160, 128}.
 static H3Plan h3_plan(int M, int N, const int* segK, int nseg) {
-    H3Plan pl;
-    pl.m_tiles = (M + H3_BM - 1) / H3_BM;
-    pl.n_tiles = (N + H3_BN - 1) / H3_BN;
-    pl.kb_total = 0;
-    for (int s = 0; s < nseg; ++s) pl.kb_total += (segK[s] + H3_BK - 1) / H3_BK;
-    const int tiles = pl.m_tiles * pl.n_tiles;
-    int splits = kNumSMs / tiles;
-    const int by_k = pl.kb_total / 4;  // at least 4 k-blocks (128 columns) per split
-    if (splits > by_k) splits = by_k;
-    if (splits > 32) splits = 32;
-    if (splits < 1) splits = 1;
-    pl.kb_per_split = (pl.kb_total + splits - 1) / splits;
-    if (pl.kb_per_split > H3_MAX_CHAIN) pl.kb_per_split = H3_MAX_CHAIN;
-    pl.splits = (pl.kb_total + pl.kb_per_split - 1) / pl.kb_per_split;
-    return pl;
+    static const int forced_bn = getenv("SUBGC_H3_BN") ? atoi(getenv("SUBGC_H3_BN")) : 0;
+    H3Plan best{};
+    double best_cost = 1e30;
+    int kb_total = 0;
+    for (int s = 0; s < nseg; ++s) kb_total += (segK[s] + H3_BK - 1) / H3_BK;
+    const int cands[5] = {256, 224, 192, 160, 128};
+    for (int ci = 0; ci < 5; ++ci) {
+        const int bn = cands[ci];
+        if (forced_bn && bn != forced_bn) continue;
+        H3Plan pl;
+        pl.bn = bn;
+        pl.m_tiles = (M + H3_BM - 1) / H3_BM;
+        pl.n_tiles = (N + bn - 1) / bn;
+        pl.kb_total = kb_total;
+        const int tiles = pl.m_tiles * pl.n_tiles;
+        int splits = kNumSMs / tiles;
+        const int by_k = kb_total / 2;  // at least 2 k-blocks (128 columns) per split
+        if (splits > by_k) splits = by_k;
+        if (splits > 32) splits = 32;
+        if (splits < 1) splits = 1;
+        pl.kb_per_split = (kb_total + splits - 1) / splits;
+        if (pl.kb_per_split > H3_MAX_CHAIN) pl.kb_per_split = H3_MAX_CHAIN;
+        pl.splits = (kb_total + pl.kb_per_split - 1) / pl.kb_per_split;
+        const int stage_bytes = 2 * bn * H3_BK * 2 + 2 * H3_X_BYTES;
+        pl.stages = H3_SMEM_BUDGET / stage_bytes;
+        if (pl.stages > H3_MAX_STAGES) pl.stages = H3_MAX_STAGES;
+        const long long ctas = (long long)tiles * pl.splits;
+        const long long waves = (ctas + kNumSMs - 1) / kNumSMs;
+        const double per_wave = (double)(ctas < kNumSMs ? ctas : kNumSMs);
+        const double hbm = (2.0 * bn * 128) / (3400.0 / per_wave < 64.0 ? 3400.0 / per_wave : 64.0);       // bytes / (bytes per cycle per CTA)
+        const double smem = ((2.0 * bn * 128 + 2.0 * H3_X_BYTES) + 3.0 * (bn * 128 + H3_X_BYTES) - H3_X_BYTES) / 128.0;
+        const double mma = 12.0 * bn / 2.0;
+        double per_kb = hbm > smem ? hbm : smem;
+        if (mma > per_kb) per_kb = mma;
+        const double epi = (pl.splits > 1 ? 2.0 : 1.0) * bn * 128.0 * 4.0 / 64.0;   // partial tile out (and read back by the consumer)
+        const double cost = waves * (pl.kb_per_split * per_kb + epi + 4000.0);
+        if (cost < best_cost) { best_cost = cost; best = pl; }
+    }
+    return best;
 }
 
 void launch_splitk_reduce(const GemmProblem& p, const float* part, int splits, cudaStream_t stream);
@@ -441,7 +504,8 @@ int launch_gemm_h3(const GemmProblem& p, void* ws_, size_t ws_bytes, cudaStream_
         const GemmSeg& g = p.seg[s];
         kb += (g.K + H3_BK - 1) / H3_BK;
         hp.seg_kb_end[s] = kb;
-        if (!make_map16(&hp.tm_wh[s], g.W16_hi, p.N, g.K, g.ldw16, H3_BN) || !make_map16(&hp.tm_wl[s], g.W16_lo, p.N, g.K, g.ldw16, H3_BN)) {
+        const int nkb_seg = (g.K + H3_BK - 1) / H3_BK;
+        if (!make_map_w16(&hp.tm_wh[s], g.W16_hi, p.N, g.w16_rows, nkb_seg, pl.bn) || !make_map_w16(&hp.tm_wl[s], g.W16_lo, p.N, g.w16_rows, nkb_seg, pl.bn)) {
             set_error("gemm(h3): cuTensorMapEncodeTiled failed for weight segment %d", s);
             return SUBGC_E_CUDA;
         }
@@ -471,7 +535,7 @@ int launch_gemm_h3(const GemmProblem& p, void* ws_, size_t ws_bytes, cudaStream_
     for (int s = p.nseg; s < H3_MAX_SEG; ++s) {
         hp.seg_kb_end[s] = kb; hp.tm_wh[s] = hp.tm_wh[0]; hp.tm_wl[s] = hp.tm_wl[0]; hp.tm_xh[s] = hp.tm_xh[0]; hp.tm_xl[s] = hp.tm_xl[0];
     }
-    hp.nseg = p.nseg; hp.M = p.M; hp.N = p.N; hp.kb_total = pl.kb_total; hp.kb_per_split = pl.kb_per_split; hp.part = part; hp.active = p.active;
+    hp.nseg = p.nseg; hp.M = p.M; hp.N = p.N; hp.bn = pl.bn; hp.stages = pl.stages; hp.kb_total = pl.kb_total; hp.kb_per_split = pl.kb_per_split; hp.part = part; hp.active = p.active;
     hp.direct = direct ? 1 : 0; hp.epi = p.epi; hp.C = p.C; hp.ldc = p.ldc;
     static const bool tma_store = getenv("SUBGC_H3_NO_TMA_STORE") == nullptr;
     hp.tma_part = 0;
@@ -479,11 +543,13 @@ int launch_gemm_h3(const GemmProblem& p, void* ws_, size_t ws_bytes, cudaStream_
     if (!direct && tma_store && (p.N & 3) == 0 && make_map_part(&hp.tm_part, part, pl.splits, p.M, p.N)) hp.tma_part = 1;
     static bool attr_set = false;
     if (!attr_set) {
-        SUBGC_CUDA(cudaFuncSetAttribute(h3_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H3_SMEM_BYTES));
+        SUBGC_CUDA(cudaFuncSetAttribute(h3_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H3_SMEM_BUDGET + H3_SMEM_EXTRA));
         attr_set = true;
     }
+    hp.trace = next_trace_slot(1);
+    const size_t smem_bytes = (size_t)pl.stages * (2 * pl.bn * H3_BK * 2 + 2 * H3_X_BYTES) + H3_SMEM_EXTRA;
     dim3 grid(pl.n_tiles, pl.m_tiles, pl.splits);
-    SUBGC_CUDA(launch_pdl(h3_gemm_kernel, grid, dim3(H3_THREADS), (size_t)H3_SMEM_BYTES, stream, hp));
+    SUBGC_CUDA(launch_pdl(h3_gemm_kernel, grid, dim3(H3_THREADS), smem_bytes, stream, hp));
     SUBGC_LAUNCH_CHECK();
     if (direct) return SUBGC_OK;
     if (raw) {
@@ -500,15 +566,21 @@ int launch_gemm_h3(const GemmProblem& p, void* ws_, size_t ws_bytes, cudaStream_
 
 using namespace subgc;
 
-extern "C" int subgc_pack_ld(int cols) { return (cols + 7) & ~7; }
+extern "C" size_t subgc_pack_elems(int rows, int n_seg, const int32_t* seg_col) {
+    PackSegs sg;
+    if (rows <= 0 || !seg_col || n_seg < 1 || n_seg > SUBGC_PACK_MAX_SEG || !make_pack_segs(seg_col[n_seg], n_seg, seg_col, sg)) return 0;
+    return (size_t)sg.kb[n_seg] * rows * H3_BK;
+}
 
-extern "C" int subgc_pack_weight(int rows, int cols, const float* w, int ldw, uint16_t* hi, uint16_t* lo, int32_t* overflow, subgc_stream_t stream) {
+extern "C" int subgc_pack_weight(int rows, int cols, const float* w, int ldw, int n_seg, const int32_t* seg_col, uint16_t* hi, uint16_t* lo,
+                                 int32_t* overflow, subgc_stream_t stream) {
     SUBGC_CHECK_ARG(rows > 0 && cols > 0 && w && hi && lo && ldw >= cols, "subgc_pack_weight: bad arguments");
-    const int ld16 = subgc_pack_ld(cols);
-    const size_t total = (size_t)rows * ld16;
+    PackSegs sg;
+    SUBGC_CHECK_ARG(make_pack_segs(cols, n_seg, seg_col, sg), "subgc_pack_weight: bad column segments");
+    const size_t total = (size_t)sg.kb[n_seg] * rows * H3_BK;
     int blocks = (int)((total + 255) / 256);
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-    pack_weight_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, rows, cols, ldw, hi, lo, ld16, overflow);
+    pack_weight_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, rows, ldw, sg, hi, lo, overflow);
     SUBGC_LAUNCH_CHECK();
     return SUBGC_OK;
 }
@@ -516,12 +588,12 @@ extern "C" int subgc_pack_weight(int rows, int cols, const float* w, int ldw, ui
 extern "C" int subgc_linear_packed_forward(int M, int N, int K, const float* A, int lda, const int64_t* a_gather, const subgc_packed* pk,
                                            const float* bias, int relu, float* C, int ldc, void* ws, size_t ws_bytes, subgc_stream_t stream) {
     SUBGC_CHECK_ARG(A && pk && pk->w && pk->hi && pk->lo && C && M >= 0 && N > 0 && K > 0, "subgc_linear_packed_forward: bad arguments");
-    SUBGC_CHECK_ARG(pk->rows == N && pk->cols == K && pk->ld16 == subgc_pack_ld(K), "subgc_linear_packed_forward: pack does not match [N, K]");
+    SUBGC_CHECK_ARG(pk->rows == N && pk->cols == K && pk->n_seg == 1, "subgc_linear_packed_forward: pack does not match [N, K] (one segment)");
     GemmProblem p;
     p.M = M; p.N = N; p.nseg = 1;
     p.seg[0] = make_seg(A, lda, pk->w, K, K);
     p.seg[0].gather = reinterpret_cast<const long long*>(a_gather);
-    p.seg[0].W16_hi = pk->hi; p.seg[0].W16_lo = pk->lo; p.seg[0].ldw16 = pk->ld16;
+    p.seg[0].W16_hi = pk->hi; p.seg[0].W16_lo = pk->lo; p.seg[0].w16_rows = pk->rows;
     p.epi.bias = bias;
     p.epi.relu = relu;
     p.C = C; p.ldc = ldc;

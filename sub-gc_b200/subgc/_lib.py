@@ -30,7 +30,8 @@ class Linear(C.Structure):
 
 
 class Packed(C.Structure):
-    _fields_ = [("w", c_fp), ("hi", c_fp), ("lo", c_fp), ("rows", C.c_int32), ("cols", C.c_int32), ("ld16", C.c_int32)]
+    _fields_ = [("w", c_fp), ("hi", c_fp), ("lo", c_fp), ("rows", C.c_int32), ("cols", C.c_int32), ("n_seg", C.c_int32),
+                ("seg_col", C.c_int32 * 5)]
 
 
 class Weights(C.Structure):
@@ -58,8 +59,10 @@ SIGNATURES = {
     "subgc_last_error": (C.c_char_p, []),
     "subgc_version": (_i, []),
     "subgc_launch_count": (C.c_ulonglong, []),
-    "subgc_pack_ld": (_i, [_i]),
-    "subgc_pack_weight": (_i, [_i, _i, c_fp, _i, c_fp, c_fp, c_fp, c_fp]),
+    "subgc_debug_att_trace": (_i, [c_fp, _i]),
+    "subgc_debug_trace": (_i, [_i, c_fp, c_fp, _i]),
+    "subgc_pack_elems": (_sz, [_i, _i, C.POINTER(C.c_int32)]),
+    "subgc_pack_weight": (_i, [_i, _i, c_fp, _i, _i, C.POINTER(C.c_int32), c_fp, c_fp, c_fp, c_fp]),
     "subgc_linear_packed_forward": (_i, [_i, _i, _i, c_fp, _i, c_fp, _P(Packed), c_fp, _i, c_fp, _i, c_fp, _sz, c_fp]),
     "subgc_linear_workspace_bytes": (_sz, [_i, _i, _i]),
     "subgc_linear_forward": (_i, [_i, _i, _i, c_fp, _i, c_fp, c_fp, _i, c_fp, _i, c_fp, _i, c_fp, _sz, c_fp]),

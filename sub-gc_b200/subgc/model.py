@@ -259,7 +259,8 @@ class TopDownModel(nn.Module):
                 self._plans.clear()
             return
         named = {n: p for n, p in params.items() if p.dim() == 2 and p.shape[0] >= 64 and n not in self._PACK_SKIP}
-        arr, cnt = self._packs.build(named)
+        H = self.rnn_size   # K segments of the un-concatenated LSTM inputs: [h_lang | fc | x_t] and [ctx | h_att]
+        arr, cnt = self._packs.build(named, {"core.att_lstm.weight_ih": [H, 2 * H], "core.lang_lstm.weight_ih": [H]})
         if self._pack_key != self._packs.array_key or not w.n_packs:
             w.packs, w.n_packs = arr, cnt
             self._pack_key = self._packs.array_key

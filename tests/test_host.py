@@ -44,7 +44,7 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(_lib.Linear) == 16
     n_linear = 3 + 2 * 4 * _lib.MAX_GCN_LAYERS + 5 + 6
     assert ctypes.sizeof(_lib.Weights) == 16 * n_linear + 8 * (3 + 8) + 16   # + packs pointer, n_packs (padded)
-    assert ctypes.sizeof(_lib.Packed) == 3 * 8 + 3 * 4 + 4
+    assert ctypes.sizeof(_lib.Packed) == 3 * 8 + 8 * 4
     assert ctypes.sizeof(_lib.Layout) == 16
 
 

@@ -21,8 +21,8 @@ for (M, N, K) in shapes:
     Ad, Wd, bd = A.cuda(), W.cuda(), b.cuda()
     ws = torch.empty(L.subgc_linear_workspace_bytes(M, N, K) + 256, dtype=torch.uint8, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
-    hi, lo, flag = packing.pack_weight(Wd)
-    pk = packing.packed_struct(Wd, hi, lo)
+    hi, lo, flag, segs = packing.pack_weight(Wd)
+    pk = packing.packed_struct(Wd, hi, lo, segs)
     scale = ref.abs().max()
     line = f"M={M} N={N} K={K}: (torch-cpu-fp32 {float((ref32.double()-ref).abs().max()/scale):.2e})"
     for name in ("h3", "tf32x3"):
