@@ -130,8 +130,8 @@ unsigned long long subgc_launch_count(void);
 /* debugging aid (env SUBGC_ATT_TRACE=1, synchronises): per-block stage time stamps [n_blocks][8] of the last fused att-phase launch */
 int subgc_debug_att_trace(unsigned long long* host_out, int n_blocks);
 /* debugging aid (env SUBGC_TRACE=1, synchronises): globaltimer stamps of the decode-loop launches, per launch
- * [first block start, last block end, first block past its dependency wait, last block past it].
- * op 0 restart slot numbering, op 1 reset stamps, op 2 copy out up to n slots (stamps [n][4], kernel ids [n]); returns slots used */
+ * [first block start, last block end, first block past its dependency wait, last block past it, 4 kernel-specific marks].
+ * op 0 restart slot numbering, op 1 reset stamps, op 2 copy out up to n slots (stamps [n][8], kernel ids [n]); returns slots used */
 int subgc_debug_trace(int op, unsigned long long* stamps, int* ids, int n);
 
 /* Packs an fp32 weight matrix [rows, cols] (leading dim ldw) into the split-fp16 form of subgc_packed, columns cut at

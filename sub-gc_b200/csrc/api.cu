@@ -27,7 +27,7 @@ TraceSlot next_trace_slot(int kernel_id) {
     static int on = -1;
     if (on < 0) {
         on = getenv("SUBGC_TRACE") != nullptr ? 1 : 0;
-        if (on) cudaMalloc(&g_trace_buf, kTraceSlots * 4 * sizeof(unsigned long long));
+        if (on) cudaMalloc(&g_trace_buf, kTraceSlots * 8 * sizeof(unsigned long long));
     }
     if (!on || g_trace_buf == nullptr) return TraceSlot{nullptr, 0};
     const int seq = g_trace_n % kTraceSlots;
@@ -42,21 +42,24 @@ extern "C" int subgc_version(void) { return SUBGC_ABI_VERSION; }
 extern "C" unsigned long long subgc_launch_count(void) { return subgc::g_launches; }
 
 /* debugging aid (SUBGC_TRACE=1): op 0 = restart slot numbering (call before the launch sequence to be traced / captured),
- * op 1 = reset the time stamps (before a replay), op 2 = copy out [n][4] stamps and the kernel ids; returns slots in use */
+ * op 1 = reset the time stamps (before a replay), op 2 = copy out [n][8] stamps and the kernel ids; returns slots in use */
 extern "C" int subgc_debug_trace(int op, unsigned long long* stamps, int* ids, int n) {
     using namespace subgc;
     if (op == 0) { g_trace_n = 0; return 0; }
     if (g_trace_buf == nullptr) return -1;
     if (op == 1) {
-        static unsigned long long init[kTraceSlots * 4];
-        for (int i = 0; i < kTraceSlots; ++i) { init[4 * i] = ~0ull; init[4 * i + 1] = 0; init[4 * i + 2] = ~0ull; init[4 * i + 3] = 0; }
+        static unsigned long long init[kTraceSlots * 8];
+        for (int i = 0; i < kTraceSlots; ++i) {
+            for (int j = 0; j < 8; ++j) init[8 * i + j] = 0;
+            init[8 * i] = ~0ull; init[8 * i + 2] = ~0ull;
+        }
         cudaDeviceSynchronize();
         cudaMemcpy(g_trace_buf, init, sizeof(init), cudaMemcpyHostToDevice);
         return 0;
     }
     cudaDeviceSynchronize();
     const int m = g_trace_n < n ? g_trace_n : n;
-    cudaMemcpy(stamps, g_trace_buf, (size_t)m * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaMemcpy(stamps, g_trace_buf, (size_t)m * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     for (int i = 0; i < m; ++i) ids[i] = g_trace_ids[i];
     return m;
 }

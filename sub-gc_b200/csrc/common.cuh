@@ -142,6 +142,25 @@ bool tc_eligible(const GemmProblem& p);
 size_t tc_workspace_bytes(int M, int N, int Ktotal);
 struct RawPartials { const float* part; int splits; };  // [splits][M][N] partial sums, to be added in z order
 int launch_gemm_tc(const GemmProblem& p, void* ws, size_t ws_bytes, cudaStream_t stream, RawPartials* raw = nullptr);
+// Fused LSTM-cell epilogue of the h3 contraction (gates [S, 4H] never reach memory): the CTA tile is gate-grouped (4 x 32 weight
+// rows: gates i, f, g, o of 32 hidden units), the k-splits of a tile form a thread-block cluster that reduces its partial tiles
+// through distributed shared memory in split order, and each CTA applies the cell to its share of the units.
+struct CellEpilogue {
+    int H = 0;
+    const float* c_prev = nullptr;        // [*, H]
+    const long long* parent = nullptr;    // nullable: previous-state row per output row (beam re-ordering)
+    const float* addend = nullptr;        // nullable [S / add_div, 4H]: pre-computed gate term incl. both biases
+    int add_div = 1;
+    const float* b_ih = nullptr;          // used when addend == nullptr
+    const float* b_hh = nullptr;
+    float* h_out = nullptr;               // [S, H]
+    float* c_out = nullptr;               // [S, H]
+    unsigned short* h16_hi = nullptr;     // nullable split-fp16 copy of h', [S, Hp]
+    unsigned short* h16_lo = nullptr;
+    int Hp = 0;
+};
+// gates = p (N must be 4H, no epilogue fields) -> LSTM cell.  *fused = false when the problem does not qualify (caller falls back)
+int launch_gemm_cell(const GemmProblem& p, const CellEpilogue& cell, void* ws, size_t ws_bytes, cudaStream_t stream, bool* fused);
 // tensor-core (tcgen05, split-fp16 "h3") variant for weights that have a packed copy, h3_gemm.cu
 bool h3_eligible(const GemmProblem& p);
 int launch_gemm_h3(const GemmProblem& p, void* ws, size_t ws_bytes, cudaStream_t stream, RawPartials* raw = nullptr);
@@ -186,16 +205,23 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 __device__ __forceinline__ void trace_begin(const TraceSlot& t) {
-    if (t.buf != nullptr && threadIdx.x == 0) atomicMin(&t.buf[4 * t.seq], globaltimer_ns());
+    if (t.buf != nullptr && threadIdx.x == 0) {
+        const unsigned long long now = globaltimer_ns();
+        atomicMin(&t.buf[8 * t.seq], now);
+        atomicMax(&t.buf[8 * t.seq + 7], now);   // last block to start
+    }
 }
 __device__ __forceinline__ void trace_end(const TraceSlot& t) {
-    if (t.buf != nullptr && threadIdx.x == 0) atomicMax(&t.buf[4 * t.seq + 1], globaltimer_ns());
+    if (t.buf != nullptr && threadIdx.x == 0) atomicMax(&t.buf[8 * t.seq + 1], globaltimer_ns());
+}
+__device__ __forceinline__ void trace_mark(const TraceSlot& t, int i) {   // extra per-kernel marks 0..3: last block to reach the point
+    if (t.buf != nullptr) atomicMax(&t.buf[8 * t.seq + 4 + i], globaltimer_ns());
 }
 __device__ __forceinline__ void trace_released(const TraceSlot& t) {   // right after pdl_wait(): [first, last] block released
     if (t.buf != nullptr && threadIdx.x == 0) {
         const unsigned long long now = globaltimer_ns();
-        atomicMin(&t.buf[4 * t.seq + 2], now);
-        atomicMax(&t.buf[4 * t.seq + 3], now);
+        atomicMin(&t.buf[8 * t.seq + 2], now);
+        atomicMax(&t.buf[8 * t.seq + 3], now);
     }
 }
 #endif

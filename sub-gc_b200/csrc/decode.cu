@@ -24,7 +24,8 @@ namespace subgc {
 
 // ---- split-K reduction + biases + LSTM cell (torch.nn.LSTMCell gate order i, f, g, o) ---------------------------
 // gates[r, g*H + j] = sum_z part[z][r][g*H + j] + b_ih + b_hh (z ascending: deterministic); c' = s(f) c + s(i) tanh(g); h' = s(o) tanh(c')
-__global__ void __launch_bounds__(256) lstm_reduce_cell_kernel(const float* __restrict__ part, int splits, const float* __restrict__ b_ih,
+// (<= 42 registers: six blocks per SM, so the whole grid is resident next to the contraction's CTAs and is released at once)
+__global__ void __launch_bounds__(256, 6) lstm_reduce_cell_kernel(const float* __restrict__ part, int splits, const float* __restrict__ b_ih,
                                                                const float* __restrict__ b_hh, const float* __restrict__ c_prev,
                                                                const long long* __restrict__ parent, float* __restrict__ h_out,
                                                                float* __restrict__ c_out, int S, int H, const int* __restrict__ active,
@@ -45,8 +46,8 @@ __global__ void __launch_bounds__(256) lstm_reduce_cell_kernel(const float* __re
     int r = idx / H, j = idx - r * H;
     const float* g = part + (size_t)r * 4 * H + j;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 9
-    for (int z = 0; z < splits; ++z) {  // one hidden unit per thread keeps ~128 K threads in flight; all 4 x splits loads independent
+#pragma unroll 2
+    for (int z = 0; z < splits; ++z) {  // one hidden unit per thread keeps ~128 K threads in flight; 8 independent loads each
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[q] += g[(size_t)z * zs + (size_t)q * H];
     }
@@ -161,7 +162,8 @@ __device__ __forceinline__ void attention_row_body(float* s_h, float* s_w, float
     }
 }
 
-__global__ void __launch_bounds__(kAttThreads) attention_kernel(const float* __restrict__ atth_part, int splits, const float* __restrict__ h2att_b,
+// (<= 40 registers: 1024 threads fit next to a contraction CTA, which then prefetches its weight ring while this kernel runs)
+__global__ void __maxnreg__(40) attention_kernel(const float* __restrict__ atth_part, int splits, const float* __restrict__ h2att_b,
                                                                 const float* __restrict__ p_att, const float* __restrict__ att,
                                                                 const float* __restrict__ masks, const float* __restrict__ alpha_w,
                                                                 const float* __restrict__ alpha_b, float* __restrict__ ctx, float* __restrict__ att_w,
@@ -539,6 +541,132 @@ __global__ void __launch_bounds__(kSelectThreads) select_kernel(const SelectArgs
     trace_end(a.trace);
 }
 
+// Same selection with the logit row held in registers (V1 <= 10 x 1024): no dynamic shared memory and <= 40 registers, so the
+// kernel fits next to the CTAs of the following contraction (they prefetch their weight ring meanwhile).
+constexpr int kSelVals = 10;
+__global__ void __maxnreg__(40) select_reg_kernel(const SelectArgs a) {
+    trace_begin(a.trace);
+    pdl_trigger();
+    pdl_wait();
+    trace_released(a.trace);
+    if (a.active != nullptr && *a.active == 0) return;
+    __shared__ float redv[32];
+    __shared__ int redi[32];
+    __shared__ float s_topv[kMaxTopK];
+    __shared__ int s_topi[kMaxTopK];
+    const int r = blockIdx.x, tid = threadIdx.x;
+    float v[kSelVals];
+#pragma unroll
+    for (int i = 0; i < kSelVals; ++i) v[i] = 0.f;
+    if (a.splits > 0) {
+        const size_t zs = (size_t)a.S * a.V1;
+        const float* p0 = a.logits + (size_t)r * a.V1;
+        for (int z = 0; z < a.splits; ++z) {
+#pragma unroll
+            for (int i = 0; i < kSelVals; ++i) {
+                const int j = tid + i * kSelectThreads;
+                if (j < a.V1) v[i] += p0[(size_t)z * zs + j];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kSelVals; ++i) {
+            const int j = tid + i * kSelectThreads;
+            if (j < a.V1) v[i] += __ldg(a.bias + j);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < kSelVals; ++i) {
+            const int j = tid + i * kSelectThreads;
+            if (j < a.V1) v[i] = a.logits[(size_t)r * a.V1 + j];
+        }
+    }
+    // max (first index) and log-sum-exp of the logits
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < kSelVals; ++i) {
+        const int j = tid + i * kSelectThreads;
+        if (j < a.V1 && (v[i] > bv || bi == 0x7fffffff)) { bv = v[i]; bi = j; }
+    }
+    block_argmax(bv, bi, redv, redi);
+    const float m = bv;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kSelVals; ++i) {
+        const int j = tid + i * kSelectThreads;
+        if (j < a.V1) s += expf(v[i] - m);
+    }
+    s = block_sum(s, redv);
+    const float lz = logf(s);
+    int tok;
+    float lp;
+    if (a.mode == 0) {
+        tok = bi;
+        lp = (m - m) - lz;  // log_softmax value at the arg-max
+    } else {
+        const float ym = ((m - m) - lz) / a.temp;
+        float s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < kSelVals; ++i) {
+            const int j = tid + i * kSelectThreads;
+            if (j < a.V1) s2 += expf(((v[i] - m) - lz) / a.temp - ym);
+        }
+        s2 = block_sum(s2, redv);
+        const float lz2 = logf(s2);
+        const int k = a.top_k;
+        for (int c = 0; c < k; ++c) {  // k rounds of arg-max with exclusion (descending q, lower index first on ties)
+            float cv = -INFINITY;
+            int ci = 0x7fffffff;
+#pragma unroll
+            for (int i = 0; i < kSelVals; ++i) {
+                const int j = tid + i * kSelectThreads;
+                if (j >= a.V1) continue;
+                bool taken = false;
+                for (int e = 0; e < c; ++e) taken |= (s_topi[e] == j);
+                if (taken) continue;
+                const float q = (((v[i] - m) - lz) / a.temp - ym) - lz2;
+                if (q > cv || ci == 0x7fffffff) { cv = q; ci = j; }
+            }
+            block_argmax(cv, ci, redv, redi);
+            if (tid == 0) { s_topv[c] = cv; s_topi[c] = ci; }
+            __syncthreads();
+        }
+        float u = a.uniforms ? a.uniforms[(size_t)a.t * a.S + r] : Philox::uniform(a.seed, a.offset, (unsigned)a.t, (unsigned)r);
+        float den = 0.f;
+        for (int c = 0; c < k; ++c) den += expf(s_topv[c] - s_topv[0]);
+        float cdf = 0.f;
+        int pos = 0;
+        for (int c = 0; c < k; ++c) {
+            cdf += expf(s_topv[c] - s_topv[0]) / den;
+            if (u >= cdf) pos = c + 1;
+        }
+        if (pos > k - 1) pos = k - 1;
+        tok = s_topi[pos];
+        lp = s_topv[pos];
+    }
+    __shared__ int s_it;
+    if (tid == 0) {
+        int unf = (a.t == 0 ? 1 : a.unfinished[r]) && (tok > 0);
+        long long it = unf ? tok : 0;
+        a.it[r] = it;
+        a.unfinished[r] = unf;
+        a.seq[(size_t)r * a.T + a.t] = it;
+        a.seq_lp[(size_t)r * a.T + a.t] = lp;
+        if (unf) atomicAdd(a.count + a.t, 1);
+        s_it = (int)it;
+    }
+    if (a.xt != nullptr) {  // embed + ReLU of the token fed to the next step (AttModel.py:332), fused here
+        __syncthreads();
+        const float* e = a.embed + (size_t)s_it * a.X;
+        for (int j = tid; j < a.X; j += blockDim.x) {
+            const float xv = fmaxf(__ldg(e + j), 0.f);
+            a.xt[(size_t)r * a.X + j] = xv;
+            if (a.xt16_hi) split_f16_store(xv, a.xt16_hi, a.xt16_lo, (size_t)r * a.Xp + j);
+        }
+    }
+    trace_end(a.trace);
+}
+
 __global__ void steps_done_kernel(const int* __restrict__ count, int T, int* __restrict__ steps_done) {
     int steps = T + 1;
     for (int t = 0; t < T; ++t)
@@ -634,6 +762,19 @@ static bool att_phase_fusable(size_t smem) {
     return mode == 1 && clus && smem <= 48 * 1024;
 }
 
+// The loop's small kernels run next to the contraction's CTAs (which hold ~193 KB of shared memory): an SM only hosts kernels with
+// the same shared-memory / L1 split, so they ask for the maximum shared-memory carve-out as well.
+static void prefer_smem_carveout() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    cudaFuncSetAttribute(lstm_reduce_cell_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(select_reg_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(select_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(log_softmax_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 // upto: 0 = whole step, 1 = stop after the attention (the reference's discarded last step, only its attention
 // weights are observable).  parent (nullable) re-maps the previous-state rows (beam re-ordering).
 // raw_logits != nullptr: the logit contraction leaves its split-K partials (no bias) for a fused consumer
@@ -657,6 +798,7 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
     // fc_pre != nullptr: W_ih[:, H:2H] fc + b_ih + b_hh was computed once for the whole loop (launch_fc_pre): the fc segment
     // (a quarter of the att-LSTM weights) is not streamed again at every step
     const int H = d->rnn, X = d->enc, AH = d->att_hid, V1 = d->vocab1;
+    prefer_smem_carveout();
     const size_t SH = (size_t)S * H;
     const int pw_blocks = (int)((SH + 255) / 256);
     GemmProblem p;
@@ -690,10 +832,18 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
     p.active = active;
     const int skip = skip_mask();
     rp.part = static_cast<const float*>(sc.gemm_ws); rp.splits = 1;
-    if (!(skip & 1)) SUBGC_TRY(launch_gemm_raw(p, sc.gemm_ws, sc.gemm_ws_bytes, st, &rp));
+    bool cell_fused = false;   // gates -> cell inside the contraction (h3 path with packed weights), else partials + cell kernel
+    if (!(skip & 1)) {
+        CellEpilogue ce;
+        ce.H = H; ce.c_prev = c_in; ce.parent = parent; ce.addend = fc_pre; ce.add_div = rows_per_ctx; ce.b_ih = w->att_b_ih; ce.b_hh = w->att_b_hh;
+        ce.h_out = h_out; ce.c_out = c_out;
+        if (use16) { ce.h16_hi = h16->hout_hi; ce.h16_lo = h16->hout_lo; ce.Hp = h16->Hp; }
+        SUBGC_TRY(launch_gemm_cell(p, ce, sc.gemm_ws, sc.gemm_ws_bytes, st, &cell_fused));
+        if (!cell_fused) SUBGC_TRY(launch_gemm_raw(p, sc.gemm_ws, sc.gemm_ws_bytes, st, &rp));
+    }
     size_t smem = (size_t)(2 * AH + 64 + 4 * H) * sizeof(float);
     const size_t smem_fused = (size_t)(2 * AH + 64 + kAttCluster * H) * sizeof(float);
-    if (att_phase_fusable(smem_fused)) {
+    if (!cell_fused && att_phase_fusable(smem_fused)) {
         // cell + h2att + attention as one kernel (one block per row, clusters of 8 rows, two cluster barriers)
         AttPhaseArgs fa;
         fa.part = rp.part; fa.splits = rp.splits; fa.b_ih = w->att_b_ih; fa.b_hh = w->att_b_hh; fa.fc_pre = fc_pre; fa.c_prev = c_in;
@@ -720,7 +870,7 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
             count_launch();
         }
     } else {
-        if (!(skip & 2)) launch_pdl(lstm_reduce_cell_kernel, dim3(pw_blocks), dim3(256), (size_t)0, st, rp.part, rp.splits, w->att_b_ih, w->att_b_hh, c_in, parent, h_out, c_out, S,
+        if (!(skip & 2) && !cell_fused) launch_pdl(lstm_reduce_cell_kernel, dim3(pw_blocks), dim3(256), (size_t)0, st, rp.part, rp.splits, w->att_b_ih, w->att_b_hh, c_in, parent, h_out, c_out, S,
                                                                             H, active, fc_pre, rows_per_ctx, use16 ? h16->hout_hi : nullptr,
                                                                             use16 ? h16->hout_lo : nullptr, use16 ? h16->Hp : 0, next_trace_slot(2));
         SUBGC_LAUNCH_CHECK();
@@ -750,8 +900,16 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
         set_a16(p.seg[2], h16->hin_hi + SHp, h16->hin_lo + SHp, h16->Hp);
     }
     p.active = active;
-    if (!(skip & 16)) SUBGC_TRY(launch_gemm_raw(p, sc.gemm_ws, sc.gemm_ws_bytes, st, &rp));
-    if (!(skip & 32)) launch_pdl(lstm_reduce_cell_kernel, dim3(pw_blocks), dim3(256), (size_t)0, st, rp.part, rp.splits, w->lang_b_ih, w->lang_b_hh, c_in + SH, parent, h_out + SH,
+    cell_fused = false;
+    if (!(skip & 16)) {
+        CellEpilogue ce;
+        ce.H = H; ce.c_prev = c_in + SH; ce.parent = parent; ce.b_ih = w->lang_b_ih; ce.b_hh = w->lang_b_hh;
+        ce.h_out = h_out + SH; ce.c_out = c_out + SH;
+        if (use16) { ce.h16_hi = h16->hout_hi + SHp; ce.h16_lo = h16->hout_lo + SHp; ce.Hp = h16->Hp; }
+        SUBGC_TRY(launch_gemm_cell(p, ce, sc.gemm_ws, sc.gemm_ws_bytes, st, &cell_fused));
+        if (!cell_fused) SUBGC_TRY(launch_gemm_raw(p, sc.gemm_ws, sc.gemm_ws_bytes, st, &rp));
+    }
+    if (!(skip & 32) && !cell_fused) launch_pdl(lstm_reduce_cell_kernel, dim3(pw_blocks), dim3(256), (size_t)0, st, rp.part, rp.splits, w->lang_b_ih, w->lang_b_hh, c_in + SH, parent, h_out + SH,
                                                                          c_out + SH, S, H, active, nullptr, 1, use16 ? h16->hout_hi + SHp : nullptr,
                                                                          use16 ? h16->hout_lo + SHp : nullptr, use16 ? h16->Hp : 0, next_trace_slot(2));
     SUBGC_LAUNCH_CHECK();
@@ -1069,7 +1227,10 @@ extern "C" int subgc_decode_sample(const subgc_dims* d, const subgc_weights* w, 
         a.embed = w->embed; a.xt = xt; a.X = d->enc;
         a.xt16_hi = s16 ? b16.xt[0] : nullptr; a.xt16_lo = s16 ? b16.xt[1] : nullptr; a.Xp = s16 ? b16.Xp : 0;
         a.trace = next_trace_slot(4);
-        if (!(skip_mask() & 128)) launch_pdl(select_kernel, dim3(S), dim3(kSelectThreads), (size_t)V1 * sizeof(float), st, a);
+        if (!(skip_mask() & 128)) {
+            if (V1 <= kSelVals * kSelectThreads) launch_pdl(select_reg_kernel, dim3(S), dim3(kSelectThreads), (size_t)0, st, a);
+            else launch_pdl(select_kernel, dim3(S), dim3(kSelectThreads), (size_t)V1 * sizeof(float), st, a);
+        }
         SUBGC_LAUNCH_CHECK();
     }
     steps_done_kernel<<<1, 1, 0, st>>>(count, T, steps_done);

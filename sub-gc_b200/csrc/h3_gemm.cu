@@ -10,12 +10,12 @@
 // at twice the TF32 rate; 22 mantissa bits per operand and fp32 accumulation keep the result at the fp32 noise floor
 // (tools/gemm_check.py).  Activations are split by their producer kernel (decode loop) or by split_rows_kernel here.
 //
-// One CTA (192 threads, 1 per SM) computes a 128 x 256 tile over its k-range:
-//   warp 0     TMA producer: per k-block (32 fp16 = one 128-byte swizzled row) four tiles  Whi | Wlo [bn x 64], Xhi | Xlo [128 x 64]
+// One CTA (128 threads = one warp per SM sub-partition, 1 CTA per SM) computes a 128 x 256 tile over its k-range:
+//   warp 0     (lane 0) TMA producer: per k-block (32 fp16 = one 128-byte swizzled row) four tiles  Whi | Wlo [bn x 64], Xhi | Xlo [128 x 64]
 //   warp 1     one thread issues 4 x 3 tcgen05.mma.kind::f16 (M=128, N=bn, K=16) per k-block: main chain -> TMEM columns [0,256),
 //              the two cross terms -> columns [256,512) (separate chains: the accumulator truncation of the main chain is not
 //              multiplied by three adds per step, and the cross sum is scaled by 2^-11 once, exactly, in the epilogue)
-//   warps 2-5  epilogue: tcgen05.ld -> main + cross * 2^-11 -> split-K partial [z][M][N] or the in-place epilogue (single split)
+//   all 4      epilogue (after their main-loop role): tcgen05.ld -> main + cross * 2^-11 -> split-K partial [z][M][N] or the in-place epilogue (single split)
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -29,7 +29,7 @@ constexpr int H3_BM = 128;
 constexpr int H3_BN_MAX = 256;
 constexpr int H3_BK = 64;   // fp16 elements per k-block: 128-byte rows (TMA issues one request per box row: 64-byte rows measured request-bound)
 constexpr int H3_MAX_STAGES = 8;
-constexpr int H3_THREADS = 192;
+constexpr int H3_THREADS = 128;   // 4 warps, one per SM sub-partition: leaves 12 K registers per sub-partition for co-resident kernels
 constexpr int H3_X_BYTES = H3_BM * H3_BK * 2;                    // 16 KB
 constexpr int H3_SMEM_EXTRA = 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int H3_SMEM_BUDGET = 196 * 1024;   // pipeline bytes: leaves ~30 KB of the SM's shared memory for a co-resident consumer kernel (PDL)
@@ -54,8 +54,26 @@ struct H3Params {
     CUtensorMap tm_part;   // [splits, M, N] fp32 partials, box 32 x 32 x 1, 128-byte swizzle (valid when tma_part)
     int tma_part;          // 1: the partial tiles leave through shared memory + TMA stores (full 128-byte lines) instead of per-thread rows
     TraceSlot trace;
+    CellEpilogue cell;     // kCell instantiation only
+    int dbg;               // timing experiments only (SUBGC_H3_DBG bit mask, results are wrong): 1 no activation loads after the first
+                           // ring round, 2 no weight loads after it, 4 no MMAs
 };
 
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_addr, uint32_t rank) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote) : "memory");
+    return v;
+}
+
+// kCell: gate-grouped tiles (bn = 128 = 4 gates x 32 hidden units, weight rows q*H + j0 .. +32 per gate), the grid's z dimension is a
+// cluster; the epilogue reduces the k-splits through distributed shared memory and applies the LSTM cell (CellEpilogue)
+template <bool kCell>
 __global__ void __launch_bounds__(H3_THREADS, 1) h3_gemm_kernel(const __grid_constant__ H3Params p) {
     extern __shared__ uint8_t smem_raw[];
     trace_begin(p.trace);
@@ -68,7 +86,7 @@ __global__ void __launch_bounds__(H3_THREADS, 1) h3_gemm_kernel(const __grid_con
     // barriers: full[s] @ +0, empty[s] @ +64, accum @ +128, tmem slot @ +136
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + (size_t)stages * stage_bytes + 136);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * bn, m0 = blockIdx.y * H3_BM;
+    const int n0 = kCell ? blockIdx.x * 32 : blockIdx.x * bn, m0 = blockIdx.y * H3_BM;   // kCell: n0 = first hidden unit of the tile
     const int kb_begin = blockIdx.z * p.kb_per_split;
     const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
     const int nkb = kb_end - kb_begin;
@@ -101,9 +119,18 @@ __global__ void __launch_bounds__(H3_THREADS, 1) h3_gemm_kernel(const __grid_con
         const int kc = (kb - (seg_w == 0 ? 0 : p.seg_kb_end[seg_w - 1])) * H3_BK;
         const int s = i % stages;
         const uint32_t st = base + s * stage_bytes, full = bar_base + 8 * s;
+        if ((p.dbg & 2) && i >= stages) { mbar_arrive(full); return; }
         mbar_arrive_expect_tx(full, 2 * w_bytes);
-        tma_load_3d(st, &p.tm_wh[seg_w], full, 0, n0, kc / H3_BK);           // packed weights are k-block-major: one contiguous run
-        tma_load_3d(st + w_bytes, &p.tm_wl[seg_w], full, 0, n0, kc / H3_BK);
+        if (kCell) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {   // 32 rows of each gate (boxes of 32 rows, 4 KB each)
+                tma_load_3d(st + q * 4096, &p.tm_wh[seg_w], full, 0, q * p.cell.H + n0, kc / H3_BK);
+                tma_load_3d(st + w_bytes + q * 4096, &p.tm_wl[seg_w], full, 0, q * p.cell.H + n0, kc / H3_BK);
+            }
+        } else {
+            tma_load_3d(st, &p.tm_wh[seg_w], full, 0, n0, kc / H3_BK);           // packed weights are k-block-major: one contiguous run
+            tma_load_3d(st + w_bytes, &p.tm_wl[seg_w], full, 0, n0, kc / H3_BK);
+        }
     };
     auto issue_x = [&](int i) {
         const int kb = kb_begin + i;
@@ -111,6 +138,7 @@ __global__ void __launch_bounds__(H3_THREADS, 1) h3_gemm_kernel(const __grid_con
         const int kc = (kb - (seg_x == 0 ? 0 : p.seg_kb_end[seg_x - 1])) * H3_BK;
         const int s = i % stages;
         const uint32_t st = base + s * stage_bytes, full = bar_base + 8 * s;
+        if ((p.dbg & 1) && i >= stages) { mbar_arrive(full); return; }
         mbar_arrive_expect_tx(full, 2 * H3_X_BYTES);
         tma_load_2d(st + 2 * w_bytes, &p.tm_xh[seg_x], full, kc, m0);
         tma_load_2d(st + 2 * w_bytes + H3_X_BYTES, &p.tm_xl[seg_x], full, kc, m0);
@@ -124,12 +152,42 @@ __global__ void __launch_bounds__(H3_THREADS, 1) h3_gemm_kernel(const __grid_con
     }
     pdl_wait();      // from here on the activations / flags written by earlier kernels are visible
     trace_released(p.trace);
+    // the activation tiles of the first ring round are requested before anything else (the `active` flag below costs an L2 round trip)
+    if (producer)
+        for (int i = 0; i < pre; ++i) issue_x(i);
     const bool act = (p.active == nullptr) || (*p.active != 0);
+    // ---- kCell: operands of the fused LSTM cell (shared by the epilogue role and the reduction below)
+    const CellEpilogue& ce = p.cell;
+    const int H = ce.H;
+    const int nsp = (int)gridDim.z, z = (int)blockIdx.z;   // cluster = the k-splits of this tile; rank == blockIdx.z
+    const int nf4 = 8 / nsp;                               // 16-byte chunks (4 units) per gate that this CTA finishes (1, 2, 4 or 8)
+    const int rl = (warp & 3) * 32 + lane;
+    const int row = m0 + rl;
+    constexpr int kMaxPre = 2;                             // chunks whose operands are prefetched (nf4 <= 2 for >= 4 splits)
+    float4 pre_c[kMaxPre], pre_a[kMaxPre][4];
+    const bool epi_thread = true;   // all four warps finish the tile
+    const long long pr = (kCell && epi_thread && row < p.M && ce.parent) ? ce.parent[row] : row;
+    auto load_operands = [&](int f, float4& cp, float4 (&ad)[4]) {
+        const int j = n0 + 4 * (z * nf4 + f);
+        if (!(row < p.M && j < H)) return;
+        cp = *reinterpret_cast<const float4*>(ce.c_prev + (size_t)pr * H + j);
+        if (ce.addend) {
+            const float* a0 = ce.addend + (size_t)(row / ce.add_div) * 4 * H + j;
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) ad[qq] = *reinterpret_cast<const float4*>(a0 + (size_t)qq * H);
+        } else {
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {   // (g + b_ih) + b_hh is the reference's association; biases are summed after the reduction
+                ad[qq] = __ldg(reinterpret_cast<const float4*>(ce.b_ih + qq * H + j));
+            }
+        }
+    };
     if (!act) {
-        if (producer)   // drain the prefetched weight tiles before the CTA retires
-            for (int i = 0; i < pre; ++i) { mbar_arrive(bar_base + 8 * i); mbar_wait(bar_base + 8 * i, 0); }
-    } else if (warp == 0) {
-        // ===== TMA producer =====
+        if (producer)   // drain the prefetched tiles before the CTA retires
+            for (int i = 0; i < pre; ++i) mbar_wait(bar_base + 8 * i, 0);
+    } else {
+    if (warp == 0) {
+        // ===== TMA producer (then epilogue warp 0) =====
         if (lane == 0) {
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % stages;
@@ -137,12 +195,13 @@ __global__ void __launch_bounds__(H3_THREADS, 1) h3_gemm_kernel(const __grid_con
                     const uint32_t ph = (uint32_t)(i / stages) & 1u;
                     mbar_wait(bar_base + 64 + 8 * s, ph ^ 1u);
                     issue_w(i);
+                    issue_x(i);
                 }
-                issue_x(i);
             }
         }
+        __syncwarp();
     } else if (warp == 1) {
-        // ===== MMA issuer =====
+        // ===== MMA issuer (then epilogue warp 1) =====
         // instruction descriptor: D fp32, A/B fp16, both K-major, N=bn, M=128
         const uint32_t idesc = (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(H3_BM >> 4) << 24);
         for (int i = 0; i < nkb; ++i) {
@@ -159,6 +218,7 @@ __global__ void __launch_bounds__(H3_THREADS, 1) h3_gemm_kernel(const __grid_con
                     const uint64_t xhi = umma_desc_sw128(st + 2 * w_bytes + ks * 32);
                     const uint64_t xlo = umma_desc_sw128(st + 2 * w_bytes + H3_X_BYTES + ks * 32);
                     const uint32_t acc = (i > 0 || ks > 0) ? 1u : 0u;
+                    if ((p.dbg & 4) && i > 0) continue;
                     umma_f16_afill(tmem_d, xhi, whi, idesc, acc);
                     umma_f16_alast(tmem_d + cross, xhi, wlo, idesc, acc);
                     umma_f16(tmem_d + cross, xlo, whi, idesc, 1u);
@@ -168,12 +228,42 @@ __global__ void __launch_bounds__(H3_THREADS, 1) h3_gemm_kernel(const __grid_con
             }
             __syncwarp();
         }
-    } else {
-        // ===== epilogue warps (2..5): TMEM lanes of this warp = 32 * (warp % 4) =====
+    }
+    {
+        // ===== epilogue, all four warps: TMEM lanes of this warp = 32 * warp =====
+        if (kCell) {   // idle until the accumulator is complete: fetch the cell's reduction-independent operands meanwhile
+#pragma unroll
+            for (int f = 0; f < kMaxPre; ++f)
+                if (f < nf4) load_operands(f, pre_c[f], pre_a[f]);
+        }
         mbar_wait(bar_base + 128, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (threadIdx.x == 0) trace_mark(p.trace, 0);   // main loop done
         const int q = warp & 3;
         const int row = m0 + q * 32 + lane;            // TMEM lane == output row
+        if (kCell) {
+            // partial tile -> shared memory, [row][gate q: 32 units] fp32, 16-byte chunks XOR-swizzled by the row so that both this
+            // (row-per-thread) write and the column-slice reads of the reduction are conflict-free
+            const uint32_t tl = tmem_d + ((uint32_t)(q * 32) << 16);
+            const int rl = q * 32 + lane;
+            uint32_t ra[32], rb[32];
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                SUBGC_TMEM_LD32(ra, tl + (uint32_t)(c * 32));
+                SUBGC_TMEM_LD32(rb, tl + cross + (uint32_t)(c * 32));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t addr = base + (uint32_t)rl * 512u + (uint32_t)(((8 * c + j) ^ (rl & 31)) << 4);
+                    const float v0 = fmaf(__uint_as_float(rb[4 * j]), H3_LO_INV, __uint_as_float(ra[4 * j]));
+                    const float v1 = fmaf(__uint_as_float(rb[4 * j + 1]), H3_LO_INV, __uint_as_float(ra[4 * j + 1]));
+                    const float v2 = fmaf(__uint_as_float(rb[4 * j + 2]), H3_LO_INV, __uint_as_float(ra[4 * j + 2]));
+                    const float v3 = fmaf(__uint_as_float(rb[4 * j + 3]), H3_LO_INV, __uint_as_float(ra[4 * j + 3]));
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        } else {
         float* out = p.part + (size_t)blockIdx.z * p.M * p.N + (size_t)row * p.N;
         const bool vec = ((p.N & 3) == 0);
         const uint32_t tlane = tmem_d + ((uint32_t)(q * 32) << 16);
@@ -271,6 +361,86 @@ __global__ void __launch_bounds__(H3_THREADS, 1) h3_gemm_kernel(const __grid_con
         }
         if (tma_out && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before the CTA retires
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        }
+    }
+    }
+    if (kCell && act) {
+        // ---- split-K reduction across the cluster (ranks in ascending order: deterministic) + LSTM cell on this CTA's share of units.
+        // The epilogue is a chain of latencies (DSMEM ~0.2 us, global ~1 us), so everything that does not depend on the reduction --
+        // previous cell state, hoisted gate term / biases -- is requested before the cluster barrier, and all remote reads of the
+        // thread are in flight together.
+        if (threadIdx.x == 0) trace_mark(p.trace, 1);   // tile staged
+        cluster_sync_all();   // every CTA's partial tile is in its shared memory
+        if (threadIdx.x == 0) trace_mark(p.trace, 2);   // cluster barrier passed
+        if (epi_thread) {
+            for (int f0 = 0; f0 < nf4; f0 += kMaxPre) {
+                float4 g[kMaxPre][4];
+#pragma unroll
+                for (int ff = 0; ff < kMaxPre; ++ff) {
+                    const int f = f0 + ff;
+                    if (f >= nf4) continue;
+                    const int u4 = z * nf4 + f;          // chunk of 4 units inside the tile's 32
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) {
+                        const uint32_t addr = base + (uint32_t)rl * 512u + (uint32_t)(((8 * qq + u4) ^ (rl & 31)) << 4);
+                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int sidx = 0; sidx < nsp; ++sidx) {
+                            const float4 v = ld_dsmem_f4(addr, (uint32_t)sidx);
+                            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                        }
+                        g[ff][qq] = acc;
+                    }
+                }
+#pragma unroll
+                for (int ff = 0; ff < kMaxPre; ++ff) {
+                    const int f = f0 + ff;
+                    if (f >= nf4) continue;
+                    const int j = n0 + 4 * (z * nf4 + f);   // first hidden unit of the chunk
+                    if (!(row < p.M && j < H)) continue;    // H % 4 == 0: a chunk is entirely valid or entirely padding
+                    float4 cp, ad[4];
+                    if (f0 == 0) {
+                        cp = pre_c[ff];
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq) ad[qq] = pre_a[ff][qq];
+                    } else {
+                        load_operands(f, cp, ad);
+                    }
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) {
+                        g[ff][qq].x += ad[qq].x; g[ff][qq].y += ad[qq].y; g[ff][qq].z += ad[qq].z; g[ff][qq].w += ad[qq].w;
+                    }
+                    if (!ce.addend) {
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq) {
+                            const float4 b2 = __ldg(reinterpret_cast<const float4*>(ce.b_hh + qq * H + j));
+                            g[ff][qq].x += b2.x; g[ff][qq].y += b2.y; g[ff][qq].z += b2.z; g[ff][qq].w += b2.w;
+                        }
+                    }
+                    const float gi[4] = {g[ff][0].x, g[ff][0].y, g[ff][0].z, g[ff][0].w}, gf[4] = {g[ff][1].x, g[ff][1].y, g[ff][1].z, g[ff][1].w};
+                    const float gg[4] = {g[ff][2].x, g[ff][2].y, g[ff][2].z, g[ff][2].w}, go[4] = {g[ff][3].x, g[ff][3].y, g[ff][3].z, g[ff][3].w};
+                    const float cpv[4] = {cp.x, cp.y, cp.z, cp.w};
+                    float cn[4], hn[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        cn[e] = sigmoidf_(gf[e]) * cpv[e] + sigmoidf_(gi[e]) * tanhf(gg[e]);
+                        hn[e] = sigmoidf_(go[e]) * tanhf(cn[e]);
+                    }
+                    *reinterpret_cast<float4*>(ce.c_out + (size_t)row * H + j) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+                    *reinterpret_cast<float4*>(ce.h_out + (size_t)row * H + j) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                    if (ce.h16_hi) {
+                        unsigned short hh[4], hl[4];
+                        int ovf = 0;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) split_f16(hn[e], hh[e], hl[e], ovf);
+                        const size_t o16 = (size_t)row * ce.Hp + j;   // Hp % 8 == 0 and j % 4 == 0: 8-byte aligned
+                        *reinterpret_cast<uint2*>(ce.h16_hi + o16) = make_uint2((uint32_t)hh[0] | ((uint32_t)hh[1] << 16), (uint32_t)hh[2] | ((uint32_t)hh[3] << 16));
+                        *reinterpret_cast<uint2*>(ce.h16_lo + o16) = make_uint2((uint32_t)hl[0] | ((uint32_t)hl[1] << 16), (uint32_t)hl[2] | ((uint32_t)hl[3] << 16));
+                    }
+                }
+            }
+        }
+        if (threadIdx.x == 0) trace_mark(p.trace, 3);   // reduction + cell done
+        cluster_sync_all();   // nobody retires while a peer may still read its tile
     }
     __syncthreads();
     trace_end(p.trace);
@@ -489,23 +659,15 @@ static H3Plan h3_plan(int M, int N, const int* segK, int nseg) {
 
 void launch_splitk_reduce(const GemmProblem& p, const float* part, int splits, cudaStream_t stream);
 
-// Workspace: within tc_workspace_bytes(M, N, Ktotal) (split activations take M * Kp * 4 bytes per segment like the fp32 copies there,
-// and the split count is never larger because a k-block covers twice the columns).
-int launch_gemm_h3(const GemmProblem& p, void* ws_, size_t ws_bytes, cudaStream_t stream, RawPartials* raw) {
-    int segK[H3_MAX_SEG];
-    for (int s = 0; s < p.nseg; ++s) segK[s] = p.seg[s].K;
-    const H3Plan pl = h3_plan(p.M, p.N, segK, p.nseg);
-    Workspace ws(ws_, ws_bytes);
-    const bool direct = (pl.splits == 1 && raw == nullptr && p.epi.div == 0.f && p.epi.addend == nullptr && p.epi.group == 0);
-    float* part = direct ? nullptr : ws.take<float>((size_t)pl.splits * p.M * p.N);
-    H3Params hp;
+// Tensor maps of every K segment (weights: boxes of box_w rows; activations: pre-split copies or split here into `ws`)
+static int h3_segments(const GemmProblem& p, int box_w, Workspace& ws, cudaStream_t stream, H3Params& hp) {
     int kb = 0;
     for (int s = 0; s < p.nseg; ++s) {
         const GemmSeg& g = p.seg[s];
-        kb += (g.K + H3_BK - 1) / H3_BK;
-        hp.seg_kb_end[s] = kb;
         const int nkb_seg = (g.K + H3_BK - 1) / H3_BK;
-        if (!make_map_w16(&hp.tm_wh[s], g.W16_hi, p.N, g.w16_rows, nkb_seg, pl.bn) || !make_map_w16(&hp.tm_wl[s], g.W16_lo, p.N, g.w16_rows, nkb_seg, pl.bn)) {
+        kb += nkb_seg;
+        hp.seg_kb_end[s] = kb;
+        if (!make_map_w16(&hp.tm_wh[s], g.W16_hi, p.N, g.w16_rows, nkb_seg, box_w) || !make_map_w16(&hp.tm_wl[s], g.W16_lo, p.N, g.w16_rows, nkb_seg, box_w)) {
             set_error("gemm(h3): cuTensorMapEncodeTiled failed for weight segment %d", s);
             return SUBGC_E_CUDA;
         }
@@ -515,7 +677,10 @@ int launch_gemm_h3(const GemmProblem& p, void* ws_, size_t ws_bytes, cudaStream_
             const int Kp = (g.K + 7) & ~7;
             unsigned short* th = ws.take<unsigned short>((size_t)p.M * Kp);
             unsigned short* tl = ws.take<unsigned short>((size_t)p.M * Kp);
-            if (!ws.ok()) break;
+            if (!ws.ok()) {
+                set_error("gemm(h3): workspace too small");
+                return SUBGC_E_WORKSPACE;
+            }
             const size_t quads = (size_t)p.M * (Kp >> 2);
             int gb = (int)((quads + 255) / 256);
             if (gb > kNumSMs * 8) gb = kNumSMs * 8;
@@ -528,28 +693,51 @@ int launch_gemm_h3(const GemmProblem& p, void* ws_, size_t ws_bytes, cudaStream_
             return SUBGC_E_CUDA;
         }
     }
+    for (int s = p.nseg; s < H3_MAX_SEG; ++s) {
+        hp.seg_kb_end[s] = kb; hp.tm_wh[s] = hp.tm_wh[0]; hp.tm_wl[s] = hp.tm_wl[0]; hp.tm_xh[s] = hp.tm_xh[0]; hp.tm_xl[s] = hp.tm_xl[0];
+    }
+    hp.nseg = p.nseg; hp.M = p.M; hp.N = p.N; hp.kb_total = kb; hp.active = p.active;
+    return SUBGC_OK;
+}
+
+static int h3_set_smem_attr() {
+    static bool attr_set = false;
+    if (!attr_set) {
+        SUBGC_CUDA(cudaFuncSetAttribute(h3_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, H3_SMEM_BUDGET + H3_SMEM_EXTRA));
+        SUBGC_CUDA(cudaFuncSetAttribute(h3_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, H3_SMEM_BUDGET + H3_SMEM_EXTRA));
+        attr_set = true;
+    }
+    return SUBGC_OK;
+}
+
+// Workspace: within tc_workspace_bytes(M, N, Ktotal) (split activations take M * Kp * 4 bytes per segment like the fp32 copies there,
+// and the split count is never larger because a k-block covers four times the columns).
+int launch_gemm_h3(const GemmProblem& p, void* ws_, size_t ws_bytes, cudaStream_t stream, RawPartials* raw) {
+    int segK[H3_MAX_SEG];
+    for (int s = 0; s < p.nseg; ++s) segK[s] = p.seg[s].K;
+    const H3Plan pl = h3_plan(p.M, p.N, segK, p.nseg);
+    Workspace ws(ws_, ws_bytes);
+    const bool direct = (pl.splits == 1 && raw == nullptr && p.epi.div == 0.f && p.epi.addend == nullptr && p.epi.group == 0);
+    float* part = direct ? nullptr : ws.take<float>((size_t)pl.splits * p.M * p.N);
     if (!ws.ok()) {
         set_error("gemm(h3): workspace too small (%zu bytes given)", ws_bytes);
         return SUBGC_E_WORKSPACE;
     }
-    for (int s = p.nseg; s < H3_MAX_SEG; ++s) {
-        hp.seg_kb_end[s] = kb; hp.tm_wh[s] = hp.tm_wh[0]; hp.tm_wl[s] = hp.tm_wl[0]; hp.tm_xh[s] = hp.tm_xh[0]; hp.tm_xl[s] = hp.tm_xl[0];
-    }
-    hp.nseg = p.nseg; hp.M = p.M; hp.N = p.N; hp.bn = pl.bn; hp.stages = pl.stages; hp.kb_total = pl.kb_total; hp.kb_per_split = pl.kb_per_split; hp.part = part; hp.active = p.active;
+    H3Params hp;
+    SUBGC_TRY(h3_segments(p, pl.bn, ws, stream, hp));
+    hp.bn = pl.bn; hp.stages = pl.stages; hp.kb_per_split = pl.kb_per_split; hp.part = part;
     hp.direct = direct ? 1 : 0; hp.epi = p.epi; hp.C = p.C; hp.ldc = p.ldc;
     static const bool tma_store = getenv("SUBGC_H3_NO_TMA_STORE") == nullptr;
     hp.tma_part = 0;
     hp.tm_part = hp.tm_wh[0];
     if (!direct && tma_store && (p.N & 3) == 0 && make_map_part(&hp.tm_part, part, pl.splits, p.M, p.N)) hp.tma_part = 1;
-    static bool attr_set = false;
-    if (!attr_set) {
-        SUBGC_CUDA(cudaFuncSetAttribute(h3_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H3_SMEM_BUDGET + H3_SMEM_EXTRA));
-        attr_set = true;
-    }
+    SUBGC_TRY(h3_set_smem_attr());
     hp.trace = next_trace_slot(1);
+    static const int dbg = getenv("SUBGC_H3_DBG") ? atoi(getenv("SUBGC_H3_DBG")) : 0;
+    hp.dbg = dbg;
     const size_t smem_bytes = (size_t)pl.stages * (2 * pl.bn * H3_BK * 2 + 2 * H3_X_BYTES) + H3_SMEM_EXTRA;
     dim3 grid(pl.n_tiles, pl.m_tiles, pl.splits);
-    SUBGC_CUDA(launch_pdl(h3_gemm_kernel, grid, dim3(H3_THREADS), smem_bytes, stream, hp));
+    SUBGC_CUDA(launch_pdl(h3_gemm_kernel<false>, grid, dim3(H3_THREADS), smem_bytes, stream, hp));
     SUBGC_LAUNCH_CHECK();
     if (direct) return SUBGC_OK;
     if (raw) {
@@ -559,6 +747,70 @@ int launch_gemm_h3(const GemmProblem& p, void* ws_, size_t ws_bytes, cudaStream_
     }
     launch_splitk_reduce(p, part, pl.splits, stream);
     SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}
+
+// gates -> LSTM cell inside the contraction (CellEpilogue): gate-grouped tiles of 32 hidden units, the k-splits of a tile are one
+// thread-block cluster (1, 1, splits), splits in {8, 4, 2, 1}
+int launch_gemm_cell(const GemmProblem& p0, const CellEpilogue& cell, void* ws_, size_t ws_bytes, cudaStream_t stream, bool* fused) {
+    *fused = false;
+    // opt-in (SUBGC_FUSED_CELL=1): correct, but the DSMEM reduction + cell on 128 threads per SM measured ~3 us slower per LSTM than
+    // split-K partials + the (all-resident, PDL-released) cell kernel -- see DESIGN.md
+    static const bool off = !(getenv("SUBGC_FUSED_CELL") != nullptr && getenv("SUBGC_FUSED_CELL")[0] == '1');
+    static int clus = -1;
+    if (clus < 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&clus, cudaDevAttrClusterLaunch, dev);
+    }
+    GemmProblem p = p0;
+    if (p.wts) { resolve_packs(p, p.wts); p.wts = nullptr; }
+    const int H = cell.H;
+    if (off || !clus || H <= 0 || (H & 3) || p.N != 4 * H || !h3_eligible(p)) return SUBGC_OK;
+    if (cell.h16_hi && (cell.Hp & 7)) return SUBGC_OK;
+    for (int s = 0; s < p.nseg; ++s)
+        if (p.seg[s].w16_rows < 4 * H) return SUBGC_OK;
+    int kb_total = 0;
+    for (int s = 0; s < p.nseg; ++s) kb_total += (p.seg[s].K + H3_BK - 1) / H3_BK;
+    const int n_tiles = (H + 31) / 32, m_tiles = (p.M + H3_BM - 1) / H3_BM;
+    const long long tiles = (long long)n_tiles * m_tiles;
+    auto valid = [&](int sp) {   // every split non-empty, at least 2 k-blocks each (unless unsplit), TMEM chain within its limit
+        const int k = (kb_total + sp - 1) / sp;
+        return (sp == 1 || k >= 2) && (kb_total + k - 1) / k == sp && k <= H3_MAX_CHAIN;
+    };
+    int splits = 0;
+    const int desc[4] = {8, 4, 2, 1};
+    for (int i = 0; i < 4 && !splits; ++i)
+        if (valid(desc[i]) && tiles * desc[i] <= kNumSMs) splits = desc[i];      // one wave: as many splits as fit
+    for (int i = 3; i >= 0 && !splits; --i)
+        if (valid(desc[i])) splits = desc[i];                                    // several waves: as few splits as the chain limit allows
+    if (!splits) return SUBGC_OK;
+    const int kps = (kb_total + splits - 1) / splits;
+    Workspace ws(ws_, ws_bytes);
+    H3Params hp;
+    SUBGC_TRY(h3_segments(p, 32, ws, stream, hp));
+    hp.bn = 128; hp.kb_per_split = kps; hp.part = nullptr; hp.direct = 0; hp.epi = GemmEpilogue(); hp.C = nullptr; hp.ldc = 0;
+    hp.tma_part = 0; hp.tm_part = hp.tm_wh[0];
+    const int stage_bytes = 2 * 128 * H3_BK * 2 + 2 * H3_X_BYTES;
+    hp.stages = H3_SMEM_BUDGET / stage_bytes;
+    hp.cell = cell;
+    SUBGC_TRY(h3_set_smem_attr());
+    hp.trace = next_trace_slot(6);
+    hp.dbg = 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_tiles, m_tiles, splits);
+    cfg.blockDim = dim3(H3_THREADS);
+    cfg.dynamicSmemBytes = (size_t)hp.stages * stage_bytes + H3_SMEM_EXTRA;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = splits;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 2;
+    SUBGC_CUDA(cudaLaunchKernelEx(&cfg, h3_gemm_kernel<true>, hp));
+    SUBGC_LAUNCH_CHECK();
+    *fused = true;
     return SUBGC_OK;
 }
 

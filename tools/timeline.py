@@ -19,7 +19,7 @@ L = _lib.lib()
 L.subgc_debug_trace.restype = C.c_int
 L.subgc_debug_trace.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int]
 opt = {"beam_size": 5 if mode == "beam" else 1}
-st0 = (C.c_ulonglong * (4 * 4096))(); ids0 = (C.c_int * 4096)()
+st0 = (C.c_ulonglong * (8 * 4096))(); ids0 = (C.c_int * 4096)()
 with torch.no_grad():
     model(*args, opt=opt, mode="sample")            # eager
     L.subgc_debug_trace(0, None, None, 0)           # slots restart: the capture call numbers the graph's launches 0..n
@@ -31,15 +31,15 @@ with torch.no_grad():
     model(*args, opt=opt, mode="sample")
 torch.cuda.synchronize()
 N = 4096
-st = (C.c_ulonglong * (4 * N))(); ids = (C.c_int * N)()
+st = (C.c_ulonglong * (8 * N))(); ids = (C.c_int * N)()
 # slot numbering was restarted before the capture call, but eager launches of later calls keep counting: read the first slots
 m = L.subgc_debug_trace(2, st, ids, N)
-t = np.array(st, dtype=np.float64).reshape(N, 4)[:m]
+t = np.array(st, dtype=np.float64).reshape(N, 8)[:m]
 k = np.array(ids[:m])
 ok = (t[:, 1] > 0) & (t[:, 0] < 1e19)
 print("slots after capture call:", n_slots, "slots now:", m, "ids histogram:", {int(i): int((k == i).sum()) for i in np.unique(k)},
       "valid per id:", {int(i): int((ok & (k == i)).sum()) for i in np.unique(k)})
-names = {1: "h3_gemm", 2: "cell", 3: "attention", 4: "select", 5: "att_phase"}
+names = {1: "h3_gemm", 2: "cell", 3: "attention", 4: "select", 5: "att_phase", 6: "h3_gemm+cell"}
 t0 = t[ok, 0].min()
 idx = np.nonzero(ok)[0]
 sel = [i for i in idx if k[i] == 4]
@@ -52,7 +52,7 @@ if len(sel) >= 12:
         if not ok[i]:
             continue
         z = t[sel[9], 1]
-        print(f"  {names.get(k[i], k[i]):10s} {(t[i,0]-z)/1e3:8.2f} {(t[i,2]-z)/1e3:8.2f} ..{(t[i,3]-z)/1e3:7.2f} {(t[i,1]-z)/1e3:8.2f}   | {(t[i,1]-prev_end)/1e3:7.2f}")
+        print(f"  {names.get(int(k[i]), str(k[i])):12s} {(t[i,0]-z)/1e3:8.2f} {(t[i,2]-z)/1e3:8.2f} ..{(t[i,3]-z)/1e3:7.2f} {(t[i,1]-z)/1e3:8.2f}   | {(t[i,1]-prev_end)/1e3:7.2f}   marks " + " ".join(f"{(t[i,4+j]-z)/1e3:7.2f}" if t[i,4+j] > 0 else "   -   " for j in range(4)))
         prev_end = t[i, 1]
     print(f"  step total {(t[sel[10],1]-t[sel[9],1])/1e3:.2f} us")
 for kid, nm in names.items():
