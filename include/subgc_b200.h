@@ -110,6 +110,9 @@ typedef struct subgc_weights {
     const float* lang_b_ih; const float* lang_b_hh;
     const subgc_packed* packs;                         /* HOST array of packed copies (nullable)                 */
     int32_t n_packs;
+    int32_t* h3_overflow;                              /* DEVICE flag (nullable): OR-ed with 1 when an activation fed to the
+                                                          split-fp16 path did not fit fp16 (|x| > 65504, saturated): the
+                                                          results of that call are invalid, re-run without packs          */
 } subgc_weights;
 
 /* How sub-graph s of a flat list maps onto the loader tensors gpn_obj_ind / att_masks [rows,2,per_half,N].

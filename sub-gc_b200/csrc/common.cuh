@@ -128,6 +128,7 @@ struct GemmProblem {
     int ldc = 0;
     const int* active = nullptr;  // optional device flag: kernel exits immediately when *active == 0
     const subgc_weights* wts = nullptr;  // when set, segments whose weight has a packed copy there take the split-fp16 path
+    int* overflow = nullptr;             // device flag raised when an activation saturates in the fp16 split (from wts->h3_overflow)
 };
 
 size_t gemm_workspace_bytes(int M, int N, int Ktotal);
@@ -292,12 +293,13 @@ __device__ __forceinline__ void split_f16(float v, unsigned short& hi, unsigned 
     hi = __half_as_ushort(h);
     lo = __half_as_ushort(__float2half_rn(r));
 }
-__device__ __forceinline__ void split_f16_store(float v, unsigned short* hi, unsigned short* lo, size_t idx) {
+__device__ __forceinline__ void split_f16_store(float v, unsigned short* hi, unsigned short* lo, size_t idx, int* overflow = nullptr) {
     int ovf = 0;
     unsigned short h, l;
     split_f16(v, h, l, ovf);
     hi[idx] = h;
     lo[idx] = l;
+    if (ovf && overflow) atomicOr(overflow, 1);
 }
 // bias / addend / divide / ReLU / zero-padding part of the contraction epilogue (accumulate-into-C is applied by the caller)
 __device__ __forceinline__ float epilogue_apply(const GemmEpilogue& e, float v, int m, int n) {

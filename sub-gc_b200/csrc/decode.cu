@@ -74,6 +74,11 @@ __global__ void __launch_bounds__(256, 6) lstm_reduce_cell_kernel(const float* _
 constexpr int kAttThreads = 1024;  // one block per row; the row is latency-bound (28 MB of att / p_att per step over 128 rows), so every
                                    // warp slot of the SM is used to keep loads in flight
 
+__device__ __forceinline__ void attention_tail(float* s_e, float* s_c, int r, int cr, const float* __restrict__ att, const float* __restrict__ masks,
+                                               float* __restrict__ ctx, float* __restrict__ att_w, int att_w_stride, int len_max, int H,
+                                               unsigned short* __restrict__ c16_hi, unsigned short* __restrict__ c16_lo, int Hp,
+                                               TraceSlot trace = TraceSlot{nullptr, 0}, int* overflow = nullptr);
+
 // body shared by attention_kernel and the fused att-phase kernel: expects s_h (atth of this row) and s_w (alpha_net weight)
 // filled and synchronised
 __device__ __forceinline__ void attention_row_body(float* s_h, float* s_w, float* s_e, float* s_c, int r, int cr, const float* __restrict__ p_att,
@@ -110,6 +115,15 @@ __device__ __forceinline__ void attention_row_body(float* s_h, float* s_w, float
         }
     }
     __syncthreads();
+    attention_tail(s_e, s_c, r, cr, att, masks, ctx, att_w, att_w_stride, len_max, H, c16_hi, c16_lo, Hp);
+}
+
+// softmax / mask / renormalise over the scores s_e[0..len_max) (filled and synchronised) and the context vector
+__device__ __forceinline__ void attention_tail(float* s_e, float* s_c, int r, int cr, const float* __restrict__ att, const float* __restrict__ masks,
+                                               float* __restrict__ ctx, float* __restrict__ att_w, int att_w_stride, int len_max, int H,
+                                               unsigned short* __restrict__ c16_hi, unsigned short* __restrict__ c16_lo, int Hp, TraceSlot trace,
+                                               int* overflow) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (wid == 0) {  // len_max <= 64: one warp finishes the softmax / mask / renormalise (two-stage, as the reference)
         float m = -INFINITY;
         for (int n = lane; n < len_max; n += 32) m = fmaxf(m, s_e[n]);
@@ -132,6 +146,7 @@ __device__ __forceinline__ void attention_row_body(float* s_h, float* s_w, float
         }
     }
     __syncthreads();
+    if (threadIdx.x == 0) trace_mark(trace, 2);   // softmax done
     // context: four thread groups take interleaved node subsets (n = g, g+4, ...), partials combined in fixed order
     const float* af = att + (size_t)cr * len_max * H;
     const int grp = threadIdx.x >> 8, tg = threadIdx.x & 255;
@@ -158,45 +173,94 @@ __device__ __forceinline__ void attention_row_body(float* s_h, float* s_w, float
     for (int j = threadIdx.x; j < H; j += blockDim.x) {
         const float cv = ((s_c[j] + s_c[H + j]) + s_c[2 * H + j]) + s_c[3 * H + j];
         ctx[(size_t)r * H + j] = cv;
-        if (c16_hi) split_f16_store(cv, c16_hi, c16_lo, (size_t)r * Hp + j);
+        if (c16_hi) split_f16_store(cv, c16_hi, c16_lo, (size_t)r * Hp + j, overflow);
     }
 }
 
 // (<= 40 registers: 1024 threads fit next to a contraction CTA, which then prefetches its weight ring while this kernel runs)
-__global__ void __maxnreg__(40) attention_kernel(const float* __restrict__ atth_part, int splits, const float* __restrict__ h2att_b,
+__global__ void __maxnreg__(48) attention_kernel(const float* __restrict__ atth_part, int splits, const float* __restrict__ h2att_b,
                                                                 const float* __restrict__ p_att, const float* __restrict__ att,
                                                                 const float* __restrict__ masks, const float* __restrict__ alpha_w,
                                                                 const float* __restrict__ alpha_b, float* __restrict__ ctx, float* __restrict__ att_w,
                                                                 int att_w_stride, int S, int len_max, int H, int AH, int rows_per_ctx,
                                                                 const int* __restrict__ active, unsigned short* __restrict__ c16_hi,
-                                                                unsigned short* __restrict__ c16_lo, int Hp, TraceSlot trace) {
+                                                                unsigned short* __restrict__ c16_lo, int Hp, TraceSlot trace, int* overflow) {
     trace_begin(trace);
     pdl_trigger();
-    {   // the row's attention operands do not depend on this step: request them into L2 while the predecessor kernels still run
-        const int cr0 = blockIdx.x / rows_per_ctx;
-        const char* pa = reinterpret_cast<const char*>(p_att + (size_t)cr0 * len_max * AH);
-        const char* af = reinterpret_cast<const char*>(att + (size_t)cr0 * len_max * H);
-        const size_t nb_p = (size_t)len_max * AH * 4, nb_a = (size_t)len_max * H * 4;
-        for (size_t o = (size_t)threadIdx.x * 128; o < nb_p; o += (size_t)blockDim.x * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + o));
-        for (size_t o = (size_t)threadIdx.x * 128; o < nb_a; o += (size_t)blockDim.x * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(af + o));
-    }
-    pdl_wait();
-    trace_released(trace);
-    if (active != nullptr && *active == 0) return;
-    extern __shared__ float s_att[];  // [AH] atth | [AH] alpha_w | [64] e | [4][H] context partials
+    extern __shared__ float s_att[];  // [AH] atth | [AH] alpha_w | [64] e | [4][H] context partials (first 256 floats: score partials)
     float* s_h = s_att;
     float* s_w = s_att + AH;
     float* s_e = s_att + 2 * AH;
     float* s_c = s_att + 2 * AH + 64;
     const int r = blockIdx.x, cr = r / rows_per_ctx;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    // p_att / att / alpha_net do not depend on this step.  Before the dependency wait: the p_att quads this thread scores go into
+    // registers (work item = (node, 32-quad slice); a warp owns items wid, wid + nw, ...), att is requested into L2.
+    constexpr int kMaxItems = 5;
+    const int AH4 = AH >> 2, Q = AH4 >> 5;
+    const int items = len_max * Q;
+    const bool fast = (AH & 127) == 0 && items <= kMaxItems * nw && items <= 256;
+    float4 pv[kMaxItems];
+    if (fast) {
+        const float4* pa4 = reinterpret_cast<const float4*>(p_att + (size_t)cr * len_max * AH);
+#pragma unroll
+        for (int k = 0; k < kMaxItems; ++k) {
+            const int item = wid + k * nw;
+            pv[k] = item < items ? __ldg(pa4 + (size_t)(item / Q) * AH4 + (item % Q) * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    {
+        const char* af = reinterpret_cast<const char*>(att + (size_t)cr * len_max * H);
+        const size_t nb_a = (size_t)len_max * H * 4;
+        for (size_t o = (size_t)threadIdx.x * 128; o < nb_a; o += (size_t)blockDim.x * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(af + o));
+        if (!fast) {
+            const char* pa = reinterpret_cast<const char*>(p_att + (size_t)cr * len_max * AH);
+            const size_t nb_p = (size_t)len_max * AH * 4;
+            for (size_t o = (size_t)threadIdx.x * 128; o < nb_p; o += (size_t)blockDim.x * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + o));
+        }
+    }
+    for (int j = threadIdx.x; j < AH; j += blockDim.x) s_w[j] = __ldg(alpha_w + j);
+    pdl_wait();
+    trace_released(trace);
+    if (active != nullptr && *active == 0) return;
     for (int j = threadIdx.x; j < AH; j += blockDim.x) {
         float a = 0.f;
         for (int z = 0; z < splits; ++z) a += atth_part[((size_t)z * S + r) * AH + j];
         s_h[j] = a + __ldg(h2att_b + j);
-        s_w[j] = __ldg(alpha_w + j);
     }
     __syncthreads();
-    attention_row_body(s_h, s_w, s_e, s_c, r, cr, p_att, att, masks, alpha_b, ctx, att_w, att_w_stride, len_max, H, AH, c16_hi, c16_lo, Hp);
+    if (threadIdx.x == 0) trace_mark(trace, 0);   // atth reduced
+    if (!fast) {
+        attention_row_body(s_h, s_w, s_e, s_c, r, cr, p_att, att, masks, alpha_b, ctx, att_w, att_w_stride, len_max, H, AH, c16_hi, c16_lo, Hp);
+        trace_end(trace);
+        return;
+    }
+    {
+        const float4* h4 = reinterpret_cast<const float4*>(s_h);
+        const float4* w4 = reinterpret_cast<const float4*>(s_w);
+#pragma unroll
+        for (int k = 0; k < kMaxItems; ++k) {
+            const int item = wid + k * nw;
+            if (item >= items) continue;
+            const int j4 = (item % Q) * 32 + lane;
+            const float4 v = pv[k], hh = h4[j4], ww = w4[j4];
+            float a = ww.x * tanhf(v.x + hh.x);
+            a = fmaf(ww.y, tanhf(v.y + hh.y), a);
+            a = fmaf(ww.z, tanhf(v.z + hh.z), a);
+            a = fmaf(ww.w, tanhf(v.w + hh.w), a);
+            a = warp_sum(a);
+            if (lane == 0) s_c[item] = a;   // score partial of (node, slice); combined below in slice order
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < len_max) {
+        float e = 0.f;
+        for (int q = 0; q < Q; ++q) e += s_c[threadIdx.x * Q + q];
+        s_e[threadIdx.x] = e + __ldg(alpha_b);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) trace_mark(trace, 1);   // scores done
+    attention_tail(s_e, s_c, r, cr, att, masks, ctx, att_w, att_w_stride, len_max, H, c16_hi, c16_lo, Hp, trace, overflow);
     trace_end(trace);
 }
 
@@ -425,6 +489,7 @@ struct SelectArgs {
     unsigned short *xt16_hi, *xt16_lo;   // nullable split-fp16 copy of xt, [S, Xp]
     int Xp;
     TraceSlot trace;
+    int* overflow;                       // nullable device flag: an embedding value did not fit the fp16 split
 };
 
 constexpr int kSelectThreads = 1024;  // one block per row: the row is latency-bound, so use every warp slot of the SM
@@ -535,7 +600,7 @@ __global__ void __launch_bounds__(kSelectThreads) select_kernel(const SelectArgs
         for (int j = threadIdx.x; j < a.X; j += blockDim.x) {
             const float xv = fmaxf(__ldg(e + j), 0.f);
             a.xt[(size_t)r * a.X + j] = xv;
-            if (a.xt16_hi) split_f16_store(xv, a.xt16_hi, a.xt16_lo, (size_t)r * a.Xp + j);
+            if (a.xt16_hi) split_f16_store(xv, a.xt16_hi, a.xt16_lo, (size_t)r * a.Xp + j, a.overflow);
         }
     }
     trace_end(a.trace);
@@ -661,7 +726,7 @@ __global__ void __maxnreg__(40) select_reg_kernel(const SelectArgs a) {
         for (int j = tid; j < a.X; j += blockDim.x) {
             const float xv = fmaxf(__ldg(e + j), 0.f);
             a.xt[(size_t)r * a.X + j] = xv;
-            if (a.xt16_hi) split_f16_store(xv, a.xt16_hi, a.xt16_lo, (size_t)r * a.Xp + j);
+            if (a.xt16_hi) split_f16_store(xv, a.xt16_hi, a.xt16_lo, (size_t)r * a.Xp + j, a.overflow);
         }
     }
     trace_end(a.trace);
@@ -883,7 +948,8 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
         if (!(skip & 4)) SUBGC_TRY(launch_gemm_raw(p, sc.gemm_ws, sc.gemm_ws_bytes, st, &rp));
         if (!(skip & 8)) launch_pdl(attention_kernel, dim3(S), dim3(kAttThreads), smem, st, rp.part, rp.splits, w->h2att.b, p_att, att, masks, w->alpha_net.w, w->alpha_net.b,
                                                                         sc.ctx, att_w, att_w_stride, S, len_max, H, AH, rows_per_ctx, active,
-                                                                        use16 ? h16->ctx_hi : nullptr, use16 ? h16->ctx_lo : nullptr, use16 ? h16->Hp : 0, next_trace_slot(3));
+                                                                        use16 ? h16->ctx_hi : nullptr, use16 ? h16->ctx_lo : nullptr, use16 ? h16->Hp : 0, next_trace_slot(3),
+                                                                        (int*)(use16 ? w->h3_overflow : nullptr));
         SUBGC_LAUNCH_CHECK();
     }
     if (upto == 1) return SUBGC_OK;
@@ -1227,6 +1293,7 @@ extern "C" int subgc_decode_sample(const subgc_dims* d, const subgc_weights* w, 
         a.embed = w->embed; a.xt = xt; a.X = d->enc;
         a.xt16_hi = s16 ? b16.xt[0] : nullptr; a.xt16_lo = s16 ? b16.xt[1] : nullptr; a.Xp = s16 ? b16.Xp : 0;
         a.trace = next_trace_slot(4);
+        a.overflow = s16 ? w->h3_overflow : nullptr;
         if (!(skip_mask() & 128)) {
             if (V1 <= kSelVals * kSelectThreads) launch_pdl(select_reg_kernel, dim3(S), dim3(kSelectThreads), (size_t)0, st, a);
             else launch_pdl(select_kernel, dim3(S), dim3(kSelectThreads), (size_t)V1 * sizeof(float), st, a);

@@ -55,6 +55,7 @@ struct H3Params {
     int tma_part;          // 1: the partial tiles leave through shared memory + TMA stores (full 128-byte lines) instead of per-thread rows
     TraceSlot trace;
     CellEpilogue cell;     // kCell instantiation only
+    int pf_dist;           // k-blocks the L2 prefetch of weight tiles runs ahead of the ring (0 = off)
     int dbg;               // timing experiments only (SUBGC_H3_DBG bit mask, results are wrong): 1 no activation loads after the first
                            // ring round, 2 no weight loads after it, 4 no MMAs
 };
@@ -132,6 +133,25 @@ __global__ void __launch_bounds__(H3_THREADS, 1) h3_gemm_kernel(const __grid_con
             tma_load_3d(st + w_bytes, &p.tm_wl[seg_w], full, 0, n0, kc / H3_BK);
         }
     };
+    // L2 prefetch of the weight tiles of k-block i: the ring holds only ~96 KB of weights per SM, which is less than HBM latency x
+    // bandwidth; requests running `pf_dist` k-blocks ahead of the ring keep enough bytes in flight without shared memory
+    int seg_p = 0;
+    auto prefetch_w = [&](int i) {
+        if (i >= nkb) return;
+        const int kb = kb_begin + i;
+        while (seg_p < p.nseg - 1 && kb >= p.seg_kb_end[seg_p]) ++seg_p;
+        const int kbi = kb - (seg_p == 0 ? 0 : p.seg_kb_end[seg_p - 1]);
+        if (kCell) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                tma_prefetch_l2_3d(&p.tm_wh[seg_p], 0, q * p.cell.H + n0, kbi);
+                tma_prefetch_l2_3d(&p.tm_wl[seg_p], 0, q * p.cell.H + n0, kbi);
+            }
+        } else {
+            tma_prefetch_l2_3d(&p.tm_wh[seg_p], 0, n0, kbi);
+            tma_prefetch_l2_3d(&p.tm_wl[seg_p], 0, n0, kbi);
+        }
+    };
     auto issue_x = [&](int i) {
         const int kb = kb_begin + i;
         while (seg_x < p.nseg - 1 && kb >= p.seg_kb_end[seg_x]) ++seg_x;
@@ -148,6 +168,7 @@ __global__ void __launch_bounds__(H3_THREADS, 1) h3_gemm_kernel(const __grid_con
     if (producer) {   // fill the weight half of the ring while the predecessor kernel is still running
         for (int sgi = 0; sgi < p.nseg; ++sgi) { prefetch_tensormap(&p.tm_wh[sgi]); prefetch_tensormap(&p.tm_wl[sgi]); }
         for (int i = 0; i < pre; ++i) issue_w(i);
+        for (int i = pre; i < pre + p.pf_dist; ++i) prefetch_w(i);
         for (int sgi = 0; sgi < p.nseg; ++sgi) { prefetch_tensormap(&p.tm_xh[sgi]); prefetch_tensormap(&p.tm_xl[sgi]); }
     }
     pdl_wait();      // from here on the activations / flags written by earlier kernels are visible
@@ -193,6 +214,7 @@ __global__ void __launch_bounds__(H3_THREADS, 1) h3_gemm_kernel(const __grid_con
                 const int s = i % stages;
                 if (i >= pre) {
                     const uint32_t ph = (uint32_t)(i / stages) & 1u;
+                    if (p.pf_dist > 0) prefetch_w(i + p.pf_dist);
                     mbar_wait(bar_base + 64 + 8 * s, ph ^ 1u);
                     issue_w(i);
                     issue_x(i);
@@ -210,6 +232,8 @@ __global__ void __launch_bounds__(H3_THREADS, 1) h3_gemm_kernel(const __grid_con
             mbar_wait(bar_base + 8 * s, ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
+                if (!kCell && i == 0) trace_mark(p.trace, 1);   // first stage landed
+                if (!kCell && i == nkb - 1) trace_mark(p.trace, 2);   // last stage landed
                 const uint32_t st = base + s * stage_bytes;
 #pragma unroll
                 for (int ks = 0; ks < H3_BK / 16; ++ks) {
@@ -587,6 +611,7 @@ bool h3_eligible(const GemmProblem& p) {
 
 void resolve_packs(GemmProblem& p, const subgc_weights* w) {
     if (!w || !w->packs || w->n_packs <= 0 || !h3_mode()) return;
+    p.overflow = w->h3_overflow;
     for (int s = 0; s < p.nseg; ++s) {
         GemmSeg& g = p.seg[s];
         if (g.W16_hi) continue;
@@ -684,7 +709,7 @@ static int h3_segments(const GemmProblem& p, int box_w, Workspace& ws, cudaStrea
             const size_t quads = (size_t)p.M * (Kp >> 2);
             int gb = (int)((quads + 255) / 256);
             if (gb > kNumSMs * 8) gb = kNumSMs * 8;
-            SUBGC_CUDA(launch_pdl(split_rows_kernel, dim3(gb), dim3(256), (size_t)0, stream, g, p.M, Kp, th, tl, p.active, (int*)nullptr));
+            SUBGC_CUDA(launch_pdl(split_rows_kernel, dim3(gb), dim3(256), (size_t)0, stream, g, p.M, Kp, th, tl, p.active, p.overflow));
             SUBGC_LAUNCH_CHECK();
             xh = th; xl = tl; xld = Kp;
         }
@@ -735,6 +760,8 @@ int launch_gemm_h3(const GemmProblem& p, void* ws_, size_t ws_bytes, cudaStream_
     hp.trace = next_trace_slot(1);
     static const int dbg = getenv("SUBGC_H3_DBG") ? atoi(getenv("SUBGC_H3_DBG")) : 0;
     hp.dbg = dbg;
+    static const int pf = getenv("SUBGC_H3_PF") ? atoi(getenv("SUBGC_H3_PF")) : 8;
+    hp.pf_dist = pf;
     const size_t smem_bytes = (size_t)pl.stages * (2 * pl.bn * H3_BK * 2 + 2 * H3_X_BYTES) + H3_SMEM_EXTRA;
     dim3 grid(pl.n_tiles, pl.m_tiles, pl.splits);
     SUBGC_CUDA(launch_pdl(h3_gemm_kernel<false>, grid, dim3(H3_THREADS), smem_bytes, stream, hp));
@@ -797,6 +824,7 @@ int launch_gemm_cell(const GemmProblem& p0, const CellEpilogue& cell, void* ws_,
     SUBGC_TRY(h3_set_smem_attr());
     hp.trace = next_trace_slot(6);
     hp.dbg = 0;
+    hp.pf_dist = 8;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(n_tiles, m_tiles, splits);
     cfg.blockDim = dim3(H3_THREADS);

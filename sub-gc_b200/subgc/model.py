@@ -185,6 +185,7 @@ class TopDownModel(nn.Module):
         self._packs = packing.PackCache()
         self._pack_key = None
         self.use_packed = True   # inference contractions read split-fp16 copies of the weights (subgc.packing)
+        self._ovf_dev = self._ovf_host = self._ovf_event = None   # fp16-range guard of the split activations (check_numerics)
         self.stage_events = None  # set to [] to collect (name, start_event, end_event) per stage (bench / profiling)
         self.dropout_enabled = True   # tests switch it off: Philox masks cannot match torch's RNG stream (SURVEY §7 hard part 5)
         self.force_train_path = False  # run the autograd-capable path in eval mode too (gradient parity tests)
@@ -256,8 +257,15 @@ class TopDownModel(nn.Module):
         if not use:
             if w.n_packs:
                 w.packs, w.n_packs = None, 0
+                w.h3_overflow = None
                 self._plans.clear()
             return
+        dev = next(iter(params.values())).device
+        if self._ovf_dev is None or self._ovf_dev.device != dev:
+            self._ovf_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._ovf_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self._plans.clear()
+        w.h3_overflow = self._ovf_dev.data_ptr()
         named = {n: p for n, p in params.items() if p.dim() == 2 and p.shape[0] >= 64 and n not in self._PACK_SKIP}
         H = self.rnn_size   # K segments of the un-concatenated LSTM inputs: [h_lang | fc | x_t] and [ctx | h_att]
         arr, cnt = self._packs.build(named, {"core.att_lstm.weight_ih": [H, 2 * H], "core.lang_lstm.weight_ih": [H]})
@@ -265,6 +273,29 @@ class TopDownModel(nn.Module):
             w.packs, w.n_packs = arr, cnt
             self._pack_key = self._packs.array_key
             self._plans.clear()  # captured graphs hold the old packed-copy addresses
+
+    def _arm_overflow_check(self):
+        """Queue an asynchronous read-back of the fp16-range flag the split-fp16 kernels raise (no synchronisation here)."""
+        if self._ovf_dev is not None and self._wcache is not None and self._wcache[1].n_packs:
+            self._ovf_host.copy_(self._ovf_dev, non_blocking=True)
+            self._ovf_event = torch.cuda.Event()
+            self._ovf_event.record()
+
+    def check_numerics(self, block=True):
+        """The split-fp16 tensor-core path saturates activations beyond +-65504 and raises a device flag.  Polled at the start of
+        every call (non-blocking) and on demand (block=True): if the flag is up, the packed path is switched off for this model
+        and the caller is told that the previous results are invalid."""
+        ev = self._ovf_event
+        if ev is None or not (block or ev.query()):
+            return
+        ev.synchronize()
+        self._ovf_event = None
+        if int(self._ovf_host[0]) != 0:
+            self._ovf_dev.zero_()
+            self.use_packed = False
+            raise _lib.SubgcError("an activation exceeded the fp16 range of the split-fp16 tensor-core path (|x| > 65504): the results of "
+                                  "the previous call are invalid.  Packed weights are now disabled for this model (fp32 split-TF32 "
+                                  "path); run the call again.")
 
     def _train_ops(self):
         from .train import CudaOps
@@ -413,6 +444,7 @@ class TopDownModel(nn.Module):
         (seq, seqLogprobs, subgraph_score, keep_ind[, att2_weights])."""
         if not self.test_LSTM:
             raise _lib.SubgcError("mode='sample' needs a model built with opt.test_LSTM=1 (as test.py does)")
+        self.check_numerics(block=False)
         beam_size = opt.get("beam_size", 1)
         return_att = opt.get("return_att", 0) == 1
         if not opt.get("sample_max", 1) and not self.topk_sampling and beam_size == 1:
@@ -457,6 +489,7 @@ class TopDownModel(nn.Module):
 
         plan.run(launch, self.use_graphs)
         self._mark("decode")
+        self._arm_overflow_check()
         self.last_steps = o["steps"]
         seq, lps = o["seq"].clone(), o["lps"].clone()
         if return_att:
@@ -492,8 +525,10 @@ class TopDownModel(nn.Module):
 
         plan.run(launch, self.use_graphs)
         self._mark("decode")
+        self._arm_overflow_check()
         # the reference hands back CPU tensors and python lists here (AttModel.py:212-213,229-231)
         seq_h, lps_h, p_h, up_h, cnt_h = o["seq"].cpu(), o["lps"].cpu(), o["p"].cpu(), o["up"].cpu(), o["cnt"].cpu()
+        self.check_numerics(block=True)   # the copies above synchronised already
         self.done_beams = [[dict(seq=seq_h[k, j], logps=lps_h[k, j], unaug_p=float(up_h[k, j]), p=float(p_h[k, j]))
                             for j in range(int(cnt_h[k]))] for k in range(n_sub)]
         return seq_h[:, 0].contiguous(), lps_h[:, 0].contiguous()
