@@ -192,7 +192,7 @@ def main():
     d = Dims()
     config = {"workload": f"BASELINE config 2: {IMAGES_PER_GPU} images/GPU x 36 nodes x 2048-d, 64 edges, 1 full sub-graph kept per image "
                           f"(NMS 0.75/max 1), {args.mode} 20-token decode, V=9487",
-              "images_per_gpu": IMAGES_PER_GPU, "rows_per_gpu": IMAGES_PER_GPU, "decode": args.mode, "weights": "random init (synthetic), fp32",
+              "images_per_gpu": IMAGES_PER_GPU, "rows_per_gpu": IMAGES_PER_GPU, "decode": args.mode, "weights": "random init (synthetic), fp32 (+ split-fp16 packed copies of the same 4 bytes per weight for the tensor cores)",
               "l2": "per-step working set (280 MB weights + 83 MB inputs + activations) exceeds the 126 MB L2; no explicit flush"}
     cores = os.cpu_count() or 1
 
@@ -331,15 +331,20 @@ def main():
         algo_steps = d.seq_length                                 # 20 algorithmic steps per caption
         algo_bytes = algo_steps * (W_BYTES + n_rows * ROW_BYTES)
         achieved = algo_bytes / t_dec / 1e9
-        line["roofline"] = {"bound": "hbm", "kernel": "decode loop (subgc_decode_sample: 20 x [att-LSTM, attention, lang-LSTM, logit, select])",
+        traffic, traffic_note = None, "no ncu capture found under profiles/"
+        tp = os.path.join(ROOT, "profiles", "r01_decode_traffic.json")
+        if os.path.isfile(tp) and args.mode == "greedy":
+            tj = json.load(open(tp))
+            traffic, traffic_note = tj["dram_bytes_per_decode_loop"], tj["note"]
+        line["roofline"] = {"bound": "hbm", "kernel": "decode loop (subgc_decode_sample: 20 x [att-LSTM, cell, h2att, attention, lang-LSTM, cell, "
+                                                      "logit, select])",
                             "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                            "traffic": 4.85e9 if args.mode == "greedy" else None,
-                            "traffic_note": "sum of dram__bytes_read+write over the 160 launches of one decode loop from profiles/r01_ncu_decode_tc.md "
-                                            "(cold-cache replay: the 1.0 GB of split-K partial reads hit L2 in the live run)",
+                            "traffic": traffic, "traffic_note": traffic_note,
                             "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
                             "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": t_dec * 1e3,
                             "tensor_equiv": {"achieved_tflops": algo_steps * n_rows * ROW_FLOPS / t_dec / 1e12, "peak_tflops": tf_peak,
-                                             "note": "fp32 FMA path: tensor pipe unused in this round"}}
+                                             "note": "algorithmic flops; the contractions run as 3 tcgen05 kind::f16 products per fp32 product "
+                                                     "(split-fp16 operands, fp32 accumulation in TMEM)"}}
     if not args.no_cpu_baseline:
         cval, cms, cn = cpu_reference(d, sd, data, args.mode, args.cpu_steps, 1, cores)
         line["cpu_baseline"] = {"value": cval, "unit": "captions/s", "cores": cores, "kind": "port", "ms_per_step": cms,

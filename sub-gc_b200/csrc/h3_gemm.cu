@@ -760,7 +760,7 @@ int launch_gemm_h3(const GemmProblem& p, void* ws_, size_t ws_bytes, cudaStream_
     hp.trace = next_trace_slot(1);
     static const int dbg = getenv("SUBGC_H3_DBG") ? atoi(getenv("SUBGC_H3_DBG")) : 0;
     hp.dbg = dbg;
-    static const int pf = getenv("SUBGC_H3_PF") ? atoi(getenv("SUBGC_H3_PF")) : 8;
+    static const int pf = getenv("SUBGC_H3_PF") ? atoi(getenv("SUBGC_H3_PF")) : 0;   // measured: no gain (the loop is bound by stage turn-around, not by HBM latency), costs TMA issue slots
     hp.pf_dist = pf;
     const size_t smem_bytes = (size_t)pl.stages * (2 * pl.bn * H3_BK * 2 + 2 * H3_X_BYTES) + H3_SMEM_EXTRA;
     dim3 grid(pl.n_tiles, pl.m_tiles, pl.splits);
@@ -824,7 +824,7 @@ int launch_gemm_cell(const GemmProblem& p0, const CellEpilogue& cell, void* ws_,
     SUBGC_TRY(h3_set_smem_attr());
     hp.trace = next_trace_slot(6);
     hp.dbg = 0;
-    hp.pf_dist = 8;
+    hp.pf_dist = 0;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(n_tiles, m_tiles, splits);
     cfg.blockDim = dim3(H3_THREADS);
