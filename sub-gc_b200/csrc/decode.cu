@@ -71,13 +71,21 @@ __global__ void __launch_bounds__(256, 6) lstm_reduce_cell_kernel(const float* _
 // ---- fused attention: one block per decode row -------------------------------------------------------------------
 // atth = sum_z part[z][r] + b_h (h2att split-K partials reduced here); e_n = w . tanh(p_att[n] + atth) + b ;
 // alpha = softmax_n(e) ; alpha *= mask ; alpha /= sum(alpha) ; ctx = sum_n alpha_n att[n]
+// tanh for the attention scores: 18 K evaluations per row and step make libdevice's tanhf (~30 instructions) a third of the
+// attention kernel.  (1 - e) / (1 + e) with e = exp(-2|x|) from the ex2 unit: absolute error <= ~2e-7 (tanhf: ~6e-8), far below the
+// 2e-5 bar once weighted by alpha_net (|w| ~ 0.04) and summed.
+__device__ __forceinline__ float tanh_score(float x) {
+    const float e = __expf(-2.f * fabsf(x));
+    return copysignf(__fdividef(1.f - e, 1.f + e), x);
+}
+
 constexpr int kAttThreads = 1024;  // one block per row; the row is latency-bound (28 MB of att / p_att per step over 128 rows), so every
                                    // warp slot of the SM is used to keep loads in flight
 
 __device__ __forceinline__ void attention_tail(float* s_e, float* s_c, int r, int cr, const float* __restrict__ att, const float* __restrict__ masks,
                                                float* __restrict__ ctx, float* __restrict__ att_w, int att_w_stride, int len_max, int H,
                                                unsigned short* __restrict__ c16_hi, unsigned short* __restrict__ c16_lo, int Hp,
-                                               TraceSlot trace = TraceSlot{nullptr, 0}, int* overflow = nullptr);
+                                               TraceSlot trace = TraceSlot{nullptr, 0}, int* overflow = nullptr, const float* s_mask = nullptr);
 
 // body shared by attention_kernel and the fused att-phase kernel: expects s_h (atth of this row) and s_w (alpha_net weight)
 // filled and synchronised
@@ -122,7 +130,7 @@ __device__ __forceinline__ void attention_row_body(float* s_h, float* s_w, float
 __device__ __forceinline__ void attention_tail(float* s_e, float* s_c, int r, int cr, const float* __restrict__ att, const float* __restrict__ masks,
                                                float* __restrict__ ctx, float* __restrict__ att_w, int att_w_stride, int len_max, int H,
                                                unsigned short* __restrict__ c16_hi, unsigned short* __restrict__ c16_lo, int Hp, TraceSlot trace,
-                                               int* overflow) {
+                                               int* overflow, const float* s_mask) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (wid == 0) {  // len_max <= 64: one warp finishes the softmax / mask / renormalise (two-stage, as the reference)
         float m = -INFINITY;
@@ -134,7 +142,7 @@ __device__ __forceinline__ void attention_tail(float* s_e, float* s_c, int r, in
         float msum = 0.f;
         for (int n = lane; n < len_max; n += 32) {
             float wv = expf(s_e[n] - m) / sum;
-            wv = wv * __ldg(masks + (size_t)cr * len_max + n);
+            wv = wv * (s_mask ? s_mask[n] : __ldg(masks + (size_t)cr * len_max + n));
             s_e[n] = wv;
             msum += wv;
         }
@@ -220,6 +228,8 @@ __global__ void __maxnreg__(48) attention_kernel(const float* __restrict__ atth_
         }
     }
     for (int j = threadIdx.x; j < AH; j += blockDim.x) s_w[j] = __ldg(alpha_w + j);
+    __shared__ float s_mask[64];   // the row's mask does not depend on the step either
+    if (threadIdx.x < len_max) s_mask[threadIdx.x] = __ldg(masks + (size_t)cr * len_max + threadIdx.x);
     pdl_wait();
     trace_released(trace);
     if (active != nullptr && *active == 0) return;
@@ -244,10 +254,10 @@ __global__ void __maxnreg__(48) attention_kernel(const float* __restrict__ atth_
             if (item >= items) continue;
             const int j4 = (item % Q) * 32 + lane;
             const float4 v = pv[k], hh = h4[j4], ww = w4[j4];
-            float a = ww.x * tanhf(v.x + hh.x);
-            a = fmaf(ww.y, tanhf(v.y + hh.y), a);
-            a = fmaf(ww.z, tanhf(v.z + hh.z), a);
-            a = fmaf(ww.w, tanhf(v.w + hh.w), a);
+            float a = ww.x * tanh_score(v.x + hh.x);
+            a = fmaf(ww.y, tanh_score(v.y + hh.y), a);
+            a = fmaf(ww.z, tanh_score(v.z + hh.z), a);
+            a = fmaf(ww.w, tanh_score(v.w + hh.w), a);
             a = warp_sum(a);
             if (lane == 0) s_c[item] = a;   // score partial of (node, slice); combined below in slice order
         }
@@ -260,7 +270,7 @@ __global__ void __maxnreg__(48) attention_kernel(const float* __restrict__ atth_
     }
     __syncthreads();
     if (threadIdx.x == 0) trace_mark(trace, 1);   // scores done
-    attention_tail(s_e, s_c, r, cr, att, masks, ctx, att_w, att_w_stride, len_max, H, c16_hi, c16_lo, Hp, trace, overflow);
+    attention_tail(s_e, s_c, r, cr, att, masks, ctx, att_w, att_w_stride, len_max, H, c16_hi, c16_lo, Hp, trace, overflow, s_mask);
     trace_end(trace);
 }
 
