@@ -113,6 +113,12 @@ typedef struct subgc_weights {
     int32_t* h3_overflow;                              /* DEVICE flag (nullable): OR-ed with 1 when an activation fed to the
                                                           split-fp16 path did not fit fp16 (|x| > 65504, saturated): the
                                                           results of that call are invalid, re-run without packs          */
+    const float* lang_early_w;                         /* optional derived tensor [AH+4H, 2H] (fp32, contiguous):
+                                                          rows 0..AH   = [ core.attention.h2att.weight | 0 ],
+                                                          rows AH..    = [ core.lang_lstm.weight_ih[:, H:2H] | core.lang_lstm.weight_hh ].
+                                                          When set, a decode step contracts everything that depends only on
+                                                          (h_att(t), h_lang(t-1)) in ONE launch before the attention (h2att + two
+                                                          thirds of the language-LSTM gates) and only the ctx segment after it. */
 } subgc_weights;
 
 /* How sub-graph s of a flat list maps onto the loader tensors gpn_obj_ind / att_masks [rows,2,per_half,N].

@@ -31,7 +31,9 @@ __global__ void __launch_bounds__(256, 6) lstm_reduce_cell_kernel(const float* _
                                                                float* __restrict__ c_out, int S, int H, const int* __restrict__ active,
                                                                const float* __restrict__ addend, int add_div,
                                                                unsigned short* __restrict__ h16_hi, unsigned short* __restrict__ h16_lo, int Hp,
-                                                               TraceSlot trace) {
+                                                               TraceSlot trace, const float* __restrict__ part_b, int splits_b, int ld_b) {
+    // part_b (nullable): a second set of split-K partials [splits_b][S][ld_b] whose first 4H columns (from the given pointer) belong
+    // to the same gates (the merged h2att | lang-early contraction); added after `part`, in split order
     // h16_hi / h16_lo (nullable, [S, Hp]): the split-fp16 copy of h' the next contractions read as their activation operand
     // addend != nullptr: a pre-computed [S / add_div, 4H] term (the step-invariant fc segment with both biases folded in)
     // replaces b_ih + b_hh
@@ -50,6 +52,15 @@ __global__ void __launch_bounds__(256, 6) lstm_reduce_cell_kernel(const float* _
     for (int z = 0; z < splits; ++z) {  // one hidden unit per thread keeps ~128 K threads in flight; 8 independent loads each
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[q] += g[(size_t)z * zs + (size_t)q * H];
+    }
+    if (part_b) {
+        const float* gb = part_b + (size_t)r * ld_b + j;
+        const size_t zb = (size_t)S * ld_b;
+#pragma unroll 2
+        for (int z = 0; z < splits_b; ++z) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q] += gb[(size_t)z * zb + (size_t)q * H];
+        }
     }
     if (addend) {
         const float* a = addend + (size_t)(r / add_div) * 4 * H + j;
@@ -192,7 +203,8 @@ __global__ void __maxnreg__(48) attention_kernel(const float* __restrict__ atth_
                                                                 const float* __restrict__ alpha_b, float* __restrict__ ctx, float* __restrict__ att_w,
                                                                 int att_w_stride, int S, int len_max, int H, int AH, int rows_per_ctx,
                                                                 const int* __restrict__ active, unsigned short* __restrict__ c16_hi,
-                                                                unsigned short* __restrict__ c16_lo, int Hp, TraceSlot trace, int* overflow) {
+                                                                unsigned short* __restrict__ c16_lo, int Hp, TraceSlot trace, int* overflow,
+                                                                int ld_part) {
     trace_begin(trace);
     pdl_trigger();
     extern __shared__ float s_att[];  // [AH] atth | [AH] alpha_w | [64] e | [4][H] context partials (first 256 floats: score partials)
@@ -235,7 +247,7 @@ __global__ void __maxnreg__(48) attention_kernel(const float* __restrict__ atth_
     if (active != nullptr && *active == 0) return;
     for (int j = threadIdx.x; j < AH; j += blockDim.x) {
         float a = 0.f;
-        for (int z = 0; z < splits; ++z) a += atth_part[((size_t)z * S + r) * AH + j];
+        for (int z = 0; z < splits; ++z) a += atth_part[((size_t)z * S + r) * ld_part + j];
         s_h[j] = a + __ldg(h2att_b + j);
     }
     __syncthreads();
@@ -778,6 +790,8 @@ struct StepScratch {
     float* ctx;     // [S, H]
     void* gemm_ws;
     size_t gemm_ws_bytes;
+    void* gemm_ws2;        // second contraction workspace: the merged [h2att | lang-early] partials live across the attention
+    size_t gemm_ws2_bytes;
 };
 
 static size_t step_gemm_ws_bytes(const subgc_dims* d, int S) {
@@ -791,9 +805,11 @@ static size_t step_gemm_ws_bytes(const subgc_dims* d, int S) {
     return align_up(g, 256);
 }
 
+static size_t step_gemm_ws2_bytes(const subgc_dims* d, int S) { return align_up(gemm_workspace_bytes(S, d->att_hid + 4 * d->rnn, 2 * d->rnn), 256); }
+
 static size_t step_scratch_bytes(const subgc_dims* d, int S) {
     return align_up((size_t)S * 4 * d->rnn * 4, 256) + align_up((size_t)S * d->att_hid * 4, 256) + align_up((size_t)S * d->rnn * 4, 256) +
-           step_gemm_ws_bytes(d, S) + 256;
+           step_gemm_ws_bytes(d, S) + step_gemm_ws2_bytes(d, S) + 512;
 }
 
 static bool take_step_scratch(const subgc_dims* d, int S, Workspace& ws, StepScratch& sc) {
@@ -802,6 +818,8 @@ static bool take_step_scratch(const subgc_dims* d, int S, Workspace& ws, StepScr
     sc.ctx = ws.take<float>((size_t)S * d->rnn);
     sc.gemm_ws_bytes = step_gemm_ws_bytes(d, S);
     sc.gemm_ws = ws.take<char>(sc.gemm_ws_bytes);
+    sc.gemm_ws2_bytes = step_gemm_ws2_bytes(d, S);
+    sc.gemm_ws2 = ws.take<char>(sc.gemm_ws2_bytes);
     return ws.ok();
 }
 
@@ -916,9 +934,14 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
         SUBGC_TRY(launch_gemm_cell(p, ce, sc.gemm_ws, sc.gemm_ws_bytes, st, &cell_fused));
         if (!cell_fused) SUBGC_TRY(launch_gemm_raw(p, sc.gemm_ws, sc.gemm_ws_bytes, st, &rp));
     }
+    // opt-in (SUBGC_MERGED=1): parity-green, but measured 0.04 ms slower per loop -- half of the merged contraction's activation tiles
+    // (h_att) were written by the kernel right before it, and reads of just-written lines take ~2.5 us instead of ~1.2 us to land
+    static const bool merge_off = !(getenv("SUBGC_MERGED") != nullptr && getenv("SUBGC_MERGED")[0] == '1');
+    bool merged = w->lang_early_w != nullptr && !merge_off && upto == 0;   // [h2att | lang-early] as one contraction before the attention
+    RawPartials rp_early{nullptr, 0};
     size_t smem = (size_t)(2 * AH + 64 + 4 * H) * sizeof(float);
     const size_t smem_fused = (size_t)(2 * AH + 64 + kAttCluster * H) * sizeof(float);
-    if (!cell_fused && att_phase_fusable(smem_fused)) {
+    if (!cell_fused && !merged && att_phase_fusable(smem_fused)) {
         // cell + h2att + attention as one kernel (one block per row, clusters of 8 rows, two cluster barriers)
         AttPhaseArgs fa;
         fa.part = rp.part; fa.splits = rp.splits; fa.b_ih = w->att_b_ih; fa.b_hh = w->att_b_hh; fa.fc_pre = fc_pre; fa.c_prev = c_in;
@@ -947,25 +970,40 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
     } else {
         if (!(skip & 2) && !cell_fused) launch_pdl(lstm_reduce_cell_kernel, dim3(pw_blocks), dim3(256), (size_t)0, st, rp.part, rp.splits, w->att_b_ih, w->att_b_hh, c_in, parent, h_out, c_out, S,
                                                                             H, active, fc_pre, rows_per_ctx, use16 ? h16->hout_hi : nullptr,
-                                                                            use16 ? h16->hout_lo : nullptr, use16 ? h16->Hp : 0, next_trace_slot(2));
+                                                                            use16 ? h16->hout_lo : nullptr, use16 ? h16->Hp : 0, next_trace_slot(2), (const float*)nullptr, 0, 0);
         SUBGC_LAUNCH_CHECK();
         // attention (AttModel.py:445-471); the h2att partials are reduced inside the attention kernel
         p = GemmProblem(); p.wts = w;
+        if (merged) {
+            // everything that depends only on (h_att(t), h_lang(t-1)): h2att and two thirds of the language-LSTM gates, one launch
+            p.M = S; p.N = AH + 4 * H; p.nseg = 2;
+            p.seg[0] = make_seg(h_out, H, w->lang_early_w, 2 * H, H);
+            p.seg[1] = make_seg(h_in + SH, H, w->lang_early_w + H, 2 * H, H);
+            p.seg[1].gather = parent;
+            if (use16) {
+                set_a16(p.seg[0], h16->hout_hi, h16->hout_lo, h16->Hp);
+                set_a16(p.seg[1], h16->hin_hi + SHp, h16->hin_lo + SHp, h16->Hp);
+            }
+            p.active = active;
+            if (!(skip & 4)) SUBGC_TRY(launch_gemm_raw(p, sc.gemm_ws2, sc.gemm_ws2_bytes, st, &rp_early));
+            rp = rp_early;
+        } else {
         p.M = S; p.N = AH; p.nseg = 1;
         p.seg[0] = make_seg(h_out, H, w->h2att.w, H, H);
         if (use16) set_a16(p.seg[0], h16->hout_hi, h16->hout_lo, h16->Hp);
         p.active = active;
         if (!(skip & 4)) SUBGC_TRY(launch_gemm_raw(p, sc.gemm_ws, sc.gemm_ws_bytes, st, &rp));
+        }
         if (!(skip & 8)) launch_pdl(attention_kernel, dim3(S), dim3(kAttThreads), smem, st, rp.part, rp.splits, w->h2att.b, p_att, att, masks, w->alpha_net.w, w->alpha_net.b,
                                                                         sc.ctx, att_w, att_w_stride, S, len_max, H, AH, rows_per_ctx, active,
                                                                         use16 ? h16->ctx_hi : nullptr, use16 ? h16->ctx_lo : nullptr, use16 ? h16->Hp : 0, next_trace_slot(3),
-                                                                        (int*)(use16 ? w->h3_overflow : nullptr));
+                                                                        (int*)(use16 ? w->h3_overflow : nullptr), merged ? AH + 4 * H : AH);
         SUBGC_LAUNCH_CHECK();
     }
     if (upto == 1) return SUBGC_OK;
     // language LSTM on [ctx | h_att] (AttModel.py:421-423)
     p = GemmProblem(); p.wts = w;
-    p.M = S; p.N = 4 * H; p.nseg = 3;
+    p.M = S; p.N = 4 * H; p.nseg = merged ? 1 : 3;
     p.seg[0] = make_seg(sc.ctx, H, w->lang_w_ih, 2 * H, H);
     p.seg[1] = make_seg(h_out, H, w->lang_w_ih + H, 2 * H, H);
     p.seg[2] = make_seg(h_in + SH, H, w->lang_w_hh, H, H);
@@ -977,7 +1015,9 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
     }
     p.active = active;
     cell_fused = false;
-    if (!(skip & 16)) {
+    if (merged) {   // only the ctx segment is left; the cell adds the lang-early partials of the merged contraction
+        if (!(skip & 16)) SUBGC_TRY(launch_gemm_raw(p, sc.gemm_ws, sc.gemm_ws_bytes, st, &rp));
+    } else if (!(skip & 16)) {
         CellEpilogue ce;
         ce.H = H; ce.c_prev = c_in + SH; ce.parent = parent; ce.b_ih = w->lang_b_ih; ce.b_hh = w->lang_b_hh;
         ce.h_out = h_out + SH; ce.c_out = c_out + SH;
@@ -987,7 +1027,9 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
     }
     if (!(skip & 32) && !cell_fused) launch_pdl(lstm_reduce_cell_kernel, dim3(pw_blocks), dim3(256), (size_t)0, st, rp.part, rp.splits, w->lang_b_ih, w->lang_b_hh, c_in + SH, parent, h_out + SH,
                                                                          c_out + SH, S, H, active, nullptr, 1, use16 ? h16->hout_hi + SHp : nullptr,
-                                                                         use16 ? h16->hout_lo + SHp : nullptr, use16 ? h16->Hp : 0, next_trace_slot(2));
+                                                                         use16 ? h16->hout_lo + SHp : nullptr, use16 ? h16->Hp : 0, next_trace_slot(2),
+                                                                         merged ? rp_early.part + AH : (const float*)nullptr, merged ? rp_early.splits : 0,
+                                                                         merged ? AH + 4 * H : 0);
     SUBGC_LAUNCH_CHECK();
     // logit (AttModel.py:336,340); eval mode: dropout is the identity
     p = GemmProblem(); p.wts = w;

@@ -675,6 +675,10 @@ static H3Plan h3_plan(int M, int N, const int* segK, int nseg) {
         const double mma = 12.0 * bn / 2.0;
         double per_kb = hbm > smem ? hbm : smem;
         if (mma > per_kb) per_kb = mma;
+        // a ring stage turns around in (TMA latency + its MMAs + barrier hand-offs); with few stages this, not bandwidth, bounds the loop
+        // (measured: 3 stages of 64 KB -> ~0.75 us per k-block whatever is switched off)
+        const double turn = (2300.0 + mma + 600.0) / pl.stages;
+        if (turn > per_kb) per_kb = turn;
         const double epi = (pl.splits > 1 ? 2.0 : 1.0) * bn * 128.0 * 4.0 / 64.0;   // partial tile out (and read back by the consumer)
         const double cost = waves * (pl.kb_per_split * per_kb + epi + 4000.0);
         if (cost < best_cost) { best_cost = cost; best = pl; }

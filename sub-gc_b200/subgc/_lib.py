@@ -43,7 +43,7 @@ class Weights(C.Structure):
         ("h2att", Linear), ("alpha_net", Linear),
         ("att_w_ih", c_fp), ("att_w_hh", c_fp), ("att_b_ih", c_fp), ("att_b_hh", c_fp),
         ("lang_w_ih", c_fp), ("lang_w_hh", c_fp), ("lang_b_ih", c_fp), ("lang_b_hh", c_fp),
-        ("packs", C.POINTER(Packed)), ("n_packs", C.c_int32), ("h3_overflow", c_fp),
+        ("packs", C.POINTER(Packed)), ("n_packs", C.c_int32), ("h3_overflow", c_fp), ("lang_early_w", c_fp),
     ]
 
 

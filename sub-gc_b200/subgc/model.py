@@ -258,6 +258,7 @@ class TopDownModel(nn.Module):
             if w.n_packs:
                 w.packs, w.n_packs = None, 0
                 w.h3_overflow = None
+                w.lang_early_w = None
                 self._plans.clear()
             return
         dev = next(iter(params.values())).device
@@ -268,7 +269,20 @@ class TopDownModel(nn.Module):
         w.h3_overflow = self._ovf_dev.data_ptr()
         named = {n: p for n, p in params.items() if p.dim() == 2 and p.shape[0] >= 64 and n not in self._PACK_SKIP}
         H = self.rnn_size   # K segments of the un-concatenated LSTM inputs: [h_lang | fc | x_t] and [ctx | h_att]
-        arr, cnt = self._packs.build(named, {"core.att_lstm.weight_ih": [H, 2 * H], "core.lang_lstm.weight_ih": [H]})
+        # derived tensor of the merged pre-attention contraction (include/subgc_b200.h: subgc_weights.lang_early_w):
+        # [[h2att.weight, 0], [lang weight_ih[:, H:2H], lang weight_hh]], rebuilt when one of its sources changed
+        src = (params["core.attention.h2att.weight"], params["core.lang_lstm.weight_ih"], params["core.lang_lstm.weight_hh"])
+        ekey = tuple((t.data_ptr(), t._version) for t in src)
+        if getattr(self, "_early_key", None) != ekey:
+            with torch.no_grad():
+                top = torch.cat([src[0], src[0].new_zeros(src[0].shape[0], H)], 1)
+                bot = torch.cat([src[1][:, H:2 * H], src[2]], 1)
+                self._early = torch.cat([top, bot], 0).contiguous()
+            self._early_key = ekey
+            self._plans.clear()
+        named["__lang_early"] = self._early
+        w.lang_early_w = self._early.data_ptr()
+        arr, cnt = self._packs.build(named, {"core.att_lstm.weight_ih": [H, 2 * H], "core.lang_lstm.weight_ih": [H], "__lang_early": [H]})
         if self._pack_key != self._packs.array_key or not w.n_packs:
             w.packs, w.n_packs = arr, cnt
             self._pack_key = self._packs.array_key

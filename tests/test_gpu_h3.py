@@ -153,8 +153,11 @@ def test_fp16_range_guard_trips_and_falls_back():
     assert torch.equal(res[0].cpu(), ref["seq"])
 
 
-def test_fused_cell_epilogue_variant_matches():
-    """SUBGC_FUSED_CELL=1 (gates -> cell inside the contraction, cluster split-K reduction over DSMEM) is an opt-in variant: same tokens."""
+@pytest.mark.parametrize("variant", ["SUBGC_FUSED_CELL", "SUBGC_MERGED", "SUBGC_FUSED_ATT", "SUBGC_NO_PDL"])
+def test_opt_in_variants_match(variant):
+    """Measured-but-not-default variants stay parity-green: SUBGC_FUSED_CELL=1 (gates -> cell inside the contraction, cluster split-K
+    reduction over DSMEM), SUBGC_MERGED=1 (h2att + lang-early as one contraction), SUBGC_FUSED_ATT=1 (cell + h2att + attention as one
+    cluster kernel), SUBGC_NO_PDL=1 (plain stream order)."""
     code = r'''
 import sys, os, torch
 sys.path.insert(0, os.path.join(%r, "sub-gc_b200")); sys.path.insert(0, os.path.join(%r, "oracle"))
@@ -175,6 +178,6 @@ err = float((res[1].cpu() - ref["seqLogprobs"]).abs().max())
 assert err <= 2e-5 * max(1.0, float(ref["seqLogprobs"].abs().max())), err
 print("OK", err)
 ''' % (ROOT, ROOT)
-    env = dict(os.environ, SUBGC_FUSED_CELL="1")
+    env = dict(os.environ, **{variant: "1"})
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

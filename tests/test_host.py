@@ -43,7 +43,7 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(_lib.Dims) == 17 * 4
     assert ctypes.sizeof(_lib.Linear) == 16
     n_linear = 3 + 2 * 4 * _lib.MAX_GCN_LAYERS + 5 + 6
-    assert ctypes.sizeof(_lib.Weights) == 16 * n_linear + 8 * (3 + 8) + 24   # + packs pointer, n_packs (padded), overflow flag pointer
+    assert ctypes.sizeof(_lib.Weights) == 16 * n_linear + 8 * (3 + 8) + 32   # + packs pointer, n_packs (padded), overflow flag pointer, lang_early_w
     assert ctypes.sizeof(_lib.Packed) == 3 * 8 + 8 * 4
     assert ctypes.sizeof(_lib.Layout) == 16
 
