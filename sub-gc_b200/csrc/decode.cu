@@ -1112,7 +1112,86 @@ struct BeamArgs {
     long long* parent;                  // [n_sub*b] state row each new beam continues
     long long* done_seq; float* done_logps; double* done_p; double* done_unaug_p; int* done_count;  // outputs
     int* done_total;                    // [n_sub] appended so far
+    const float* ys_in; const int* ix_in;  // nullable [n_sub*b, kMaxBeam]: per-row top-b (value, token) from beam_topb_kernel
 };
+
+// Per-row top-b of the UNK-suppressed log-probs, one 1024-thread block per decode row with the logit row in registers (V1 <= 10 x 1024):
+// split-K reduce of the logit partials + bias, log-softmax statistics, b rounds of arg-max with exclusion (descending value, lower index
+// first on ties: the order torch.sort gives the reference, CaptionModel.py:131-135).  beam_step_kernel then only merges b x b candidates.
+struct BeamTopArgs {
+    const float* logits; int splits; const float* bias;   // partials [splits][S][V1] (+ bias) or materialised logits (splits == 0)
+    int V1, S, T, t, b, decoding_constraint;
+    const int* seq_prev;     // [n_sub, b, T]
+    float* ys; int* ix;      // [S, kMaxBeam]
+};
+__global__ void __maxnreg__(48) beam_topb_kernel(const BeamTopArgs a) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float redv[32];
+    __shared__ int redi[32];
+    const int r = blockIdx.x, tid = threadIdx.x, q = r % a.b;
+    if (a.t == 0 && q != 0) return;   // the <bos> step expands one row per sub-graph
+    float v[kSelVals];
+#pragma unroll
+    for (int i = 0; i < kSelVals; ++i) v[i] = 0.f;
+    if (a.splits > 0) {
+        const size_t zs = (size_t)a.S * a.V1;
+        const float* p0 = a.logits + (size_t)r * a.V1;
+        for (int z = 0; z < a.splits; ++z) {
+#pragma unroll
+            for (int i = 0; i < kSelVals; ++i) {
+                const int j = tid + i * kSelectThreads;
+                if (j < a.V1) v[i] += p0[(size_t)z * zs + j];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kSelVals; ++i) {
+            const int j = tid + i * kSelectThreads;
+            if (j < a.V1) v[i] += __ldg(a.bias + j);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < kSelVals; ++i) {
+            const int j = tid + i * kSelectThreads;
+            if (j < a.V1) v[i] = a.logits[(size_t)r * a.V1 + j];
+        }
+    }
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < kSelVals; ++i)
+        if (tid + i * kSelectThreads < a.V1) m = fmaxf(m, v[i]);
+    m = block_max(m, redv);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kSelVals; ++i)
+        if (tid + i * kSelectThreads < a.V1) s += expf(v[i] - m);
+    s = block_sum(s, redv);
+    const float lz = logf(s);
+    const int banned = (a.decoding_constraint && a.t > 0) ? a.seq_prev[(size_t)r * a.T + a.t - 1] : -1;
+#pragma unroll
+    for (int i = 0; i < kSelVals; ++i) {
+        const int j = tid + i * kSelectThreads;
+        float lp = (v[i] - m) - lz;
+        if (j == banned) lp = -INFINITY;
+        if (j == a.V1 - 1) lp = lp - 1000.f;  // UNK suppression (CaptionModel.py:131)
+        v[i] = lp;
+    }
+    unsigned taken = 0;
+    for (int c = 0; c < a.b; ++c) {
+        float cv = -INFINITY;
+        int ci = 0x7fffffff;
+#pragma unroll
+        for (int i = 0; i < kSelVals; ++i) {
+            const int j = tid + i * kSelectThreads;
+            if (j >= a.V1 || ((taken >> i) & 1u)) continue;
+            if (v[i] > cv || ci == 0x7fffffff) { cv = v[i]; ci = j; }
+        }
+        block_argmax(cv, ci, redv, redi);
+        if ((ci % kSelectThreads) == tid && ci != 0x7fffffff) taken |= 1u << (ci / kSelectThreads);
+        if (tid == 0) { a.ys[(size_t)r * kMaxBeam + c] = cv; a.ix[(size_t)r * kMaxBeam + c] = ci; }
+        __syncthreads();
+    }
+}
 
 __global__ void __launch_bounds__(256) beam_step_kernel(const BeamArgs a) {
     __shared__ float redv[32];
@@ -1129,7 +1208,15 @@ __global__ void __launch_bounds__(256) beam_step_kernel(const BeamArgs a) {
     int* seq_next = a.seq_next + (size_t)sg * b * T;
     const float* lp_prev = a.lp_prev + (size_t)sg * b * T;
     float* lp_next = a.lp_next + (size_t)sg * b * T;
-    for (int q = 0; q < rows; ++q) {
+    if (a.ix_in != nullptr) {   // per-row top-b already computed (beam_topb_kernel)
+        if (threadIdx.x < rows * b) {
+            const int q = threadIdx.x / b, c = threadIdx.x % b;
+            s_ys[q][c] = a.ys_in[((size_t)sg * b + q) * kMaxBeam + c];
+            s_ix[q][c] = a.ix_in[((size_t)sg * b + q) * kMaxBeam + c];
+        }
+        __syncthreads();
+    }
+    for (int q = 0; q < (a.ix_in != nullptr ? 0 : rows); ++q) {
         const float* x = a.logits + ((size_t)sg * b + q) * V1;
         float m = -INFINITY;
         for (int j = threadIdx.x; j < V1; j += blockDim.x) m = fmaxf(m, x[j]);
@@ -1404,6 +1491,7 @@ extern "C" size_t subgc_beam_workspace_bytes(const subgc_dims* d, int n_sub, int
     b += 2 * align_up(S * 8, 256);                          // it, parent
     b += 4 * align_up(S * T * 4, 256);                      // histories
     b += align_up(S * 4, 256) + align_up((size_t)n_sub * 4, 256);
+    b += 2 * align_up(S * kMaxBeam * 4, 256);                // per-row top-b candidates
     return b + 1024;
 }
 
@@ -1432,7 +1520,11 @@ extern "C" int subgc_decode_beam(const subgc_dims* d, const subgc_weights* w, in
     float* lpb[2] = {ws.take<float>((size_t)S * T), ws.take<float>((size_t)S * T)};
     float* sum = ws.take<float>(S);
     int* done_total = ws.take<int>(n_sub);
+    float* top_ys = ws.take<float>((size_t)S * kMaxBeam);
+    int* top_ix = ws.take<int>((size_t)S * kMaxBeam);
     if (!ok || !ws.ok()) { set_error("subgc_decode_beam: workspace too small"); return SUBGC_E_WORKSPACE; }
+    const bool fast_top = V1 <= kSelVals * kSelectThreads;   // logit row fits the register-resident top-b kernel
+    RawPartials rl{nullptr, 0};
     SUBGC_CUDA(cudaMemsetAsync(hbuf[0], 0, 2 * (size_t)S * H * 4, st));
     SUBGC_CUDA(cudaMemsetAsync(cbuf[0], 0, 2 * (size_t)S * H * 4, st));
     SUBGC_CUDA(cudaMemsetAsync(it, 0, (size_t)S * 8, st));
@@ -1447,10 +1539,19 @@ extern "C" int subgc_decode_beam(const subgc_dims* d, const subgc_weights* w, in
     SUBGC_CUDA(cudaMemsetAsync(done_unaug_p, 0, (size_t)S * 8, st));
     // <bos> step on b identical rows per sub-graph (AttModel.py:216-227)
     SUBGC_TRY(launch_fc_pre(d, w, n_sub, fc, sc, st));
-    SUBGC_TRY(launch_step(d, w, S, len_max, b, it, nullptr, nullptr, fc, att, p_att, masks, hbuf[0], cbuf[0], hbuf[1], cbuf[1], logits, nullptr, nullptr,
-                          0, sc, nullptr, 0, st, sc.gates));
+    SUBGC_TRY(launch_step(d, w, S, len_max, b, it, nullptr, nullptr, fc, att, p_att, masks, hbuf[0], cbuf[0], hbuf[1], cbuf[1], logits,
+                          fast_top ? &rl : nullptr, nullptr, 0, sc, nullptr, 0, st, sc.gates));
     for (int t = 0; t < T; ++t) {
         BeamArgs a;
+        a.ys_in = nullptr; a.ix_in = nullptr;
+        if (fast_top) {
+            BeamTopArgs ta;
+            ta.logits = rl.part; ta.splits = rl.splits; ta.bias = w->logit.b; ta.V1 = V1; ta.S = S; ta.T = T; ta.t = t; ta.b = b;
+            ta.decoding_constraint = decoding_constraint; ta.seq_prev = seqb[t & 1]; ta.ys = top_ys; ta.ix = top_ix;
+            launch_pdl(beam_topb_kernel, dim3(S), dim3(kSelectThreads), (size_t)0, st, ta);
+            SUBGC_LAUNCH_CHECK();
+            a.ys_in = top_ys; a.ix_in = top_ix;
+        }
         a.logits = logits; a.V1 = V1; a.T = T; a.t = t; a.b = b; a.length_penalty = length_penalty; a.lp_alpha = lp_alpha;
         a.decoding_constraint = decoding_constraint;
         a.seq_prev = seqb[t & 1]; a.seq_next = seqb[(t & 1) ^ 1]; a.lp_prev = lpb[t & 1]; a.lp_next = lpb[(t & 1) ^ 1];
@@ -1461,8 +1562,8 @@ extern "C" int subgc_decode_beam(const subgc_dims* d, const subgc_weights* w, in
         SUBGC_LAUNCH_CHECK();
         if (t == T - 1) break;  // the reference's final get_logprobs_state result is never read (CaptionModel.py:170-171)
         const int in = (t + 1) & 1, out = in ^ 1;
-        SUBGC_TRY(launch_step(d, w, S, len_max, b, it, nullptr, parent, fc, att, p_att, masks, hbuf[in], cbuf[in], hbuf[out], cbuf[out], logits, nullptr,
-                              nullptr, 0, sc, nullptr, 0, st, sc.gates));
+        SUBGC_TRY(launch_step(d, w, S, len_max, b, it, nullptr, parent, fc, att, p_att, masks, hbuf[in], cbuf[in], hbuf[out], cbuf[out], logits,
+                              fast_top ? &rl : nullptr, nullptr, 0, sc, nullptr, 0, st, sc.gates));
     }
     return SUBGC_OK;
 }

@@ -44,6 +44,12 @@ t0 = t[ok, 0].min()
 idx = np.nonzero(ok)[0]
 sel = [i for i in idx if k[i] == 4]
 print(f"{ok.sum()} traced launches, loop span {(t[ok,1].max()-t0)/1e3:.1f} us, {len(sel)} select launches")
+if mode == "beam":
+    # no selection kernel in the beam loop: print 16 consecutive launches from the middle of the loop
+    mid = idx[len(idx) // 2: len(idx) // 2 + 16]
+    z = t[mid[0], 0]
+    for i in mid:
+        print(f"  {names.get(int(k[i]), str(k[i])):12s} start {(t[i,0]-z)/1e3:8.2f} released {(t[i,2]-z)/1e3:8.2f} end {(t[i,1]-z)/1e3:8.2f}  dur {(t[i,1]-t[i,0])/1e3:7.2f}")
 if len(sel) >= 12:
     a, b = sel[9] + 1, sel[10] + 1
     prev_end = t[sel[9], 1]
