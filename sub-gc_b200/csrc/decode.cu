@@ -900,10 +900,13 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
     // attention LSTM: gates = W_ih [h_lang | fc | relu(E[it])] + b_ih + W_hh h_att + b_hh   (AttModel.py:410-413)
     p.M = S; p.N = 4 * H;
     int ns = 0;
-    const bool use16 = h16 != nullptr && parent == nullptr && h16->hin_hi != nullptr;
-    const size_t SHp = use16 ? (size_t)S * h16->Hp : 0;
+    // split-fp16 copies: what this step produces (h_att, ctx, h_lang) is always written / read as such; the previous state only when
+    // rows are not re-mapped (beam search gathers them by `parent`, which goes through split_rows_kernel)
+    const bool out16 = h16 != nullptr && h16->hout_hi != nullptr;
+    const bool in16 = out16 && parent == nullptr && h16->hin_hi != nullptr;
+    const size_t SHp = out16 ? (size_t)S * h16->Hp : 0;
     p.seg[ns] = make_seg(h_in + SH, H, w->att_w_ih, X + 2 * H, H);
-    if (use16) set_a16(p.seg[ns], h16->hin_hi + SHp, h16->hin_lo + SHp, h16->Hp);
+    if (in16) set_a16(p.seg[ns], h16->hin_hi + SHp, h16->hin_lo + SHp, h16->Hp);
     p.seg[ns++].gather = parent;
     if (!fc_pre) {
         p.seg[ns] = make_seg(fc, H, w->att_w_ih + H, X + 2 * H, H);
@@ -911,7 +914,7 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
     }
     if (xt) {  // relu(E[it]) already materialised by the previous step's selection kernel
         p.seg[ns] = make_seg(xt, X, w->att_w_ih + 2 * H, X + 2 * H, X);
-        if (use16 && h16->xt_hi) set_a16(p.seg[ns], h16->xt_hi, h16->xt_lo, h16->Xp);
+        if (in16 && h16->xt_hi) set_a16(p.seg[ns], h16->xt_hi, h16->xt_lo, h16->Xp);
         ++ns;
     } else {
         p.seg[ns] = make_seg(w->embed, X, w->att_w_ih + 2 * H, X + 2 * H, X);
@@ -919,7 +922,7 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
         p.seg[ns++].relu_a = 1;
     }
     p.seg[ns] = make_seg(h_in, H, w->att_w_hh, H, H);
-    if (use16) set_a16(p.seg[ns], h16->hin_hi, h16->hin_lo, h16->Hp);
+    if (in16) set_a16(p.seg[ns], h16->hin_hi, h16->hin_lo, h16->Hp);
     p.seg[ns++].gather = parent;
     p.nseg = ns;
     p.active = active;
@@ -930,7 +933,7 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
         CellEpilogue ce;
         ce.H = H; ce.c_prev = c_in; ce.parent = parent; ce.addend = fc_pre; ce.add_div = rows_per_ctx; ce.b_ih = w->att_b_ih; ce.b_hh = w->att_b_hh;
         ce.h_out = h_out; ce.c_out = c_out;
-        if (use16) { ce.h16_hi = h16->hout_hi; ce.h16_lo = h16->hout_lo; ce.Hp = h16->Hp; }
+        if (out16) { ce.h16_hi = h16->hout_hi; ce.h16_lo = h16->hout_lo; ce.Hp = h16->Hp; }
         SUBGC_TRY(launch_gemm_cell(p, ce, sc.gemm_ws, sc.gemm_ws_bytes, st, &cell_fused));
         if (!cell_fused) SUBGC_TRY(launch_gemm_raw(p, sc.gemm_ws, sc.gemm_ws_bytes, st, &rp));
     }
@@ -949,8 +952,8 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
         fa.masks = masks; fa.alpha_w = w->alpha_net.w; fa.alpha_b = w->alpha_net.b; fa.ctx = sc.ctx; fa.att_w = att_w;
         fa.att_w_stride = att_w_stride; fa.S = S; fa.len_max = len_max; fa.H = H; fa.AH = AH;
         fa.cols_per_block = (AH + kAttCluster - 1) / kAttCluster; fa.rows_per_ctx = rows_per_ctx; fa.active = active;
-        fa.h16_hi = use16 ? h16->hout_hi : nullptr; fa.h16_lo = use16 ? h16->hout_lo : nullptr;
-        fa.c16_hi = use16 ? h16->ctx_hi : nullptr; fa.c16_lo = use16 ? h16->ctx_lo : nullptr; fa.Hp = use16 ? h16->Hp : 0;
+        fa.h16_hi = out16 ? h16->hout_hi : nullptr; fa.h16_lo = out16 ? h16->hout_lo : nullptr;
+        fa.c16_hi = out16 ? h16->ctx_hi : nullptr; fa.c16_lo = out16 ? h16->ctx_lo : nullptr; fa.Hp = out16 ? h16->Hp : 0;
         fa.trace = att_trace_buffer();
         if (!(skip & 2)) {
             cudaLaunchConfig_t cfg = {};
@@ -969,8 +972,8 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
         }
     } else {
         if (!(skip & 2) && !cell_fused) launch_pdl(lstm_reduce_cell_kernel, dim3(pw_blocks), dim3(256), (size_t)0, st, rp.part, rp.splits, w->att_b_ih, w->att_b_hh, c_in, parent, h_out, c_out, S,
-                                                                            H, active, fc_pre, rows_per_ctx, use16 ? h16->hout_hi : nullptr,
-                                                                            use16 ? h16->hout_lo : nullptr, use16 ? h16->Hp : 0, next_trace_slot(2), (const float*)nullptr, 0, 0);
+                                                                            H, active, fc_pre, rows_per_ctx, out16 ? h16->hout_hi : nullptr,
+                                                                            out16 ? h16->hout_lo : nullptr, out16 ? h16->Hp : 0, next_trace_slot(2), (const float*)nullptr, 0, 0);
         SUBGC_LAUNCH_CHECK();
         // attention (AttModel.py:445-471); the h2att partials are reduced inside the attention kernel
         p = GemmProblem(); p.wts = w;
@@ -980,24 +983,22 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
             p.seg[0] = make_seg(h_out, H, w->lang_early_w, 2 * H, H);
             p.seg[1] = make_seg(h_in + SH, H, w->lang_early_w + H, 2 * H, H);
             p.seg[1].gather = parent;
-            if (use16) {
-                set_a16(p.seg[0], h16->hout_hi, h16->hout_lo, h16->Hp);
-                set_a16(p.seg[1], h16->hin_hi + SHp, h16->hin_lo + SHp, h16->Hp);
-            }
+            if (out16) set_a16(p.seg[0], h16->hout_hi, h16->hout_lo, h16->Hp);
+            if (in16) set_a16(p.seg[1], h16->hin_hi + SHp, h16->hin_lo + SHp, h16->Hp);
             p.active = active;
             if (!(skip & 4)) SUBGC_TRY(launch_gemm_raw(p, sc.gemm_ws2, sc.gemm_ws2_bytes, st, &rp_early));
             rp = rp_early;
         } else {
         p.M = S; p.N = AH; p.nseg = 1;
         p.seg[0] = make_seg(h_out, H, w->h2att.w, H, H);
-        if (use16) set_a16(p.seg[0], h16->hout_hi, h16->hout_lo, h16->Hp);
+        if (out16) set_a16(p.seg[0], h16->hout_hi, h16->hout_lo, h16->Hp);
         p.active = active;
         if (!(skip & 4)) SUBGC_TRY(launch_gemm_raw(p, sc.gemm_ws, sc.gemm_ws_bytes, st, &rp));
         }
         if (!(skip & 8)) launch_pdl(attention_kernel, dim3(S), dim3(kAttThreads), smem, st, rp.part, rp.splits, w->h2att.b, p_att, att, masks, w->alpha_net.w, w->alpha_net.b,
                                                                         sc.ctx, att_w, att_w_stride, S, len_max, H, AH, rows_per_ctx, active,
-                                                                        use16 ? h16->ctx_hi : nullptr, use16 ? h16->ctx_lo : nullptr, use16 ? h16->Hp : 0, next_trace_slot(3),
-                                                                        (int*)(use16 ? w->h3_overflow : nullptr), merged ? AH + 4 * H : AH);
+                                                                        out16 ? h16->ctx_hi : nullptr, out16 ? h16->ctx_lo : nullptr, out16 ? h16->Hp : 0, next_trace_slot(3),
+                                                                        (int*)(out16 ? w->h3_overflow : nullptr), merged ? AH + 4 * H : AH);
         SUBGC_LAUNCH_CHECK();
     }
     if (upto == 1) return SUBGC_OK;
@@ -1008,11 +1009,11 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
     p.seg[1] = make_seg(h_out, H, w->lang_w_ih + H, 2 * H, H);
     p.seg[2] = make_seg(h_in + SH, H, w->lang_w_hh, H, H);
     p.seg[2].gather = parent;
-    if (use16) {
+    if (out16) {
         set_a16(p.seg[0], h16->ctx_hi, h16->ctx_lo, h16->Hp);
         set_a16(p.seg[1], h16->hout_hi, h16->hout_lo, h16->Hp);
-        set_a16(p.seg[2], h16->hin_hi + SHp, h16->hin_lo + SHp, h16->Hp);
     }
+    if (in16) set_a16(p.seg[2], h16->hin_hi + SHp, h16->hin_lo + SHp, h16->Hp);
     p.active = active;
     cell_fused = false;
     if (merged) {   // only the ctx segment is left; the cell adds the lang-early partials of the merged contraction
@@ -1021,13 +1022,13 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
         CellEpilogue ce;
         ce.H = H; ce.c_prev = c_in + SH; ce.parent = parent; ce.b_ih = w->lang_b_ih; ce.b_hh = w->lang_b_hh;
         ce.h_out = h_out + SH; ce.c_out = c_out + SH;
-        if (use16) { ce.h16_hi = h16->hout_hi + SHp; ce.h16_lo = h16->hout_lo + SHp; ce.Hp = h16->Hp; }
+        if (out16) { ce.h16_hi = h16->hout_hi + SHp; ce.h16_lo = h16->hout_lo + SHp; ce.Hp = h16->Hp; }
         SUBGC_TRY(launch_gemm_cell(p, ce, sc.gemm_ws, sc.gemm_ws_bytes, st, &cell_fused));
         if (!cell_fused) SUBGC_TRY(launch_gemm_raw(p, sc.gemm_ws, sc.gemm_ws_bytes, st, &rp));
     }
     if (!(skip & 32) && !cell_fused) launch_pdl(lstm_reduce_cell_kernel, dim3(pw_blocks), dim3(256), (size_t)0, st, rp.part, rp.splits, w->lang_b_ih, w->lang_b_hh, c_in + SH, parent, h_out + SH,
-                                                                         c_out + SH, S, H, active, nullptr, 1, use16 ? h16->hout_hi + SHp : nullptr,
-                                                                         use16 ? h16->hout_lo + SHp : nullptr, use16 ? h16->Hp : 0, next_trace_slot(2),
+                                                                         c_out + SH, S, H, active, nullptr, 1, out16 ? h16->hout_hi + SHp : nullptr,
+                                                                         out16 ? h16->hout_lo + SHp : nullptr, out16 ? h16->Hp : 0, next_trace_slot(2),
                                                                          merged ? rp_early.part + AH : (const float*)nullptr, merged ? rp_early.splits : 0,
                                                                          merged ? AH + 4 * H : 0);
     SUBGC_LAUNCH_CHECK();
@@ -1035,7 +1036,7 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
     p = GemmProblem(); p.wts = w;
     p.M = S; p.N = V1; p.nseg = 1;
     p.seg[0] = make_seg(h_out + SH, H, w->logit.w, H, H);
-    if (use16) set_a16(p.seg[0], h16->hout_hi + SHp, h16->hout_lo + SHp, h16->Hp);
+    if (out16) set_a16(p.seg[0], h16->hout_hi + SHp, h16->hout_lo + SHp, h16->Hp);
     p.active = active;
     if (raw_logits) {
         raw_logits->part = static_cast<const float*>(sc.gemm_ws); raw_logits->splits = 1;
@@ -1492,6 +1493,7 @@ extern "C" size_t subgc_beam_workspace_bytes(const subgc_dims* d, int n_sub, int
     b += 4 * align_up(S * T * 4, 256);                      // histories
     b += align_up(S * 4, 256) + align_up((size_t)n_sub * 4, 256);
     b += 2 * align_up(S * kMaxBeam * 4, 256);                // per-row top-b candidates
+    b += step16_bytes(d, (int)S);                            // split-fp16 copies of this step's h_att / ctx / h_lang
     return b + 1024;
 }
 
@@ -1522,7 +1524,13 @@ extern "C" int subgc_decode_beam(const subgc_dims* d, const subgc_weights* w, in
     int* done_total = ws.take<int>(n_sub);
     float* top_ys = ws.take<float>((size_t)S * kMaxBeam);
     int* top_ix = ws.take<int>((size_t)S * kMaxBeam);
+    Step16Bufs b16;
+    const bool s16 = use_step16(w);
+    if (s16) ok = take_step16(d, S, ws, b16) && ok;
     if (!ok || !ws.ok()) { set_error("subgc_decode_beam: workspace too small"); return SUBGC_E_WORKSPACE; }
+    Step16 h16v = s16 ? step16_of(b16, 0, 1, false) : Step16();   // only this step's outputs are read as split copies:
+    h16v.hin_hi = nullptr; h16v.hin_lo = nullptr;                  // the previous state is re-mapped by `parent` (and never written in split form)
+    const Step16* h16 = s16 ? &h16v : nullptr;
     const bool fast_top = V1 <= kSelVals * kSelectThreads;   // logit row fits the register-resident top-b kernel
     RawPartials rl{nullptr, 0};
     SUBGC_CUDA(cudaMemsetAsync(hbuf[0], 0, 2 * (size_t)S * H * 4, st));
@@ -1540,7 +1548,7 @@ extern "C" int subgc_decode_beam(const subgc_dims* d, const subgc_weights* w, in
     // <bos> step on b identical rows per sub-graph (AttModel.py:216-227)
     SUBGC_TRY(launch_fc_pre(d, w, n_sub, fc, sc, st));
     SUBGC_TRY(launch_step(d, w, S, len_max, b, it, nullptr, nullptr, fc, att, p_att, masks, hbuf[0], cbuf[0], hbuf[1], cbuf[1], logits,
-                          fast_top ? &rl : nullptr, nullptr, 0, sc, nullptr, 0, st, sc.gates));
+                          fast_top ? &rl : nullptr, nullptr, 0, sc, nullptr, 0, st, sc.gates, h16));
     for (int t = 0; t < T; ++t) {
         BeamArgs a;
         a.ys_in = nullptr; a.ix_in = nullptr;
@@ -1563,7 +1571,7 @@ extern "C" int subgc_decode_beam(const subgc_dims* d, const subgc_weights* w, in
         if (t == T - 1) break;  // the reference's final get_logprobs_state result is never read (CaptionModel.py:170-171)
         const int in = (t + 1) & 1, out = in ^ 1;
         SUBGC_TRY(launch_step(d, w, S, len_max, b, it, nullptr, parent, fc, att, p_att, masks, hbuf[in], cbuf[in], hbuf[out], cbuf[out], logits,
-                              fast_top ? &rl : nullptr, nullptr, 0, sc, nullptr, 0, st, sc.gates));
+                              fast_top ? &rl : nullptr, nullptr, 0, sc, nullptr, 0, st, sc.gates, h16));
     }
     return SUBGC_OK;
 }
