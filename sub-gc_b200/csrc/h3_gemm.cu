@@ -679,7 +679,8 @@ static H3Plan h3_plan(int M, int N, const int* segK, int nseg) {
         // (measured: 3 stages of 64 KB -> ~0.75 us per k-block whatever is switched off)
         const double turn = (2300.0 + mma + 600.0) / pl.stages;
         if (turn > per_kb) per_kb = turn;
-        const double epi = (pl.splits > 1 ? 2.0 : 1.0) * bn * 128.0 * 4.0 / 64.0;   // partial tile out (and read back by the consumer)
+        static const double epi_w = getenv("SUBGC_H3_EPIW") ? atof(getenv("SUBGC_H3_EPIW")) : 1.0;
+        const double epi = (pl.splits > 1 ? 1.0 + epi_w * pl.splits / 2.0 : 1.0) * bn * 128.0 * 4.0 / 64.0;   // partial tile out + the consumer's read of all splits
         const double cost = waves * (pl.kb_per_split * per_kb + epi + 4000.0);
         if (cost < best_cost) { best_cost = cost; best = pl; }
     }
