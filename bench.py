@@ -61,7 +61,30 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.rows, self.stop_flag, self.th = index, [], False, None
 
+    def _run_nvml(self):
+        import pynvml as N
+        N.nvmlInit()
+        h = N.nvmlDeviceGetHandleByIndex(self.index)
+        mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+        while not self.stop_flag:
+            try:
+                sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+                try:
+                    rs = N.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                flags = ["Active" if rs & names[n] else "Not Active" for n in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")]
+                self.rows.append([str(sm), str(mx), "0"] + flags)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _run(self):
+        try:
+            return self._run_nvml()
+        except Exception:
+            pass
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
@@ -277,15 +300,16 @@ def main():
         barrier()
         if sampler:
             sampler.start()
+        from subgc.model import _DecodePlan
         model.stage_events = []
-        launches0 = L.subgc_launch_count()
+        launches0 = L.subgc_launch_count() + _DecodePlan.replayed_launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
             out = step_resident()
         e1.record()
         barrier()
-        launches = L.subgc_launch_count() - launches0
+        launches = L.subgc_launch_count() + _DecodePlan.replayed_launches - launches0   # direct launches + kernels inside graph replays
         ms_total = e0.elapsed_time(e1)
         stage_ms = {}
         for name, a, b in model.stage_events:

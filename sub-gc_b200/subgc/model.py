@@ -77,7 +77,10 @@ class _DecodePlan:
         self.masks = torch.empty(n_rows, len_max, device=dev)
         self.graph = None
         self.calls = 0
+        self.launches = 0
         self.out = {}
+
+    replayed_launches = 0   # kernels launched through graph replays (the C ABI's own counter only sees direct launches)
 
     def run(self, launch, use_graph):
         """launch() enqueues the C call on the current stream.  First call: eager (also sets kernel attributes);
@@ -87,12 +90,15 @@ class _DecodePlan:
             launch()
         elif self.graph is not None:
             self.graph.replay()
+            _DecodePlan.replayed_launches += self.launches
         elif self.calls == 1:
             launch()
         else:
+            c0 = lib().subgc_launch_count()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 launch()
+            self.launches = int(lib().subgc_launch_count() - c0)   # kernels per replay (counted while capturing; capture does not run them)
             self.graph = g
             g.replay()
 
