@@ -52,24 +52,63 @@ __global__ void __launch_bounds__(256) gcn_edge_update_kernel(const float* __res
 __global__ void __launch_bounds__(256) gcn_node_update_kernel(const float* __restrict__ m_subj, const float* __restrict__ m_obj,
                                                               const long long* __restrict__ rel_ind, const float* __restrict__ res,
                                                               float* __restrict__ out, int B, int N, int K, int L) {
-    extern __shared__ int s_list[];  // [2][K] edge lists of this node
+    extern __shared__ int s_list[];  // [2][K] edge lists of this node | [2][K] (subject, object) of the image's edges
     __shared__ int s_cnt[2];
+    int* s_raw = s_list + 2 * K;
     const int bn = blockIdx.x;
     const int b = bn / N, n = bn - b * N;
-    if (threadIdx.x == 0) {  // K is small (65): a serial scan keeps the ascending edge order
-        int cs = 0, co = 0;
-        for (int k = 0; k < K; ++k) {
-            long long s = rel_ind[((size_t)b * K + k) * 2], o = rel_ind[((size_t)b * K + k) * 2 + 1];
-            if (s == n) s_list[cs++] = k;
-            if (o == n) s_list[K + co++] = k;
-        }
-        s_cnt[0] = cs; s_cnt[1] = co;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {   // one coalesced read of the edge list instead of a serial scan of global memory
+        s_raw[k] = (int)rel_ind[((size_t)b * K + k) * 2];
+        s_raw[K + k] = (int)rel_ind[((size_t)b * K + k) * 2 + 1];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 || threadIdx.x == 32) {  // K is small (65): a serial scan (of shared memory) keeps the ascending edge order
+        const int which = threadIdx.x >> 5;
+        int c = 0;
+        for (int k = 0; k < K; ++k)
+            if (s_raw[which * K + k] == n) s_list[which * K + c++] = k;
+        s_cnt[which] = c;
     }
     __syncthreads();
     const int cs = s_cnt[0], co = s_cnt[1];
     const float ds = (float)cs + 1e-7f, dob = (float)co + 1e-7f;
     const float* ms = m_subj + (size_t)b * K * L;
     const float* mo = m_obj + (size_t)b * K * L;
+    if ((L & 3) == 0) {
+        const int L4 = L >> 2;
+        for (int c4 = threadIdx.x; c4 < L4; c4 += blockDim.x) {
+            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+            for (int i = 0; i < cs; i += 4) {   // four independent 16-byte loads in flight, added in ascending edge order
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    v[u] = (i + u < cs) ? __ldg(reinterpret_cast<const float4*>(ms + (size_t)s_list[i + u] * L) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (i + u < cs) { a0.x += v[u].x; a0.y += v[u].y; a0.z += v[u].z; a0.w += v[u].w; }
+            }
+            for (int i = 0; i < co; i += 4) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    v[u] = (i + u < co) ? __ldg(reinterpret_cast<const float4*>(mo + (size_t)s_list[K + i + u] * L) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (i + u < co) { a1.x += v[u].x; a1.y += v[u].y; a1.z += v[u].z; a1.w += v[u].w; }
+            }
+            float4 v;
+            v.x = (fmaxf(a0.x / ds, 0.f) + fmaxf(a1.x / dob, 0.f)) * 0.5f;
+            v.y = (fmaxf(a0.y / ds, 0.f) + fmaxf(a1.y / dob, 0.f)) * 0.5f;
+            v.z = (fmaxf(a0.z / ds, 0.f) + fmaxf(a1.z / dob, 0.f)) * 0.5f;
+            v.w = (fmaxf(a0.w / ds, 0.f) + fmaxf(a1.w / dob, 0.f)) * 0.5f;
+            if (res) {
+                const float4 rr = __ldg(reinterpret_cast<const float4*>(res + (size_t)bn * L) + c4);
+                v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+            }
+            reinterpret_cast<float4*>(out + (size_t)bn * L)[c4] = v;
+        }
+        return;
+    }
     for (int c = threadIdx.x; c < L; c += blockDim.x) {
         float a0 = 0.f, a1 = 0.f;
         for (int i = 0; i < cs; ++i) a0 += __ldg(ms + (size_t)s_list[i] * L + c);
@@ -240,7 +279,7 @@ extern "C" int subgc_gcn_forward(const subgc_dims* d, const subgc_weights* w, in
             SUBGC_TRY(linear(w, T, B * K, R, w->gcn_rgt[l][0], L, Ma, ws, st));
             SUBGC_TRY(linear(w, p, B * K, L, w->gcn_lft[l][1], R, T, ws, st));
             SUBGC_TRY(linear(w, T, B * K, R, w->gcn_rgt[l][1], L, Mb, ws, st));
-            gcn_node_update_kernel<<<B * N, 256, 2 * K * sizeof(int), st>>>(Ma, Mb, rel, boundary ? x_res : nullptr, x_next, B, N, K, L);
+            gcn_node_update_kernel<<<B * N, 256, 4 * K * sizeof(int), st>>>(Ma, Mb, rel, boundary ? x_res : nullptr, x_next, B, N, K, L);
             SUBGC_LAUNCH_CHECK();
         }
         x = x_next; p = p_next;

@@ -33,6 +33,29 @@ __global__ void __launch_bounds__(256) sgpn_pool_kernel(const subgc_subgraph_lay
     const int len = s_len;
     const float* xi = x_obj + (size_t)image * N * L;
     const float flen = (float)len;
+    if ((L & 3) == 0) {   // 16-byte columns, six independent row loads in flight, sum kept in ascending row order
+        const int L4 = L >> 2;
+        for (int c4 = threadIdx.x; c4 < L4; c4 += blockDim.x) {
+            const float m0 = (len < N) ? 0.f : -INFINITY;
+            float4 mx = make_float4(m0, m0, m0, m0), sm = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int n = 0; n < len; n += 6) {
+                float4 v[6];
+#pragma unroll
+                for (int u = 0; u < 6; ++u)
+                    v[u] = (n + u < len) ? __ldg(reinterpret_cast<const float4*>(xi + (size_t)s_ids[n + u] * L) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 6; ++u) {
+                    if (n + u < len) {
+                        mx.x = fmaxf(mx.x, v[u].x); mx.y = fmaxf(mx.y, v[u].y); mx.z = fmaxf(mx.z, v[u].z); mx.w = fmaxf(mx.w, v[u].w);
+                        sm.x += v[u].x; sm.y += v[u].y; sm.z += v[u].z; sm.w += v[u].w;
+                    }
+                }
+            }
+            reinterpret_cast<float4*>(read_out + (size_t)s * 2 * L)[c4] = mx;
+            reinterpret_cast<float4*>(read_out + (size_t)s * 2 * L + L)[c4] = make_float4(sm.x / flen, sm.y / flen, sm.z / flen, sm.w / flen);
+        }
+        return;
+    }
     for (int c = threadIdx.x; c < L; c += blockDim.x) {
         float mx = (len < N) ? 0.f : -INFINITY;  // rows beyond len are zeros in the reference and take part in the max
         float sm = 0.f;
