@@ -167,6 +167,10 @@ bool h3_eligible(const GemmProblem& p);
 int launch_gemm_h3(const GemmProblem& p, void* ws, size_t ws_bytes, cudaStream_t stream, RawPartials* raw = nullptr);
 // fills W16_hi / W16_lo of every segment whose weight pointer lies inside a packed tensor of `w` (no-op without packs)
 void resolve_packs(GemmProblem& p, const subgc_weights* w);
+// Splits plain activation rows A [M, K] once into hi / lo [M, K rounded up to 8] (taken from `ws`) so that several contractions can
+// share the copy through GemmSeg::A16_*; returns false (and takes nothing) when the split-fp16 path is not in use for `w`
+bool h3_presplit(const float* A, int M, int K, int lda, const subgc_weights* w, Workspace& ws, cudaStream_t stream, const unsigned short** hi,
+                 const unsigned short** lo, int* ld16);
 void* tc_encode_fn();  // cuTensorMapEncodeTiled through the runtime's driver entry point (nullptr when unavailable)
 // contraction without epilogue: the partial sums stay in `ws` for a consumer kernel that reduces them itself
 int launch_gemm_raw(const GemmProblem& p, void* ws, size_t ws_bytes, cudaStream_t stream, RawPartials* raw);

@@ -23,7 +23,8 @@ __global__ void __launch_bounds__(256) class_argmax_kernel(const float* __restri
     const float* p = dist + (size_t)row * C;
     float bv = -INFINITY;
     int bi = 0x7fffffff;
-    for (int j = off + lane; j < C; j += 32) {
+#pragma unroll 8
+    for (int j = off + lane; j < C; j += 32) {   // eight independent loads in flight per lane
         float v = __ldg(p + j);
         if (v > bv || bi == 0x7fffffff) { bv = v; bi = j; }  // strictly greater keeps the first index within a lane
     }
@@ -41,6 +42,23 @@ __global__ void __launch_bounds__(256) gcn_edge_update_kernel(const float* __res
     const float d = 1.f + 1e-7f;
     const float* ms = m_subj + ((size_t)b * N + s) * L;
     const float* mo = m_obj + ((size_t)b * N + o) * L;
+    if ((L & 3) == 0) {
+        const int L4 = L >> 2;
+        for (int c4 = threadIdx.x; c4 < L4; c4 += blockDim.x) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(ms) + c4), bb = __ldg(reinterpret_cast<const float4*>(mo) + c4);
+            float4 v;
+            v.x = 0.5f * (fmaxf(a.x / d, 0.f) + fmaxf(bb.x / d, 0.f));
+            v.y = 0.5f * (fmaxf(a.y / d, 0.f) + fmaxf(bb.y / d, 0.f));
+            v.z = 0.5f * (fmaxf(a.z / d, 0.f) + fmaxf(bb.z / d, 0.f));
+            v.w = 0.5f * (fmaxf(a.w / d, 0.f) + fmaxf(bb.w / d, 0.f));
+            if (res) {
+                const float4 rr = __ldg(reinterpret_cast<const float4*>(res + (size_t)bk * L) + c4);
+                v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+            }
+            reinterpret_cast<float4*>(out + (size_t)bk * L)[c4] = v;
+        }
+        return;
+    }
     for (int c = threadIdx.x; c < L; c += blockDim.x) {
         float v = 0.5f * (fmaxf(__ldg(ms + c) / d, 0.f) + fmaxf(__ldg(mo + c) / d, 0.f));
         if (res) v += __ldg(res + (size_t)bk * L + c);
@@ -154,6 +172,7 @@ static size_t gcn_ws_bytes(const subgc_dims* d, int B) {
     b += (size_t)d->gcn_layers * (align_up((size_t)B * d->obj_num * d->gcn * 4, 256) + align_up((size_t)B * d->rel_num * d->gcn * 4, 256));
     size_t g1 = gemm_workspace_bytes((int)rows, d->low_rank, d->gcn), g2 = gemm_workspace_bytes((int)rows, d->gcn, d->low_rank);
     b += align_up(g1 > g2 ? g1 : g2, 256) + 1024;
+    b += 2 * align_up(rows * (size_t)((d->gcn + 7) & ~7) * 2, 256) + 1024;   // split-fp16 copy of a layer input shared by two units
     return b;
 }
 
@@ -165,11 +184,13 @@ static size_t fuse_ws_bytes(const subgc_dims* d, int B) {
     return b;
 }
 
-static int linear(const subgc_weights* w, const float* A, int M, int K, const subgc_linear& lin, int N, float* C, Workspace& ws, cudaStream_t st) {
+static int linear(const subgc_weights* w, const float* A, int M, int K, const subgc_linear& lin, int N, float* C, Workspace& ws, cudaStream_t st,
+                  const unsigned short* a16_hi = nullptr, const unsigned short* a16_lo = nullptr, int lda16 = 0) {
     GemmProblem p;
     p.wts = w;
     p.M = M; p.N = N; p.nseg = 1;
     p.seg[0] = make_seg(A, K, lin.w, K, K);
+    if (a16_hi) { p.seg[0].A16_hi = a16_hi; p.seg[0].A16_lo = a16_lo; p.seg[0].lda16 = lda16; }   // shared split copy of A
     p.epi.bias = lin.b;
     p.C = C; p.ldc = N;
     return launch_gemm(p, ws.cursor(), ws.remaining(), st);
@@ -254,6 +275,9 @@ extern "C" int subgc_gcn_forward(const subgc_dims* d, const subgc_weights* w, in
     float* T = ws.take<float>(rows_max * R);
     float* Ma = ws.take<float>(rows_max * L);
     float* Mb = ws.take<float>(rows_max * L);
+    // both units of a direction contract the same layer input: split it once (split-fp16 path), in a region reserved up front
+    const size_t split_bytes = 2 * align_up(rows_max * (size_t)((L + 7) & ~7) * 2, 256) + 1024;
+    char* split_region = ws.take<char>(split_bytes);
     const float* x = x0;
     const float* p = p0;
     const float* x_res = x0;
@@ -267,17 +291,23 @@ extern "C" int subgc_gcn_forward(const subgc_dims* d, const subgc_weights* w, in
         if (need_p[l + 1]) p_next = last ? x_pred : ws.take<float>(pn);
         if (!ws.ok() || !T || !Ma || !Mb) { set_error("subgc_gcn_forward: workspace too small"); return SUBGC_E_WORKSPACE; }
         if (p_next) {  // units 2,3: edge <- node (graph_conv.py:29-33)
-            SUBGC_TRY(linear(w, x, B * N, L, w->gcn_lft[l][2], R, T, ws, st));
+            const unsigned short *xh = nullptr, *xl = nullptr;
+            int xld = 0;
+            if (split_region) { Workspace sw(split_region, split_bytes); if (!h3_presplit(x, B * N, L, L, w, sw, st, &xh, &xl, &xld)) xh = xl = nullptr; }
+            SUBGC_TRY(linear(w, x, B * N, L, w->gcn_lft[l][2], R, T, ws, st, xh, xl, xld));
             SUBGC_TRY(linear(w, T, B * N, R, w->gcn_rgt[l][2], L, Ma, ws, st));
-            SUBGC_TRY(linear(w, x, B * N, L, w->gcn_lft[l][3], R, T, ws, st));
+            SUBGC_TRY(linear(w, x, B * N, L, w->gcn_lft[l][3], R, T, ws, st, xh, xl, xld));
             SUBGC_TRY(linear(w, T, B * N, R, w->gcn_rgt[l][3], L, Mb, ws, st));
             gcn_edge_update_kernel<<<B * K, 256, 0, st>>>(Ma, Mb, rel, boundary ? p_res : nullptr, p_next, B, N, K, L);
             SUBGC_LAUNCH_CHECK();
         }
         if (x_next) {  // units 0,1: node <- edges (graph_conv.py:22-26)
-            SUBGC_TRY(linear(w, p, B * K, L, w->gcn_lft[l][0], R, T, ws, st));
+            const unsigned short *ph = nullptr, *pl = nullptr;
+            int pld = 0;
+            if (split_region) { Workspace sw(split_region, split_bytes); if (!h3_presplit(p, B * K, L, L, w, sw, st, &ph, &pl, &pld)) ph = pl = nullptr; }
+            SUBGC_TRY(linear(w, p, B * K, L, w->gcn_lft[l][0], R, T, ws, st, ph, pl, pld));
             SUBGC_TRY(linear(w, T, B * K, R, w->gcn_rgt[l][0], L, Ma, ws, st));
-            SUBGC_TRY(linear(w, p, B * K, L, w->gcn_lft[l][1], R, T, ws, st));
+            SUBGC_TRY(linear(w, p, B * K, L, w->gcn_lft[l][1], R, T, ws, st, ph, pl, pld));
             SUBGC_TRY(linear(w, T, B * K, R, w->gcn_rgt[l][1], L, Mb, ws, st));
             gcn_node_update_kernel<<<B * N, 256, 4 * K * sizeof(int), st>>>(Ma, Mb, rel, boundary ? x_res : nullptr, x_next, B, N, K, L);
             SUBGC_LAUNCH_CHECK();

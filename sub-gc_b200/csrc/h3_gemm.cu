@@ -634,6 +634,24 @@ void resolve_packs(GemmProblem& p, const subgc_weights* w) {
     }
 }
 
+bool h3_presplit(const float* A, int M, int K, int lda, const subgc_weights* w, Workspace& ws, cudaStream_t stream, const unsigned short** hi,
+                 const unsigned short** lo, int* ld16) {
+    if (!w || !w->packs || w->n_packs <= 0 || !h3_mode() || M <= 0 || K <= 0) return false;
+    const int Kp = (K + 7) & ~7;
+    if (ws.remaining() < 2 * align_up((size_t)M * Kp * 2, 256) + 512) return false;
+    unsigned short* th = ws.take<unsigned short>((size_t)M * Kp);
+    unsigned short* tl = ws.take<unsigned short>((size_t)M * Kp);
+    if (!ws.ok()) return false;
+    GemmSeg g = make_seg(A, lda, nullptr, 0, K);
+    const size_t quads = (size_t)M * (Kp >> 2);
+    int gb = (int)((quads + 255) / 256);
+    if (gb > kNumSMs * 8) gb = kNumSMs * 8;
+    if (launch_pdl(split_rows_kernel, dim3(gb), dim3(256), (size_t)0, stream, g, M, Kp, th, tl, (const int*)nullptr, w->h3_overflow) != cudaSuccess) return false;
+    count_launch();
+    *hi = th; *lo = tl; *ld16 = Kp;
+    return true;
+}
+
 struct H3Plan { int m_tiles, n_tiles, kb_total, splits, kb_per_split, bn, stages; };
 
 // Tile width and split count.  One CTA streams bn weight rows over its k-range; narrow tiles leave more n-tiles, i.e. fewer
