@@ -19,6 +19,7 @@ L = _lib.lib()
 L.subgc_debug_trace.restype = C.c_int
 L.subgc_debug_trace.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int]
 opt = {"beam_size": 5 if mode == "beam" else 1}
+decode_only = mode == "head"
 st0 = (C.c_ulonglong * (8 * 4096))(); ids0 = (C.c_int * 4096)()
 with torch.no_grad():
     model(*args, opt=opt, mode="sample")            # eager
@@ -44,6 +45,12 @@ t0 = t[ok, 0].min()
 idx = np.nonzero(ok)[0]
 sel = [i for i in idx if k[i] == 4]
 print(f"{ok.sum()} traced launches, loop span {(t[ok,1].max()-t0)/1e3:.1f} us, {len(sel)} select launches")
+if mode == "head":
+    # the start of the loop: everything before the third selection
+    z = t[idx[0], 0]
+    for i in idx[:22]:
+        print(f"  {names.get(int(k[i]), str(k[i])):12s} start {(t[i,0]-z)/1e3:8.2f} released {(t[i,2]-z)/1e3:8.2f} end {(t[i,1]-z)/1e3:8.2f}")
+    print(f"  last kernel end {(t[idx[-1],1]-z)/1e3:8.2f}")
 if mode == "beam":
     # no selection kernel in the beam loop: print 16 consecutive launches from the middle of the loop
     mid = idx[len(idx) // 2: len(idx) // 2 + 16]
