@@ -181,3 +181,25 @@ print("OK", err)
     env = dict(os.environ, **{variant: "1"})
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_benchmark_configuration_matches_oracle():
+    """BASELINE config 2 at full size -- exactly what bench.py times (128 images x 36 nodes x 2048-d, one full sub-graph kept per
+    image, greedy 20-token decode, the bench's seed): every token id equals the oracle's, log-probs within RTOL; three calls so
+    that the compared result comes from the replayed CUDA graph."""
+    d = Dims()
+    sd = synth.make_state_dict(d, 2019)
+    data = synth.make_test_inputs(d, 2019, n_images=128, per_half=1, ragged=False, ragged_edges=False)
+    dev = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in data.items()}
+    args = [dev[k] for k in synth.SAMPLE_ARG_ORDER]
+    m = _model(d, sd, gpn_nms_thres=0.75, gpn_max_subg=1)
+    with torch.no_grad():
+        for _ in range(3):
+            seq, lps, score, keep = m(*args, opt={"beam_size": 1}, mode="sample")
+        m.check_numerics()
+        ref = O.sample(sd, d, data, use_nms=True, iou_thres=0.75, max_subgraphs=1)
+    assert seq.shape == (128, d.seq_length)
+    assert torch.equal(keep.cpu(), ref["keep_ind"])
+    assert torch.equal(seq.cpu(), ref["seq"]), int((seq.cpu() != ref["seq"]).sum())
+    assert float((lps.cpu() - ref["seqLogprobs"]).abs().max()) <= RTOL * max(1.0, float(ref["seqLogprobs"].abs().max()))
+    assert float((score.cpu() - ref["subgraph_score"]).abs().max()) <= RTOL
