@@ -203,3 +203,31 @@ def test_benchmark_configuration_matches_oracle():
     assert torch.equal(seq.cpu(), ref["seq"]), int((seq.cpu() != ref["seq"]).sum())
     assert float((lps.cpu() - ref["seqLogprobs"]).abs().max()) <= RTOL * max(1.0, float(ref["seqLogprobs"].abs().max()))
     assert float((score.cpu() - ref["subgraph_score"]).abs().max()) <= RTOL
+
+
+@pytest.mark.parametrize("mode,n_images", [("topk", 128), ("beam", 32)])
+def test_other_baseline_configurations_match_oracle(mode, n_images):
+    """BASELINE config 4 shard (top-k sampling, k=3, temp 0.6, 128 images; the same uniforms injected into oracle and kernel) and
+    config 3 (beam 5; 32 images keep the oracle's CPU beam search at a few seconds): exact token ids, log-probs within RTOL."""
+    d = Dims()
+    sd = synth.make_state_dict(d, 2019)
+    data = synth.make_test_inputs(d, 2019, n_images=n_images, per_half=1, ragged=False, ragged_edges=False)
+    dev = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in data.items()}
+    args = [dev[k] for k in synth.SAMPLE_ARG_ORDER]
+    m = _model(d, sd, gpn_nms_thres=0.75, gpn_max_subg=1, use_topk_sampling=1 if mode == "topk" else 0)
+    opt = {"beam_size": 5 if mode == "beam" else 1}
+    okw = dict(use_nms=True, iou_thres=0.75, max_subgraphs=1)
+    if mode == "topk":
+        u = torch.rand(d.seq_length, n_images, generator=torch.Generator().manual_seed(7))
+        opt["topk_uniforms"] = u
+        okw.update(topk=True, temp=0.6, k=3, uniforms=u)
+    else:
+        okw.update(beam_size=5)
+    with torch.no_grad():
+        for _ in range(3):
+            res = m(*args, opt=opt, mode="sample")
+        m.check_numerics()
+        ref = O.sample(sd, d, data, **okw)
+    seq, lps = res[0].cpu(), res[1].cpu()
+    assert torch.equal(seq, ref["seq"]), int((seq != ref["seq"]).sum())
+    assert float((lps - ref["seqLogprobs"]).abs().max()) <= RTOL * max(1.0, float(ref["seqLogprobs"].abs().max()))
