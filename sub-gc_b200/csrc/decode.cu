@@ -204,7 +204,10 @@ __global__ void __maxnreg__(48) attention_kernel(const float* __restrict__ atth_
                                                                 int att_w_stride, int S, int len_max, int H, int AH, int rows_per_ctx,
                                                                 const int* __restrict__ active, unsigned short* __restrict__ c16_hi,
                                                                 unsigned short* __restrict__ c16_lo, int Hp, TraceSlot trace, int* overflow,
-                                                                int ld_part) {
+                                                                int ld_part, int early_ok) {
+    // early_ok: p_att / masks were written before this launch sequence began (the decode loops: their buffers come from the prepare
+    // stage and memset nodes separate it from the loop), so they may be read before the dependency wait.  A single step through the
+    // C ABI (subgc_decode_step) may directly follow the kernel that produced them: there they are only read after the wait.
     trace_begin(trace);
     pdl_trigger();
     extern __shared__ float s_att[];  // [AH] atth | [AH] alpha_w | [64] e | [4][H] context partials (first 256 floats: score partials)
@@ -221,7 +224,7 @@ __global__ void __maxnreg__(48) attention_kernel(const float* __restrict__ atth_
     const int items = len_max * Q;
     const bool fast = (AH & 127) == 0 && items <= kMaxItems * nw && items <= 256;
     float4 pv[kMaxItems];
-    if (fast) {
+    if (fast && early_ok) {
         const float4* pa4 = reinterpret_cast<const float4*>(p_att + (size_t)cr * len_max * AH);
 #pragma unroll
         for (int k = 0; k < kMaxItems; ++k) {
@@ -241,10 +244,21 @@ __global__ void __maxnreg__(48) attention_kernel(const float* __restrict__ atth_
     }
     for (int j = threadIdx.x; j < AH; j += blockDim.x) s_w[j] = __ldg(alpha_w + j);
     __shared__ float s_mask[64];   // the row's mask does not depend on the step either
-    if (threadIdx.x < len_max) s_mask[threadIdx.x] = __ldg(masks + (size_t)cr * len_max + threadIdx.x);
+    if (early_ok && threadIdx.x < len_max) s_mask[threadIdx.x] = __ldg(masks + (size_t)cr * len_max + threadIdx.x);
     pdl_wait();
     trace_released(trace);
     if (active != nullptr && *active == 0) return;
+    if (!early_ok) {
+        if (threadIdx.x < len_max) s_mask[threadIdx.x] = masks[(size_t)cr * len_max + threadIdx.x];
+        if (fast) {
+            const float4* pa4 = reinterpret_cast<const float4*>(p_att + (size_t)cr * len_max * AH);
+#pragma unroll
+            for (int k = 0; k < kMaxItems; ++k) {
+                const int item = wid + k * nw;
+                pv[k] = item < items ? pa4[(size_t)(item / Q) * AH4 + (item % Q) * 32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
     for (int j = threadIdx.x; j < AH; j += blockDim.x) {
         float a = 0.f;
         for (int z = 0; z < splits; ++z) a += atth_part[((size_t)z * S + r) * ld_part + j];
@@ -998,7 +1012,8 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
         if (!(skip & 8)) launch_pdl(attention_kernel, dim3(S), dim3(kAttThreads), smem, st, rp.part, rp.splits, w->h2att.b, p_att, att, masks, w->alpha_net.w, w->alpha_net.b,
                                                                         sc.ctx, att_w, att_w_stride, S, len_max, H, AH, rows_per_ctx, active,
                                                                         out16 ? h16->ctx_hi : nullptr, out16 ? h16->ctx_lo : nullptr, out16 ? h16->Hp : 0, next_trace_slot(3),
-                                                                        (int*)(out16 ? w->h3_overflow : nullptr), merged ? AH + 4 * H : AH);
+                                                                        (int*)(out16 ? w->h3_overflow : nullptr), merged ? AH + 4 * H : AH,
+                                                                        fc_pre != nullptr ? 1 : 0);
         SUBGC_LAUNCH_CHECK();
     }
     if (upto == 1) return SUBGC_OK;
