@@ -49,6 +49,17 @@ void count_launch();  // per-thread tally of kernels launched through this libra
 
 constexpr int kNumSMs = 148;  // B200
 
+// Function attributes (dynamic shared-memory limit, carve-out) are per device: `first_use_on_device(flags)` is true once per
+// device for the given per-call-site flag array, so that DataParallel-style threads driving several GPUs from one process work.
+inline bool first_use_on_device(bool (&seen)[64]) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return true;
+    if (seen[dev]) return false;
+    seen[dev] = true;
+    return true;
+}
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Bump allocator over the caller-provided workspace.

@@ -872,9 +872,8 @@ static bool att_phase_fusable(size_t smem) {
 // The loop's small kernels run next to the contraction's CTAs (which hold ~193 KB of shared memory): an SM only hosts kernels with
 // the same shared-memory / L1 split, so they ask for the maximum shared-memory carve-out as well.
 static void prefer_smem_carveout() {
-    static bool done = false;
-    if (done) return;
-    done = true;
+    static bool seen[64] = {};
+    if (!first_use_on_device(seen)) return;
     cudaFuncSetAttribute(lstm_reduce_cell_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(select_reg_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);

@@ -749,11 +749,10 @@ static int h3_segments(const GemmProblem& p, int box_w, Workspace& ws, cudaStrea
 }
 
 static int h3_set_smem_attr() {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool seen[64] = {};
+    if (first_use_on_device(seen)) {
         SUBGC_CUDA(cudaFuncSetAttribute(h3_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, H3_SMEM_BUDGET + H3_SMEM_EXTRA));
         SUBGC_CUDA(cudaFuncSetAttribute(h3_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, H3_SMEM_BUDGET + H3_SMEM_EXTRA));
-        attr_set = true;
     }
     return SUBGC_OK;
 }
