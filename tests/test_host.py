@@ -91,3 +91,18 @@ def test_unsupported_variants_are_rejected():
     for over in (dict(use_gpn=0), dict(noun_fuse=0), dict(gcn_bn=1), dict(use_bn=1)):
         with pytest.raises(NotImplementedError):
             dims_from_opt(make_opt(Dims(), **over))
+
+
+def test_pack_segment_descriptor_and_abi_entries():
+    """Host side of the packed-weight format (include/subgc_b200.h: subgc_packed): column cuts -> seg_col array; the element count
+    of a packed copy (k-block-major, every K segment padded to 64 columns) comes from the library itself (no device needed)."""
+    from subgc import packing
+    seg, n = packing._seg_array(3000, [1000, 2000])
+    assert n == 3 and list(seg)[:4] == [0, 1000, 2000, 3000]
+    seg1, n1 = packing._seg_array(300, None)
+    assert n1 == 1 and list(seg1)[:2] == [0, 300]
+    L = _lib.lib()
+    assert L.subgc_pack_elems(4000, n, seg) == 3 * 16 * 4000 * 64      # 3 segments x ceil(1000 / 64) k-blocks x rows x 64
+    assert L.subgc_pack_elems(1024, n1, seg1) == 5 * 1024 * 64
+    with pytest.raises(AssertionError):
+        packing._seg_array(100, [50, 40])
