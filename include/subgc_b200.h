@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SUBGC_ABI_VERSION 2
+#define SUBGC_ABI_VERSION 3
 #define SUBGC_MAX_GCN_LAYERS 8
 
 typedef void* subgc_stream_t; /* cudaStream_t */
@@ -119,6 +119,12 @@ typedef struct subgc_weights {
                                                           When set, a decode step contracts everything that depends only on
                                                           (h_att(t), h_lang(t-1)) in ONE launch before the attention (h2att + two
                                                           thirds of the language-LSTM gates) and only the ctx segment after it. */
+    const void* mega;                                  /* DEVICE (nullable): schedule tables + "stream pack" of the decoder weights for the
+                                                          persistent decode kernel, built by subgc_mega_pack for `mega_ctas` CTAs.  When
+                                                          set, subgc_decode_sample runs its whole loop as ONE cooperative launch
+                                                          (<= 128 rows, no attention-weight output); otherwise one launch per stage.   */
+    uint64_t mega_bytes;
+    int32_t mega_ctas;                                 /* CTAs the schedule was built for (= SMs of the device, one CTA each)           */
 } subgc_weights;
 
 /* How sub-graph s of a flat list maps onto the loader tensors gpn_obj_ind / att_masks [rows,2,per_half,N].
@@ -150,6 +156,18 @@ int subgc_debug_trace(int op, unsigned long long* stamps, int* ids, int n);
 size_t subgc_pack_elems(int rows, int n_seg, const int32_t* seg_col);
 int subgc_pack_weight(int rows, int cols, const float* w, int ldw, int n_seg, const int32_t* seg_col, uint16_t* hi,
                       uint16_t* lo, int32_t* overflow, subgc_stream_t stream);
+
+/* Persistent decode kernel (csrc/mega_decode.cu): the greedy / top-k loop of AttModel._sample (models/AttModel.py:278-326) as one
+ * cooperative launch with one CTA per SM.  Every CTA streams a fixed slice of the four per-step weight matrices
+ * (core.att_lstm, core.attention.h2att, core.lang_lstm, logit: models/AttModel.py:393-398,438-443,87) from its own contiguous
+ * region of the "stream pack": split-fp16 tiles (as subgc_packed: v = hi + lo * 2^-11) already in the shared-memory layout of the
+ * tensor core, in the order the CTA contracts them.  subgc_mega_pack_bytes: size of tables + pack for these dims and `n_cta` CTAs
+ * (0: dims not supported by the kernel).  subgc_mega_pack: builds both into `buf` (device, 1024-byte aligned) from the fp32
+ * parameters in `w`; `overflow` (device, nullable) is OR-ed with 1 when a weight does not fit fp16.  Re-pack after the parameters
+ * change.  Not capturable (copies the tables from host memory). */
+size_t subgc_mega_pack_bytes(const subgc_dims* d, int n_cta);
+int subgc_mega_pack(const subgc_dims* d, const subgc_weights* w, int n_cta, void* buf, size_t bytes, int32_t* overflow,
+                    subgc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Building block: C[M,N] = act((A[gather] . W^T + bias + addend) / div), the nn.Linear contraction every stage

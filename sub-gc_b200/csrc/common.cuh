@@ -188,6 +188,13 @@ int launch_gemm_raw(const GemmProblem& p, void* ws, size_t ws_bytes, cudaStream_
 // upper bound of splits * M * N floats for launch_gemm_ex raw partials
 size_t gemm_partial_elems(int M, int N, int Ktotal);
 
+// ---- persistent decode kernel (mega_decode.cu): the greedy / top-k loop as one cooperative launch ---------------------------
+bool mega_decode_eligible(const subgc_dims* d, const subgc_weights* w, int S, int len_max, const float* att_weights);
+size_t mega_decode_scratch_bytes_max(const subgc_dims* d);
+int launch_mega_decode(const subgc_dims* d, const subgc_weights* w, int S, int len_max, int mode, float temp, int top_k, uint64_t seed, uint64_t offset,
+                       const float* uniforms, const float* fc_pre, const float* att, const float* p_att, const float* masks, int64_t* seq,
+                       float* seq_lp, int32_t* steps_done, Workspace& ws, cudaStream_t st);
+
 // ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
 // The decode loop is a chain of ~6 dependent kernels per token, each of them short: launch latency, grid drain and kernel
 // prologues are a third of the step.  Kernels launched through launch_pdl may start while their predecessor in the stream is

@@ -1358,6 +1358,7 @@ extern "C" size_t subgc_decode_workspace_bytes(const subgc_dims* d, int n_rows, 
     b += align_up(S * 8, 256) + align_up(S * 4, 256) + align_up(S * d->enc * 4, 256);  // it, unfinished, xt
     b += align_up((size_t)(d->seq_length + 2) * 4, 256);   // count
     b += step16_bytes(d, n_rows);                          // split-fp16 activation copies
+    if (n_rows <= 128) b += mega_decode_scratch_bytes_max(d);   // activation tiles / partials / counters of the persistent kernel
     return b + 1024;
 }
 
@@ -1423,6 +1424,9 @@ extern "C" int subgc_decode_sample(const subgc_dims* d, const subgc_weights* w, 
         SUBGC_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(V1 * sizeof(float))));
     }
     SUBGC_TRY(launch_fc_pre(d, w, S, fc, sc, st));
+    if (mega_decode_eligible(d, w, S, len_max, att_weights))   // the whole loop as one persistent kernel (mega_decode.cu)
+        return launch_mega_decode(d, w, S, len_max, mode, temp, top_k, seed, offset, uniforms, sc.gates, att, p_att, masks, seq, seq_logprobs,
+                                  steps_done, ws, st);
     for (int t = 0; t <= T; ++t) {
         const int* active = (t == 0) ? nullptr : count + (t - 1);
         const int in = t & 1, out = in ^ 1;

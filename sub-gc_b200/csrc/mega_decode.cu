@@ -1,0 +1,1036 @@
+// Persistent decode kernel: the whole greedy / top-k sampling loop of AttModel._sample (reference models/AttModel.py:278-326) as ONE
+// cooperative launch -- every step = get_logprobs_state (AttModel.py:328-341) = TopDownCore (:400-431) + Attention (:445-471) + logit.
+//
+// Why: with one kernel per stage (decode.cu) a step is 8 dependent launches and the weight stream (152 MB per token) stops at every
+// kernel boundary; measured 0.33 of the HBM roofline.  tools/ubench_ingest.cu showed that the SMs can ingest the weight stream at
+// 7.0-7.3 TB/s next to an equally large L2-resident activation stream, as long as >= 96 KB per SM stay in flight, and that a grid-wide
+// hand-off costs 1.2-2.4 us.  So here one CTA per SM owns a fixed slice of every contraction of the step and
+//   * a producer thread streams that slice (its own contiguous, pre-swizzled region of the "stream pack", cp.async.bulk, L2 evict-first)
+//     into a 4-deep ring and never waits for anything but a free slot: the HBM pipe keeps running across phase hand-offs;
+//   * a second thread loads the activation tiles (split-fp16, pre-swizzled by their producers) once their dependency counter is up;
+//   * one thread issues the tcgen05.mma chains (split-fp16: main + cross accumulators in TMEM, two accumulator sets);
+//   * 16 worker warps drain accumulators (TMEM -> split-K partial in L2), and run the LSTM cells, the attention of "their" row and the
+//     token selection of "their" row, handing results over through global counters (release / acquire), not kernel boundaries.
+// Work that does not depend on the newest result (the h_att / h_lang segments of the NEXT contraction) is issued while a hand-off is
+// in flight.  The schedule (which CTA contracts which weight tile in which order) is a table built on the host (mega_plan).
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <math.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace subgc {
+
+// ---- geometry ------------------------------------------------------------------------------------------------------------
+constexpr int MG_THREADS = 640;          // warps 0-3: W producer, X loader, MMA issuer, TMEM owner; warps 4-19: workers
+constexpr int MG_NW = 512;               // worker threads
+constexpr int MG_WSLOTS = 4, MG_WSLOT_BYTES = 36864;   // weight ring: tiles of <= 144 rows x 64 k (hi | lo)
+constexpr int MG_XSLOTS = 2, MG_XTILE_BYTES = 32768;   // activation ring: [128 rows x 64 k] hi | lo
+constexpr int MG_SCR_BYTES = 16384;
+constexpr int MG_OFF_X = MG_WSLOTS * MG_WSLOT_BYTES;            // 147456
+constexpr int MG_OFF_SCR = MG_OFF_X + MG_XSLOTS * MG_XTILE_BYTES;   // 212992
+constexpr int MG_OFF_BAR = MG_OFF_SCR + MG_SCR_BYTES;           // 229376
+constexpr int MG_SMEM = MG_OFF_BAR + 1024 + 1024;               // + control block + alignment slack
+// TMEM columns of the two accumulator sets (set 0: tiles <= 112 wide, set 1: <= 144) and the offset of the cross-term accumulator
+__host__ __device__ constexpr int mg_set_col(int set) { return set ? 224 : 0; }
+__host__ __device__ constexpr int mg_set_cross(int set) { return set ? 144 : 112; }
+constexpr int MG_MAX_TASKS = 8;
+constexpr int MG_MAX_TILES = 192;
+
+enum { MG_X_XT = 0, MG_X_CTX = 1, MG_X_HATT = 2, MG_X_HLANG_PREV = 3, MG_X_HLANG = 4 };
+enum { MG_F_START = 1, MG_F_COMMIT = 2, MG_F_NEXT = 4, MG_F_AXT = 8 };
+enum { MG_JOB_A = 0, MG_JOB_B = 1, MG_JOB_C = 2, MG_JOB_D = 3 };
+// sync counters (uint32 indices into MgParams::sync)
+enum { MG_C_XT = 0, MG_C_HATT = 32, MG_C_HLANG = 64, MG_C_CTX = 96, MG_C_B = 128, MG_C_D = 160, MG_C_ABORT = 192, MG_C_TILE_A = 256,
+       MG_C_TILE_C = 256 + MG_MAX_TILES, MG_C_UNF = 256 + 2 * MG_MAX_TILES, MG_C_TOTAL = 1024 };
+
+struct MgTask { int n_blk, n_rows, x_src, x_kb0, acc_set, flags, pad0, pad1; };
+struct MgJob {
+    int present, set, n_rows;
+    int part_off;      // floats: A/C: this job's [col][128] tile; B/D: first column inside the plane
+    int plane;         // B/D: split index (plane of the row-major partials)
+    int tile, n_split; // A/C: tile id (sync counter) and partials per tile
+    int tile_u0, tile_units;   // A/C: hidden units of the tile
+    int u_lo, u_n;     // A/C: this CTA's share of the tile's units in the cell
+    int part_tile_off; // A/C: floats, partial of split 0 of the tile (split z at + z * 16384)
+};
+struct MgCta {
+    MgTask task[MG_MAX_TASKS];
+    MgJob job[4];
+    int n_task;
+    int step_bytes;
+    unsigned long long w_off;
+};
+
+struct MgParams {
+    const MgCta* ctas;
+    const uint8_t* wstream;
+    int n_cta, S, T, len_max, H, E, AH, V1, kbH, kbE;
+    int nL, nB, nD, zB, zD, ldB, ldD;
+    const float* fc_pre; const float* att; const float* p_att; const float* masks;
+    const float* h2att_b; const float* alpha_w; const float* alpha_b; const float* logit_b; const float* embed;
+    const float* lang_b_ih; const float* lang_b_hh;
+    uint8_t* x_xt; uint8_t* x_ctx; uint8_t* x_hatt[2]; uint8_t* x_hlang[2];
+    float* partA; float* partC; float* partB; float* partD;
+    unsigned* sync;
+    long long* seq; float* seq_lp; int* steps_done; int* overflow;
+    int mode; float temp; int top_k; unsigned long long seed, offset; const float* uniforms;
+};
+
+// ---- PTX helpers local to this kernel ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t}\n"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release(unsigned* p, unsigned v) { asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_load_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+#define MG_TMEM_LD16(R, ADDR)                                                                                                          \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];" \
+                 : "=r"(R[0]), "=r"(R[1]), "=r"(R[2]), "=r"(R[3]), "=r"(R[4]), "=r"(R[5]), "=r"(R[6]), "=r"(R[7]), "=r"(R[8]), "=r"(R[9]),  \
+                   "=r"(R[10]), "=r"(R[11]), "=r"(R[12]), "=r"(R[13]), "=r"(R[14]), "=r"(R[15])                                          \
+                 : "r"(ADDR))
+
+// control block in shared memory (after the rings and the worker scratch)
+struct MgCtl {
+    unsigned long long w_full[MG_WSLOTS], w_empty[MG_WSLOTS], x_full[MG_XSLOTS], x_empty[MG_XSLOTS], acc_full[2], acc_free[2], mma_done;
+    uint32_t tmem_slot;
+    volatile int stop;      // 1: all rows finished (normal early exit), 2: aborted (time-out; MG_C_ABORT holds the site)
+    volatile int flag[2];   // worker broadcast of a wait result
+    int red_i[16];
+    float red_f[16];
+    float topv[16];
+    int topi[16];
+    int s_it;
+    MgCta cta;
+};
+static_assert(sizeof(MgCtl) <= 1024, "control block must fit its 1 KB");
+
+constexpr unsigned long long MG_TIMEOUT_NS = 4000000000ull;   // a wait longer than this aborts the kernel (debug guard: never hang the GPU)
+
+struct MgWait {
+    MgCtl* ctl;
+    unsigned* sync;
+    unsigned long long t0;
+    __device__ __forceinline__ bool expired(int site) {
+        if (ld_acquire(sync + MG_C_ABORT) != 0) { ctl->stop = 2; return true; }
+        if (globaltimer_ns() - t0 > MG_TIMEOUT_NS) {
+            atomicCAS(sync + MG_C_ABORT, 0u, (unsigned)(site * 1000 + (int)blockIdx.x + 1));
+            ctl->stop = 2;
+            return true;
+        }
+        return false;
+    }
+    // false: the kernel is stopping (early exit or abort)
+    __device__ __forceinline__ bool mbar(unsigned long long* bar, uint32_t parity, int site) {
+        const uint32_t b = smem_u32(bar);
+        for (uint32_t it = 1;; ++it) {
+            if (mbar_try(b, parity)) return true;
+            if (ctl->stop) return false;
+            if ((it & 255u) == 0 && expired(site)) return false;
+        }
+    }
+    __device__ __forceinline__ bool counter(const unsigned* c, unsigned target, int site) {
+        for (uint32_t it = 1;; ++it) {
+            if (ld_acquire(c) >= target) return true;
+            if (ctl->stop) return false;
+            if ((it & 255u) == 0 && expired(site)) return false;
+        }
+    }
+};
+
+// element (row, col) of a split-fp16 activation tensor in tile layout: [kb][hi | lo][128 rows][64 cols], 128-byte swizzle
+__device__ __forceinline__ size_t x_tile_off(int row, int col) {
+    const int kb = col >> 6, c = col & 63;
+    return (size_t)kb * MG_XTILE_BYTES + (size_t)row * 128 + (size_t)((((c >> 3) ^ (row & 7)) << 4) + ((c & 7) << 1));
+}
+__device__ __forceinline__ void x_store(uint8_t* buf, int row, int col, float v, int& ovf) {
+    unsigned short h, l;
+    split_f16(v, h, l, ovf);
+    const size_t o = x_tile_off(row, col);
+    *reinterpret_cast<unsigned short*>(buf + o) = h;
+    *reinterpret_cast<unsigned short*>(buf + o + MG_XTILE_BYTES / 2) = l;
+}
+
+__device__ __forceinline__ float mg_tanh_score(float x) {   // same form as decode.cu: ex2-based, |err| <= 2e-7
+    const float e = __expf(-2.f * fabsf(x));
+    return copysignf(__fdividef(1.f - e, 1.f + e), x);
+}
+
+// reductions over the 512 worker threads (wt = worker thread id); every worker must call
+__device__ __forceinline__ float workers_sum(float v, MgCtl* ctl, int wt) {
+    v = warp_sum(v);
+    worker_bar();
+    if ((wt & 31) == 0) ctl->red_f[wt >> 5] = v;
+    worker_bar();
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t += ctl->red_f[i];
+    return t;
+}
+__device__ __forceinline__ void workers_argmax(float& v, int& i, MgCtl* ctl, int wt) {
+    warp_argmax(v, i);
+    worker_bar();
+    if ((wt & 31) == 0) { ctl->red_f[wt >> 5] = v; ctl->red_i[wt >> 5] = i; }
+    worker_bar();
+    v = ctl->red_f[0]; i = ctl->red_i[0];
+#pragma unroll
+    for (int w = 1; w < 16; ++w) argmax_combine(v, i, ctl->red_f[w], ctl->red_i[w]);
+}
+
+struct MgPhilox {
+    static __device__ __forceinline__ void round(unsigned (&c)[4], unsigned k0, unsigned k1) {
+        unsigned hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        unsigned hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        unsigned n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    }
+    static __device__ float uniform(unsigned long long seed, unsigned long long offset, unsigned t, unsigned r) {   // identical to decode.cu's stream
+        unsigned c[4] = {(unsigned)offset, (unsigned)(offset >> 32), t, r};
+        unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+        for (int i = 0; i < 10; ++i) { round(c, k0, k1); k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+        return (float)(c[0] >> 8) * (1.0f / 16777216.0f);
+    }
+};
+
+constexpr int MG_SELVALS = 20;   // logit values per worker thread: V1 <= 10240
+constexpr int MG_ATT_ITEMS = 10; // (node, 32-quad slice) items per worker warp and pass
+
+__global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid_constant__ MgParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+    MgCtl* ctl = reinterpret_cast<MgCtl*>(gbase + MG_OFF_BAR);
+    float* scr = reinterpret_cast<float*>(gbase + MG_OFF_SCR);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cta_id = blockIdx.x;
+    const int S = p.S, T = p.T, H = p.H;
+
+    // ---- set-up: schedule of this CTA, barriers, tensor memory
+    {
+        const int* src = reinterpret_cast<const int*>(p.ctas + cta_id);
+        int* dst = reinterpret_cast<int*>(&ctl->cta);
+        for (int i = tid; i < (int)(sizeof(MgCta) / 4); i += MG_THREADS) dst[i] = src[i];
+    }
+    if (tid == 0) {
+        for (int s = 0; s < MG_WSLOTS; ++s) { mbar_init(smem_u32(&ctl->w_full[s]), 1); mbar_init(smem_u32(&ctl->w_empty[s]), 1); }
+        for (int s = 0; s < MG_XSLOTS; ++s) { mbar_init(smem_u32(&ctl->x_full[s]), 1); mbar_init(smem_u32(&ctl->x_empty[s]), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&ctl->acc_full[s]), 1); mbar_init(smem_u32(&ctl->acc_free[s]), 16); }
+        mbar_init(smem_u32(&ctl->mma_done), 1);
+        ctl->stop = 0; ctl->flag[0] = 0; ctl->flag[1] = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 3) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = ctl->tmem_slot;
+    const MgCta& cta = ctl->cta;
+    MgWait wt_{ctl, p.sync, globaltimer_ns()};
+
+    if (warp == 0) {
+        // ===================================================== weight stream producer =====================================================
+        if (lane == 0) {
+            uint64_t pol;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+            uint32_t cnt = 0;
+            bool alive = true;
+            for (int t = 0; t < T && alive; ++t) {
+                const uint8_t* src = p.wstream + cta.w_off;
+                for (int k = 0; k < cta.n_task && alive; ++k) {
+                    const MgTask& tk = cta.task[k];
+                    const uint32_t bytes = (uint32_t)tk.n_rows * 256u;
+                    if ((tk.flags & MG_F_NEXT) && t == T - 1) { src += (size_t)tk.n_blk * bytes; continue; }
+                    for (int b = 0; b < tk.n_blk; ++b) {
+                        const uint32_t s = cnt % MG_WSLOTS;
+                        if (cnt >= MG_WSLOTS && !wt_.mbar(&ctl->w_empty[s], ((cnt / MG_WSLOTS) & 1u) ^ 1u, 1)) { alive = false; break; }
+                        const uint32_t full = smem_u32(&ctl->w_full[s]);
+                        mbar_arrive_expect_tx(full, bytes);
+                        bulk_load_hint(base + s * MG_WSLOT_BYTES, src, bytes, full, pol);
+                        src += bytes;
+                        ++cnt;
+                    }
+                }
+            }
+            // tiles still in flight must land before the CTA may retire (they were requested ahead of a stop)
+            if (!alive && ctl->stop == 1)
+                for (uint32_t i = (cnt > MG_WSLOTS ? cnt - MG_WSLOTS : 0); i < cnt; ++i)
+                    while (!mbar_try(smem_u32(&ctl->w_full[i % MG_WSLOTS]), (i / MG_WSLOTS) & 1u)) {}
+        }
+    } else if (warp == 1) {
+        // ===================================================== activation tile loader =====================================================
+        if (lane == 0) {
+            uint32_t cnt = 0;
+            bool alive = true;
+            int steps = T + 1;   // executed steps as the reference counts them (AttModel.py:312-314)
+            for (int t = 0; t < T && alive; ++t) {
+                if (t >= 1) {   // xt(t) complete <=> every row's selection of step t-1 is done: the all-finished early exit is decided here
+                    if (!wt_.counter(p.sync + MG_C_XT, (unsigned)S * (unsigned)(t + 1), 2)) { alive = false; break; }
+                    if (ld_acquire(p.sync + MG_C_UNF + (t - 1)) == 0) { ctl->stop = 1; steps = t; alive = false; break; }
+                }
+                for (int k = 0; k < cta.n_task && alive; ++k) {
+                    const MgTask& tk = cta.task[k];
+                    if ((tk.flags & MG_F_NEXT) && t == T - 1) continue;
+                    const uint8_t* xb;
+                    const unsigned* c;
+                    unsigned target;
+                    switch (tk.x_src) {
+                        case MG_X_XT: xb = p.x_xt; c = p.sync + MG_C_XT; target = (unsigned)S * (unsigned)(t + 1); break;
+                        case MG_X_CTX: xb = p.x_ctx; c = p.sync + MG_C_CTX; target = (unsigned)S * (unsigned)(t + 1); break;
+                        case MG_X_HATT: xb = p.x_hatt[t & 1]; c = p.sync + MG_C_HATT; target = (unsigned)p.nL * (unsigned)(t + 1); break;
+                        case MG_X_HLANG_PREV: xb = p.x_hlang[(t + 1) & 1]; c = p.sync + MG_C_HLANG; target = (unsigned)p.nL * (unsigned)t; break;
+                        default: xb = p.x_hlang[t & 1]; c = p.sync + MG_C_HLANG; target = (unsigned)p.nL * (unsigned)(t + 1); break;
+                    }
+                    if (target > 0 && !wt_.counter(c, target, 3)) { alive = false; break; }
+                    fence_proxy_async_all();   // the tiles were written with generic stores by other SMs; the bulk copies below read them
+                    for (int b = 0; b < tk.n_blk; ++b) {
+                        const uint32_t s = cnt % MG_XSLOTS;
+                        if (cnt >= MG_XSLOTS && !wt_.mbar(&ctl->x_empty[s], ((cnt / MG_XSLOTS) & 1u) ^ 1u, 4)) { alive = false; break; }
+                        const uint32_t full = smem_u32(&ctl->x_full[s]);
+                        mbar_arrive_expect_tx(full, MG_XTILE_BYTES);
+                        bulk_load(base + MG_OFF_X + s * MG_XTILE_BYTES, xb + (size_t)(tk.x_kb0 + b) * MG_XTILE_BYTES, MG_XTILE_BYTES, full);
+                        ++cnt;
+                    }
+                }
+            }
+            if (cta_id == 0 && ctl->stop != 2) {
+                if (alive && wt_.counter(p.sync + MG_C_XT, (unsigned)S * (unsigned)(T + 1), 13) && ld_acquire(p.sync + MG_C_UNF + (T - 1)) == 0) steps = T;
+                if (ctl->stop != 2) p.steps_done[0] = steps;
+            }
+        }
+    } else if (warp == 2) {
+        // ===================================================== MMA issuer =====================================================
+        if (lane == 0) {
+            uint32_t wcnt = 0, xcnt = 0, jobs[2] = {0, 0};
+            bool alive = true;
+            for (int t = 0; t < T && alive; ++t) {
+                for (int k = 0; k < cta.n_task && alive; ++k) {
+                    const MgTask& tk = cta.task[k];
+                    if ((tk.flags & MG_F_NEXT) && t == T - 1) continue;
+                    const int set = tk.acc_set;
+                    const bool fresh = (tk.flags & MG_F_START) || ((tk.flags & MG_F_AXT) && t == 0);
+                    if (fresh && jobs[set] > 0) {   // the workers must have drained the previous accumulator of this set
+                        if (!wt_.mbar(&ctl->acc_free[set], (jobs[set] - 1) & 1u, 5)) { alive = false; break; }
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
+                    const uint32_t n = (uint32_t)tk.n_rows;
+                    const uint32_t idesc = (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24);   // D fp32, A/B fp16 K-major, N = n, M = 128
+                    const uint32_t d_main = tmem + (uint32_t)mg_set_col(set), d_cross = d_main + (uint32_t)mg_set_cross(set);
+                    for (int b = 0; b < tk.n_blk; ++b) {
+                        const uint32_t ws = wcnt % MG_WSLOTS, xs = xcnt % MG_XSLOTS;
+                        if (!wt_.mbar(&ctl->w_full[ws], (wcnt / MG_WSLOTS) & 1u, 6)) { alive = false; break; }
+                        if (!wt_.mbar(&ctl->x_full[xs], (xcnt / MG_XSLOTS) & 1u, 7)) { alive = false; break; }
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t wa = base + ws * MG_WSLOT_BYTES, xa = base + MG_OFF_X + xs * MG_XTILE_BYTES;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint64_t whi = umma_desc_sw128(wa + ks * 32);
+                            const uint64_t wlo = umma_desc_sw128(wa + n * 128u + ks * 32);
+                            const uint64_t xhi = umma_desc_sw128(xa + ks * 32);
+                            const uint64_t xlo = umma_desc_sw128(xa + MG_XTILE_BYTES / 2 + ks * 32);
+                            const uint32_t acc = (fresh && b == 0 && ks == 0) ? 0u : 1u;
+                            umma_f16_afill(d_main, xhi, whi, idesc, acc);
+                            umma_f16_alast(d_cross, xhi, wlo, idesc, acc);
+                            umma_f16(d_cross, xlo, whi, idesc, 1u);
+                        }
+                        umma_commit(smem_u32(&ctl->w_empty[ws]));
+                        umma_commit(smem_u32(&ctl->x_empty[xs]));
+                        ++wcnt; ++xcnt;
+                    }
+                    if (alive && (tk.flags & MG_F_COMMIT)) { umma_commit(smem_u32(&ctl->acc_full[set])); ++jobs[set]; }
+                }
+            }
+            // every MMA issued so far (the early exit leaves next-step work behind) has retired before tensor memory is released
+            if (ctl->stop != 2) {
+                umma_commit(smem_u32(&ctl->mma_done));
+                for (uint32_t it = 0; it < (1u << 24) && !mbar_try(smem_u32(&ctl->mma_done), 0); ++it) {}
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================================================== workers =====================================================
+        const int wt = tid - 128, ww = wt >> 5;
+        uint32_t epis[2] = {0, 0};
+        uint32_t nwait = 0;
+        bool alive = true;
+        const bool has_row = cta_id < S;
+        const int row = cta_id;
+        // broadcast wait helpers: worker thread 0 waits, everybody learns the outcome
+        auto w_mbar = [&](unsigned long long* bar, uint32_t parity, int site) -> bool {
+            if (wt == 0) ctl->flag[nwait & 1] = wt_.mbar(bar, parity, site) ? 1 : 0;
+            worker_bar();
+            const bool ok = ctl->flag[nwait & 1] != 0;
+            ++nwait;
+            return ok;
+        };
+        auto w_counter = [&](const unsigned* c, unsigned target, int site) -> bool {
+            if (wt == 0) ctl->flag[nwait & 1] = wt_.counter(c, target, site) ? 1 : 0;
+            worker_bar();
+            const bool ok = ctl->flag[nwait & 1] != 0;
+            ++nwait;
+            return ok;
+        };
+        // everything this CTA's workers wrote becomes visible to whoever acquires the counter afterwards
+        auto w_signal = [&](unsigned* c) {
+            fence_proxy_async_all();
+            worker_bar();
+            if (wt == 0) { __threadfence(); red_release(c, 1u); }
+        };
+        // accumulator -> split-K partial.  col_major: [col][128 rows] (cells read rows of a column), else row-major plane [128][ld]
+        auto epilogue = [&](const MgJob& jb, float* dst, int ld, bool col_major) -> bool {
+            const int set = jb.set;
+            if (!w_mbar(&ctl->acc_full[set], epis[set] & 1u, 8)) return false;
+            ++epis[set];
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int q = ww & 3, g = ww >> 2;
+            const int r = q * 32 + lane;
+            const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)mg_set_col(set);
+#pragma unroll 1
+            for (int cc = 0; cc < 3; ++cc) {
+                const int chunk = g + 4 * cc;   // 16-column chunks, interleaved over the 4 warps of a lane quarter (<= 9 chunks)
+                if (chunk * 16 >= jb.n_rows) break;
+                uint32_t ra[16], rb[16];
+                MG_TMEM_LD16(ra, tl + (uint32_t)(chunk * 16));
+                MG_TMEM_LD16(rb, tl + (uint32_t)mg_set_cross(set) + (uint32_t)(chunk * 16));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(rb[j]), kH3LoInv, __uint_as_float(ra[j]));
+                if (col_major) {
+                    float* o = dst + (size_t)(chunk * 16) * 128 + r;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) __stcg(o + (size_t)j * 128, v[j]);
+                } else {
+                    float4* o = reinterpret_cast<float4*>(dst + (size_t)r * ld + chunk * 16);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) __stcg(o + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&ctl->acc_free[set]));
+            return true;
+        };
+
+        const MgJob& jA = cta.job[MG_JOB_A];
+        const MgJob& jB = cta.job[MG_JOB_B];
+        const MgJob& jC = cta.job[MG_JOB_C];
+        const MgJob& jD = cta.job[MG_JOB_D];
+        // cell state of this thread's (row, unit) elements lives in registers for the whole loop (init_hidden: zeros)
+        float cA[2] = {0.f, 0.f}, cC[2] = {0.f, 0.f};
+        int unfinished = 1;   // worker thread 0 of a row CTA
+        int ovf = 0;
+        // scratch: [AH] atth | [AH] alpha_net weight | [64] scores | [64] mask | [256] score partials | [2][H] context partials
+        float* s_h = scr;
+        float* s_w = scr + p.AH;
+        float* s_e = scr + 2 * p.AH;
+        float* s_mask = s_e + 64;
+        float* s_sp = s_mask + 64;
+        float* s_c = s_sp + 256;
+        if (has_row) {
+            for (int j = wt; j < p.AH; j += MG_NW) s_w[j] = __ldg(p.alpha_w + j);
+            if (wt < p.len_max) s_mask[wt] = __ldg(p.masks + (size_t)row * p.len_max + wt);
+            // xt(0) = relu(E[<bos> = 0]) (AttModel.py:283-284,332)
+            for (int j = wt; j < p.E; j += MG_NW) x_store(p.x_xt, row, j, fmaxf(__ldg(p.embed + j), 0.f), ovf);
+            w_signal(p.sync + MG_C_XT);
+        }
+
+        // LSTM cell on this CTA's share of a tile: gates = sum of the tile's split-K partials (split order) + addend
+        auto cell = [&](const MgJob& jb, const float* part, unsigned* tile_cnt, int t, float (&cst)[2], bool is_att, uint8_t* xout) -> bool {
+            const int nel = 128 * jb.u_n;
+            float add[2][4];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {   // operands that do not depend on the partials are requested before the wait
+                const int e = wt + k * MG_NW;
+                const int r = e & 127, u = jb.tile_u0 + jb.u_lo + (e >> 7);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) add[k][q] = 0.f;
+                if (e < nel && r < S) {
+                    if (is_att) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) add[k][q] = __ldg(p.fc_pre + (size_t)r * 4 * H + (size_t)q * H + u);
+                    }
+                }
+            }
+            if (!w_counter(tile_cnt, (unsigned)jb.n_split * (unsigned)(t + 1), 9)) return false;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int e = wt + k * MG_NW;
+                if (e >= nel) continue;
+                const int r = e & 127, ul = jb.u_lo + (e >> 7), u = jb.tile_u0 + ul;
+                if (r >= S) continue;
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                const float* g = part + jb.part_tile_off + r;
+                for (int z = 0; z < jb.n_split; ++z) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[q] += __ldcg(g + (size_t)z * 16384 + (size_t)(q * jb.tile_units + ul) * 128);
+                }
+                if (is_att) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[q] += add[k][q];
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[q] = (acc[q] + __ldg(p.lang_b_ih + q * H + u)) + __ldg(p.lang_b_hh + q * H + u);
+                }
+                const float c = sigmoidf_(acc[1]) * cst[k] + sigmoidf_(acc[0]) * tanhf(acc[2]);
+                cst[k] = c;
+                x_store(xout, r, u, sigmoidf_(acc[3]) * tanhf(c), ovf);
+            }
+            return true;
+        };
+
+        for (int t = 0; t < T && alive; ++t) {
+            // ---------------- attention LSTM: gates -> partial -> cell -> h_att(t)
+            if (jA.present) {
+                if (!epilogue(jA, p.partA + jA.part_off, 128, true)) break;
+                w_signal(p.sync + MG_C_TILE_A + jA.tile);
+                if (!cell(jA, p.partA, p.sync + MG_C_TILE_A + jA.tile, t, cA, true, p.x_hatt[t & 1])) break;
+                w_signal(p.sync + MG_C_HATT);
+            }
+            // ---------------- h2att partial
+            if (jB.present) {
+                if (!epilogue(jB, p.partB + (size_t)jB.plane * 128 * p.ldB + jB.part_off, p.ldB, false)) break;
+                w_signal(p.sync + MG_C_B);
+            }
+            // ---------------- attention of this CTA's row (AttModel.py:445-471) -> ctx(t)
+            if (has_row) {
+                const int AH = p.AH, len_max = p.len_max;
+                const int AH4 = AH >> 2, Q = AH4 >> 5;          // AH % 128 == 0 (checked on the host)
+                const int items = len_max * Q;                  // (node, 32-quad slice)
+                const float4* pa4 = reinterpret_cast<const float4*>(p.p_att + (size_t)row * len_max * AH);
+                {   // att row -> L2 (the weight stream may have evicted it)
+                    const char* af = reinterpret_cast<const char*>(p.att + (size_t)row * len_max * H);
+                    const size_t nb_a = (size_t)len_max * H * 4;
+                    for (size_t o = (size_t)wt * 128; o < nb_a; o += (size_t)MG_NW * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(af + o));
+                }
+                for (int i0 = 0; i0 < items && alive; i0 += MG_ATT_ITEMS * 16) {
+                    float4 pv[MG_ATT_ITEMS];
+#pragma unroll
+                    for (int k = 0; k < MG_ATT_ITEMS; ++k) {   // p_att does not depend on the step: in flight during the wait below
+                        const int item = i0 + ww + k * 16;
+                        pv[k] = item < items ? __ldg(pa4 + (size_t)(item / Q) * AH4 + (item % Q) * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    if (i0 == 0) {
+                        if (!w_counter(p.sync + MG_C_B, (unsigned)p.nB * (unsigned)(t + 1), 10)) { alive = false; break; }
+                        for (int j = wt; j < AH; j += MG_NW) {
+                            float a = 0.f;
+                            for (int z = 0; z < p.zB; ++z) a += __ldcg(p.partB + ((size_t)z * 128 + row) * p.ldB + j);
+                            s_h[j] = a + __ldg(p.h2att_b + j);
+                        }
+                        worker_bar();
+                    }
+                    const float4* h4 = reinterpret_cast<const float4*>(s_h);
+                    const float4* w4 = reinterpret_cast<const float4*>(s_w);
+#pragma unroll
+                    for (int k = 0; k < MG_ATT_ITEMS; ++k) {
+                        const int item = i0 + ww + k * 16;
+                        if (item >= items) continue;
+                        const int j4 = (item % Q) * 32 + lane;
+                        const float4 v = pv[k], hh = h4[j4], wv = w4[j4];
+                        float a = wv.x * mg_tanh_score(v.x + hh.x);
+                        a = fmaf(wv.y, mg_tanh_score(v.y + hh.y), a);
+                        a = fmaf(wv.z, mg_tanh_score(v.z + hh.z), a);
+                        a = fmaf(wv.w, mg_tanh_score(v.w + hh.w), a);
+                        a = warp_sum(a);
+                        if (lane == 0) s_sp[item] = a;
+                    }
+                }
+                if (!alive) break;
+                worker_bar();
+                if (wt < len_max) {
+                    float e = 0.f;
+                    for (int q = 0; q < Q; ++q) e += s_sp[wt * Q + q];
+                    s_e[wt] = e + __ldg(p.alpha_b);
+                }
+                worker_bar();
+                if (ww == 0) {   // softmax, then mask, then renormalise: two-stage as the reference (AttModel.py:462-466)
+                    float m = -INFINITY;
+                    for (int n = lane; n < len_max; n += 32) m = fmaxf(m, s_e[n]);
+                    m = warp_max(m);
+                    float sum = 0.f;
+                    for (int n = lane; n < len_max; n += 32) sum += expf(s_e[n] - m);
+                    sum = warp_sum(sum);
+                    float msum = 0.f;
+                    for (int n = lane; n < len_max; n += 32) {
+                        const float wv = expf(s_e[n] - m) / sum * s_mask[n];
+                        s_e[n] = wv;
+                        msum += wv;
+                    }
+                    msum = warp_sum(msum);
+                    for (int n = lane; n < len_max; n += 32) s_e[n] = s_e[n] / msum;
+                }
+                worker_bar();
+                {   // context: two thread groups take interleaved node subsets, partials combined in fixed order
+                    const float* af = p.att + (size_t)row * len_max * H;
+                    const int grp = wt >> 8, tg = wt & 255, H4 = H >> 2;
+                    for (int j4 = tg; j4 < H4; j4 += 256) {
+                        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 6
+                        for (int n = grp; n < len_max; n += 2) {
+                            const float4 v = __ldg(reinterpret_cast<const float4*>(af + (size_t)n * H) + j4);
+                            const float wv = s_e[n];
+                            a.x = fmaf(wv, v.x, a.x); a.y = fmaf(wv, v.y, a.y); a.z = fmaf(wv, v.z, a.z); a.w = fmaf(wv, v.w, a.w);
+                        }
+                        reinterpret_cast<float4*>(s_c + (size_t)grp * H)[j4] = a;
+                    }
+                    worker_bar();
+                    for (int j = wt; j < H; j += MG_NW) x_store(p.x_ctx, row, j, s_c[j] + s_c[H + j], ovf);
+                }
+                w_signal(p.sync + MG_C_CTX);
+            }
+            // ---------------- language LSTM -> h_lang(t)
+            if (jC.present) {
+                if (!epilogue(jC, p.partC + jC.part_off, 128, true)) break;
+                w_signal(p.sync + MG_C_TILE_C + jC.tile);
+                if (!cell(jC, p.partC, p.sync + MG_C_TILE_C + jC.tile, t, cC, false, p.x_hlang[t & 1])) break;
+                w_signal(p.sync + MG_C_HLANG);
+            }
+            // ---------------- logit partial
+            if (jD.present) {
+                if (!epilogue(jD, p.partD + (size_t)jD.plane * 128 * p.ldD + jD.part_off, p.ldD, false)) break;
+                w_signal(p.sync + MG_C_D);
+            }
+            // ---------------- token selection of this CTA's row (AttModel.py:292-318) -> xt(t+1)
+            if (has_row) {
+                if (!w_counter(p.sync + MG_C_D, (unsigned)p.nD * (unsigned)(t + 1), 11)) break;
+                const int V1 = p.V1;
+                float v[MG_SELVALS];
+#pragma unroll
+                for (int i = 0; i < MG_SELVALS; ++i) {
+                    const int j = wt + i * MG_NW;
+                    float a = 0.f;
+                    if (j < V1) {
+                        for (int z = 0; z < p.zD; ++z) a += __ldcg(p.partD + ((size_t)z * 128 + row) * p.ldD + j);
+                        a += __ldg(p.logit_b + j);
+                    }
+                    v[i] = a;
+                }
+                float bv = -INFINITY;
+                int bi = 0x7fffffff;
+#pragma unroll
+                for (int i = 0; i < MG_SELVALS; ++i) {
+                    const int j = wt + i * MG_NW;
+                    if (j < V1 && (v[i] > bv || bi == 0x7fffffff)) { bv = v[i]; bi = j; }
+                }
+                workers_argmax(bv, bi, ctl, wt);
+                const float m = bv;
+                float s = 0.f;
+#pragma unroll
+                for (int i = 0; i < MG_SELVALS; ++i)
+                    if (wt + i * MG_NW < V1) s += expf(v[i] - m);
+                s = workers_sum(s, ctl, wt);
+                const float lz = logf(s);
+                int tok;
+                float lp;
+                if (p.mode == 0) {
+                    tok = bi;
+                    lp = (m - m) - lz;
+                } else {   // top-k sampling: q = log_softmax(logp / temp), keep the k best, Categorical over them (AttModel.py:296-303)
+                    const float ym = ((m - m) - lz) / p.temp;
+                    float s2 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < MG_SELVALS; ++i)
+                        if (wt + i * MG_NW < V1) s2 += expf(((v[i] - m) - lz) / p.temp - ym);
+                    s2 = workers_sum(s2, ctl, wt);
+                    const float lz2 = logf(s2);
+                    unsigned taken = 0;
+                    for (int c = 0; c < p.top_k; ++c) {
+                        float cv = -INFINITY;
+                        int ci = 0x7fffffff;
+#pragma unroll
+                        for (int i = 0; i < MG_SELVALS; ++i) {
+                            const int j = wt + i * MG_NW;
+                            if (j >= V1 || ((taken >> i) & 1u)) continue;
+                            const float qv = (((v[i] - m) - lz) / p.temp - ym) - lz2;
+                            if (qv > cv || ci == 0x7fffffff) { cv = qv; ci = j; }
+                        }
+                        workers_argmax(cv, ci, ctl, wt);
+                        if (ci != 0x7fffffff && (ci % MG_NW) == wt) taken |= 1u << (ci / MG_NW);
+                        if (wt == 0) { ctl->topv[c] = cv; ctl->topi[c] = ci; }
+                    }
+                    worker_bar();
+                    const int k = p.top_k;
+                    const float u = p.uniforms ? p.uniforms[(size_t)t * S + row] : MgPhilox::uniform(p.seed, p.offset, (unsigned)t, (unsigned)row);
+                    float den = 0.f;
+                    for (int c = 0; c < k; ++c) den += expf(ctl->topv[c] - ctl->topv[0]);
+                    float cdf = 0.f;
+                    int pos = 0;
+                    for (int c = 0; c < k; ++c) {
+                        cdf += expf(ctl->topv[c] - ctl->topv[0]) / den;
+                        if (u >= cdf) pos = c + 1;
+                    }
+                    if (pos > k - 1) pos = k - 1;
+                    tok = ctl->topi[pos];
+                    lp = ctl->topv[pos];
+                }
+                if (wt == 0) {
+                    const int unf = (t == 0 ? 1 : unfinished) && (tok > 0);
+                    unfinished = unf;
+                    const long long it = unf ? tok : 0;
+                    p.seq[(size_t)row * T + t] = it;
+                    p.seq_lp[(size_t)row * T + t] = lp;
+                    if (unf) atomicAdd(p.sync + MG_C_UNF + t, 1u);
+                    ctl->s_it = (int)it;
+                }
+                worker_bar();
+                const float* e = p.embed + (size_t)ctl->s_it * p.E;
+                for (int j = wt; j < p.E; j += MG_NW) x_store(p.x_xt, row, j, fmaxf(__ldg(e + j), 0.f), ovf);
+                w_signal(p.sync + MG_C_XT);
+            }
+        }
+        if (ovf && p.overflow) atomicOr(p.overflow, 1);
+    }
+    __syncthreads();
+    if (tid == 0) {   // a time-out anywhere is reported as a negative step count (site * 1000 + CTA + 1)
+        const unsigned ab = ld_acquire(p.sync + MG_C_ABORT);
+        if (ab != 0) p.steps_done[0] = -(int)ab;
+    }
+    if (warp == 3) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
+// ---- stream pack ---------------------------------------------------------------------------------------------------------------
+// One block = the [n_rows x 64] weight tile of one k-block as the tensor core wants it in shared memory: hi tile then lo tile, rows of
+// 128 bytes, 16-byte chunks XOR-swizzled by (row & 7).  The blocks of a CTA follow each other in the order the CTA contracts them.
+struct MgBlockDesc {
+    const float* src; int ld;
+    int gate;          // 1: rows are gate-grouped (row r = gate r / U, unit u0 + r % U -> source row gate * H + unit), 0: row r -> r0 + r
+    int r0, U, Hrows;  // plain: first source row and number of source rows; gate: first unit, units in the tile, H
+    int n_rows;
+    int col0, ncols;   // source columns [col0, col0 + ncols) are valid (the rest of the 64 is zero)
+    unsigned long long dst;
+};
+__global__ void __launch_bounds__(256) mega_pack_kernel(const MgBlockDesc* __restrict__ descs, uint8_t* __restrict__ out, int* __restrict__ overflow) {
+    const MgBlockDesc d = descs[blockIdx.x];
+    uint8_t* hi = out + d.dst;
+    uint8_t* lo = hi + (size_t)d.n_rows * 128;
+    int ovf = 0;
+    for (int idx = threadIdx.x; idx < d.n_rows * 64; idx += blockDim.x) {
+        const int r = idx >> 6, c = idx & 63;
+        long long srow;
+        bool valid;
+        if (d.gate) {
+            const int q = r / d.U, u = d.r0 + (r - q * d.U);
+            valid = q < 4 && u < d.Hrows;
+            srow = (long long)q * d.Hrows + u;
+        } else {
+            valid = d.r0 + r < d.Hrows;
+            srow = d.r0 + r;
+        }
+        valid = valid && c < d.ncols;
+        unsigned short h = 0, l = 0;
+        if (valid) split_f16(d.src[srow * d.ld + d.col0 + c], h, l, ovf);
+        const size_t o = (size_t)r * 128 + (size_t)((((c >> 3) ^ (r & 7)) << 4) + ((c & 7) << 1));
+        *reinterpret_cast<unsigned short*>(hi + o) = h;
+        *reinterpret_cast<unsigned short*>(lo + o) = l;
+    }
+    if (ovf && overflow) atomicOr(overflow, 1);
+}
+
+// ---- schedule ------------------------------------------------------------------------------------------------------------------
+struct MgPlan {
+    bool ok = false;
+    int n_cta = 0, kbH = 0, kbE = 0;
+    int zL = 0, tilesL = 0, nL = 0;
+    int zB = 0, tilesB = 0, nB = 0, ldB = 0;
+    int zD = 0, tilesD = 0, nD = 0, ldD = 0;
+    std::vector<MgCta> ctas;
+    std::vector<MgBlockDesc> blocks;   // src pointers filled by mega_fill_sources
+    std::vector<int> block_src;        // source matrix id per block
+    unsigned long long w_bytes = 0;
+};
+enum { MG_SRC_ATT_IH = 0, MG_SRC_ATT_HH, MG_SRC_LANG_IH, MG_SRC_LANG_HH, MG_SRC_H2ATT, MG_SRC_LOGIT };
+
+static void split_groups(int groups, int tiles, std::vector<int>& g0, std::vector<int>& gn) {   // as even as possible
+    g0.resize(tiles); gn.resize(tiles);
+    const int b = groups / tiles, rem = groups % tiles;
+    int at = 0;
+    for (int i = 0; i < tiles; ++i) { gn[i] = b + (i < rem ? 1 : 0); g0[i] = at; at += gn[i]; }
+}
+
+static MgPlan mega_plan(const subgc_dims* d, int n_cta) {
+    MgPlan pl;
+    const int H = d->rnn, E = d->enc, AH = d->att_hid, V1 = d->vocab1;
+    if (n_cta < 1 || n_cta > 1024 || H < 4 || (H & 3) || E < 1 || AH < 128 || (AH & 127) || AH > 512 || V1 < 2 || V1 > MG_SELVALS * MG_NW) return pl;
+    if ((size_t)(2 * AH + 64 + 64 + 256 + 2 * H) * 4 > MG_SCR_BYTES) return pl;
+    pl.n_cta = n_cta;
+    const int kbH = (H + 63) / 64, kbE = (E + 63) / 64;
+    pl.kbH = kbH; pl.kbE = kbE;
+    // LSTM contractions: tiles of <= 7 groups of 4 hidden units (x 4 gates = <= 112 weight rows), zL k-splits per tile
+    const int G = H / 4;
+    int zL = 0, tilesL = 0;
+    for (int z = 8; z >= 1; z >>= 1) {
+        if (z > kbH || z > kbE) continue;
+        const int tl = std::min(G, n_cta / z);
+        if (tl < 1 || (G + tl - 1) / tl > 7) continue;
+        const int umax = 4 * ((G + tl - 1) / tl);
+        if ((umax + z - 1) / z > 8) continue;   // the cell keeps <= 2 elements per worker thread: <= 8 units x 128 rows per CTA
+        zL = z; tilesL = tl;
+        break;
+    }
+    if (!zL || tilesL > MG_MAX_TILES) return pl;
+    pl.zL = zL; pl.tilesL = tilesL; pl.nL = zL * tilesL;
+    // h2att: tiles of <= 7 groups of 16 rows
+    const int GB = (AH + 15) / 16;
+    int zB = 1;
+    while (zB * 2 <= 8 && zB * 2 <= kbH) zB *= 2;
+    int tilesB = (GB + 6) / 7;
+    while (zB > 1 && tilesB * zB > n_cta) zB >>= 1;
+    if (tilesB * zB > n_cta) return pl;
+    pl.zB = zB; pl.tilesB = tilesB; pl.nB = zB * tilesB; pl.ldB = GB * 16;
+    // logit: tiles of <= 9 groups of 16 rows
+    const int GD = (V1 + 15) / 16;
+    int zD = 0, tilesD = 0;
+    for (int z = 4; z >= 1; z >>= 1) {
+        if (z > kbH) continue;
+        const int td = std::min(GD, n_cta / z);
+        if (td < 1 || (GD + td - 1) / td > 9) continue;
+        zD = z; tilesD = td;
+        break;
+    }
+    if (!zD) return pl;
+    pl.zD = zD; pl.tilesD = tilesD; pl.nD = zD * tilesD; pl.ldD = GD * 16;
+
+    std::vector<int> gL0, gLn, gB0, gBn, gD0, gDn;
+    split_groups(G, tilesL, gL0, gLn);
+    split_groups(GB, tilesB, gB0, gBn);
+    split_groups(GD, tilesD, gD0, gDn);
+    pl.ctas.assign(n_cta, MgCta());
+    for (auto& c : pl.ctas) memset(&c, 0, sizeof(MgCta));
+    auto kb_range = [](int kb, int z, int Z, int& a, int& n) { a = z * kb / Z; n = (z + 1) * kb / Z - a; };
+    unsigned long long w_at = 0;
+    for (int c = 0; c < n_cta; ++c) {
+        MgCta& ct = pl.ctas[c];
+        ct.w_off = w_at;
+        int nt = 0;
+        auto add_task = [&](int src_id, const float*, int gate, int r0, int U, int Hrows, int n_rows, int seg_col0, int seg_cols, int kb0, int nkb, int x_src,
+                            int set, int flags) {
+            if (nkb <= 0) return;
+            MgTask& tk = ct.task[nt++];
+            tk.n_blk = nkb; tk.n_rows = n_rows; tk.x_src = x_src; tk.x_kb0 = kb0; tk.acc_set = set; tk.flags = flags;
+            for (int b = 0; b < nkb; ++b) {
+                MgBlockDesc bd;
+                memset(&bd, 0, sizeof(bd));
+                bd.gate = gate; bd.r0 = r0; bd.U = U; bd.Hrows = Hrows; bd.n_rows = n_rows;
+                const int k0 = (kb0 + b) * 64;
+                bd.col0 = seg_col0 + k0;
+                bd.ncols = std::max(0, std::min(64, seg_cols - k0));
+                bd.dst = w_at;
+                pl.blocks.push_back(bd);
+                pl.block_src.push_back(src_id);
+                w_at += (unsigned long long)n_rows * 256;
+            }
+        };
+        const bool hasL = c < pl.nL;
+        const int tileL = hasL ? c / zL : 0, zl = hasL ? c % zL : 0;
+        const int bidx = c - (n_cta - pl.nB);
+        const bool hasB = bidx >= 0;
+        const bool hasD = c < pl.nD;
+        int U = 0, u0 = 0, nrL = 0, ha = 0, hn = 0, ea = 0, en = 0;
+        if (hasL) {
+            U = 4 * gLn[tileL]; u0 = 4 * gL0[tileL]; nrL = 4 * U;
+            kb_range(kbH, zl, zL, ha, hn);
+            kb_range(kbE, zl, zL, ea, en);
+        }
+        // issue order of a step (see the header): A_xt(t) | C_hlang(t) | B(t) | C_hatt(t) | A_hatt(t+1) | C_ctx(t) | D(t) | A_hlang(t+1)
+        if (hasL) add_task(MG_SRC_ATT_IH, nullptr, 1, u0, U, H, nrL, 2 * H, E, ea, en, MG_X_XT, 0, MG_F_COMMIT | MG_F_AXT);
+        if (hasL) add_task(MG_SRC_LANG_HH, nullptr, 1, u0, U, H, nrL, 0, H, ha, hn, MG_X_HLANG_PREV, 1, MG_F_START);
+        if (hasB) {
+            const int tb = bidx / zB, zb = bidx % zB;
+            int a, n;
+            kb_range(kbH, zb, zB, a, n);
+            add_task(MG_SRC_H2ATT, nullptr, 0, 16 * gB0[tb], 0, AH, 16 * gBn[tb], 0, H, a, n, MG_X_HATT, 0, MG_F_START | MG_F_COMMIT);
+            MgJob& jb = ct.job[MG_JOB_B];
+            jb.present = n > 0; jb.set = 0; jb.n_rows = 16 * gBn[tb]; jb.part_off = 16 * gB0[tb]; jb.plane = zb;
+        }
+        if (hasL) add_task(MG_SRC_LANG_IH, nullptr, 1, u0, U, H, nrL, H, H, ha, hn, MG_X_HATT, 1, 0);
+        if (hasL) add_task(MG_SRC_ATT_HH, nullptr, 1, u0, U, H, nrL, 0, H, ha, hn, MG_X_HATT, 0, MG_F_START | MG_F_NEXT);
+        if (hasL) add_task(MG_SRC_LANG_IH, nullptr, 1, u0, U, H, nrL, 0, H, ha, hn, MG_X_CTX, 1, MG_F_COMMIT);
+        if (hasD) {
+            const int td = c / zD, zd = c % zD;
+            int a, n;
+            kb_range(kbH, zd, zD, a, n);
+            add_task(MG_SRC_LOGIT, nullptr, 0, 16 * gD0[td], 0, V1, 16 * gDn[td], 0, H, a, n, MG_X_HLANG, 1, MG_F_START | MG_F_COMMIT);
+            MgJob& jb = ct.job[MG_JOB_D];
+            jb.present = n > 0; jb.set = 1; jb.n_rows = 16 * gDn[td]; jb.part_off = 16 * gD0[td]; jb.plane = zd;
+        }
+        if (hasL) add_task(MG_SRC_ATT_IH, nullptr, 1, u0, U, H, nrL, 0, H, ha, hn, MG_X_HLANG, 0, MG_F_NEXT);
+        ct.n_task = nt;
+        ct.step_bytes = (int)(w_at - ct.w_off);
+        if (hasL) {
+            for (int which = 0; which < 2; ++which) {
+                MgJob& jb = ct.job[which == 0 ? MG_JOB_A : MG_JOB_C];
+                jb.present = 1; jb.set = which; jb.n_rows = nrL;
+                jb.part_off = (tileL * zL + zl) * 16384;
+                jb.tile = tileL; jb.n_split = zL; jb.tile_u0 = u0; jb.tile_units = U;
+                jb.u_lo = zl * U / zL; jb.u_n = (zl + 1) * U / zL - jb.u_lo;
+                jb.part_tile_off = tileL * zL * 16384;
+            }
+        }
+    }
+    pl.w_bytes = w_at;
+    pl.ok = true;
+    return pl;
+}
+
+static size_t mega_table_bytes(const MgPlan& pl) {
+    return align_up(pl.ctas.size() * sizeof(MgCta), 1024) + align_up(pl.blocks.size() * sizeof(MgBlockDesc), 1024);
+}
+
+struct MgScratch {   // per-call device scratch (inside the decode workspace)
+    uint8_t *x_xt, *x_ctx, *x_hatt[2], *x_hlang[2];
+    float *partA, *partC, *partB, *partD;
+    unsigned* sync;
+    size_t zero_bytes;   // bytes from x_xt that must be zero at launch (activation tiles + counters)
+};
+static size_t mega_scratch_bytes(const MgPlan& pl) {
+    size_t b = 0;
+    b += align_up((size_t)pl.kbE * MG_XTILE_BYTES, 1024) + 5 * align_up((size_t)pl.kbH * MG_XTILE_BYTES, 1024) + MG_C_TOTAL * 4;
+    b += 2 * align_up((size_t)pl.nL * 16384 * 4, 1024);
+    b += align_up((size_t)pl.zB * 128 * pl.ldB * 4, 1024) + align_up((size_t)pl.zD * 128 * pl.ldD * 4, 1024);
+    return b + 2048;
+}
+static bool mega_take_scratch(const MgPlan& pl, Workspace& ws, MgScratch& sc) {
+    const size_t xe = align_up((size_t)pl.kbE * MG_XTILE_BYTES, 1024), xh = align_up((size_t)pl.kbH * MG_XTILE_BYTES, 1024);
+    uint8_t* z = ws.take<uint8_t>(xe + 5 * xh + MG_C_TOTAL * 4 + 1024);
+    if (!z) return false;
+    z = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(z), 1024));
+    sc.x_xt = z; sc.x_ctx = z + xe; sc.x_hatt[0] = sc.x_ctx + xh; sc.x_hatt[1] = sc.x_hatt[0] + xh; sc.x_hlang[0] = sc.x_hatt[1] + xh;
+    sc.x_hlang[1] = sc.x_hlang[0] + xh;
+    sc.sync = reinterpret_cast<unsigned*>(sc.x_hlang[1] + xh);
+    sc.zero_bytes = xe + 5 * xh + MG_C_TOTAL * 4;
+    sc.partA = ws.take<float>((size_t)pl.nL * 16384);
+    sc.partC = ws.take<float>((size_t)pl.nL * 16384);
+    sc.partB = ws.take<float>((size_t)pl.zB * 128 * pl.ldB);
+    sc.partD = ws.take<float>((size_t)pl.zD * 128 * pl.ldD);
+    return ws.ok();
+}
+
+static const MgPlan& cached_plan(const subgc_dims* d, int n_cta) {   // the schedule is a pure function of (dims, CTA count)
+    struct Key { int H, E, AH, V1, n; };
+    static thread_local Key key{0, 0, 0, 0, 0};
+    static thread_local MgPlan plan;
+    if (!(key.H == d->rnn && key.E == d->enc && key.AH == d->att_hid && key.V1 == d->vocab1 && key.n == n_cta)) {
+        plan = mega_plan(d, n_cta);
+        key = Key{d->rnn, d->enc, d->att_hid, d->vocab1, n_cta};
+    }
+    return plan;
+}
+
+bool mega_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("SUBGC_MEGA"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on == 1;
+}
+
+size_t mega_decode_scratch_bytes(const subgc_dims* d, const subgc_weights* w) {
+    if (!w || !w->mega || w->mega_ctas <= 0) return 0;
+    const MgPlan& pl = cached_plan(d, w->mega_ctas);
+    return pl.ok ? mega_scratch_bytes(pl) : 0;
+}
+// worst case over CTA counts, for workspace queries that have no weights at hand
+size_t mega_decode_scratch_bytes_max(const subgc_dims* d) {
+    const MgPlan& pl = cached_plan(d, kNumSMs);
+    return pl.ok ? mega_scratch_bytes(pl) + (1u << 20) : 0;
+}
+
+bool mega_decode_eligible(const subgc_dims* d, const subgc_weights* w, int S, int len_max, const float* att_weights) {
+    if (!mega_enabled() || !w || !w->mega || w->mega_ctas <= 0 || att_weights != nullptr) return false;
+    if (S < 1 || S > 128 || S > w->mega_ctas || len_max < 1 || len_max > 64) return false;
+    const MgPlan& pl = cached_plan(d, w->mega_ctas);
+    return pl.ok && w->mega_bytes >= mega_table_bytes(pl) + pl.w_bytes;
+}
+
+// The loop of subgc_decode_sample as one cooperative launch.  fc_pre: [S, 4H] hoisted fc segment + both biases (launch_fc_pre).
+int launch_mega_decode(const subgc_dims* d, const subgc_weights* w, int S, int len_max, int mode, float temp, int top_k, uint64_t seed, uint64_t offset,
+                       const float* uniforms, const float* fc_pre, const float* att, const float* p_att, const float* masks, int64_t* seq,
+                       float* seq_lp, int32_t* steps_done, Workspace& ws, cudaStream_t st) {
+    const MgPlan& pl = cached_plan(d, w->mega_ctas);
+    MgScratch sc;
+    if (!mega_take_scratch(pl, ws, sc)) { set_error("subgc_decode_sample: workspace too small for the persistent decode kernel"); return SUBGC_E_WORKSPACE; }
+    SUBGC_CUDA(cudaMemsetAsync(sc.x_xt, 0, sc.zero_bytes, st));
+    MgParams p;
+    memset(&p, 0, sizeof(p));
+    const uint8_t* mb = static_cast<const uint8_t*>(w->mega);
+    p.ctas = reinterpret_cast<const MgCta*>(mb);
+    p.wstream = mb + mega_table_bytes(pl);
+    p.n_cta = pl.n_cta; p.S = S; p.T = d->seq_length; p.len_max = len_max; p.H = d->rnn; p.E = d->enc; p.AH = d->att_hid; p.V1 = d->vocab1;
+    p.kbH = pl.kbH; p.kbE = pl.kbE; p.nL = pl.nL; p.nB = pl.nB; p.nD = pl.nD; p.zB = pl.zB; p.zD = pl.zD; p.ldB = pl.ldB; p.ldD = pl.ldD;
+    p.fc_pre = fc_pre; p.att = att; p.p_att = p_att; p.masks = masks;
+    p.h2att_b = w->h2att.b; p.alpha_w = w->alpha_net.w; p.alpha_b = w->alpha_net.b; p.logit_b = w->logit.b; p.embed = w->embed;
+    p.lang_b_ih = w->lang_b_ih; p.lang_b_hh = w->lang_b_hh;
+    p.x_xt = sc.x_xt; p.x_ctx = sc.x_ctx; p.x_hatt[0] = sc.x_hatt[0]; p.x_hatt[1] = sc.x_hatt[1]; p.x_hlang[0] = sc.x_hlang[0]; p.x_hlang[1] = sc.x_hlang[1];
+    p.partA = sc.partA; p.partC = sc.partC; p.partB = sc.partB; p.partD = sc.partD; p.sync = sc.sync;
+    p.seq = reinterpret_cast<long long*>(seq); p.seq_lp = seq_lp; p.steps_done = steps_done; p.overflow = w->h3_overflow;
+    p.mode = mode; p.temp = temp; p.top_k = top_k; p.seed = seed; p.offset = offset; p.uniforms = uniforms;
+    static bool seen[64] = {};
+    if (first_use_on_device(seen)) SUBGC_CUDA(cudaFuncSetAttribute(mega_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(pl.n_cta); cfg.blockDim = dim3(MG_THREADS); cfg.dynamicSmemBytes = MG_SMEM; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;   // every CTA must be resident: they wait for each other
+    at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    SUBGC_CUDA(cudaLaunchKernelEx(&cfg, mega_decode_kernel, p));
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}
+
+}  // namespace subgc
+
+using namespace subgc;
+
+extern "C" size_t subgc_mega_pack_bytes(const subgc_dims* d, int n_cta) {
+    if (!d) return 0;
+    const MgPlan& pl = cached_plan(d, n_cta);
+    return pl.ok ? mega_table_bytes(pl) + (size_t)pl.w_bytes : 0;
+}
+
+extern "C" int subgc_mega_pack(const subgc_dims* d, const subgc_weights* w, int n_cta, void* buf, size_t bytes, int32_t* overflow, subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(d && w && buf, "subgc_mega_pack: null argument");
+    const MgPlan& pl = cached_plan(d, n_cta);
+    SUBGC_CHECK_ARG(pl.ok, "subgc_mega_pack: these dimensions are not supported by the persistent decode kernel");
+    const size_t tb = mega_table_bytes(pl);
+    SUBGC_CHECK_ARG(bytes >= tb + pl.w_bytes, "subgc_mega_pack: buffer too small (%zu < %zu)", bytes, tb + (size_t)pl.w_bytes);
+    SUBGC_CHECK_ARG((reinterpret_cast<uintptr_t>(buf) & 1023) == 0, "subgc_mega_pack: buffer must be 1024-byte aligned");
+    const int H = d->rnn, E = d->enc;
+    const float* srcs[6] = {w->att_w_ih, w->att_w_hh, w->lang_w_ih, w->lang_w_hh, w->h2att.w, w->logit.w};
+    const int lds[6] = {E + 2 * H, H, 2 * H, H, H, H};
+    std::vector<MgBlockDesc> blocks = pl.blocks;
+    for (size_t i = 0; i < blocks.size(); ++i) { blocks[i].src = srcs[pl.block_src[i]]; blocks[i].ld = lds[pl.block_src[i]]; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint8_t* b = static_cast<uint8_t*>(buf);
+    const size_t cta_bytes = align_up(pl.ctas.size() * sizeof(MgCta), 1024);
+    // tables: plain (pageable) host memory, so the copies are staged before these calls return
+    SUBGC_CUDA(cudaMemcpyAsync(b, pl.ctas.data(), pl.ctas.size() * sizeof(MgCta), cudaMemcpyHostToDevice, st));
+    SUBGC_CUDA(cudaMemcpyAsync(b + cta_bytes, blocks.data(), blocks.size() * sizeof(MgBlockDesc), cudaMemcpyHostToDevice, st));
+    mega_pack_kernel<<<(unsigned)blocks.size(), 256, 0, st>>>(reinterpret_cast<const MgBlockDesc*>(b + cta_bytes), b + tb, overflow);
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}

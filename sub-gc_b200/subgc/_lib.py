@@ -11,6 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsubgc_b200.so")
 MAX_GCN_LAYERS = 8
+ABI_VERSION = 3   # include/subgc_b200.h: SUBGC_ABI_VERSION (struct layouts below mirror that header)
 
 c_fp = C.c_void_p  # device pointers travel as plain integers
 
@@ -44,6 +45,7 @@ class Weights(C.Structure):
         ("att_w_ih", c_fp), ("att_w_hh", c_fp), ("att_b_ih", c_fp), ("att_b_hh", c_fp),
         ("lang_w_ih", c_fp), ("lang_w_hh", c_fp), ("lang_b_ih", c_fp), ("lang_b_hh", c_fp),
         ("packs", C.POINTER(Packed)), ("n_packs", C.c_int32), ("h3_overflow", c_fp), ("lang_early_w", c_fp),
+        ("mega", c_fp), ("mega_bytes", C.c_uint64), ("mega_ctas", C.c_int32),
     ]
 
 
@@ -64,6 +66,8 @@ SIGNATURES = {
     "subgc_pack_elems": (_sz, [_i, _i, C.POINTER(C.c_int32)]),
     "subgc_pack_weight": (_i, [_i, _i, c_fp, _i, _i, C.POINTER(C.c_int32), c_fp, c_fp, c_fp, c_fp]),
     "subgc_linear_packed_forward": (_i, [_i, _i, _i, c_fp, _i, c_fp, _P(Packed), c_fp, _i, c_fp, _i, c_fp, _sz, c_fp]),
+    "subgc_mega_pack_bytes": (_sz, [_P(Dims), _i]),
+    "subgc_mega_pack": (_i, [_P(Dims), _P(Weights), _i, c_fp, _sz, c_fp, c_fp]),
     "subgc_linear_workspace_bytes": (_sz, [_i, _i, _i]),
     "subgc_linear_forward": (_i, [_i, _i, _i, c_fp, _i, c_fp, c_fp, _i, c_fp, _i, c_fp, _i, c_fp, _sz, c_fp]),
     "subgc_encoder_workspace_bytes": (_sz, [_P(Dims), _i]),
@@ -131,6 +135,9 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
+        if handle.subgc_version() != ABI_VERSION:
+            raise SubgcError(f"{LIB_PATH} has ABI version {handle.subgc_version()}, this package expects {ABI_VERSION}: "
+                             "rebuild it with `python -m subgc.build --force`")
         _lib = handle
     return _lib
 

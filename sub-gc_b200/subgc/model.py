@@ -191,6 +191,7 @@ class TopDownModel(nn.Module):
         self._packs = packing.PackCache()
         self._pack_key = None
         self.use_packed = True   # inference contractions read split-fp16 copies of the weights (subgc.packing)
+        self.use_mega = True     # greedy / top-k loops of <= 128 rows run as one persistent kernel (csrc/mega_decode.cu)
         self._ovf_dev = self._ovf_host = self._ovf_event = None   # fp16-range guard of the split activations (check_numerics)
         self.stage_events = None  # set to [] to collect (name, start_event, end_event) per stage (bench / profiling)
         self.dropout_enabled = True   # tests switch it off: Philox masks cannot match torch's RNG stream (SURVEY §7 hard part 5)
@@ -266,6 +267,7 @@ class TopDownModel(nn.Module):
                 w.h3_overflow = None
                 w.lang_early_w = None
                 self._plans.clear()
+            w.mega, w.mega_bytes, w.mega_ctas = None, 0, 0
             return
         dev = next(iter(params.values())).device
         if self._ovf_dev is None or self._ovf_dev.device != dev:
@@ -293,6 +295,41 @@ class TopDownModel(nn.Module):
             w.packs, w.n_packs = arr, cnt
             self._pack_key = self._packs.array_key
             self._plans.clear()  # captured graphs hold the old packed-copy addresses
+        self._attach_mega(w, params, dev)
+
+    _MEGA_SOURCES = ("core.att_lstm.weight_ih", "core.att_lstm.weight_hh", "core.lang_lstm.weight_ih", "core.lang_lstm.weight_hh",
+                     "core.attention.h2att.weight", "logit.weight")
+
+    def _attach_mega(self, w, params, dev):
+        """Schedule tables + stream pack of the persistent decode kernel (include/subgc_b200.h: subgc_mega_pack), rebuilt when one of
+        the six decoder weight matrices changed.  Dimensions the kernel does not take (or weights beyond the fp16 range) leave
+        w.mega NULL: the decode loop then runs one launch per stage."""
+        if os.environ.get("SUBGC_MEGA", "1") == "0" or not self.use_mega:
+            if w.mega:
+                self._plans.clear()
+            w.mega, w.mega_bytes, w.mega_ctas = None, 0, 0
+            return
+        key = tuple((params[n].data_ptr(), params[n]._version) for n in self._MEGA_SOURCES) + (dev.index,)
+        if getattr(self, "_mega_key", None) != key:
+            L, cd = lib(), self._cdims
+            n_cta = torch.cuda.get_device_properties(dev).multi_processor_count
+            nbytes = int(L.subgc_mega_pack_bytes(C.byref(cd), n_cta))
+            self._mega = None
+            if nbytes:
+                buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+                base = (buf.data_ptr() + 1023) // 1024 * 1024
+                flag = torch.zeros(1, dtype=torch.int32, device=dev)
+                check(L.subgc_mega_pack(C.byref(cd), C.byref(w), n_cta, base, nbytes, ptr(flag), self._stream()), "subgc_mega_pack")
+                if int(flag.item()) == 0:   # one host read at parameter-load time, never inside a decode loop
+                    self._mega = (buf, base, nbytes, n_cta)
+            self._mega_key = key
+            self._plans.clear()
+        if self._mega is None:
+            w.mega, w.mega_bytes, w.mega_ctas = None, 0, 0
+        else:
+            if not w.mega:
+                self._plans.clear()
+            w.mega, w.mega_bytes, w.mega_ctas = self._mega[1], self._mega[2], self._mega[3]
 
     def _arm_overflow_check(self):
         """Queue an asynchronous read-back of the fp16-range flag the split-fp16 kernels raise (no synchronisation here)."""
@@ -316,6 +353,26 @@ class TopDownModel(nn.Module):
             raise _lib.SubgcError("an activation exceeded the fp16 range of the split-fp16 tensor-core path (|x| > 65504): the results of "
                                   "the previous call are invalid.  Packed weights are now disabled for this model (fp32 split-TF32 "
                                   "path); run the call again.")
+
+    def _check_call(self, steps_dev):
+        """Status of the decode call that was just enqueued, read back with ONE small blocking copy: (executed steps, fp16-range
+        flag).  Results of a call whose activations saturated the split-fp16 path are never handed out: the packed path is switched
+        off and None is returned so that the caller repeats the call on the fp32 path (the reference has no such failure mode)."""
+        have_flag = self._ovf_dev is not None and self._wcache is not None and self._wcache[1].n_packs
+        st = torch.cat([steps_dev.view(1), self._ovf_dev.view(1)]) if have_flag else steps_dev.view(1)
+        st_h = st.cpu()
+        steps = int(st_h[0])
+        if steps < 0:
+            raise _lib.SubgcError(f"persistent decode kernel timed out (wait site {(-steps) // 1000}, CTA {(-steps) % 1000 - 1}); "
+                                  "set SUBGC_MEGA=0 to decode with one launch per stage")
+        if have_flag and int(st_h[1]) != 0:
+            import warnings
+            self._ovf_dev.zero_()
+            self.use_packed = False
+            warnings.warn("subgc: an activation exceeded the fp16 range of the split-fp16 tensor-core path (|x| > 65504); "
+                          "repeating the call on the fp32 (split-TF32) path, which this model keeps using from now on")
+            return None
+        return steps
 
     def _train_ops(self):
         from .train import CudaOps
@@ -476,8 +533,11 @@ class TopDownModel(nn.Module):
                                                                                           pred_dist, gpn_obj_ind, plan_kind=kind)
         plan = self._cur_plan
         if beam_size > 1:
-            seq, lps = self._beam(fc, att, p_att, masks, n_rows, len_max, opt, plan)
-            return seq, lps, sub_score, keep_ind
+            res = self._beam(fc, att, p_att, masks, n_rows, len_max, opt, plan)
+            if res is None:   # fp16-range overflow: repeated on the fp32 path (see _check_call)
+                return self._sample(fc_feats, att_feats, att_masks, trip_pred, obj_dist, obj_box, rel_ind, pred_fmap, pred_dist, gpn_obj_ind,
+                                    gpn_pred_ind, gpn_nrel_ind, gpn_pool_mtx, opt)
+            return res[0], res[1], sub_score, keep_ind
         dev = fc.device
         L, w, cd, T = lib(), self._weights(), self._cdims, self.seq_length
         o = plan.out
@@ -509,11 +569,14 @@ class TopDownModel(nn.Module):
 
         plan.run(launch, self.use_graphs)
         self._mark("decode")
-        self._arm_overflow_check()
         self.last_steps = o["steps"]
         seq, lps = o["seq"].clone(), o["lps"].clone()
+        steps = self._check_call(o["steps"])
+        if steps is None:   # an activation left the fp16 range: this call's results are invalid, run it again on the fp32 path
+            return self._sample(fc_feats, att_feats, att_masks, trip_pred, obj_dist, obj_box, rel_ind, pred_fmap, pred_dist, gpn_obj_ind,
+                                gpn_pred_ind, gpn_nrel_ind, gpn_pool_mtx, opt)
         if return_att:
-            return seq, lps, sub_score, keep_ind, o["attw"][:, :int(o["steps"].item())].clone()
+            return seq, lps, sub_score, keep_ind, o["attw"][:, :steps].clone()
         return seq, lps, sub_score, keep_ind
 
     def _beam(self, fc, att, p_att, masks, n_sub, len_max, opt, plan):
@@ -548,7 +611,16 @@ class TopDownModel(nn.Module):
         self._arm_overflow_check()
         # the reference hands back CPU tensors and python lists here (AttModel.py:212-213,229-231)
         seq_h, lps_h, p_h, up_h, cnt_h = o["seq"].cpu(), o["lps"].cpu(), o["p"].cpu(), o["up"].cpu(), o["cnt"].cpu()
-        self.check_numerics(block=True)   # the copies above synchronised already
+        if self._ovf_event is not None:   # the copies above synchronised already
+            self._ovf_event.synchronize()
+            self._ovf_event = None
+            if int(self._ovf_host[0]) != 0:
+                import warnings
+                self._ovf_dev.zero_()
+                self.use_packed = False
+                warnings.warn("subgc: an activation exceeded the fp16 range of the split-fp16 tensor-core path (|x| > 65504); "
+                              "repeating the beam search on the fp32 (split-TF32) path, which this model keeps using from now on")
+                return None
         self.done_beams = [[dict(seq=seq_h[k, j], logps=lps_h[k, j], unaug_p=float(up_h[k, j]), p=float(p_h[k, j]))
                             for j in range(int(cnt_h[k]))] for k in range(n_sub)]
         return seq_h[:, 0].contiguous(), lps_h[:, 0].contiguous()

@@ -36,14 +36,15 @@ def test_library_exports_every_declared_symbol(libpath):
     for name in header_symbols():
         assert hasattr(handle, name), name
     handle.subgc_version.restype = ctypes.c_int
-    assert handle.subgc_version() == 2
+    assert handle.subgc_version() == _lib.ABI_VERSION == 3
 
 
 def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(_lib.Dims) == 17 * 4
     assert ctypes.sizeof(_lib.Linear) == 16
     n_linear = 3 + 2 * 4 * _lib.MAX_GCN_LAYERS + 5 + 6
-    assert ctypes.sizeof(_lib.Weights) == 16 * n_linear + 8 * (3 + 8) + 32   # + packs pointer, n_packs (padded), overflow flag pointer, lang_early_w
+    # + packs pointer, n_packs (padded), overflow flag pointer, lang_early_w, + mega pointer, mega_bytes, mega_ctas (padded)
+    assert ctypes.sizeof(_lib.Weights) == 16 * n_linear + 8 * (3 + 8) + 32 + 24
     assert ctypes.sizeof(_lib.Packed) == 3 * 8 + 8 * 4
     assert ctypes.sizeof(_lib.Layout) == 16
 
