@@ -148,6 +148,8 @@ int subgc_debug_att_trace(unsigned long long* host_out, int n_blocks);
  * [first block start, last block end, first block past its dependency wait, last block past it, 4 kernel-specific marks].
  * op 0 restart slot numbering, op 1 reset stamps, op 2 copy out up to n slots (stamps [n][8], kernel ids [n]); returns slots used */
 int subgc_debug_trace(int op, unsigned long long* stamps, int* ids, int n);
+/* debugging aid (env SUBGC_MEGA_TRACE=1, synchronises): [n_cta][n_steps][48] globaltimer stamps of the last persistent decode launch */
+int subgc_debug_mega_trace(unsigned long long* host_out, int n_cta, int n_steps);
 
 /* Packs an fp32 weight matrix [rows, cols] (leading dim ldw) into the split-fp16 form of subgc_packed, columns cut at
  * seg_col[0..n_seg].  Each output array holds subgc_pack_elems(rows, n_seg, seg_col) fp16 values.  `overflow` (device,

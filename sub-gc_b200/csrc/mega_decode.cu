@@ -29,17 +29,18 @@ namespace subgc {
 // ---- geometry ------------------------------------------------------------------------------------------------------------
 constexpr int MG_THREADS = 640;          // warps 0-3: W producer, X loader, MMA issuer, TMEM owner; warps 4-19: workers
 constexpr int MG_NW = 512;               // worker threads
-constexpr int MG_WSLOTS = 4, MG_WSLOT_BYTES = 36864;   // weight ring: tiles of <= 144 rows x 64 k (hi | lo)
-constexpr int MG_XSLOTS = 2, MG_XTILE_BYTES = 32768;   // activation ring: [128 rows x 64 k] hi | lo
+constexpr int MG_WSLOTS = 3, MG_WSLOT_BYTES = 36864;   // weight ring: tiles of <= 144 rows x 64 k (hi | lo)
+constexpr int MG_XSLOTS = 3, MG_XTILE_BYTES = 32768;   // activation ring: [128 rows x 64 k] hi | lo
 constexpr int MG_SCR_BYTES = 16384;
-constexpr int MG_OFF_X = MG_WSLOTS * MG_WSLOT_BYTES;            // 147456
-constexpr int MG_OFF_SCR = MG_OFF_X + MG_XSLOTS * MG_XTILE_BYTES;   // 212992
-constexpr int MG_OFF_BAR = MG_OFF_SCR + MG_SCR_BYTES;           // 229376
+constexpr int MG_OFF_X = MG_WSLOTS * MG_WSLOT_BYTES;            // 110592
+constexpr int MG_OFF_SCR = MG_OFF_X + MG_XSLOTS * MG_XTILE_BYTES;   // 208896
+constexpr int MG_OFF_BAR = MG_OFF_SCR + MG_SCR_BYTES;           // 225280
 constexpr int MG_SMEM = MG_OFF_BAR + 1024 + 1024;               // + control block + alignment slack
 // TMEM columns of the two accumulator sets (set 0: tiles <= 112 wide, set 1: <= 144) and the offset of the cross-term accumulator
 __host__ __device__ constexpr int mg_set_col(int set) { return set ? 224 : 0; }
 __host__ __device__ constexpr int mg_set_cross(int set) { return set ? 144 : 112; }
 constexpr int MG_MAX_TASKS = 8;
+constexpr int MG_TRACE_EVENTS = 48;   // 0-16 workers, 20 + 2k / 21 + 2k MMA task k (operands landed / issued), 40 producer (step issued)
 constexpr int MG_MAX_TILES = 192;
 
 enum { MG_X_XT = 0, MG_X_CTX = 1, MG_X_HATT = 2, MG_X_HLANG_PREV = 3, MG_X_HLANG = 4 };
@@ -49,7 +50,7 @@ enum { MG_JOB_A = 0, MG_JOB_B = 1, MG_JOB_C = 2, MG_JOB_D = 3 };
 enum { MG_C_XT = 0, MG_C_HATT = 32, MG_C_HLANG = 64, MG_C_CTX = 96, MG_C_B = 128, MG_C_D = 160, MG_C_ABORT = 192, MG_C_TILE_A = 256,
        MG_C_TILE_C = 256 + MG_MAX_TILES, MG_C_UNF = 256 + 2 * MG_MAX_TILES, MG_C_TOTAL = 1024 };
 
-struct MgTask { int n_blk, n_rows, x_src, x_kb0, acc_set, flags, pad0, pad1; };
+struct MgTask { int n_blk, n_rows, x_src, x_kb0, acc_set, flags, rot, pad1; };   // block b covers k-block x_kb0 + (b + rot) % n_blk
 struct MgJob {
     int present, set, n_rows;
     int part_off;      // floats: A/C: this job's [col][128] tile; B/D: first column inside the plane
@@ -80,6 +81,7 @@ struct MgParams {
     unsigned* sync;
     long long* seq; float* seq_lp; int* steps_done; int* overflow;
     int mode; float temp; int top_k; unsigned long long seed, offset; const float* uniforms;
+    unsigned long long* trace;   // debug (SUBGC_MEGA_TRACE=1): [cta][step][MG_TRACE_EVENTS] globaltimer stamps, else nullptr
 };
 
 // ---- PTX helpers local to this kernel ------------------------------------------------------------------------------------------
@@ -98,7 +100,7 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
     return v;
 }
 __device__ __forceinline__ void red_release(unsigned* p, unsigned v) { asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async.global;" ::: "memory"); }   // generic <-> async proxy, global memory
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
@@ -252,6 +254,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
     const uint32_t tmem = ctl->tmem_slot;
     const MgCta& cta = ctl->cta;
     MgWait wt_{ctl, p.sync, globaltimer_ns()};
+#define MG_STAMP(T_, EV_) do { if (p.trace) p.trace[((size_t)cta_id * T + (T_)) * MG_TRACE_EVENTS + (EV_)] = globaltimer_ns(); } while (0)
 
     if (warp == 0) {
         // ===================================================== weight stream producer =====================================================
@@ -276,6 +279,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                         ++cnt;
                     }
                 }
+                MG_STAMP(t, 40);
             }
             // tiles still in flight must land before the CTA may retire (they were requested ahead of a stop)
             if (!alive && ctl->stop == 1)
@@ -313,7 +317,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                         if (cnt >= MG_XSLOTS && !wt_.mbar(&ctl->x_empty[s], ((cnt / MG_XSLOTS) & 1u) ^ 1u, 4)) { alive = false; break; }
                         const uint32_t full = smem_u32(&ctl->x_full[s]);
                         mbar_arrive_expect_tx(full, MG_XTILE_BYTES);
-                        bulk_load(base + MG_OFF_X + s * MG_XTILE_BYTES, xb + (size_t)(tk.x_kb0 + b) * MG_XTILE_BYTES, MG_XTILE_BYTES, full);
+                        bulk_load(base + MG_OFF_X + s * MG_XTILE_BYTES, xb + (size_t)(tk.x_kb0 + (b + tk.rot) % tk.n_blk) * MG_XTILE_BYTES, MG_XTILE_BYTES, full);
                         ++cnt;
                     }
                 }
@@ -327,12 +331,20 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
         // ===================================================== MMA issuer =====================================================
         if (lane == 0) {
             uint32_t wcnt = 0, xcnt = 0, jobs[2] = {0, 0};
+            int drain_set = -1;   // accumulator set whose epilogue is in progress
             bool alive = true;
             for (int t = 0; t < T && alive; ++t) {
                 for (int k = 0; k < cta.n_task && alive; ++k) {
                     const MgTask& tk = cta.task[k];
                     if ((tk.flags & MG_F_NEXT) && t == T - 1) continue;
                     const int set = tk.acc_set;
+                    if (drain_set >= 0) {
+                        // tcgen05.ld of an epilogue runs ~2.5x slower while MMAs write tensor memory (measured): the work issued next is
+                        // never what the hand-off waits for, so it starts once the accumulator has been drained
+                        if (!wt_.mbar(&ctl->acc_free[drain_set], (jobs[drain_set] - 1) & 1u, 14)) { alive = false; break; }
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        drain_set = -1;
+                    }
                     const bool fresh = (tk.flags & MG_F_START) || ((tk.flags & MG_F_AXT) && t == 0);
                     if (fresh && jobs[set] > 0) {   // the workers must have drained the previous accumulator of this set
                         if (!wt_.mbar(&ctl->acc_free[set], (jobs[set] - 1) & 1u, 5)) { alive = false; break; }
@@ -346,6 +358,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                         if (!wt_.mbar(&ctl->w_full[ws], (wcnt / MG_WSLOTS) & 1u, 6)) { alive = false; break; }
                         if (!wt_.mbar(&ctl->x_full[xs], (xcnt / MG_XSLOTS) & 1u, 7)) { alive = false; break; }
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        if (b == 0) MG_STAMP(t, 20 + 2 * k);
                         const uint32_t wa = base + ws * MG_WSLOT_BYTES, xa = base + MG_OFF_X + xs * MG_XTILE_BYTES;
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
@@ -362,7 +375,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                         umma_commit(smem_u32(&ctl->x_empty[xs]));
                         ++wcnt; ++xcnt;
                     }
-                    if (alive && (tk.flags & MG_F_COMMIT)) { umma_commit(smem_u32(&ctl->acc_full[set])); ++jobs[set]; }
+                    if (alive && (tk.flags & MG_F_COMMIT)) { umma_commit(smem_u32(&ctl->acc_full[set])); ++jobs[set]; drain_set = set; }
+                    MG_STAMP(t, 21 + 2 * k);
                 }
             }
             // every MMA issued so far (the early exit leaves next-step work behind) has retired before tensor memory is released
@@ -395,16 +409,17 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
             return ok;
         };
         // everything this CTA's workers wrote becomes visible to whoever acquires the counter afterwards
-        auto w_signal = [&](unsigned* c) {
-            fence_proxy_async_all();
+        auto w_signal = [&](unsigned* c, bool tiles = false) {
+            if (tiles) fence_proxy_async_all();   // activation tiles are read through the async proxy (bulk copies) on the other side
             worker_bar();
-            if (wt == 0) { __threadfence(); red_release(c, 1u); }
+            if (wt == 0) red_release(c, 1u);   // release at gpu scope: cumulative over what the barrier made visible to this thread
         };
         // accumulator -> split-K partial.  col_major: [col][128 rows] (cells read rows of a column), else row-major plane [128][ld]
-        auto epilogue = [&](const MgJob& jb, float* dst, int ld, bool col_major) -> bool {
+        auto epilogue = [&](const MgJob& jb, float* dst, int ld, bool col_major, int t, int ev) -> bool {
             const int set = jb.set;
             if (!w_mbar(&ctl->acc_full[set], epis[set] & 1u, 8)) return false;
             ++epis[set];
+            if (wt == 0) MG_STAMP(t, ev);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int q = ww & 3, g = ww >> 2;
             const int r = q * 32 + lane;
@@ -456,11 +471,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
             if (wt < p.len_max) s_mask[wt] = __ldg(p.masks + (size_t)row * p.len_max + wt);
             // xt(0) = relu(E[<bos> = 0]) (AttModel.py:283-284,332)
             for (int j = wt; j < p.E; j += MG_NW) x_store(p.x_xt, row, j, fmaxf(__ldg(p.embed + j), 0.f), ovf);
-            w_signal(p.sync + MG_C_XT);
+            w_signal(p.sync + MG_C_XT, true);
         }
 
         // LSTM cell on this CTA's share of a tile: gates = sum of the tile's split-K partials (split order) + addend
-        auto cell = [&](const MgJob& jb, const float* part, unsigned* tile_cnt, int t, float (&cst)[2], bool is_att, uint8_t* xout) -> bool {
+        auto cell = [&](const MgJob& jb, const float* part, unsigned* tile_cnt, int t, float (&cst)[2], bool is_att, uint8_t* xout, int ev) -> bool {
             const int nel = 128 * jb.u_n;
             float add[2][4];
 #pragma unroll
@@ -477,6 +492,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                 }
             }
             if (!w_counter(tile_cnt, (unsigned)jb.n_split * (unsigned)(t + 1), 9)) return false;
+            if (wt == 0) MG_STAMP(t, ev);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const int e = wt + k * MG_NW;
@@ -485,9 +501,16 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                 if (r >= S) continue;
                 float acc[4] = {0.f, 0.f, 0.f, 0.f};
                 const float* g = part + jb.part_tile_off + r;
-                for (int z = 0; z < jb.n_split; ++z) {
+                float pz[8][4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) acc[q] += __ldcg(g + (size_t)z * 16384 + (size_t)(q * jb.tile_units + ul) * 128);
+                for (int z = 0; z < 8; ++z) {   // n_split <= 8: every load of the element is in flight before the first add
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) pz[z][q] = z < jb.n_split ? __ldcg(g + (size_t)z * 16384 + (size_t)(q * jb.tile_units + ul) * 128) : 0.f;
+                }
+#pragma unroll
+                for (int z = 0; z < 8; ++z) {   // split order: deterministic
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[q] += pz[z][q];
                 }
                 if (is_att) {
 #pragma unroll
@@ -500,21 +523,27 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                 cst[k] = c;
                 x_store(xout, r, u, sigmoidf_(acc[3]) * tanhf(c), ovf);
             }
+            if (wt == 0) MG_STAMP(t, ev == 3 ? 17 : 19);
             return true;
         };
 
+#define MG_WSTAMP(EV_) do { if (wt == 0) MG_STAMP(t, EV_); } while (0)
         for (int t = 0; t < T && alive; ++t) {
+            MG_WSTAMP(0);
             // ---------------- attention LSTM: gates -> partial -> cell -> h_att(t)
             if (jA.present) {
-                if (!epilogue(jA, p.partA + jA.part_off, 128, true)) break;
+                if (!epilogue(jA, p.partA + jA.part_off, 128, true, t, 1)) break;
                 w_signal(p.sync + MG_C_TILE_A + jA.tile);
-                if (!cell(jA, p.partA, p.sync + MG_C_TILE_A + jA.tile, t, cA, true, p.x_hatt[t & 1])) break;
-                w_signal(p.sync + MG_C_HATT);
+                MG_WSTAMP(2);
+                if (!cell(jA, p.partA, p.sync + MG_C_TILE_A + jA.tile, t, cA, true, p.x_hatt[t & 1], 3)) break;
+                w_signal(p.sync + MG_C_HATT, true);
+                MG_WSTAMP(4);
             }
             // ---------------- h2att partial
             if (jB.present) {
-                if (!epilogue(jB, p.partB + (size_t)jB.plane * 128 * p.ldB + jB.part_off, p.ldB, false)) break;
+                if (!epilogue(jB, p.partB + (size_t)jB.plane * 128 * p.ldB + jB.part_off, p.ldB, false, t, 5)) break;
                 w_signal(p.sync + MG_C_B);
+                MG_WSTAMP(6);
             }
             // ---------------- attention of this CTA's row (AttModel.py:445-471) -> ctx(t)
             if (has_row) {
@@ -536,12 +565,18 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                     }
                     if (i0 == 0) {
                         if (!w_counter(p.sync + MG_C_B, (unsigned)p.nB * (unsigned)(t + 1), 10)) { alive = false; break; }
+                        MG_WSTAMP(7);
                         for (int j = wt; j < AH; j += MG_NW) {
+                            float pz[8];
+#pragma unroll
+                            for (int z = 0; z < 8; ++z) pz[z] = z < p.zB ? __ldcg(p.partB + ((size_t)z * 128 + row) * p.ldB + j) : 0.f;
                             float a = 0.f;
-                            for (int z = 0; z < p.zB; ++z) a += __ldcg(p.partB + ((size_t)z * 128 + row) * p.ldB + j);
+#pragma unroll
+                            for (int z = 0; z < 8; ++z) a += pz[z];
                             s_h[j] = a + __ldg(p.h2att_b + j);
                         }
                         worker_bar();
+                        MG_WSTAMP(41);
                     }
                     const float4* h4 = reinterpret_cast<const float4*>(s_h);
                     const float4* w4 = reinterpret_cast<const float4*>(s_w);
@@ -561,6 +596,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                 }
                 if (!alive) break;
                 worker_bar();
+                MG_WSTAMP(42);
                 if (wt < len_max) {
                     float e = 0.f;
                     for (int q = 0; q < Q; ++q) e += s_sp[wt * Q + q];
@@ -584,12 +620,13 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                     for (int n = lane; n < len_max; n += 32) s_e[n] = s_e[n] / msum;
                 }
                 worker_bar();
+                MG_WSTAMP(43);
                 {   // context: two thread groups take interleaved node subsets, partials combined in fixed order
                     const float* af = p.att + (size_t)row * len_max * H;
                     const int grp = wt >> 8, tg = wt & 255, H4 = H >> 2;
                     for (int j4 = tg; j4 < H4; j4 += 256) {
                         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 6
+#pragma unroll 10
                         for (int n = grp; n < len_max; n += 2) {
                             const float4 v = __ldg(reinterpret_cast<const float4*>(af + (size_t)n * H) + j4);
                             const float wv = s_e[n];
@@ -598,37 +635,48 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                         reinterpret_cast<float4*>(s_c + (size_t)grp * H)[j4] = a;
                     }
                     worker_bar();
+                    MG_WSTAMP(44);
                     for (int j = wt; j < H; j += MG_NW) x_store(p.x_ctx, row, j, s_c[j] + s_c[H + j], ovf);
+                    MG_WSTAMP(18);
                 }
-                w_signal(p.sync + MG_C_CTX);
+                w_signal(p.sync + MG_C_CTX, true);
+                MG_WSTAMP(8);
             }
             // ---------------- language LSTM -> h_lang(t)
             if (jC.present) {
-                if (!epilogue(jC, p.partC + jC.part_off, 128, true)) break;
+                if (!epilogue(jC, p.partC + jC.part_off, 128, true, t, 9)) break;
                 w_signal(p.sync + MG_C_TILE_C + jC.tile);
-                if (!cell(jC, p.partC, p.sync + MG_C_TILE_C + jC.tile, t, cC, false, p.x_hlang[t & 1])) break;
-                w_signal(p.sync + MG_C_HLANG);
+                MG_WSTAMP(10);
+                if (!cell(jC, p.partC, p.sync + MG_C_TILE_C + jC.tile, t, cC, false, p.x_hlang[t & 1], 11)) break;
+                w_signal(p.sync + MG_C_HLANG, true);
+                MG_WSTAMP(12);
             }
             // ---------------- logit partial
             if (jD.present) {
-                if (!epilogue(jD, p.partD + (size_t)jD.plane * 128 * p.ldD + jD.part_off, p.ldD, false)) break;
+                if (!epilogue(jD, p.partD + (size_t)jD.plane * 128 * p.ldD + jD.part_off, p.ldD, false, t, 13)) break;
                 w_signal(p.sync + MG_C_D);
+                MG_WSTAMP(14);
             }
             // ---------------- token selection of this CTA's row (AttModel.py:292-318) -> xt(t+1)
             if (has_row) {
                 if (!w_counter(p.sync + MG_C_D, (unsigned)p.nD * (unsigned)(t + 1), 11)) break;
+                MG_WSTAMP(15);
                 const int V1 = p.V1;
                 float v[MG_SELVALS];
 #pragma unroll
-                for (int i = 0; i < MG_SELVALS; ++i) {
-                    const int j = wt + i * MG_NW;
-                    float a = 0.f;
-                    if (j < V1) {
-                        for (int z = 0; z < p.zD; ++z) a += __ldcg(p.partD + ((size_t)z * 128 + row) * p.ldD + j);
-                        a += __ldg(p.logit_b + j);
-                    }
-                    v[i] = a;
+                for (int i = 0; i < MG_SELVALS; ++i) v[i] = 0.f;
+                for (int z = 0; z < p.zD; ++z) {   // split order; the loads of a plane are all in flight together
+                    const float* pl = p.partD + ((size_t)z * 128 + row) * p.ldD;
+                    float tmp[MG_SELVALS];
+#pragma unroll
+                    for (int i = 0; i < MG_SELVALS; ++i) tmp[i] = (wt + i * MG_NW < V1) ? __ldcg(pl + wt + i * MG_NW) : 0.f;
+#pragma unroll
+                    for (int i = 0; i < MG_SELVALS; ++i) v[i] += tmp[i];
                 }
+#pragma unroll
+                for (int i = 0; i < MG_SELVALS; ++i)
+                    if (wt + i * MG_NW < V1) v[i] += __ldg(p.logit_b + wt + i * MG_NW);
+                MG_WSTAMP(45);
                 float bv = -INFINITY;
                 int bi = 0x7fffffff;
 #pragma unroll
@@ -644,6 +692,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                     if (wt + i * MG_NW < V1) s += expf(v[i] - m);
                 s = workers_sum(s, ctl, wt);
                 const float lz = logf(s);
+                MG_WSTAMP(46);
                 int tok;
                 float lp;
                 if (p.mode == 0) {
@@ -699,7 +748,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                 worker_bar();
                 const float* e = p.embed + (size_t)ctl->s_it * p.E;
                 for (int j = wt; j < p.E; j += MG_NW) x_store(p.x_xt, row, j, fmaxf(__ldg(e + j), 0.f), ovf);
-                w_signal(p.sync + MG_C_XT);
+                MG_WSTAMP(47);
+                w_signal(p.sync + MG_C_XT, true);
+                MG_WSTAMP(16);
             }
         }
         if (ovf && p.overflow) atomicOr(p.overflow, 1);
@@ -829,16 +880,19 @@ static MgPlan mega_plan(const subgc_dims* d, int n_cta) {
         MgCta& ct = pl.ctas[c];
         ct.w_off = w_at;
         int nt = 0;
-        auto add_task = [&](int src_id, const float*, int gate, int r0, int U, int Hrows, int n_rows, int seg_col0, int seg_cols, int kb0, int nkb, int x_src,
+        // CTAs that contract the same k-blocks start at different ones (rot): they would otherwise all ask L2 for the same activation
+        // tile at the same moment
+        auto add_task = [&](int src_id, int rot_seed, int gate, int r0, int U, int Hrows, int n_rows, int seg_col0, int seg_cols, int kb0, int nkb, int x_src,
                             int set, int flags) {
             if (nkb <= 0) return;
             MgTask& tk = ct.task[nt++];
             tk.n_blk = nkb; tk.n_rows = n_rows; tk.x_src = x_src; tk.x_kb0 = kb0; tk.acc_set = set; tk.flags = flags;
+            tk.rot = rot_seed % nkb;
             for (int b = 0; b < nkb; ++b) {
                 MgBlockDesc bd;
                 memset(&bd, 0, sizeof(bd));
                 bd.gate = gate; bd.r0 = r0; bd.U = U; bd.Hrows = Hrows; bd.n_rows = n_rows;
-                const int k0 = (kb0 + b) * 64;
+                const int k0 = (kb0 + (b + tk.rot) % nkb) * 64;
                 bd.col0 = seg_col0 + k0;
                 bd.ncols = std::max(0, std::min(64, seg_cols - k0));
                 bd.dst = w_at;
@@ -859,28 +913,28 @@ static MgPlan mega_plan(const subgc_dims* d, int n_cta) {
             kb_range(kbE, zl, zL, ea, en);
         }
         // issue order of a step (see the header): A_xt(t) | C_hlang(t) | B(t) | C_hatt(t) | A_hatt(t+1) | C_ctx(t) | D(t) | A_hlang(t+1)
-        if (hasL) add_task(MG_SRC_ATT_IH, nullptr, 1, u0, U, H, nrL, 2 * H, E, ea, en, MG_X_XT, 0, MG_F_COMMIT | MG_F_AXT);
-        if (hasL) add_task(MG_SRC_LANG_HH, nullptr, 1, u0, U, H, nrL, 0, H, ha, hn, MG_X_HLANG_PREV, 1, MG_F_START);
+        if (hasL) add_task(MG_SRC_ATT_IH, tileL, 1, u0, U, H, nrL, 2 * H, E, ea, en, MG_X_XT, 0, MG_F_COMMIT | MG_F_AXT);
+        if (hasL) add_task(MG_SRC_LANG_HH, tileL, 1, u0, U, H, nrL, 0, H, ha, hn, MG_X_HLANG_PREV, 1, MG_F_START);
         if (hasB) {
             const int tb = bidx / zB, zb = bidx % zB;
             int a, n;
             kb_range(kbH, zb, zB, a, n);
-            add_task(MG_SRC_H2ATT, nullptr, 0, 16 * gB0[tb], 0, AH, 16 * gBn[tb], 0, H, a, n, MG_X_HATT, 0, MG_F_START | MG_F_COMMIT);
+            add_task(MG_SRC_H2ATT, tb, 0, 16 * gB0[tb], 0, AH, 16 * gBn[tb], 0, H, a, n, MG_X_HATT, 0, MG_F_START | MG_F_COMMIT);
             MgJob& jb = ct.job[MG_JOB_B];
             jb.present = n > 0; jb.set = 0; jb.n_rows = 16 * gBn[tb]; jb.part_off = 16 * gB0[tb]; jb.plane = zb;
         }
-        if (hasL) add_task(MG_SRC_LANG_IH, nullptr, 1, u0, U, H, nrL, H, H, ha, hn, MG_X_HATT, 1, 0);
-        if (hasL) add_task(MG_SRC_ATT_HH, nullptr, 1, u0, U, H, nrL, 0, H, ha, hn, MG_X_HATT, 0, MG_F_START | MG_F_NEXT);
-        if (hasL) add_task(MG_SRC_LANG_IH, nullptr, 1, u0, U, H, nrL, 0, H, ha, hn, MG_X_CTX, 1, MG_F_COMMIT);
+        if (hasL) add_task(MG_SRC_LANG_IH, tileL, 1, u0, U, H, nrL, H, H, ha, hn, MG_X_HATT, 1, 0);
+        if (hasL) add_task(MG_SRC_ATT_HH, tileL, 1, u0, U, H, nrL, 0, H, ha, hn, MG_X_HATT, 0, MG_F_START | MG_F_NEXT);
+        if (hasL) add_task(MG_SRC_LANG_IH, tileL, 1, u0, U, H, nrL, 0, H, ha, hn, MG_X_CTX, 1, MG_F_COMMIT);
         if (hasD) {
             const int td = c / zD, zd = c % zD;
             int a, n;
             kb_range(kbH, zd, zD, a, n);
-            add_task(MG_SRC_LOGIT, nullptr, 0, 16 * gD0[td], 0, V1, 16 * gDn[td], 0, H, a, n, MG_X_HLANG, 1, MG_F_START | MG_F_COMMIT);
+            add_task(MG_SRC_LOGIT, td, 0, 16 * gD0[td], 0, V1, 16 * gDn[td], 0, H, a, n, MG_X_HLANG, 1, MG_F_START | MG_F_COMMIT);
             MgJob& jb = ct.job[MG_JOB_D];
             jb.present = n > 0; jb.set = 1; jb.n_rows = 16 * gDn[td]; jb.part_off = 16 * gD0[td]; jb.plane = zd;
         }
-        if (hasL) add_task(MG_SRC_ATT_IH, nullptr, 1, u0, U, H, nrL, 0, H, ha, hn, MG_X_HLANG, 0, MG_F_NEXT);
+        if (hasL) add_task(MG_SRC_ATT_IH, tileL, 1, u0, U, H, nrL, 0, H, ha, hn, MG_X_HLANG, 0, MG_F_NEXT);
         ct.n_task = nt;
         ct.step_bytes = (int)(w_at - ct.w_off);
         if (hasL) {
@@ -943,6 +997,19 @@ static const MgPlan& cached_plan(const subgc_dims* d, int n_cta) {   // the sche
     return plan;
 }
 
+// debug (SUBGC_MEGA_TRACE=1): per-CTA, per-step time stamps of the most recent launch, read back by subgc_debug_mega_trace
+static unsigned long long* mega_trace_buffer(size_t* elems) {
+    static unsigned long long* buf = nullptr;
+    static int on = -1;
+    static const size_t n = (size_t)256 * 32 * MG_TRACE_EVENTS;
+    if (on < 0) {
+        on = getenv("SUBGC_MEGA_TRACE") != nullptr ? 1 : 0;
+        if (on) { cudaMalloc(&buf, n * sizeof(unsigned long long)); cudaMemset(buf, 0, n * sizeof(unsigned long long)); }
+    }
+    if (elems) *elems = n;
+    return buf;
+}
+
 bool mega_enabled() {
     static int on = -1;
     if (on < 0) { const char* e = getenv("SUBGC_MEGA"); on = (e && e[0] == '0') ? 0 : 1; }
@@ -989,6 +1056,7 @@ int launch_mega_decode(const subgc_dims* d, const subgc_weights* w, int S, int l
     p.partA = sc.partA; p.partC = sc.partC; p.partB = sc.partB; p.partD = sc.partD; p.sync = sc.sync;
     p.seq = reinterpret_cast<long long*>(seq); p.seq_lp = seq_lp; p.steps_done = steps_done; p.overflow = w->h3_overflow;
     p.mode = mode; p.temp = temp; p.top_k = top_k; p.seed = seed; p.offset = offset; p.uniforms = uniforms;
+    p.trace = (pl.n_cta <= 256 && d->seq_length <= 32) ? mega_trace_buffer(nullptr) : nullptr;
     static bool seen[64] = {};
     if (first_use_on_device(seen)) SUBGC_CUDA(cudaFuncSetAttribute(mega_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM));
     cudaLaunchConfig_t cfg = {};
@@ -1005,6 +1073,14 @@ int launch_mega_decode(const subgc_dims* d, const subgc_weights* w, int S, int l
 }  // namespace subgc
 
 using namespace subgc;
+
+extern "C" int subgc_debug_mega_trace(unsigned long long* host_out, int n_cta, int n_steps) {
+    size_t n = 0;
+    unsigned long long* buf = mega_trace_buffer(&n);
+    if (!buf || !host_out || (size_t)n_cta * n_steps * MG_TRACE_EVENTS > n) return SUBGC_E_INVALID;
+    cudaDeviceSynchronize();
+    return cudaMemcpy(host_out, buf, (size_t)n_cta * n_steps * MG_TRACE_EVENTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess ? SUBGC_OK : SUBGC_E_CUDA;
+}
 
 extern "C" size_t subgc_mega_pack_bytes(const subgc_dims* d, int n_cta) {
     if (!d) return 0;

@@ -63,6 +63,7 @@ SIGNATURES = {
     "subgc_launch_count": (C.c_ulonglong, []),
     "subgc_debug_att_trace": (_i, [c_fp, _i]),
     "subgc_debug_trace": (_i, [_i, c_fp, c_fp, _i]),
+    "subgc_debug_mega_trace": (_i, [c_fp, _i, _i]),
     "subgc_pack_elems": (_sz, [_i, _i, C.POINTER(C.c_int32)]),
     "subgc_pack_weight": (_i, [_i, _i, c_fp, _i, _i, C.POINTER(C.c_int32), c_fp, c_fp, c_fp, c_fp]),
     "subgc_linear_packed_forward": (_i, [_i, _i, _i, c_fp, _i, c_fp, _P(Packed), c_fp, _i, c_fp, _i, c_fp, _sz, c_fp]),

@@ -1,0 +1,60 @@
+"""Timeline of the persistent decode kernel (SUBGC_MEGA_TRACE=1): per step, when each hand-off happens (globaltimer stamps written by
+worker thread 0 / the MMA thread / the producer of every CTA).   python tools/mega_timeline.py [n_images] [step]"""
+import os, sys, ctypes as C
+os.environ["SUBGC_MEGA_TRACE"] = "1"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "sub-gc_b200"))
+import numpy as np
+import torch
+from subgc import synth, _lib
+from subgc.config import Dims, make_opt
+from subgc.model import setup
+
+n_images = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+step = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+d = Dims()
+m = setup(make_opt(d, test_LSTM=1, gpn_nms_thres=0.75, gpn_max_subg=1))
+m.load_state_dict(synth.make_state_dict(d, 2019)); m.cuda().eval()
+data = synth.make_test_inputs(d, 2019, n_images=n_images, per_half=1, ragged=False, ragged_edges=False)
+args = [data[k].cuda() if data[k] is not None else None for k in synth.SAMPLE_ARG_ORDER]
+with torch.no_grad():
+    for _ in range(5):
+        m(*args, opt={"beam_size": 1}, mode="sample")
+torch.cuda.synchronize()
+n_cta = torch.cuda.get_device_properties(0).multi_processor_count
+T, EV = d.seq_length, 48
+buf = (C.c_ulonglong * (n_cta * T * EV))()
+_lib.check(_lib.lib().subgc_debug_mega_trace(buf, n_cta, T), "trace")
+a = np.array(buf, dtype=np.float64).reshape(n_cta, T, EV)
+a[a == 0] = np.nan
+names = {0: "step begins (workers)", 1: "acc A complete", 2: "partial A published", 3: "tile A partials complete", 4: "h_att published",
+         5: "acc B complete", 6: "partial B published", 7: "all B partials seen (attention)", 8: "ctx published", 9: "acc C complete",
+         10: "partial C published", 11: "tile C partials complete", 12: "h_lang published", 13: "acc D complete", 14: "partial D published",
+         15: "all D partials seen (select)", 16: "xt published", 40: "producer: step issued",
+         17: "  cell A computed + stored", 19: "  cell C computed + stored", 41: "  atth reduced", 42: "  scores done", 43: "  softmax done",
+         44: "  ctx partials done", 18: "  ctx stored", 45: "  logits loaded", 46: "  argmax + lse done", 47: "  xt stored"}
+tasks = ["A_xt", "C_hlang", "B", "C_hatt", "A_hatt+", "C_ctx", "D", "A_hlang+"]
+t0 = np.nanmin(a[:, step, 0])
+print(f"step {step} of {T}; us relative to the first CTA entering the step; min / median / max over CTAs")
+rows = []
+for ev in sorted(names):
+    v = (a[:, step, ev] - t0) / 1e3
+    if np.all(np.isnan(v)):
+        continue
+    rows.append((np.nanmedian(v), f"  {names[ev]:36s} {np.nanmin(v):8.2f} {np.nanmedian(v):8.2f} {np.nanmax(v):8.2f}   (n={int(np.sum(~np.isnan(v)))})"))
+# MMA tasks: the task index differs between CTAs that have / have not a B task; report by CTA class
+for cls, sel in (("CTAs without B", np.isnan(a[:, step, 5])), ("CTAs with B", ~np.isnan(a[:, step, 5]))):
+    if not sel.any():
+        continue
+    for k in range(8):
+        v0 = (a[sel, step, 20 + 2 * k] - t0) / 1e3
+        v1 = (a[sel, step, 21 + 2 * k] - t0) / 1e3
+        if np.all(np.isnan(v0)):
+            continue
+        rows.append((np.nanmedian(v0), f"  MMA task {k} [{cls}] operands landed   {np.nanmin(v0):8.2f} {np.nanmedian(v0):8.2f} {np.nanmax(v0):8.2f}"))
+        rows.append((np.nanmedian(v1), f"  MMA task {k} [{cls}] issued            {np.nanmin(v1):8.2f} {np.nanmedian(v1):8.2f} {np.nanmax(v1):8.2f}"))
+for _, line in sorted(rows, key=lambda r: r[0]):
+    print(line)
+per_step = (np.nanmax(a[:, 1:, 16], axis=0) - np.nanmax(a[:, :-1, 16], axis=0)) / 1e3
+print("step time (xt published -> next xt published), us:", np.array2string(per_step, precision=1))
+print("kernel span us:", (np.nanmax(a[:, T - 1, 16]) - np.nanmin(a[:, 0, 0])) / 1e3)
