@@ -199,6 +199,12 @@ size_t subgc_encoder_workspace_bytes(const subgc_dims* d, int n_images);
 int subgc_fuse_nodes(const subgc_dims* d, const subgc_weights* w, int n_images, const float* att_feats,
                      const float* obj_dist, const float* pred_dist, float* x0, float* p0 /*nullable*/,
                      void* ws, size_t ws_bytes, subgc_stream_t stream);
+/* Same fusion with the class ids already known (loader-side input compaction): obj_cls [n_images, N] = 1 + argmax_first(
+ * obj_dist[:, :, 1:]) and pred_cls [n_images, K] (nullable with p0) as int64, i.e. what AttModel.py:374,382-385 derives from the score
+ * tensors the loaders ship (dataloaders/dataloader_test.py:234-273) -- 30 MB of fp32 scores per 128 images become 9.5 KB of ids. */
+int subgc_fuse_nodes_cls(const subgc_dims* d, const subgc_weights* w, int n_images, const float* att_feats,
+                         const int64_t* obj_cls, const int64_t* pred_cls /*nullable*/, float* x0, float* p0 /*nullable*/,
+                         void* ws, size_t ws_bytes, subgc_stream_t stream);
 int subgc_gcn_forward(const subgc_dims* d, const subgc_weights* w, int n_images, const float* x0,
                       const float* p0 /*nullable iff not needed*/, const int64_t* rel_ind, float* x_obj,
                       float* x_pred /*nullable*/, void* ws, size_t ws_bytes, subgc_stream_t stream);

@@ -213,27 +213,28 @@ extern "C" int subgc_gcn_needs_pred(const subgc_dims* d, int want_x_pred) {
     return np[0] ? 1 : 0;
 }
 
-extern "C" int subgc_fuse_nodes(const subgc_dims* d, const subgc_weights* w, int n_images, const float* att_feats, const float* obj_dist,
-                                const float* pred_dist, float* x0, float* p0, void* ws_, size_t ws_bytes, subgc_stream_t stream) {
-    SUBGC_TRY(check_dims(d));
-    SUBGC_CHECK_ARG(w && att_feats && obj_dist && x0 && n_images > 0, "subgc_fuse_nodes: null argument");
-    SUBGC_CHECK_ARG(p0 == nullptr || pred_dist != nullptr, "subgc_fuse_nodes: p0 requested without pred_dist");
-    SUBGC_CHECK_ARG(d->pred_emb_type == 1 || d->pred_emb_type == 2, "subgc_fuse_nodes: pred_emb_type must be 1 or 2");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+// obj_cls / pred_cls (nullable, int64 device): class ids computed by the caller (loader-side compaction); when null they are taken
+// from the score tensors here
+static int fuse_nodes_impl(const subgc_dims* d, const subgc_weights* w, int n_images, const float* att_feats, const float* obj_dist,
+                           const float* pred_dist, const long long* obj_cls, const long long* pred_cls, float* x0, float* p0, void* ws_,
+                           size_t ws_bytes, cudaStream_t st) {
     Workspace ws(ws_, ws_bytes);
     const int rows_n = n_images * d->obj_num, rows_k = n_images * d->rel_num;
     long long* cls = ws.take<long long>(rows_n);
     long long* pcls = ws.take<long long>(rows_k);
     if (!ws.ok()) { set_error("subgc_fuse_nodes: workspace too small"); return SUBGC_E_WORKSPACE; }
-    class_argmax_kernel<<<(rows_n + 7) / 8, 256, 0, st>>>(obj_dist, rows_n, d->obj_classes, 1, cls);
-    SUBGC_LAUNCH_CHECK();
+    if (!obj_cls) {
+        class_argmax_kernel<<<(rows_n + 7) / 8, 256, 0, st>>>(obj_dist, rows_n, d->obj_classes, 1, cls);
+        SUBGC_LAUNCH_CHECK();
+        obj_cls = cls;
+    }
     {
         GemmProblem p;
         p.wts = w;
         p.M = rows_n; p.N = d->gcn; p.nseg = 2;
         p.seg[0] = make_seg(att_feats, d->att_feat, w->obj_v_proj.w, d->att_feat, d->att_feat);
         p.seg[1] = make_seg(w->sg_obj_embed, d->embed, w->obj_emb_proj.w, d->embed, d->embed);
-        p.seg[1].gather = cls;
+        p.seg[1].gather = obj_cls;
         p.epi.bias = w->obj_v_proj.b;
         p.epi.bias2 = w->obj_emb_proj.b;
         p.epi.relu = 1;
@@ -241,18 +242,39 @@ extern "C" int subgc_fuse_nodes(const subgc_dims* d, const subgc_weights* w, int
         SUBGC_TRY(launch_gemm(p, ws.cursor(), ws.remaining(), st));
     }
     if (p0) {
-        class_argmax_kernel<<<(rows_k + 7) / 8, 256, 0, st>>>(pred_dist, rows_k, d->pred_classes, d->pred_emb_type == 1 ? 1 : 0, pcls);
-        SUBGC_LAUNCH_CHECK();
+        if (!pred_cls) {
+            class_argmax_kernel<<<(rows_k + 7) / 8, 256, 0, st>>>(pred_dist, rows_k, d->pred_classes, d->pred_emb_type == 1 ? 1 : 0, pcls);
+            SUBGC_LAUNCH_CHECK();
+            pred_cls = pcls;
+        }
         GemmProblem p;
         p.wts = w;
         p.M = rows_k; p.N = d->gcn; p.nseg = 1;
         p.seg[0] = make_seg(w->sg_pred_embed, d->embed, w->pred_emb_prj.w, d->embed, d->embed);
-        p.seg[0].gather = pcls;
+        p.seg[0].gather = pred_cls;
         p.epi.bias = w->pred_emb_prj.b;
         p.C = p0; p.ldc = d->gcn;
         SUBGC_TRY(launch_gemm(p, ws.cursor(), ws.remaining(), st));
     }
     return SUBGC_OK;
+}
+
+extern "C" int subgc_fuse_nodes(const subgc_dims* d, const subgc_weights* w, int n_images, const float* att_feats, const float* obj_dist,
+                                const float* pred_dist, float* x0, float* p0, void* ws_, size_t ws_bytes, subgc_stream_t stream) {
+    SUBGC_TRY(check_dims(d));
+    SUBGC_CHECK_ARG(w && att_feats && obj_dist && x0 && n_images > 0, "subgc_fuse_nodes: null argument");
+    SUBGC_CHECK_ARG(p0 == nullptr || pred_dist != nullptr, "subgc_fuse_nodes: p0 requested without pred_dist");
+    SUBGC_CHECK_ARG(d->pred_emb_type == 1 || d->pred_emb_type == 2, "subgc_fuse_nodes: pred_emb_type must be 1 or 2");
+    return fuse_nodes_impl(d, w, n_images, att_feats, obj_dist, pred_dist, nullptr, nullptr, x0, p0, ws_, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int subgc_fuse_nodes_cls(const subgc_dims* d, const subgc_weights* w, int n_images, const float* att_feats, const int64_t* obj_cls,
+                                    const int64_t* pred_cls, float* x0, float* p0, void* ws_, size_t ws_bytes, subgc_stream_t stream) {
+    SUBGC_TRY(check_dims(d));
+    SUBGC_CHECK_ARG(w && att_feats && obj_cls && x0 && n_images > 0, "subgc_fuse_nodes_cls: null argument");
+    SUBGC_CHECK_ARG(p0 == nullptr || pred_cls != nullptr, "subgc_fuse_nodes_cls: p0 requested without pred_cls");
+    return fuse_nodes_impl(d, w, n_images, att_feats, nullptr, nullptr, reinterpret_cast<const long long*>(obj_cls),
+                           reinterpret_cast<const long long*>(pred_cls), x0, p0, ws_, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int subgc_gcn_forward(const subgc_dims* d, const subgc_weights* w, int n_images, const float* x0, const float* p0,

@@ -154,6 +154,14 @@ struct MgWait {
             if ((it & 255u) == 0 && expired(site)) return false;
         }
     }
+    __device__ __forceinline__ bool counter_masked(const unsigned* c, unsigned target, unsigned mask, int site, unsigned& out) {
+        for (uint32_t it = 1;; ++it) {
+            const unsigned v = ld_acquire(c);
+            if ((v & mask) >= target) { out = v; return true; }
+            if (ctl->stop) return false;
+            if ((it & 255u) == 0 && expired(site)) return false;
+        }
+    }
     __device__ __forceinline__ bool counter(const unsigned* c, unsigned target, int site) {
         for (uint32_t it = 1;; ++it) {
             if (ld_acquire(c) >= target) return true;
@@ -292,25 +300,37 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
             uint32_t cnt = 0;
             bool alive = true;
             int steps = T + 1;   // executed steps as the reference counts them (AttModel.py:312-314)
+            // last value seen of every counter: a dependency that is known to be satisfied costs no further L2 round trip.
+            // MG_C_XT packs two counts: bits 0-15 rows whose xt is published, bits 16+ rows still unfinished, summed over the steps
+            unsigned seen_xt = 0, seen_ctx = 0, seen_hatt = 0, seen_hlang = 0, unf_before = 0;
+            auto need = [&](const unsigned* c, unsigned& seen, unsigned target, unsigned mask, int site) -> bool {
+                while ((seen & mask) < target) {
+                    unsigned v = 0;
+                    if (!wt_.counter_masked(c, target, mask, site, v)) return false;
+                    seen = v;
+                }
+                return true;
+            };
             for (int t = 0; t < T && alive; ++t) {
+                if (!need(p.sync + MG_C_XT, seen_xt, (unsigned)S * (unsigned)(t + 1), 0xffffu, 2)) { alive = false; break; }
                 if (t >= 1) {   // xt(t) complete <=> every row's selection of step t-1 is done: the all-finished early exit is decided here
-                    if (!wt_.counter(p.sync + MG_C_XT, (unsigned)S * (unsigned)(t + 1), 2)) { alive = false; break; }
-                    if (ld_acquire(p.sync + MG_C_UNF + (t - 1)) == 0) { ctl->stop = 1; steps = t; alive = false; break; }
+                    const unsigned unf = seen_xt >> 16;
+                    if (unf == unf_before) { ctl->stop = 1; steps = t; alive = false; break; }
+                    unf_before = unf;
                 }
                 for (int k = 0; k < cta.n_task && alive; ++k) {
                     const MgTask& tk = cta.task[k];
                     if ((tk.flags & MG_F_NEXT) && t == T - 1) continue;
                     const uint8_t* xb;
-                    const unsigned* c;
-                    unsigned target;
+                    bool ok = true;
                     switch (tk.x_src) {
-                        case MG_X_XT: xb = p.x_xt; c = p.sync + MG_C_XT; target = (unsigned)S * (unsigned)(t + 1); break;
-                        case MG_X_CTX: xb = p.x_ctx; c = p.sync + MG_C_CTX; target = (unsigned)S * (unsigned)(t + 1); break;
-                        case MG_X_HATT: xb = p.x_hatt[t & 1]; c = p.sync + MG_C_HATT; target = (unsigned)p.nL * (unsigned)(t + 1); break;
-                        case MG_X_HLANG_PREV: xb = p.x_hlang[(t + 1) & 1]; c = p.sync + MG_C_HLANG; target = (unsigned)p.nL * (unsigned)t; break;
-                        default: xb = p.x_hlang[t & 1]; c = p.sync + MG_C_HLANG; target = (unsigned)p.nL * (unsigned)(t + 1); break;
+                        case MG_X_XT: xb = p.x_xt; break;   // checked at the top of the step
+                        case MG_X_CTX: xb = p.x_ctx; ok = need(p.sync + MG_C_CTX, seen_ctx, (unsigned)S * (unsigned)(t + 1), ~0u, 3); break;
+                        case MG_X_HATT: xb = p.x_hatt[t & 1]; ok = need(p.sync + MG_C_HATT, seen_hatt, (unsigned)p.nL * (unsigned)(t + 1), ~0u, 3); break;
+                        case MG_X_HLANG_PREV: xb = p.x_hlang[(t + 1) & 1]; ok = need(p.sync + MG_C_HLANG, seen_hlang, (unsigned)p.nL * (unsigned)t, ~0u, 3); break;
+                        default: xb = p.x_hlang[t & 1]; ok = need(p.sync + MG_C_HLANG, seen_hlang, (unsigned)p.nL * (unsigned)(t + 1), ~0u, 3); break;
                     }
-                    if (target > 0 && !wt_.counter(c, target, 3)) { alive = false; break; }
+                    if (!ok) { alive = false; break; }
                     fence_proxy_async_all();   // the tiles were written with generic stores by other SMs; the bulk copies below read them
                     for (int b = 0; b < tk.n_blk; ++b) {
                         const uint32_t s = cnt % MG_XSLOTS;
@@ -323,7 +343,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                 }
             }
             if (cta_id == 0 && ctl->stop != 2) {
-                if (alive && wt_.counter(p.sync + MG_C_XT, (unsigned)S * (unsigned)(T + 1), 13) && ld_acquire(p.sync + MG_C_UNF + (T - 1)) == 0) steps = T;
+                if (alive && need(p.sync + MG_C_XT, seen_xt, (unsigned)S * (unsigned)(T + 1), 0xffffu, 13) && (seen_xt >> 16) == unf_before) steps = T;
                 if (ctl->stop != 2) p.steps_done[0] = steps;
             }
         }
@@ -409,10 +429,10 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
             return ok;
         };
         // everything this CTA's workers wrote becomes visible to whoever acquires the counter afterwards
-        auto w_signal = [&](unsigned* c, bool tiles = false) {
+        auto w_signal = [&](unsigned* c, bool tiles = false, unsigned inc = 1u) {
             if (tiles) fence_proxy_async_all();   // activation tiles are read through the async proxy (bulk copies) on the other side
             worker_bar();
-            if (wt == 0) red_release(c, 1u);   // release at gpu scope: cumulative over what the barrier made visible to this thread
+            if (wt == 0) red_release(c, inc);   // release at gpu scope: cumulative over what the barrier made visible to this thread
         };
         // accumulator -> split-K partial.  col_major: [col][128 rows] (cells read rows of a column), else row-major plane [128][ld]
         auto epilogue = [&](const MgJob& jb, float* dst, int ld, bool col_major, int t, int ev) -> bool {
@@ -665,13 +685,17 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                 float v[MG_SELVALS];
 #pragma unroll
                 for (int i = 0; i < MG_SELVALS; ++i) v[i] = 0.f;
-                for (int z = 0; z < p.zD; ++z) {   // split order; the loads of a plane are all in flight together
+                for (int z = 0; z < p.zD; z += 2) {   // split order; the loads of two planes are in flight together
                     const float* pl = p.partD + ((size_t)z * 128 + row) * p.ldD;
-                    float tmp[MG_SELVALS];
+                    const float* pl1 = pl + (size_t)128 * p.ldD;
+                    const bool two = z + 1 < p.zD;
+                    float tmp[MG_SELVALS], tmp1[MG_SELVALS];
 #pragma unroll
                     for (int i = 0; i < MG_SELVALS; ++i) tmp[i] = (wt + i * MG_NW < V1) ? __ldcg(pl + wt + i * MG_NW) : 0.f;
 #pragma unroll
-                    for (int i = 0; i < MG_SELVALS; ++i) v[i] += tmp[i];
+                    for (int i = 0; i < MG_SELVALS; ++i) tmp1[i] = (two && wt + i * MG_NW < V1) ? __ldcg(pl1 + wt + i * MG_NW) : 0.f;
+#pragma unroll
+                    for (int i = 0; i < MG_SELVALS; ++i) v[i] = (v[i] + tmp[i]) + tmp1[i];
                 }
 #pragma unroll
                 for (int i = 0; i < MG_SELVALS; ++i)
@@ -742,14 +766,13 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                     const long long it = unf ? tok : 0;
                     p.seq[(size_t)row * T + t] = it;
                     p.seq_lp[(size_t)row * T + t] = lp;
-                    if (unf) atomicAdd(p.sync + MG_C_UNF + t, 1u);
                     ctl->s_it = (int)it;
                 }
                 worker_bar();
                 const float* e = p.embed + (size_t)ctl->s_it * p.E;
                 for (int j = wt; j < p.E; j += MG_NW) x_store(p.x_xt, row, j, fmaxf(__ldg(e + j), 0.f), ovf);
                 MG_WSTAMP(47);
-                w_signal(p.sync + MG_C_XT, true);
+                w_signal(p.sync + MG_C_XT, true, 1u + (unfinished ? 0x10000u : 0u));   // only worker thread 0 uses the increment
                 MG_WSTAMP(16);
             }
         }

@@ -73,6 +73,7 @@ SIGNATURES = {
     "subgc_linear_forward": (_i, [_i, _i, _i, c_fp, _i, c_fp, c_fp, _i, c_fp, _i, c_fp, _i, c_fp, _sz, c_fp]),
     "subgc_encoder_workspace_bytes": (_sz, [_P(Dims), _i]),
     "subgc_fuse_nodes": (_i, [_P(Dims), _P(Weights), _i, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, _sz, c_fp]),
+    "subgc_fuse_nodes_cls": (_i, [_P(Dims), _P(Weights), _i, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, _sz, c_fp]),
     "subgc_gcn_forward": (_i, [_P(Dims), _P(Weights), _i, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, _sz, c_fp]),
     "subgc_gcn_needs_pred": (_i, [_P(Dims), _i]),
     "subgc_sgpn_workspace_bytes": (_sz, [_P(Dims), _i]),

@@ -3,7 +3,9 @@
     python -m subgc.build [--force]
 
 The library sits next to this file so that it travels with the repository snapshot to the GPU box; it is
-git-ignored.  A content hash of the sources + flags is stored beside it and the build is skipped when unchanged.
+git-ignored, and so is the stamp beside it (a content hash of the sources + flags over repo-relative paths): a checkout
+never carries a stamp that vouches for somebody else's binary.  The build is skipped when library and stamp match the
+sources; `subgc._lib.lib()` additionally refuses a library whose ABI version differs from the binding's.
 """
 from __future__ import annotations
 
@@ -31,7 +33,7 @@ def _digest():
     files = _sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
     files += [os.path.join(INCLUDE, f) for f in sorted(os.listdir(INCLUDE))]
     for f in files:
-        h.update(f.encode())
+        h.update(os.path.relpath(f, ROOT).encode())   # repo-relative: the digest does not depend on where the checkout lives
         with open(f, "rb") as fh:
             h.update(fh.read())
     return h.hexdigest()
@@ -43,9 +45,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return OUT
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
-        if os.path.isfile(OUT):  # GPU box without a toolkit: use the library that travelled with the snapshot
+        # box without a toolkit: only a library whose stamp matches these sources may be used (it travelled with the snapshot)
+        if os.path.isfile(OUT) and os.path.isfile(STAMP) and open(STAMP).read().strip() == digest:
             return OUT
-        raise RuntimeError("nvcc not found and no prebuilt libsubgc_b200.so present")
+        raise RuntimeError("nvcc not found and no libsubgc_b200.so built from these sources is present")
     cmd = [nvcc] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-I", CSRC, "-o", OUT] + _sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

@@ -414,12 +414,15 @@ class TopDownModel(nn.Module):
     # ------------------------------------------------------------------------------------------------------------
     # stages (each one is one C-ABI call)
     # ------------------------------------------------------------------------------------------------------------
-    def encode(self, att_feats, obj_dist, pred_dist, rel_ind, want_x_pred=False):
+    def encode(self, att_feats, obj_dist, pred_dist, rel_ind, want_x_pred=False, obj_cls=None, pred_cls=None):
         """feat_fusion + gcn_backbone (reference models/AttModel.py:370-387, models/lib/gcn_backbone.py:29-53) WITHOUT the x5
-        replication.  Returns x_obj [B,N,L] (and x_pred [B,K,L] when asked)."""
-        dev = self._check_device(att_feats, obj_dist, pred_dist, rel_ind)
+        replication.  Returns x_obj [B,N,L] (and x_pred [B,K,L] when asked).  obj_cls / pred_cls (int64 [B,N] / [B,K]): class ids
+        known from the loader (subgc.compact) instead of the score tensors."""
+        dev = self._check_device(att_feats, obj_dist, pred_dist, rel_ind, obj_cls, pred_cls)
         L, d, w, cd = lib(), self.dims, self._weights(), self._cdims
-        att_feats, obj_dist, rel_ind = self._f32(att_feats), self._f32(obj_dist), self._i64(rel_ind)
+        att_feats, rel_ind = self._f32(att_feats), self._i64(rel_ind)
+        if obj_cls is None:
+            obj_dist = self._f32(obj_dist)
         B = att_feats.shape[0]
         need_pred = bool(L.subgc_gcn_needs_pred(C.byref(cd), int(want_x_pred)))
         x0 = torch.empty(B, d.obj_num, d.gcn, device=dev)
@@ -429,20 +432,28 @@ class TopDownModel(nn.Module):
         wsb = L.subgc_encoder_workspace_bytes(C.byref(cd), B)
         ws = self._ws.get(wsb, dev)
         st = self._stream()
-        pd = self._f32(pred_dist) if need_pred else None
-        check(L.subgc_fuse_nodes(C.byref(cd), C.byref(w), B, ptr(att_feats), ptr(obj_dist), ptr(pd), ptr(x0), ptr(p0), ptr(ws),
-                                 ws.numel(), st), "subgc_fuse_nodes")
+        if obj_cls is not None:
+            if need_pred and pred_cls is None:
+                raise _lib.SubgcError("this configuration needs the predicate classes (compact_batch(..., with_pred=True))")
+            check(L.subgc_fuse_nodes_cls(C.byref(cd), C.byref(w), B, ptr(att_feats), ptr(self._i64(obj_cls)),
+                                         ptr(self._i64(pred_cls)) if need_pred else None, ptr(x0), ptr(p0), ptr(ws), ws.numel(), st),
+                  "subgc_fuse_nodes_cls")
+        else:
+            pd = self._f32(pred_dist) if need_pred else None
+            check(L.subgc_fuse_nodes(C.byref(cd), C.byref(w), B, ptr(att_feats), ptr(obj_dist), ptr(pd), ptr(x0), ptr(p0), ptr(ws),
+                                     ws.numel(), st), "subgc_fuse_nodes")
         check(L.subgc_gcn_forward(C.byref(cd), C.byref(w), B, ptr(x0), ptr(p0), ptr(rel_ind), ptr(x_obj), ptr(x_pred), ptr(ws),
                                   ws.numel(), st), "subgc_gcn_forward")
         self._x0 = x0
         return (x_obj, x_pred) if want_x_pred else x_obj
 
-    def _sgpn(self, x_obj, gpn_obj_ind, att_masks, order):
+    def _sgpn(self, x_obj, gpn_obj_ind, att_masks, order, seq_per_img=None):
         dev = x_obj.device
         L, w, cd = lib(), self._weights(), self._cdims
         rows, _, per_half, _ = gpn_obj_ind.shape
-        lay = _lib.Layout(rows, per_half, self.seq_per_img, order)
-        n_sub = 2 * rows * per_half if order == 0 else 2 * (rows // self.seq_per_img) * per_half
+        spi = seq_per_img or self.seq_per_img
+        lay = _lib.Layout(rows, per_half, spi, order)
+        n_sub = 2 * rows * per_half if order == 0 else 2 * (rows // spi) * per_half
         read_out = torch.empty(n_sub, 2 * self.dims.gcn, device=dev)
         score = torch.empty(n_sub, device=dev)
         sub_len = torch.empty(n_sub, dtype=torch.int32, device=dev)
@@ -474,17 +485,18 @@ class TopDownModel(nn.Module):
                                       ws.numel(), self._stream()), "subgc_prepare_forward")
         return g_fc, fc, att, p_att, masks
 
-    def _front(self, att_feats, att_masks, obj_dist, rel_ind, pred_dist, gpn_obj_ind, plan_kind=None):
+    def _front(self, att_feats, att_masks, obj_dist, rel_ind, pred_dist, gpn_obj_ind, plan_kind=None, seq_per_img=None, obj_cls=None,
+               pred_cls=None):
         """Encoder + sGPN + NMS + feature preparation for inference.  One host read-back (kept count, clip length) —
         the reference synchronises at the same two places (NMS on the host, clip_att's .max())."""
         dev = self._check_device(att_feats, att_masks, obj_dist, rel_ind, gpn_obj_ind)
         L, cd = lib(), self._cdims
         gpn_obj_ind, att_masks = self._i64(gpn_obj_ind), self._f32(att_masks)
         self._mark()
-        x_obj = self.encode(att_feats, obj_dist, pred_dist, rel_ind)
+        x_obj = self.encode(att_feats, obj_dist, pred_dist, rel_ind, obj_cls=obj_cls, pred_cls=pred_cls)
         self._mark("encode")
-        lay, n_sub, read_out, score, sub_len, loss = self._sgpn(x_obj, gpn_obj_ind, att_masks, order=1)
-        n_images = lay.rows // self.seq_per_img
+        lay, n_sub, read_out, score, sub_len, loss = self._sgpn(x_obj, gpn_obj_ind, att_masks, order=1, seq_per_img=seq_per_img)
+        n_images = lay.rows // lay.seq_per_img
         P = 2 * lay.per_half
         sel = torch.empty(n_sub, dtype=torch.int32, device=dev)
         keep = torch.empty(n_sub, dtype=torch.int64, device=dev)
@@ -519,6 +531,21 @@ class TopDownModel(nn.Module):
                 pred_dist=None, gpn_obj_ind=None, gpn_pred_ind=None, gpn_nrel_ind=None, gpn_pool_mtx=None, opt={}):
         """Reference models/AttModel.py:236-326 (greedy / top-k) and :179-234 (beam).  Returns
         (seq, seqLogprobs, subgraph_score, keep_ind[, att2_weights])."""
+        return self._sample_impl(dict(att_feats=att_feats, att_masks=att_masks, obj_dist=obj_dist, rel_ind=rel_ind, pred_dist=pred_dist,
+                                      gpn_obj_ind=gpn_obj_ind), opt)
+
+    def _sample_compact(self, batch, opt={}):
+        """`mode='sample_compact'`: AttModel._sample (models/AttModel.py:236-326) from a subgc.compact.CompactBatch on the device --
+        class ids instead of score tensors, node lists + lengths instead of masks / pooling matrices, one copy per image.  Same
+        return tuple, identical results (the few index / mask tensors the kernels read are rebuilt on the device: ~100 KB)."""
+        d = self.dims
+        N = batch.sub_nodes.shape[-1]
+        masks = (torch.arange(N, device=batch.sub_len.device).view(1, 1, 1, N) < batch.sub_len.unsqueeze(-1)).float()
+        return self._sample_impl(dict(att_feats=batch.att_feats, att_masks=masks, obj_dist=None, rel_ind=batch.rel_ind.long(), pred_dist=None,
+                                      gpn_obj_ind=batch.sub_nodes.long(), seq_per_img=1, obj_cls=batch.obj_cls.long(),
+                                      pred_cls=None if batch.pred_cls is None else batch.pred_cls.long()), opt)
+
+    def _sample_impl(self, front, opt):
         if not self.test_LSTM:
             raise _lib.SubgcError("mode='sample' needs a model built with opt.test_LSTM=1 (as test.py does)")
         self.check_numerics(block=False)
@@ -529,14 +556,12 @@ class TopDownModel(nn.Module):
         uniforms = opt.get("topk_uniforms", None)
         kind = ("beam", beam_size, opt.get("length_penalty", ""), int(opt.get("decoding_constraint", 0))) if beam_size > 1 else \
             ("sample", bool(self.topk_sampling), float(self.topk_temp), int(self.the_k), return_att)
-        (g_fc, fc, att, p_att, masks), sub_score, keep_ind, n_rows, len_max = self._front(att_feats, att_masks, obj_dist, rel_ind,
-                                                                                          pred_dist, gpn_obj_ind, plan_kind=kind)
+        (g_fc, fc, att, p_att, masks), sub_score, keep_ind, n_rows, len_max = self._front(plan_kind=kind, **front)
         plan = self._cur_plan
         if beam_size > 1:
             res = self._beam(fc, att, p_att, masks, n_rows, len_max, opt, plan)
             if res is None:   # fp16-range overflow: repeated on the fp32 path (see _check_call)
-                return self._sample(fc_feats, att_feats, att_masks, trip_pred, obj_dist, obj_box, rel_ind, pred_fmap, pred_dist, gpn_obj_ind,
-                                    gpn_pred_ind, gpn_nrel_ind, gpn_pool_mtx, opt)
+                return self._sample_impl(front, opt)
             return res[0], res[1], sub_score, keep_ind
         dev = fc.device
         L, w, cd, T = lib(), self._weights(), self._cdims, self.seq_length
@@ -573,8 +598,7 @@ class TopDownModel(nn.Module):
         seq, lps = o["seq"].clone(), o["lps"].clone()
         steps = self._check_call(o["steps"])
         if steps is None:   # an activation left the fp16 range: this call's results are invalid, run it again on the fp32 path
-            return self._sample(fc_feats, att_feats, att_masks, trip_pred, obj_dist, obj_box, rel_ind, pred_fmap, pred_dist, gpn_obj_ind,
-                                gpn_pred_ind, gpn_nrel_ind, gpn_pool_mtx, opt)
+            return self._sample_impl(front, opt)
         if return_att:
             return seq, lps, sub_score, keep_ind, o["attw"][:, :steps].clone()
         return seq, lps, sub_score, keep_ind

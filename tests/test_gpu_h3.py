@@ -129,28 +129,38 @@ def test_packed_path_matches_fp32_path_and_oracle(mode):
     assert float((lp_p - ref["seqLogprobs"]).abs().max()) <= RTOL * max(1.0, float(ref["seqLogprobs"].abs().max()))
 
 
-def test_fp16_range_guard_trips_and_falls_back():
-    """An embedding value beyond the fp16 range saturates in the split-fp16 copy: the device flag must come up, the model must
-    refuse the result and switch to the fp32 path, whose rerun matches the oracle."""
-    d = SMALL
-    sd = synth.make_state_dict(d, 3)
-    sd["embed.0.weight"] = sd["embed.0.weight"].clone()
-    sd["embed.0.weight"][0, :] = 9.0e4          # row 0 = <bos>: fed at t = 0 of every caption
-    data = synth.make_test_inputs(d, 3, n_images=2, per_half=2, ragged=True, ragged_edges=True)
-    dev = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in data.items()}
-    args = [dev[k] for k in synth.SAMPLE_ARG_ORDER]
-    m = _model(d, sd, gpn_nms_thres=0.5, gpn_max_subg=2)
-    with torch.no_grad():
-        m(*args, opt={"beam_size": 1}, mode="sample")
-        if m._weights().n_packs == 0:
-            pytest.skip("no packed weights at these dims")
-        with pytest.raises(_lib.SubgcError):
-            m.check_numerics()
-        assert m.use_packed is False
-        res = m(*args, opt={"beam_size": 1}, mode="sample")
-        m.check_numerics()
-        ref = O.sample(sd, d, data, use_nms=True, iou_thres=0.5, max_subgraphs=2)
-    assert torch.equal(res[0].cpu(), ref["seq"])
+def test_fp16_range_guard_repeats_the_call_on_the_fp32_path():
+    """An embedding value beyond the fp16 range saturates in the split-fp16 copy.  The results of such a call must never reach the
+    caller: the SAME call notices the device flag, warns, switches the model to the fp32 path and returns that path's results (which
+    match the oracle).  Checked with the persistent decode kernel (full dims) and with the per-stage kernels (small dims)."""
+    import warnings
+    for d, seed in ((Dims(), 3), (SMALL, 3)):
+        sd = synth.make_state_dict(d, seed)
+        sd["embed.0.weight"] = sd["embed.0.weight"].clone()
+        sd["embed.0.weight"][0, :] = 9.0e4          # row 0 = <bos>: fed at t = 0 of every caption
+        data = synth.make_test_inputs(d, seed, n_images=2, per_half=2, ragged=True, ragged_edges=True)
+        dev = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in data.items()}
+        args = [dev[k] for k in synth.SAMPLE_ARG_ORDER]
+        m = _model(d, sd, gpn_nms_thres=0.5, gpn_max_subg=2)
+        with torch.no_grad():
+            m._weights()
+            had_packs = m._weights().n_packs > 0
+            with warnings.catch_warnings(record=True) as caught:
+                warnings.simplefilter("always")
+                res = m(*args, opt={"beam_size": 1}, mode="sample")       # the FIRST call already returns valid results
+            ref = O.sample(sd, d, data, use_nms=True, iou_thres=0.5, max_subgraphs=2)
+        if had_packs:
+            assert any("fp16 range" in str(w.message) for w in caught), "the overflow must be reported"
+            assert m.use_packed is False
+        assert torch.equal(res[0].cpu(), ref["seq"])
+        assert float((res[1].cpu() - ref["seqLogprobs"]).abs().max()) <= RTOL * max(1.0, float(ref["seqLogprobs"].abs().max()))
+        with torch.no_grad():   # and the beam path does the same
+            m2 = _model(d, sd, gpn_nms_thres=0.5, gpn_max_subg=2)
+            with warnings.catch_warnings(record=True):
+                warnings.simplefilter("always")
+                res2 = m2(*args, opt={"beam_size": 2}, mode="sample")
+            ref2 = O.sample(sd, d, data, use_nms=True, iou_thres=0.5, max_subgraphs=2, beam_size=2)
+        assert torch.equal(res2[0], ref2["seq"])
 
 
 @pytest.mark.parametrize("variant", ["SUBGC_FUSED_CELL", "SUBGC_MERGED", "SUBGC_FUSED_ATT", "SUBGC_NO_PDL"])

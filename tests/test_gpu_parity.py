@@ -118,10 +118,12 @@ def test_golden_greedy(case):
     assert rel_err(t2n(score), g["greedy_score"]) <= RTOL
     assert tuple(attw.shape) == g["greedy_att_weights"].shape
     assert rel_err(t2n(attw), g["greedy_att_weights"]) <= RTOL
-    # without attention weights the discarded last step is skipped: results must not change
+    # without attention weights the discarded last step is skipped (and, at full size, the loop runs as the persistent kernel, whose
+    # split-K partials cover different k-ranges): same tokens, log-probs within the bar
     with torch.no_grad():
         seq2, lps2, _, _ = model(*synth.sample_args(dev), opt={"beam_size": 1}, mode="sample")
-    assert torch.equal(seq, seq2) and torch.equal(lps, lps2)
+    assert torch.equal(seq, seq2)
+    assert rel_err(t2n(lps2), g["greedy_logprobs"]) <= RTOL
 
 
 def test_golden_beam(case):

@@ -107,3 +107,25 @@ def test_pack_segment_descriptor_and_abi_entries():
     assert L.subgc_pack_elems(1024, n1, seg1) == 5 * 1024 * 64
     with pytest.raises(AssertionError):
         packing._seg_array(100, [50, 40])
+
+
+def test_compact_batch_host_side():
+    """subgc.compact.compact_batch is loader-side host code: class ids as the reference's own arg-max (AttModel.py:374), one copy of
+    the sub-graph tensors per image, lengths = ones in att_masks = trace of gpn_pool_mtx (dataloader_test.py:280-286)."""
+    import torch
+    from subgc import compact, synth
+    from subgc.config import SMALL
+    data = synth.make_test_inputs(SMALL, 4, n_images=3, per_half=2, ragged=True, ragged_edges=True)
+    host = [data[k] for k in synth.SAMPLE_ARG_ORDER]
+    cb = compact.compact_batch(*host, with_pred=True)
+    B, N, K = 3, SMALL.obj_num, SMALL.rel_num
+    assert cb.obj_cls.dtype == torch.int16 and tuple(cb.obj_cls.shape) == (B, N)
+    assert torch.equal(cb.obj_cls.long(), data["obj_dist"][:, :, 1:].max(2)[1] + 1)
+    assert torch.equal(cb.pred_cls.long(), data["pred_dist"][:, :, 1:].max(2)[1] + 1)
+    assert cb.rel_ind.dtype == torch.uint8 and torch.equal(cb.rel_ind.long(), data["rel_ind"])
+    assert tuple(cb.sub_nodes.shape) == (B, 2, 2, N) and torch.equal(cb.sub_nodes.long(), data["gpn_obj_ind"][::5])
+    assert torch.equal(cb.sub_len.float(), data["att_masks"][::5].sum(-1))
+    assert torch.equal(cb.sub_len.float(), torch.diagonal(data["gpn_pool_mtx"][::5], dim1=-2, dim2=-1).sum(-1))
+    lean = compact.needed_only(*host)
+    assert lean[0] is None and lean[8] is None and lean[10] is None and lean[11] is None and lean[12] is None and lean[1] is host[1]
+    assert cb.nbytes() < sum(t.numel() * t.element_size() for t in host if t is not None) / 1.5
