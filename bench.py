@@ -305,14 +305,15 @@ def main():
         return res
 
     def time_e2e(fmt):
+        n_warm = 2 * max(warmup, 3)   # each of the two device-side input sets goes through eager -> graph capture -> replay first
         prefetch(0, fmt)
-        for i in range(2):
-            r = step_e2e(i, i == 1, fmt)
+        for i in range(n_warm):
+            r = step_e2e(i, i == n_warm - 1, fmt)
         barrier()
         t0 = time.perf_counter()
-        prefetch(2, fmt)                                        # all K host->device copies happen inside the timed region
-        for i in range(2, 2 + args.steps):
-            r = step_e2e(i, i == 1 + args.steps, fmt)
+        prefetch(n_warm, fmt)                                   # all K host->device copies happen inside the timed region
+        for i in range(n_warm, n_warm + args.steps):
+            r = step_e2e(i, i == n_warm - 1 + args.steps, fmt)
         ms = (time.perf_counter() - t0) * 1e3                   # host wall clock: every step ends with a device synchronisation
         barrier()
         return ms, r
@@ -329,7 +330,6 @@ def main():
         if sampler:
             sampler.start()
         from subgc.model import _DecodePlan
-        model.stage_events = []
         launches0 = L.subgc_launch_count() + _DecodePlan.replayed_launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -339,6 +339,16 @@ def main():
         barrier()
         launches = L.subgc_launch_count() + _DecodePlan.replayed_launches - launches0   # direct launches + kernels inside graph replays
         ms_total = e0.elapsed_time(e1)
+        # ---- stage split and the decode launch time behind `roofline`: a second pass over the same inputs with CUDA events between
+        # the stages (the timed pass above replays the whole step as one graph, which has no place for events); same kernels
+        model.stage_events = []
+        for _ in range(3):
+            step_resident()
+        torch.cuda.synchronize()
+        model.stage_events = []
+        for _ in range(args.steps):
+            step_resident()
+        torch.cuda.synchronize()
         stage_ms = {}
         for name, a, b in model.stage_events:
             stage_ms[name] = stage_ms.get(name, 0.0) + a.elapsed_time(b)
@@ -376,6 +386,8 @@ def main():
                                       "input": "reference-signature call, tensors the kernels never read not uploaded "
                                                f"(the loaders' full tuple is {loader_bytes} bytes)"}},
             "gpu_launches": int(launches), "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
+            "stage_note": "stage times and roofline.launch_ms come from a second pass with CUDA events between the stages; `value` is the "
+                          "whole step replayed as one CUDA graph (encoder .. persistent decode kernel, no host round trip before the results)",
             "decode_steps_executed": steps_exec}
     if args.mode != "beam" and "decode" in stage_ms:
         t_dec = stage_ms["decode"] / args.steps * 1e-3           # one launch of the decode loop (subgc_decode_sample)
@@ -387,8 +399,8 @@ def main():
         if os.path.isfile(tp) and args.mode == "greedy":
             tj = json.load(open(tp))
             traffic, traffic_note = tj["dram_bytes_per_decode_loop"], tj["note"]
-        line["roofline"] = {"bound": "hbm", "kernel": "decode loop (subgc_decode_sample: 20 x [att-LSTM, cell, h2att, attention, lang-LSTM, cell, "
-                                                      "logit, select])",
+        line["roofline"] = {"bound": "hbm", "kernel": "mega_decode_kernel: the decode loop of subgc_decode_sample as one persistent cooperative "
+                                                      "launch (20 x [att-LSTM, cell, h2att, attention, lang-LSTM, cell, logit, select])",
                             "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                             "traffic": traffic, "traffic_note": traffic_note,
                             "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",

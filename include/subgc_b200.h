@@ -285,6 +285,17 @@ int subgc_decode_sample(const subgc_dims* d, const subgc_weights* w, int n_rows,
                         int64_t* seq, float* seq_logprobs, float* att_weights /*nullable*/,
                         int32_t* steps_done, void* ws, size_t ws_bytes, subgc_stream_t stream);
 
+/* Same loop with the row count and the attention length decided ON THE DEVICE: counts (device int32[2]) = (rows kept by
+ * subgc_subgraph_nms = its stats[0], longest kept sub-graph = stats[1]) is read by the kernel; rows_cap / len_cap are upper bounds and
+ * the strides of fc / att / p_att / masks / seq / seq_logprobs.  The reference synchronises with the host at exactly these two points
+ * (NMS on the host, models/lib/gpn.py:114; clip_att's .max(), models/AttModel.py:351); here encoder -> sGPN -> NMS -> prepare -> decode
+ * is one uninterrupted stream of launches (capturable as one CUDA graph).  Rows >= counts[0] of the outputs stay zero.  uniforms
+ * (nullable) is [T, rows_cap].  Needs the persistent decode kernel (w->mega): SUBGC_E_UNSUPPORTED otherwise. */
+int subgc_decode_sample_dyn(const subgc_dims* d, const subgc_weights* w, int rows_cap, int len_cap, const int32_t* counts,
+                            int mode, float temp, int top_k, uint64_t seed, uint64_t offset, const float* uniforms /*nullable*/,
+                            const float* fc, const float* att, const float* p_att, const float* masks, int64_t* seq,
+                            float* seq_logprobs, int32_t* steps_done, void* ws, size_t ws_bytes, subgc_stream_t stream);
+
 /* Teacher-forced decoding of AttModel._forward (models/AttModel.py:150-177, sampling_prob == 0, eval mode): step i
  * is fed tokens[:, i]; outputs[:, i] = log-probs; from the first column i >= 1 that is entirely zero on, the loop
  * stops and the remaining outputs stay zero (AttModel.py:170-171), evaluated on the device.

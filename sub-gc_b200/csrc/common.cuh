@@ -7,6 +7,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "subgc_b200.h"
 
 namespace subgc {
@@ -49,16 +52,26 @@ void count_launch();  // per-thread tally of kernels launched through this libra
 
 constexpr int kNumSMs = 148;  // B200
 
-// Function attributes (dynamic shared-memory limit, carve-out) are per device: `first_use_on_device(flags)` is true once per
-// device for the given per-call-site flag array, so that DataParallel-style threads driving several GPUs from one process work.
-inline bool first_use_on_device(bool (&seen)[64]) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64) return true;
-    if (seen[dev]) return false;
-    seen[dev] = true;
-    return true;
-}
+// Function attributes (dynamic shared-memory limit, carve-out) are per device.  DeviceOnce::run(f) runs f() once per device for its
+// call site and remembers the device only when f succeeded; threads driving the same device (DataParallel-style) wait for the one
+// that sets the attributes instead of launching before they are applied.
+struct DeviceOnce {
+    std::mutex mu;
+    std::atomic<bool> done[64];
+    DeviceOnce() { for (auto& d : done) d.store(false); }
+    template <typename F>
+    cudaError_t run(F&& f) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64) return f();
+        if (done[dev].load(std::memory_order_acquire)) return cudaSuccess;
+        std::lock_guard<std::mutex> lock(mu);
+        if (done[dev].load(std::memory_order_relaxed)) return cudaSuccess;
+        const cudaError_t e = f();
+        if (e == cudaSuccess) done[dev].store(true, std::memory_order_release);
+        return e;
+    }
+};
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -193,7 +206,7 @@ bool mega_decode_eligible(const subgc_dims* d, const subgc_weights* w, int S, in
 size_t mega_decode_scratch_bytes_max(const subgc_dims* d);
 int launch_mega_decode(const subgc_dims* d, const subgc_weights* w, int S, int len_max, int mode, float temp, int top_k, uint64_t seed, uint64_t offset,
                        const float* uniforms, const float* fc_pre, const float* att, const float* p_att, const float* masks, int64_t* seq,
-                       float* seq_lp, int32_t* steps_done, Workspace& ws, cudaStream_t st);
+                       float* seq_lp, int32_t* steps_done, Workspace& ws, cudaStream_t st, const int32_t* counts = nullptr);
 
 // ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
 // The decode loop is a chain of ~6 dependent kernels per token, each of them short: launch latency, grid drain and kernel

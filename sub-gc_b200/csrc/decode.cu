@@ -858,27 +858,30 @@ static unsigned long long* att_trace_buffer() {
 
 // The fused att-phase kernel runs as clusters of 8 row-blocks (distributed shared memory carries the h2att results).
 static bool att_phase_fusable(size_t smem) {
-    static int mode = -1, clus = 0;
+    static int mode = -1;
     if (mode < 0) {
         const char* e = getenv("SUBGC_FUSED_ATT");   // opt-in: measured slower than the three separate kernels under PDL
         mode = (e && e[0] == '1') ? 1 : 0;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&clus, cudaDevAttrClusterLaunch, dev);
     }
-    return mode == 1 && clus && smem <= 48 * 1024;
+    if (mode != 1 || smem > 48 * 1024) return false;
+    int dev = 0, clus = 0;   // cluster launch support is a property of the current device, not of the process
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&clus, cudaDevAttrClusterLaunch, dev);
+    return clus != 0;
 }
 
 // The loop's small kernels run next to the contraction's CTAs (which hold ~193 KB of shared memory): an SM only hosts kernels with
 // the same shared-memory / L1 split, so they ask for the maximum shared-memory carve-out as well.
 static void prefer_smem_carveout() {
-    static bool seen[64] = {};
-    if (!first_use_on_device(seen)) return;
-    cudaFuncSetAttribute(lstm_reduce_cell_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(select_reg_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(select_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(log_softmax_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    static DeviceOnce once;
+    once.run([]() -> cudaError_t {   // a preference only: a failure costs overlap, not correctness, and is retried at the next call
+        cudaError_t e = cudaFuncSetAttribute(lstm_reduce_cell_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(select_reg_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(select_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(log_softmax_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        return e;
+    });
 }
 
 // upto: 0 = whole step, 1 = stop after the attention (the reference's discarded last step, only its attention
@@ -1383,10 +1386,10 @@ extern "C" int subgc_decode_step(const subgc_dims* d, const subgc_weights* w, in
     return SUBGC_OK;
 }
 
-extern "C" int subgc_decode_sample(const subgc_dims* d, const subgc_weights* w, int n_rows, int len_max, int mode, float temp, int top_k,
-                                   uint64_t seed, uint64_t offset, const float* uniforms, const float* fc, const float* att,
-                                   const float* p_att, const float* masks, int64_t* seq, float* seq_logprobs, float* att_weights,
-                                   int32_t* steps_done, void* ws_, size_t ws_bytes, subgc_stream_t stream) {
+static int decode_sample_impl(const subgc_dims* d, const subgc_weights* w, int n_rows, int len_max, int mode, float temp, int top_k,
+                              uint64_t seed, uint64_t offset, const float* uniforms, const float* fc, const float* att,
+                              const float* p_att, const float* masks, int64_t* seq, float* seq_logprobs, float* att_weights,
+                              int32_t* steps_done, void* ws_, size_t ws_bytes, subgc_stream_t stream, const int32_t* counts) {
     SUBGC_TRY(check_decode_args(d, w, n_rows, len_max, "subgc_decode_sample"));
     SUBGC_CHECK_ARG(fc && att && p_att && masks && seq && seq_logprobs && steps_done, "subgc_decode_sample: null argument");
     SUBGC_CHECK_ARG(mode == 0 || mode == 1, "subgc_decode_sample: mode must be 0 (greedy) or 1 (top-k)");
@@ -1426,7 +1429,11 @@ extern "C" int subgc_decode_sample(const subgc_dims* d, const subgc_weights* w, 
     SUBGC_TRY(launch_fc_pre(d, w, S, fc, sc, st));
     if (mega_decode_eligible(d, w, S, len_max, att_weights))   // the whole loop as one persistent kernel (mega_decode.cu)
         return launch_mega_decode(d, w, S, len_max, mode, temp, top_k, seed, offset, uniforms, sc.gates, att, p_att, masks, seq, seq_logprobs,
-                                  steps_done, ws, st);
+                                  steps_done, ws, st, counts);
+    if (counts) {
+        set_error("subgc_decode_sample_dyn: device-side row counts need the persistent decode kernel (w->mega, <= 128 rows, no attention weights)");
+        return SUBGC_E_UNSUPPORTED;
+    }
     for (int t = 0; t <= T; ++t) {
         const int* active = (t == 0) ? nullptr : count + (t - 1);
         const int in = t & 1, out = in ^ 1;
@@ -1461,6 +1468,23 @@ extern "C" int subgc_decode_sample(const subgc_dims* d, const subgc_weights* w, 
     steps_done_kernel<<<1, 1, 0, st>>>(count, T, steps_done);
     SUBGC_LAUNCH_CHECK();
     return SUBGC_OK;
+}
+
+extern "C" int subgc_decode_sample(const subgc_dims* d, const subgc_weights* w, int n_rows, int len_max, int mode, float temp, int top_k,
+                                   uint64_t seed, uint64_t offset, const float* uniforms, const float* fc, const float* att,
+                                   const float* p_att, const float* masks, int64_t* seq, float* seq_logprobs, float* att_weights,
+                                   int32_t* steps_done, void* ws_, size_t ws_bytes, subgc_stream_t stream) {
+    return decode_sample_impl(d, w, n_rows, len_max, mode, temp, top_k, seed, offset, uniforms, fc, att, p_att, masks, seq, seq_logprobs, att_weights,
+                              steps_done, ws_, ws_bytes, stream, nullptr);
+}
+
+extern "C" int subgc_decode_sample_dyn(const subgc_dims* d, const subgc_weights* w, int rows_cap, int len_cap, const int32_t* counts, int mode,
+                                       float temp, int top_k, uint64_t seed, uint64_t offset, const float* uniforms, const float* fc, const float* att,
+                                       const float* p_att, const float* masks, int64_t* seq, float* seq_logprobs, int32_t* steps_done, void* ws_,
+                                       size_t ws_bytes, subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(counts != nullptr, "subgc_decode_sample_dyn: null counts");
+    return decode_sample_impl(d, w, rows_cap, len_cap, mode, temp, top_k, seed, offset, uniforms, fc, att, p_att, masks, seq, seq_logprobs, nullptr,
+                              steps_done, ws_, ws_bytes, stream, counts);
 }
 
 extern "C" size_t subgc_teacher_workspace_bytes(const subgc_dims* d, int n_rows, int n_steps) {

@@ -749,11 +749,12 @@ static int h3_segments(const GemmProblem& p, int box_w, Workspace& ws, cudaStrea
 }
 
 static int h3_set_smem_attr() {
-    static bool seen[64] = {};
-    if (first_use_on_device(seen)) {
-        SUBGC_CUDA(cudaFuncSetAttribute(h3_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, H3_SMEM_BUDGET + H3_SMEM_EXTRA));
-        SUBGC_CUDA(cudaFuncSetAttribute(h3_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, H3_SMEM_BUDGET + H3_SMEM_EXTRA));
-    }
+    static DeviceOnce once;
+    SUBGC_CUDA(once.run([]() -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(h3_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, H3_SMEM_BUDGET + H3_SMEM_EXTRA);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(h3_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, H3_SMEM_BUDGET + H3_SMEM_EXTRA);
+        return e;
+    }));
     return SUBGC_OK;
 }
 
@@ -806,8 +807,8 @@ int launch_gemm_cell(const GemmProblem& p0, const CellEpilogue& cell, void* ws_,
     // opt-in (SUBGC_FUSED_CELL=1): correct, but the DSMEM reduction + cell on 128 threads per SM measured ~3 us slower per LSTM than
     // split-K partials + the (all-resident, PDL-released) cell kernel -- see DESIGN.md
     static const bool off = !(getenv("SUBGC_FUSED_CELL") != nullptr && getenv("SUBGC_FUSED_CELL")[0] == '1');
-    static int clus = -1;
-    if (clus < 0) {
+    int clus = 0;
+    if (!off) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&clus, cudaDevAttrClusterLaunch, dev);

@@ -81,6 +81,9 @@ struct MgParams {
     unsigned* sync;
     long long* seq; float* seq_lp; int* steps_done; int* overflow;
     int mode; float temp; int top_k; unsigned long long seed, offset; const float* uniforms;
+    const int* counts;           // nullable DEVICE int32[2]: (rows, longest sub-graph) decided by the NMS kernel earlier in the stream; S / len_max
+                                 // are then upper bounds (buffer strides) and the real values are read here: no host round trip
+    int len_stride;              // nodes per row in att / p_att / masks
     unsigned long long* trace;   // debug (SUBGC_MEGA_TRACE=1): [cta][step][MG_TRACE_EVENTS] globaltimer stamps, else nullptr
 };
 
@@ -236,7 +239,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
     float* scr = reinterpret_cast<float*>(gbase + MG_OFF_SCR);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cta_id = blockIdx.x;
-    const int S = p.S, T = p.T, H = p.H;
+    const int S = p.counts ? min(p.S, __ldg(p.counts)) : p.S, T = p.T, H = p.H;
+    const int len_rt = p.counts ? min(p.len_max, __ldg(p.counts + 1)) : p.len_max;   // attention length (<= len_stride)
 
     // ---- set-up: schedule of this CTA, barriers, tensor memory
     {
@@ -488,7 +492,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
         float* s_c = s_sp + 256;
         if (has_row) {
             for (int j = wt; j < p.AH; j += MG_NW) s_w[j] = __ldg(p.alpha_w + j);
-            if (wt < p.len_max) s_mask[wt] = __ldg(p.masks + (size_t)row * p.len_max + wt);
+            if (wt < len_rt) s_mask[wt] = __ldg(p.masks + (size_t)row * p.len_stride + wt);
             // xt(0) = relu(E[<bos> = 0]) (AttModel.py:283-284,332)
             for (int j = wt; j < p.E; j += MG_NW) x_store(p.x_xt, row, j, fmaxf(__ldg(p.embed + j), 0.f), ovf);
             w_signal(p.sync + MG_C_XT, true);
@@ -567,12 +571,12 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
             }
             // ---------------- attention of this CTA's row (AttModel.py:445-471) -> ctx(t)
             if (has_row) {
-                const int AH = p.AH, len_max = p.len_max;
+                const int AH = p.AH, len_max = len_rt, lst = p.len_stride;
                 const int AH4 = AH >> 2, Q = AH4 >> 5;          // AH % 128 == 0 (checked on the host)
                 const int items = len_max * Q;                  // (node, 32-quad slice)
-                const float4* pa4 = reinterpret_cast<const float4*>(p.p_att + (size_t)row * len_max * AH);
+                const float4* pa4 = reinterpret_cast<const float4*>(p.p_att + (size_t)row * lst * AH);
                 {   // att row -> L2 (the weight stream may have evicted it)
-                    const char* af = reinterpret_cast<const char*>(p.att + (size_t)row * len_max * H);
+                    const char* af = reinterpret_cast<const char*>(p.att + (size_t)row * lst * H);
                     const size_t nb_a = (size_t)len_max * H * 4;
                     for (size_t o = (size_t)wt * 128; o < nb_a; o += (size_t)MG_NW * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(af + o));
                 }
@@ -642,7 +646,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                 worker_bar();
                 MG_WSTAMP(43);
                 {   // context: two thread groups take interleaved node subsets, partials combined in fixed order
-                    const float* af = p.att + (size_t)row * len_max * H;
+                    const float* af = p.att + (size_t)row * lst * H;
                     const int grp = wt >> 8, tg = wt & 255, H4 = H >> 2;
                     for (int j4 = tg; j4 < H4; j4 += 256) {
                         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -747,7 +751,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                     }
                     worker_bar();
                     const int k = p.top_k;
-                    const float u = p.uniforms ? p.uniforms[(size_t)t * S + row] : MgPhilox::uniform(p.seed, p.offset, (unsigned)t, (unsigned)row);
+                    const float u = p.uniforms ? p.uniforms[(size_t)t * p.S + row] : MgPhilox::uniform(p.seed, p.offset, (unsigned)t, (unsigned)row);
                     float den = 0.f;
                     for (int c = 0; c < k; ++c) den += expf(ctl->topv[c] - ctl->topv[0]);
                     float cdf = 0.f;
@@ -1060,7 +1064,7 @@ bool mega_decode_eligible(const subgc_dims* d, const subgc_weights* w, int S, in
 // The loop of subgc_decode_sample as one cooperative launch.  fc_pre: [S, 4H] hoisted fc segment + both biases (launch_fc_pre).
 int launch_mega_decode(const subgc_dims* d, const subgc_weights* w, int S, int len_max, int mode, float temp, int top_k, uint64_t seed, uint64_t offset,
                        const float* uniforms, const float* fc_pre, const float* att, const float* p_att, const float* masks, int64_t* seq,
-                       float* seq_lp, int32_t* steps_done, Workspace& ws, cudaStream_t st) {
+                       float* seq_lp, int32_t* steps_done, Workspace& ws, cudaStream_t st, const int32_t* counts) {
     const MgPlan& pl = cached_plan(d, w->mega_ctas);
     MgScratch sc;
     if (!mega_take_scratch(pl, ws, sc)) { set_error("subgc_decode_sample: workspace too small for the persistent decode kernel"); return SUBGC_E_WORKSPACE; }
@@ -1079,9 +1083,10 @@ int launch_mega_decode(const subgc_dims* d, const subgc_weights* w, int S, int l
     p.partA = sc.partA; p.partC = sc.partC; p.partB = sc.partB; p.partD = sc.partD; p.sync = sc.sync;
     p.seq = reinterpret_cast<long long*>(seq); p.seq_lp = seq_lp; p.steps_done = steps_done; p.overflow = w->h3_overflow;
     p.mode = mode; p.temp = temp; p.top_k = top_k; p.seed = seed; p.offset = offset; p.uniforms = uniforms;
+    p.counts = counts; p.len_stride = len_max;
     p.trace = (pl.n_cta <= 256 && d->seq_length <= 32) ? mega_trace_buffer(nullptr) : nullptr;
-    static bool seen[64] = {};
-    if (first_use_on_device(seen)) SUBGC_CUDA(cudaFuncSetAttribute(mega_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM));
+    static DeviceOnce once;
+    SUBGC_CUDA(once.run([]() { return cudaFuncSetAttribute(mega_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM); }));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(pl.n_cta); cfg.blockDim = dim3(MG_THREADS); cfg.dynamicSmemBytes = MG_SMEM; cfg.stream = st;
     cudaLaunchAttribute at[1];

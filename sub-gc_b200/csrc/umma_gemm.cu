@@ -527,8 +527,8 @@ int launch_gemm_tc(const GemmProblem& p, void* ws_, size_t ws_bytes, cudaStream_
     if (!TC_L2_PREFETCH) for (int s = 0; s < p.nseg; ++s) tp.tm_wpf[s] = tp.tm_w[s];
     tp.nseg = p.nseg; tp.M = p.M; tp.N = p.N; tp.kb_total = pl.kb_total; tp.kb_per_split = pl.kb_per_split; tp.part = part; tp.active = p.active;
     tp.direct = direct ? 1 : 0; tp.epi = p.epi; tp.C = p.C; tp.ldc = p.ldc;
-    static bool seen[64] = {};
-    if (first_use_on_device(seen)) SUBGC_CUDA(cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    static DeviceOnce once;
+    SUBGC_CUDA(once.run([]() { return cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES); }));
     dim3 grid(pl.n_tiles, pl.m_tiles, pl.splits);
     static const bool trace_on = getenv("SUBGC_TC_TRACE") != nullptr;  // debugging aid only: allocates and synchronises
     static long long* trace_buf = nullptr;

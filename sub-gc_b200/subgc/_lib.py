@@ -89,6 +89,8 @@ SIGNATURES = {
                                c_fp, _sz, c_fp]),
     "subgc_decode_sample": (_i, [_P(Dims), _P(Weights), _i, _i, _i, _f, _i, _u64, _u64, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp,
                                  c_fp, c_fp, c_fp, _sz, c_fp]),
+    "subgc_decode_sample_dyn": (_i, [_P(Dims), _P(Weights), _i, _i, c_fp, _i, _f, _i, _u64, _u64, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp,
+                                     c_fp, _sz, c_fp]),
     "subgc_teacher_workspace_bytes": (_sz, [_P(Dims), _i, _i]),
     "subgc_decode_teacher": (_i, [_P(Dims), _P(Weights), _i, _i, _i, c_fp, _i, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, _sz, c_fp]),
     "subgc_beam_workspace_bytes": (_sz, [_P(Dims), _i, _i, _i]),

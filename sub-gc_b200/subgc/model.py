@@ -128,8 +128,69 @@ class _TrainStep(torch.autograd.Function):
         return (None, None, None, None) + tuple(G.get(n) for n in names)
 
 
+class _DeviceState:
+    """Everything the model caches per device: scratch, weight tables, packed copies, plans / captured graphs, the fp16-range flag.
+    nn.DataParallel (reference train.py:96-98) runs replicas of ONE module object's __dict__ in one thread per device: state kept on
+    the module itself would be shared by those threads, state keyed by the device of the calling replica's parameters is not."""
+
+    def __init__(self):
+        self.ws = Workspace()
+        self.wcache = None
+        self.packs = packing.PackCache()
+        self.pack_key = None
+        self.ovf_dev = self.ovf_host = self.ovf_event = None
+        self.early = self.early_key = None
+        self.mega = self.mega_key = None
+        self.plans = {}
+        self.tops = None
+        self.cur_plan = None
+        self.params = None
+
+
+def _state_property(name):
+    return property(lambda self: getattr(self._state(), name), lambda self, v: setattr(self._state(), name, v))
+
+
 class TopDownModel(nn.Module):
     """Drop-in for reference `TopDownModel(AttModel(CaptionModel))`, Sub-GC configuration."""
+    _ws = _state_property("ws")
+    _wcache = _state_property("wcache")
+    _packs = _state_property("packs")
+    _pack_key = _state_property("pack_key")
+    _ovf_dev = _state_property("ovf_dev")
+    _ovf_host = _state_property("ovf_host")
+    _ovf_event = _state_property("ovf_event")
+    _early = _state_property("early")
+    _early_key = _state_property("early_key")
+    _mega = _state_property("mega")
+    _mega_key = _state_property("mega_key")
+    _plans = _state_property("plans")
+    _tops = _state_property("tops")
+    _cur_plan = _state_property("cur_plan")
+
+    def _state(self):
+        dev = self.logit.weight.device
+        key = dev.index if dev.type == "cuda" else -1
+        st = self._states.get(key)
+        if st is None:
+            st = self._states.setdefault(key, _DeviceState())
+        return st
+
+    def _named_params(self):
+        """name -> tensor of every parameter of THIS module object.  A DataParallel replica has no registered Parameters (its weights
+        are plain attributes, torch/nn/parallel/replicate.py), so the tensors are fetched by attribute path, not by named_parameters()."""
+        st = self._state()
+        cached = st.params
+        if cached is not None and cached[0] is self.logit.weight and cached[1] is self.obj_v_proj.weight:
+            return cached[2]
+        out = {}
+        for name in self._param_names:
+            obj = self
+            for part in name.split("."):
+                obj = obj[int(part)] if part.isdigit() else getattr(obj, part)
+            out[name] = obj
+        st.params = (self.logit.weight, self.obj_v_proj.weight, out)
+        return out
 
     def __init__(self, opt):
         super().__init__()
@@ -186,21 +247,17 @@ class TopDownModel(nn.Module):
         self.last_gpn_loss = None
         self.last_image_of_row = None
         self.last_steps = None
-        self._ws = Workspace()
-        self._wcache = None
-        self._packs = packing.PackCache()
-        self._pack_key = None
+        self._states = {}   # device index -> _DeviceState (shared by DataParallel replicas, which live on different devices)
         self.use_packed = True   # inference contractions read split-fp16 copies of the weights (subgc.packing)
         self.use_mega = True     # greedy / top-k loops of <= 128 rows run as one persistent kernel (csrc/mega_decode.cu)
-        self._ovf_dev = self._ovf_host = self._ovf_event = None   # fp16-range guard of the split activations (check_numerics)
+        self.use_step_graph = True   # ... and then the whole call (encoder .. decode) replays as ONE CUDA graph without host round trips
         self.stage_events = None  # set to [] to collect (name, start_event, end_event) per stage (bench / profiling)
         self.dropout_enabled = True   # tests switch it off: Philox masks cannot match torch's RNG stream (SURVEY §7 hard part 5)
         self.force_train_path = False  # run the autograd-capable path in eval mode too (gradient parity tests)
-        self._tops = None
         self.use_graphs = os.environ.get("SUBGC_NO_GRAPH", "0") != "1"
-        self._plans = {}
         self._cdims = _lib.Dims(d.v1, d.enc, d.rnn, d.att_hid, d.fc_feat, d.att_feat, d.gcn, d.low_rank, d.embed, d.obj_classes,
                                 d.pred_classes, d.gcn_layers, d.gcn_residual, d.pred_emb_type, d.seq_length, d.obj_num, d.rel_num)
+        self._param_names = tuple(n for n, _ in self.named_parameters())
 
     # ------------------------------------------------------------------------------------------------------------
     # plumbing
@@ -219,7 +276,7 @@ class TopDownModel(nn.Module):
 
     def _weights(self):
         """subgc_weights over the live parameter storage (rebuilt when a tensor moved, e.g. after .cuda() / load)."""
-        params = dict(self.named_parameters())
+        params = self._named_params()
         key = tuple(p.data_ptr() for p in params.values())
         if self._wcache is not None and self._wcache[0] == key:
             w = self._wcache[1]
@@ -281,7 +338,7 @@ class TopDownModel(nn.Module):
         # [[h2att.weight, 0], [lang weight_ih[:, H:2H], lang weight_hh]], rebuilt when one of its sources changed
         src = (params["core.attention.h2att.weight"], params["core.lang_lstm.weight_ih"], params["core.lang_lstm.weight_hh"])
         ekey = tuple((t.data_ptr(), t._version) for t in src)
-        if getattr(self, "_early_key", None) != ekey:
+        if self._early_key != ekey:
             with torch.no_grad():
                 top = torch.cat([src[0], src[0].new_zeros(src[0].shape[0], H)], 1)
                 bot = torch.cat([src[1][:, H:2 * H], src[2]], 1)
@@ -310,7 +367,7 @@ class TopDownModel(nn.Module):
             w.mega, w.mega_bytes, w.mega_ctas = None, 0, 0
             return
         key = tuple((params[n].data_ptr(), params[n]._version) for n in self._MEGA_SOURCES) + (dev.index,)
-        if getattr(self, "_mega_key", None) != key:
+        if self._mega_key != key:
             L, cd = lib(), self._cdims
             n_cta = torch.cuda.get_device_properties(dev).multi_processor_count
             nbytes = int(L.subgc_mega_pack_bytes(C.byref(cd), n_cta))
@@ -444,7 +501,7 @@ class TopDownModel(nn.Module):
                                      ws.numel(), st), "subgc_fuse_nodes")
         check(L.subgc_gcn_forward(C.byref(cd), C.byref(w), B, ptr(x0), ptr(p0), ptr(rel_ind), ptr(x_obj), ptr(x_pred), ptr(ws),
                                   ws.numel(), st), "subgc_gcn_forward")
-        self._x0 = x0
+        self._x0, self._p0 = x0, p0
         return (x_obj, x_pred) if want_x_pred else x_obj
 
     def _sgpn(self, x_obj, gpn_obj_ind, att_masks, order, seq_per_img=None):
@@ -538,16 +595,192 @@ class TopDownModel(nn.Module):
         """`mode='sample_compact'`: AttModel._sample (models/AttModel.py:236-326) from a subgc.compact.CompactBatch on the device --
         class ids instead of score tensors, node lists + lengths instead of masks / pooling matrices, one copy per image.  Same
         return tuple, identical results (the few index / mask tensors the kernels read are rebuilt on the device: ~100 KB)."""
-        d = self.dims
+        return self._sample_impl(dict(compact=batch), opt)
+
+    @staticmethod
+    def _expand_compact(batch):
+        """CompactBatch -> the operands of the stages (device ops only: capturable)."""
         N = batch.sub_nodes.shape[-1]
         masks = (torch.arange(N, device=batch.sub_len.device).view(1, 1, 1, N) < batch.sub_len.unsqueeze(-1)).float()
-        return self._sample_impl(dict(att_feats=batch.att_feats, att_masks=masks, obj_dist=None, rel_ind=batch.rel_ind.long(), pred_dist=None,
-                                      gpn_obj_ind=batch.sub_nodes.long(), seq_per_img=1, obj_cls=batch.obj_cls.long(),
-                                      pred_cls=None if batch.pred_cls is None else batch.pred_cls.long()), opt)
+        return dict(att_feats=batch.att_feats, att_masks=masks, obj_dist=None, rel_ind=batch.rel_ind.long(), pred_dist=None,
+                    gpn_obj_ind=batch.sub_nodes.long(), seq_per_img=1, obj_cls=batch.obj_cls.long(),
+                    pred_cls=None if batch.pred_cls is None else batch.pred_cls.long())
+
+    # ------------------------------------------------------------------------------------------------------------
+    # whole-step graph: encoder -> sGPN -> NMS -> prepare -> persistent decode kernel without a host round trip
+    # ------------------------------------------------------------------------------------------------------------
+    def _dyn_eligible(self, front, opt):
+        """The reference synchronises with the host after NMS (kept rows) and in clip_att (longest sub-graph).  With the persistent
+        decode kernel both numbers stay on the device (subgc_decode_sample_dyn): every stage runs at the upper bound of the row count,
+        the decode kernel reads the real one.  Returns (rows_cap, n_images) or None (beam search, attention-weight output, injected
+        uniforms, more than 128 rows, per-stage timing requested, graphs or the persistent kernel switched off)."""
+        if (opt.get("beam_size", 1) != 1 or opt.get("return_att", 0) == 1 or opt.get("topk_uniforms", None) is not None
+                or not self.use_graphs or not self.use_mega or not self.use_step_graph or self.stage_events is not None):
+            return None
+        if not self._weights().mega:
+            return None
+        if "compact" in front:
+            rows, _, per_half, _ = front["compact"].sub_nodes.shape
+            n_images = rows
+        else:
+            rows, _, per_half, _ = front["gpn_obj_ind"].shape
+            n_images = rows // (front.get("seq_per_img") or self.seq_per_img)
+        g = self.gpn_layer
+        per_image = min(int(g.max_subgraphs), 2 * per_half) if g.use_nms else 2 * per_half
+        rows_cap = n_images * per_image
+        if rows_cap < 1 or rows_cap > 128 or rows_cap > self._weights().mega_ctas:
+            return None
+        return rows_cap, n_images
+
+    def _step_body(self, plan, front, rows_cap, n_images):
+        """Launch sequence of one whole step at the row-count upper bound; every pointer it uses lives in `plan` or in `front`."""
+        if "compact" in front:
+            front = self._expand_compact(front["compact"])
+        dev = front["att_feats"].device
+        L, w, cd, T, N = lib(), self._weights(), self._cdims, self.seq_length, self.dims.obj_num
+        gpn_obj_ind, att_masks = front["gpn_obj_ind"], front["att_masks"]
+        x_obj = self.encode(front["att_feats"], front["obj_dist"], front["pred_dist"], front["rel_ind"], obj_cls=front.get("obj_cls"),
+                            pred_cls=front.get("pred_cls"))
+        lay, n_sub, read_out, score, sub_len, loss = self._sgpn(x_obj, gpn_obj_ind, att_masks, order=1, seq_per_img=front.get("seq_per_img"))
+        P = 2 * lay.per_half
+        sel = torch.zeros(max(n_sub, rows_cap), dtype=torch.int32, device=dev)   # rows beyond the kept count stay at sub-graph 0 (valid, unused)
+        keep = torch.zeros(n_sub, dtype=torch.int64, device=dev)
+        stats = torch.zeros(2 + n_images, dtype=torch.int32, device=dev)
+        ws = self._ws.get(L.subgc_nms_workspace_bytes(n_images, P), dev)
+        g = self.gpn_layer
+        check(L.subgc_subgraph_nms(C.byref(cd), C.byref(lay), ptr(score), ptr(sub_len), ptr(gpn_obj_ind), ptr(att_masks), int(bool(g.use_nms)),
+                                   float(g.iou_thres), int(g.max_subgraphs), ptr(sel), ptr(keep), ptr(stats), ptr(ws), ws.numel(),
+                                   self._stream()), "subgc_subgraph_nms")
+        g_fc, fc, att, p_att, masks = self._prepare(lay, rows_cap, N, sel, x_obj, gpn_obj_ind, att_masks, read_out, plan)
+        o = plan.out
+        check(L.subgc_decode_sample_dyn(C.byref(cd), C.byref(w), rows_cap, N, ptr(stats), 1 if self.topk_sampling else 0, float(self.topk_temp),
+                                        int(self.the_k), 0, 0, ptr(o["uniforms"]), ptr(fc), ptr(att), ptr(p_att), ptr(masks), ptr(o["seq"]),
+                                        ptr(o["lps"]), ptr(o["steps"]), ptr(o["ws"]), o["ws"].numel(), self._stream()), "subgc_decode_sample_dyn")
+        have_flag = self._ovf_dev is not None and w.n_packs
+        status = torch.cat([o["steps"], self._ovf_dev if have_flag else torch.zeros(1, dtype=torch.int32, device=dev), stats[:2]])
+        sel_l = sel[:rows_cap].long()
+        return dict(status=status, seq=o["seq"], lps=o["lps"], score=score, sub_score=score[sel_l], keep=keep, sel=sel_l, loss=loss, x_obj=x_obj,
+                    image=torch.div(sel_l, P, rounding_mode="floor"))
+
+    _STEP_INPUTS = ("att_feats", "att_masks", "obj_dist", "rel_ind", "pred_dist", "gpn_obj_ind", "obj_cls", "pred_cls")
+
+    def _sample_dyn(self, front, opt, rows_cap, n_images):
+        front = dict(front)
+        batch = front.get("compact")
+        if batch is not None:
+            from dataclasses import fields as _fields
+            names = [f.name for f in _fields(batch) if getattr(batch, f.name) is not None]
+            tensors = [getattr(batch, n).contiguous() for n in names]
+            dev = self._check_device(*tensors)
+        else:
+            dev = self._check_device(front["att_feats"], front["att_masks"], front["obj_dist"], front["rel_ind"], front["gpn_obj_ind"])
+            front["gpn_obj_ind"], front["att_masks"] = self._i64(front["gpn_obj_ind"]), self._f32(front["att_masks"])
+            front["att_feats"], front["rel_ind"] = self._f32(front["att_feats"]), self._i64(front["rel_ind"])
+            front["obj_dist"] = self._f32(front["obj_dist"])
+            front["pred_dist"] = None if front.get("pred_dist") is None else self._f32(front["pred_dist"])
+            names = [k for k in self._STEP_INPUTS if front.get(k) is not None]
+            tensors = [front[k] for k in names]
+        w = self._weights()   # (re)packs and drops stale plans before the lookup
+        g = self.gpn_layer
+        skey = ("step", dev.index, batch is not None, tuple(names), tuple(tuple(t.shape) for t in tensors), front.get("seq_per_img"), bool(self.topk_sampling),
+                float(self.topk_temp), int(self.the_k), bool(g.use_nms), float(g.iou_thres), int(g.max_subgraphs))
+        group = self._plans.get(skey)
+        if group is None:
+            while len(self._plans) >= 8:
+                self._plans.pop(next(iter(self._plans)))
+            group = self._plans[skey] = {"ptr": {}, "copy": None}
+        # A captured graph holds the addresses of its inputs.  Callers that pass the same device buffers again (a loader with a fixed
+        # set of staging buffers) get one zero-copy plan per buffer set; any other caller goes through one plan with its own input
+        # buffers, filled by a device-to-device copy per call.
+        pkey = tuple(t.data_ptr() for t in tensors)
+        plan = group["ptr"].get(pkey)
+        if plan is None:
+            if len(group["ptr"]) < 4:
+                plan = group["ptr"][pkey] = self._new_step_plan(dev, rows_cap, tensors, None)
+            else:
+                if group["copy"] is None:
+                    group["copy"] = self._new_step_plan(dev, rows_cap, None, [torch.empty_like(t) for t in tensors])
+                plan = group["copy"]
+        if plan.static_in is not None:
+            for dst, src in zip(plan.static_in, tensors):
+                dst.copy_(src, non_blocking=True)
+            tensors = plan.static_in
+        if batch is not None:
+            from .compact import CompactBatch
+            front["compact"] = CompactBatch(**{**{f.name: None for f in _fields(batch)}, **dict(zip(names, tensors))})
+        else:
+            front.update(dict(zip(names, tensors)))
+        if self.topk_sampling:   # the kernel maps uniforms to tokens by inverse CDF over the kept candidates
+            if "seed" in opt:
+                gen = torch.Generator(device=dev)
+                gen.manual_seed(int(opt["seed"]))
+                plan.out["uniforms"].copy_(torch.rand(self.seq_length, rows_cap, device=dev, generator=gen))
+            else:
+                plan.out["uniforms"].uniform_()
+        plan.calls += 1
+        saved_ws, self._ws = self._ws, plan.ws_obj   # the captured launches keep pointing into this plan's own workspace
+        try:
+            if plan.graph is not None:
+                plan.graph.replay()
+                _DecodePlan.replayed_launches += plan.launches
+                outs = plan.outs
+            elif plan.calls == 1:
+                outs = self._step_body(plan, front, rows_cap, n_images)   # eager: also sets kernel attributes and sizes the workspace
+            else:
+                c0 = lib().subgc_launch_count()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    plan.outs = self._step_body(plan, front, rows_cap, n_images)
+                plan.launches = int(lib().subgc_launch_count() - c0)
+                plan.graph = graph
+                graph.replay()
+                _DecodePlan.replayed_launches += plan.launches
+                outs = plan.outs
+        finally:
+            self._ws = saved_ws
+        # private copies of the results are queued BEFORE the host waits: the launches overlap with the graph's execution
+        res = {k: outs[k].clone() for k in ("seq", "lps", "sub_score", "keep", "image", "status")}
+        st_h = outs["status"].cpu()   # the one host round trip of the call: (steps, fp16-range flag, rows, longest sub-graph)
+        steps, ovf, n_rows = int(st_h[0]), int(st_h[1]), int(st_h[2])
+        if steps < 0:
+            raise _lib.SubgcError(f"persistent decode kernel timed out (wait site {(-steps) // 1000}, CTA {(-steps) % 1000 - 1}); "
+                                  "set SUBGC_MEGA=0 to decode with one launch per stage")
+        if ovf != 0:
+            import warnings
+            self._ovf_dev.zero_()
+            self.use_packed = False
+            warnings.warn("subgc: an activation exceeded the fp16 range of the split-fp16 tensor-core path (|x| > 65504); "
+                          "repeating the call on the fp32 (split-TF32) path, which this model keeps using from now on")
+            return self._sample_impl(front, opt)
+        self.last_steps = res["status"][:1]
+        self.last_gpn_loss = outs["loss"][0]       # these three alias the plan's buffers: valid until the next call with this shape
+        self.last_x_obj = outs["x_obj"]
+        self.last_all_scores = outs["score"]
+        self.last_image_of_row = res["image"][:n_rows]
+        keep = res["keep"][:n_rows]
+        keep_ind = keep if self.gpn_layer.use_nms else keep.to(outs["score"].dtype)
+        return res["seq"][:n_rows], res["lps"][:n_rows], res["sub_score"][:n_rows], keep_ind
+
+    def _new_step_plan(self, dev, rows_cap, keepalive, static_in):
+        L, cd, T, N = lib(), self._cdims, self.seq_length, self.dims.obj_num
+        plan = _DecodePlan(dev, self.dims, rows_cap, N)
+        plan.ws_obj, plan.outs, plan.keepalive, plan.static_in = Workspace(), None, keepalive, static_in
+        o = plan.out
+        o["seq"] = torch.empty(rows_cap, T, dtype=torch.int64, device=dev)
+        o["lps"] = torch.empty(rows_cap, T, device=dev)
+        o["steps"] = torch.empty(1, dtype=torch.int32, device=dev)
+        o["uniforms"] = torch.empty(T, rows_cap, device=dev) if self.topk_sampling else None
+        o["ws"] = torch.empty(L.subgc_decode_workspace_bytes(C.byref(cd), rows_cap, N) + 256, dtype=torch.uint8, device=dev)
+        return plan
 
     def _sample_impl(self, front, opt):
         if not self.test_LSTM:
             raise _lib.SubgcError("mode='sample' needs a model built with opt.test_LSTM=1 (as test.py does)")
+        dyn = self._dyn_eligible(front, opt)
+        if dyn is not None:
+            return self._sample_dyn(front, opt, *dyn)
+        if "compact" in front:
+            front = self._expand_compact(front["compact"])
         self.check_numerics(block=False)
         beam_size = opt.get("beam_size", 1)
         return_att = opt.get("return_att", 0) == 1
@@ -701,9 +934,16 @@ def _forward_train(self, att_feats, seq, att_masks, obj_dist, rel_ind, gpn_obj_i
     data = dict(att_feats=self._f32(att_feats), obj_dist=self._f32(obj_dist), rel_ind=self._i64(rel_ind), labels=self._i64(seq),
                 att_masks=self._f32(att_masks), gpn_obj_ind=self._i64(gpn_obj_ind))
     drop = None
-    if self.training and self.dropout_enabled and self.drop_prob_lm > 0:
-        drop = dict(p=float(self.drop_prob_lm), seed=int(torch.randint(0, 2 ** 31 - 1, (1,)).item()))
-    names, params = zip(*self.named_parameters())
+    if self.training and self.dropout_enabled:
+        # gpn_fc's Dropout(0.5) is active in train mode whatever drop_prob_lm is (reference models/lib/gpn.py:24-28); p = 0 only switches
+        # the four language-model sites off.  The seed comes from torch's CPU generator; rank and device are mixed in so that data-parallel
+        # workers seeded identically still draw different masks (as their independent CUDA generators would)
+        import torch.distributed as dist
+        rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+        seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+        seed = (seed * 1000003 + rank * 8191 + (att_feats.device.index or 0) * 131) % (2 ** 31 - 1)
+        drop = dict(p=float(self.drop_prob_lm), seed=seed)
+    names, params = zip(*self._named_params().items())
     outputs, gpn_loss, score = _TrainStep.apply(self, data, drop, names, *params)
     return outputs, gpn_loss, score
 

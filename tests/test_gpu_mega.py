@@ -170,3 +170,51 @@ def test_return_att_takes_the_per_stage_path():
         ref = O.sample(sd, d, data, use_nms=True, iou_thres=0.75, max_subgraphs=2, return_att=True)
     assert torch.equal(res[0].cpu(), ref["seq"])
     assert _close(res[4].cpu(), ref["att_weights"])
+
+
+@pytest.mark.parametrize("mega", [True, False])
+def test_philox_top3_sampler_distribution(mega):
+    """SURVEY §7 hard part 4: Categorical.sample()'s RNG stream cannot be matched, so the sampler is checked statistically.  128 decode
+    rows share one context, so at t = 0 every row sees the same logits; the first tokens drawn through the C ABI's own Philox stream
+    (uniforms = NULL) over 40 (seed, offset) pairs must follow softmax(q[top 3]) with q = log_softmax(logp / 0.6) (AttModel.py:296-303):
+    chi-square with 2 degrees of freedom, rejected above 18.42 (p = 1e-4); the reported log-prob must be q[token]."""
+    L = _lib.lib()
+    d = Dims()
+    sd = synth.make_state_dict(d, 41, logit_gain=40.0)    # peaked enough for three clearly different probabilities
+    data = synth.make_test_inputs(d, 41, n_images=1, per_half=1, ragged=False, ragged_edges=False)
+    m = _model(d, sd, mega, gpn_nms_thres=0.75, gpn_max_subg=1, use_topk_sampling=1)
+    dev = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in data.items()}
+    S, T = 128, d.seq_length
+    with torch.no_grad():
+        (g_fc, fc, att, p_att, masks), _, _, n_rows, len_max = m._front(dev["att_feats"], dev["att_masks"], dev["obj_dist"], dev["rel_ind"],
+                                                                        dev["pred_dist"], dev["gpn_obj_ind"])
+        assert n_rows == 1
+        fc, att, p_att, masks = (t.expand(S, *t.shape[1:]).contiguous() for t in (fc, att, p_att, masks))
+        logp0, _ = m.get_logprobs_state(torch.zeros(1, dtype=torch.long, device="cuda"), fc[:1], att[:1], p_att[:1], masks[:1], m.init_hidden(1))
+    q = torch.log_softmax(logp0[0].double().cpu() / 0.6, 0)
+    top = q.topk(3)
+    probs = torch.softmax(top.values, 0).numpy()
+    assert probs.min() > 0.02, probs          # every cell gets enough expected counts
+    w, cd = m._weights(), m._cdims
+    assert bool(w.mega) == mega
+    seq = torch.empty(S, T, dtype=torch.int64, device="cuda")
+    lps = torch.empty(S, T, device="cuda")
+    steps = torch.empty(1, dtype=torch.int32, device="cuda")
+    ws = torch.empty(L.subgc_decode_workspace_bytes(C.byref(cd), S, len_max) + 256, dtype=torch.uint8, device="cuda")
+    counts = np.zeros(3)
+    draws = 0
+    for rep in range(40):
+        _lib.check(L.subgc_decode_sample(C.byref(cd), C.byref(w), S, len_max, 1, 0.6, 3, 1234 + rep, 77 * rep, None, fc.data_ptr(), att.data_ptr(),
+                                         p_att.data_ptr(), masks.data_ptr(), seq.data_ptr(), lps.data_ptr(), None, steps.data_ptr(), ws.data_ptr(),
+                                         ws.numel(), torch.cuda.current_stream().cuda_stream), "subgc_decode_sample")
+        tok, lp = seq[:, 0].cpu(), lps[:, 0].cpu()
+        for c in range(3):
+            hit = tok == int(top.indices[c])
+            counts[c] += int(hit.sum())
+            if hit.any():
+                assert float((lp[hit].double() - top.values[c]).abs().max()) <= 2e-5 * max(1.0, float(top.values.abs().max()))
+        draws += S
+    assert counts.sum() == draws, "a token outside the top 3 was drawn"
+    chi2 = float(((counts - draws * probs) ** 2 / (draws * probs)).sum())
+    assert chi2 < 18.42, (chi2, counts, draws * probs)
+    assert len(set(seq[:, 0].tolist())) > 1, "rows must not share one uniform"

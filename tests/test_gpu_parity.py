@@ -107,6 +107,42 @@ def test_golden_stages(case):
         assert rel_err(t2n(st0[0][:, :, :64]), g["step0_h_slice"]) <= RTOL
 
 
+def test_golden_edge_stream(case):
+    """The predicate half of the encoder: p0 = W_p E_pred[argmax] + b_p (AttModel.py:382-387) and x_pred, the edge
+    output of gcn_backbone (models/lib/gcn_backbone.py:29-53: layer-0 units 0/1, layer-1 units 2/3, residual on the edge stream), which
+    the Sub-GC decoder never reads and encode() therefore skips unless asked."""
+    g, d, sd, data, nms, model, dev = case
+    with torch.no_grad():
+        x_obj, x_pred = model.encode(dev["att_feats"], dev["obj_dist"], dev["pred_dist"], dev["rel_ind"], want_x_pred=True)
+        p0 = model._p0
+        x_obj_only = model.encode(dev["att_feats"], dev["obj_dist"], dev["pred_dist"], dev["rel_ind"])
+        assert model._p0 is None, "without the edge output the predicate embedding is not computed at all (Sub-GC: dead sub-path)"
+    if "x_pred" in g.files:   # fixtures of the real reference
+        ref_p0, ref_xp, ref_xo = g["p0"][0], g["x_pred"], g["x_obj"]
+    else:                      # full size: the oracle (pinned to the reference by the small fixtures)
+        with torch.no_grad():
+            rx0, rp0 = O.fuse_features(sd, d, data["att_feats"], data["obj_dist"], data["pred_dist"])
+            rxo, rxp = O.gcn_encode(sd, d, rx0, rp0, data["rel_ind"])
+        ref_p0, ref_xp, ref_xo = rp0[0].numpy(), rxp[0].numpy(), rxo[0].numpy()
+    assert x_pred.shape == (1, d.rel_num, d.gcn)
+    assert rel_err(t2n(p0[0]), ref_p0) <= RTOL
+    assert rel_err(t2n(x_pred[0]), ref_xp) <= RTOL
+    assert rel_err(t2n(x_obj[0]), ref_xo) <= RTOL
+    assert torch.equal(x_obj, x_obj_only), "x_obj must not depend on whether the edge stream is materialised"
+
+
+def test_edge_stream_multi_image_against_oracle():
+    d = Dims()
+    sd = synth.make_state_dict(d, 5)
+    data = synth.make_test_inputs(d, 5, n_images=3, per_half=1, ragged=True, ragged_edges=True)
+    model = make_model(d, sd)
+    dev = to_dev(data)
+    with torch.no_grad():
+        x_obj, x_pred = model.encode(dev["att_feats"], dev["obj_dist"], dev["pred_dist"], dev["rel_ind"], want_x_pred=True)
+        rxo, rxp = O.encode(sd, d, data["att_feats"], data["obj_dist"], data["pred_dist"], data["rel_ind"])
+    assert rel_err(t2n(x_pred), rxp.numpy()) <= RTOL and rel_err(t2n(x_obj), rxo.numpy()) <= RTOL
+
+
 def test_golden_greedy(case):
     g, d, sd, data, nms, model, dev = case
     with torch.no_grad():
