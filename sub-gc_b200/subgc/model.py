@@ -96,11 +96,23 @@ class _DecodePlan:
         else:
             c0 = lib().subgc_launch_count()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # torch.cuda.graph caches ONE default capture stream per process (on the device that was current first): pass a stream
+            # of the device this plan lives on
+            with torch.cuda.graph(g, stream=_capture_stream(self.fc.device)):
                 launch()
             self.launches = int(lib().subgc_launch_count() - c0)   # kernels per replay (counted while capturing; capture does not run them)
             self.graph = g
             g.replay()
+
+
+_capture_streams = {}
+
+
+def _capture_stream(dev):
+    st = _capture_streams.get(dev.index)
+    if st is None:
+        st = _capture_streams[dev.index] = torch.cuda.Stream(device=dev)
+    return st
 
 
 class _TrainStep(torch.autograd.Function):
@@ -729,7 +741,7 @@ class TopDownModel(nn.Module):
             else:
                 c0 = lib().subgc_launch_count()
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
+                with torch.cuda.graph(graph, stream=_capture_stream(dev)):
                     plan.outs = self._step_body(plan, front, rows_cap, n_images)
                 plan.launches = int(lib().subgc_launch_count() - c0)
                 plan.graph = graph

@@ -53,8 +53,11 @@ def test_loss_wrapper_under_dataparallel_matches_per_shard_mean():
     for s in range(2):
         assert abs(float(out["lang_loss"][s]) - shard_losses[s][0]) <= 1e-5 * max(1.0, abs(shard_losses[s][0]))
         assert abs(float(out["gpn_loss"][s]) - shard_losses[s][1]) <= 1e-5
-    assert set(got) == set(shard_grads[0])
+    assert set(shard_grads[0]) <= set(got)
     for n in got:
+        if n not in shard_grads[0]:   # parameters of the dead GCN sub-path: no gradient on one device, zeros through DataParallel's broadcast
+            assert float(got[n].abs().sum()) == 0.0, n
+            continue
         ref = 0.5 * (shard_grads[0][n] + shard_grads[1][n])
         assert rel_err(t2n(got[n]), t2n(ref)) <= 2e-5 or float(ref.abs().max()) < 1e-12, n
 
