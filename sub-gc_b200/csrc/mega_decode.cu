@@ -187,6 +187,13 @@ __device__ __forceinline__ void x_store(uint8_t* buf, int row, int col, float v,
     *reinterpret_cast<unsigned short*>(buf + o + MG_XTILE_BYTES / 2) = l;
 }
 
+// LSTM cell non-linearities from the ex2 / rcp units: sigmoid and tanh to ~2e-7 absolute (libdevice's expf / tanhf cost ~5x the
+// instructions, and the cells are two of the hand-offs every step waits for); |h| < 1, so this is far below the 2e-5 bar
+__device__ __forceinline__ float mg_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float mg_tanh(float x) {
+    const float e = __expf(-2.f * fabsf(x));
+    return copysignf(__fdividef(1.f - e, 1.f + e), x);
+}
 __device__ __forceinline__ float mg_tanh_score(float x) {   // same form as decode.cu: ex2-based, |err| <= 2e-7
     const float e = __expf(-2.f * fabsf(x));
     return copysignf(__fdividef(1.f - e, 1.f + e), x);
@@ -464,9 +471,26 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
 #pragma unroll
                     for (int j = 0; j < 16; ++j) __stcg(o + (size_t)j * 128, v[j]);
                 } else {
-                    float4* o = reinterpret_cast<float4*>(dst + (size_t)r * ld + chunk * 16);
+                    // A lane holds 64 contiguous bytes of its row.  Lane pairs swap halves so that every store instruction writes
+                    // 32 contiguous bytes per pair (full sectors) instead of 16 per lane (half sectors: measured ~1.5 us slower per tile)
+                    const bool odd = lane & 1;
+                    float sa[4], sb[4], ra_[4], rb_[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) __stcg(o + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+                    for (int e = 0; e < 4; ++e) { sa[e] = odd ? v[e] : v[4 + e]; sb[e] = odd ? v[8 + e] : v[12 + e]; }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { ra_[e] = __shfl_xor_sync(0xffffffffu, sa[e], 1); rb_[e] = __shfl_xor_sync(0xffffffffu, sb[e], 1); }
+                    const int r_even = r & ~1, r_odd = r | 1;
+                    float* oe = dst + (size_t)r_even * ld + chunk * 16 + (odd ? 4 : 0);
+                    float* oo = dst + (size_t)r_odd * ld + chunk * 16 + (odd ? 4 : 0);
+                    // even row: pieces 0,1 then 2,3; odd row: pieces 0,1 then 2,3 (piece = 4 floats; the even lane writes pieces 0 / 2)
+                    const float4 e0 = odd ? make_float4(ra_[0], ra_[1], ra_[2], ra_[3]) : make_float4(v[0], v[1], v[2], v[3]);
+                    const float4 e1 = odd ? make_float4(rb_[0], rb_[1], rb_[2], rb_[3]) : make_float4(v[8], v[9], v[10], v[11]);
+                    const float4 o0 = odd ? make_float4(v[4], v[5], v[6], v[7]) : make_float4(ra_[0], ra_[1], ra_[2], ra_[3]);
+                    const float4 o1 = odd ? make_float4(v[12], v[13], v[14], v[15]) : make_float4(rb_[0], rb_[1], rb_[2], rb_[3]);
+                    __stcg(reinterpret_cast<float4*>(oe), e0);
+                    __stcg(reinterpret_cast<float4*>(oe + 8), e1);
+                    __stcg(reinterpret_cast<float4*>(oo), o0);
+                    __stcg(reinterpret_cast<float4*>(oo + 8), o1);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -517,25 +541,50 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
             }
             if (!w_counter(tile_cnt, (unsigned)jb.n_split * (unsigned)(t + 1), 9)) return false;
             if (wt == 0) MG_STAMP(t, ev);
+            // every partial of both elements of this thread is requested before the first one is used (one L2 round trip)
+            float acc2[2][4];
+            if (jb.n_split <= 4) {
+                float pz[2][4][4];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const int e = wt + k * MG_NW;
+                    const int r = e & 127, ul = jb.u_lo + (e >> 7);
+                    const bool live = e < nel && r < S;
+                    const float* g = part + jb.part_tile_off + r;
+#pragma unroll
+                    for (int z = 0; z < 4; ++z) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            pz[k][z][q] = (live && z < jb.n_split) ? __ldcg(g + (size_t)z * 16384 + (size_t)(q * jb.tile_units + ul) * 128) : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc2[k][q] = ((pz[k][0][q] + pz[k][1][q]) + pz[k][2][q]) + pz[k][3][q];   // split order
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const int e = wt + k * MG_NW;
+                    const int r = e & 127, ul = jb.u_lo + (e >> 7);
+                    const bool live = e < nel && r < S;
+                    const float* g = part + jb.part_tile_off + r;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc2[k][q] = 0.f;
+                    for (int z = 0; z < jb.n_split; ++z) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) acc2[k][q] += live ? __ldcg(g + (size_t)z * 16384 + (size_t)(q * jb.tile_units + ul) * 128) : 0.f;
+                    }
+                }
+            }
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const int e = wt + k * MG_NW;
                 if (e >= nel) continue;
                 const int r = e & 127, ul = jb.u_lo + (e >> 7), u = jb.tile_u0 + ul;
                 if (r >= S) continue;
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                const float* g = part + jb.part_tile_off + r;
-                float pz[8][4];
-#pragma unroll
-                for (int z = 0; z < 8; ++z) {   // n_split <= 8: every load of the element is in flight before the first add
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) pz[z][q] = z < jb.n_split ? __ldcg(g + (size_t)z * 16384 + (size_t)(q * jb.tile_units + ul) * 128) : 0.f;
-                }
-#pragma unroll
-                for (int z = 0; z < 8; ++z) {   // split order: deterministic
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) acc[q] += pz[z][q];
-                }
+                float acc[4] = {acc2[k][0], acc2[k][1], acc2[k][2], acc2[k][3]};
                 if (is_att) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) acc[q] += add[k][q];
@@ -543,9 +592,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
 #pragma unroll
                     for (int q = 0; q < 4; ++q) acc[q] = (acc[q] + __ldg(p.lang_b_ih + q * H + u)) + __ldg(p.lang_b_hh + q * H + u);
                 }
-                const float c = sigmoidf_(acc[1]) * cst[k] + sigmoidf_(acc[0]) * tanhf(acc[2]);
+                const float c = mg_sigmoid(acc[1]) * cst[k] + mg_sigmoid(acc[0]) * mg_tanh(acc[2]);
                 cst[k] = c;
-                x_store(xout, r, u, sigmoidf_(acc[3]) * tanhf(c), ovf);
+                x_store(xout, r, u, mg_sigmoid(acc[3]) * mg_tanh(c), ovf);
             }
             if (wt == 0) MG_STAMP(t, ev == 3 ? 17 : 19);
             return true;
@@ -627,30 +676,65 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                     s_e[wt] = e + __ldg(p.alpha_b);
                 }
                 worker_bar();
+                // the att rows of the context sum do not depend on the weights: the first nodes of this thread's column quad are requested
+                // now and land while one warp finishes the softmax
+                constexpr int kPre = 8;
+                const float* af = p.att + (size_t)row * lst * H;
+                const int grp = wt >> 8, tg = wt & 255, H4 = H >> 2;
+                float4 pre[kPre];
+#pragma unroll
+                for (int i = 0; i < kPre; ++i) {
+                    const int n = grp + 2 * i;
+                    pre[i] = (tg < H4 && n < len_max) ? __ldg(reinterpret_cast<const float4*>(af + (size_t)n * H) + tg) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
                 if (ww == 0) {   // softmax, then mask, then renormalise: two-stage as the reference (AttModel.py:462-466)
                     float m = -INFINITY;
                     for (int n = lane; n < len_max; n += 32) m = fmaxf(m, s_e[n]);
                     m = warp_max(m);
+                    float ex[2] = {0.f, 0.f};   // len_max <= 64: two elements per lane, exponentials evaluated once
                     float sum = 0.f;
-                    for (int n = lane; n < len_max; n += 32) sum += expf(s_e[n] - m);
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int n = lane + 32 * i;
+                        if (n < len_max) { ex[i] = expf(s_e[n] - m); sum += ex[i]; }
+                    }
                     sum = warp_sum(sum);
                     float msum = 0.f;
-                    for (int n = lane; n < len_max; n += 32) {
-                        const float wv = expf(s_e[n] - m) / sum * s_mask[n];
-                        s_e[n] = wv;
-                        msum += wv;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int n = lane + 32 * i;
+                        if (n < len_max) { ex[i] = ex[i] / sum * s_mask[n]; msum += ex[i]; }
                     }
                     msum = warp_sum(msum);
-                    for (int n = lane; n < len_max; n += 32) s_e[n] = s_e[n] / msum;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int n = lane + 32 * i;
+                        if (n < len_max) s_e[n] = ex[i] / msum;
+                    }
                 }
                 worker_bar();
                 MG_WSTAMP(43);
                 {   // context: two thread groups take interleaved node subsets, partials combined in fixed order
-                    const float* af = p.att + (size_t)row * lst * H;
-                    const int grp = wt >> 8, tg = wt & 255, H4 = H >> 2;
-                    for (int j4 = tg; j4 < H4; j4 += 256) {
+                    if (tg < H4) {
                         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 10
+#pragma unroll
+                        for (int i = 0; i < kPre; ++i) {
+                            const int n = grp + 2 * i;
+                            if (n < len_max) {
+                                const float wv = s_e[n];
+                                a.x = fmaf(wv, pre[i].x, a.x); a.y = fmaf(wv, pre[i].y, a.y); a.z = fmaf(wv, pre[i].z, a.z); a.w = fmaf(wv, pre[i].w, a.w);
+                            }
+                        }
+#pragma unroll 12
+                        for (int n = grp + 2 * kPre; n < len_max; n += 2) {
+                            const float4 v = __ldg(reinterpret_cast<const float4*>(af + (size_t)n * H) + tg);
+                            const float wv = s_e[n];
+                            a.x = fmaf(wv, v.x, a.x); a.y = fmaf(wv, v.y, a.y); a.z = fmaf(wv, v.z, a.z); a.w = fmaf(wv, v.w, a.w);
+                        }
+                        reinterpret_cast<float4*>(s_c + (size_t)grp * H)[tg] = a;
+                    }
+                    for (int j4 = tg + 256; j4 < H4; j4 += 256) {   // H > 1024 only
+                        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
                         for (int n = grp; n < len_max; n += 2) {
                             const float4 v = __ldg(reinterpret_cast<const float4*>(af + (size_t)n * H) + j4);
                             const float wv = s_e[n];
