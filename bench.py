@@ -239,7 +239,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     d = Dims()
-    config = {"workload": f"BASELINE config 2: {IMAGES_PER_GPU} images/GPU x 36 nodes x 2048-d, 64 edges, 1 full sub-graph kept per image "
+    cfg_no = {"greedy": "2", "beam": "3 (beam_size 5)", "topk": "4 shard (top-k sampling, k=3, temp 0.6)", "train": "5"}[args.mode]
+    config = {"workload": f"BASELINE config {cfg_no}: {IMAGES_PER_GPU} images/GPU x 36 nodes x 2048-d, 64 edges, 1 full sub-graph kept per image "
                           f"(NMS 0.75/max 1), {args.mode} 20-token decode, V=9487",
               "images_per_gpu": IMAGES_PER_GPU, "rows_per_gpu": IMAGES_PER_GPU, "decode": args.mode, "weights": "random init (synthetic), fp32 (+ split-fp16 packed copies of the same 4 bytes per weight for the tensor cores)",
               "l2": "per-step working set (280 MB weights + 83 MB inputs + activations) exceeds the 126 MB L2; no explicit flush"}
@@ -426,25 +427,34 @@ def main():
             "stage_note": "stage times and roofline.launch_ms come from a second pass with CUDA events between the stages; `value` is the "
                           "whole step replayed as one CUDA graph (encoder .. persistent decode kernel, no host round trip before the results)",
             "decode_steps_executed": steps_exec}
-    if args.mode != "beam" and "decode" in stage_ms:
-        t_dec = stage_ms["decode"] / args.steps * 1e-3           # one launch of the decode loop (subgc_decode_sample)
+    if "decode" in stage_ms:
+        t_dec = stage_ms["decode"] / args.steps * 1e-3           # one launch of the decode loop
         algo_steps = d.seq_length                                 # 20 algorithmic steps per caption
-        algo_bytes = algo_steps * (W_BYTES + n_rows * ROW_BYTES)
-        achieved = algo_bytes / t_dec / 1e9
+        dec_rows = n_rows * (5 if args.mode == "beam" else 1)     # decoder rows in flight (beam search: 5 beams per sub-graph)
+        algo_bytes = algo_steps * (W_BYTES + dec_rows * ROW_BYTES)
+        algo_flops = algo_steps * dec_rows * ROW_FLOPS
+        hbm = {"achieved": algo_bytes / t_dec / 1e9, "peak": hbm_peak, "unit": "GB/s"}
+        # the contractions run as 3 tcgen05 kind::f16 products per fp32 product (split-fp16 operands): the tensor-pipe roofline counts them
+        tens = {"achieved": 3 * algo_flops / t_dec / 1e12, "peak": tf_peak, "unit": "TFLOP/s"}
         traffic, traffic_note = None, "no ncu capture found under profiles/"
-        tp = os.path.join(ROOT, "profiles", "r01_decode_traffic.json")
-        if os.path.isfile(tp) and args.mode == "greedy":
+        tp = os.path.join(ROOT, "profiles", "r02_decode_traffic.json")
+        if os.path.isfile(tp) and args.mode in ("greedy", "topk"):
             tj = json.load(open(tp))
             traffic, traffic_note = tj["dram_bytes_per_decode_loop"], tj["note"]
-        line["roofline"] = {"bound": "hbm", "kernel": "mega_decode_kernel: the decode loop of subgc_decode_sample as one persistent cooperative "
-                                                      "launch (20 x [att-LSTM, cell, h2att, attention, lang-LSTM, cell, logit, select])",
-                            "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                            "traffic": traffic, "traffic_note": traffic_note,
-                            "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
-                            "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": t_dec * 1e3,
-                            "tensor_equiv": {"achieved_tflops": algo_steps * n_rows * ROW_FLOPS / t_dec / 1e12, "peak_tflops": tf_peak,
-                                             "note": "algorithmic flops; the contractions run as 3 tcgen05 kind::f16 products per fp32 product "
-                                                     "(split-fp16 operands, fp32 accumulation in TMEM)"}}
+        bound = "tensor" if tens["achieved"] / tens["peak"] > hbm["achieved"] / hbm["peak"] else "hbm"
+        main = tens if bound == "tensor" else hbm
+        kernel = ("mega_decode_kernel: the decode loop of subgc_decode_sample as one persistent cooperative launch (20 x [att-LSTM, cell, h2att, "
+                  "attention, lang-LSTM, cell, logit, select])") if args.mode != "beam" else \
+                 ("decode loop of subgc_decode_beam: 20 x [att-LSTM, cell, h2att, attention, lang-LSTM, cell, logit contraction (h3_gemm_kernel), "
+                  "per-row top-b, beam step], 640 rows, one CUDA graph")
+        line["roofline"] = {"bound": bound, "kernel": kernel, "achieved": main["achieved"], "peak": main["peak"], "unit": main["unit"],
+                            "frac": main["achieved"] / main["peak"], "traffic": traffic, "traffic_note": traffic_note,
+                            "peak_source": peak_kind + " (MEASURED_PEAKS.json: hbm_gbs / bf16_tflops_sustained)",
+                            "algorithmic_bytes_per_launch": algo_bytes, "algorithmic_flops_per_launch": algo_flops, "launch_ms": t_dec * 1e3,
+                            "hbm": dict(hbm, frac=hbm["achieved"] / hbm["peak"]),
+                            "tensor": dict(tens, frac=tens["achieved"] / tens["peak"],
+                                           note="3 x algorithmic flops: every fp32 product is three fp16 tensor-core products (hi.hi, hi.lo, lo.hi) "
+                                                "with fp32 accumulation in TMEM")}
     if not args.no_cpu_baseline:
         n_sample = 16 if args.mode == "beam" else IMAGES_PER_GPU
         ref = reference_arm(d, sd, data, args.mode, 1, 1, cores, n_sample, check_seq=out[0])

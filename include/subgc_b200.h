@@ -242,6 +242,11 @@ int subgc_subgraph_nms(const subgc_dims* d, const subgc_subgraph_layout* lay, co
                        double iou_thres, int max_subgraphs, int32_t* sel, int64_t* keep_ind, int32_t* stats,
                        void* ws, size_t ws_bytes, subgc_stream_t stream);
 
+/* Post-decode ordering (misc/eval_utils.py:105-110: `torch.sort(subgraph_score, descending=True)` per image, then seq / keep_ind are
+ * indexed with it).  Rows of an image are contiguous; order [n_rows] lists, image by image, the rows by descending score (ties: lower
+ * row first).  score [n_rows], image_of_row [n_rows] int64 (ascending). */
+int subgc_rank_rows(int n_rows, const float* score, const int64_t* image_of_row, int64_t* order, subgc_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Decoder feature preparation: replaces gpn read_out_proj (models/lib/gpn.py:79,95), AttModel.clip_att /
  * _prepare_feature / pack_wrapper (models/AttModel.py:16-36,348-368) for the n_rows selected sub-graphs `sel`:
@@ -378,6 +383,17 @@ int subgc_gcn_node_bwd(int B, int N, int K, int L, const float* dx, const float*
                        const int64_t* rel_ind, float* dm_subj, float* dm_obj, subgc_stream_t stream);
 int subgc_gcn_edge_bwd(int B, int N, int K, int L, const float* dp, const float* m_subj, const float* m_obj,
                        const int64_t* rel_ind, float* dm_subj, float* dm_obj, subgc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Optimiser step: utils.clip_gradient_norm(optimizer, clip) (misc/utils.py:174-200) + torch.optim.Adam.step()
+ * (misc/utils.py:236, train.py:107,163-164) over every parameter in two multi-tensor passes.  `chunks` is a DEVICE table of
+ * n_chunks entries {float* p; const float* g; float* m; float* v; int32 n; int32 pad} (24 + 8 bytes), each covering at most
+ * subgc_opt_chunk_elems() consecutive elements of one parameter.  partial [n_chunks] is scratch; norm_out[0] = total gradient
+ * norm, norm_out[1] = clip coefficient (both stay on the device: no host sync).  step = 1, 2, ... (bias correction).
+ * write_grad != 0 also stores the scaled gradients back, as the reference's in-place p.grad.mul_(norm) does. */
+int subgc_opt_chunk_elems(void);
+int subgc_clip_adam_step(const void* chunks, int n_chunks, float clip_norm, float lr, float beta1, float beta2, float eps,
+                         float weight_decay, int step, int write_grad, float* partial, float* norm_out, subgc_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -444,3 +444,40 @@ def loss_wrapper(sd, dims, data, seq_per_img=5, drop=None):
     r = forward_train(sd, dims, data, seq_per_img, drop)
     lang = language_model_criterion(r["outputs"], data["labels"][:, 1:], data["masks"][:, 1:])
     return dict(gpn_loss=r["gpn_loss"], lang_loss=lang, **{k: v for k, v in r.items() if k not in ("gpn_loss",)})
+
+
+# ----------------------------------------------------------------------------------------------------------
+# post-decode
+# ----------------------------------------------------------------------------------------------------------
+BAD_ENDINGS = ['with', 'in', 'on', 'of', 'a', 'at', 'to', 'for', 'an', 'this', 'his', 'her', 'that', 'the']   # misc/utils.py:16-17
+
+
+def decode_sequence(ix_to_word, seq, remove_bad_endings=False):
+    """misc/utils.py:59-81, token by token as the reference does it."""
+    out = []
+    for i in range(seq.shape[0]):
+        txt = ''
+        for j in range(seq.shape[1]):
+            ix = int(seq[i, j])
+            if ix > 0:
+                if j >= 1:
+                    txt = txt + ' '
+                txt = txt + ix_to_word[str(ix)]
+            else:
+                break
+        if remove_bad_endings:
+            flag = 0
+            words = txt.split(' ')
+            for j in range(len(words)):
+                if words[-j - 1] not in BAD_ENDINGS:
+                    flag = -j
+                    break
+            txt = ' '.join(words[0:len(words) + flag])
+        out.append(txt)
+    return out
+
+
+def sort_by_score(seq, subgraph_score, keep_ind):
+    """misc/eval_utils.py:105-110 for ONE image."""
+    sorted_score, sort_ind = torch.sort(subgraph_score, descending=True, stable=True)
+    return seq[sort_ind], sorted_score, keep_ind[sort_ind], sort_ind

@@ -219,6 +219,24 @@ __global__ void __launch_bounds__(256) nms_compact_kernel(const subgc_subgraph_l
     if (threadIdx.x == 0) stats[1] = s_maxlen;
 }
 
+// Post-decode ordering (reference misc/eval_utils.py:105-110): the captions of an image are listed by descending sGPN score.  Rows of
+// one image are contiguous (subgc_subgraph_nms emits images in order); order[first + rank] = row with rank = number of rows of the
+// same image that come before it (higher score, or equal score and lower row index: a stable descending sort).
+__global__ void __launch_bounds__(256) rank_rows_kernel(const float* __restrict__ score, const long long* __restrict__ image_of_row, int n_rows,
+                                                        long long* __restrict__ order) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    const long long img = image_of_row[i];
+    const float si = score[i];
+    int first = i, rank = 0;
+    while (first > 0 && image_of_row[first - 1] == img) --first;
+    for (int j = first; j < n_rows && image_of_row[j] == img; ++j) {
+        const float sj = score[j];
+        rank += (sj > si || (sj == si && j < i)) ? 1 : 0;
+    }
+    order[first + rank] = i;
+}
+
 static int check_layout(const subgc_subgraph_layout* l) {
     SUBGC_CHECK_ARG(l != nullptr, "layout is null");
     SUBGC_CHECK_ARG(l->rows > 0 && l->per_half > 0 && l->seq_per_img > 0 && (l->order == 0 || l->order == 1), "bad sub-graph layout");
@@ -302,6 +320,14 @@ extern "C" int subgc_subgraph_nms(const subgc_dims* d, const subgc_subgraph_layo
                                                   use_nms, iou_thres, max_subgraphs, kept, counts);
     SUBGC_LAUNCH_CHECK();
     nms_compact_kernel<<<1, 256, 0, st>>>(*lay, kept, counts, sub_len, n_images, sel, reinterpret_cast<long long*>(keep_ind), stats, offsets);
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}
+
+extern "C" int subgc_rank_rows(int n_rows, const float* score, const int64_t* image_of_row, int64_t* order, subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(n_rows > 0 && score && image_of_row && order, "subgc_rank_rows: bad arguments");
+    rank_rows_kernel<<<(n_rows + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(score, reinterpret_cast<const long long*>(image_of_row), n_rows,
+                                                                                       reinterpret_cast<long long*>(order));
     SUBGC_LAUNCH_CHECK();
     return SUBGC_OK;
 }

@@ -81,6 +81,7 @@ SIGNATURES = {
     "subgc_sgpn_select_train": (_i, [_P(Layout), c_fp, c_fp, c_fp, c_fp, c_fp]),
     "subgc_nms_workspace_bytes": (_sz, [_i, _i]),
     "subgc_subgraph_nms": (_i, [_P(Dims), _P(Layout), c_fp, c_fp, c_fp, c_fp, _i, _d, _i, c_fp, c_fp, c_fp, c_fp, _sz, c_fp]),
+    "subgc_rank_rows": (_i, [_i, c_fp, c_fp, c_fp, c_fp]),
     "subgc_prepare_workspace_bytes": (_sz, [_P(Dims), _i, _i]),
     "subgc_prepare_forward": (_i, [_P(Dims), _P(Weights), _P(Layout), _i, _i, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp,
                                    c_fp, c_fp, c_fp, _sz, c_fp]),
@@ -96,6 +97,8 @@ SIGNATURES = {
     "subgc_beam_workspace_bytes": (_sz, [_P(Dims), _i, _i, _i]),
     "subgc_decode_beam": (_i, [_P(Dims), _P(Weights), _i, _i, _i, _i, _d, _i, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp,
                                c_fp, _sz, c_fp]),
+    "subgc_opt_chunk_elems": (_i, []),
+    "subgc_clip_adam_step": (_i, [c_fp, _i, _f, _f, _f, _f, _f, _f, _i, _i, c_fp, c_fp, c_fp]),
     # training building blocks
     "subgc_gemm_nt_workspace_bytes": (_sz, [_i, _i, _i]),
     "subgc_gemm_nt": (_i, [_i, _i, _i, c_fp, _i, c_fp, c_fp, _i, c_fp, _i, _i, c_fp, _i, c_fp, _sz, c_fp]),
