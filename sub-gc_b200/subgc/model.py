@@ -136,7 +136,7 @@ class _TrainStep(torch.autograd.Function):
         if d_outputs is None:
             d_outputs = torch.zeros_like(saved["outputs"])
         dg = 0.0 if d_gpn_loss is None else float(d_gpn_loss)
-        G = train.backward(ops, P, model.dims, saved, d_outputs.contiguous(), dg)
+        G = train.backward(ops, P, model.dims, saved, d_outputs.contiguous(), dg, reducer=getattr(model, "grad_reducer", None))
         return (None, None, None, None) + tuple(G.get(n) for n in names)
 
 
@@ -262,6 +262,7 @@ class TopDownModel(nn.Module):
         self._states = {}   # device index -> _DeviceState (shared by DataParallel replicas, which live on different devices)
         self.use_packed = True   # inference contractions read split-fp16 copies of the weights (subgc.packing)
         self.use_mega = True     # greedy / top-k loops of <= 128 rows run as one persistent kernel (csrc/mega_decode.cu)
+        self.grad_reducer = None     # subgc.parallel.GradReducer: gradient all-reduce overlapped with the hand-written backward (one process per GPU)
         self.use_step_graph = True   # ... and then the whole call (encoder .. decode) replays as ONE CUDA graph without host round trips
         self.stage_events = None  # set to [] to collect (name, start_event, end_event) per stage (bench / profiling)
         self.dropout_enabled = True   # tests switch it off: Philox masks cannot match torch's RNG stream (SURVEY §7 hard part 5)

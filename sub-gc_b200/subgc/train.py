@@ -406,21 +406,28 @@ def need_pred_path(d):
 # ------------------------------------------------------------------------------------------------------------------
 # backward
 # ------------------------------------------------------------------------------------------------------------------
-def backward(ops, P, d, S, d_outputs, d_gpn_loss):
+def backward(ops, P, d, S, d_outputs, d_gpn_loss, reducer=None):
     """Gradients of every parameter given d(outputs) [rows, T, V1] and the scalar d(gpn_loss).  Returns name -> tensor
-    (parameters that cannot influence the outputs are absent: the reference leaves their .grad at None)."""
+    (parameters that cannot influence the outputs are absent: the reference leaves their .grad at None).
+    reducer (subgc.parallel.GradReducer, optional): gradients are allocated inside its flat buckets and each bucket's all-reduce is
+    started as soon as its last gradient kernel is enqueued (decoder -> prepare -> sGPN / GCN / fusion)."""
     dev = S["x0"].device
     G = {}
+    if reducer is not None:
+        reducer.begin()
+
+    def new_grad(name):
+        return torch.zeros_like(P[name]) if reducer is None else reducer.alloc(name, P[name])
 
     def acc_w(name, dy, x):
         """grad[name] += dy^T @ x   (dy [rows, N], x [rows, K])"""
         if name not in G:
-            G[name] = torch.zeros_like(P[name])
+            G[name] = new_grad(name)
         ops.linear(ops.transpose(dy), ops.transpose(x), out=G[name], accumulate=True)
 
     def acc_b(name, dy):
         if name not in G:
-            G[name] = torch.zeros_like(P[name])
+            G[name] = new_grad(name)
         ops.colsum(dy, G[name], accumulate=True)
 
     tcache = {}
@@ -445,8 +452,8 @@ def backward(ops, P, d, S, d_outputs, d_gpn_loss):
     d_fc = torch.zeros(rows, H, device=dev)
     dh_att_n = dc_att_n = dh_lang_n = dc_lang_n = None
     aw = P["core.attention.alpha_net.weight"]
-    G["core.attention.alpha_net.bias"] = torch.zeros_like(P["core.attention.alpha_net.bias"])  # softmax is shift-invariant: exactly zero
-    G["embed.0.weight"] = torch.zeros_like(P["embed.0.weight"])
+    G["core.attention.alpha_net.bias"] = new_grad("core.attention.alpha_net.bias")  # softmax is shift-invariant: exactly zero
+    G["embed.0.weight"] = new_grad("embed.0.weight")
 
     for t in range(S["n_exec"] - 1, -1, -1):
         st = S["steps"][t]
@@ -488,6 +495,8 @@ def backward(ops, P, d, S, d_outputs, d_gpn_loss):
         dh_att_n = dx_of(dg1, "core.att_lstm.weight_hh")
         dc_att_n, dc_lang_n = dc_att_prev, dc_lang_prev
 
+    if reducer is not None:
+        reducer.bucket_done(0, G)   # logit / embed / LSTMs / attention are final: their all-reduce overlaps everything below
     # ---- feature preparation ----
     if S["m_fc"] is not None:
         d_fc = ops.mul(d_fc, S["m_fc"])
@@ -509,6 +518,8 @@ def backward(ops, P, d, S, d_outputs, d_gpn_loss):
     d_xobj = torch.zeros(B * N, Lg, device=dev)
     ops.scatter_add_rows(dx_of(d_attp, "att_embed.0.weight"), S["node_row"], d_xobj)
 
+    if reducer is not None:
+        reducer.bucket_done(1, G)
     # ---- sGPN ----
     n_sub = S["n_sub"]
     dz = ops.bce_bwd(S["lay"], S["score"], float(d_gpn_loss) / n_sub).view(n_sub, 1)
@@ -563,6 +574,9 @@ def backward(ops, P, d, S, d_outputs, d_gpn_loss):
     acc_w("obj_v_proj.weight", d_x0, S["att_feats"].reshape(B * N, -1)); acc_b("obj_v_proj.bias", d_x0)
     emb_rows = ops.gather_rows(P["sg_obj_embed.weight"], S["cls"])
     acc_w("obj_emb_proj.weight", d_x0, emb_rows); acc_b("obj_emb_proj.bias", d_x0)
-    G["sg_obj_embed.weight"] = torch.zeros_like(P["sg_obj_embed.weight"])
+    G["sg_obj_embed.weight"] = new_grad("sg_obj_embed.weight")
     ops.scatter_add_rows(dx_of(d_x0, "obj_emb_proj.weight"), S["cls"], G["sg_obj_embed.weight"])
+    if reducer is not None:
+        reducer.bucket_done(2, G)
+        reducer.finish(G)
     return G

@@ -69,3 +69,59 @@ def test_shard_batch_partitions_the_loader_tensors():
         sizes = [p["att_feats"].shape[0] for p in parts]
         assert sum(sizes) == 5 and max(sizes) - min(sizes) <= 1
         assert all(p["labels"].shape[0] == 5 * p["att_feats"].shape[0] for p in parts)
+
+
+def _reducer_worker(rank, world, port, ret):
+    """Two ranks run the hand-written backward (torch emulation of the CUDA blocks) on their shard with a GradReducer; twice, so that the
+    second pass uses the frozen flat-bucket layout."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from emu_ops import EmuOps
+    from helpers import load_golden, rebuild_train_case
+    from subgc import train
+    from subgc.model import LanguageModelCriterion
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        d, sd, data = rebuild_train_case(load_golden("small_train"))
+        shard = parallel.shard_batch(data, rank, world)
+        red = parallel.GradReducer(world)
+        ops = EmuOps()
+        for _ in range(2):
+            with torch.no_grad():
+                outputs, gpn_loss, score, S = train.forward(ops, sd, sd, d, shard, drop=None)
+            leaf = outputs.clone().requires_grad_(True)
+            LanguageModelCriterion()(leaf, shard["labels"][:, 1:], shard["masks"][:, 1:]).backward()
+            with torch.no_grad():
+                G = train.backward(ops, sd, d, S, leaf.grad, 1.0, reducer=red)
+        ret[rank] = {k: v.clone() for k, v in G.items()}
+    finally:
+        dist.destroy_process_group()
+
+
+def test_overlapped_bucket_allreduce_equals_mean_of_shard_gradients():
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from emu_ops import EmuOps
+    from helpers import load_golden, rebuild_train_case
+    from subgc import train
+    from subgc.model import LanguageModelCriterion
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_reducer_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    d, sd, data = rebuild_train_case(load_golden("small_train"))
+    ops, per = EmuOps(), []
+    for r in range(world):
+        shard = parallel.shard_batch(data, r, world)
+        with torch.no_grad():
+            outputs, gpn_loss, score, S = train.forward(ops, sd, sd, d, shard, drop=None)
+        leaf = outputs.clone().requires_grad_(True)
+        LanguageModelCriterion()(leaf, shard["labels"][:, 1:], shard["masks"][:, 1:]).backward()
+        with torch.no_grad():
+            per.append(train.backward(ops, sd, d, S, leaf.grad, 1.0))
+    assert set(ret[0]) == set(per[0]) == set(ret[1])
+    assert {parallel.bucket_of(n) for n in per[0]} == {0, 1, 2}
+    for n in per[0]:
+        mean = 0.5 * (per[0][n] + per[1][n])
+        for r in range(world):
+            assert torch.allclose(ret[r][n], mean, rtol=1e-5, atol=1e-7), n
