@@ -140,7 +140,7 @@ typedef struct subgc_subgraph_layout {
 
 const char* subgc_last_error(void);
 int subgc_version(void);
-/* kernels launched so far by the calling thread through this library (instrumentation for bench.py's gpu_launches) */
+/* kernels launched so far by this process through this library, all threads (instrumentation for bench.py's gpu_launches) */
 unsigned long long subgc_launch_count(void);
 /* debugging aid (env SUBGC_ATT_TRACE=1, synchronises): per-block stage time stamps [n_blocks][8] of the last fused att-phase launch */
 int subgc_debug_att_trace(unsigned long long* host_out, int n_blocks);
@@ -342,6 +342,10 @@ int subgc_ew(int op, size_t n, const float* a, const float* b /*nullable*/, floa
 int subgc_dropout_mask(size_t n, float p, uint64_t seed, uint64_t offset, float* mask, subgc_stream_t stream);
 int subgc_gather_rows(int n_rows, int cols, const float* src, int ld_src, const int64_t* idx, float* out, int relu,
                       subgc_stream_t stream);
+/* Scheduled sampling (models/AttModel.py:158-167): it[r] = labels[r * ld_lab] or, with probability ss_prob per row, a token drawn from
+ * exp(prev_logp[r, :]) (the previous step's log-probs, leading dim ld) by inverse CDF; Philox4x32-10 keyed by (seed; row, offset). */
+int subgc_ss_sample(int rows, int V1, const float* prev_logp, size_t ld, const int64_t* labels, int ld_lab, float ss_prob,
+                    uint64_t seed, uint64_t offset, int64_t* it, subgc_stream_t stream);
 /* op 0: relu, 1: sigmoid */
 int subgc_unary(int op, size_t n, const float* a, float* out, subgc_stream_t stream);
 int subgc_scatter_add_rows(int n_rows, int cols, const float* src, int ld_src, const int64_t* idx, float* dst, int ld_dst,

@@ -12,8 +12,9 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
-static thread_local unsigned long long g_launches = 0;
-void count_launch() { ++g_launches; }
+// process-wide: the backward pass of a training step runs on autograd's worker thread
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 bool pdl_enabled() {
     static int on = -1;
     if (on < 0) { const char* e = getenv("SUBGC_NO_PDL"); on = (e && e[0] == '1') ? 0 : 1; }
@@ -39,7 +40,7 @@ TraceSlot next_trace_slot(int kernel_id) {
 
 extern "C" const char* subgc_last_error(void) { return subgc::g_err; }
 extern "C" int subgc_version(void) { return SUBGC_ABI_VERSION; }
-extern "C" unsigned long long subgc_launch_count(void) { return subgc::g_launches; }
+extern "C" unsigned long long subgc_launch_count(void) { return subgc::g_launches.load(std::memory_order_relaxed); }
 
 /* debugging aid (SUBGC_TRACE=1): op 0 = restart slot numbering (call before the launch sequence to be traced / captured),
  * op 1 = reset the time stamps (before a replay), op 2 = copy out [n][8] stamps and the kernel ids; returns slots in use */

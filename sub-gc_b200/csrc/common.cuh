@@ -15,7 +15,7 @@
 namespace subgc {
 
 void set_error(const char* fmt, ...);
-void count_launch();  // per-thread tally of kernels launched through this library (subgc_launch_count)
+void count_launch();  // process-wide tally of kernels launched through this library (subgc_launch_count)
 
 #define SUBGC_CHECK_ARG(cond, ...)                 \
     do {                                           \

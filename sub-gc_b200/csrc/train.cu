@@ -79,6 +79,53 @@ __global__ void __launch_bounds__(256) dropout_mask_kernel(size_t n, float p, un
     }
 }
 
+// Scheduled sampling (reference models/AttModel.py:158-167): with probability ss_prob the token fed to step i is drawn from
+// exp(outputs[:, i-1]) instead of the ground truth.  One block per row: u1 decides, u2 is mapped through the inverse CDF of the row's
+// probabilities (torch.multinomial draws from the same distribution; the RNG streams differ).  Philox4x32-10 keyed by (seed; row, offset).
+__global__ void __launch_bounds__(256) ss_sample_kernel(const float* __restrict__ prev_logp, size_t ld, int V1, const long long* __restrict__ labels,
+                                                        int ld_lab, float ss_prob, unsigned long long seed, unsigned long long offset,
+                                                        long long* __restrict__ it) {
+    __shared__ float s_part[256];
+    __shared__ float s_u[2];
+    const int r = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) {
+        unsigned c[4] = {(unsigned)r, 0x5353u, (unsigned)offset, (unsigned)(offset >> 32)};
+        unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+        for (int i = 0; i < 10; ++i) { philox_round(c, k0, k1); k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+        s_u[0] = (float)(c[0] >> 8) * (1.0f / 16777216.0f);
+        s_u[1] = (float)(c[1] >> 8) * (1.0f / 16777216.0f);
+    }
+    __syncthreads();
+    const long long truth = labels[(size_t)r * ld_lab];
+    if (!(s_u[0] < ss_prob)) {   // uniform decision per row, so the whole block takes the same branch
+        if (tid == 0) it[r] = truth;
+        return;
+    }
+    const float* lp = prev_logp + (size_t)r * ld;
+    const int per = (V1 + 255) / 256, lo = tid * per, hi = min(V1, lo + per);   // contiguous slice per thread: the CDF runs in index order
+    float s = 0.f;
+    for (int j = lo; j < hi; ++j) s += expf(lp[j]);
+    s_part[tid] = s;
+    __syncthreads();
+    if (tid == 0) {
+        float tot = 0.f;
+        for (int i = 0; i < 256; ++i) tot += s_part[i];
+        const float target = s_u[1] * tot;
+        float run = 0.f;
+        int blk = 255;
+        for (int i = 0; i < 256; ++i) {
+            if (run + s_part[i] > target) { blk = i; break; }
+            run += s_part[i];
+        }
+        int tok = min(V1, (blk + 1) * per) - 1;
+        for (int j = blk * per; j < min(V1, (blk + 1) * per); ++j) {
+            run += expf(lp[j]);
+            if (run > target) { tok = j; break; }
+        }
+        it[r] = tok;
+    }
+}
+
 // dst[idx[r], :] += src[r, :]   (embedding / node-feature gradient; atomics: order-independent up to fp32 rounding)
 __global__ void __launch_bounds__(256) scatter_add_rows_kernel(const float* __restrict__ src, const long long* __restrict__ idx, int n_rows,
                                                                int cols, int ld_src, float* __restrict__ dst, int ld_dst) {
@@ -426,6 +473,15 @@ extern "C" int subgc_dropout_mask(size_t n, float p, uint64_t seed, uint64_t off
     SUBGC_CHECK_ARG(mask && p >= 0.f && p < 1.f, "subgc_dropout_mask: bad arguments");
     if (n == 0) return SUBGC_OK;
     dropout_mask_kernel<<<ew_blocks((n + 3) / 4), 256, 0, ST>>>(n, p, seed, offset, mask);
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}
+
+extern "C" int subgc_ss_sample(int rows, int V1, const float* prev_logp, size_t ld, const int64_t* labels, int ld_lab, float ss_prob,
+                               uint64_t seed, uint64_t offset, int64_t* it, subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(rows > 0 && V1 > 0 && prev_logp && labels && it && ld >= (size_t)V1 && ss_prob >= 0.f && ss_prob <= 1.f, "subgc_ss_sample: bad arguments");
+    ss_sample_kernel<<<rows, 256, 0, ST>>>(prev_logp, ld, V1, reinterpret_cast<const long long*>(labels), ld_lab, ss_prob, seed, offset,
+                                           reinterpret_cast<long long*>(it));
     SUBGC_LAUNCH_CHECK();
     return SUBGC_OK;
 }

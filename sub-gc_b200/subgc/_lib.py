@@ -107,6 +107,7 @@ SIGNATURES = {
     "subgc_ew": (_i, [_i, _sz, c_fp, c_fp, c_fp, _f, c_fp]),
     "subgc_dropout_mask": (_i, [_sz, _f, _u64, _u64, c_fp, c_fp]),
     "subgc_gather_rows": (_i, [_i, _i, c_fp, _i, c_fp, c_fp, _i, c_fp]),
+    "subgc_ss_sample": (_i, [_i, _i, c_fp, _sz, c_fp, _i, _f, _u64, _u64, c_fp, c_fp]),
     "subgc_unary": (_i, [_i, _sz, c_fp, c_fp, c_fp]),
     "subgc_scatter_add_rows": (_i, [_i, _i, c_fp, _i, c_fp, c_fp, _i, c_fp]),
     "subgc_lstm_cell_train_fwd": (_i, [_i, _i, c_fp, c_fp, c_fp, c_fp, c_fp]),

@@ -124,7 +124,7 @@ class _TrainStep(torch.autograd.Function):
         from . import train
         P = dict(zip(names, (p.detach() for p in params)))
         ops = model._train_ops()
-        outputs, gpn_loss, score, saved = train.forward(ops, P, model._weights(), model.dims, data, drop, model.seq_per_img)
+        outputs, gpn_loss, score, saved = train.forward(ops, P, model._weights(), model.dims, data, drop, model.seq_per_img, ss=data.get("ss"))
         ctx.pack = (model, ops, P, saved, names)
         ctx.mark_non_differentiable(score)
         return outputs, gpn_loss[0], score
@@ -942,8 +942,6 @@ class TopDownModel(nn.Module):
 
 def _forward_train(self, att_feats, seq, att_masks, obj_dist, rel_ind, gpn_obj_ind):
     """Training-mode AttModel._forward: CUDA forward with dropout + saved activations, gradients through _TrainStep."""
-    if self.ss_prob > 0:
-        raise NotImplementedError("scheduled sampling (ss_prob > 0) is not implemented by the CUDA training path (SURVEY §8f n4)")
     data = dict(att_feats=self._f32(att_feats), obj_dist=self._f32(obj_dist), rel_ind=self._i64(rel_ind), labels=self._i64(seq),
                 att_masks=self._f32(att_masks), gpn_obj_ind=self._i64(gpn_obj_ind))
     drop = None
@@ -956,6 +954,8 @@ def _forward_train(self, att_feats, seq, att_masks, obj_dist, rel_ind, gpn_obj_i
         seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
         seed = (seed * 1000003 + rank * 8191 + (att_feats.device.index or 0) * 131) % (2 ** 31 - 1)
         drop = dict(p=float(self.drop_prob_lm), seed=seed)
+    if self.training and self.ss_prob > 0:   # scheduled sampling (train.py:131: model.ss_prob is raised during training)
+        data["ss"] = dict(prob=float(self.ss_prob), seed=int(torch.randint(0, 2 ** 31 - 1, (1,)).item()))
     names, params = zip(*self._named_params().items())
     outputs, gpn_loss, score = _TrainStep.apply(self, data, drop, names, *params)
     return outputs, gpn_loss, score

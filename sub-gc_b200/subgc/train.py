@@ -103,6 +103,14 @@ class CudaOps:
         check(lib().subgc_dropout_mask(m.numel(), float(p), int(seed), int(offset), ptr(m), self._st()), "subgc_dropout_mask")
         return m
 
+    def ss_sample(self, prev_logp, labels_col, ss_prob, seed, offset):
+        """models/AttModel.py:158-167: ground-truth token or, with probability ss_prob per row, a draw from exp(prev_logp)."""
+        rows, V1 = prev_logp.shape
+        it = torch.empty(rows, dtype=torch.int64, device=prev_logp.device)
+        check(lib().subgc_ss_sample(rows, V1, ptr(prev_logp), prev_logp.stride(0), ptr(labels_col), labels_col.stride(0), float(ss_prob), int(seed),
+                                    int(offset), ptr(it), self._st()), "subgc_ss_sample")
+        return it
+
     def gather_rows(self, src, idx, relu=False):
         out = torch.empty(idx.shape[0], src.shape[1], device=src.device)
         check(lib().subgc_gather_rows(idx.shape[0], src.shape[1], ptr(src), src.stride(0), ptr(idx), ptr(out), int(relu), self._st()),
@@ -266,7 +274,7 @@ def _unit(l, u):
 # ------------------------------------------------------------------------------------------------------------------
 # forward
 # ------------------------------------------------------------------------------------------------------------------
-def forward(ops, P, weights, d, data, drop=None, seq_per_img=5):
+def forward(ops, P, weights, d, data, drop=None, seq_per_img=5, ss=None):
     """Train-mode AttModel._forward.  P: name -> parameter tensor; weights: subgc_weights struct (for subgc_fuse_nodes);
     drop: None (dropout off) or dict(p=drop_prob_lm, seed=int).  Returns (outputs, gpn_loss, score, saved)."""
     S = {}
@@ -372,7 +380,10 @@ def forward(ops, P, weights, d, data, drop=None, seq_per_img=5):
     E = P["embed.0.weight"]
     steps = []
     for t in range(n_exec):
-        it = labels[:, t].contiguous()
+        if ss is not None and t >= 1 and ss["prob"] > 0.0:   # scheduled sampling (AttModel.py:158-167); the sampled token is a constant
+            it = ops.ss_sample(outputs[:, t - 1], labels[:, t], ss["prob"], ss["seed"], t)
+        else:
+            it = labels[:, t].contiguous()
         x_relu = ops.gather_rows(E, it, relu=True)
         m_x = dmask(x_relu.shape, p_lm)
         xt = x_relu if m_x is None else ops.mul(x_relu, m_x)

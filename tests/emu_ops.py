@@ -56,6 +56,12 @@ class EmuOps:
         g = torch.Generator().manual_seed(seed * 1000 + offset)
         return (torch.rand(shape, generator=g) >= p).float() / (1 - p)
 
+    def ss_sample(self, prev_logp, labels_col, ss_prob, seed, offset):
+        g = torch.Generator().manual_seed(seed * 1000 + offset)
+        take = torch.rand(prev_logp.shape[0], generator=g) < ss_prob
+        drawn = torch.multinomial(torch.exp(prev_logp), 1, generator=g).view(-1)
+        return torch.where(take, drawn, labels_col)
+
     def gather_rows(self, src, idx, relu=False):
         y = src[idx]
         return torch.relu(y) if relu else y.clone()

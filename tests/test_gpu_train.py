@@ -207,3 +207,56 @@ def test_train_mode_with_dropout_runs_and_is_stochastic():
     with torch.no_grad():
         e1 = lw(*args); e2 = lw(*args)
     assert float(e1["lang_loss"]) == float(e2["lang_loss"])
+
+
+def test_scheduled_sampling_kernel_distribution_and_rate(ops):
+    """models/AttModel.py:158-167: per row, with probability ss_prob the fed token is drawn from exp(previous log-probs).  RNG streams cannot
+    match torch.multinomial's, so the kernel is checked statistically: the rate of replaced rows and a chi-square of the drawn tokens."""
+    c, _, _ = ops
+    V1, rows = 50, 4096
+    g = torch.Generator().manual_seed(3)
+    logits = torch.randn(V1, generator=g) * 1.5
+    logp = torch.log_softmax(logits, 0)
+    prev = logp.unsqueeze(0).expand(rows, V1).contiguous().cuda()
+    labels = torch.full((rows, 3), V1 + 7, dtype=torch.int64).cuda()          # a token id that cannot be drawn marks "ground truth kept"
+    counts = torch.zeros(V1, dtype=torch.float64)
+    replaced = total = 0
+    for rep in range(6):
+        it = c.ss_sample(prev, labels[:, 1], 0.25, 99, rep).cpu()
+        drawn = it[it != V1 + 7]
+        replaced += drawn.numel(); total += rows
+        counts += torch.bincount(drawn, minlength=V1).double()
+    rate = replaced / total
+    assert abs(rate - 0.25) < 4 * (0.25 * 0.75 / total) ** 0.5, rate
+    expect = torch.exp(logp).double() * replaced
+    keep = expect > 5
+    chi2 = float((((counts - expect) ** 2) / expect)[keep].sum())
+    assert chi2 < 2.2 * int(keep.sum()), (chi2, int(keep.sum()))            # ~ p = 1e-5 for 30-50 degrees of freedom
+    assert torch.equal(c.ss_sample(prev, labels[:, 1], 0.25, 99, 1), c.ss_sample(prev, labels[:, 1], 0.25, 99, 1))   # reproducible
+    assert int((c.ss_sample(prev, labels[:, 1], 0.0, 99, 1) != V1 + 7).sum()) == 0
+    assert int((c.ss_sample(prev, labels[:, 1], 1.0, 99, 1) == V1 + 7).sum()) == 0
+
+
+def test_training_with_scheduled_sampling_runs():
+    d = SMALL
+    sd = synth.make_state_dict(d, 9, logit_gain=4.0)
+    data = {k: cu(v) for k, v in synth.make_train_inputs(d, 9, n_images=2, gpn_batch=2).items()}
+    model = setup(make_opt(d))
+    model.load_state_dict(sd)
+    model.cuda().train()
+    model.dropout_enabled = False
+    lw = LossWrapper(model, None)
+    args = (data["fc_feats"], data["att_feats"], data["labels"], data["masks"], data["att_masks"], None, None, None, data["obj_dist"], None,
+            data["rel_ind"], None, data["pred_dist"], data["gpn_obj_ind"], data["gpn_pred_ind"], data["gpn_nrel_ind"], data["gpn_pool_mtx"])
+    base = float(lw(*args)["lang_loss"])
+    model.ss_prob = 0.75                                    # train.py:131 raises it epoch by epoch
+    torch.manual_seed(1)
+    a = lw(*args)
+    (a["lang_loss"] + a["gpn_loss"]).backward()
+    assert torch.isfinite(model.logit.weight.grad).all() and float(model.logit.weight.grad.abs().sum()) > 0
+    assert float(a["lang_loss"]) != base                   # sampled tokens were fed
+    torch.manual_seed(1)
+    assert float(lw(*args)["lang_loss"]) == float(a["lang_loss"])
+    model.eval()                                            # evaluation never samples (AttModel.py:158: `self.training and ...`)
+    with torch.no_grad():
+        assert abs(float(lw(*args)["lang_loss"]) - base) <= 1e-5 * max(1.0, abs(base))
