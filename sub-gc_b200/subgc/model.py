@@ -157,6 +157,7 @@ class _DeviceState:
         self.tops = None
         self.cur_plan = None
         self.params = None
+        self.wfast = None
 
 
 def _state_property(name):
@@ -290,10 +291,16 @@ class TopDownModel(nn.Module):
     def _weights(self):
         """subgc_weights over the live parameter storage (rebuilt when a tensor moved, e.g. after .cuda() / load)."""
         params = self._named_params()
-        key = tuple(p.data_ptr() for p in params.values())
+        st = self._state()
+        # fast path of every call: nothing moved, nothing was updated in place, no switch was flipped since the last validation
+        fast = (tuple([(p.data_ptr(), p._version) for p in params.values()]), self.training, self.use_packed, self.use_mega)
+        if st.wfast == fast and st.wcache is not None:
+            return st.wcache[1]
+        key = tuple(k[0] for k in fast[0])
         if self._wcache is not None and self._wcache[0] == key:
             w = self._wcache[1]
             self._attach_packs(w, params)
+            st.wfast = fast
             return w
         for n, p in params.items():
             if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
@@ -322,6 +329,7 @@ class TopDownModel(nn.Module):
         self._plans.clear()  # captured graphs hold the old parameter addresses
         self._pack_key = None
         self._attach_packs(w, params)
+        st.wfast = fast
         return w
 
     # weight matrices that are the W operand of a contraction on the inference path (embedding tables are A operands)
@@ -630,7 +638,8 @@ class TopDownModel(nn.Module):
         if (opt.get("beam_size", 1) != 1 or opt.get("return_att", 0) == 1 or opt.get("topk_uniforms", None) is not None
                 or not self.use_graphs or not self.use_mega or not self.use_step_graph or self.stage_events is not None):
             return None
-        if not self._weights().mega:
+        w = self._weights()
+        if not w.mega:
             return None
         if "compact" in front:
             rows, _, per_half, _ = front["compact"].sub_nodes.shape
@@ -641,7 +650,7 @@ class TopDownModel(nn.Module):
         g = self.gpn_layer
         per_image = min(int(g.max_subgraphs), 2 * per_half) if g.use_nms else 2 * per_half
         rows_cap = n_images * per_image
-        if rows_cap < 1 or rows_cap > 128 or rows_cap > self._weights().mega_ctas:
+        if rows_cap < 1 or rows_cap > 128 or rows_cap > w.mega_ctas:
             return None
         return rows_cap, n_images
 
@@ -693,8 +702,7 @@ class TopDownModel(nn.Module):
             front["pred_dist"] = None if front.get("pred_dist") is None else self._f32(front["pred_dist"])
             names = [k for k in self._STEP_INPUTS if front.get(k) is not None]
             tensors = [front[k] for k in names]
-        w = self._weights()   # (re)packs and drops stale plans before the lookup
-        g = self.gpn_layer
+        g = self.gpn_layer   # (_dyn_eligible validated the weight tables and dropped stale plans a moment ago)
         skey = ("step", dev.index, batch is not None, tuple(names), tuple(tuple(t.shape) for t in tensors), front.get("seq_per_img"), bool(self.topk_sampling),
                 float(self.topk_temp), int(self.the_k), bool(g.use_nms), float(g.iou_thres), int(g.max_subgraphs))
         group = self._plans.get(skey)
