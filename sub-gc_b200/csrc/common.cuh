@@ -141,6 +141,12 @@ struct GemmEpilogue {
     const int* group_len = nullptr;
     const int* group_sel = nullptr;
     int group = 0;
+    // optional split-fp16 copy of the result (v = hi + lo * 2^-11), [M, ld16], for a consumer contraction that reads it as its
+    // activation operand (GemmSeg::A16_*): written by the h3 contraction's own epilogue when it finishes the tile itself, otherwise
+    // by one split pass over C after the contraction (launch_gemm guarantees it is there either way)
+    unsigned short* c16_hi = nullptr;
+    unsigned short* c16_lo = nullptr;
+    int ld16 = 0;
 };
 
 struct GemmProblem {
@@ -188,7 +194,9 @@ struct CellEpilogue {
 int launch_gemm_cell(const GemmProblem& p, const CellEpilogue& cell, void* ws, size_t ws_bytes, cudaStream_t stream, bool* fused);
 // tensor-core (tcgen05, split-fp16 "h3") variant for weights that have a packed copy, h3_gemm.cu
 bool h3_eligible(const GemmProblem& p);
-int launch_gemm_h3(const GemmProblem& p, void* ws, size_t ws_bytes, cudaStream_t stream, RawPartials* raw = nullptr);
+int launch_gemm_h3(const GemmProblem& p, void* ws, size_t ws_bytes, cudaStream_t stream, RawPartials* raw = nullptr, bool* wrote_c16 = nullptr);
+// fp32 rows [M, K] (leading dim lda) -> split-fp16 hi / lo [M, ld16] (ld16 % 8 == 0, >= K)
+int launch_split_rows(const float* A, int M, int K, int lda, unsigned short* hi, unsigned short* lo, int ld16, int* overflow, cudaStream_t stream);
 // fills W16_hi / W16_lo of every segment whose weight pointer lies inside a packed tensor of `w` (no-op without packs)
 void resolve_packs(GemmProblem& p, const subgc_weights* w);
 // Splits plain activation rows A [M, K] once into hi / lo [M, K rounded up to 8] (taken from `ws`) so that several contractions can

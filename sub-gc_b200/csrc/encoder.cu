@@ -35,7 +35,10 @@ __global__ void __launch_bounds__(256) class_argmax_kernel(const float* __restri
 // p_new[b,k,:] = 0.5 * ( relu(M2[b, s_k, :] / (1+1e-7)) + relu(M3[b, o_k, :] / (1+1e-7)) ) (+ residual)
 __global__ void __launch_bounds__(256) gcn_edge_update_kernel(const float* __restrict__ m_subj, const float* __restrict__ m_obj,
                                                               const long long* __restrict__ rel_ind, const float* __restrict__ res,
-                                                              float* __restrict__ out, int B, int N, int K, int L) {
+                                                              float* __restrict__ out, int B, int N, int K, int L,
+                                                              unsigned short* __restrict__ o16_hi = nullptr, unsigned short* __restrict__ o16_lo = nullptr,
+                                                              int ld16 = 0, int* __restrict__ overflow = nullptr) {
+    // o16_hi / o16_lo (nullable, [B*K, ld16]): split-fp16 copy of the new edge features for the contractions of the next layer
     const int bk = blockIdx.x;  // b*K + k
     const int b = bk / K;
     const long long s = rel_ind[(size_t)bk * 2], o = rel_ind[(size_t)bk * 2 + 1];
@@ -56,6 +59,15 @@ __global__ void __launch_bounds__(256) gcn_edge_update_kernel(const float* __res
                 v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
             }
             reinterpret_cast<float4*>(out + (size_t)bk * L)[c4] = v;
+            if (o16_hi) {
+                unsigned short hh[4], hl[4];
+                int ovf = 0;
+                split_f16(v.x, hh[0], hl[0], ovf); split_f16(v.y, hh[1], hl[1], ovf); split_f16(v.z, hh[2], hl[2], ovf); split_f16(v.w, hh[3], hl[3], ovf);
+                const size_t o = (size_t)bk * ld16 + 4 * c4;
+                *reinterpret_cast<uint2*>(o16_hi + o) = make_uint2((uint32_t)hh[0] | ((uint32_t)hh[1] << 16), (uint32_t)hh[2] | ((uint32_t)hh[3] << 16));
+                *reinterpret_cast<uint2*>(o16_lo + o) = make_uint2((uint32_t)hl[0] | ((uint32_t)hl[1] << 16), (uint32_t)hl[2] | ((uint32_t)hl[3] << 16));
+                if (ovf && overflow) atomicOr(overflow, 1);
+            }
         }
         return;
     }
@@ -63,6 +75,7 @@ __global__ void __launch_bounds__(256) gcn_edge_update_kernel(const float* __res
         float v = 0.5f * (fmaxf(__ldg(ms + c) / d, 0.f) + fmaxf(__ldg(mo + c) / d, 0.f));
         if (res) v += __ldg(res + (size_t)bk * L + c);
         out[(size_t)bk * L + c] = v;
+        if (o16_hi) split_f16_store(v, o16_hi, o16_lo, (size_t)bk * ld16 + c, overflow);
     }
 }
 
@@ -173,6 +186,8 @@ static size_t gcn_ws_bytes(const subgc_dims* d, int B) {
     size_t g1 = gemm_workspace_bytes((int)rows, d->low_rank, d->gcn), g2 = gemm_workspace_bytes((int)rows, d->gcn, d->low_rank);
     b += align_up(g1 > g2 ? g1 : g2, 256) + 1024;
     b += 2 * align_up(rows * (size_t)((d->gcn + 7) & ~7) * 2, 256) + 1024;   // split-fp16 copy of a layer input shared by two units
+    b += 2 * align_up(rows * (size_t)((d->low_rank + 7) & ~7) * 2, 256) + 1024;   // split-fp16 copy of T written by the fc_lft contraction
+    b += 4 * align_up((size_t)B * d->rel_num * (size_t)((d->gcn + 7) & ~7) * 2, 256) + 1024;   // split-fp16 copies (two sets) of the edge stream written by the edge update kernel
     return b;
 }
 
@@ -185,13 +200,15 @@ static size_t fuse_ws_bytes(const subgc_dims* d, int B) {
 }
 
 static int linear(const subgc_weights* w, const float* A, int M, int K, const subgc_linear& lin, int N, float* C, Workspace& ws, cudaStream_t st,
-                  const unsigned short* a16_hi = nullptr, const unsigned short* a16_lo = nullptr, int lda16 = 0) {
+                  const unsigned short* a16_hi = nullptr, const unsigned short* a16_lo = nullptr, int lda16 = 0, unsigned short* c16_hi = nullptr,
+                  unsigned short* c16_lo = nullptr, int ld16 = 0) {
     GemmProblem p;
     p.wts = w;
     p.M = M; p.N = N; p.nseg = 1;
     p.seg[0] = make_seg(A, K, lin.w, K, K);
     if (a16_hi) { p.seg[0].A16_hi = a16_hi; p.seg[0].A16_lo = a16_lo; p.seg[0].lda16 = lda16; }   // shared split copy of A
     p.epi.bias = lin.b;
+    p.epi.c16_hi = c16_hi; p.epi.c16_lo = c16_lo; p.epi.ld16 = ld16;                               // split copy of the result for the next contraction
     p.C = C; p.ldc = N;
     return launch_gemm(p, ws.cursor(), ws.remaining(), st);
 }
@@ -300,6 +317,15 @@ extern "C" int subgc_gcn_forward(const subgc_dims* d, const subgc_weights* w, in
     // both units of a direction contract the same layer input: split it once (split-fp16 path), in a region reserved up front
     const size_t split_bytes = 2 * align_up(rows_max * (size_t)((L + 7) & ~7) * 2, 256) + 1024;
     char* split_region = ws.take<char>(split_bytes);
+    // split-fp16 copies that their producers write themselves (only when the packed path is in use): T by the fc_lft contraction's
+    // epilogue, the edge stream of the next layer by the edge update kernel
+    const bool fuse16 = w->packs != nullptr && w->n_packs > 0 && (R & 7) == 0 && (L & 7) == 0;
+    unsigned short* t16_hi = fuse16 ? ws.take<unsigned short>(rows_max * R) : nullptr;
+    unsigned short* t16_lo = fuse16 ? ws.take<unsigned short>(rows_max * R) : nullptr;
+    // two sets: a layer's edge update writes the NEXT layer's copy while its node update still reads the current one
+    unsigned short* n16_hi[2] = {fuse16 ? ws.take<unsigned short>((size_t)B * K * L) : nullptr, fuse16 ? ws.take<unsigned short>((size_t)B * K * L) : nullptr};
+    unsigned short* n16_lo[2] = {fuse16 ? ws.take<unsigned short>((size_t)B * K * L) : nullptr, fuse16 ? ws.take<unsigned short>((size_t)B * K * L) : nullptr};
+    const unsigned short *cur16_hi = nullptr, *cur16_lo = nullptr;   // split copy of the current edge stream p, if its producer wrote one
     const float* x = x0;
     const float* p = p0;
     const float* x_res = x0;
@@ -307,6 +333,7 @@ extern "C" int subgc_gcn_forward(const subgc_dims* d, const subgc_weights* w, in
     const long long* rel = reinterpret_cast<const long long*>(rel_ind);
     for (int l = 0; l < Ln; ++l) {
         const bool last = (l == Ln - 1), boundary = ((l + 1) % d->gcn_residual == 0);
+        bool next16 = false;
         float* x_next = nullptr;
         float* p_next = nullptr;
         if (need_x[l + 1]) x_next = last ? x_obj : ws.take<float>(xn);
@@ -316,24 +343,32 @@ extern "C" int subgc_gcn_forward(const subgc_dims* d, const subgc_weights* w, in
             const unsigned short *xh = nullptr, *xl = nullptr;
             int xld = 0;
             if (split_region) { Workspace sw(split_region, split_bytes); if (!h3_presplit(x, B * N, L, L, w, sw, st, &xh, &xl, &xld)) xh = xl = nullptr; }
-            SUBGC_TRY(linear(w, x, B * N, L, w->gcn_lft[l][2], R, T, ws, st, xh, xl, xld));
-            SUBGC_TRY(linear(w, T, B * N, R, w->gcn_rgt[l][2], L, Ma, ws, st));
-            SUBGC_TRY(linear(w, x, B * N, L, w->gcn_lft[l][3], R, T, ws, st, xh, xl, xld));
-            SUBGC_TRY(linear(w, T, B * N, R, w->gcn_rgt[l][3], L, Mb, ws, st));
-            gcn_edge_update_kernel<<<B * K, 256, 0, st>>>(Ma, Mb, rel, boundary ? p_res : nullptr, p_next, B, N, K, L);
+            SUBGC_TRY(linear(w, x, B * N, L, w->gcn_lft[l][2], R, T, ws, st, xh, xl, xld, t16_hi, t16_lo, R));
+            SUBGC_TRY(linear(w, T, B * N, R, w->gcn_rgt[l][2], L, Ma, ws, st, t16_hi, t16_lo, R));
+            SUBGC_TRY(linear(w, x, B * N, L, w->gcn_lft[l][3], R, T, ws, st, xh, xl, xld, t16_hi, t16_lo, R));
+            SUBGC_TRY(linear(w, T, B * N, R, w->gcn_rgt[l][3], L, Mb, ws, st, t16_hi, t16_lo, R));
+            next16 = fuse16 && !last && need_x[l + 2];   // layer l+1 contracts this edge stream (its units 0, 1 produce x of layer l+2)
+            gcn_edge_update_kernel<<<B * K, 256, 0, st>>>(Ma, Mb, rel, boundary ? p_res : nullptr, p_next, B, N, K, L, next16 ? n16_hi[l & 1] : nullptr,
+                                                          next16 ? n16_lo[l & 1] : nullptr, L, w->h3_overflow);
             SUBGC_LAUNCH_CHECK();
         }
         if (x_next) {  // units 0,1: node <- edges (graph_conv.py:22-26)
             const unsigned short *ph = nullptr, *pl = nullptr;
             int pld = 0;
-            if (split_region) { Workspace sw(split_region, split_bytes); if (!h3_presplit(p, B * K, L, L, w, sw, st, &ph, &pl, &pld)) ph = pl = nullptr; }
-            SUBGC_TRY(linear(w, p, B * K, L, w->gcn_lft[l][0], R, T, ws, st, ph, pl, pld));
-            SUBGC_TRY(linear(w, T, B * K, R, w->gcn_rgt[l][0], L, Ma, ws, st));
-            SUBGC_TRY(linear(w, p, B * K, L, w->gcn_lft[l][1], R, T, ws, st, ph, pl, pld));
-            SUBGC_TRY(linear(w, T, B * K, R, w->gcn_rgt[l][1], L, Mb, ws, st));
+            if (cur16_hi) {   // the edge update of the previous layer already wrote the split copy of this input
+                ph = cur16_hi; pl = cur16_lo; pld = L;
+            } else if (split_region) {
+                Workspace sw(split_region, split_bytes);
+                if (!h3_presplit(p, B * K, L, L, w, sw, st, &ph, &pl, &pld)) ph = pl = nullptr;
+            }
+            SUBGC_TRY(linear(w, p, B * K, L, w->gcn_lft[l][0], R, T, ws, st, ph, pl, pld, t16_hi, t16_lo, R));
+            SUBGC_TRY(linear(w, T, B * K, R, w->gcn_rgt[l][0], L, Ma, ws, st, t16_hi, t16_lo, R));
+            SUBGC_TRY(linear(w, p, B * K, L, w->gcn_lft[l][1], R, T, ws, st, ph, pl, pld, t16_hi, t16_lo, R));
+            SUBGC_TRY(linear(w, T, B * K, R, w->gcn_rgt[l][1], L, Mb, ws, st, t16_hi, t16_lo, R));
             gcn_node_update_kernel<<<B * N, 256, 4 * K * sizeof(int), st>>>(Ma, Mb, rel, boundary ? x_res : nullptr, x_next, B, N, K, L);
             SUBGC_LAUNCH_CHECK();
         }
+        cur16_hi = next16 ? n16_hi[l & 1] : nullptr; cur16_lo = next16 ? n16_lo[l & 1] : nullptr;
         x = x_next; p = p_next;
         if (boundary) { x_res = x; p_res = p; }
     }

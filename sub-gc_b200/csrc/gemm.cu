@@ -366,15 +366,20 @@ int launch_gemm(const GemmProblem& p, void* ws, size_t ws_bytes, cudaStream_t st
         resolve_packs(q, p.wts);
         return launch_gemm(q, ws, ws_bytes, stream);
     }
+    bool wrote16 = false;
+    int rc;
     if (p.M > 0 && h3_eligible(p)) {
         SUBGC_CHECK_ARG(p.N > 0 && p.C != nullptr && p.ldc >= p.N, "gemm: bad output");
-        return launch_gemm_h3(p, ws, ws_bytes, stream);
-    }
-    if (p.M > 0 && tc_eligible(p)) {
+        rc = launch_gemm_h3(p, ws, ws_bytes, stream, nullptr, &wrote16);
+    } else if (p.M > 0 && tc_eligible(p)) {
         SUBGC_CHECK_ARG(p.N > 0 && p.C != nullptr && p.ldc >= p.N, "gemm: bad output");
-        return launch_gemm_tc(p, ws, ws_bytes, stream);
+        rc = launch_gemm_tc(p, ws, ws_bytes, stream);
+    } else {
+        rc = launch_gemm_ex(p, nullptr, 0, nullptr, ws, ws_bytes, stream);
     }
-    return launch_gemm_ex(p, nullptr, 0, nullptr, ws, ws_bytes, stream);
+    if (rc == SUBGC_OK && p.M > 0 && p.epi.c16_hi && p.epi.c16_lo && !wrote16)   // the path taken did not split its result itself
+        rc = launch_split_rows(p.C, p.M, p.N, p.ldc, p.epi.c16_hi, p.epi.c16_lo, p.epi.ld16, p.overflow, stream);
+    return rc;
 }
 
 }  // namespace subgc

@@ -55,6 +55,7 @@ struct H3Params {
     int tma_part;          // 1: the partial tiles leave through shared memory + TMA stores (full 128-byte lines) instead of per-thread rows
     TraceSlot trace;
     CellEpilogue cell;     // kCell instantiation only
+    int* overflow;         // fp16-range flag for the split copy of the result (epi.c16_*)
     int pf_dist;           // k-blocks the L2 prefetch of weight tiles runs ahead of the ring (0 = off)
     int dbg;               // timing experiments only (SUBGC_H3_DBG bit mask, results are wrong): 1 no activation loads after the first
                            // ring round, 2 no weight loads after it, 4 no MMAs
@@ -350,6 +351,18 @@ __global__ void __launch_bounds__(H3_THREADS, 1) h3_gemm_kernel(const __grid_con
                         if (p.epi.bias) tv += b1[u];
                         if (p.epi.bias2) tv += b2[u];
                         v[u] = p.epi.relu ? fmaxf(tv, 0.f) : tv;
+                    }
+                    if (p.epi.c16_hi && col0 + j + 8 <= p.N) {   // split-fp16 copy for the consumer contraction: 8 values = 16 bytes of hi and of lo
+                        unsigned short hh[8], hl[8];
+                        int ovf = 0;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) split_f16(v[u], hh[u], hl[u], ovf);
+                        const size_t o16 = (size_t)row * p.epi.ld16 + col0 + j;
+                        *reinterpret_cast<uint4*>(p.epi.c16_hi + o16) = make_uint4((uint32_t)hh[0] | ((uint32_t)hh[1] << 16), (uint32_t)hh[2] | ((uint32_t)hh[3] << 16),
+                                                                                   (uint32_t)hh[4] | ((uint32_t)hh[5] << 16), (uint32_t)hh[6] | ((uint32_t)hh[7] << 16));
+                        *reinterpret_cast<uint4*>(p.epi.c16_lo + o16) = make_uint4((uint32_t)hl[0] | ((uint32_t)hl[1] << 16), (uint32_t)hl[2] | ((uint32_t)hl[3] << 16),
+                                                                                   (uint32_t)hl[4] | ((uint32_t)hl[5] << 16), (uint32_t)hl[6] | ((uint32_t)hl[7] << 16));
+                        if (ovf && p.overflow) atomicOr(p.overflow, 1);
                     }
                     if (vecc) {
 #pragma unroll
@@ -760,7 +773,18 @@ static int h3_set_smem_attr() {
 
 // Workspace: within tc_workspace_bytes(M, N, Ktotal) (split activations take M * Kp * 4 bytes per segment like the fp32 copies there,
 // and the split count is never larger because a k-block covers four times the columns).
-int launch_gemm_h3(const GemmProblem& p, void* ws_, size_t ws_bytes, cudaStream_t stream, RawPartials* raw) {
+int launch_split_rows(const float* A, int M, int K, int lda, unsigned short* hi, unsigned short* lo, int ld16, int* overflow, cudaStream_t stream) {
+    GemmSeg g = make_seg(A, lda, nullptr, 0, K);
+    const size_t quads = (size_t)M * (ld16 >> 2);
+    int gb = (int)((quads + 255) / 256);
+    if (gb > kNumSMs * 8) gb = kNumSMs * 8;
+    if (gb < 1) gb = 1;
+    SUBGC_CUDA(launch_pdl(split_rows_kernel, dim3(gb), dim3(256), (size_t)0, stream, g, M, ld16, hi, lo, (const int*)nullptr, overflow));
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}
+
+int launch_gemm_h3(const GemmProblem& p, void* ws_, size_t ws_bytes, cudaStream_t stream, RawPartials* raw, bool* wrote_c16) {
     int segK[H3_MAX_SEG];
     for (int s = 0; s < p.nseg; ++s) segK[s] = p.seg[s].K;
     const H3Plan pl = h3_plan(p.M, p.N, segK, p.nseg);
@@ -774,7 +798,12 @@ int launch_gemm_h3(const GemmProblem& p, void* ws_, size_t ws_bytes, cudaStream_
     H3Params hp;
     SUBGC_TRY(h3_segments(p, pl.bn, ws, stream, hp));
     hp.bn = pl.bn; hp.stages = pl.stages; hp.kb_per_split = pl.kb_per_split; hp.part = part;
-    hp.direct = direct ? 1 : 0; hp.epi = p.epi; hp.C = p.C; hp.ldc = p.ldc;
+    hp.direct = direct ? 1 : 0; hp.epi = p.epi; hp.C = p.C; hp.ldc = p.ldc; hp.overflow = p.overflow;
+    // the in-kernel split copy needs whole 8-column groups and 16-byte aligned rows; anything else is split by the caller afterwards
+    const bool c16_here = direct && p.epi.c16_hi && p.epi.c16_lo && (p.N & 7) == 0 && (p.epi.ld16 & 7) == 0 && ((p.ldc & 3) == 0) &&
+                          (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && !p.epi.accumulate;
+    if (!c16_here) { hp.epi.c16_hi = nullptr; hp.epi.c16_lo = nullptr; }
+    if (wrote_c16) *wrote_c16 = c16_here;
     static const bool tma_store = getenv("SUBGC_H3_NO_TMA_STORE") == nullptr;
     hp.tma_part = 0;
     hp.tm_part = hp.tm_wh[0];
@@ -839,7 +868,7 @@ int launch_gemm_cell(const GemmProblem& p0, const CellEpilogue& cell, void* ws_,
     Workspace ws(ws_, ws_bytes);
     H3Params hp;
     SUBGC_TRY(h3_segments(p, 32, ws, stream, hp));
-    hp.bn = 128; hp.kb_per_split = kps; hp.part = nullptr; hp.direct = 0; hp.epi = GemmEpilogue(); hp.C = nullptr; hp.ldc = 0;
+    hp.bn = 128; hp.kb_per_split = kps; hp.part = nullptr; hp.direct = 0; hp.epi = GemmEpilogue(); hp.C = nullptr; hp.ldc = 0; hp.overflow = nullptr;
     hp.tma_part = 0; hp.tm_part = hp.tm_wh[0];
     const int stage_bytes = 2 * 128 * H3_BK * 2 + 2 * H3_X_BYTES;
     hp.stages = H3_SMEM_BUDGET / stage_bytes;

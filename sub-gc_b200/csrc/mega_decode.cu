@@ -85,6 +85,7 @@ struct MgParams {
                                  // are then upper bounds (buffer strides) and the real values are read here: no host round trip
     int len_stride;              // nodes per row in att / p_att / masks
     unsigned long long* trace;   // debug (SUBGC_MEGA_TRACE=1): [cta][step][MG_TRACE_EVENTS] globaltimer stamps, else nullptr
+    unsigned long long timeout_ns;   // a wait longer than this aborts the kernel (SUBGC_MEGA_TIMEOUT_S, default 4 s)
 };
 
 // ---- PTX helpers local to this kernel ------------------------------------------------------------------------------------------
@@ -133,15 +134,17 @@ struct MgCtl {
 };
 static_assert(sizeof(MgCtl) <= 1024, "control block must fit its 1 KB");
 
-constexpr unsigned long long MG_TIMEOUT_NS = 4000000000ull;   // a wait longer than this aborts the kernel (debug guard: never hang the GPU)
+// a wait longer than MgParams::timeout_ns aborts the kernel (guard: never hang the GPU).  Default 4 s; SUBGC_MEGA_TIMEOUT_S raises it
+// for runs under compute-sanitizer, where the kernel is ~100x slower.
 
 struct MgWait {
     MgCtl* ctl;
     unsigned* sync;
     unsigned long long t0;
+    unsigned long long timeout_ns;
     __device__ __forceinline__ bool expired(int site) {
         if (ld_acquire(sync + MG_C_ABORT) != 0) { ctl->stop = 2; return true; }
-        if (globaltimer_ns() - t0 > MG_TIMEOUT_NS) {
+        if (globaltimer_ns() - t0 > timeout_ns) {
             atomicCAS(sync + MG_C_ABORT, 0u, (unsigned)(site * 1000 + (int)blockIdx.x + 1));
             ctl->stop = 2;
             return true;
@@ -272,7 +275,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = ctl->tmem_slot;
     const MgCta& cta = ctl->cta;
-    MgWait wt_{ctl, p.sync, globaltimer_ns()};
+    MgWait wt_{ctl, p.sync, globaltimer_ns(), p.timeout_ns};
 #define MG_STAMP(T_, EV_) do { if (p.trace) p.trace[((size_t)cta_id * T + (T_)) * MG_TRACE_EVENTS + (EV_)] = globaltimer_ns(); } while (0)
 
     if (warp == 0) {
@@ -1169,6 +1172,12 @@ int launch_mega_decode(const subgc_dims* d, const subgc_weights* w, int S, int l
     p.mode = mode; p.temp = temp; p.top_k = top_k; p.seed = seed; p.offset = offset; p.uniforms = uniforms;
     p.counts = counts; p.len_stride = len_max;
     p.trace = (pl.n_cta <= 256 && d->seq_length <= 32) ? mega_trace_buffer(nullptr) : nullptr;
+    static const unsigned long long timeout_ns = [] {
+        const char* e = getenv("SUBGC_MEGA_TIMEOUT_S");
+        const double s = e ? atof(e) : 0.0;
+        return (unsigned long long)((s > 0.0 ? s : 4.0) * 1e9);
+    }();
+    p.timeout_ns = timeout_ns;
     static DeviceOnce once;
     SUBGC_CUDA(once.run([]() { return cudaFuncSetAttribute(mega_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM); }));
     cudaLaunchConfig_t cfg = {};

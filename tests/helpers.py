@@ -67,3 +67,15 @@ def rel_err(a, b):
 
 def t2n(t):
     return t.detach().cpu().numpy() if torch.is_tensor(t) else np.asarray(t)
+
+
+def check_train_outputs(outputs, g, tol):
+    """outputs [rows, T, V1] of a training-case fixture: stored in full at small dims, as a slice + checksums + row-wise arg-max at full
+    dims (oracle/make_golden.py: run_train_case(store_full=False))."""
+    o = t2n(outputs)
+    if "outputs" in g.files:
+        assert o.shape == g["outputs"].shape and rel_err(o, g["outputs"]) <= tol
+        return
+    assert rel_err(o[:, :, :48], g["outputs_slice"]) <= tol
+    assert abs(float(np.asarray(o, np.float64).sum()) - float(g["outputs_sum"])) <= tol * float(g["outputs_abssum"])
+    assert np.array_equal(o.argmax(2), g["outputs_argmax"])

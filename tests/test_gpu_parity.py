@@ -12,7 +12,7 @@ import pytest
 import torch
 
 import subgc_oracle as O
-from helpers import beam_sizes_in, load_golden, rebuild_test_case, rebuild_train_case, rel_err, t2n
+from helpers import check_train_outputs, beam_sizes_in, load_golden, rebuild_test_case, rebuild_train_case, rel_err, t2n
 from subgc import synth
 from subgc.config import SMALL, Dims, make_opt
 from subgc.model import LossWrapper, setup
@@ -272,7 +272,7 @@ def test_nms_golden_cases_on_device():
     assert ci == 6
 
 
-@pytest.mark.parametrize("name", ["small_train", "small_train_refinit"])
+@pytest.mark.parametrize("name", ["small_train", "small_train_refinit", "full_train"])
 def test_golden_forward_mode_and_losses(name):
     """mode='forward' in eval (validation-loss branch, eval_utils.py:73-86) against the reference's outputs."""
     g = load_golden(name)
@@ -284,8 +284,7 @@ def test_golden_forward_mode_and_losses(name):
         lw = LossWrapper(model, None)
         res = lw(dev["fc_feats"], dev["att_feats"], dev["labels"], dev["masks"], dev["att_masks"], None, None, None, dev["obj_dist"], None,
                  dev["rel_ind"], None, dev["pred_dist"], dev["gpn_obj_ind"], dev["gpn_pred_ind"], dev["gpn_nrel_ind"], dev["gpn_pool_mtx"])
-    assert tuple(outputs.shape) == g["outputs"].shape
-    assert rel_err(t2n(outputs), g["outputs"]) <= RTOL
+    check_train_outputs(outputs, g, RTOL)
     assert tuple(score.shape) == g["subgraph_score"].shape and rel_err(t2n(score), g["subgraph_score"]) <= RTOL
     assert abs(float(gpn_loss) - float(g["gpn_loss"])) <= RTOL * 10
     assert abs(float(res["lang_loss"]) - float(g["lang_loss"])) <= RTOL * 10 * max(1.0, abs(float(g["lang_loss"])))

@@ -145,8 +145,10 @@ def test_graph_blocks(ops):
     assert torch.equal(cls.cpu(), e.class_argmax(data["obj_dist"].reshape(B * N, -1), 1))
 
 
-@pytest.mark.parametrize("name", ["small_train", "small_train_refinit"])
+@pytest.mark.parametrize("name", ["small_train", "small_train_refinit", "full_train"])
 def test_loss_wrapper_backward_matches_reference(name):
+    """full_train: the reference's own autograd gradients at FULL dimensions (V = 9487, H = 1000, 2048-d features; 2 images, 10
+    sentences): the training path's tensor-core contractions (split-TF32, K up to 3000, N = 9488) against something real."""
     g = load_golden(name)
     d, sd, data = rebuild_train_case(g)
     model = setup(make_opt(d))

@@ -10,7 +10,7 @@ import pytest
 import torch
 
 import subgc_oracle as O
-from helpers import beam_sizes_in, load_golden, rebuild_test_case, rebuild_train_case, rel_err, t2n
+from helpers import check_train_outputs, beam_sizes_in, load_golden, rebuild_test_case, rebuild_train_case, rel_err, t2n
 
 TOL = 1e-6
 TEST_CASES = ["small_test_ragged", "small_test_nms", "small_test_full", "full_test", "full_test_peaked"]
@@ -79,13 +79,13 @@ def test_beam(case):
                 assert abs(bm["p"] - g[f"beam{b}_beam_p"][s, j]) <= 1e-5 * max(1.0, abs(g[f"beam{b}_beam_p"][s, j]))
 
 
-@pytest.mark.parametrize("name", ["small_train", "small_train_refinit"])
+@pytest.mark.parametrize("name", ["small_train", "small_train_refinit", "full_train"])
 def test_train_forward_losses_and_grads(name):
     g = load_golden(name)
     d, sd, data = rebuild_train_case(g)
     sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     r = O.loss_wrapper(sd, d, data)
-    assert rel_err(t2n(r["outputs"]), g["outputs"]) <= TOL
+    check_train_outputs(r["outputs"], g, TOL)
     assert rel_err(t2n(r["subgraph_score"]), g["subgraph_score"]) <= TOL
     assert abs(float(r["lang_loss"]) - float(g["lang_loss"])) <= TOL * 10
     assert abs(float(r["gpn_loss"]) - float(g["gpn_loss"])) <= TOL

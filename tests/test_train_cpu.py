@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from emu_ops import EmuOps
-from helpers import load_golden, rebuild_train_case, rel_err, t2n
+from helpers import check_train_outputs, load_golden, rebuild_train_case, rel_err, t2n
 from subgc import train
 from subgc.model import LanguageModelCriterion
 
@@ -17,7 +17,7 @@ def test_train_step_matches_reference_gradients(name):
     ops = EmuOps()
     with torch.no_grad():
         outputs, gpn_loss, score, S = train.forward(ops, sd, sd, d, data, drop=None)
-    assert rel_err(t2n(outputs), g["outputs"]) <= 1e-5
+    check_train_outputs(outputs, g, 1e-5)
     assert rel_err(t2n(score), g["subgraph_score"]) <= 1e-5
     assert abs(float(gpn_loss) - float(g["gpn_loss"])) <= 1e-5
     leaf = outputs.clone().requires_grad_(True)
