@@ -43,8 +43,8 @@ constexpr int MG_MAX_TASKS = 8;
 constexpr int MG_TRACE_EVENTS = 48;   // 0-16 workers, 20 + 2k / 21 + 2k MMA task k (operands landed / issued), 40 producer (step issued)
 constexpr int MG_MAX_TILES = 192;
 
-enum { MG_X_XT = 0, MG_X_CTX = 1, MG_X_HATT = 2, MG_X_HLANG_PREV = 3, MG_X_HLANG = 4 };
-enum { MG_F_START = 1, MG_F_COMMIT = 2, MG_F_NEXT = 4, MG_F_AXT = 8 };
+enum { MG_X_CTX = 1, MG_X_HATT = 2, MG_X_HLANG_PREV = 3, MG_X_HLANG = 4 };
+enum { MG_F_START = 1, MG_F_COMMIT = 2, MG_F_NEXT = 4 };
 enum { MG_JOB_A = 0, MG_JOB_B = 1, MG_JOB_C = 2, MG_JOB_D = 3 };
 // sync counters (uint32 indices into MgParams::sync)
 enum { MG_C_XT = 0, MG_C_HATT = 32, MG_C_HLANG = 64, MG_C_CTX = 96, MG_C_B = 128, MG_C_D = 160, MG_C_ABORT = 192, MG_C_TILE_A = 256,
@@ -71,14 +71,16 @@ struct MgCta {
 struct MgParams {
     const MgCta* ctas;
     const uint8_t* wstream;
-    int n_cta, S, T, len_max, H, E, AH, V1, kbH, kbE;
+    int n_cta, S, T, len_max, H, AH, V1, kbH;
     int nL, nB, nD, zB, zD, ldB, ldD;
     const float* fc_pre; const float* att; const float* p_att; const float* masks;
-    const float* h2att_b; const float* alpha_w; const float* alpha_b; const float* logit_b; const float* embed;
+    const float* h2att_b; const float* alpha_w; const float* alpha_b; const float* logit_b;
+    const float* xt_table;       // [V1, H, 4] (gates i,f,g,o of a unit adjacent): W_ih[:, 2H:2H+E] relu(E[v]) for every token v (subgc_mega_pack)
     const float* lang_b_ih; const float* lang_b_hh;
-    uint8_t* x_xt; uint8_t* x_ctx; uint8_t* x_hatt[2]; uint8_t* x_hlang[2];
+    uint8_t* x_ctx; uint8_t* x_hatt[2]; uint8_t* x_hlang[2];
     float* partA; float* partC; float* partB; float* partD;
     unsigned* sync;
+    int* tok_slots;              // [T][128], zero at launch: token of (step, row) + 1 once selected (the cells of the next step spin on it)
     long long* seq; float* seq_lp; int* steps_done; int* overflow;
     int mode; float temp; int top_k; unsigned long long seed, offset; const float* uniforms;
     const int* counts;           // nullable DEVICE int32[2]: (rows, longest sub-graph) decided by the NMS kernel earlier in the stream; S / len_max
@@ -103,6 +105,12 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ int ld_relaxed_s32(const int* p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_s32(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void red_release(unsigned* p, unsigned v) { asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async.global;" ::: "memory"); }   // generic <-> async proxy, global memory
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -124,12 +132,12 @@ struct MgCtl {
     unsigned long long w_full[MG_WSLOTS], w_empty[MG_WSLOTS], x_full[MG_XSLOTS], x_empty[MG_XSLOTS], acc_full[2], acc_free[2], mma_done;
     uint32_t tmem_slot;
     volatile int stop;      // 1: all rows finished (normal early exit), 2: aborted (time-out; MG_C_ABORT holds the site)
-    volatile int flag[2];   // worker broadcast of a wait result
+    volatile int fail;      // sticky: a worker thread gave up a spin wait (the kernel is stopping)
+    volatile int flag[4];   // worker broadcast of wait results (two per round, rounds alternate)
     int red_i[16];
     float red_f[16];
     float topv[16];
     int topi[16];
-    int s_it;
     MgCta cta;
 };
 static_assert(sizeof(MgCtl) <= 1024, "control block must fit its 1 KB");
@@ -263,7 +271,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
         for (int s = 0; s < MG_XSLOTS; ++s) { mbar_init(smem_u32(&ctl->x_full[s]), 1); mbar_init(smem_u32(&ctl->x_empty[s]), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&ctl->acc_full[s]), 1); mbar_init(smem_u32(&ctl->acc_free[s]), 16); }
         mbar_init(smem_u32(&ctl->mma_done), 1);
-        ctl->stop = 0; ctl->flag[0] = 0; ctl->flag[1] = 0;
+        ctl->stop = 0; ctl->fail = 0; ctl->flag[0] = 0; ctl->flag[1] = 0; ctl->flag[2] = 0; ctl->flag[3] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 3) {
@@ -315,7 +323,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
             bool alive = true;
             int steps = T + 1;   // executed steps as the reference counts them (AttModel.py:312-314)
             // last value seen of every counter: a dependency that is known to be satisfied costs no further L2 round trip.
-            // MG_C_XT packs two counts: bits 0-15 rows whose xt is published, bits 16+ rows still unfinished, summed over the steps
+            // MG_C_XT packs two counts: bits 0-15 rows whose token is selected, bits 16+ rows still unfinished, summed over the steps
             unsigned seen_xt = 0, seen_ctx = 0, seen_hatt = 0, seen_hlang = 0, unf_before = 0;
             auto need = [&](const unsigned* c, unsigned& seen, unsigned target, unsigned mask, int site) -> bool {
                 while ((seen & mask) < target) {
@@ -326,8 +334,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                 return true;
             };
             for (int t = 0; t < T && alive; ++t) {
-                if (!need(p.sync + MG_C_XT, seen_xt, (unsigned)S * (unsigned)(t + 1), 0xffffu, 2)) { alive = false; break; }
-                if (t >= 1) {   // xt(t) complete <=> every row's selection of step t-1 is done: the all-finished early exit is decided here
+                if (t >= 1) {   // every row's selection of step t-1 is done: the all-finished early exit is decided here
+                    if (!need(p.sync + MG_C_XT, seen_xt, (unsigned)S * (unsigned)t, 0xffffu, 2)) { alive = false; break; }
                     const unsigned unf = seen_xt >> 16;
                     if (unf == unf_before) { ctl->stop = 1; steps = t; alive = false; break; }
                     unf_before = unf;
@@ -338,7 +346,6 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                     const uint8_t* xb;
                     bool ok = true;
                     switch (tk.x_src) {
-                        case MG_X_XT: xb = p.x_xt; break;   // checked at the top of the step
                         case MG_X_CTX: xb = p.x_ctx; ok = need(p.sync + MG_C_CTX, seen_ctx, (unsigned)S * (unsigned)(t + 1), ~0u, 3); break;
                         case MG_X_HATT: xb = p.x_hatt[t & 1]; ok = need(p.sync + MG_C_HATT, seen_hatt, (unsigned)p.nL * (unsigned)(t + 1), ~0u, 3); break;
                         case MG_X_HLANG_PREV: xb = p.x_hlang[(t + 1) & 1]; ok = need(p.sync + MG_C_HLANG, seen_hlang, (unsigned)p.nL * (unsigned)t, ~0u, 3); break;
@@ -357,7 +364,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                 }
             }
             if (cta_id == 0 && ctl->stop != 2) {
-                if (alive && need(p.sync + MG_C_XT, seen_xt, (unsigned)S * (unsigned)(T + 1), 0xffffu, 13) && (seen_xt >> 16) == unf_before) steps = T;
+                if (alive && need(p.sync + MG_C_XT, seen_xt, (unsigned)S * (unsigned)T, 0xffffu, 13) && (seen_xt >> 16) == unf_before) steps = T;
                 if (ctl->stop != 2) p.steps_done[0] = steps;
             }
         }
@@ -379,7 +386,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         drain_set = -1;
                     }
-                    const bool fresh = (tk.flags & MG_F_START) || ((tk.flags & MG_F_AXT) && t == 0);
+                    const bool fresh = (tk.flags & MG_F_START) != 0;
                     if (fresh && jobs[set] > 0) {   // the workers must have drained the previous accumulator of this set
                         if (!wt_.mbar(&ctl->acc_free[set], (jobs[set] - 1) & 1u, 5)) { alive = false; break; }
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -520,30 +527,63 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
         if (has_row) {
             for (int j = wt; j < p.AH; j += MG_NW) s_w[j] = __ldg(p.alpha_w + j);
             if (wt < len_rt) s_mask[wt] = __ldg(p.masks + (size_t)row * p.len_stride + wt);
-            // xt(0) = relu(E[<bos> = 0]) (AttModel.py:283-284,332)
-            for (int j = wt; j < p.E; j += MG_NW) x_store(p.x_xt, row, j, fmaxf(__ldg(p.embed + j), 0.f), ovf);
-            w_signal(p.sync + MG_C_XT, true);
         }
 
-        // LSTM cell on this CTA's share of a tile: gates = sum of the tile's split-K partials (split order) + addend
+        // LSTM cell on this CTA's share of a tile: gates = sum of the tile's split-K partials (split order) + addend.
+        // Attention LSTM (is_att): the partials hold W_hh h_att(t-1) + W_ih[:, :H] h_lang(t-1) (contracted and drained during step t-1,
+        // nothing at t = 0: init_hidden is zero); the addends are fc_pre (fc segment + both biases) and the token's row of xt_table
+        // (= W_ih[:, 2H:] relu(E[it]), AttModel.py:332,410-413; it = <bos> = 0 at t = 0, AttModel.py:283-284), so the embedding segment
+        // is a 16 KB row gather instead of a contraction that has to wait for the selection.
         auto cell = [&](const MgJob& jb, const float* part, unsigned* tile_cnt, int t, float (&cst)[2], bool is_att, uint8_t* xout, int ev) -> bool {
             const int nel = 128 * jb.u_n;
-            float add[2][4];
+            const bool have_part = !is_att || t > 0;
+            // nothing is requested before the polls: an acquire load is not served before the thread's earlier loads have landed
+            // (measured: operands requested ahead of the wait delayed the poll by ~2 us)
+            int tok[2] = {0, 0};
+            if (is_att && t > 0) {
+                // Every thread spins on the token slot of its row (both of its elements belong to row wt & 127): the poll returns the
+                // token itself, one L2 round trip instead of counter poll + barrier + token load.  Worker thread 0 polls the tile's
+                // partial counter in the same loop; the barrier below makes its result (and any give-up) common knowledge.
+                const int r = wt & 127;
+                const int* slot = p.tok_slots + (size_t)(t - 1) * 128 + r;
+                const bool want_tok = wt < nel && r < S;
+                const unsigned tile_target = (unsigned)jb.n_split * (unsigned)t;
+                int v = want_tok ? 0 : 1;
+                bool tile_ok = wt != 0;
+                for (uint32_t it = 1; v == 0 || !tile_ok; ++it) {
+                    if (v == 0) v = ld_relaxed_s32(slot);
+                    if (!tile_ok) tile_ok = ld_acquire(tile_cnt) >= tile_target;
+                    if (v != 0 && tile_ok) break;
+                    if (ctl->stop || ((it & 1023u) == 0 && wt_.expired(15))) { ctl->fail = 1; break; }
+                }
+                tok[0] = tok[1] = v - 1;
+                worker_bar();
+                if (ctl->fail) return false;
+            } else if (!is_att) {
+                if (!w_counter(tile_cnt, (unsigned)jb.n_split * (unsigned)(t + 1), 9)) return false;
+            }
+            if (wt == 0) MG_STAMP(t, ev);
+            // fc_pre and xt_table keep the four gates of a unit adjacent: one 16-byte load per element, and the rows of this CTA's units
+            // are 16 x u_n contiguous bytes (gate-major rows cost a 32-byte sector per scalar: measured 7 us per cell)
+            float4 add[2], tab[2];
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {   // operands that do not depend on the partials are requested before the wait
+            for (int k = 0; k < 2; ++k) {
                 const int e = wt + k * MG_NW;
                 const int r = e & 127, u = jb.tile_u0 + jb.u_lo + (e >> 7);
+                const bool live = is_att && e < nel && r < S;
+                add[k] = live ? __ldg(reinterpret_cast<const float4*>(p.fc_pre) + (size_t)r * H + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            float bi[2][4], bh[2][4];   // language LSTM: both biases, requested together with the partials
 #pragma unroll
-                for (int q = 0; q < 4; ++q) add[k][q] = 0.f;
-                if (e < nel && r < S) {
-                    if (is_att) {
+            for (int k = 0; k < 2; ++k) {
+                const int e = wt + k * MG_NW;
+                const int u = jb.tile_u0 + jb.u_lo + (e >> 7);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) add[k][q] = __ldg(p.fc_pre + (size_t)r * 4 * H + (size_t)q * H + u);
-                    }
+                for (int q = 0; q < 4; ++q) {
+                    bi[k][q] = (!is_att && e < nel) ? __ldg(p.lang_b_ih + q * H + u) : 0.f;
+                    bh[k][q] = (!is_att && e < nel) ? __ldg(p.lang_b_hh + q * H + u) : 0.f;
                 }
             }
-            if (!w_counter(tile_cnt, (unsigned)jb.n_split * (unsigned)(t + 1), 9)) return false;
-            if (wt == 0) MG_STAMP(t, ev);
             // every partial of both elements of this thread is requested before the first one is used (one L2 round trip)
             float acc2[2][4];
             if (jb.n_split <= 4) {
@@ -552,7 +592,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                 for (int k = 0; k < 2; ++k) {
                     const int e = wt + k * MG_NW;
                     const int r = e & 127, ul = jb.u_lo + (e >> 7);
-                    const bool live = e < nel && r < S;
+                    const bool live = e < nel && r < S && have_part;
                     const float* g = part + jb.part_tile_off + r;
 #pragma unroll
                     for (int z = 0; z < 4; ++z) {
@@ -571,7 +611,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                 for (int k = 0; k < 2; ++k) {
                     const int e = wt + k * MG_NW;
                     const int r = e & 127, ul = jb.u_lo + (e >> 7);
-                    const bool live = e < nel && r < S;
+                    const bool live = e < nel && r < S && have_part;
                     const float* g = part + jb.part_tile_off + r;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) acc2[k][q] = 0.f;
@@ -584,16 +624,29 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const int e = wt + k * MG_NW;
+                const int r = e & 127, u = jb.tile_u0 + jb.u_lo + (e >> 7);
+                const bool live = is_att && e < nel && r < S;
+                tab[k] = live ? __ldg(reinterpret_cast<const float4*>(p.xt_table) + (size_t)tok[k] * H + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (p.trace && wt == 0) {   // the stamp must not be taken before the operands have landed
+                asm volatile("" ::"f"(acc2[0][0]), "f"(acc2[1][3]), "f"(tab[0].x), "f"(tab[1].w), "f"(add[0].x), "f"(add[1].w) : "memory");
+                MG_STAMP(t, is_att ? 36 : 37);
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int e = wt + k * MG_NW;
                 if (e >= nel) continue;
                 const int r = e & 127, ul = jb.u_lo + (e >> 7), u = jb.tile_u0 + ul;
                 if (r >= S) continue;
                 float acc[4] = {acc2[k][0], acc2[k][1], acc2[k][2], acc2[k][3]};
                 if (is_att) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) acc[q] += add[k][q];
+                    const float a4[4] = {add[k].x, add[k].y, add[k].z, add[k].w}, t4[4] = {tab[k].x, tab[k].y, tab[k].z, tab[k].w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[q] = (acc[q] + a4[q]) + t4[q];
                 } else {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) acc[q] = (acc[q] + __ldg(p.lang_b_ih + q * H + u)) + __ldg(p.lang_b_hh + q * H + u);
+                    for (int q = 0; q < 4; ++q) acc[q] = (acc[q] + bi[k][q]) + bh[k][q];
                 }
                 const float c = mg_sigmoid(acc[1]) * cst[k] + mg_sigmoid(acc[0]) * mg_tanh(acc[2]);
                 cst[k] = c;
@@ -608,9 +661,6 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
             MG_WSTAMP(0);
             // ---------------- attention LSTM: gates -> partial -> cell -> h_att(t)
             if (jA.present) {
-                if (!epilogue(jA, p.partA + jA.part_off, 128, true, t, 1)) break;
-                w_signal(p.sync + MG_C_TILE_A + jA.tile);
-                MG_WSTAMP(2);
                 if (!cell(jA, p.partA, p.sync + MG_C_TILE_A + jA.tile, t, cA, true, p.x_hatt[t & 1], 3)) break;
                 w_signal(p.sync + MG_C_HATT, true);
                 MG_WSTAMP(4);
@@ -857,14 +907,22 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                     const long long it = unf ? tok : 0;
                     p.seq[(size_t)row * T + t] = it;
                     p.seq_lp[(size_t)row * T + t] = lp;
-                    ctl->s_it = (int)it;
+                    st_release_s32(p.tok_slots + (size_t)t * 128 + row, (int)it + 1);   // the cells of step t + 1 spin on this
                 }
-                worker_bar();
-                const float* e = p.embed + (size_t)ctl->s_it * p.E;
-                for (int j = wt; j < p.E; j += MG_NW) x_store(p.x_xt, row, j, fmaxf(__ldg(e + j), 0.f), ovf);
+                {   // the cells gather this token's xt_table row next: on its way into L2 while the token is published and polled for
+                    const size_t row_bytes = (size_t)4 * H * sizeof(float);
+                    const char* tr = reinterpret_cast<const char*>(p.xt_table) + (size_t)tok * row_bytes;
+                    if (wt == 32) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(tr), "r"((uint32_t)row_bytes) : "memory");
+                }
                 MG_WSTAMP(47);
-                w_signal(p.sync + MG_C_XT, true, 1u + (unfinished ? 0x10000u : 0u));   // only worker thread 0 uses the increment
+                w_signal(p.sync + MG_C_XT, false, 1u + (unfinished ? 0x10000u : 0u));   // only worker thread 0 uses the increment
                 MG_WSTAMP(16);
+            }
+            // ---------------- attention LSTM of the NEXT step: the h_att(t) / h_lang(t) segments are contracted by now -> partial
+            if (jA.present && t + 1 < T) {
+                if (!epilogue(jA, p.partA + jA.part_off, 128, true, t, 1)) break;
+                w_signal(p.sync + MG_C_TILE_A + jA.tile);
+                MG_WSTAMP(2);
             }
         }
         if (ovf && p.overflow) atomicOr(p.overflow, 1);
@@ -878,6 +936,22 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
     }
+}
+
+// [rows, 4H] gate-major (row q * H + u of an LSTM weight) -> [rows, H, 4]: the cell reads the four gates of a unit with one 16-byte load
+__global__ void __launch_bounds__(256) gate_interleave_kernel(const float* __restrict__ src, float4* __restrict__ dst, int rows, int H) {
+    const size_t n = (size_t)rows * H;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / H;
+        const int u = (int)(i - r * H);
+        const float* s = src + r * 4 * H + u;
+        dst[i] = make_float4(s[0], s[H], s[2 * (size_t)H], s[3 * (size_t)H]);
+    }
+}
+static void launch_gate_interleave(const float* src, float* dst, int rows, int H, cudaStream_t st) {
+    const size_t n = (size_t)rows * H;
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)kNumSMs * 8);
+    gate_interleave_kernel<<<blocks, 256, 0, st>>>(src, reinterpret_cast<float4*>(dst), rows, H);
 }
 
 // ---- stream pack ---------------------------------------------------------------------------------------------------------------
@@ -921,7 +995,7 @@ __global__ void __launch_bounds__(256) mega_pack_kernel(const MgBlockDesc* __res
 // ---- schedule ------------------------------------------------------------------------------------------------------------------
 struct MgPlan {
     bool ok = false;
-    int n_cta = 0, kbH = 0, kbE = 0;
+    int n_cta = 0, kbH = 0, H = 0, T = 0;
     int zL = 0, tilesL = 0, nL = 0;
     int zB = 0, tilesB = 0, nB = 0, ldB = 0;
     int zD = 0, tilesD = 0, nD = 0, ldD = 0;
@@ -945,13 +1019,13 @@ static MgPlan mega_plan(const subgc_dims* d, int n_cta) {
     if (n_cta < 1 || n_cta > 1024 || H < 4 || (H & 3) || E < 1 || AH < 128 || (AH & 127) || AH > 512 || V1 < 2 || V1 > MG_SELVALS * MG_NW) return pl;
     if ((size_t)(2 * AH + 64 + 64 + 256 + 2 * H) * 4 > MG_SCR_BYTES) return pl;
     pl.n_cta = n_cta;
-    const int kbH = (H + 63) / 64, kbE = (E + 63) / 64;
-    pl.kbH = kbH; pl.kbE = kbE;
+    const int kbH = (H + 63) / 64;
+    pl.kbH = kbH; pl.H = H; pl.T = d->seq_length;
     // LSTM contractions: tiles of <= 7 groups of 4 hidden units (x 4 gates = <= 112 weight rows), zL k-splits per tile
     const int G = H / 4;
     int zL = 0, tilesL = 0;
     for (int z = 8; z >= 1; z >>= 1) {
-        if (z > kbH || z > kbE) continue;
+        if (z > kbH) continue;
         const int tl = std::min(G, n_cta / z);
         if (tl < 1 || (G + tl - 1) / tl > 7) continue;
         const int umax = 4 * ((G + tl - 1) / tl);
@@ -1020,14 +1094,12 @@ static MgPlan mega_plan(const subgc_dims* d, int n_cta) {
         const int bidx = c - (n_cta - pl.nB);
         const bool hasB = bidx >= 0;
         const bool hasD = c < pl.nD;
-        int U = 0, u0 = 0, nrL = 0, ha = 0, hn = 0, ea = 0, en = 0;
+        int U = 0, u0 = 0, nrL = 0, ha = 0, hn = 0;
         if (hasL) {
             U = 4 * gLn[tileL]; u0 = 4 * gL0[tileL]; nrL = 4 * U;
             kb_range(kbH, zl, zL, ha, hn);
-            kb_range(kbE, zl, zL, ea, en);
         }
-        // issue order of a step (see the header): A_xt(t) | C_hlang(t) | B(t) | C_hatt(t) | A_hatt(t+1) | C_ctx(t) | D(t) | A_hlang(t+1)
-        if (hasL) add_task(MG_SRC_ATT_IH, tileL, 1, u0, U, H, nrL, 2 * H, E, ea, en, MG_X_XT, 0, MG_F_COMMIT | MG_F_AXT);
+        // issue order of a step (see the header): C_hlang(t) | B(t) | C_hatt(t) | A_hatt(t+1) | C_ctx(t) | D(t) | A_hlang(t+1)
         if (hasL) add_task(MG_SRC_LANG_HH, tileL, 1, u0, U, H, nrL, 0, H, ha, hn, MG_X_HLANG_PREV, 1, MG_F_START);
         if (hasB) {
             const int tb = bidx / zB, zb = bidx % zB;
@@ -1048,7 +1120,7 @@ static MgPlan mega_plan(const subgc_dims* d, int n_cta) {
             MgJob& jb = ct.job[MG_JOB_D];
             jb.present = n > 0; jb.set = 1; jb.n_rows = 16 * gDn[td]; jb.part_off = 16 * gD0[td]; jb.plane = zd;
         }
-        if (hasL) add_task(MG_SRC_ATT_IH, tileL, 1, u0, U, H, nrL, 0, H, ha, hn, MG_X_HLANG, 0, MG_F_NEXT);
+        if (hasL) add_task(MG_SRC_ATT_IH, tileL, 1, u0, U, H, nrL, 0, H, ha, hn, MG_X_HLANG, 0, MG_F_NEXT | MG_F_COMMIT);
         ct.n_task = nt;
         ct.step_bytes = (int)(w_at - ct.w_off);
         if (hasL) {
@@ -1070,43 +1142,56 @@ static MgPlan mega_plan(const subgc_dims* d, int n_cta) {
 static size_t mega_table_bytes(const MgPlan& pl) {
     return align_up(pl.ctas.size() * sizeof(MgCta), 1024) + align_up(pl.blocks.size() * sizeof(MgBlockDesc), 1024);
 }
+// the pack buffer: schedule tables | weight stream | xt_table [V1, 4H] fp32 | workspace of the contraction that builds the table
+constexpr int MG_XT_CHUNK = 1024;   // token rows per contraction when xt_table is built
+static size_t mega_table_off(const MgPlan& pl) { return align_up((size_t)pl.w_bytes, 1024); }   // from the start of the weight stream
+static size_t mega_xt_bytes(const subgc_dims* d) { return align_up((size_t)d->vocab1 * 4 * d->rnn * sizeof(float), 1024); }
+static size_t mega_xt_tmp_bytes(const subgc_dims* d) { return align_up((size_t)MG_XT_CHUNK * 4 * d->rnn * sizeof(float), 1024); }   // gate-major chunk
+static size_t mega_xt_ws_bytes(const subgc_dims* d) { return mega_xt_tmp_bytes(d) + align_up(gemm_workspace_bytes(MG_XT_CHUNK, 4 * d->rnn, d->enc), 1024) + 1024; }
+static size_t mega_pack_total(const subgc_dims* d, const MgPlan& pl) {
+    return mega_table_bytes(pl) + mega_table_off(pl) + mega_xt_bytes(d) + mega_xt_ws_bytes(d);
+}
 
 struct MgScratch {   // per-call device scratch (inside the decode workspace)
-    uint8_t *x_xt, *x_ctx, *x_hatt[2], *x_hlang[2];
-    float *partA, *partC, *partB, *partD;
+    uint8_t *x_ctx, *x_hatt[2], *x_hlang[2];
+    int* tok_slots;
+    float *partA, *partC, *partB, *partD, *fc_il;
     unsigned* sync;
-    size_t zero_bytes;   // bytes from x_xt that must be zero at launch (activation tiles + counters)
+    size_t zero_bytes;   // bytes from x_ctx that must be zero at launch (activation tiles + counters)
 };
 static size_t mega_scratch_bytes(const MgPlan& pl) {
     size_t b = 0;
-    b += align_up((size_t)pl.kbE * MG_XTILE_BYTES, 1024) + 5 * align_up((size_t)pl.kbH * MG_XTILE_BYTES, 1024) + MG_C_TOTAL * 4;
+    b += 5 * align_up((size_t)pl.kbH * MG_XTILE_BYTES, 1024) + MG_C_TOTAL * 4 + (size_t)pl.T * 128 * 4;
     b += 2 * align_up((size_t)pl.nL * 16384 * 4, 1024);
     b += align_up((size_t)pl.zB * 128 * pl.ldB * 4, 1024) + align_up((size_t)pl.zD * 128 * pl.ldD * 4, 1024);
+    b += align_up((size_t)128 * 4 * pl.H * 4, 1024);   // gate-interleaved copy of fc_pre
     return b + 2048;
 }
 static bool mega_take_scratch(const MgPlan& pl, Workspace& ws, MgScratch& sc) {
-    const size_t xe = align_up((size_t)pl.kbE * MG_XTILE_BYTES, 1024), xh = align_up((size_t)pl.kbH * MG_XTILE_BYTES, 1024);
-    uint8_t* z = ws.take<uint8_t>(xe + 5 * xh + MG_C_TOTAL * 4 + 1024);
+    const size_t xh = align_up((size_t)pl.kbH * MG_XTILE_BYTES, 1024);
+    uint8_t* z = ws.take<uint8_t>(5 * xh + MG_C_TOTAL * 4 + (size_t)pl.T * 128 * 4 + 1024);
     if (!z) return false;
     z = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(z), 1024));
-    sc.x_xt = z; sc.x_ctx = z + xe; sc.x_hatt[0] = sc.x_ctx + xh; sc.x_hatt[1] = sc.x_hatt[0] + xh; sc.x_hlang[0] = sc.x_hatt[1] + xh;
+    sc.x_ctx = z; sc.x_hatt[0] = sc.x_ctx + xh; sc.x_hatt[1] = sc.x_hatt[0] + xh; sc.x_hlang[0] = sc.x_hatt[1] + xh;
     sc.x_hlang[1] = sc.x_hlang[0] + xh;
     sc.sync = reinterpret_cast<unsigned*>(sc.x_hlang[1] + xh);
-    sc.zero_bytes = xe + 5 * xh + MG_C_TOTAL * 4;
+    sc.tok_slots = reinterpret_cast<int*>(sc.sync + MG_C_TOTAL);
+    sc.zero_bytes = 5 * xh + MG_C_TOTAL * 4 + (size_t)pl.T * 128 * 4;
     sc.partA = ws.take<float>((size_t)pl.nL * 16384);
     sc.partC = ws.take<float>((size_t)pl.nL * 16384);
     sc.partB = ws.take<float>((size_t)pl.zB * 128 * pl.ldB);
     sc.partD = ws.take<float>((size_t)pl.zD * 128 * pl.ldD);
+    sc.fc_il = ws.take<float>((size_t)128 * 4 * pl.H);
     return ws.ok();
 }
 
 static const MgPlan& cached_plan(const subgc_dims* d, int n_cta) {   // the schedule is a pure function of (dims, CTA count)
-    struct Key { int H, E, AH, V1, n; };
-    static thread_local Key key{0, 0, 0, 0, 0};
+    struct Key { int H, E, AH, V1, n, T; };
+    static thread_local Key key{0, 0, 0, 0, 0, 0};
     static thread_local MgPlan plan;
-    if (!(key.H == d->rnn && key.E == d->enc && key.AH == d->att_hid && key.V1 == d->vocab1 && key.n == n_cta)) {
+    if (!(key.H == d->rnn && key.E == d->enc && key.AH == d->att_hid && key.V1 == d->vocab1 && key.n == n_cta && key.T == d->seq_length)) {
         plan = mega_plan(d, n_cta);
-        key = Key{d->rnn, d->enc, d->att_hid, d->vocab1, n_cta};
+        key = Key{d->rnn, d->enc, d->att_hid, d->vocab1, n_cta, d->seq_length};
     }
     return plan;
 }
@@ -1145,7 +1230,7 @@ bool mega_decode_eligible(const subgc_dims* d, const subgc_weights* w, int S, in
     if (!mega_enabled() || !w || !w->mega || w->mega_ctas <= 0 || att_weights != nullptr) return false;
     if (S < 1 || S > 128 || S > w->mega_ctas || len_max < 1 || len_max > 64) return false;
     const MgPlan& pl = cached_plan(d, w->mega_ctas);
-    return pl.ok && w->mega_bytes >= mega_table_bytes(pl) + pl.w_bytes;
+    return pl.ok && w->mega_bytes >= mega_pack_total(d, pl);
 }
 
 // The loop of subgc_decode_sample as one cooperative launch.  fc_pre: [S, 4H] hoisted fc segment + both biases (launch_fc_pre).
@@ -1155,19 +1240,22 @@ int launch_mega_decode(const subgc_dims* d, const subgc_weights* w, int S, int l
     const MgPlan& pl = cached_plan(d, w->mega_ctas);
     MgScratch sc;
     if (!mega_take_scratch(pl, ws, sc)) { set_error("subgc_decode_sample: workspace too small for the persistent decode kernel"); return SUBGC_E_WORKSPACE; }
-    SUBGC_CUDA(cudaMemsetAsync(sc.x_xt, 0, sc.zero_bytes, st));
+    SUBGC_CUDA(cudaMemsetAsync(sc.x_ctx, 0, sc.zero_bytes, st));
     MgParams p;
     memset(&p, 0, sizeof(p));
     const uint8_t* mb = static_cast<const uint8_t*>(w->mega);
     p.ctas = reinterpret_cast<const MgCta*>(mb);
     p.wstream = mb + mega_table_bytes(pl);
-    p.n_cta = pl.n_cta; p.S = S; p.T = d->seq_length; p.len_max = len_max; p.H = d->rnn; p.E = d->enc; p.AH = d->att_hid; p.V1 = d->vocab1;
-    p.kbH = pl.kbH; p.kbE = pl.kbE; p.nL = pl.nL; p.nB = pl.nB; p.nD = pl.nD; p.zB = pl.zB; p.zD = pl.zD; p.ldB = pl.ldB; p.ldD = pl.ldD;
-    p.fc_pre = fc_pre; p.att = att; p.p_att = p_att; p.masks = masks;
-    p.h2att_b = w->h2att.b; p.alpha_w = w->alpha_net.w; p.alpha_b = w->alpha_net.b; p.logit_b = w->logit.b; p.embed = w->embed;
+    p.n_cta = pl.n_cta; p.S = S; p.T = d->seq_length; p.len_max = len_max; p.H = d->rnn; p.AH = d->att_hid; p.V1 = d->vocab1;
+    p.kbH = pl.kbH; p.nL = pl.nL; p.nB = pl.nB; p.nD = pl.nD; p.zB = pl.zB; p.zD = pl.zD; p.ldB = pl.ldB; p.ldD = pl.ldD;
+    launch_gate_interleave(fc_pre, sc.fc_il, S, d->rnn, st);   // S is the row capacity when `counts` decides the real count
+    SUBGC_LAUNCH_CHECK();
+    p.fc_pre = sc.fc_il; p.att = att; p.p_att = p_att; p.masks = masks;
+    p.h2att_b = w->h2att.b; p.alpha_w = w->alpha_net.w; p.alpha_b = w->alpha_net.b; p.logit_b = w->logit.b;
+    p.xt_table = reinterpret_cast<const float*>(p.wstream + mega_table_off(pl));
     p.lang_b_ih = w->lang_b_ih; p.lang_b_hh = w->lang_b_hh;
-    p.x_xt = sc.x_xt; p.x_ctx = sc.x_ctx; p.x_hatt[0] = sc.x_hatt[0]; p.x_hatt[1] = sc.x_hatt[1]; p.x_hlang[0] = sc.x_hlang[0]; p.x_hlang[1] = sc.x_hlang[1];
-    p.partA = sc.partA; p.partC = sc.partC; p.partB = sc.partB; p.partD = sc.partD; p.sync = sc.sync;
+    p.x_ctx = sc.x_ctx; p.x_hatt[0] = sc.x_hatt[0]; p.x_hatt[1] = sc.x_hatt[1]; p.x_hlang[0] = sc.x_hlang[0]; p.x_hlang[1] = sc.x_hlang[1];
+    p.partA = sc.partA; p.partC = sc.partC; p.partB = sc.partB; p.partD = sc.partD; p.sync = sc.sync; p.tok_slots = sc.tok_slots;
     p.seq = reinterpret_cast<long long*>(seq); p.seq_lp = seq_lp; p.steps_done = steps_done; p.overflow = w->h3_overflow;
     p.mode = mode; p.temp = temp; p.top_k = top_k; p.seed = seed; p.offset = offset; p.uniforms = uniforms;
     p.counts = counts; p.len_stride = len_max;
@@ -1206,7 +1294,7 @@ extern "C" int subgc_debug_mega_trace(unsigned long long* host_out, int n_cta, i
 extern "C" size_t subgc_mega_pack_bytes(const subgc_dims* d, int n_cta) {
     if (!d) return 0;
     const MgPlan& pl = cached_plan(d, n_cta);
-    return pl.ok ? mega_table_bytes(pl) + (size_t)pl.w_bytes : 0;
+    return pl.ok ? mega_pack_total(d, pl) : 0;
 }
 
 extern "C" int subgc_mega_pack(const subgc_dims* d, const subgc_weights* w, int n_cta, void* buf, size_t bytes, int32_t* overflow, subgc_stream_t stream) {
@@ -1214,7 +1302,7 @@ extern "C" int subgc_mega_pack(const subgc_dims* d, const subgc_weights* w, int 
     const MgPlan& pl = cached_plan(d, n_cta);
     SUBGC_CHECK_ARG(pl.ok, "subgc_mega_pack: these dimensions are not supported by the persistent decode kernel");
     const size_t tb = mega_table_bytes(pl);
-    SUBGC_CHECK_ARG(bytes >= tb + pl.w_bytes, "subgc_mega_pack: buffer too small (%zu < %zu)", bytes, tb + (size_t)pl.w_bytes);
+    SUBGC_CHECK_ARG(bytes >= mega_pack_total(d, pl), "subgc_mega_pack: buffer too small (%zu < %zu)", bytes, mega_pack_total(d, pl));
     SUBGC_CHECK_ARG((reinterpret_cast<uintptr_t>(buf) & 1023) == 0, "subgc_mega_pack: buffer must be 1024-byte aligned");
     const int H = d->rnn, E = d->enc;
     const float* srcs[6] = {w->att_w_ih, w->att_w_hh, w->lang_w_ih, w->lang_w_hh, w->h2att.w, w->logit.w};
@@ -1229,5 +1317,23 @@ extern "C" int subgc_mega_pack(const subgc_dims* d, const subgc_weights* w, int 
     SUBGC_CUDA(cudaMemcpyAsync(b + cta_bytes, blocks.data(), blocks.size() * sizeof(MgBlockDesc), cudaMemcpyHostToDevice, st));
     mega_pack_kernel<<<(unsigned)blocks.size(), 256, 0, st>>>(reinterpret_cast<const MgBlockDesc*>(b + cta_bytes), b + tb, overflow);
     SUBGC_LAUNCH_CHECK();
+    // xt_table[v] = W_ih[:, 2H:2H+E] relu(E[v]) (AttModel.py:332,410): the embedding segment of the attention LSTM for every token, so
+    // that the decode loop gathers a row instead of contracting the segment after every selection
+    float* table = reinterpret_cast<float*>(b + tb + mega_table_off(pl));
+    float* tmp = reinterpret_cast<float*>(b + tb + mega_table_off(pl) + mega_xt_bytes(d));
+    void* gws = reinterpret_cast<uint8_t*>(tmp) + mega_xt_tmp_bytes(d);
+    const size_t gws_bytes = mega_xt_ws_bytes(d) - mega_xt_tmp_bytes(d) - 1024;
+    for (int v0 = 0; v0 < d->vocab1; v0 += MG_XT_CHUNK) {
+        GemmProblem gp;
+        gp.wts = w;
+        gp.M = std::min(MG_XT_CHUNK, d->vocab1 - v0); gp.N = 4 * H; gp.nseg = 1;
+        gp.seg[0] = make_seg(w->embed + (size_t)v0 * E, E, w->att_w_ih + 2 * H, E + 2 * H, E);
+        gp.seg[0].relu_a = 1;
+        gp.C = tmp; gp.ldc = 4 * H;
+        gp.overflow = overflow;
+        SUBGC_TRY(launch_gemm(gp, gws, gws_bytes, st));
+        launch_gate_interleave(tmp, table + (size_t)v0 * 4 * H, gp.M, H, st);
+        SUBGC_LAUNCH_CHECK();
+    }
     return SUBGC_OK;
 }

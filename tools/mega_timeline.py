@@ -27,13 +27,13 @@ buf = (C.c_ulonglong * (n_cta * T * EV))()
 _lib.check(_lib.lib().subgc_debug_mega_trace(buf, n_cta, T), "trace")
 a = np.array(buf, dtype=np.float64).reshape(n_cta, T, EV)
 a[a == 0] = np.nan
-names = {0: "step begins (workers)", 1: "acc A complete", 2: "partial A published", 3: "tile A partials complete", 4: "h_att published",
+names = {0: "step begins (workers)", 1: "acc A(t+1) complete", 2: "partial A(t+1) published", 3: "tokens + tile A partials seen (cell A)", 4: "h_att published",
          5: "acc B complete", 6: "partial B published", 7: "all B partials seen (attention)", 8: "ctx published", 9: "acc C complete",
          10: "partial C published", 11: "tile C partials complete", 12: "h_lang published", 13: "acc D complete", 14: "partial D published",
-         15: "all D partials seen (select)", 16: "xt published", 40: "producer: step issued",
-         17: "  cell A computed + stored", 19: "  cell C computed + stored", 41: "  atth reduced", 42: "  scores done", 43: "  softmax done",
-         44: "  ctx partials done", 18: "  ctx stored", 45: "  logits loaded", 46: "  argmax + lse done", 47: "  xt stored"}
-tasks = ["A_xt", "C_hlang", "B", "C_hatt", "A_hatt+", "C_ctx", "D", "A_hlang+"]
+         15: "all D partials seen (select)", 16: "token published", 40: "producer: step issued",
+         36: "  cell A operands landed", 37: "  cell C operands landed", 17: "  cell A computed + stored", 19: "  cell C computed + stored", 41: "  atth reduced", 42: "  scores done", 43: "  softmax done",
+         44: "  ctx partials done", 18: "  ctx stored", 45: "  logits loaded", 46: "  argmax + lse done", 47: "  token chosen"}
+tasks = ["C_hlang", "B", "C_hatt", "A_hatt+", "C_ctx", "D", "A_hlang+"]
 t0 = np.nanmin(a[:, step, 0])
 print(f"step {step} of {T}; us relative to the first CTA entering the step; min / median / max over CTAs")
 rows = []
@@ -56,5 +56,5 @@ for cls, sel in (("CTAs without B", np.isnan(a[:, step, 5])), ("CTAs with B", ~n
 for _, line in sorted(rows, key=lambda r: r[0]):
     print(line)
 per_step = (np.nanmax(a[:, 1:, 16], axis=0) - np.nanmax(a[:, :-1, 16], axis=0)) / 1e3
-print("step time (xt published -> next xt published), us:", np.array2string(per_step, precision=1))
+print("step time (token published -> next token published), us:", np.array2string(per_step, precision=1))
 print("kernel span us:", (np.nanmax(a[:, T - 1, 16]) - np.nanmin(a[:, 0, 0])) / 1e3)
