@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SUBGC_ABI_VERSION 3
+#define SUBGC_ABI_VERSION 4
 #define SUBGC_MAX_GCN_LAYERS 8
 
 typedef void* subgc_stream_t; /* cudaStream_t */
@@ -387,6 +387,53 @@ int subgc_gcn_node_bwd(int B, int N, int K, int L, const float* dx, const float*
                        const int64_t* rel_ind, float* dm_subj, float* dm_obj, subgc_stream_t stream);
 int subgc_gcn_edge_bwd(int B, int N, int K, int L, const float* dp, const float* m_subj, const float* m_obj,
                        const int64_t* rel_ind, float* dm_subj, float* dm_obj, subgc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Stage-level training entries: the teacher-forced decoder of AttModel._forward (models/AttModel.py:150-177:
+ * embed -> TopDownCore (:400-431) -> Attention (:445-471) -> logit + log_softmax (:339-340)) and its backward, ONE call each.
+ * The recurrence is sequenced in C++; the logit contraction, log-softmax, d(logits) and every weight / bias gradient are
+ * batched over the T executed steps (dW = dY_all^T . X_all is one contraction over K = T * R per weight block).
+ * All pointers DEVICE, fp32 unless noted, contiguous.  R rows (sentences), T executed steps, T_total = labels.size(1) - 1.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct subgc_decoder_train_bufs {
+    /* inputs */
+    const int64_t* tokens; /* [T, R] token fed at step t (labels[:, t])                                         */
+    const float* fc;       /* [R, H] fc_embed output after dropout                                              */
+    const float* att;      /* [R, len, H] att_embed output (padded rows exact zeros)                            */
+    const float* p_att;    /* [R, len, AH] ctx2att(att)                                                         */
+    const float* masks;    /* [R, len]                                                                          */
+    const float* m_x;      /* nullable [T, R, E] dropout mask of the word embedding (values 0 or 1/(1-p))       */
+    const float* m_h;      /* nullable [T, R, H] dropout mask of h_lang before the logit                        */
+    /* saved by the forward, read by the backward */
+    float* xt;             /* [T, R, E] relu(E[token]) * m_x                                                    */
+    float* act1;           /* [T, R, 4H] attention-LSTM gate activations (i, f, g, o after their non-linearities) */
+    float* c_att;          /* [T+1, R, H] cell states, slot 0 = init_hidden zeros                               */
+    float* h_att;          /* [T+1, R, H]                                                                       */
+    float* atth;           /* [T, R, AH] h2att(h_att)                                                           */
+    float* ctx;            /* [T, R, H] attention context                                                       */
+    float* alpha;          /* [T, R, len] attention weights                                                     */
+    float* sm;             /* [T, R, len] softmax before masking                                                */
+    float* act2;           /* [T, R, 4H] language-LSTM gate activations                                         */
+    float* c_lang;         /* [T+1, R, H]                                                                       */
+    float* h_lang;         /* [T+1, R, H]                                                                       */
+    float* hd;             /* [T, R, H] h_lang * m_h (unused when m_h is NULL)                                  */
+    float* outputs;        /* [R, T_total, V1] log-probabilities; steps >= T are left untouched                 */
+} subgc_decoder_train_bufs;
+
+typedef struct subgc_decoder_grads { /* gradients, same shapes as the parameters; ACCUMULATED into (caller zero-fills) */
+    float* logit_w; float* logit_b; float* embed;
+    float* att_w_ih; float* att_w_hh; float* att_b_ih; float* att_b_hh;
+    float* lang_w_ih; float* lang_w_hh; float* lang_b_ih; float* lang_b_hh;
+    float* h2att_w; float* h2att_b; float* alpha_w;
+} subgc_decoder_grads;
+
+size_t subgc_decoder_train_workspace_bytes(const subgc_dims* d, int R, int len, int T);
+int subgc_decoder_train_forward(const subgc_dims* d, const subgc_weights* w, int R, int len, int T, int T_total,
+                                const subgc_decoder_train_bufs* b, void* ws, size_t ws_bytes, subgc_stream_t stream);
+/* d_fc [R, H], d_att [R, len, H], d_p_att [R, len, AH]: gradients of the decoder's inputs (overwritten). */
+int subgc_decoder_train_backward(const subgc_dims* d, const subgc_weights* w, int R, int len, int T, int T_total,
+                                 const subgc_decoder_train_bufs* b, const float* d_outputs, const subgc_decoder_grads* g,
+                                 float* d_fc, float* d_att, float* d_p_att, void* ws, size_t ws_bytes, subgc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Optimiser step: utils.clip_gradient_norm(optimizer, clip) (misc/utils.py:174-200) + torch.optim.Adam.step()

@@ -230,12 +230,12 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(const float* __restr
                                                             const float* __restrict__ alpha_w, const float* __restrict__ alpha,
                                                             const float* __restrict__ sm, const float* __restrict__ dctx,
                                                             float* __restrict__ d_att, float* __restrict__ d_p_att, float* __restrict__ d_atth,
-                                                            float* __restrict__ d_w_rows, int len, int H, int AH) {
+                                                            float* __restrict__ d_w_rows, int len, int H, int AH, int ld_dctx) {
     extern __shared__ float s_b[];  // [len] d_e | [len] alpha | [32] red
     float* s_de = s_b; float* s_al = s_b + len; float* red = s_b + 2 * len;
     const int r = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const float* af = att + (size_t)r * len * H;
-    const float* dc = dctx + (size_t)r * H;
+    const float* dc = dctx + (size_t)r * ld_dctx;   // dctx may be a column block of a wider gradient
     for (int n = wid; n < len; n += nw) {  // d_alpha_n
         float a = 0.f;
         for (int j = lane; j < H; j += 32) a = fmaf(dc[j], af[(size_t)n * H + j], a);
@@ -527,7 +527,7 @@ extern "C" int subgc_attention_bwd(int S, int len, int H, int AH, const float* a
                         len > 0 && len <= 64,
                     "subgc_attention_bwd: bad arguments");
     attention_bwd_kernel<<<S, 256, (size_t)(2 * len + 32) * 4, ST>>>(atth, p_att, att, masks, alpha_w, alpha, sm, dctx, d_att, d_p_att, d_atth,
-                                                                      d_w_rows, len, H, AH);
+                                                                      d_w_rows, len, H, AH, H);
     SUBGC_LAUNCH_CHECK();
     return SUBGC_OK;
 }
@@ -623,5 +623,326 @@ extern "C" int subgc_unary(int op, size_t n, const float* a, float* out, subgc_s
     if (n == 0) return SUBGC_OK;
     ew2_kernel<<<ew_blocks(n), 256, 0, ST>>>(op, n, a, out);
     SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}
+
+// =====================================================================================================================================
+// Stage-level training entries: the teacher-forced decoder of AttModel._forward (models/AttModel.py:150-177) and its
+// backward as ONE C call each.  Same arithmetic as the building blocks above, sequenced here instead of from Python, with everything
+// that does not depend on the recurrence batched over the executed steps:
+//   forward : per step ONE multi-segment contraction per LSTM ([h_lang | fc | x_t] . W_ih^T + h_att . W_hh^T, no concat buffer), the
+//             logit contraction + log-softmax once over all T * R rows;
+//   backward: d(logits) / d(h) of all steps in one contraction, per step only the recurrence (cells, attention, dX through transposed
+//             weight blocks prepared once), and every weight / bias gradient as ONE contraction over K = T * R (dW = dY_all^T . X_all).
+// =====================================================================================================================================
+namespace subgc {
+
+// x_t = relu(E[it]) * mask  (AttModel.py:332 embed = Embedding + ReLU + Dropout); one block per row
+__global__ void __launch_bounds__(256) dec_embed_kernel(const float* __restrict__ embed, const long long* __restrict__ it, const float* __restrict__ mask,
+                                                        float* __restrict__ xt, int E) {
+    const int r = blockIdx.x;
+    const float* e = embed + (size_t)it[r] * E;
+    for (int j = threadIdx.x; j < E; j += blockDim.x) {
+        float v = fmaxf(e[j], 0.f);
+        if (mask) v *= mask[(size_t)r * E + j];
+        xt[(size_t)r * E + j] = v;
+    }
+}
+
+// out[r, j] = a[r * lda + j] (+ b[r * ldb + j]) (+ c[r * ldc + j]),  j < n  (column blocks of wider gradients)
+__global__ void __launch_bounds__(256) add_cols_kernel(int R, int n, const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb,
+                                                       const float* __restrict__ c, int ldc, float* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)R * n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / n, j = i - r * n;
+        float v = a[r * lda + j];
+        if (b) v += b[r * ldb + j];
+        if (c) v += c[r * ldc + j];
+        out[i] = v;
+    }
+}
+
+// tail of one backward step.  d_xa [R, ld] = dgates_att . [W_ih | W_hh]: columns [0,H) d(h_lang(t-1)), [H,2H) d(fc), [2H,2H+E) d(x_t),
+// [2H+E, 3H+E) d(h_att(t-1)) (read in place by the next step).  d_fc += ; dh_lang_n = dh_lang_prev + ; embedding rows += d(x_t) through
+// dropout mask and ReLU (x_t > 0 <=> relu'(E[it]) = 1 and the element was kept)
+__global__ void __launch_bounds__(256) dec_bwd_tail_kernel(int R, int H, int E, const float* __restrict__ d_xa, int ld, const float* __restrict__ dh_lang_prev,
+                                                           int ld_prev, const float* __restrict__ xt, const float* __restrict__ mask,
+                                                           const long long* __restrict__ it, float* __restrict__ d_fc, float* __restrict__ dh_lang_n,
+                                                           float* __restrict__ g_embed) {
+    const int r = blockIdx.x;
+    const float* row = d_xa + (size_t)r * ld;
+    for (int j = threadIdx.x; j < H; j += blockDim.x) {
+        d_fc[(size_t)r * H + j] += row[H + j];
+        dh_lang_n[(size_t)r * H + j] = dh_lang_prev[(size_t)r * ld_prev + j] + row[j];
+    }
+    float* ge = g_embed + (size_t)it[r] * E;
+    for (int j = threadIdx.x; j < E; j += blockDim.x) {
+        if (xt[(size_t)r * E + j] > 0.f) {
+            float g = row[2 * H + j];
+            if (mask) g *= mask[(size_t)r * E + j];
+            atomicAdd(ge + j, g);
+        }
+    }
+}
+
+// out[i] = sum over t of in[t * n + i]
+__global__ void __launch_bounds__(256) sum_steps_kernel(int T, size_t n, const float* __restrict__ in, float* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float a = 0.f;
+        for (int t = 0; t < T; ++t) a += in[(size_t)t * n + i];
+        out[i] = a;
+    }
+}
+
+struct StageWs {   // bump allocator over the caller's workspace; everything 256-byte aligned
+    Workspace ws;
+    StageWs(void* p, size_t n) : ws(p, n) {}
+    float* f(size_t n) { return ws.take<float>(n); }
+};
+
+static size_t dec_gemm_ws_bytes(const subgc_dims* d, int R, int T) {
+    const int H = d->rnn, E = d->enc, V1 = d->vocab1, AH = d->att_hid, TR = T * R;
+    size_t m = 0;
+    auto up = [&](int M, int N, int K) { const size_t b = gemm_workspace_bytes(M, N, K); if (b > m) m = b; };
+    up(R, 4 * H, 3 * H + E); up(R, AH, H); up(TR, V1, H);                     // forward
+    up(TR, H, V1); up(V1, H, TR); up(R, 3 * H, 4 * H); up(R, 3 * H + E, 4 * H); up(R, H, AH);
+    up(4 * H, H, TR); up(4 * H, E, TR); up(4 * H, H, R); up(AH, H, TR);       // weight gradients
+    return align_up(m, 256) + 1024;
+}
+
+static int gemm1(int M, int N, int K, const float* A, int lda, const float* W, int ldw, const float* bias, int accumulate, float* C, int ldc, void* ws,
+                 size_t ws_bytes, cudaStream_t st) {
+    GemmProblem p;
+    p.M = M; p.N = N; p.nseg = 1;
+    p.seg[0] = make_seg(A, lda, W, ldw, K);
+    p.epi.bias = bias; p.epi.accumulate = accumulate;
+    p.C = C; p.ldc = ldc;
+    return launch_gemm(p, ws, ws_bytes, st);
+}
+static void tr(const float* in, int rows, int cols, int ld_in, float* out, int ld_out, cudaStream_t st) {
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+    transpose_kernel<<<grid, 256, 0, st>>>(in, rows, cols, ld_in, out, ld_out);
+}
+
+}  // namespace subgc
+
+extern "C" size_t subgc_decoder_train_workspace_bytes(const subgc_dims* d, int R, int len, int T) {
+    if (!d || R < 1 || T < 1) return 0;
+    const size_t H = d->rnn, E = d->enc, V1 = d->vocab1, AH = d->att_hid, TR = (size_t)T * R;
+    size_t b = dec_gemm_ws_bytes(d, R, T);
+    auto add = [&](size_t floats) { b += align_up(floats * 4, 256); };
+    // forward: logits of all steps.  backward (the larger one): transposed weights, d(logits) + its transpose, per-step gate gradients ...
+    add(H * V1); add(3 * H * 4 * H); add((3 * H + E) * 4 * H); add(H * AH);     // W^T blocks
+    add(TR * V1); add(TR * V1);                                                 // dlogits_all, its transpose (forward: logits_all)
+    add(TR * H); add(TR * 4 * H); add(TR * 4 * H); add(TR * AH); add(TR * AH);  // d_hd_all, dg2_all, dg1_all, d_atth_all, d_wrows_all
+    add(4 * H * TR); add((H > E ? H : E) * TR);                                 // dY^T, X^T
+    add((size_t)R * 3 * H); add((size_t)R * (3 * H + E)); add((size_t)R * H * 8); add((size_t)R * 4 * H);
+    (void)len;
+    return b + 4096;
+}
+
+/* Teacher-forced decoder, train mode (models/AttModel.py:150-177 with get_logprobs_state :328-341, TopDownCore :400-431, Attention :445-471).
+ * tokens [T, R]: the token fed at step t (labels[:, t]).  Saved activations land in `b` (see include/subgc_b200.h). */
+extern "C" int subgc_decoder_train_forward(const subgc_dims* d, const subgc_weights* w, int R, int len, int T, int T_total,
+                                           const subgc_decoder_train_bufs* b, void* ws_, size_t ws_bytes, subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(d && w && b && ws_ && R > 0 && T > 0 && T <= T_total && len > 0 && len <= 64, "subgc_decoder_train_forward: bad arguments");
+    SUBGC_CHECK_ARG(ws_bytes >= subgc_decoder_train_workspace_bytes(d, R, len, T), "subgc_decoder_train_forward: workspace too small");
+    cudaStream_t st = ST;
+    const int H = d->rnn, E = d->enc, V1 = d->vocab1, AH = d->att_hid;
+    const size_t RH = (size_t)R * H;
+    StageWs sw(ws_, ws_bytes);
+    const size_t gws_bytes = dec_gemm_ws_bytes(d, R, T);
+    void* gws = sw.ws.take<char>(gws_bytes);
+    float* logits = sw.f((size_t)T * R * V1);
+    SUBGC_CHECK_ARG(sw.ws.ok(), "subgc_decoder_train_forward: workspace too small");
+    // init_hidden (AttModel.py:343-346): slot 0 of the state histories
+    SUBGC_CUDA(cudaMemsetAsync(b->h_att, 0, RH * 4, st)); SUBGC_CUDA(cudaMemsetAsync(b->c_att, 0, RH * 4, st));
+    SUBGC_CUDA(cudaMemsetAsync(b->h_lang, 0, RH * 4, st)); SUBGC_CUDA(cudaMemsetAsync(b->c_lang, 0, RH * 4, st));
+    for (int t = 0; t < T; ++t) {
+        const float* h_att_p = b->h_att + (size_t)t * RH;   float* h_att_n = b->h_att + (size_t)(t + 1) * RH;
+        const float* h_lang_p = b->h_lang + (size_t)t * RH; float* h_lang_n = b->h_lang + (size_t)(t + 1) * RH;
+        float* xt = b->xt + (size_t)t * R * E;
+        dec_embed_kernel<<<R, 256, 0, st>>>(w->embed, reinterpret_cast<const long long*>(b->tokens) + (size_t)t * R,
+                                            b->m_x ? b->m_x + (size_t)t * R * E : nullptr, xt, E);
+        SUBGC_LAUNCH_CHECK();
+        // attention LSTM (AttModel.py:410-413): gates = W_ih [h_lang(t-1) | fc | x_t] + b_ih + W_hh h_att(t-1) + b_hh
+        float* act1 = b->act1 + (size_t)t * R * 4 * H;
+        {
+            GemmProblem p;
+            p.M = R; p.N = 4 * H; p.nseg = 4;
+            p.seg[0] = make_seg(h_lang_p, H, w->att_w_ih, E + 2 * H, H);
+            p.seg[1] = make_seg(b->fc, H, w->att_w_ih + H, E + 2 * H, H);
+            p.seg[2] = make_seg(xt, E, w->att_w_ih + 2 * H, E + 2 * H, E);
+            p.seg[3] = make_seg(h_att_p, H, w->att_w_hh, H, H);
+            p.epi.bias = w->att_b_ih; p.epi.bias2 = w->att_b_hh;
+            p.C = act1; p.ldc = 4 * H;
+            SUBGC_TRY(launch_gemm(p, gws, gws_bytes, st));
+        }
+        SUBGC_TRY(subgc_lstm_cell_train_fwd(R, H, act1, b->c_att + (size_t)t * RH, h_att_n, b->c_att + (size_t)(t + 1) * RH, stream));
+        // attention (AttModel.py:445-471)
+        float* atth = b->atth + (size_t)t * R * AH;
+        SUBGC_TRY(gemm1(R, AH, H, h_att_n, H, w->h2att.w, H, w->h2att.b, 0, atth, AH, gws, gws_bytes, st));
+        float* ctx = b->ctx + (size_t)t * RH;
+        SUBGC_TRY(subgc_attention_train_fwd(R, len, H, AH, atth, b->p_att, b->att, b->masks, w->alpha_net.w, w->alpha_net.b, ctx,
+                                            b->alpha + (size_t)t * R * len, b->sm + (size_t)t * R * len, stream));
+        // language LSTM (AttModel.py:423-426): gates = W_ih [ctx | h_att(t)] + b_ih + W_hh h_lang(t-1) + b_hh
+        float* act2 = b->act2 + (size_t)t * R * 4 * H;
+        {
+            GemmProblem p;
+            p.M = R; p.N = 4 * H; p.nseg = 3;
+            p.seg[0] = make_seg(ctx, H, w->lang_w_ih, 2 * H, H);
+            p.seg[1] = make_seg(h_att_n, H, w->lang_w_ih + H, 2 * H, H);
+            p.seg[2] = make_seg(h_lang_p, H, w->lang_w_hh, H, H);
+            p.epi.bias = w->lang_b_ih; p.epi.bias2 = w->lang_b_hh;
+            p.C = act2; p.ldc = 4 * H;
+            SUBGC_TRY(launch_gemm(p, gws, gws_bytes, st));
+        }
+        SUBGC_TRY(subgc_lstm_cell_train_fwd(R, H, act2, b->c_lang + (size_t)t * RH, h_lang_n, b->c_lang + (size_t)(t + 1) * RH, stream));
+    }
+    // output dropout, logit, log-softmax (AttModel.py:339-340,428-429) over all steps at once
+    const float* hd = b->h_lang + RH;
+    if (b->m_h) {
+        SUBGC_TRY(subgc_ew(EW_MUL, (size_t)T * RH, b->h_lang + RH, b->m_h, b->hd, 0.f, stream));
+        hd = b->hd;
+    }
+    SUBGC_TRY(gemm1(T * R, V1, H, hd, H, w->logit.w, H, w->logit.b, 0, logits, V1, gws, gws_bytes, st));
+    for (int t = 0; t < T; ++t)
+        SUBGC_TRY(subgc_log_softmax_fwd(R, V1, logits + (size_t)t * R * V1, b->outputs + (size_t)t * V1, (size_t)T_total * V1, stream));
+    return SUBGC_OK;
+}
+
+/* Backward of the above given d(outputs) [R, T_total, V1].  Gradients are ACCUMULATED into `g` (the caller zero-fills); d_fc [R, H],
+ * d_att [R, len, H] and d_p_att [R, len, AH] are overwritten with the gradients of the decoder's inputs. */
+extern "C" int subgc_decoder_train_backward(const subgc_dims* d, const subgc_weights* w, int R, int len, int T, int T_total,
+                                            const subgc_decoder_train_bufs* b, const float* d_outputs, const subgc_decoder_grads* g, float* d_fc,
+                                            float* d_att, float* d_p_att, void* ws_, size_t ws_bytes, subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(d && w && b && g && d_outputs && d_fc && d_att && d_p_att && ws_ && R > 0 && T > 0 && T <= T_total && len > 0 && len <= 64,
+                    "subgc_decoder_train_backward: bad arguments");
+    SUBGC_CHECK_ARG(ws_bytes >= subgc_decoder_train_workspace_bytes(d, R, len, T), "subgc_decoder_train_backward: workspace too small");
+    cudaStream_t st = ST;
+    const int H = d->rnn, E = d->enc, V1 = d->vocab1, AH = d->att_hid, TR = T * R;
+    const size_t RH = (size_t)R * H;
+    const int XA = 3 * H + E;   // columns of d_xa: [h_lang | fc | x_t | h_att]
+    StageWs sw(ws_, ws_bytes);
+    const size_t gws_bytes = dec_gemm_ws_bytes(d, R, T);
+    void* gws = sw.ws.take<char>(gws_bytes);
+    float* wt_logit = sw.f((size_t)H * V1);            // [H, V1]
+    float* wt_lang = sw.f((size_t)3 * H * 4 * H);      // [2H + H, 4H] = [W_ih^T ; W_hh^T]
+    float* wt_att = sw.f((size_t)XA * 4 * H);          // [(2H + E) + H, 4H] = [W_ih^T ; W_hh^T]
+    float* wt_h2att = sw.f((size_t)H * AH);            // [H, AH]
+    float* dlogits = sw.f((size_t)TR * V1);
+    float* big_t = sw.f((size_t)TR * V1);              // transposes of the dY operands (largest: [V1, TR])
+    float* d_hd = sw.f((size_t)TR * H);
+    float* dg2 = sw.f((size_t)TR * 4 * H);
+    float* dg1 = sw.f((size_t)TR * 4 * H);
+    float* d_atth = sw.f((size_t)TR * AH);
+    float* d_wrows = sw.f((size_t)TR * AH);
+    float* dyt = sw.f((size_t)4 * H * TR);
+    float* xT = sw.f((size_t)(H > E ? H : E) * TR);
+    float* d_xl = sw.f((size_t)R * 3 * H);             // [d_ctx | d_h_att | d_h_lang(t-1)]
+    float* d_xa = sw.f((size_t)R * XA);
+    float* tmp = sw.f((size_t)R * H * 8);
+    float* dg1_sum = sw.f((size_t)R * 4 * H);
+    SUBGC_CHECK_ARG(sw.ws.ok(), "subgc_decoder_train_backward: workspace too small");
+    float* dh = tmp;                     // d(h_lang(t)) / d(h_att(t)) assembled for the cell backward
+    float* dh_lang_n = tmp + RH;         // from step t+1
+    float* dc_lang[2] = {tmp + 2 * RH, tmp + 3 * RH};
+    float* dc_att[2] = {tmp + 4 * RH, tmp + 5 * RH};
+    const int eb = ew_blocks(RH);
+
+    // transposed weight blocks, once per backward pass (dX = dY . W needs W^T K-major)
+    tr(w->logit.w, V1, H, H, wt_logit, V1, st);
+    tr(w->lang_w_ih, 4 * H, 2 * H, 2 * H, wt_lang, 4 * H, st);
+    tr(w->lang_w_hh, 4 * H, H, H, wt_lang + (size_t)2 * H * 4 * H, 4 * H, st);
+    tr(w->att_w_ih, 4 * H, 2 * H + E, 2 * H + E, wt_att, 4 * H, st);
+    tr(w->att_w_hh, 4 * H, H, H, wt_att + (size_t)(2 * H + E) * 4 * H, 4 * H, st);
+    tr(w->h2att.w, AH, H, H, wt_h2att, AH, st);
+    SUBGC_LAUNCH_CHECK();
+    SUBGC_CUDA(cudaMemsetAsync(d_fc, 0, RH * 4, st));
+    SUBGC_CUDA(cudaMemsetAsync(d_att, 0, (size_t)R * len * H * 4, st));
+    SUBGC_CUDA(cudaMemsetAsync(d_p_att, 0, (size_t)R * len * AH * 4, st));
+
+    // ---- logit + log-softmax of all steps: d(logits), logit.weight / bias, d(h_lang after dropout)
+    for (int t = 0; t < T; ++t)
+        SUBGC_TRY(subgc_log_softmax_bwd(R, V1, b->outputs + (size_t)t * V1, d_outputs + (size_t)t * V1, (size_t)T_total * V1,
+                                        dlogits + (size_t)t * R * V1, stream));
+    const float* hd = b->m_h ? b->hd : b->h_lang + RH;
+    tr(dlogits, TR, V1, V1, big_t, TR, st);
+    tr(hd, TR, H, H, xT, TR, st);
+    SUBGC_LAUNCH_CHECK();
+    SUBGC_TRY(gemm1(V1, H, TR, big_t, TR, xT, TR, nullptr, 1, g->logit_w, H, gws, gws_bytes, st));
+    SUBGC_TRY(subgc_colsum(TR, V1, dlogits, V1, g->logit_b, 1, stream));
+    SUBGC_TRY(gemm1(TR, H, V1, dlogits, V1, wt_logit, V1, nullptr, 0, d_hd, H, gws, gws_bytes, st));
+    if (b->m_h) SUBGC_TRY(subgc_ew(EW_MUL, (size_t)TR * H, d_hd, b->m_h, d_hd, 0.f, stream));
+
+    // ---- the recurrence, last step first
+    for (int t = T - 1; t >= 0; --t) {
+        const bool last = (t == T - 1);
+        const int cur = t & 1, nxt = cur ^ 1;   // dc ping-pong: [nxt] came from step t+1, [cur] is written for step t-1
+        // language LSTM cell: d(h_lang(t)) = d(hd(t)) + what step t+1 sent back
+        const float* dh_l = d_hd + (size_t)t * RH;
+        if (!last) {
+            add_cols_kernel<<<eb, 256, 0, st>>>(R, H, d_hd + (size_t)t * RH, H, dh_lang_n, H, nullptr, 0, dh);
+            SUBGC_LAUNCH_CHECK();
+            dh_l = dh;
+        }
+        float* dg2_t = dg2 + (size_t)t * R * 4 * H;
+        SUBGC_TRY(subgc_lstm_cell_bwd(R, H, b->act2 + (size_t)t * R * 4 * H, b->c_lang + (size_t)t * RH, b->c_lang + (size_t)(t + 1) * RH, dh_l,
+                                      last ? nullptr : dc_lang[nxt], dg2_t, dc_lang[cur], stream));
+        // d[ctx | h_att(t) | h_lang(t-1)] = dgates . [W_ih | W_hh]
+        SUBGC_TRY(gemm1(R, 3 * H, 4 * H, dg2_t, 4 * H, wt_lang, 4 * H, nullptr, 0, d_xl, 3 * H, gws, gws_bytes, st));
+        // attention backward (d_att / d_p_att accumulate over the steps)
+        float* d_atth_t = d_atth + (size_t)t * R * AH;
+        attention_bwd_kernel<<<R, 256, (size_t)(2 * len + 32) * 4, st>>>(b->atth + (size_t)t * R * AH, b->p_att, b->att, b->masks, w->alpha_net.w,
+                                                                         b->alpha + (size_t)t * R * len, b->sm + (size_t)t * R * len, d_xl, d_att, d_p_att,
+                                                                         d_atth_t, d_wrows + (size_t)t * R * AH, len, H, AH, 3 * H);
+        SUBGC_LAUNCH_CHECK();
+        // d(h_att(t)) = language-LSTM input part + h2att part + what step t+1's attention LSTM sent back through W_hh
+        add_cols_kernel<<<eb, 256, 0, st>>>(R, H, d_xl + H, 3 * H, last ? nullptr : d_xa + (2 * H + E), XA, nullptr, 0, dh);
+        SUBGC_LAUNCH_CHECK();
+        SUBGC_TRY(gemm1(R, H, AH, d_atth_t, AH, wt_h2att, AH, nullptr, 1, dh, H, gws, gws_bytes, st));
+        float* dg1_t = dg1 + (size_t)t * R * 4 * H;
+        SUBGC_TRY(subgc_lstm_cell_bwd(R, H, b->act1 + (size_t)t * R * 4 * H, b->c_att + (size_t)t * RH, b->c_att + (size_t)(t + 1) * RH, dh,
+                                      last ? nullptr : dc_att[nxt], dg1_t, dc_att[cur], stream));
+        // d[h_lang(t-1) | fc | x_t | h_att(t-1)] = dgates . [W_ih | W_hh]
+        SUBGC_TRY(gemm1(R, XA, 4 * H, dg1_t, 4 * H, wt_att, 4 * H, nullptr, 0, d_xa, XA, gws, gws_bytes, st));
+        dec_bwd_tail_kernel<<<R, 256, 0, st>>>(R, H, E, d_xa, XA, d_xl + 2 * H, 3 * H, b->xt + (size_t)t * R * E,
+                                               b->m_x ? b->m_x + (size_t)t * R * E : nullptr,
+                                               reinterpret_cast<const long long*>(b->tokens) + (size_t)t * R, d_fc, dh_lang_n, g->embed);
+        SUBGC_LAUNCH_CHECK();
+    }
+
+    // ---- weight / bias gradients: one contraction over K = T * R per weight block
+    auto dW = [&](const float* dy_t, int Mw, const float* x, int Kx, int ldx, int rowsK, float* G, int ldg) -> int {   // G[Mw, Kx] += dy^T . x
+        tr(x, rowsK, Kx, ldx, xT, rowsK, st);
+        SUBGC_LAUNCH_CHECK();
+        return gemm1(Mw, Kx, rowsK, dy_t, rowsK, xT, rowsK, nullptr, 1, G, ldg, gws, gws_bytes, st);
+    };
+    // language LSTM
+    tr(dg2, TR, 4 * H, 4 * H, dyt, TR, st);
+    SUBGC_LAUNCH_CHECK();
+    SUBGC_TRY(dW(dyt, 4 * H, b->ctx, H, H, TR, g->lang_w_ih, 2 * H));
+    SUBGC_TRY(dW(dyt, 4 * H, b->h_att + RH, H, H, TR, g->lang_w_ih + H, 2 * H));
+    SUBGC_TRY(dW(dyt, 4 * H, b->h_lang, H, H, TR, g->lang_w_hh, H));
+    SUBGC_TRY(subgc_colsum(TR, 4 * H, dg2, 4 * H, g->lang_b_ih, 1, stream));
+    SUBGC_TRY(subgc_colsum(TR, 4 * H, dg2, 4 * H, g->lang_b_hh, 1, stream));
+    // attention LSTM
+    tr(dg1, TR, 4 * H, 4 * H, dyt, TR, st);
+    SUBGC_LAUNCH_CHECK();
+    SUBGC_TRY(dW(dyt, 4 * H, b->h_lang, H, H, TR, g->att_w_ih, E + 2 * H));
+    SUBGC_TRY(dW(dyt, 4 * H, b->xt, E, E, TR, g->att_w_ih + 2 * H, E + 2 * H));
+    SUBGC_TRY(dW(dyt, 4 * H, b->h_att, H, H, TR, g->att_w_hh, H));
+    SUBGC_TRY(subgc_colsum(TR, 4 * H, dg1, 4 * H, g->att_b_ih, 1, stream));
+    SUBGC_TRY(subgc_colsum(TR, 4 * H, dg1, 4 * H, g->att_b_hh, 1, stream));
+    // fc is the same at every step: contract the step sum of the gate gradients (K = R)
+    sum_steps_kernel<<<ew_blocks((size_t)R * 4 * H), 256, 0, st>>>(T, (size_t)R * 4 * H, dg1, dg1_sum);
+    tr(dg1_sum, R, 4 * H, 4 * H, dyt, R, st);
+    SUBGC_LAUNCH_CHECK();
+    SUBGC_TRY(dW(dyt, 4 * H, b->fc, H, H, R, g->att_w_ih + H, E + 2 * H));
+    // h2att, alpha_net
+    tr(d_atth, TR, AH, AH, dyt, TR, st);
+    SUBGC_LAUNCH_CHECK();
+    SUBGC_TRY(dW(dyt, AH, b->h_att + RH, H, H, TR, g->h2att_w, H));
+    SUBGC_TRY(subgc_colsum(TR, AH, d_atth, AH, g->h2att_b, 1, stream));
+    SUBGC_TRY(subgc_colsum(TR, AH, d_wrows, AH, g->alpha_w, 1, stream));
     return SUBGC_OK;
 }

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsubgc_b200.so")
 MAX_GCN_LAYERS = 8
-ABI_VERSION = 3   # include/subgc_b200.h: SUBGC_ABI_VERSION (struct layouts below mirror that header)
+ABI_VERSION = 4   # include/subgc_b200.h: SUBGC_ABI_VERSION (struct layouts below mirror that header)
 
 c_fp = C.c_void_p  # device pointers travel as plain integers
 
@@ -47,6 +47,16 @@ class Weights(C.Structure):
         ("packs", C.POINTER(Packed)), ("n_packs", C.c_int32), ("h3_overflow", c_fp), ("lang_early_w", c_fp),
         ("mega", c_fp), ("mega_bytes", C.c_uint64), ("mega_ctas", C.c_int32),
     ]
+
+
+class DecoderTrainBufs(C.Structure):   # subgc_decoder_train_bufs
+    _fields_ = [(n, c_fp) for n in ("tokens", "fc", "att", "p_att", "masks", "m_x", "m_h", "xt", "act1", "c_att", "h_att", "atth", "ctx", "alpha",
+                                    "sm", "act2", "c_lang", "h_lang", "hd", "outputs")]
+
+
+class DecoderGrads(C.Structure):       # subgc_decoder_grads
+    _fields_ = [(n, c_fp) for n in ("logit_w", "logit_b", "embed", "att_w_ih", "att_w_hh", "att_b_ih", "att_b_hh", "lang_w_ih", "lang_w_hh",
+                                    "lang_b_ih", "lang_b_hh", "h2att_w", "h2att_b", "alpha_w")]
 
 
 class Layout(C.Structure):
@@ -111,6 +121,10 @@ SIGNATURES = {
     "subgc_unary": (_i, [_i, _sz, c_fp, c_fp, c_fp]),
     "subgc_scatter_add_rows": (_i, [_i, _i, c_fp, _i, c_fp, c_fp, _i, c_fp]),
     "subgc_lstm_cell_train_fwd": (_i, [_i, _i, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "subgc_decoder_train_workspace_bytes": (_sz, [_P(Dims), _i, _i, _i]),
+    "subgc_decoder_train_forward": (_i, [_P(Dims), _P(Weights), _i, _i, _i, _i, _P(DecoderTrainBufs), c_fp, _sz, c_fp]),
+    "subgc_decoder_train_backward": (_i, [_P(Dims), _P(Weights), _i, _i, _i, _i, _P(DecoderTrainBufs), c_fp, _P(DecoderGrads), c_fp, c_fp, c_fp,
+                                          c_fp, _sz, c_fp]),
     "subgc_lstm_cell_bwd": (_i, [_i, _i, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
     "subgc_attention_train_fwd": (_i, [_i, _i, _i, _i, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
     "subgc_attention_bwd": (_i, [_i, _i, _i, _i, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),

@@ -25,6 +25,15 @@ from ._lib import check, lib, ptr
 EW_MUL, EW_ADD, EW_RELU_BWD, EW_SCALE, EW_COPY = 0, 1, 2, 3, 4
 
 
+DECODER_GRAD_FIELDS = {   # subgc_decoder_grads field -> state_dict name
+    "logit_w": "logit.weight", "logit_b": "logit.bias", "embed": "embed.0.weight",
+    "att_w_ih": "core.att_lstm.weight_ih", "att_w_hh": "core.att_lstm.weight_hh", "att_b_ih": "core.att_lstm.bias_ih", "att_b_hh": "core.att_lstm.bias_hh",
+    "lang_w_ih": "core.lang_lstm.weight_ih", "lang_w_hh": "core.lang_lstm.weight_hh", "lang_b_ih": "core.lang_lstm.bias_ih",
+    "lang_b_hh": "core.lang_lstm.bias_hh", "h2att_w": "core.attention.h2att.weight", "h2att_b": "core.attention.h2att.bias",
+    "alpha_w": "core.attention.alpha_net.weight",
+}
+
+
 class CudaOps:
     """Building blocks on CUDA tensors (fp32, contiguous).  One method == one C-ABI call."""
 
@@ -151,6 +160,39 @@ class CudaOps:
                                         ptr(dctx.contiguous()), ptr(d_att), ptr(d_p_att), ptr(d_atth), ptr(d_w), self._st()),
               "subgc_attention_bwd")
         return d_atth, d_w
+
+    # -- stage-level decoder (one C call per direction, include/subgc_b200.h: subgc_decoder_train_forward / _backward) ------------
+    def decoder_forward(self, weights, tokens, fc, att3, p_att3, masks_c, m_x, m_h, outputs):
+        """tokens [T, R] int64.  Returns the saved-activation record the backward needs."""
+        L = lib()
+        T, R = tokens.shape
+        _, ln, H = att3.shape
+        AH, E = p_att3.shape[2], self.cd.enc
+        dev = att3.device
+        f = lambda *shape: torch.empty(*shape, device=dev)
+        rec = dict(tokens=tokens, fc=fc, att=att3, p_att=p_att3, masks=masks_c, m_x=m_x, m_h=m_h, xt=f(T, R, E), act1=f(T, R, 4 * H),
+                   c_att=f(T + 1, R, H), h_att=f(T + 1, R, H), atth=f(T, R, AH), ctx=f(T, R, H), alpha=f(T, R, ln), sm=f(T, R, ln),
+                   act2=f(T, R, 4 * H), c_lang=f(T + 1, R, H), h_lang=f(T + 1, R, H), hd=f(T, R, H) if m_h is not None else None, outputs=outputs)
+        bufs = _lib.DecoderTrainBufs(**{k: ptr(v) for k, v in rec.items()})
+        ws = self._wsbuf(L.subgc_decoder_train_workspace_bytes(C.byref(self.cd), R, ln, T), dev)
+        check(L.subgc_decoder_train_forward(C.byref(self.cd), C.byref(weights), R, ln, T, outputs.shape[1], C.byref(bufs), ptr(ws), ws.numel(),
+                                            self._st()), "subgc_decoder_train_forward")
+        rec.update(bufs=bufs, T=T, R=R, len=ln, weights=weights, outputs=None)   # the caller keeps a detached alias of outputs alive
+        return rec
+
+    def decoder_backward(self, rec, d_outputs, grads):
+        """grads: name -> zero-filled gradient tensor of the 14 decoder parameters.  Returns (d_fc, d_att, d_p_att)."""
+        L = lib()
+        T, R, ln = rec["T"], rec["R"], rec["len"]
+        dev = d_outputs.device
+        H, AH = rec["att"].shape[2], rec["p_att"].shape[2]
+        d_fc, d_att, d_patt = torch.empty(R, H, device=dev), torch.empty(R, ln, H, device=dev), torch.empty(R, ln, AH, device=dev)
+        g = _lib.DecoderGrads(**{k: ptr(grads[n]) for k, n in DECODER_GRAD_FIELDS.items()})
+        ws = self._wsbuf(L.subgc_decoder_train_workspace_bytes(C.byref(self.cd), R, ln, T), dev)
+        check(L.subgc_decoder_train_backward(C.byref(self.cd), C.byref(rec["weights"]), R, ln, T, d_outputs.shape[1], C.byref(rec["bufs"]),
+                                             ptr(d_outputs), C.byref(g), ptr(d_fc), ptr(d_att), ptr(d_patt), ptr(ws), ws.numel(), self._st()),
+              "subgc_decoder_train_backward")
+        return d_fc, d_att, d_patt
 
     def log_softmax_fwd(self, logits, out_view):
         """out_view: [rows, V1] view with unit inner stride (e.g. outputs[:, t])."""
@@ -375,6 +417,15 @@ def forward(ops, P, weights, d, data, drop=None, seq_per_img=5, ss=None):
             n_exec = i
             break
     outputs = torch.zeros(rows, T, V1, device=dev)
+    use_ss = ss is not None and ss["prob"] > 0.0
+    if hasattr(ops, "decoder_forward") and not use_ss:
+        # stage-level C entry: the whole teacher-forced loop, the batched logit contraction and the log-softmax are one call
+        tokens = labels[:, :n_exec].t().contiguous()
+        m_x = dmask((n_exec, rows, d.enc), p_lm)
+        m_h = dmask((n_exec, rows, H), p_lm)
+        dec = ops.decoder_forward(weights, tokens, fc, att3, p_att3, masks_c, m_x, m_h, outputs)
+        S.update(dec=dec, outputs=outputs.detach(), n_exec=n_exec, B=B, N=N, K=K, rows=rows, rel_ind=rel_ind, obj_ind=obj_ind, att_feats=att_feats)
+        return outputs, gpn_loss, score.view(-1, 1), S
     zeros = torch.zeros(rows, H, device=dev)
     h_att, c_att, h_lang, c_lang = zeros, zeros, zeros, zeros
     E = P["embed.0.weight"]
@@ -405,7 +456,7 @@ def forward(ops, P, weights, d, data, drop=None, seq_per_img=5, ss=None):
                           atth=atth, alpha=alpha, sm=sm, x_lang=x_lang, h_lang_prev=h_lang, act2=g2, c_lang_prev=c_lang, c_lang=c_lang_n,
                           m_h=m_h, hd=hd))
         h_att, c_att, h_lang, c_lang = h_att_n, c_att_n, h_lang_n, c_lang_n
-    S.update(steps=steps, outputs=outputs, n_exec=n_exec, B=B, N=N, K=K, rows=rows, rel_ind=rel_ind, obj_ind=obj_ind, att_feats=att_feats)
+    S.update(steps=steps, outputs=outputs.detach(), n_exec=n_exec, B=B, N=N, K=K, rows=rows, rel_ind=rel_ind, obj_ind=obj_ind, att_feats=att_feats)
     return outputs, gpn_loss, score.view(-1, 1), S
 
 
@@ -458,15 +509,21 @@ def backward(ops, P, d, S, d_outputs, d_gpn_loss, reducer=None):
     H, X, AH, Lg = d.rnn, d.enc, d.att_hid, d.gcn
     rows, len_max = S["rows"], S["len_max"]
     att3, p_att3, masks_c = S["att"], S["p_att"], S["masks_c"]
-    d_att = torch.zeros_like(att3)
-    d_patt = torch.zeros_like(p_att3)
-    d_fc = torch.zeros(rows, H, device=dev)
+    if "dec" not in S:
+        d_att = torch.zeros_like(att3)
+        d_patt = torch.zeros_like(p_att3)
+        d_fc = torch.zeros(rows, H, device=dev)
     dh_att_n = dc_att_n = dh_lang_n = dc_lang_n = None
     aw = P["core.attention.alpha_net.weight"]
     G["core.attention.alpha_net.bias"] = new_grad("core.attention.alpha_net.bias")  # softmax is shift-invariant: exactly zero
     G["embed.0.weight"] = new_grad("embed.0.weight")
 
-    for t in range(S["n_exec"] - 1, -1, -1):
+    if "dec" in S:
+        for n in DECODER_GRAD_FIELDS.values():
+            if n not in G:
+                G[n] = new_grad(n)
+        d_fc, d_att, d_patt = ops.decoder_backward(S["dec"], d_outputs, G)
+    for t in (range(S["n_exec"] - 1, -1, -1) if "dec" not in S else ()):
         st = S["steps"][t]
         dlogits = ops.log_softmax_bwd(S["outputs"][:, t], d_outputs[:, t])
         acc_w("logit.weight", dlogits, st["hd"])

@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol(libpath):
     for name in header_symbols():
         assert hasattr(handle, name), name
     handle.subgc_version.restype = ctypes.c_int
-    assert handle.subgc_version() == _lib.ABI_VERSION == 3
+    assert handle.subgc_version() == _lib.ABI_VERSION == 4
 
 
 def test_struct_layouts_match_the_header():
@@ -47,6 +47,7 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(_lib.Weights) == 16 * n_linear + 8 * (3 + 8) + 32 + 24
     assert ctypes.sizeof(_lib.Packed) == 3 * 8 + 8 * 4
     assert ctypes.sizeof(_lib.Layout) == 16
+    assert ctypes.sizeof(_lib.DecoderTrainBufs) == 20 * 8 and ctypes.sizeof(_lib.DecoderGrads) == 14 * 8
 
 
 @pytest.mark.parametrize("d", [SMALL, Dims()])
