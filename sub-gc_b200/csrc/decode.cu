@@ -1411,6 +1411,13 @@ static int decode_sample_impl(const subgc_dims* d, const subgc_weights* w, int n
     const bool s16 = use_step16(w);
     if (s16) ok = take_step16(d, S, ws, b16) && ok;
     if (!ok || !ws.ok()) { set_error("subgc_decode_sample: workspace too small"); return SUBGC_E_WORKSPACE; }
+    SUBGC_CUDA(cudaMemsetAsync(seq, 0, (size_t)S * T * 8, st));
+    SUBGC_CUDA(cudaMemsetAsync(seq_logprobs, 0, (size_t)S * T * 4, st));
+    if (mega_decode_eligible(d, w, S, len_max, att_weights)) {   // the whole loop as one persistent kernel (mega_decode.cu)
+        SUBGC_TRY(launch_fc_pre(d, w, S, fc, sc, st));
+        return launch_mega_decode(d, w, S, len_max, mode, temp, top_k, seed, offset, uniforms, sc.gates, att, p_att, masks, seq, seq_logprobs,
+                                  steps_done, ws, st, counts);
+    }
     if (s16) {
         SUBGC_CUDA(cudaMemsetAsync(b16.h[0][0], 0, 2 * (size_t)S * b16.Hp * 2, st));   // fp16 zeros: split copy of the zero state
         SUBGC_CUDA(cudaMemsetAsync(b16.h[0][1], 0, 2 * (size_t)S * b16.Hp * 2, st));
@@ -1419,17 +1426,12 @@ static int decode_sample_impl(const subgc_dims* d, const subgc_weights* w, int n
     SUBGC_CUDA(cudaMemsetAsync(cbuf[0], 0, 2 * (size_t)S * H * 4, st));
     SUBGC_CUDA(cudaMemsetAsync(it, 0, (size_t)S * 8, st));                // <bos>
     SUBGC_CUDA(cudaMemsetAsync(count, 0, (size_t)(T + 2) * 4, st));
-    SUBGC_CUDA(cudaMemsetAsync(seq, 0, (size_t)S * T * 8, st));
-    SUBGC_CUDA(cudaMemsetAsync(seq_logprobs, 0, (size_t)S * T * 4, st));
     if (att_weights) SUBGC_CUDA(cudaMemsetAsync(att_weights, 0, (size_t)S * (T + 1) * len_max * 4, st));
     if ((size_t)V1 * sizeof(float) > 48 * 1024) {
         SUBGC_CHECK_ARG((size_t)V1 * sizeof(float) <= 200 * 1024, "subgc_decode_sample: vocabulary too large for the selection kernel");
         SUBGC_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(V1 * sizeof(float))));
     }
     SUBGC_TRY(launch_fc_pre(d, w, S, fc, sc, st));
-    if (mega_decode_eligible(d, w, S, len_max, att_weights))   // the whole loop as one persistent kernel (mega_decode.cu)
-        return launch_mega_decode(d, w, S, len_max, mode, temp, top_k, seed, offset, uniforms, sc.gates, att, p_att, masks, seq, seq_logprobs,
-                                  steps_done, ws, st, counts);
     if (counts) {
         set_error("subgc_decode_sample_dyn: device-side row counts need the persistent decode kernel (w->mega, <= 128 rows, no attention weights)");
         return SUBGC_E_UNSUPPORTED;

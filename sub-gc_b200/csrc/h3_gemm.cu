@@ -34,7 +34,7 @@ constexpr int H3_X_BYTES = H3_BM * H3_BK * 2;                    // 16 KB
 constexpr int H3_SMEM_EXTRA = 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int H3_SMEM_BUDGET = 196 * 1024;   // pipeline bytes: leaves ~30 KB of the SM's shared memory for a co-resident consumer kernel (PDL)
 constexpr int H3_MAX_SEG = 4;
-constexpr int H3_MAX_CHAIN = 32;   // k-blocks (128 MMA accumulation steps) per TMEM chain before the fp32 combine of split-K
+constexpr int H3_MAX_CHAIN = 40;   // k-blocks (128 MMA accumulation steps) per TMEM chain before the fp32 combine of split-K
 constexpr float H3_LO_INV = kH3LoInv;
 
 struct H3Params {
@@ -296,15 +296,20 @@ __global__ void __launch_bounds__(H3_THREADS, 1) h3_gemm_kernel(const __grid_con
         uint32_t ra[32], rb[32];
         // staging tiles of the TMA-store path live in the pipeline stages (idle by now: every MMA has retired): 2 x 4 KB per warp
         const uint32_t sbuf = base + (uint32_t)q * 8192u;
-        const bool tma_out = !p.direct && p.tma_part && (m0 + q * 32 < p.M);
+        const bool tma_out = p.tma_part && (m0 + q * 32 < p.M);   // partial planes, or C itself (direct: epilogue applied on the way)
 #pragma unroll 1
         for (int c = 0; c < nchunks; ++c) {
             const int col0 = n0 + c * 32;
             SUBGC_TMEM_LD32(ra, tlane + (uint32_t)(c * 32));
             SUBGC_TMEM_LD32(rb, tlane + cross + (uint32_t)(c * 32));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (!p.direct && p.tma_part) {
+            if (p.tma_part) {
                 if (tma_out) {
+                    bool keep = true;   // direct: rows beyond their group's length are written as exact zeros (pack_padded_sequence)
+                    if (p.direct && p.epi.group && row < p.M) {
+                        const int g = row / p.epi.group, jg = row - g * p.epi.group;
+                        keep = jg < p.epi.group_len[p.epi.group_sel ? p.epi.group_sel[g] : g];
+                    }
                     const uint32_t buf = sbuf + (uint32_t)(c & 1) * 4096u;
                     if (c >= 2) {  // the store that read this buffer two chunks ago must have drained it
                         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -313,10 +318,32 @@ __global__ void __launch_bounds__(H3_THREADS, 1) h3_gemm_kernel(const __grid_con
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {  // 16-byte chunk j of row `lane` sits at chunk j ^ (lane & 7): conflict-free, and what SWIZZLE_128B expects
                         const uint32_t addr = buf + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
-                        const float v0 = fmaf(__uint_as_float(rb[4 * j]), H3_LO_INV, __uint_as_float(ra[4 * j]));
-                        const float v1 = fmaf(__uint_as_float(rb[4 * j + 1]), H3_LO_INV, __uint_as_float(ra[4 * j + 1]));
-                        const float v2 = fmaf(__uint_as_float(rb[4 * j + 2]), H3_LO_INV, __uint_as_float(ra[4 * j + 2]));
-                        const float v3 = fmaf(__uint_as_float(rb[4 * j + 3]), H3_LO_INV, __uint_as_float(ra[4 * j + 3]));
+                        float v0 = fmaf(__uint_as_float(rb[4 * j]), H3_LO_INV, __uint_as_float(ra[4 * j]));
+                        float v1 = fmaf(__uint_as_float(rb[4 * j + 1]), H3_LO_INV, __uint_as_float(ra[4 * j + 1]));
+                        float v2 = fmaf(__uint_as_float(rb[4 * j + 2]), H3_LO_INV, __uint_as_float(ra[4 * j + 2]));
+                        float v3 = fmaf(__uint_as_float(rb[4 * j + 3]), H3_LO_INV, __uint_as_float(ra[4 * j + 3]));
+                        if (p.direct) {   // bias / ReLU / zero rows here; the tile leaves as full 128-byte lines instead of 16 bytes per row and store
+                            const int cn = col0 + 4 * j, cl = p.N - 1;
+                            if (p.epi.bias) {
+                                v0 += __ldg(p.epi.bias + min(cn, cl)); v1 += __ldg(p.epi.bias + min(cn + 1, cl));
+                                v2 += __ldg(p.epi.bias + min(cn + 2, cl)); v3 += __ldg(p.epi.bias + min(cn + 3, cl));
+                            }
+                            if (p.epi.bias2) {
+                                v0 += __ldg(p.epi.bias2 + min(cn, cl)); v1 += __ldg(p.epi.bias2 + min(cn + 1, cl));
+                                v2 += __ldg(p.epi.bias2 + min(cn + 2, cl)); v3 += __ldg(p.epi.bias2 + min(cn + 3, cl));
+                            }
+                            if (p.epi.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+                            if (!keep) { v0 = 0.f; v1 = 0.f; v2 = 0.f; v3 = 0.f; }
+                            if (p.epi.c16_hi && row < p.M && cn + 4 <= p.N) {   // split-fp16 copy for the consumer contraction (8 bytes of hi and of lo)
+                                unsigned short hh[4], hl[4];
+                                int ovf = 0;
+                                split_f16(v0, hh[0], hl[0], ovf); split_f16(v1, hh[1], hl[1], ovf); split_f16(v2, hh[2], hl[2], ovf); split_f16(v3, hh[3], hl[3], ovf);
+                                const size_t o16 = (size_t)row * p.epi.ld16 + cn;
+                                *reinterpret_cast<uint2*>(p.epi.c16_hi + o16) = make_uint2((uint32_t)hh[0] | ((uint32_t)hh[1] << 16), (uint32_t)hh[2] | ((uint32_t)hh[3] << 16));
+                                *reinterpret_cast<uint2*>(p.epi.c16_lo + o16) = make_uint2((uint32_t)hl[0] | ((uint32_t)hl[1] << 16), (uint32_t)hl[2] | ((uint32_t)hl[3] << 16));
+                                if (ovf && p.overflow) atomicOr(p.overflow, 1);
+                            }
+                        }
                         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -324,7 +351,7 @@ __global__ void __launch_bounds__(H3_THREADS, 1) h3_gemm_kernel(const __grid_con
                     if (lane == 0) {
                         asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
                                          reinterpret_cast<uint64_t>(&p.tm_part)),
-                                     "r"(buf), "r"(col0), "r"(m0 + q * 32), "r"((int)blockIdx.z)
+                                     "r"(buf), "r"(col0), "r"(m0 + q * 32), "r"(p.direct ? 0 : (int)blockIdx.z)
                                      : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
@@ -586,11 +613,13 @@ static bool make_map16(CUtensorMap* out, const unsigned short* base, int rows, i
 }
 
 // 3-D fp32 map of the split-K partials [splits, M, N]: box 32 columns x 32 rows x 1 split, 128-byte swizzle
-static bool make_map_part(CUtensorMap* out, float* part, int splits, int M, int N) {
+// ld: floats between consecutive rows (N for the partial planes, ldc for the in-place epilogue writing C itself)
+static bool make_map_part(CUtensorMap* out, float* part, int splits, int M, int N, long long ld = 0) {
     EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(tc_encode_fn());
     if (!fn) return false;
+    if (ld <= 0) ld = N;
     cuuint64_t gdim[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)splits};
-    cuuint64_t gstride[2] = {(cuuint64_t)N * 4, (cuuint64_t)M * N * 4};
+    cuuint64_t gstride[2] = {(cuuint64_t)ld * 4, (cuuint64_t)M * (cuuint64_t)ld * 4};
     cuuint32_t box[3] = {32, 32, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, part, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -789,7 +818,10 @@ int launch_gemm_h3(const GemmProblem& p, void* ws_, size_t ws_bytes, cudaStream_
     for (int s = 0; s < p.nseg; ++s) segK[s] = p.seg[s].K;
     const H3Plan pl = h3_plan(p.M, p.N, segK, p.nseg);
     Workspace ws(ws_, ws_bytes);
-    const bool direct = (pl.splits == 1 && raw == nullptr && p.epi.div == 0.f && p.epi.addend == nullptr && p.epi.group == 0);
+    // in-place epilogue of single-split problems; zero-padded row groups need the TMA-store variant (decided below)
+    const bool c_tma_ok = (p.N & 3) == 0 && (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && !p.epi.accumulate &&
+                          getenv("SUBGC_H3_NO_TMA_STORE") == nullptr && getenv("SUBGC_H3_NO_TMA_C") == nullptr;
+    const bool direct = (pl.splits == 1 && raw == nullptr && p.epi.div == 0.f && p.epi.addend == nullptr && (p.epi.group == 0 || c_tma_ok));
     float* part = direct ? nullptr : ws.take<float>((size_t)pl.splits * p.M * p.N);
     if (!ws.ok()) {
         set_error("gemm(h3): workspace too small (%zu bytes given)", ws_bytes);
@@ -801,13 +833,16 @@ int launch_gemm_h3(const GemmProblem& p, void* ws_, size_t ws_bytes, cudaStream_
     hp.direct = direct ? 1 : 0; hp.epi = p.epi; hp.C = p.C; hp.ldc = p.ldc; hp.overflow = p.overflow;
     // the in-kernel split copy needs whole 8-column groups and 16-byte aligned rows; anything else is split by the caller afterwards
     const bool c16_here = direct && p.epi.c16_hi && p.epi.c16_lo && (p.N & 7) == 0 && (p.epi.ld16 & 7) == 0 && ((p.ldc & 3) == 0) &&
-                          (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && !p.epi.accumulate;
+                          (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && !p.epi.accumulate &&
+                          (reinterpret_cast<uintptr_t>(p.epi.c16_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.epi.c16_lo) & 15) == 0;
     if (!c16_here) { hp.epi.c16_hi = nullptr; hp.epi.c16_lo = nullptr; }
     if (wrote_c16) *wrote_c16 = c16_here;
     static const bool tma_store = getenv("SUBGC_H3_NO_TMA_STORE") == nullptr;
     hp.tma_part = 0;
     hp.tm_part = hp.tm_wh[0];
     if (!direct && tma_store && (p.N & 3) == 0 && make_map_part(&hp.tm_part, part, pl.splits, p.M, p.N)) hp.tma_part = 1;
+    if (direct && c_tma_ok && make_map_part(&hp.tm_part, p.C, 1, p.M, p.N, p.ldc)) hp.tma_part = 1;   // C leaves through shared memory + TMA stores
+    if (direct && p.epi.group && !hp.tma_part) { set_error("gemm(h3): tensor map of C could not be encoded"); return SUBGC_E_CUDA; }
     SUBGC_TRY(h3_set_smem_attr());
     hp.trace = next_trace_slot(1);
     static const int dbg = getenv("SUBGC_H3_DBG") ? atoi(getenv("SUBGC_H3_DBG")) : 0;
