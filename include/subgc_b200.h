@@ -125,6 +125,14 @@ typedef struct subgc_weights {
                                                           (<= 128 rows, no attention-weight output); otherwise one launch per stage.   */
     uint64_t mega_bytes;
     int32_t mega_ctas;                                 /* CTAs the schedule was built for (= SMs of the device, one CTA each)           */
+    /* Optional derived tensors (inference): a _Collection_Unit applies fc_rgt(fc_lft(.)) with nothing in between
+     * (models/lib/graph_conv_unit.py:29-31), so the two units of a direction fold into ONE weight
+     *   gcn_fold[l][dir].w = 2^s [W_rgt(u) W_lft(u) ; W_rgt(u') W_lft(u')]  [2L, L],  .b = 2^s [W_rgt b_lft + b_rgt ; ...]  [2L]
+     * with (u, u') = (0, 1) for dir 0 (node <- edges) and (2, 3) for dir 1 (edge <- nodes); gcn_fold_scale = 2^s (> 0 when set; a
+     * power of two that keeps the folded products of small weights inside the normal fp16 range of the split-fp16 copy, undone
+     * exactly when the messages are consumed).  The same FLOPs as the low-rank pair, one contraction instead of four per direction. */
+    subgc_linear gcn_fold[SUBGC_MAX_GCN_LAYERS][2];
+    float gcn_fold_scale[SUBGC_MAX_GCN_LAYERS][2];
 } subgc_weights;
 
 /* How sub-graph s of a flat list maps onto the loader tensors gpn_obj_ind / att_masks [rows,2,per_half,N].

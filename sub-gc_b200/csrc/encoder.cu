@@ -37,18 +37,22 @@ __global__ void __launch_bounds__(256) gcn_edge_update_kernel(const float* __res
                                                               const long long* __restrict__ rel_ind, const float* __restrict__ res,
                                                               float* __restrict__ out, int B, int N, int K, int L,
                                                               unsigned short* __restrict__ o16_hi = nullptr, unsigned short* __restrict__ o16_lo = nullptr,
-                                                              int ld16 = 0, int* __restrict__ overflow = nullptr) {
+                                                              int ld16 = 0, int* __restrict__ overflow = nullptr, int ldm = 0, float mscale = 1.f) {
     // o16_hi / o16_lo (nullable, [B*K, ld16]): split-fp16 copy of the new edge features for the contractions of the next layer
+    // ldm: row stride of m_subj / m_obj (0 = L; 2L when both units of the direction came out of one folded contraction)
     const int bk = blockIdx.x;  // b*K + k
     const int b = bk / K;
     const long long s = rel_ind[(size_t)bk * 2], o = rel_ind[(size_t)bk * 2 + 1];
     const float d = 1.f + 1e-7f;
-    const float* ms = m_subj + ((size_t)b * N + s) * L;
-    const float* mo = m_obj + ((size_t)b * N + o) * L;
+    if (ldm == 0) ldm = L;
+    // mscale: messages of a folded contraction arrive multiplied by a power of two (exact), undone here
+    const float* ms = m_subj + ((size_t)b * N + s) * ldm;
+    const float* mo = m_obj + ((size_t)b * N + o) * ldm;
     if ((L & 3) == 0) {
         const int L4 = L >> 2;
         for (int c4 = threadIdx.x; c4 < L4; c4 += blockDim.x) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(ms) + c4), bb = __ldg(reinterpret_cast<const float4*>(mo) + c4);
+            float4 a = __ldg(reinterpret_cast<const float4*>(ms) + c4), bb = __ldg(reinterpret_cast<const float4*>(mo) + c4);
+            a.x *= mscale; a.y *= mscale; a.z *= mscale; a.w *= mscale; bb.x *= mscale; bb.y *= mscale; bb.z *= mscale; bb.w *= mscale;
             float4 v;
             v.x = 0.5f * (fmaxf(a.x / d, 0.f) + fmaxf(bb.x / d, 0.f));
             v.y = 0.5f * (fmaxf(a.y / d, 0.f) + fmaxf(bb.y / d, 0.f));
@@ -72,7 +76,7 @@ __global__ void __launch_bounds__(256) gcn_edge_update_kernel(const float* __res
         return;
     }
     for (int c = threadIdx.x; c < L; c += blockDim.x) {
-        float v = 0.5f * (fmaxf(__ldg(ms + c) / d, 0.f) + fmaxf(__ldg(mo + c) / d, 0.f));
+        float v = 0.5f * (fmaxf(__ldg(ms + c) * mscale / d, 0.f) + fmaxf(__ldg(mo + c) * mscale / d, 0.f));
         if (res) v += __ldg(res + (size_t)bk * L + c);
         out[(size_t)bk * L + c] = v;
         if (o16_hi) split_f16_store(v, o16_hi, o16_lo, (size_t)bk * ld16 + c, overflow);
@@ -82,8 +86,9 @@ __global__ void __launch_bounds__(256) gcn_edge_update_kernel(const float* __res
 // x_new[b,n,:] = 0.5 * ( relu(sum_{k: s_k = n} M0[b,k,:] / (cnt_s + 1e-7)) + relu(sum_{k: o_k = n} M1[b,k,:] / (cnt_o + 1e-7)) )
 __global__ void __launch_bounds__(256) gcn_node_update_kernel(const float* __restrict__ m_subj, const float* __restrict__ m_obj,
                                                               const long long* __restrict__ rel_ind, const float* __restrict__ res,
-                                                              float* __restrict__ out, int B, int N, int K, int L) {
+                                                              float* __restrict__ out, int B, int N, int K, int L, int ldm = 0, float mscale = 1.f) {
     extern __shared__ int s_list[];  // [2][K] edge lists of this node | [2][K] (subject, object) of the image's edges
+    if (ldm == 0) ldm = L;           // row stride of m_subj / m_obj
     __shared__ int s_cnt[2];
     int* s_raw = s_list + 2 * K;
     const int bn = blockIdx.x;
@@ -103,8 +108,8 @@ __global__ void __launch_bounds__(256) gcn_node_update_kernel(const float* __res
     __syncthreads();
     const int cs = s_cnt[0], co = s_cnt[1];
     const float ds = (float)cs + 1e-7f, dob = (float)co + 1e-7f;
-    const float* ms = m_subj + (size_t)b * K * L;
-    const float* mo = m_obj + (size_t)b * K * L;
+    const float* ms = m_subj + (size_t)b * K * ldm;
+    const float* mo = m_obj + (size_t)b * K * ldm;
     if ((L & 3) == 0) {
         const int L4 = L >> 2;
         for (int c4 = threadIdx.x; c4 < L4; c4 += blockDim.x) {
@@ -113,7 +118,7 @@ __global__ void __launch_bounds__(256) gcn_node_update_kernel(const float* __res
                 float4 v[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
-                    v[u] = (i + u < cs) ? __ldg(reinterpret_cast<const float4*>(ms + (size_t)s_list[i + u] * L) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[u] = (i + u < cs) ? __ldg(reinterpret_cast<const float4*>(ms + (size_t)s_list[i + u] * ldm) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
                     if (i + u < cs) { a0.x += v[u].x; a0.y += v[u].y; a0.z += v[u].z; a0.w += v[u].w; }
@@ -122,12 +127,13 @@ __global__ void __launch_bounds__(256) gcn_node_update_kernel(const float* __res
                 float4 v[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
-                    v[u] = (i + u < co) ? __ldg(reinterpret_cast<const float4*>(mo + (size_t)s_list[K + i + u] * L) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[u] = (i + u < co) ? __ldg(reinterpret_cast<const float4*>(mo + (size_t)s_list[K + i + u] * ldm) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
                     if (i + u < co) { a1.x += v[u].x; a1.y += v[u].y; a1.z += v[u].z; a1.w += v[u].w; }
             }
             float4 v;
+            a0.x *= mscale; a0.y *= mscale; a0.z *= mscale; a0.w *= mscale; a1.x *= mscale; a1.y *= mscale; a1.z *= mscale; a1.w *= mscale;
             v.x = (fmaxf(a0.x / ds, 0.f) + fmaxf(a1.x / dob, 0.f)) * 0.5f;
             v.y = (fmaxf(a0.y / ds, 0.f) + fmaxf(a1.y / dob, 0.f)) * 0.5f;
             v.z = (fmaxf(a0.z / ds, 0.f) + fmaxf(a1.z / dob, 0.f)) * 0.5f;
@@ -142,9 +148,9 @@ __global__ void __launch_bounds__(256) gcn_node_update_kernel(const float* __res
     }
     for (int c = threadIdx.x; c < L; c += blockDim.x) {
         float a0 = 0.f, a1 = 0.f;
-        for (int i = 0; i < cs; ++i) a0 += __ldg(ms + (size_t)s_list[i] * L + c);
-        for (int i = 0; i < co; ++i) a1 += __ldg(mo + (size_t)s_list[K + i] * L + c);
-        float v = (fmaxf(a0 / ds, 0.f) + fmaxf(a1 / dob, 0.f)) * 0.5f;
+        for (int i = 0; i < cs; ++i) a0 += __ldg(ms + (size_t)s_list[i] * ldm + c);
+        for (int i = 0; i < co; ++i) a1 += __ldg(mo + (size_t)s_list[K + i] * ldm + c);
+        float v = (fmaxf(a0 * mscale / ds, 0.f) + fmaxf(a1 * mscale / dob, 0.f)) * 0.5f;
         if (res) v += __ldg(res + (size_t)bn * L + c);
         out[(size_t)bn * L + c] = v;
     }
@@ -184,6 +190,8 @@ static size_t gcn_ws_bytes(const subgc_dims* d, int B) {
     b += 2 * align_up(rows * d->gcn * 4, 256);           // two message buffers
     b += (size_t)d->gcn_layers * (align_up((size_t)B * d->obj_num * d->gcn * 4, 256) + align_up((size_t)B * d->rel_num * d->gcn * 4, 256));
     size_t g1 = gemm_workspace_bytes((int)rows, d->low_rank, d->gcn), g2 = gemm_workspace_bytes((int)rows, d->gcn, d->low_rank);
+    const size_t g3 = gemm_workspace_bytes((int)rows, 2 * d->gcn, d->gcn);   // folded direction: both units in one contraction
+    if (g3 > g1) g1 = g3;
     b += align_up(g1 > g2 ? g1 : g2, 256) + 1024;
     b += 2 * align_up(rows * (size_t)((d->gcn + 7) & ~7) * 2, 256) + 1024;   // split-fp16 copy of a layer input shared by two units
     b += 2 * align_up(rows * (size_t)((d->low_rank + 7) & ~7) * 2, 256) + 1024;   // split-fp16 copy of T written by the fc_lft contraction
@@ -312,8 +320,9 @@ extern "C" int subgc_gcn_forward(const subgc_dims* d, const subgc_weights* w, in
     Workspace ws(ws_, ws_bytes);
     const size_t rows_max = (size_t)B * (N > K ? N : K);
     float* T = ws.take<float>(rows_max * R);
-    float* Ma = ws.take<float>(rows_max * L);
-    float* Mb = ws.take<float>(rows_max * L);
+    float* M2 = ws.take<float>(2 * rows_max * L);   // [rows, L] x 2 (one per unit), or [rows, 2L] when a direction is one folded contraction
+    float* Ma = M2;
+    float* Mb = M2 ? M2 + rows_max * L : nullptr;
     // both units of a direction contract the same layer input: split it once (split-fp16 path), in a region reserved up front
     const size_t split_bytes = 2 * align_up(rows_max * (size_t)((L + 7) & ~7) * 2, 256) + 1024;
     char* split_region = ws.take<char>(split_bytes);
@@ -343,13 +352,22 @@ extern "C" int subgc_gcn_forward(const subgc_dims* d, const subgc_weights* w, in
             const unsigned short *xh = nullptr, *xl = nullptr;
             int xld = 0;
             if (split_region) { Workspace sw(split_region, split_bytes); if (!h3_presplit(x, B * N, L, L, w, sw, st, &xh, &xl, &xld)) xh = xl = nullptr; }
-            SUBGC_TRY(linear(w, x, B * N, L, w->gcn_lft[l][2], R, T, ws, st, xh, xl, xld, t16_hi, t16_lo, R));
-            SUBGC_TRY(linear(w, T, B * N, R, w->gcn_rgt[l][2], L, Ma, ws, st, t16_hi, t16_lo, R));
-            SUBGC_TRY(linear(w, x, B * N, L, w->gcn_lft[l][3], R, T, ws, st, xh, xl, xld, t16_hi, t16_lo, R));
-            SUBGC_TRY(linear(w, T, B * N, R, w->gcn_rgt[l][3], L, Mb, ws, st, t16_hi, t16_lo, R));
+            // fc_rgt(fc_lft(.)) has no non-linearity in between (graph_conv_unit.py:29-31): when the host supplies the folded weights
+            // [W_rgt W_lft of unit 2 ; of unit 3] (x 2^s, undone exactly by the update kernel), the direction is ONE contraction
+            const subgc_linear& fold = w->gcn_fold[l][1];
+            const bool folded = fold.w != nullptr && w->gcn_fold_scale[l][1] > 0.f;
+            if (folded) {
+                SUBGC_TRY(linear(w, x, B * N, L, fold, 2 * L, M2, ws, st, xh, xl, xld));
+            } else {
+                SUBGC_TRY(linear(w, x, B * N, L, w->gcn_lft[l][2], R, T, ws, st, xh, xl, xld, t16_hi, t16_lo, R));
+                SUBGC_TRY(linear(w, T, B * N, R, w->gcn_rgt[l][2], L, Ma, ws, st, t16_hi, t16_lo, R));
+                SUBGC_TRY(linear(w, x, B * N, L, w->gcn_lft[l][3], R, T, ws, st, xh, xl, xld, t16_hi, t16_lo, R));
+                SUBGC_TRY(linear(w, T, B * N, R, w->gcn_rgt[l][3], L, Mb, ws, st, t16_hi, t16_lo, R));
+            }
             next16 = fuse16 && !last && need_x[l + 2];   // layer l+1 contracts this edge stream (its units 0, 1 produce x of layer l+2)
-            gcn_edge_update_kernel<<<B * K, 256, 0, st>>>(Ma, Mb, rel, boundary ? p_res : nullptr, p_next, B, N, K, L, next16 ? n16_hi[l & 1] : nullptr,
-                                                          next16 ? n16_lo[l & 1] : nullptr, L, w->h3_overflow);
+            gcn_edge_update_kernel<<<B * K, 256, 0, st>>>(folded ? M2 : Ma, folded ? M2 + L : Mb, rel, boundary ? p_res : nullptr, p_next, B, N, K, L,
+                                                          next16 ? n16_hi[l & 1] : nullptr, next16 ? n16_lo[l & 1] : nullptr, L, w->h3_overflow,
+                                                          folded ? 2 * L : L, folded ? 1.f / w->gcn_fold_scale[l][1] : 1.f);
             SUBGC_LAUNCH_CHECK();
         }
         if (x_next) {  // units 0,1: node <- edges (graph_conv.py:22-26)
@@ -361,11 +379,18 @@ extern "C" int subgc_gcn_forward(const subgc_dims* d, const subgc_weights* w, in
                 Workspace sw(split_region, split_bytes);
                 if (!h3_presplit(p, B * K, L, L, w, sw, st, &ph, &pl, &pld)) ph = pl = nullptr;
             }
-            SUBGC_TRY(linear(w, p, B * K, L, w->gcn_lft[l][0], R, T, ws, st, ph, pl, pld, t16_hi, t16_lo, R));
-            SUBGC_TRY(linear(w, T, B * K, R, w->gcn_rgt[l][0], L, Ma, ws, st, t16_hi, t16_lo, R));
-            SUBGC_TRY(linear(w, p, B * K, L, w->gcn_lft[l][1], R, T, ws, st, ph, pl, pld, t16_hi, t16_lo, R));
-            SUBGC_TRY(linear(w, T, B * K, R, w->gcn_rgt[l][1], L, Mb, ws, st, t16_hi, t16_lo, R));
-            gcn_node_update_kernel<<<B * N, 256, 4 * K * sizeof(int), st>>>(Ma, Mb, rel, boundary ? x_res : nullptr, x_next, B, N, K, L);
+            const subgc_linear& fold = w->gcn_fold[l][0];
+            const bool folded = fold.w != nullptr && w->gcn_fold_scale[l][0] > 0.f;
+            if (folded) {
+                SUBGC_TRY(linear(w, p, B * K, L, fold, 2 * L, M2, ws, st, ph, pl, pld));
+            } else {
+                SUBGC_TRY(linear(w, p, B * K, L, w->gcn_lft[l][0], R, T, ws, st, ph, pl, pld, t16_hi, t16_lo, R));
+                SUBGC_TRY(linear(w, T, B * K, R, w->gcn_rgt[l][0], L, Ma, ws, st, t16_hi, t16_lo, R));
+                SUBGC_TRY(linear(w, p, B * K, L, w->gcn_lft[l][1], R, T, ws, st, ph, pl, pld, t16_hi, t16_lo, R));
+                SUBGC_TRY(linear(w, T, B * K, R, w->gcn_rgt[l][1], L, Mb, ws, st, t16_hi, t16_lo, R));
+            }
+            gcn_node_update_kernel<<<B * N, 256, 4 * K * sizeof(int), st>>>(folded ? M2 : Ma, folded ? M2 + L : Mb, rel, boundary ? x_res : nullptr, x_next,
+                                                                            B, N, K, L, folded ? 2 * L : L, folded ? 1.f / w->gcn_fold_scale[l][0] : 1.f);
             SUBGC_LAUNCH_CHECK();
         }
         cur16_hi = next16 ? n16_hi[l & 1] : nullptr; cur16_lo = next16 ? n16_lo[l & 1] : nullptr;

@@ -15,6 +15,7 @@ of every returned row is in `model.last_image_of_row`.
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 
 import torch
@@ -153,6 +154,7 @@ class _DeviceState:
         self.pack_key = None
         self.ovf_dev = self.ovf_host = self.ovf_event = None
         self.early = self.early_key = None
+        self.fold = self.fold_key = None
         self.mega = self.mega_key = None
         self.plans = {}
         self.tops = None
@@ -176,6 +178,8 @@ class TopDownModel(nn.Module):
     _ovf_event = _state_property("ovf_event")
     _early = _state_property("early")
     _early_key = _state_property("early_key")
+    _fold = _state_property("fold")
+    _fold_key = _state_property("fold_key")
     _mega = _state_property("mega")
     _mega_key = _state_property("mega_key")
     _plans = _state_property("plans")
@@ -347,6 +351,10 @@ class TopDownModel(nn.Module):
                 w.lang_early_w = None
                 self._plans.clear()
             w.mega, w.mega_bytes, w.mega_ctas = None, 0, 0
+            for l in range(self.dims.gcn_layers):   # folded GCN weights are an inference-only derived copy
+                for dr in range(2):
+                    w.gcn_fold[l][dr] = _lib.Linear(None, None)
+                    w.gcn_fold_scale[l][dr] = 0.0
             return
         dev = next(iter(params.values())).device
         if self._ovf_dev is None or self._ovf_dev.device != dev:
@@ -369,12 +377,50 @@ class TopDownModel(nn.Module):
             self._plans.clear()
         named["__lang_early"] = self._early
         w.lang_early_w = self._early.data_ptr()
+        self._attach_gcn_fold(w, params, named)
         arr, cnt = self._packs.build(named, {"core.att_lstm.weight_ih": [H, 2 * H], "core.lang_lstm.weight_ih": [H], "__lang_early": [H]})
         if self._pack_key != self._packs.array_key or not w.n_packs:
             w.packs, w.n_packs = arr, cnt
             self._pack_key = self._packs.array_key
             self._plans.clear()  # captured graphs hold the old packed-copy addresses
         self._attach_mega(w, params, dev)
+
+    def _attach_gcn_fold(self, w, params, named):
+        """Folded GCN weights (include/subgc_b200.h: subgc_weights.gcn_fold): fc_rgt(fc_lft(.)) of a _Collection_Unit is linear
+        (reference models/lib/graph_conv_unit.py:29-31), so both units of a direction become one [2L, L] matrix, computed in fp64 and
+        scaled by a power of two (undone exactly by the consumer).  Rebuilt when a source parameter changed."""
+        Ln = self.dims.gcn_layers
+        if os.environ.get("SUBGC_GCN_FOLD", "1") == "0" or Ln == 0:
+            for l in range(Ln):
+                for dr in range(2):
+                    w.gcn_fold[l][dr] = _lib.Linear(None, None)
+                    w.gcn_fold_scale[l][dr] = 0.0
+            return
+        pre = lambda l, u: f"gcn_backbone.gcn.{l}.gcn_collect.collect_units.{u}."
+        src = [params[pre(l, u) + k] for l in range(Ln) for u in range(4) for k in ("fc_lft.weight", "fc_lft.bias", "fc_rgt.weight", "fc_rgt.bias")]
+        fkey = tuple((t.data_ptr(), t._version) for t in src)
+        if self._fold_key != fkey:
+            fold = {}
+            with torch.no_grad():
+                for l in range(Ln):
+                    for dr, units in enumerate(((0, 1), (2, 3))):
+                        ws, bs = [], []
+                        for u in units:
+                            wl, bl = params[pre(l, u) + "fc_lft.weight"].double(), params[pre(l, u) + "fc_lft.bias"].double()
+                            wr, br = params[pre(l, u) + "fc_rgt.weight"].double(), params[pre(l, u) + "fc_rgt.bias"].double()
+                            ws.append(wr @ wl)
+                            bs.append(wr @ bl + br)
+                        wf, bf = torch.cat(ws, 0), torch.cat(bs, 0)
+                        mx = float(wf.abs().max())
+                        e = 0 if not (mx > 0.0 and math.isfinite(mx)) else max(0, min(40, int(math.floor(math.log2(1024.0 / mx)))))
+                        scale = float(2.0 ** e)
+                        fold[(l, dr)] = ((wf * scale).float().contiguous(), (bf * scale).float().contiguous(), scale)
+            self._fold, self._fold_key = fold, fkey
+            self._plans.clear()
+        for (l, dr), (wf, bf, scale) in self._fold.items():
+            named[f"__gcn_fold_{l}_{dr}"] = wf
+            w.gcn_fold[l][dr] = _lib.Linear(wf.data_ptr(), bf.data_ptr())
+            w.gcn_fold_scale[l][dr] = scale
 
     _MEGA_SOURCES = ("core.att_lstm.weight_ih", "core.att_lstm.weight_hh", "core.lang_lstm.weight_ih", "core.lang_lstm.weight_hh",
                      "core.attention.h2att.weight", "logit.weight")
