@@ -425,7 +425,15 @@ typedef struct subgc_decoder_train_bufs {
     float* c_lang;         /* [T+1, R, H]                                                                       */
     float* h_lang;         /* [T+1, R, H]                                                                       */
     float* hd;             /* [T, R, H] h_lang * m_h (unused when m_h is NULL)                                  */
-    float* outputs;        /* [R, T_total, V1] log-probabilities; steps >= T are left untouched                 */
+    float* outputs;        /* nullable [R, T_total, V1] log-probabilities; steps >= T are left untouched        */
+    /* fused log-softmax + LanguageModelCriterion (misc/utils.py:115-124), used when the caller is LossWrapper
+     * (models/loss_wrapper.py:22): with `nll` set the log-probs need not exist (outputs may be NULL)            */
+    float* logits;         /* nullable [T*R, V1]: where the logits of all steps are kept (required for the fused loss) */
+    const int64_t* targets;/* [T, R] labels[:, t+1]                                                             */
+    const float* tmask;    /* [T, R] masks[:, t+1]                                                              */
+    float* lse;            /* [T, R] log-sum-exp of every row (saved for the backward)                          */
+    float* nll;            /* [T, R] -logp[target] * mask                                                       */
+    const float* coef;     /* backward with d_outputs == NULL: [T, R] mask * d(lang_loss) / sum(mask)           */
 } subgc_decoder_train_bufs;
 
 typedef struct subgc_decoder_grads { /* gradients, same shapes as the parameters; ACCUMULATED into (caller zero-fills) */
@@ -438,7 +446,8 @@ typedef struct subgc_decoder_grads { /* gradients, same shapes as the parameters
 size_t subgc_decoder_train_workspace_bytes(const subgc_dims* d, int R, int len, int T);
 int subgc_decoder_train_forward(const subgc_dims* d, const subgc_weights* w, int R, int len, int T, int T_total,
                                 const subgc_decoder_train_bufs* b, void* ws, size_t ws_bytes, subgc_stream_t stream);
-/* d_fc [R, H], d_att [R, len, H], d_p_att [R, len, AH]: gradients of the decoder's inputs (overwritten). */
+/* d_fc [R, H], d_att [R, len, H], d_p_att [R, len, AH]: gradients of the decoder's inputs (overwritten).
+ * d_outputs [R, T_total, V1], or NULL when the forward ran the fused loss (b->coef then carries d(lang_loss)). */
 int subgc_decoder_train_backward(const subgc_dims* d, const subgc_weights* w, int R, int len, int T, int T_total,
                                  const subgc_decoder_train_bufs* b, const float* d_outputs, const subgc_decoder_grads* g,
                                  float* d_fc, float* d_att, float* d_p_att, void* ws, size_t ws_bytes, subgc_stream_t stream);

@@ -693,6 +693,36 @@ __global__ void __launch_bounds__(256) sum_steps_kernel(int T, size_t n, const f
     }
 }
 
+// Fused log-softmax + LanguageModelCriterion term of one row (misc/utils.py:115-124: -logp[target] * mask): the [rows, V1] log-probs are
+// never written.  lse is kept for the backward; nll[r] = (lse - logit[target]) * mask[r].
+__global__ void __launch_bounds__(256) nll_fwd_kernel(const float* __restrict__ logits, int V1, const long long* __restrict__ target,
+                                                      const float* __restrict__ mask, float* __restrict__ lse, float* __restrict__ nll) {
+    __shared__ float red[32];
+    const size_t r = blockIdx.x;
+    const float* x = logits + r * V1;
+    float m = -INFINITY;
+    for (int j = threadIdx.x; j < V1; j += blockDim.x) m = fmaxf(m, x[j]);
+    m = block_max(m, red);
+    float s = 0.f;
+    for (int j = threadIdx.x; j < V1; j += blockDim.x) s += expf(x[j] - m);
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) {
+        const float lz = logf(s);
+        lse[r] = m + lz;
+        nll[r] = -((x[target[r]] - m) - lz) * mask[r];   // same rounding sequence as log_softmax_kernel: (x - max) - log(sum)
+    }
+}
+// d(logits)[r, j] = coef[r] * (softmax[r, j] - [j == target[r]]),  coef[r] = mask[r] * d(loss) / sum(mask)
+__global__ void __launch_bounds__(256) nll_bwd_kernel(const float* __restrict__ logits, int V1, const long long* __restrict__ target,
+                                                      const float* __restrict__ lse, const float* __restrict__ coef, float* __restrict__ dlogits) {
+    const size_t r = blockIdx.x;
+    const float* x = logits + r * V1;
+    float* dx = dlogits + r * V1;
+    const float c = coef[r], l = lse[r];
+    const int tg = (int)target[r];
+    for (int j = threadIdx.x; j < V1; j += blockDim.x) dx[j] = c * (expf(x[j] - l) - (j == tg ? 1.f : 0.f));
+}
+
 struct StageWs {   // bump allocator over the caller's workspace; everything 256-byte aligned
     Workspace ws;
     StageWs(void* p, size_t n) : ws(p, n) {}
@@ -752,8 +782,10 @@ extern "C" int subgc_decoder_train_forward(const subgc_dims* d, const subgc_weig
     StageWs sw(ws_, ws_bytes);
     const size_t gws_bytes = dec_gemm_ws_bytes(d, R, T);
     void* gws = sw.ws.take<char>(gws_bytes);
-    float* logits = sw.f((size_t)T * R * V1);
+    float* logits = b->logits ? b->logits : sw.f((size_t)T * R * V1);
     SUBGC_CHECK_ARG(sw.ws.ok(), "subgc_decoder_train_forward: workspace too small");
+    SUBGC_CHECK_ARG(b->outputs || (b->nll && b->lse && b->targets && b->tmask && b->logits),
+                    "subgc_decoder_train_forward: either outputs or the fused-loss buffers (logits, targets, tmask, lse, nll) are needed");
     // init_hidden (AttModel.py:343-346): slot 0 of the state histories
     SUBGC_CUDA(cudaMemsetAsync(b->h_att, 0, RH * 4, st)); SUBGC_CUDA(cudaMemsetAsync(b->c_att, 0, RH * 4, st));
     SUBGC_CUDA(cudaMemsetAsync(b->h_lang, 0, RH * 4, st)); SUBGC_CUDA(cudaMemsetAsync(b->c_lang, 0, RH * 4, st));
@@ -805,8 +837,14 @@ extern "C" int subgc_decoder_train_forward(const subgc_dims* d, const subgc_weig
         hd = b->hd;
     }
     SUBGC_TRY(gemm1(T * R, V1, H, hd, H, w->logit.w, H, w->logit.b, 0, logits, V1, gws, gws_bytes, st));
-    for (int t = 0; t < T; ++t)
-        SUBGC_TRY(subgc_log_softmax_fwd(R, V1, logits + (size_t)t * R * V1, b->outputs + (size_t)t * V1, (size_t)T_total * V1, stream));
+    if (b->outputs) {
+        for (int t = 0; t < T; ++t)
+            SUBGC_TRY(subgc_log_softmax_fwd(R, V1, logits + (size_t)t * R * V1, b->outputs + (size_t)t * V1, (size_t)T_total * V1, stream));
+    }
+    if (b->nll) {   // LossWrapper path: log-softmax + criterion fused, the log-probs are never materialised
+        nll_fwd_kernel<<<T * R, 256, 0, st>>>(logits, V1, reinterpret_cast<const long long*>(b->targets), b->tmask, b->lse, b->nll);
+        SUBGC_LAUNCH_CHECK();
+    }
     return SUBGC_OK;
 }
 
@@ -815,8 +853,10 @@ extern "C" int subgc_decoder_train_forward(const subgc_dims* d, const subgc_weig
 extern "C" int subgc_decoder_train_backward(const subgc_dims* d, const subgc_weights* w, int R, int len, int T, int T_total,
                                             const subgc_decoder_train_bufs* b, const float* d_outputs, const subgc_decoder_grads* g, float* d_fc,
                                             float* d_att, float* d_p_att, void* ws_, size_t ws_bytes, subgc_stream_t stream) {
-    SUBGC_CHECK_ARG(d && w && b && g && d_outputs && d_fc && d_att && d_p_att && ws_ && R > 0 && T > 0 && T <= T_total && len > 0 && len <= 64,
+    SUBGC_CHECK_ARG(d && w && b && g && d_fc && d_att && d_p_att && ws_ && R > 0 && T > 0 && T <= T_total && len > 0 && len <= 64,
                     "subgc_decoder_train_backward: bad arguments");
+    SUBGC_CHECK_ARG(d_outputs || (b->coef && b->lse && b->targets && b->logits),
+                    "subgc_decoder_train_backward: either d_outputs or the fused-loss buffers (coef, lse, targets, logits) are needed");
     SUBGC_CHECK_ARG(ws_bytes >= subgc_decoder_train_workspace_bytes(d, R, len, T), "subgc_decoder_train_backward: workspace too small");
     cudaStream_t st = ST;
     const int H = d->rnn, E = d->enc, V1 = d->vocab1, AH = d->att_hid, TR = T * R;
@@ -862,9 +902,14 @@ extern "C" int subgc_decoder_train_backward(const subgc_dims* d, const subgc_wei
     SUBGC_CUDA(cudaMemsetAsync(d_p_att, 0, (size_t)R * len * AH * 4, st));
 
     // ---- logit + log-softmax of all steps: d(logits), logit.weight / bias, d(h_lang after dropout)
-    for (int t = 0; t < T; ++t)
-        SUBGC_TRY(subgc_log_softmax_bwd(R, V1, b->outputs + (size_t)t * V1, d_outputs + (size_t)t * V1, (size_t)T_total * V1,
-                                        dlogits + (size_t)t * R * V1, stream));
+    if (d_outputs) {
+        for (int t = 0; t < T; ++t)
+            SUBGC_TRY(subgc_log_softmax_bwd(R, V1, b->outputs + (size_t)t * V1, d_outputs + (size_t)t * V1, (size_t)T_total * V1,
+                                            dlogits + (size_t)t * R * V1, stream));
+    } else {
+        nll_bwd_kernel<<<TR, 256, 0, st>>>(b->logits, V1, reinterpret_cast<const long long*>(b->targets), b->lse, b->coef, dlogits);
+        SUBGC_LAUNCH_CHECK();
+    }
     const float* hd = b->m_h ? b->hd : b->h_lang + RH;
     tr(dlogits, TR, V1, V1, big_t, TR, st);
     tr(hd, TR, H, H, xT, TR, st);

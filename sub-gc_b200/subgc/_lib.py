@@ -52,7 +52,7 @@ class Weights(C.Structure):
 
 class DecoderTrainBufs(C.Structure):   # subgc_decoder_train_bufs
     _fields_ = [(n, c_fp) for n in ("tokens", "fc", "att", "p_att", "masks", "m_x", "m_h", "xt", "act1", "c_att", "h_att", "atth", "ctx", "alpha",
-                                    "sm", "act2", "c_lang", "h_lang", "hd", "outputs")]
+                                    "sm", "act2", "c_lang", "h_lang", "hd", "outputs", "logits", "targets", "tmask", "lse", "nll", "coef")]
 
 
 class DecoderGrads(C.Structure):       # subgc_decoder_grads

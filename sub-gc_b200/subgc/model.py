@@ -125,7 +125,8 @@ class _TrainStep(torch.autograd.Function):
         from . import train
         P = dict(zip(names, (p.detach() for p in params)))
         ops = model._train_ops()
-        outputs, gpn_loss, score, saved = train.forward(ops, P, model._weights(), model.dims, data, drop, model.seq_per_img, ss=data.get("ss"))
+        outputs, gpn_loss, score, saved = train.forward(ops, P, model._weights(), model.dims, data, drop, model.seq_per_img, ss=data.get("ss"),
+                                                        loss=data.get("loss"))   # with `loss`, `outputs` is the scalar lang_loss
         ctx.pack = (model, ops, P, saved, names)
         ctx.mark_non_differentiable(score)
         return outputs, gpn_loss[0], score
@@ -136,7 +137,7 @@ class _TrainStep(torch.autograd.Function):
         model, ops, P, saved, names = ctx.pack
         ctx.pack = None   # the saved activations (~1.5 GB per step at 160 sentences) go back to the allocator when this call returns
         if d_outputs is None:
-            d_outputs = torch.zeros_like(saved["outputs"])
+            d_outputs = torch.zeros_like(saved["outputs"]) if saved.get("outputs") is not None else torch.zeros((), device=saved["x0"].device)
         dg = 0.0 if d_gpn_loss is None else float(d_gpn_loss)
         G = train.backward(ops, P, model.dims, saved, d_outputs.contiguous(), dg, reducer=getattr(model, "grad_reducer", None))
         return (None, None, None, None) + tuple(G.get(n) for n in names)
@@ -267,6 +268,7 @@ class TopDownModel(nn.Module):
         self.last_steps = None
         self._states = {}   # device index -> _DeviceState (shared by DataParallel replicas, which live on different devices)
         self.use_packed = True   # inference contractions read split-fp16 copies of the weights (subgc.packing)
+        self.fused_loss = True   # LossWrapper in train mode: log-softmax + LanguageModelCriterion inside the decoder stage
         self.use_mega = True     # greedy / top-k loops of <= 128 rows run as one persistent kernel (csrc/mega_decode.cu)
         self.grad_reducer = None     # subgc.parallel.GradReducer: gradient all-reduce overlapped with the hand-written backward (one process per GPU)
         self.use_step_graph = True   # ... and then the whole call (encoder .. decode) replays as ONE CUDA graph without host round trips
@@ -1016,8 +1018,9 @@ class TopDownModel(nn.Module):
         return outputs, loss[0], score.view(-1, 1)
 
 
-def _forward_train(self, att_feats, seq, att_masks, obj_dist, rel_ind, gpn_obj_ind):
-    """Training-mode AttModel._forward: CUDA forward with dropout + saved activations, gradients through _TrainStep."""
+def _forward_train(self, att_feats, seq, att_masks, obj_dist, rel_ind, gpn_obj_ind, loss=None):
+    """Training-mode AttModel._forward: CUDA forward with dropout + saved activations, gradients through _TrainStep.
+    loss = (labels[:, 1:], masks[:, 1:]) (LossWrapper): returns (lang_loss, gpn_loss, score) with log-softmax + criterion fused."""
     data = dict(att_feats=self._f32(att_feats), obj_dist=self._f32(obj_dist), rel_ind=self._i64(rel_ind), labels=self._i64(seq),
                 att_masks=self._f32(att_masks), gpn_obj_ind=self._i64(gpn_obj_ind))
     drop = None
@@ -1032,6 +1035,8 @@ def _forward_train(self, att_feats, seq, att_masks, obj_dist, rel_ind, gpn_obj_i
         drop = dict(p=float(self.drop_prob_lm), seed=seed)
     if self.training and self.ss_prob > 0:   # scheduled sampling (train.py:131: model.ss_prob is raised during training)
         data["ss"] = dict(prob=float(self.ss_prob), seed=int(torch.randint(0, 2 ** 31 - 1, (1,)).item()))
+    if loss is not None and "ss" not in data:
+        data["loss"] = (self._i64(loss[0]).contiguous(), self._f32(loss[1]).contiguous())
     names, params = zip(*self._named_params().items())
     outputs, gpn_loss, score = _TrainStep.apply(self, data, drop, names, *params)
     return outputs, gpn_loss, score
@@ -1061,6 +1066,13 @@ class LossWrapper(nn.Module):
 
     def forward(self, fc_feats, att_feats, labels, masks, att_masks, gts, gt_indices, trip_pred, obj_dist, obj_box, rel_ind, pred_fmap,
                 pred_dist, gpn_obj_ind, gpn_pred_ind, gpn_nrel_ind, gpn_pool_mtx):
+        m = self.model
+        if (isinstance(m, TopDownModel) and m.training and m.fused_loss and att_feats.is_cuda and not (m.ss_prob > 0)
+                and labels.shape[1] == masks.shape[1]):
+            # same result as the two lines below, with the log-softmax and the criterion inside the decoder stage (no [rows, T, V+1] tensor)
+            m._check_device(att_feats, labels, att_masks, obj_dist, rel_ind, gpn_obj_ind)
+            lang_loss, gpn_loss, _ = m._forward_train(att_feats, labels, att_masks, obj_dist, rel_ind, gpn_obj_ind, loss=(labels[:, 1:], masks[:, 1:]))
+            return {"gpn_loss": gpn_loss, "lang_loss": lang_loss}
         lang_output, gpn_loss, _ = self.model(fc_feats, att_feats, labels, att_masks, trip_pred, obj_dist, obj_box, rel_ind, pred_fmap,
                                               pred_dist, gpn_obj_ind, gpn_pred_ind, gpn_nrel_ind, gpn_pool_mtx)
         lang_loss = self.crit(lang_output, labels[:, 1:], masks[:, 1:]) if lang_output is not None else None

@@ -162,8 +162,9 @@ class CudaOps:
         return d_atth, d_w
 
     # -- stage-level decoder (one C call per direction, include/subgc_b200.h: subgc_decoder_train_forward / _backward) ------------
-    def decoder_forward(self, weights, tokens, fc, att3, p_att3, masks_c, m_x, m_h, outputs):
-        """tokens [T, R] int64.  Returns the saved-activation record the backward needs."""
+    def decoder_forward(self, weights, tokens, fc, att3, p_att3, masks_c, m_x, m_h, outputs, loss=None):
+        """tokens [T, R] int64.  Returns the saved-activation record the backward needs.  loss = (targets [T, R] int64, mask [T, R]):
+        fused log-softmax + criterion, `outputs` is then None and rec["nll"] holds -logp[target] * mask per row."""
         L = lib()
         T, R = tokens.shape
         _, ln, H = att3.shape
@@ -173,23 +174,31 @@ class CudaOps:
         rec = dict(tokens=tokens, fc=fc, att=att3, p_att=p_att3, masks=masks_c, m_x=m_x, m_h=m_h, xt=f(T, R, E), act1=f(T, R, 4 * H),
                    c_att=f(T + 1, R, H), h_att=f(T + 1, R, H), atth=f(T, R, AH), ctx=f(T, R, H), alpha=f(T, R, ln), sm=f(T, R, ln),
                    act2=f(T, R, 4 * H), c_lang=f(T + 1, R, H), h_lang=f(T + 1, R, H), hd=f(T, R, H) if m_h is not None else None, outputs=outputs)
+        if loss is not None:
+            rec.update(logits=f(T * R, self.cd.vocab1), targets=loss[0], tmask=loss[1], lse=f(T, R), nll=f(T, R))
         bufs = _lib.DecoderTrainBufs(**{k: ptr(v) for k, v in rec.items()})
         ws = self._wsbuf(L.subgc_decoder_train_workspace_bytes(C.byref(self.cd), R, ln, T), dev)
-        check(L.subgc_decoder_train_forward(C.byref(self.cd), C.byref(weights), R, ln, T, outputs.shape[1], C.byref(bufs), ptr(ws), ws.numel(),
+        T_total = outputs.shape[1] if outputs is not None else T
+        check(L.subgc_decoder_train_forward(C.byref(self.cd), C.byref(weights), R, ln, T, T_total, C.byref(bufs), ptr(ws), ws.numel(),
                                             self._st()), "subgc_decoder_train_forward")
+        rec["T_total"] = T_total
         rec.update(bufs=bufs, T=T, R=R, len=ln, weights=weights, outputs=None)   # the caller keeps a detached alias of outputs alive
         return rec
 
-    def decoder_backward(self, rec, d_outputs, grads):
-        """grads: name -> zero-filled gradient tensor of the 14 decoder parameters.  Returns (d_fc, d_att, d_p_att)."""
+    def decoder_backward(self, rec, d_outputs, grads, coef=None):
+        """grads: name -> zero-filled gradient tensor of the 14 decoder parameters.  Returns (d_fc, d_att, d_p_att).
+        coef [T, R] (fused loss: mask * d(lang_loss) / sum(mask)) replaces d_outputs."""
         L = lib()
         T, R, ln = rec["T"], rec["R"], rec["len"]
-        dev = d_outputs.device
+        dev = rec["att"].device
         H, AH = rec["att"].shape[2], rec["p_att"].shape[2]
+        if coef is not None:
+            rec["coef"] = coef   # keeps the tensor alive until the launches are enqueued
+            rec["bufs"].coef = ptr(coef)
         d_fc, d_att, d_patt = torch.empty(R, H, device=dev), torch.empty(R, ln, H, device=dev), torch.empty(R, ln, AH, device=dev)
         g = _lib.DecoderGrads(**{k: ptr(grads[n]) for k, n in DECODER_GRAD_FIELDS.items()})
         ws = self._wsbuf(L.subgc_decoder_train_workspace_bytes(C.byref(self.cd), R, ln, T), dev)
-        check(L.subgc_decoder_train_backward(C.byref(self.cd), C.byref(rec["weights"]), R, ln, T, d_outputs.shape[1], C.byref(rec["bufs"]),
+        check(L.subgc_decoder_train_backward(C.byref(self.cd), C.byref(rec["weights"]), R, ln, T, rec["T_total"], C.byref(rec["bufs"]),
                                              ptr(d_outputs), C.byref(g), ptr(d_fc), ptr(d_att), ptr(d_patt), ptr(ws), ws.numel(), self._st()),
               "subgc_decoder_train_backward")
         return d_fc, d_att, d_patt
@@ -316,7 +325,7 @@ def _unit(l, u):
 # ------------------------------------------------------------------------------------------------------------------
 # forward
 # ------------------------------------------------------------------------------------------------------------------
-def forward(ops, P, weights, d, data, drop=None, seq_per_img=5, ss=None):
+def forward(ops, P, weights, d, data, drop=None, seq_per_img=5, ss=None, loss=None):
     """Train-mode AttModel._forward.  P: name -> parameter tensor; weights: subgc_weights struct (for subgc_fuse_nodes);
     drop: None (dropout off) or dict(p=drop_prob_lm, seed=int).  Returns (outputs, gpn_loss, score, saved)."""
     S = {}
@@ -416,8 +425,22 @@ def forward(ops, P, weights, d, data, drop=None, seq_per_img=5, ss=None):
         if int(lab_h[:, i].sum()) == 0:
             n_exec = i
             break
-    outputs = torch.zeros(rows, T, V1, device=dev)
     use_ss = ss is not None and ss["prob"] > 0.0
+    if loss is not None and hasattr(ops, "decoder_forward") and not use_ss:
+        # LossWrapper path (models/loss_wrapper.py:22 + misc/utils.py:115-124): log-softmax and the criterion are fused into the decoder
+        # stage, the [rows, T, V1] log-probs are never written.  loss = (labels[:, 1:], masks[:, 1:]); returns the scalar lang_loss
+        tgt, msk = loss
+        tokens = labels[:, :n_exec].t().contiguous()
+        m_x = dmask((n_exec, rows, d.enc), p_lm)
+        m_h = dmask((n_exec, rows, H), p_lm)
+        tmask = msk[:, :n_exec].t().contiguous().float()
+        dec = ops.decoder_forward(weights, tokens, fc, att3, p_att3, masks_c, m_x, m_h, None, loss=(tgt[:, :n_exec].t().contiguous(), tmask))
+        mask_total = msk[:, :T].sum()
+        lang_loss = dec["nll"].sum() / mask_total
+        S.update(dec=dec, outputs=None, n_exec=n_exec, B=B, N=N, K=K, rows=rows, rel_ind=rel_ind, obj_ind=obj_ind, att_feats=att_feats,
+                 tmask=tmask, mask_total=mask_total)
+        return lang_loss, gpn_loss, score.view(-1, 1), S
+    outputs = torch.zeros(rows, T, V1, device=dev)
     if hasattr(ops, "decoder_forward") and not use_ss:
         # stage-level C entry: the whole teacher-forced loop, the batched logit contraction and the log-softmax are one call
         tokens = labels[:, :n_exec].t().contiguous()
@@ -522,7 +545,11 @@ def backward(ops, P, d, S, d_outputs, d_gpn_loss, reducer=None):
         for n in DECODER_GRAD_FIELDS.values():
             if n not in G:
                 G[n] = new_grad(n)
-        d_fc, d_att, d_patt = ops.decoder_backward(S["dec"], d_outputs, G)
+        if S.get("tmask") is not None:   # fused loss: d_outputs is the scalar d(lang_loss)
+            coef = (S["tmask"] * (d_outputs / S["mask_total"])).contiguous()
+            d_fc, d_att, d_patt = ops.decoder_backward(S["dec"], None, G, coef=coef)
+        else:
+            d_fc, d_att, d_patt = ops.decoder_backward(S["dec"], d_outputs, G)
     for t in (range(S["n_exec"] - 1, -1, -1) if "dec" not in S else ()):
         st = S["steps"][t]
         dlogits = ops.log_softmax_bwd(S["outputs"][:, t], d_outputs[:, t])

@@ -145,9 +145,11 @@ def test_graph_blocks(ops):
     assert torch.equal(cls.cpu(), e.class_argmax(data["obj_dist"].reshape(B * N, -1), 1))
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("name", ["small_train", "small_train_refinit", "full_train"])
-def test_loss_wrapper_backward_matches_reference(name):
-    """full_train: the reference's own autograd gradients at FULL dimensions (V = 9487, H = 1000, 2048-d features; 2 images, 10
+def test_loss_wrapper_backward_matches_reference(name, fused):
+    """fused: LossWrapper's log-softmax + LanguageModelCriterion inside the decoder stage (no [rows, T, V+1] tensor) / the model's
+    log-probs followed by the criterion as in models/loss_wrapper.py:22.  full_train: the reference's own autograd gradients at FULL dimensions (V = 9487, H = 1000, 2048-d features; 2 images, 10
     sentences): the training path's tensor-core contractions (split-TF32, K up to 3000, N = 9488) against something real."""
     g = load_golden(name)
     d, sd, data = rebuild_train_case(g)
@@ -155,6 +157,7 @@ def test_loss_wrapper_backward_matches_reference(name):
     model.load_state_dict(sd)
     model.cuda().train()
     model.dropout_enabled = False
+    model.fused_loss = fused
     lw = LossWrapper(model, None)
     dev = {k: cu(v) for k, v in data.items()}
     res = lw(dev["fc_feats"], dev["att_feats"], dev["labels"], dev["masks"], dev["att_masks"], None, None, None, dev["obj_dist"], None,

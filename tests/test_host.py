@@ -48,7 +48,7 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(_lib.Weights) == 16 * n_linear + 8 * (3 + 8) + 32 + 24 + _lib.MAX_GCN_LAYERS * (2 * 16 + 2 * 4)
     assert ctypes.sizeof(_lib.Packed) == 3 * 8 + 8 * 4
     assert ctypes.sizeof(_lib.Layout) == 16
-    assert ctypes.sizeof(_lib.DecoderTrainBufs) == 20 * 8 and ctypes.sizeof(_lib.DecoderGrads) == 14 * 8
+    assert ctypes.sizeof(_lib.DecoderTrainBufs) == 26 * 8 and ctypes.sizeof(_lib.DecoderGrads) == 14 * 8
 
 
 @pytest.mark.parametrize("d", [SMALL, Dims()])
