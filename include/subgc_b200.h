@@ -452,6 +452,63 @@ int subgc_decoder_train_backward(const subgc_dims* d, const subgc_weights* w, in
                                  const subgc_decoder_train_bufs* b, const float* d_outputs, const subgc_decoder_grads* g,
                                  float* d_fc, float* d_att, float* d_p_att, void* ws, size_t ws_bytes, subgc_stream_t stream);
 
+/* Front-end backward stages.  `*_saved`: train-mode forward activations; `*_grads`: parameter gradients, ACCUMULATED
+ * into (caller zero-fills).  One workspace query covers the three calls. */
+typedef struct subgc_prepare_train_saved {
+    const float* m_fc;       /* nullable [R, H] dropout mask of fc_embed's output                                 */
+    const float* fc_pre;     /* [R, H] fc_embed output before dropout                                             */
+    const float* f1;         /* [R, FC] relu(fc_embed.0)                                                          */
+    const float* g_fc;       /* [R, 2L] read_out_proj output                                                      */
+    const float* hr;         /* [R, AH] read_out_proj.0 output                                                    */
+    const float* read_sel;   /* [R, 2L] pooled read-out of the selected sub-graphs (detached, gpn.py:78)          */
+    const float* att;        /* [R*len, H] att_embed output after mask                                            */
+    const float* att_pre;    /* [R*len, H] relu(att_embed.0)                                                      */
+    const float* m_att;      /* [R*len, H] dropout mask x valid-row mask                                          */
+    const float* x_rows;     /* [R*len, L] gathered node features                                                 */
+    const int64_t* node_row; /* [R*len] row of x_obj [B*N, L] each attention row was gathered from                */
+} subgc_prepare_train_saved;
+typedef struct subgc_prepare_grads {
+    float* fc2_w; float* fc2_b; float* fc0_w; float* fc0_b; float* ro1_w; float* ro1_b; float* ro0_w; float* ro0_b;
+    float* ctx2att_w; float* ctx2att_b; float* att_embed_w; float* att_embed_b;
+} subgc_prepare_grads;
+typedef struct subgc_sgpn_train_saved {
+    const float* score;      /* [n_sub] sigmoid output                                                            */
+    const float* hid;        /* [n_sub, AH] relu(gpn_fc.0)                                                        */
+    const float* hid_d;      /* [n_sub, AH] after Dropout(0.5) (= hid when m_gpn is NULL)                         */
+    const float* m_gpn;      /* nullable [n_sub, AH]                                                              */
+    const float* read_out;   /* [n_sub, 2L]                                                                       */
+    const int32_t* sub_len;  /* [n_sub]                                                                           */
+} subgc_sgpn_train_saved;
+typedef struct subgc_sgpn_grads { float* fc3_w; float* fc3_b; float* fc0_w; float* fc0_b; } subgc_sgpn_grads;
+typedef struct subgc_gcn_layer_saved { /* NULL where the unit pair is dead (gcn liveness) */
+    const float* x_in; const float* p_in;   /* [B, N, L] / [B, K, L] streams entering the layer                   */
+    const float* t0; const float* t1;       /* [B*K, R] fc_lft outputs of units 0, 1                              */
+    const float* y0; const float* y1;       /* [B, N, L] pre-ReLU segment means of units 0, 1                     */
+    const float* t2; const float* t3;       /* [B*N, R] fc_lft outputs of units 2, 3                              */
+    const float* m2; const float* m3;       /* [B, N, L] messages of units 2, 3                                   */
+} subgc_gcn_layer_saved;
+typedef struct subgc_gcn_train_saved {
+    subgc_gcn_layer_saved layer[SUBGC_MAX_GCN_LAYERS];
+    const float* x0;         /* [B, N, L] fused node features                                                     */
+    const float* att_feats;  /* [B, N, A]                                                                         */
+    const int64_t* cls;      /* [B*N] object class ids                                                            */
+    const int64_t* rel_ind;  /* [B, K, 2]                                                                         */
+} subgc_gcn_train_saved;
+typedef struct subgc_gcn_grads {
+    float* lft_w[SUBGC_MAX_GCN_LAYERS][4]; float* lft_b[SUBGC_MAX_GCN_LAYERS][4];
+    float* rgt_w[SUBGC_MAX_GCN_LAYERS][4]; float* rgt_b[SUBGC_MAX_GCN_LAYERS][4];
+    float* obj_v_w; float* obj_v_b; float* obj_emb_w; float* obj_emb_b; float* sg_obj_embed;
+} subgc_gcn_grads;
+size_t subgc_frontend_backward_workspace_bytes(const subgc_dims* d, int n_images, int R, int len, int n_sub);
+int subgc_prepare_backward(const subgc_dims* d, const subgc_weights* w, int R, int len, int n_nodes,
+                           const subgc_prepare_train_saved* s, float* d_fc, const float* d_att, const float* d_p_att,
+                           const subgc_prepare_grads* g, float* d_x_obj, void* ws, size_t ws_bytes, subgc_stream_t stream);
+int subgc_sgpn_backward(const subgc_dims* d, const subgc_weights* w, const subgc_subgraph_layout* lay,
+                        const subgc_sgpn_train_saved* s, float scale, const float* x_obj, const int64_t* gpn_obj_ind,
+                        const subgc_sgpn_grads* g, float* d_x_obj, void* ws, size_t ws_bytes, subgc_stream_t stream);
+int subgc_gcn_backward(const subgc_dims* d, const subgc_weights* w, int n_images, const subgc_gcn_train_saved* s,
+                       const float* d_x_obj, const subgc_gcn_grads* g, void* ws, size_t ws_bytes, subgc_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Optimiser step: utils.clip_gradient_norm(optimizer, clip) (misc/utils.py:174-200) + torch.optim.Adam.step()
  * (misc/utils.py:236, train.py:107,163-164) over every parameter in two multi-tensor passes.  `chunks` is a DEVICE table of

@@ -991,3 +991,206 @@ extern "C" int subgc_decoder_train_backward(const subgc_dims* d, const subgc_wei
     SUBGC_TRY(subgc_colsum(TR, AH, d_wrows, AH, g->alpha_w, 1, stream));
     return SUBGC_OK;
 }
+
+// =====================================================================================================================================
+// Stage-level backward entries of the front-end: feature preparation, sGPN, GCN + fusion.  Each sequences the same
+// building blocks as sub-gc_b200/subgc/train.py's reference orchestration (kept for the CPU emulation tests) in one C call.
+// =====================================================================================================================================
+namespace subgc {
+
+struct BwdCtx {   // scratch shared by the dW / dX helpers of one call
+    float* dyT; float* xT; float* wT; void* gws; size_t gws_bytes; cudaStream_t st;
+    // G[Mw, Kx] (ld ldg) += dy^T . x        dy [rows, Mw], x [rows, Kx]
+    int dW(float* G, int ldg, const float* dy, int Mw, const float* x, int Kx, int rows) const {
+        tr(dy, rows, Mw, Mw, dyT, rows, st);
+        tr(x, rows, Kx, Kx, xT, rows, st);
+        return gemm1(Mw, Kx, rows, dyT, rows, xT, rows, nullptr, 1, G, ldg, gws, gws_bytes, st);
+    }
+    // out[rows, Kx] = dy . W                 W [Mw, Kx] (nn.Linear layout)
+    int dX(float* out, const float* dy, int rows, int Mw, const float* W, int Kx) const {
+        tr(W, Mw, Kx, Kx, wT, Mw, st);
+        return gemm1(rows, Kx, Mw, dy, Mw, wT, Mw, nullptr, 0, out, Kx, gws, gws_bytes, st);
+    }
+};
+static size_t bwd_scratch_floats(size_t rows_max, size_t dim_max) { return 2 * rows_max * dim_max + dim_max * dim_max; }
+static size_t bwd_gemm_ws(size_t rows_max, int dim_max) {
+    size_t a = gemm_workspace_bytes(dim_max, dim_max, (int)rows_max), b = gemm_workspace_bytes((int)rows_max, dim_max, dim_max);
+    return align_up(a > b ? a : b, 256) + 1024;
+}
+static bool bwd_ctx(BwdCtx& c, Workspace& ws, size_t rows_max, int dim_max, cudaStream_t st) {
+    c.gws_bytes = bwd_gemm_ws(rows_max, dim_max);
+    c.gws = ws.take<char>(c.gws_bytes);
+    c.dyT = ws.take<float>(rows_max * dim_max);
+    c.xT = ws.take<float>(rows_max * dim_max);
+    c.wT = ws.take<float>((size_t)dim_max * dim_max);
+    c.st = st;
+    return ws.ok();
+}
+static inline int imax(int a, int b) { return a > b ? a : b; }
+static int ew(int op, size_t n, const float* a, const float* b, float* out, cudaStream_t st) {
+    if (n == 0) return SUBGC_OK;
+    ew_kernel<<<ew_blocks(n), 256, 0, st>>>(op, n, a, b, out, 0.f);
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}
+
+}  // namespace subgc
+
+extern "C" size_t subgc_frontend_backward_workspace_bytes(const subgc_dims* d, int n_images, int R, int len, int n_sub) {
+    if (!d) return 0;
+    const int dim = imax(imax(imax(2 * d->gcn, d->att_feat), imax(imax(d->fc_feat, d->rnn), imax(d->att_hid, d->embed))), d->low_rank);
+    const size_t rows = (size_t)imax(imax(n_images * imax(d->obj_num, d->rel_num), R * len), imax(n_sub, R));
+    size_t b = bwd_gemm_ws(rows, dim) + align_up(bwd_scratch_floats(rows, dim) * 4, 256) + 4096;
+    b += 12 * align_up(rows * (size_t)dim * 4, 256);   // stage temporaries (gradients of intermediate activations)
+    b += (size_t)(2 * d->gcn_layers + 2) * align_up((size_t)n_images * imax(d->obj_num, d->rel_num) * d->gcn * 4, 256);   // gx / gp per layer
+    return b;
+}
+
+/* Backward of the feature preparation (AttModel.py:348-368 after gpn.py:79): fc_embed, read_out_proj (the read-out itself is detached,
+ * gpn.py:78), att_embed (pack_wrapper: padded rows masked), ctx2att.  d_fc is modified in place.  d_x_obj [n_nodes, L] is overwritten. */
+extern "C" int subgc_prepare_backward(const subgc_dims* d, const subgc_weights* w, int R, int len, int n_nodes, const subgc_prepare_train_saved* s,
+                                      float* d_fc, const float* d_att, const float* d_p_att, const subgc_prepare_grads* g, float* d_x_obj,
+                                      void* ws_, size_t ws_bytes, subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(d && w && s && g && d_fc && d_att && d_p_att && d_x_obj && ws_ && R > 0 && len > 0 && n_nodes > 0, "subgc_prepare_backward: bad arguments");
+    cudaStream_t st = ST;
+    const int H = d->rnn, FC = d->fc_feat, L = d->gcn, AH = d->att_hid, RL = R * len;
+    Workspace ws(ws_, ws_bytes);
+    BwdCtx c;
+    const int dim = imax(imax(2 * L, FC), imax(H, AH));
+    SUBGC_CHECK_ARG(bwd_ctx(c, ws, (size_t)imax(RL, R), dim, st), "subgc_prepare_backward: workspace too small");
+    float* d_fcp = ws.take<float>((size_t)R * H);
+    float* d_f1 = ws.take<float>((size_t)R * FC);
+    float* d_gfc = ws.take<float>((size_t)R * 2 * L);
+    float* d_hr = ws.take<float>((size_t)R * AH);
+    float* d_att2 = ws.take<float>((size_t)RL * H);
+    float* d_rows = ws.take<float>((size_t)RL * L);
+    SUBGC_CHECK_ARG(ws.ok(), "subgc_prepare_backward: workspace too small");
+    // fc path: dropout -> ReLU -> fc_embed.2 -> ReLU -> fc_embed.0 -> read_out_proj.1 -> read_out_proj.0
+    if (s->m_fc) SUBGC_TRY(ew(EW_MUL, (size_t)R * H, d_fc, s->m_fc, d_fc, st));
+    SUBGC_TRY(ew(EW_RELU_BWD, (size_t)R * H, s->fc_pre, d_fc, d_fcp, st));
+    SUBGC_TRY(c.dW(g->fc2_w, FC, d_fcp, H, s->f1, FC, R)); SUBGC_TRY(subgc_colsum(R, H, d_fcp, H, g->fc2_b, 1, stream));
+    SUBGC_TRY(c.dX(d_f1, d_fcp, R, H, w->fc_embed2.w, FC));
+    SUBGC_TRY(ew(EW_RELU_BWD, (size_t)R * FC, s->f1, d_f1, d_f1, st));
+    SUBGC_TRY(c.dW(g->fc0_w, 2 * L, d_f1, FC, s->g_fc, 2 * L, R)); SUBGC_TRY(subgc_colsum(R, FC, d_f1, FC, g->fc0_b, 1, stream));
+    SUBGC_TRY(c.dX(d_gfc, d_f1, R, FC, w->fc_embed0.w, 2 * L));
+    SUBGC_TRY(c.dW(g->ro1_w, AH, d_gfc, 2 * L, s->hr, AH, R)); SUBGC_TRY(subgc_colsum(R, 2 * L, d_gfc, 2 * L, g->ro1_b, 1, stream));
+    SUBGC_TRY(c.dX(d_hr, d_gfc, R, 2 * L, w->read_out1.w, AH));
+    SUBGC_TRY(c.dW(g->ro0_w, 2 * L, d_hr, AH, s->read_sel, 2 * L, R)); SUBGC_TRY(subgc_colsum(R, AH, d_hr, AH, g->ro0_b, 1, stream));
+    // attention features: ctx2att, then att_embed through mask (dropout x valid rows) and ReLU, scattered back to the node rows
+    SUBGC_TRY(c.dW(g->ctx2att_w, H, d_p_att, AH, s->att, H, RL)); SUBGC_TRY(subgc_colsum(RL, AH, d_p_att, AH, g->ctx2att_b, 1, stream));
+    SUBGC_TRY(c.dX(d_att2, d_p_att, RL, AH, w->ctx2att.w, H));
+    SUBGC_TRY(ew(EW_ADD, (size_t)RL * H, d_att2, d_att, d_att2, st));
+    SUBGC_TRY(ew(EW_MUL, (size_t)RL * H, d_att2, s->m_att, d_att2, st));
+    SUBGC_TRY(ew(EW_RELU_BWD, (size_t)RL * H, s->att_pre, d_att2, d_att2, st));
+    SUBGC_TRY(c.dW(g->att_embed_w, L, d_att2, H, s->x_rows, L, RL)); SUBGC_TRY(subgc_colsum(RL, H, d_att2, H, g->att_embed_b, 1, stream));
+    SUBGC_TRY(c.dX(d_rows, d_att2, RL, H, w->att_embed.w, L));
+    SUBGC_CUDA(cudaMemsetAsync(d_x_obj, 0, (size_t)n_nodes * L * 4, st));
+    SUBGC_TRY(subgc_scatter_add_rows(RL, L, d_rows, L, s->node_row, d_x_obj, L, stream));
+    return SUBGC_OK;
+}
+
+/* Backward of the sGPN scorer (gpn.py:41-58): BCE(sigmoid) -> gpn_fc.3 -> Dropout(0.5) -> ReLU -> gpn_fc.0 -> max / mean pooling.
+ * scale = d(gpn_loss) / n_sub.  d_x_obj [B, N, L] is ACCUMULATED into. */
+extern "C" int subgc_sgpn_backward(const subgc_dims* d, const subgc_weights* w, const subgc_subgraph_layout* lay, const subgc_sgpn_train_saved* s,
+                                   float scale, const float* x_obj, const int64_t* gpn_obj_ind, const subgc_sgpn_grads* g, float* d_x_obj, void* ws_,
+                                   size_t ws_bytes, subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(d && w && lay && s && g && x_obj && gpn_obj_ind && d_x_obj && ws_, "subgc_sgpn_backward: bad arguments");
+    cudaStream_t st = ST;
+    const int n_sub = subgraph_count(*lay), L = d->gcn, AH = d->att_hid;
+    Workspace ws(ws_, ws_bytes);
+    BwdCtx c;
+    SUBGC_CHECK_ARG(bwd_ctx(c, ws, (size_t)n_sub, imax(2 * L, AH), st), "subgc_sgpn_backward: workspace too small");
+    float* dz = ws.take<float>(n_sub);
+    float* d_hid = ws.take<float>((size_t)n_sub * AH);
+    float* d_read = ws.take<float>((size_t)n_sub * 2 * L);
+    SUBGC_CHECK_ARG(ws.ok(), "subgc_sgpn_backward: workspace too small");
+    SUBGC_TRY(subgc_bce_sigmoid_bwd(lay, s->score, scale, dz, stream));
+    SUBGC_TRY(c.dW(g->fc3_w, AH, dz, 1, s->hid_d, AH, n_sub)); SUBGC_TRY(subgc_colsum(n_sub, 1, dz, 1, g->fc3_b, 1, stream));
+    SUBGC_TRY(c.dX(d_hid, dz, n_sub, 1, w->gpn_fc3.w, AH));
+    if (s->m_gpn) SUBGC_TRY(ew(EW_MUL, (size_t)n_sub * AH, d_hid, s->m_gpn, d_hid, st));
+    SUBGC_TRY(ew(EW_RELU_BWD, (size_t)n_sub * AH, s->hid, d_hid, d_hid, st));
+    SUBGC_TRY(c.dW(g->fc0_w, 2 * L, d_hid, AH, s->read_out, 2 * L, n_sub)); SUBGC_TRY(subgc_colsum(n_sub, AH, d_hid, AH, g->fc0_b, 1, stream));
+    SUBGC_TRY(c.dX(d_read, d_hid, n_sub, AH, w->gpn_fc0.w, 2 * L));
+    return subgc_sgpn_pool_bwd(d, lay, x_obj, gpn_obj_ind, s->sub_len, d_read, d_x_obj, stream);
+}
+
+/* Backward of the GCN backbone (gcn_backbone.py:29-53, graph_conv.py:15-34, graph_conv_unit.py:28-36: live units only) and of the node
+ * fusion (AttModel.py:370-378).  d_x_obj [B, N, L]: gradient of the encoder output (not modified). */
+extern "C" int subgc_gcn_backward(const subgc_dims* d, const subgc_weights* w, int n_images, const subgc_gcn_train_saved* s, const float* d_x_obj,
+                                  const subgc_gcn_grads* g, void* ws_, size_t ws_bytes, subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(d && w && s && g && d_x_obj && ws_ && n_images > 0, "subgc_gcn_backward: bad arguments");
+    cudaStream_t st = ST;
+    const int B = n_images, N = d->obj_num, K = d->rel_num, L = d->gcn, Rk = d->low_rank, Ln = d->gcn_layers, Rs = d->gcn_residual;
+    const int E = d->embed, A = d->att_feat;
+    const size_t xn = (size_t)B * N * L, pn = (size_t)B * K * L;
+    Workspace ws(ws_, ws_bytes);
+    BwdCtx c;
+    SUBGC_CHECK_ARG(bwd_ctx(c, ws, (size_t)B * imax(N, K), imax(imax(L, A), imax(E, Rk)), st), "subgc_gcn_backward: workspace too small");
+    float* gx[SUBGC_MAX_GCN_LAYERS + 1];
+    float* gp[SUBGC_MAX_GCN_LAYERS + 1];
+    bool hx[SUBGC_MAX_GCN_LAYERS + 1], hp[SUBGC_MAX_GCN_LAYERS + 1];
+    for (int l = 0; l <= Ln; ++l) { gx[l] = ws.take<float>(xn); gp[l] = ws.take<float>(pn); hx[l] = hp[l] = false; }
+    const size_t big = (size_t)B * imax(N, K);
+    float* dm_a = ws.take<float>(big * L);
+    float* dm_b = ws.take<float>(big * L);
+    float* dt = ws.take<float>(big * Rk);
+    float* dsrc = ws.take<float>(big * L);
+    float* d_emb = ws.take<float>((size_t)B * N * E);
+    float* emb_rows = ws.take<float>((size_t)B * N * E);
+    SUBGC_CHECK_ARG(ws.ok(), "subgc_gcn_backward: workspace too small");
+    SUBGC_CUDA(cudaMemcpyAsync(gx[Ln], d_x_obj, xn * 4, cudaMemcpyDeviceToDevice, st));
+    hx[Ln] = true;
+    auto add_to = [&](float** lst, bool* has, int i, const float* v, size_t n) -> int {
+        if (!has[i]) { SUBGC_CUDA(cudaMemcpyAsync(lst[i], v, n * 4, cudaMemcpyDeviceToDevice, st)); has[i] = true; return SUBGC_OK; }
+        return ew(EW_ADD, n, lst[i], v, lst[i], st);
+    };
+    // backward of M = fc_rgt(fc_lft(src)) for one unit: gradients of both linears, d(src) accumulated into `acc` (first: overwrite)
+    auto unit_bwd = [&](int l, int u, const float* src, const float* tmid, const float* dm, int rows, float* acc, bool first) -> int {
+        SUBGC_TRY(c.dW(g->rgt_w[l][u], Rk, dm, L, tmid, Rk, rows)); SUBGC_TRY(subgc_colsum(rows, L, dm, L, g->rgt_b[l][u], 1, stream));
+        SUBGC_TRY(c.dX(dt, dm, rows, L, w->gcn_rgt[l][u].w, Rk));
+        SUBGC_TRY(c.dW(g->lft_w[l][u], L, dt, Rk, src, L, rows)); SUBGC_TRY(subgc_colsum(rows, Rk, dt, Rk, g->lft_b[l][u], 1, stream));
+        if (first) return c.dX(acc, dt, rows, Rk, w->gcn_lft[l][u].w, L);
+        SUBGC_TRY(c.dX(dm_a, dt, rows, Rk, w->gcn_lft[l][u].w, L));   // dm_a is free again by now
+        return ew(EW_ADD, (size_t)rows * L, acc, dm_a, acc, st);
+    };
+    for (int l = Ln - 1; l >= 0; --l) {
+        const subgc_gcn_layer_saved& rec = s->layer[l];
+        const bool boundary = ((l + 1) % Rs == 0);
+        if (hx[l + 1] && rec.y0) {   // units 0, 1 produced x(l+1) from the edge stream p(l)
+            if (boundary) SUBGC_TRY(add_to(gx, hx, l + 1 - Rs, gx[l + 1], xn));
+            SUBGC_TRY(subgc_gcn_node_bwd(B, N, K, L, gx[l + 1], rec.y0, rec.y1, s->rel_ind, dm_a, dm_b, stream));
+            // unit 1 first (its d(src) lands in dsrc), then unit 0 adds to it: dm_a is consumed by unit 0's first contraction before reuse
+            SUBGC_TRY(unit_bwd(l, 1, rec.p_in, rec.t1, dm_b, B * K, dsrc, true));
+            {
+                SUBGC_TRY(c.dW(g->rgt_w[l][0], Rk, dm_a, L, rec.t0, Rk, B * K)); SUBGC_TRY(subgc_colsum(B * K, L, dm_a, L, g->rgt_b[l][0], 1, stream));
+                SUBGC_TRY(c.dX(dt, dm_a, B * K, L, w->gcn_rgt[l][0].w, Rk));
+                SUBGC_TRY(c.dW(g->lft_w[l][0], L, dt, Rk, rec.p_in, L, B * K)); SUBGC_TRY(subgc_colsum(B * K, Rk, dt, Rk, g->lft_b[l][0], 1, stream));
+                SUBGC_TRY(c.dX(dm_a, dt, B * K, Rk, w->gcn_lft[l][0].w, L));
+                SUBGC_TRY(ew(EW_ADD, pn, dsrc, dm_a, dsrc, st));
+            }
+            SUBGC_TRY(add_to(gp, hp, l, dsrc, pn));
+        }
+        if (hp[l + 1] && rec.m2) {   // units 2, 3 produced p(l+1) from the node stream x(l)
+            if (boundary) SUBGC_TRY(add_to(gp, hp, l + 1 - Rs, gp[l + 1], pn));
+            SUBGC_TRY(subgc_gcn_edge_bwd(B, N, K, L, gp[l + 1], rec.m2, rec.m3, s->rel_ind, dm_a, dm_b, stream));
+            SUBGC_TRY(unit_bwd(l, 3, rec.x_in, rec.t3, dm_b, B * N, dsrc, true));
+            {
+                SUBGC_TRY(c.dW(g->rgt_w[l][2], Rk, dm_a, L, rec.t2, Rk, B * N)); SUBGC_TRY(subgc_colsum(B * N, L, dm_a, L, g->rgt_b[l][2], 1, stream));
+                SUBGC_TRY(c.dX(dt, dm_a, B * N, L, w->gcn_rgt[l][2].w, Rk));
+                SUBGC_TRY(c.dW(g->lft_w[l][2], L, dt, Rk, rec.x_in, L, B * N)); SUBGC_TRY(subgc_colsum(B * N, Rk, dt, Rk, g->lft_b[l][2], 1, stream));
+                SUBGC_TRY(c.dX(dm_a, dt, B * N, Rk, w->gcn_lft[l][2].w, L));
+                SUBGC_TRY(ew(EW_ADD, xn, dsrc, dm_a, dsrc, st));
+            }
+            SUBGC_TRY(add_to(gx, hx, l, dsrc, xn));
+        }
+    }
+    SUBGC_CHECK_ARG(hx[0], "subgc_gcn_backward: no gradient reached the fused node features");
+    // fusion: x0 = relu(W_v att + b_v + W_e E[cls] + b_e)
+    float* d_x0 = gx[0];
+    SUBGC_TRY(ew(EW_RELU_BWD, xn, s->x0, d_x0, d_x0, st));
+    SUBGC_TRY(c.dW(g->obj_v_w, A, d_x0, L, s->att_feats, A, B * N)); SUBGC_TRY(subgc_colsum(B * N, L, d_x0, L, g->obj_v_b, 1, stream));
+    SUBGC_TRY(subgc_gather_rows(B * N, E, w->sg_obj_embed, E, s->cls, emb_rows, 0, stream));
+    SUBGC_TRY(c.dW(g->obj_emb_w, E, d_x0, L, emb_rows, E, B * N)); SUBGC_TRY(subgc_colsum(B * N, L, d_x0, L, g->obj_emb_b, 1, stream));
+    SUBGC_TRY(c.dX(d_emb, d_x0, B * N, L, w->obj_emb_proj.w, E));
+    return subgc_scatter_add_rows(B * N, E, d_emb, E, s->cls, g->sg_obj_embed, E, stream);
+}

@@ -60,6 +60,40 @@ class DecoderGrads(C.Structure):       # subgc_decoder_grads
                                     "lang_b_ih", "lang_b_hh", "h2att_w", "h2att_b", "alpha_w")]
 
 
+def _ptr_struct(names):
+    return [(n, c_fp) for n in names]
+
+
+class PrepareSaved(C.Structure):
+    _fields_ = _ptr_struct(("m_fc", "fc_pre", "f1", "g_fc", "hr", "read_sel", "att", "att_pre", "m_att", "x_rows", "node_row"))
+
+
+class PrepareGrads(C.Structure):
+    _fields_ = _ptr_struct(("fc2_w", "fc2_b", "fc0_w", "fc0_b", "ro1_w", "ro1_b", "ro0_w", "ro0_b", "ctx2att_w", "ctx2att_b", "att_embed_w", "att_embed_b"))
+
+
+class SgpnSaved(C.Structure):
+    _fields_ = _ptr_struct(("score", "hid", "hid_d", "m_gpn", "read_out", "sub_len"))
+
+
+class SgpnGrads(C.Structure):
+    _fields_ = _ptr_struct(("fc3_w", "fc3_b", "fc0_w", "fc0_b"))
+
+
+class GcnLayerSaved(C.Structure):
+    _fields_ = _ptr_struct(("x_in", "p_in", "t0", "t1", "y0", "y1", "t2", "t3", "m2", "m3"))
+
+
+class GcnSaved(C.Structure):
+    _fields_ = [("layer", GcnLayerSaved * MAX_GCN_LAYERS), ("x0", c_fp), ("att_feats", c_fp), ("cls", c_fp), ("rel_ind", c_fp)]
+
+
+class GcnGrads(C.Structure):
+    _fields_ = [("lft_w", (c_fp * 4) * MAX_GCN_LAYERS), ("lft_b", (c_fp * 4) * MAX_GCN_LAYERS), ("rgt_w", (c_fp * 4) * MAX_GCN_LAYERS),
+                ("rgt_b", (c_fp * 4) * MAX_GCN_LAYERS), ("obj_v_w", c_fp), ("obj_v_b", c_fp), ("obj_emb_w", c_fp), ("obj_emb_b", c_fp),
+                ("sg_obj_embed", c_fp)]
+
+
 class Layout(C.Structure):
     _fields_ = [("rows", C.c_int32), ("per_half", C.c_int32), ("seq_per_img", C.c_int32), ("order", C.c_int32)]
 
@@ -122,6 +156,10 @@ SIGNATURES = {
     "subgc_unary": (_i, [_i, _sz, c_fp, c_fp, c_fp]),
     "subgc_scatter_add_rows": (_i, [_i, _i, c_fp, _i, c_fp, c_fp, _i, c_fp]),
     "subgc_lstm_cell_train_fwd": (_i, [_i, _i, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "subgc_frontend_backward_workspace_bytes": (_sz, [_P(Dims), _i, _i, _i, _i]),
+    "subgc_prepare_backward": (_i, [_P(Dims), _P(Weights), _i, _i, _i, _P(PrepareSaved), c_fp, c_fp, c_fp, _P(PrepareGrads), c_fp, c_fp, _sz, c_fp]),
+    "subgc_sgpn_backward": (_i, [_P(Dims), _P(Weights), _P(Layout), _P(SgpnSaved), _f, c_fp, c_fp, _P(SgpnGrads), c_fp, c_fp, _sz, c_fp]),
+    "subgc_gcn_backward": (_i, [_P(Dims), _P(Weights), _i, _P(GcnSaved), c_fp, _P(GcnGrads), c_fp, _sz, c_fp]),
     "subgc_decoder_train_workspace_bytes": (_sz, [_P(Dims), _i, _i, _i]),
     "subgc_decoder_train_forward": (_i, [_P(Dims), _P(Weights), _i, _i, _i, _i, _P(DecoderTrainBufs), c_fp, _sz, c_fp]),
     "subgc_decoder_train_backward": (_i, [_P(Dims), _P(Weights), _i, _i, _i, _i, _P(DecoderTrainBufs), c_fp, _P(DecoderGrads), c_fp, c_fp, c_fp,

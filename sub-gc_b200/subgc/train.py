@@ -34,6 +34,14 @@ DECODER_GRAD_FIELDS = {   # subgc_decoder_grads field -> state_dict name
 }
 
 
+PREPARE_GRAD_FIELDS = {   # subgc_prepare_grads field -> state_dict name
+    "fc2_w": "fc_embed.2.weight", "fc2_b": "fc_embed.2.bias", "fc0_w": "fc_embed.0.weight", "fc0_b": "fc_embed.0.bias",
+    "ro1_w": "gpn_layer.read_out_proj.1.weight", "ro1_b": "gpn_layer.read_out_proj.1.bias",
+    "ro0_w": "gpn_layer.read_out_proj.0.weight", "ro0_b": "gpn_layer.read_out_proj.0.bias",
+    "ctx2att_w": "ctx2att.weight", "ctx2att_b": "ctx2att.bias", "att_embed_w": "att_embed.0.weight", "att_embed_b": "att_embed.0.bias",
+}
+
+
 class CudaOps:
     """Building blocks on CUDA tensors (fp32, contiguous).  One method == one C-ABI call."""
 
@@ -203,6 +211,56 @@ class CudaOps:
               "subgc_decoder_train_backward")
         return d_fc, d_att, d_patt
 
+    # -- stage-level front-end backward (subgc_prepare_backward / subgc_sgpn_backward / subgc_gcn_backward) -------------------
+    def _front_ws(self, S):
+        L = lib()
+        n_sub = S["n_sub"]
+        nb = L.subgc_frontend_backward_workspace_bytes(C.byref(self.cd), S["B"], S["rows"], S["len_max"], n_sub)
+        return self._wsbuf(nb, S["x0"].device)
+
+    def prepare_backward(self, S, weights, d_fc, d_att, d_patt, G):
+        dev = S["x0"].device
+        R, ln = S["rows"], S["len_max"]
+        H = d_fc.shape[1]
+        saved = _lib.PrepareSaved(m_fc=ptr(S["m_fc"]), fc_pre=ptr(S["fc_pre"]), f1=ptr(S["f1"]), g_fc=ptr(S["g_fc"]), hr=ptr(S["hr"]),
+                                  read_sel=ptr(S["read_sel"]), att=ptr(S["att"]), att_pre=ptr(S["att_pre"]), m_att=ptr(S["m_att"]),
+                                  x_rows=ptr(S["x_rows"]), node_row=ptr(S["node_row"]))
+        g = _lib.PrepareGrads(**{k: ptr(G[n]) for k, n in PREPARE_GRAD_FIELDS.items()})
+        n_nodes = S["B"] * S["N"]
+        d_xobj = torch.empty(n_nodes, self.cd.gcn, device=dev)
+        ws = self._front_ws(S)
+        check(lib().subgc_prepare_backward(C.byref(self.cd), C.byref(weights), R, ln, n_nodes, C.byref(saved), ptr(d_fc), ptr(d_att.contiguous()),
+                                           ptr(d_patt.contiguous()), C.byref(g), ptr(d_xobj), ptr(ws), ws.numel(), self._st()), "subgc_prepare_backward")
+        return d_xobj
+
+    def sgpn_backward(self, S, weights, scale, G, d_xobj):
+        saved = _lib.SgpnSaved(score=ptr(S["score"]), hid=ptr(S["hid"]), hid_d=ptr(S["hid_d"]), m_gpn=ptr(S["m_gpn"]), read_out=ptr(S["read_out"]),
+                               sub_len=ptr(S["sub_len"]))
+        g = _lib.SgpnGrads(fc3_w=ptr(G["gpn_layer.gpn_fc.3.weight"]), fc3_b=ptr(G["gpn_layer.gpn_fc.3.bias"]),
+                           fc0_w=ptr(G["gpn_layer.gpn_fc.0.weight"]), fc0_b=ptr(G["gpn_layer.gpn_fc.0.bias"]))
+        ws = self._front_ws(S)
+        check(lib().subgc_sgpn_backward(C.byref(self.cd), C.byref(weights), C.byref(S["lay"]), C.byref(saved), float(scale), ptr(S["x_obj"]),
+                                        ptr(S["obj_ind"]), C.byref(g), ptr(d_xobj), ptr(ws), ws.numel(), self._st()), "subgc_sgpn_backward")
+
+    def gcn_backward(self, S, weights, d_xobj, G, live):
+        saved = _lib.GcnSaved()
+        for l, rec in enumerate(S["layers"]):
+            ls = saved.layer[l]
+            ls.x_in, ls.p_in = ptr(rec["x_in"]), ptr(rec["p_in"])
+            for k in ("t0", "t1", "y0", "y1", "t2", "t3", "m2", "m3"):
+                setattr(ls, k, ptr(rec.get(k)))
+        saved.x0, saved.att_feats, saved.cls, saved.rel_ind = ptr(S["x0"]), ptr(S["att_feats"]), ptr(S["cls"]), ptr(S["rel_ind"])
+        g = _lib.GcnGrads()
+        for (l, u) in live:
+            pre = _unit(l, u)
+            g.lft_w[l][u], g.lft_b[l][u] = ptr(G[pre + "fc_lft.weight"]), ptr(G[pre + "fc_lft.bias"])
+            g.rgt_w[l][u], g.rgt_b[l][u] = ptr(G[pre + "fc_rgt.weight"]), ptr(G[pre + "fc_rgt.bias"])
+        g.obj_v_w, g.obj_v_b = ptr(G["obj_v_proj.weight"]), ptr(G["obj_v_proj.bias"])
+        g.obj_emb_w, g.obj_emb_b, g.sg_obj_embed = ptr(G["obj_emb_proj.weight"]), ptr(G["obj_emb_proj.bias"]), ptr(G["sg_obj_embed.weight"])
+        ws = self._front_ws(S)
+        check(lib().subgc_gcn_backward(C.byref(self.cd), C.byref(weights), S["B"], C.byref(saved), ptr(d_xobj), C.byref(g), ptr(ws), ws.numel(),
+                                       self._st()), "subgc_gcn_backward")
+
     def log_softmax_fwd(self, logits, out_view):
         """out_view: [rows, V1] view with unit inner stride (e.g. outputs[:, t])."""
         check(lib().subgc_log_softmax_fwd(logits.shape[0], logits.shape[1], ptr(logits), ptr(out_view), out_view.stride(0), self._st()),
@@ -328,7 +386,7 @@ def _unit(l, u):
 def forward(ops, P, weights, d, data, drop=None, seq_per_img=5, ss=None, loss=None):
     """Train-mode AttModel._forward.  P: name -> parameter tensor; weights: subgc_weights struct (for subgc_fuse_nodes);
     drop: None (dropout off) or dict(p=drop_prob_lm, seed=int).  Returns (outputs, gpn_loss, score, saved)."""
-    S = {}
+    S = {"weights": weights}
     att_feats, obj_dist, rel_ind = data["att_feats"], data["obj_dist"], data["rel_ind"]
     labels, att_masks, obj_ind = data["labels"], data["att_masks"], data["gpn_obj_ind"]
     dev = att_feats.device
@@ -592,6 +650,43 @@ def backward(ops, P, d, S, d_outputs, d_gpn_loss, reducer=None):
 
     if reducer is not None:
         reducer.bucket_done(0, G)   # logit / embed / LSTMs / attention are final: their all-reduce overlaps everything below
+    if hasattr(ops, "prepare_backward") and S.get("weights") is not None:
+        # stage-level C entries: one call per front-end stage (same building blocks, sequenced in C++)
+        W_ = S["weights"]
+        for n in PREPARE_GRAD_FIELDS.values():
+            G[n] = new_grad(n)
+        d_xobj = ops.prepare_backward(S, W_, d_fc, d_att, d_patt, G)
+        if reducer is not None:
+            reducer.bucket_done(1, G)
+        for n in ("gpn_layer.gpn_fc.3.weight", "gpn_layer.gpn_fc.3.bias", "gpn_layer.gpn_fc.0.weight", "gpn_layer.gpn_fc.0.bias"):
+            G[n] = new_grad(n)
+        ops.sgpn_backward(S, W_, float(d_gpn_loss) / S["n_sub"], G, d_xobj)
+        # which collection units receive a gradient (the reference leaves .grad of the others at None)
+        Ln, R = d.gcn_layers, d.gcn_residual
+        hx, hp, live = [False] * (Ln + 1), [False] * (Ln + 1), []
+        hx[Ln] = True
+        for l in range(Ln - 1, -1, -1):
+            rec = S["layers"][l]
+            if hx[l + 1] and "y0" in rec:
+                if rec["boundary"]:
+                    hx[l + 1 - R] = True
+                hp[l] = True
+                live += [(l, 0), (l, 1)]
+            if hp[l + 1] and "m2" in rec:
+                if rec["boundary"]:
+                    hp[l + 1 - R] = True
+                hx[l] = True
+                live += [(l, 2), (l, 3)]
+        for (l, u) in live:
+            for k in ("fc_lft.weight", "fc_lft.bias", "fc_rgt.weight", "fc_rgt.bias"):
+                G[_unit(l, u) + k] = new_grad(_unit(l, u) + k)
+        for n in ("obj_v_proj.weight", "obj_v_proj.bias", "obj_emb_proj.weight", "obj_emb_proj.bias", "sg_obj_embed.weight"):
+            G[n] = new_grad(n)
+        ops.gcn_backward(S, W_, d_xobj, G, live)
+        if reducer is not None:
+            reducer.bucket_done(2, G)
+            reducer.finish(G)
+        return G
     # ---- feature preparation ----
     if S["m_fc"] is not None:
         d_fc = ops.mul(d_fc, S["m_fc"])
