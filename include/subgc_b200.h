@@ -376,6 +376,8 @@ int subgc_log_softmax_fwd(int rows, int V1, const float* logits, float* logp, si
 int subgc_log_softmax_bwd(int rows, int V1, const float* logp, const float* dlogp, size_t ld, float* dlogits,
                           subgc_stream_t stream);
 int subgc_class_argmax(int rows, int n_classes, int skip_first, const float* dist, int64_t* cls, subgc_stream_t stream);
+/* Full-GC read-out (models/AttModel.py:146,200,265): out [B, L] = mean over the N nodes of x [B, N, L]. */
+int subgc_mean_nodes(int B, int N, int L, const float* x, float* out, subgc_stream_t stream);
 int subgc_sgpn_pool(const subgc_dims* d, const subgc_subgraph_layout* lay, const float* x_obj, const int64_t* gpn_obj_ind,
                     const float* att_masks, float* read_out, int32_t* sub_len, subgc_stream_t stream);
 int subgc_sgpn_bce(const subgc_subgraph_layout* lay, const float* score, float* loss, subgc_stream_t stream);

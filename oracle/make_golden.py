@@ -236,6 +236,56 @@ CASES = {
 }
 
 
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# Full-GC (train.sh:27-36: use_gpn=0, noun_fuse=0, pred_emb_type=2, gcn_layers=4, gcn_residual=1, gcn_bn=1): the reference's own
+# _sample on its no-sGPN branch (AttModel.py:261-271), eval mode (BatchNorm running statistics), one image
+# ------------------------------------------------------------------------------------------------------------------------------
+FULLGC_OPT = dict(use_gpn=0, noun_fuse=0, pred_emb_type=2, gcn_layers=4, gcn_residual=1, gcn_bn=1, test_LSTM=1)
+
+
+def run_fullgc_case(name, dims, seed, topk=False):
+    from subgc.fullgc import make_fullgc_state_dict
+    over = dict(FULLGC_OPT)
+    if topk:
+        over.update(use_topk_sampling=1, topk_temp=0.6, the_k=3)
+    opt = make_opt(dims, **over)
+    tmp = tempfile.mkdtemp()
+    opt.obj_name_path, opt.rel_name_path = os.path.join(tmp, "obj.npy"), os.path.join(tmp, "rel.npy")
+    np.save(opt.obj_name_path, np.array([f"o{i}" for i in range(dims.obj_classes)]))
+    np.save(opt.rel_name_path, np.array([f"p{i}" for i in range(dims.pred_classes)]))
+    model = ref_models.setup(opt)
+    sd = make_fullgc_state_dict(model, seed)
+    res = model.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    model.eval()
+    data = synth.make_test_inputs(dims, seed, n_images=1, per_half=1, ragged=False, ragged_edges=True)
+    args = synth.sample_args(data)
+    out = dict(meta_seed=seed, meta_dims=np.array(list(dims.as_dict().values()), np.int64), meta_topk=int(topk),
+               meta_state_keys=np.array(list(sd.keys())), meta_fp_weights=synth.fingerprint(sd),
+               meta_fp_inputs=synth.fingerprint([a for a in args if a is not None]))
+    with torch.no_grad():
+        x0, p0 = model.feat_fusion(data["obj_dist"], data["att_feats"], data["pred_dist"])
+        N, K, L = dims.obj_num, dims.rel_num, dims.gcn
+        x_obj5, _ = model.gcn_backbone(1, N, K, L, x0, data["obj_dist"], p0, data["rel_ind"])
+        read_out = torch.mean(x_obj5[0:1], 1)
+        g_fc = model.read_out_proj(read_out)
+        out.update(x0=np_(x0), p0=np_(p0), x_obj=np_(x_obj5[0]), g_fc=np_(g_fc))
+        if topk:   # the reference draws from torch's generator: record the uniforms of an equivalent inverse-CDF draw is not possible;
+            torch.manual_seed(1234)   # keep the reference's own sample + its log-probs for a statistical check only
+        margs = [a.clone() if torch.is_tensor(a) else a for a in args]   # the branch mutates att_masks in place (AttModel.py:269)
+        seq, lps, score, keep = model(*margs, opt={"beam_size": 1}, mode="sample")
+        out.update(seq=np_(seq), lps=np_(lps), score=np_(score), keep=np_(keep))
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print("wrote", name, {k: np.asarray(v).shape for k, v in out.items() if not k.startswith("meta")})
+
+
+FULLGC_SMALL = Dims(vocab=61, enc=24, rnn=40, att_hid=16, fc_feat=48, att_feat=48, gcn=24, low_rank=512, embed=12, obj_classes=23, pred_classes=7,
+                    gcn_layers=4, gcn_residual=1, pred_emb_type=2, seq_length=8, obj_num=37, rel_num=65)
+CASES["fullgc_small"] = lambda: run_fullgc_case("fullgc_small", FULLGC_SMALL, 41)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)

@@ -400,6 +400,22 @@ extern "C" int subgc_gcn_forward(const subgc_dims* d, const subgc_weights* w, in
     return SUBGC_OK;
 }
 
+// Full-GC read-out (models/AttModel.py:146,200,265: torch.mean(att_feats, 1)): out[b, c] = mean over the N nodes of x[b, n, c]
+__global__ void __launch_bounds__(256) mean_nodes_kernel(const float* __restrict__ x, float* __restrict__ out, int N, int L) {
+    const int b = blockIdx.x;
+    for (int c = threadIdx.x; c < L; c += blockDim.x) {
+        float a = 0.f;
+        for (int n = 0; n < N; ++n) a += x[((size_t)b * N + n) * L + c];   // ascending node order, as torch's reduction over a short dim
+        out[(size_t)b * L + c] = a / (float)N;
+    }
+}
+extern "C" int subgc_mean_nodes(int B, int N, int L, const float* x, float* out, subgc_stream_t stream) {
+    SUBGC_CHECK_ARG(x && out && B > 0 && N > 0 && L > 0, "subgc_mean_nodes: bad arguments");
+    mean_nodes_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, N, L);
+    SUBGC_LAUNCH_CHECK();
+    return SUBGC_OK;
+}
+
 extern "C" int subgc_class_argmax(int rows, int n_classes, int skip_first, const float* dist, int64_t* cls, subgc_stream_t stream) {
     SUBGC_CHECK_ARG(dist && cls && rows > 0 && n_classes > skip_first, "subgc_class_argmax: bad arguments");
     class_argmax_kernel<<<(rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(dist, rows, n_classes, skip_first ? 1 : 0,

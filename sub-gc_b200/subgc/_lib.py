@@ -156,6 +156,7 @@ SIGNATURES = {
     "subgc_unary": (_i, [_i, _sz, c_fp, c_fp, c_fp]),
     "subgc_scatter_add_rows": (_i, [_i, _i, c_fp, _i, c_fp, c_fp, _i, c_fp]),
     "subgc_lstm_cell_train_fwd": (_i, [_i, _i, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "subgc_mean_nodes": (_i, [_i, _i, _i, c_fp, c_fp, c_fp]),
     "subgc_frontend_backward_workspace_bytes": (_sz, [_P(Dims), _i, _i, _i, _i]),
     "subgc_prepare_backward": (_i, [_P(Dims), _P(Weights), _i, _i, _i, _P(PrepareSaved), c_fp, c_fp, c_fp, _P(PrepareGrads), c_fp, c_fp, _sz, c_fp]),
     "subgc_sgpn_backward": (_i, [_P(Dims), _P(Weights), _P(Layout), _P(SgpnSaved), _f, c_fp, c_fp, _P(SgpnGrads), c_fp, c_fp, _sz, c_fp]),

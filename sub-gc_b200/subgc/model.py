@@ -1084,7 +1084,11 @@ def setup(opt):
     import os
     if opt.caption_model != "topdown":
         raise Exception("Caption model not supported: {}".format(opt.caption_model))
-    model = TopDownModel(opt)
+    if getattr(opt, "use_gpn", 1) == 0:   # Full-GC (train.sh:27-36): no sGPN, full scene graph, BatchNorm in the GCN units
+        from .fullgc import FullGCModel
+        model = FullGCModel(opt)
+    else:
+        model = TopDownModel(opt)
     if vars(opt).get("start_from", None) is not None:
         assert os.path.isdir(opt.start_from), " %s must be a a path" % opt.start_from
         assert os.path.isfile(os.path.join(opt.start_from, "infos_" + opt.id + ".pkl")), \
