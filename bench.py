@@ -323,7 +323,7 @@ def main():
     lean = dict(zip(names, compact.needed_only(*[data[k] for k in names])))
     host = {k: (lean[k].pin_memory() if lean[k] is not None else None) for k in names}
     resident = {k: (host[k].to(dev) if host[k] is not None else None) for k in names}
-    host_cb = compact.compact_batch(*[data[k] for k in names]).pin_memory()
+    host_cb = compact.compact_batch(*[data[k] for k in names]).packed(pin=True)   # one pinned buffer: the upload is ONE host->device copy
     opt = {"beam_size": 5 if args.mode == "beam" else 1}
     if args.mode == "topk":
         opt["seed"] = SEED
@@ -345,7 +345,7 @@ def main():
     # reference-signature call, unread tensors not uploaded).
     copy_stream = torch.cuda.Stream(device=dev)
     dev_in = [{k: (torch.empty_like(resident[k]) if resident[k] is not None else None) for k in names} for _ in range(2)]
-    dev_cb = [host_cb.empty_like(dev) for _ in range(2)]
+    dev_cb = [host_cb.packed(device=dev, copy=False) for _ in range(2)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
 
     def prefetch(i, fmt):
@@ -366,7 +366,12 @@ def main():
             out = model(dev_cb[i % 2], opt=opt, mode="sample_compact")
         else:
             out = model(*[dev_in[i % 2][k] for k in names], opt=opt, mode="sample")
-        res = [t.to("cpu", non_blocking=True) if t.is_cuda else t for t in out]
+        hr = getattr(model, "last_host_results", None)
+        if hr is not None:
+            # the call itself read its whole result pack back (one device-to-host copy, see TopDownModel._sample_dyn): the host tensors
+            res = [hr["seq"], hr["seqLogprobs"], hr["subgraph_score"], hr["keep_ind"]]
+        else:
+            res = [t.to("cpu", non_blocking=True) if t.is_cuda else t for t in out]
         torch.cuda.synchronize()
         return res
 

@@ -35,16 +35,38 @@ class CompactBatch:
     def pin_memory(self):
         return CompactBatch(*[(getattr(self, f.name).pin_memory() if getattr(self, f.name) is not None else None) for f in fields(self)])
 
+    def empty_like(self, device):
+        return CompactBatch(*[(torch.empty_like(getattr(self, f.name), device=device) if getattr(self, f.name) is not None else None)
+                              for f in fields(self)])
+
+    def packed(self, device=None, pin=False, copy=True):
+        """The same batch with every field a view into ONE contiguous byte buffer (256-byte aligned fields): a host->device transfer of
+        the batch is then a single copy (`copy_` between two packed batches of the same shapes moves the buffer, not the fields)."""
+        present = [(f.name, getattr(self, f.name)) for f in fields(self) if getattr(self, f.name) is not None]
+        off, spec = 0, []
+        for name, t in present:
+            nb = t.numel() * t.element_size()
+            spec.append((name, t.dtype, tuple(t.shape), off, nb))
+            off += (nb + 255) // 256 * 256
+        dev = device if device is not None else present[0][1].device
+        buf = torch.empty(off, dtype=torch.uint8, device=dev, pin_memory=bool(pin) and torch.device(dev).type == "cpu")
+        views = {name: buf[o:o + nb].view(dt).view(shape) for name, dt, shape, o, nb in spec}
+        if copy:
+            for name, t in present:
+                views[name].copy_(t)
+        out = CompactBatch(**{f.name: views.get(f.name) for f in fields(self)})
+        out._buf, out._layout = buf, tuple((n, str(dt), sh, o) for n, dt, sh, o, _ in spec)
+        return out
+
     def copy_(self, other, non_blocking=False):
+        if getattr(self, "_buf", None) is not None and getattr(other, "_buf", None) is not None and self._layout == other._layout:
+            self._buf.copy_(other._buf, non_blocking=non_blocking)   # one transfer for the whole batch
+            return self
         for f in fields(self):
             a, b = getattr(self, f.name), getattr(other, f.name)
             if a is not None:
                 a.copy_(b, non_blocking=non_blocking)
         return self
-
-    def empty_like(self, device):
-        return CompactBatch(*[(torch.empty_like(getattr(self, f.name), device=device) if getattr(self, f.name) is not None else None)
-                              for f in fields(self)])
 
     def nbytes(self):
         return sum(getattr(self, f.name).numel() * getattr(self, f.name).element_size() for f in fields(self) if getattr(self, f.name) is not None)

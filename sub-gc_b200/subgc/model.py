@@ -266,6 +266,7 @@ class TopDownModel(nn.Module):
         self.last_gpn_loss = None
         self.last_image_of_row = None
         self.last_steps = None
+        self.last_host_results = None   # host copies of the most recent whole-call-graph results (see _sample_dyn)
         self._states = {}   # device index -> _DeviceState (shared by DataParallel replicas, which live on different devices)
         self.use_packed = True   # inference contractions read split-fp16 copies of the weights (subgc.packing)
         self.fused_loss = True   # LossWrapper in train mode: log-softmax + LanguageModelCriterion inside the decoder stage
@@ -830,7 +831,16 @@ class TopDownModel(nn.Module):
             self._ws = saved_ws
         # private copies of the results are queued BEFORE the host waits: the launches overlap with the graph's execution
         res = self._pack_views(plan.pack.clone(), plan.pack_spec)
-        st_h = outs["status"].cpu()   # the one host round trip of the call: (steps, fp16-range flag, rows, longest sub-graph)
+        # the one host round trip of the call: the whole result pack (32 KB at 128 rows) in ONE device-to-host copy -- status = (steps,
+        # fp16-range flag, rows, longest sub-graph) decides the shapes returned below, and callers that want the results on the host
+        # (eval loops do) find them in `last_host_results` without further copies (valid until the second next call with this shape)
+        if plan.host_pack is None:
+            plan.host_pack = [torch.empty(plan.pack.numel(), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        hp = plan.host_pack[plan.calls & 1]
+        hp.copy_(plan.pack, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        host = self._pack_views(hp, plan.pack_spec)
+        st_h = host["status"]
         steps, ovf, n_rows = int(st_h[0]), int(st_h[1]), int(st_h[2])
         if steps < 0:
             raise _lib.SubgcError(f"persistent decode kernel timed out (wait site {(-steps) // 1000}, CTA {(-steps) % 1000 - 1}); "
@@ -848,6 +858,8 @@ class TopDownModel(nn.Module):
         self.last_all_scores = outs["score"]
         self.last_image_of_row = res["image"][:n_rows]
         keep = res["keep"][:n_rows]
+        self.last_host_results = dict(seq=host["seq"][:n_rows], seqLogprobs=host["lps"][:n_rows], subgraph_score=host["sub_score"][:n_rows],
+                                      keep_ind=host["keep"][:n_rows], image=host["image"][:n_rows])
         keep_ind = keep if self.gpn_layer.use_nms else keep.to(outs["score"].dtype)
         return res["seq"][:n_rows], res["lps"][:n_rows], res["sub_score"][:n_rows], keep_ind
 
@@ -855,7 +867,7 @@ class TopDownModel(nn.Module):
         L, cd, T, N = lib(), self._cdims, self.seq_length, self.dims.obj_num
         plan = _DecodePlan(dev, self.dims, rows_cap, N)
         plan.ws_obj, plan.outs, plan.keepalive, plan.static_in = Workspace(), None, keepalive, static_in
-        plan.pack = plan.pack_spec = plan.pack_views = None
+        plan.pack = plan.pack_spec = plan.pack_views = plan.host_pack = None
         o = plan.out
         o["seq"] = torch.empty(rows_cap, T, dtype=torch.int64, device=dev)
         o["lps"] = torch.empty(rows_cap, T, device=dev)
@@ -867,6 +879,7 @@ class TopDownModel(nn.Module):
     def _sample_impl(self, front, opt):
         if not self.test_LSTM:
             raise _lib.SubgcError("mode='sample' needs a model built with opt.test_LSTM=1 (as test.py does)")
+        self.last_host_results = None
         dyn = self._dyn_eligible(front, opt)
         if dyn is not None:
             return self._sample_dyn(front, opt, *dyn)
