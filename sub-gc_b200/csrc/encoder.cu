@@ -156,6 +156,92 @@ __global__ void __launch_bounds__(256) gcn_node_update_kernel(const float* __res
     }
 }
 
+// Aggregate-then-transform for the node <- edges direction with folded unit weights: a unit's message is LINEAR in its source row
+// (graph_conv_unit.py:29-35: collect = A (W src + b), collect / (rowsum(A) + 1e-7)), so the segment mean over the edges of a node is taken
+// BEFORE the contraction: agg_s[b,n] = sum_{k: s_k = n} p[b,k] / (c_s + 1e-7) (ascending edge order), likewise agg_o; the contraction then
+// runs over 37 node rows per image instead of 65 edge rows (-43 % FLOPs for the layer), and the bias enters as b * c / (c + 1e-7).
+__global__ void __launch_bounds__(256) gcn_edge_aggregate_kernel(const float* __restrict__ p, const long long* __restrict__ rel_ind, float* __restrict__ agg_s,
+                                                                 float* __restrict__ agg_o, float* __restrict__ ratio, unsigned short* __restrict__ s16_hi,
+                                                                 unsigned short* __restrict__ s16_lo, unsigned short* __restrict__ o16_hi,
+                                                                 unsigned short* __restrict__ o16_lo, int* __restrict__ overflow, int N, int K, int L) {
+    extern __shared__ int s_list[];  // [2][K] edge lists of this node (ascending)
+    __shared__ int s_cnt[2];
+    __shared__ int s_wcnt[2][8];
+    const int bn = blockIdx.x;
+    const int b = bn / N, n = bn - b * N;
+    // order-preserving compaction of the edges whose subject / object is this node: ballot + prefix counts (K <= 256)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int k = threadIdx.x;
+    const bool fs = k < K && (int)rel_ind[((size_t)b * K + k) * 2] == n;
+    const bool fo = k < K && (int)rel_ind[((size_t)b * K + k) * 2 + 1] == n;
+    const unsigned ms_ = __ballot_sync(0xffffffffu, fs), mo_ = __ballot_sync(0xffffffffu, fo);
+    if (lane == 0) { s_wcnt[0][wid] = __popc(ms_); s_wcnt[1][wid] = __popc(mo_); }
+    __syncthreads();
+    {
+        int off_s = 0, off_o = 0;
+        for (int w2 = 0; w2 < wid; ++w2) { off_s += s_wcnt[0][w2]; off_o += s_wcnt[1][w2]; }
+        const unsigned lt = (1u << lane) - 1u;
+        if (fs) s_list[off_s + __popc(ms_ & lt)] = k;
+        if (fo) s_list[K + off_o + __popc(mo_ & lt)] = k;
+        if (threadIdx.x == 0) {
+            int cs_ = 0, co_ = 0;
+            for (int w2 = 0; w2 < 8; ++w2) { cs_ += s_wcnt[0][w2]; co_ += s_wcnt[1][w2]; }
+            s_cnt[0] = cs_; s_cnt[1] = co_;
+        }
+    }
+    __syncthreads();
+    const int cs = s_cnt[0], co = s_cnt[1];
+    const float ds = (float)cs + 1e-7f, dob = (float)co + 1e-7f;
+    if (threadIdx.x == 0) { ratio[2 * (size_t)bn] = (float)cs / ds; ratio[2 * (size_t)bn + 1] = (float)co / dob; }
+    const float* pb = p + (size_t)b * K * L;
+    const int L4 = L >> 2;   // L % 4 == 0 (checked by the caller)
+    for (int c4 = threadIdx.x; c4 < L4; c4 += blockDim.x) {
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+            const int cnt = which ? co : cs;
+            const int* lst = s_list + which * K;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < cnt; i += 8) {   // eight independent 16-byte loads in flight, added in ascending edge order
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    v[u] = (i + u < cnt) ? __ldg(reinterpret_cast<const float4*>(pb + (size_t)lst[i + u] * L) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (i + u < cnt) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
+            }
+            const float dv = which ? dob : ds;
+            a.x /= dv; a.y /= dv; a.z /= dv; a.w /= dv;
+            if (agg_s) reinterpret_cast<float4*>((which ? agg_o : agg_s) + (size_t)bn * L)[c4] = a;   // fp32 copy only when a contraction reads it
+            unsigned short* h16 = which ? o16_hi : s16_hi;
+            if (h16) {
+                unsigned short* l16 = which ? o16_lo : s16_lo;
+                unsigned short hh[4], hl[4];
+                int ovf = 0;
+                split_f16(a.x, hh[0], hl[0], ovf); split_f16(a.y, hh[1], hl[1], ovf); split_f16(a.z, hh[2], hl[2], ovf); split_f16(a.w, hh[3], hl[3], ovf);
+                const size_t o = (size_t)bn * L + 4 * c4;
+                *reinterpret_cast<uint2*>(h16 + o) = make_uint2((uint32_t)hh[0] | ((uint32_t)hh[1] << 16), (uint32_t)hh[2] | ((uint32_t)hh[3] << 16));
+                *reinterpret_cast<uint2*>(l16 + o) = make_uint2((uint32_t)hl[0] | ((uint32_t)hl[1] << 16), (uint32_t)hl[2] | ((uint32_t)hl[3] << 16));
+                if (ovf && overflow) atomicOr(overflow, 1);
+            }
+        }
+    }
+}
+// x_new[bn, c] = 0.5 * ( relu((Y_s + b0 * r_s) * inv) + relu((Y_o + b1 * r_o) * inv) ) (+ residual);  y [B*N, 2L] = [Y_s | Y_o], bias [2L]
+__global__ void __launch_bounds__(256) gcn_node_finish_kernel(const float* __restrict__ y, const float* __restrict__ bias, const float* __restrict__ ratio,
+                                                              float inv, const float* __restrict__ res, float* __restrict__ out, int L) {
+    const size_t bn = blockIdx.x;
+    const float rs = ratio[2 * bn], ro = ratio[2 * bn + 1];
+    const float* yr = y + bn * 2 * L;
+    for (int c = threadIdx.x; c < L; c += blockDim.x) {
+        const float vs = fmaxf((yr[c] + __ldg(bias + c) * rs) * inv, 0.f);
+        const float vo = fmaxf((yr[L + c] + __ldg(bias + L + c) * ro) * inv, 0.f);
+        float v = (vs + vo) * 0.5f;
+        if (res) v += res[bn * L + c];
+        out[bn * L + c] = v;
+    }
+}
+
 static int check_dims(const subgc_dims* d) {
     SUBGC_CHECK_ARG(d != nullptr, "dims is null");
     SUBGC_CHECK_ARG(d->gcn > 0 && d->low_rank > 0 && d->att_feat > 0 && d->embed > 0 && d->obj_num > 1 && d->rel_num > 0 &&
@@ -196,6 +282,8 @@ static size_t gcn_ws_bytes(const subgc_dims* d, int B) {
     b += 2 * align_up(rows * (size_t)((d->gcn + 7) & ~7) * 2, 256) + 1024;   // split-fp16 copy of a layer input shared by two units
     b += 2 * align_up(rows * (size_t)((d->low_rank + 7) & ~7) * 2, 256) + 1024;   // split-fp16 copy of T written by the fc_lft contraction
     b += 4 * align_up((size_t)B * d->rel_num * (size_t)((d->gcn + 7) & ~7) * 2, 256) + 1024;   // split-fp16 copies (two sets) of the edge stream written by the edge update kernel
+    // aggregate-then-transform (folded node <- edges direction): two aggregated inputs, their split copies, count ratios
+    b += 2 * align_up((size_t)B * d->obj_num * d->gcn * 4, 256) + 4 * align_up((size_t)B * d->obj_num * d->gcn * 2, 256) + align_up((size_t)B * d->obj_num * 8, 256) + 1024;
     return b;
 }
 
@@ -335,6 +423,17 @@ extern "C" int subgc_gcn_forward(const subgc_dims* d, const subgc_weights* w, in
     unsigned short* n16_hi[2] = {fuse16 ? ws.take<unsigned short>((size_t)B * K * L) : nullptr, fuse16 ? ws.take<unsigned short>((size_t)B * K * L) : nullptr};
     unsigned short* n16_lo[2] = {fuse16 ? ws.take<unsigned short>((size_t)B * K * L) : nullptr, fuse16 ? ws.take<unsigned short>((size_t)B * K * L) : nullptr};
     const unsigned short *cur16_hi = nullptr, *cur16_lo = nullptr;   // split copy of the current edge stream p, if its producer wrote one
+    // aggregate-then-transform buffers (folded node <- edges direction)
+    static const bool agg_off = getenv("SUBGC_GCN_AGG") != nullptr && getenv("SUBGC_GCN_AGG")[0] == '0';
+    bool any_fold0 = false;
+    for (int l = 0; l < Ln; ++l) any_fold0 = any_fold0 || (w->gcn_fold[l][0].w != nullptr && w->gcn_fold_scale[l][0] > 0.f);
+    const bool agg = any_fold0 && !agg_off && (L & 3) == 0;
+    float* agg_s = agg ? ws.take<float>(xn) : nullptr;
+    float* agg_o = agg ? ws.take<float>(xn) : nullptr;
+    float* agg_ratio = agg ? ws.take<float>((size_t)2 * B * N) : nullptr;
+    unsigned short* ag16[4] = {nullptr, nullptr, nullptr, nullptr};   // s_hi, s_lo, o_hi, o_lo
+    if (agg && fuse16)
+        for (int i = 0; i < 4; ++i) ag16[i] = ws.take<unsigned short>(xn);
     const float* x = x0;
     const float* p = p0;
     const float* x_res = x0;
@@ -365,23 +464,45 @@ extern "C" int subgc_gcn_forward(const subgc_dims* d, const subgc_weights* w, in
                 SUBGC_TRY(linear(w, T, B * N, R, w->gcn_rgt[l][3], L, Mb, ws, st, t16_hi, t16_lo, R));
             }
             next16 = fuse16 && !last && need_x[l + 2];   // layer l+1 contracts this edge stream (its units 0, 1 produce x of layer l+2)
+            if (agg && !last && w->gcn_fold[l + 1][0].w != nullptr && w->gcn_fold_scale[l + 1][0] > 0.f) next16 = false;   // ... unless it aggregates first
             gcn_edge_update_kernel<<<B * K, 256, 0, st>>>(folded ? M2 : Ma, folded ? M2 + L : Mb, rel, boundary ? p_res : nullptr, p_next, B, N, K, L,
                                                           next16 ? n16_hi[l & 1] : nullptr, next16 ? n16_lo[l & 1] : nullptr, L, w->h3_overflow,
                                                           folded ? 2 * L : L, folded ? 1.f / w->gcn_fold_scale[l][1] : 1.f);
             SUBGC_LAUNCH_CHECK();
         }
         if (x_next) {  // units 0,1: node <- edges (graph_conv.py:22-26)
+            const subgc_linear& fold = w->gcn_fold[l][0];
+            const bool folded = fold.w != nullptr && w->gcn_fold_scale[l][0] > 0.f;
             const unsigned short *ph = nullptr, *pl = nullptr;
             int pld = 0;
-            if (cur16_hi) {   // the edge update of the previous layer already wrote the split copy of this input
+            if (folded && agg) {
+                // the aggregation kernel reads the fp32 edge stream: no split copy of p is needed
+            } else if (cur16_hi) {   // the edge update of the previous layer already wrote the split copy of this input
                 ph = cur16_hi; pl = cur16_lo; pld = L;
             } else if (split_region) {
                 Workspace sw(split_region, split_bytes);
                 if (!h3_presplit(p, B * K, L, L, w, sw, st, &ph, &pl, &pld)) ph = pl = nullptr;
             }
-            const subgc_linear& fold = w->gcn_fold[l][0];
-            const bool folded = fold.w != nullptr && w->gcn_fold_scale[l][0] > 0.f;
-            if (folded) {
+            if (folded && agg) {
+                // aggregate first (37 node rows per image instead of 65 edge rows), one contraction per unit, bias / ReLU / mean of both after
+                GemmProblem gp[2];
+                bool all16 = ag16[0] != nullptr;
+                for (int u = 0; u < 2; ++u) {
+                    gp[u].M = B * N; gp[u].N = L; gp[u].nseg = 1;
+                    gp[u].seg[0] = make_seg(u ? agg_o : agg_s, L, fold.w + (size_t)u * L * L, L, L);
+                    if (ag16[0]) { gp[u].seg[0].A16_hi = ag16[2 * u]; gp[u].seg[0].A16_lo = ag16[2 * u + 1]; gp[u].seg[0].lda16 = L; }
+                    gp[u].C = M2 + (size_t)u * L; gp[u].ldc = 2 * L;
+                    resolve_packs(gp[u], w);
+                    all16 = all16 && h3_eligible(gp[u]);   // the contraction will read the split copy only
+                }
+                SUBGC_CHECK_ARG(K <= 256, "subgc_gcn_forward: at most 256 edges per image");
+                gcn_edge_aggregate_kernel<<<B * N, 256, 2 * K * sizeof(int), st>>>(p, rel, all16 ? nullptr : agg_s, all16 ? nullptr : agg_o, agg_ratio, ag16[0],
+                                                                                   ag16[1], ag16[2], ag16[3], w->h3_overflow, N, K, L);
+                SUBGC_LAUNCH_CHECK();
+                for (int u = 0; u < 2; ++u) SUBGC_TRY(launch_gemm(gp[u], ws.cursor(), ws.remaining(), st));
+                gcn_node_finish_kernel<<<B * N, 256, 0, st>>>(M2, fold.b, agg_ratio, 1.f / w->gcn_fold_scale[l][0], boundary ? x_res : nullptr, x_next, L);
+                SUBGC_LAUNCH_CHECK();
+            } else if (folded) {
                 SUBGC_TRY(linear(w, p, B * K, L, fold, 2 * L, M2, ws, st, ph, pl, pld));
             } else {
                 SUBGC_TRY(linear(w, p, B * K, L, w->gcn_lft[l][0], R, T, ws, st, ph, pl, pld, t16_hi, t16_lo, R));
@@ -389,9 +510,11 @@ extern "C" int subgc_gcn_forward(const subgc_dims* d, const subgc_weights* w, in
                 SUBGC_TRY(linear(w, p, B * K, L, w->gcn_lft[l][1], R, T, ws, st, ph, pl, pld, t16_hi, t16_lo, R));
                 SUBGC_TRY(linear(w, T, B * K, R, w->gcn_rgt[l][1], L, Mb, ws, st, t16_hi, t16_lo, R));
             }
-            gcn_node_update_kernel<<<B * N, 256, 4 * K * sizeof(int), st>>>(folded ? M2 : Ma, folded ? M2 + L : Mb, rel, boundary ? x_res : nullptr, x_next,
-                                                                            B, N, K, L, folded ? 2 * L : L, folded ? 1.f / w->gcn_fold_scale[l][0] : 1.f);
-            SUBGC_LAUNCH_CHECK();
+            if (!(folded && agg)) {
+                gcn_node_update_kernel<<<B * N, 256, 4 * K * sizeof(int), st>>>(folded ? M2 : Ma, folded ? M2 + L : Mb, rel, boundary ? x_res : nullptr, x_next,
+                                                                                B, N, K, L, folded ? 2 * L : L, folded ? 1.f / w->gcn_fold_scale[l][0] : 1.f);
+                SUBGC_LAUNCH_CHECK();
+            }
         }
         cur16_hi = next16 ? n16_hi[l & 1] : nullptr; cur16_lo = next16 ? n16_lo[l & 1] : nullptr;
         x = x_next; p = p_next;
