@@ -865,12 +865,18 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                     lp = (m - m) - lz;
                 } else {   // top-k sampling: q = log_softmax(logp / temp), keep the k best, Categorical over them (AttModel.py:296-303)
                     const float ym = ((m - m) - lz) / p.temp;
+                    // the scaled log-probs are evaluated ONCE per element (one division each; the same expression as before, so the same
+                    // bits): v[i] <- (logp / temp) - max, then <- q = that - log(sum) for the k selection rounds
                     float s2 = 0.f;
 #pragma unroll
-                    for (int i = 0; i < MG_SELVALS; ++i)
-                        if (wt + i * MG_NW < V1) s2 += expf(((v[i] - m) - lz) / p.temp - ym);
+                    for (int i = 0; i < MG_SELVALS; ++i) {
+                        v[i] = ((v[i] - m) - lz) / p.temp - ym;
+                        if (wt + i * MG_NW < V1) s2 += expf(v[i]);
+                    }
                     s2 = workers_sum(s2, ctl, wt);
                     const float lz2 = logf(s2);
+#pragma unroll
+                    for (int i = 0; i < MG_SELVALS; ++i) v[i] -= lz2;
                     unsigned taken = 0;
                     for (int c = 0; c < p.top_k; ++c) {
                         float cv = -INFINITY;
@@ -879,7 +885,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                         for (int i = 0; i < MG_SELVALS; ++i) {
                             const int j = wt + i * MG_NW;
                             if (j >= V1 || ((taken >> i) & 1u)) continue;
-                            const float qv = (((v[i] - m) - lz) / p.temp - ym) - lz2;
+                            const float qv = v[i];
                             if (qv > cv || ci == 0x7fffffff) { cv = qv; ci = j; }
                         }
                         workers_argmax(cv, ci, ctl, wt);
