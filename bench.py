@@ -488,6 +488,20 @@ def main():
                             "tensor": dict(tens, frac=tens["achieved"] / tens["peak"],
                                            note="3 x algorithmic flops: every fp32 product is three fp16 tensor-core products (hi.hi, hi.lo, lo.hi) "
                                                 "with fp32 accumulation in TMEM")}
+    if "encode" in stage_ms and "roofline" in line:
+        # front-end: tensor-bound.  Executed contraction work per image with folded units and the node <- edges layer
+        # aggregated before its contraction: fusion 37 x (2048 + 300) x 1024, L0 37 x 1024 x 2048, L1 2 x 37 x 1024 x 1024,
+        # sGPN / prepare as BASELINE.md counts them; every fp32 product = 3 fp16 tensor-core products
+        enc_flops = IMAGES_PER_GPU * 2.0 * (37 * 2348 * 1024 + 37 * 1024 * 2048 + 2 * 37 * 1024 * 1024)
+        prep_flops = n_rows * 132.2e6
+        t_enc, t_prep = stage_ms["encode"] / args.steps * 1e-3, stage_ms.get("prepare", 0.0) / args.steps * 1e-3
+        line["roofline"]["front_end"] = {
+            "bound": "tensor", "peak": tf_peak, "unit": "TFLOP/s",
+            "encode": {"ms": t_enc * 1e3, "executed_flops": enc_flops, "achieved": 3 * enc_flops / t_enc / 1e12, "frac": 3 * enc_flops / t_enc / 1e12 / tf_peak},
+            "prepare": {"ms": t_prep * 1e3, "executed_flops": prep_flops, "achieved": 3 * prep_flops / max(t_prep, 1e-9) / 1e12,
+                        "frac": 3 * prep_flops / max(t_prep, 1e-9) / 1e12 / tf_peak},
+            "note": "stage time includes the non-contraction kernels (splits, segment means, pooling); per-kernel tensor-pipe activity: "
+                    "profiles/r02c_ncu_encoder.md"}
     if not args.no_cpu_baseline:
         n_sample = 16 if args.mode == "beam" else IMAGES_PER_GPU
         ref = reference_arm(d, sd, data, args.mode, 1, 1, cores, n_sample, check_seq=out[0])

@@ -22,3 +22,10 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:mega
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${R}_ncu_mega.log 2>&1
 ncu -i gpurun_out/${R}_mega.ncu-rep --page raw --csv > gpurun_out/${R}_mega_raw.csv 2>/dev/null
 python tools/ncu_pick.py gpurun_out/${R}_mega_raw.csv > gpurun_out/${R}_mega_pick.txt 2>&1; cat gpurun_out/${R}_mega_pick.txt | cut -c1-160
+# front-end: one full capture of the three big encoder contractions (fusion, folded L0, one of the aggregated L1 pair): tensor-pipe activity
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:h3_gemm_kernel -s 36 -c 4 -f -o gpurun_out/${R}_encoder \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${R}_ncu_encoder.log 2>&1
+ncu -i gpurun_out/${R}_encoder.ncu-rep --page raw --csv > gpurun_out/${R}_encoder_raw.csv 2>/dev/null
+python tools/ncu_pick.py gpurun_out/${R}_encoder_raw.csv > gpurun_out/${R}_encoder_pick.txt 2>&1; cut -c1-200 gpurun_out/${R}_encoder_pick.txt | head -60
+timeout 300 python tools/graph_kernels.py greedy > gpurun_out/${R}_graph_kernels.txt 2>&1; tail -3 gpurun_out/${R}_graph_kernels.txt
+timeout 300 python tools/train_profile.py 32 > gpurun_out/${R}_train_profile.txt 2>&1; head -3 gpurun_out/${R}_train_profile.txt

@@ -38,3 +38,10 @@ if len(idx) >= 2:
         json.dump({"dram_bytes_per_decode_loop": 20 * sb, "dram_bytes_per_step": sb,
                    "note": "dram__bytes_read+write summed over the launches of one decode step (ncu, cold-cache replay, graphs off) x 20 steps"},
                   open(sys.argv[2], "w"))
+mega = [r for r in rows if "mega_decode_kernel" in r["name"]]
+if mega and len(sys.argv) > 2:   # persistent decode kernel: one launch IS the decode loop of a call
+    b = sum(r["rd"] + r["wr"] for r in mega) / len(mega)
+    print(f"\npersistent decode kernel: {len(mega)} launches, avg {sum(r['t'] for r in mega) / len(mega) / 1e3:.1f} us, avg DRAM {b / 1e6:.1f} MB per launch")
+    json.dump({"dram_bytes_per_decode_loop": b, "dram_bytes_per_step": b / 20,
+               "note": "dram__bytes_read+write of one mega_decode_kernel launch (= the 20-step decode loop of one call), ncu launch list, "
+                       "average over the captured launches"}, open(sys.argv[2], "w"))
