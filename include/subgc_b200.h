@@ -176,6 +176,9 @@ int subgc_pack_weight(int rows, int cols, const float* w, int ldw, int n_seg, co
  * parameters in `w`; `overflow` (device, nullable) is OR-ed with 1 when a weight does not fit fp16.  Re-pack after the parameters
  * change.  Not capturable (copies the tables from host memory). */
 size_t subgc_mega_pack_bytes(const subgc_dims* d, int n_cta);
+/* Bench / profiling: with `on`, every eager (not graph-captured) launch of the persistent kernel by this thread is bracketed by CUDA events
+ * on its stream; last_ms (nullable) receives the duration of the most recent one (blocks until it finished; -1 if none). */
+int subgc_mega_timing(int on, float* last_ms);
 int subgc_mega_pack(const subgc_dims* d, const subgc_weights* w, int n_cta, void* buf, size_t bytes, int32_t* overflow,
                     subgc_stream_t stream);
 

@@ -1215,6 +1215,9 @@ static unsigned long long* mega_trace_buffer(size_t* elems) {
     return buf;
 }
 
+struct MgTiming { bool on = false, pending = false; cudaEvent_t e0 = nullptr, e1 = nullptr; };
+static MgTiming& mega_timing() { static thread_local MgTiming t; return t; }
+
 bool mega_enabled() {
     static int on = -1;
     if (on < 0) { const char* e = getenv("SUBGC_MEGA"); on = (e && e[0] == '0') ? 0 : 1; }
@@ -1280,7 +1283,17 @@ int launch_mega_decode(const subgc_dims* d, const subgc_weights* w, int S, int l
     at[0].id = cudaLaunchAttributeCooperative;   // every CTA must be resident: they wait for each other
     at[0].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
+    // bench / profiling (subgc_mega_timing): CUDA events around this launch alone, on the launching stream (not while capturing a graph)
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    MgTiming& tm = mega_timing();
+    const bool timed = tm.on && cap == cudaStreamCaptureStatusNone;
+    if (timed) {
+        if (!tm.e0) { cudaEventCreate(&tm.e0); cudaEventCreate(&tm.e1); }
+        cudaEventRecord(tm.e0, st);
+    }
     SUBGC_CUDA(cudaLaunchKernelEx(&cfg, mega_decode_kernel, p));
+    if (timed) { cudaEventRecord(tm.e1, st); tm.pending = true; }
     SUBGC_LAUNCH_CHECK();
     return SUBGC_OK;
 }
@@ -1295,6 +1308,17 @@ extern "C" int subgc_debug_mega_trace(unsigned long long* host_out, int n_cta, i
     if (!buf || !host_out || (size_t)n_cta * n_steps * MG_TRACE_EVENTS > n) return SUBGC_E_INVALID;
     cudaDeviceSynchronize();
     return cudaMemcpy(host_out, buf, (size_t)n_cta * n_steps * MG_TRACE_EVENTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess ? SUBGC_OK : SUBGC_E_CUDA;
+}
+
+extern "C" int subgc_mega_timing(int on, float* last_ms) {
+    MgTiming& tm = mega_timing();
+    if (last_ms) {
+        *last_ms = -1.f;
+        if (tm.pending && tm.e0 && tm.e1 && cudaEventSynchronize(tm.e1) == cudaSuccess) cudaEventElapsedTime(last_ms, tm.e0, tm.e1);
+        tm.pending = false;
+    }
+    tm.on = on != 0;
+    return SUBGC_OK;
 }
 
 extern "C" size_t subgc_mega_pack_bytes(const subgc_dims* d, int n_cta) {

@@ -225,18 +225,24 @@ __global__ void __launch_bounds__(256) attention_train_fwd_kernel(const float* _
 //   d_alpha_n = dctx . att_n ; d_w_n = (d_alpha_n - sum_k alpha_k d_alpha_k) / Z ; d_s_n = d_w_n m_n ; d_e_n = s_n (d_s_n - sum_k s_k d_s_k)
 //   d_att_n += alpha_n dctx ; u_nj = tanh(p_att_nj + atth_j) ; d_pre_nj = d_e_n w_j (1 - u^2) ; d_p_att_nj += d_pre_nj ;
 //   d_atth_j = sum_n d_pre_nj ; d_w_row_j = sum_n d_e_n u_nj  (per-row partial of alpha_net.weight's gradient)
+constexpr int kAttBwdParts = 4;   // blocks per row: 160 rows alone leave most of the 148 SMs with one 8-warp block (measured 146 us per launch)
+__device__ __forceinline__ float fast_tanh_(float x) {   // ex2-based, |err| <= 2e-7 (the forward's scores use the same form)
+    const float e = __expf(-2.f * fabsf(x));
+    return copysignf(__fdividef(1.f - e, 1.f + e), x);
+}
 __global__ void __launch_bounds__(256) attention_bwd_kernel(const float* __restrict__ atth, const float* __restrict__ p_att,
                                                             const float* __restrict__ att, const float* __restrict__ masks,
                                                             const float* __restrict__ alpha_w, const float* __restrict__ alpha,
                                                             const float* __restrict__ sm, const float* __restrict__ dctx,
                                                             float* __restrict__ d_att, float* __restrict__ d_p_att, float* __restrict__ d_atth,
                                                             float* __restrict__ d_w_rows, int len, int H, int AH, int ld_dctx) {
-    extern __shared__ float s_b[];  // [len] d_e | [len] alpha | [32] red
-    float* s_de = s_b; float* s_al = s_b + len; float* red = s_b + 2 * len;
-    const int r = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    extern __shared__ float s_b[];  // [len] d_e | [len] alpha | [2 * 256] partials of the two node halves
+    float* s_de = s_b; float* s_al = s_b + len; float* s_part = s_b + 2 * len;
+    const int r = blockIdx.x, part = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const float* af = att + (size_t)r * len * H;
     const float* dc = dctx + (size_t)r * ld_dctx;   // dctx may be a column block of a wider gradient
-    for (int n = wid; n < len; n += nw) {  // d_alpha_n
+    // every block of the row needs d(e): the len dot products d_alpha_n = <dctx, att_n> and the softmax / mask / renormalise backward
+    for (int n = wid; n < len; n += nw) {
         float a = 0.f;
         for (int j = lane; j < H; j += 32) a = fmaf(dc[j], af[(size_t)n * H + j], a);
         a = warp_sum(a);
@@ -260,27 +266,43 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(const float* __restr
         for (int n = lane; n < len; n += 32) s_de[n] = sm[(size_t)r * len + n] * (s_de[n] - dot2);
     }
     __syncthreads();
+    // d_att += alpha_n dctx: this block's quarter of the row's len x H elements
     float* da = d_att + (size_t)r * len * H;
-    for (int idx = threadIdx.x; idx < len * H; idx += blockDim.x) {
-        int n = idx / H, j = idx - n * H;
+    const int total = len * H, chunk = (total + kAttBwdParts - 1) / kAttBwdParts;
+    const int hi = min(total, (part + 1) * chunk);
+    for (int idx = part * chunk + threadIdx.x; idx < hi; idx += blockDim.x) {
+        const int n = idx / H, j = idx - n * H;
         da[idx] += s_al[n] * dc[j];
     }
+    // attention-hidden columns: this block's quarter of AH, the two thread halves take the two halves of the nodes
     const float* pa = p_att + (size_t)r * len * AH;
     float* dpa = d_p_att + (size_t)r * len * AH;
-    for (int j = threadIdx.x; j < AH; j += blockDim.x) {
-        const float hj = atth[(size_t)r * AH + j], wj = alpha_w[j];
+    const int jw = (AH + kAttBwdParts - 1) / kAttBwdParts;            // columns per block
+    const int half = threadIdx.x >> 7, tj = threadIdx.x & 127;
+    const int n0 = half ? (len + 1) / 2 : 0, n1 = half ? len : (len + 1) / 2;
+    for (int j0 = part * jw; j0 < min(AH, (part + 1) * jw); j0 += 128) {
+        const int j = j0 + tj;
+        const bool live = j < min(AH, (part + 1) * jw);
         float dh = 0.f, dw = 0.f;
-        for (int n = 0; n < len; ++n) {
-            float u = tanhf(pa[(size_t)n * AH + j] + hj);
-            float dpre = s_de[n] * wj * (1.f - u * u);
-            dpa[(size_t)n * AH + j] += dpre;
-            dh += dpre;
-            dw = fmaf(s_de[n], u, dw);
+        if (live) {
+            const float hj = atth[(size_t)r * AH + j], wj = alpha_w[j];
+#pragma unroll 6
+            for (int n = n0; n < n1; ++n) {
+                const float u = fast_tanh_(pa[(size_t)n * AH + j] + hj);
+                const float dpre = s_de[n] * wj * (1.f - u * u);
+                dpa[(size_t)n * AH + j] += dpre;
+                dh += dpre;
+                dw = fmaf(s_de[n], u, dw);
+            }
         }
-        d_atth[(size_t)r * AH + j] = dh;
-        d_w_rows[(size_t)r * AH + j] = dw;
+        s_part[half * 256 + tj] = dh; s_part[half * 256 + 128 + tj] = dw;
+        __syncthreads();
+        if (half == 0 && live) {
+            d_atth[(size_t)r * AH + j] = s_part[tj] + s_part[256 + tj];
+            d_w_rows[(size_t)r * AH + j] = s_part[128 + tj] + s_part[256 + 128 + tj];
+        }
+        __syncthreads();
     }
-    (void)red;
 }
 
 // dlogits = dlogp - exp(logp) * rowsum(dlogp)
@@ -526,8 +548,8 @@ extern "C" int subgc_attention_bwd(int S, int len, int H, int AH, const float* a
     SUBGC_CHECK_ARG(atth && p_att && att && masks && alpha_w && alpha && sm && dctx && d_att && d_p_att && d_atth && d_w_rows && S > 0 &&
                         len > 0 && len <= 64,
                     "subgc_attention_bwd: bad arguments");
-    attention_bwd_kernel<<<S, 256, (size_t)(2 * len + 32) * 4, ST>>>(atth, p_att, att, masks, alpha_w, alpha, sm, dctx, d_att, d_p_att, d_atth,
-                                                                      d_w_rows, len, H, AH, H);
+    attention_bwd_kernel<<<dim3(S, kAttBwdParts), 256, (size_t)(2 * len + 512) * 4, ST>>>(atth, p_att, att, masks, alpha_w, alpha, sm, dctx, d_att,
+                                                                                           d_p_att, d_atth, d_w_rows, len, H, AH, H);
     SUBGC_LAUNCH_CHECK();
     return SUBGC_OK;
 }
@@ -937,7 +959,7 @@ extern "C" int subgc_decoder_train_backward(const subgc_dims* d, const subgc_wei
         SUBGC_TRY(gemm1(R, 3 * H, 4 * H, dg2_t, 4 * H, wt_lang, 4 * H, nullptr, 0, d_xl, 3 * H, gws, gws_bytes, st));
         // attention backward (d_att / d_p_att accumulate over the steps)
         float* d_atth_t = d_atth + (size_t)t * R * AH;
-        attention_bwd_kernel<<<R, 256, (size_t)(2 * len + 32) * 4, st>>>(b->atth + (size_t)t * R * AH, b->p_att, b->att, b->masks, w->alpha_net.w,
+        attention_bwd_kernel<<<dim3(R, kAttBwdParts), 256, (size_t)(2 * len + 512) * 4, st>>>(b->atth + (size_t)t * R * AH, b->p_att, b->att, b->masks, w->alpha_net.w,
                                                                          b->alpha + (size_t)t * R * len, b->sm + (size_t)t * R * len, d_xl, d_att, d_p_att,
                                                                          d_atth_t, d_wrows + (size_t)t * R * AH, len, H, AH, 3 * H);
         SUBGC_LAUNCH_CHECK();

@@ -112,6 +112,7 @@ SIGNATURES = {
     "subgc_pack_elems": (_sz, [_i, _i, C.POINTER(C.c_int32)]),
     "subgc_pack_weight": (_i, [_i, _i, c_fp, _i, _i, C.POINTER(C.c_int32), c_fp, c_fp, c_fp, c_fp]),
     "subgc_linear_packed_forward": (_i, [_i, _i, _i, c_fp, _i, c_fp, _P(Packed), c_fp, _i, c_fp, _i, c_fp, _sz, c_fp]),
+    "subgc_mega_timing": (_i, [_i, _P(_f)]),
     "subgc_mega_pack_bytes": (_sz, [_P(Dims), _i]),
     "subgc_mega_pack": (_i, [_P(Dims), _P(Weights), _i, c_fp, _sz, c_fp, c_fp]),
     "subgc_linear_workspace_bytes": (_sz, [_i, _i, _i]),
