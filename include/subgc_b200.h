@@ -133,6 +133,10 @@ typedef struct subgc_weights {
      * exactly when the messages are consumed).  The same FLOPs as the low-rank pair, one contraction instead of four per direction. */
     subgc_linear gcn_fold[SUBGC_MAX_GCN_LAYERS][2];
     float gcn_fold_scale[SUBGC_MAX_GCN_LAYERS][2];
+    /* read_out_proj.0 -> read_out_proj.1 -> fc_embed.0 are three Linears in a row (models/lib/gpn.py:35-36, models/AttModel.py:109):
+     *   prep_fold.w = W_fc0 W_ro1 W_ro0  [FC, 2L],  prep_fold.b = W_fc0 (W_ro1 b_ro0 + b_ro1) + b_fc0  [FC]
+     * used by subgc_prepare_forward when the caller does not ask for g_fc (the reference's intermediate `fc_feats`). */
+    subgc_linear prep_fold;
 } subgc_weights;
 
 /* How sub-graph s of a flat list maps onto the loader tensors gpn_obj_ind / att_masks [rows,2,per_half,N].
@@ -261,7 +265,8 @@ int subgc_rank_rows(int n_rows, const float* score, const int64_t* image_of_row,
 /* ---------------------------------------------------------------------------------------------------------
  * Decoder feature preparation: replaces gpn read_out_proj (models/lib/gpn.py:79,95), AttModel.clip_att /
  * _prepare_feature / pack_wrapper (models/AttModel.py:16-36,348-368) for the n_rows selected sub-graphs `sel`:
- *    g_fc  = W_b(W_a read_out[sel] + b_a) + b_b                      [n_rows, 2L]   (reference `fc_feats`)
+ *    g_fc  = W_b(W_a read_out[sel] + b_a) + b_b                      [n_rows, 2L]   (reference `fc_feats`; NULL: not wanted --
+ *            with w->prep_fold the three Linears up to fc_embed.0 are then ONE contraction)
  *    fc    = relu(W2 relu(W1 g_fc + b1) + b2)                        [n_rows, H]
  *    att   = relu(W_a x_obj[image, ids[n]] + b_a) for n < len else 0 [n_rows, len_max, H]
  *    p_att = W_c att + b_c                                           [n_rows, len_max, AH]

@@ -199,6 +199,15 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmProblem p,
             float4* dst = reinterpret_cast<float4*>(p.C + (size_t)m * p.ldc + n);
             if (p.epi.accumulate) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
             *dst = v;
+            if (p.epi.c16_hi) {   // split-fp16 copy for the consumer contraction (ld16 % 4 == 0, 8-byte aligned: checked by the launcher)
+                unsigned short hh[4], hl[4];
+                int ovf = 0;
+                split_f16(v.x, hh[0], hl[0], ovf); split_f16(v.y, hh[1], hl[1], ovf); split_f16(v.z, hh[2], hl[2], ovf); split_f16(v.w, hh[3], hl[3], ovf);
+                const size_t o16 = (size_t)m * p.epi.ld16 + n;
+                *reinterpret_cast<uint2*>(p.epi.c16_hi + o16) = make_uint2((uint32_t)hh[0] | ((uint32_t)hh[1] << 16), (uint32_t)hh[2] | ((uint32_t)hh[3] << 16));
+                *reinterpret_cast<uint2*>(p.epi.c16_lo + o16) = make_uint2((uint32_t)hl[0] | ((uint32_t)hl[1] << 16), (uint32_t)hl[2] | ((uint32_t)hl[3] << 16));
+                if (ovf && p.overflow) atomicOr(p.overflow, 1);
+            }
         }
         return;
     }
@@ -327,13 +336,18 @@ int launch_gemm_ex(const GemmProblem& p, float* raw_part, size_t raw_part_elems,
         size_t total = (size_t)p.M * p.N;
         int blocks = (int)((total + 255) / 256);
         if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-        splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(p, a.part, pl.splits);
+        GemmProblem pr = p;   // the split-fp16 copy (epi.c16_*) is written by launch_gemm's split pass on this path
+        pr.epi.c16_hi = nullptr; pr.epi.c16_lo = nullptr;
+        splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(pr, a.part, pl.splits);
         SUBGC_LAUNCH_CHECK();
     }
     return SUBGC_OK;
 }
 
-void launch_splitk_reduce(const GemmProblem& p, const float* part, int splits, cudaStream_t stream) {
+// write_c16: the caller has checked the alignment the vector path's split-fp16 stores need; otherwise epi.c16_* is ignored here
+void launch_splitk_reduce(const GemmProblem& p0, const float* part, int splits, cudaStream_t stream, bool write_c16) {
+    GemmProblem p = p0;
+    if (!write_c16) { p.epi.c16_hi = nullptr; p.epi.c16_lo = nullptr; }
     size_t total = (size_t)p.M * p.N;
     size_t work = ((p.N & 3) == 0) ? total / 4 : total;
     int blocks = (int)((work + 255) / 256);

@@ -747,7 +747,7 @@ static H3Plan h3_plan(int M, int N, const int* segK, int nseg) {
     return best;
 }
 
-void launch_splitk_reduce(const GemmProblem& p, const float* part, int splits, cudaStream_t stream);
+void launch_splitk_reduce(const GemmProblem& p, const float* part, int splits, cudaStream_t stream, bool write_c16 = false);
 
 // Tensor maps of every K segment (weights: boxes of box_w rows; activations: pre-split copies or split here into `ws`)
 static int h3_segments(const GemmProblem& p, int box_w, Workspace& ws, cudaStream_t stream, H3Params& hp) {
@@ -859,8 +859,12 @@ int launch_gemm_h3(const GemmProblem& p, void* ws_, size_t ws_bytes, cudaStream_
         raw->splits = pl.splits;
         return SUBGC_OK;
     }
-    launch_splitk_reduce(p, part, pl.splits, stream);
+    // the reduction pass writes the split-fp16 copy of the result itself when its vector path applies
+    const bool red16 = p.epi.c16_hi && p.epi.c16_lo && (p.N & 3) == 0 && (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 &&
+                       (p.epi.ld16 & 3) == 0 && (reinterpret_cast<uintptr_t>(p.epi.c16_hi) & 7) == 0 && (reinterpret_cast<uintptr_t>(p.epi.c16_lo) & 7) == 0;
+    launch_splitk_reduce(p, part, pl.splits, stream, red16);
     SUBGC_LAUNCH_CHECK();
+    if (wrote_c16) *wrote_c16 = red16;
     return SUBGC_OK;
 }
 

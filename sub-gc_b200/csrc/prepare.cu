@@ -42,7 +42,9 @@ extern "C" size_t subgc_prepare_workspace_bytes(const subgc_dims* d, int n_rows,
     size_t b = align_up(rows * 8, 256) + align_up((size_t)n_rows * 4, 256);  // node_row, row_len
     b += align_up((size_t)n_rows * d->att_hid * 4, 256);                   // read_out_proj hidden
     b += align_up((size_t)n_rows * d->fc_feat * 4, 256);                   // fc_embed hidden
+    b += 2 * align_up((size_t)n_rows * d->fc_feat * 2, 256) + 2 * align_up(rows * d->rnn * 2, 256) + 1024;   // split-fp16 copies of fc hidden / att
     size_t g = gemm_workspace_bytes(n_rows, d->att_hid, 2 * d->gcn);
+    g = max2(g, gemm_workspace_bytes(n_rows, d->fc_feat, 2 * d->gcn));
     g = max2(g, gemm_workspace_bytes(n_rows, 2 * d->gcn, d->att_hid));
     g = max2(g, gemm_workspace_bytes(n_rows, d->fc_feat, d->att_feat));
     g = max2(g, gemm_workspace_bytes(n_rows, d->rnn, d->fc_feat));
@@ -55,8 +57,9 @@ extern "C" int subgc_prepare_forward(const subgc_dims* d, const subgc_weights* w
                                      const int32_t* sel, const float* x_obj, const int64_t* gpn_obj_ind, const float* att_masks,
                                      const float* read_out, float* g_fc, float* fc, float* att, float* p_att, float* masks, void* ws_,
                                      size_t ws_bytes, subgc_stream_t stream) {
-    SUBGC_CHECK_ARG(d && w && lay && sel && x_obj && gpn_obj_ind && att_masks && read_out && g_fc && fc && att && p_att && masks,
+    SUBGC_CHECK_ARG(d && w && lay && sel && x_obj && gpn_obj_ind && att_masks && read_out && fc && att && p_att && masks,
                     "subgc_prepare_forward: null argument");
+    SUBGC_CHECK_ARG(g_fc || w->prep_fold.w, "subgc_prepare_forward: g_fc may only be NULL when w->prep_fold is set");
     SUBGC_CHECK_ARG(n_rows > 0 && len_max > 0 && len_max <= d->obj_num, "subgc_prepare_forward: bad n_rows/len_max (%d, %d)", n_rows, len_max);
     SUBGC_CHECK_ARG(d->att_feat == 2 * d->gcn, "subgc_prepare_forward: fc_embed input (att_feat_size) must equal 2*gcn_dim");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -73,6 +76,24 @@ extern "C" int subgc_prepare_forward(const subgc_dims* d, const subgc_weights* w
     SUBGC_LAUNCH_CHECK();
     GemmProblem p;
     p.wts = w;
+    // split-fp16 copies handed from a contraction to the next one (written by the producer's epilogue / split-K reduction)
+    const bool c16 = w->packs != nullptr && w->n_packs > 0 && (FC & 7) == 0 && (H & 7) == 0;
+    unsigned short* f16_hi = c16 ? ws.take<unsigned short>((size_t)n_rows * FC) : nullptr;
+    unsigned short* f16_lo = c16 ? ws.take<unsigned short>((size_t)n_rows * FC) : nullptr;
+    unsigned short* a16_hi = c16 ? ws.take<unsigned short>((size_t)rows * H) : nullptr;
+    unsigned short* a16_lo = c16 ? ws.take<unsigned short>((size_t)rows * H) : nullptr;
+    if (!ws.ok()) { set_error("subgc_prepare_forward: workspace too small"); return SUBGC_E_WORKSPACE; }
+    if (!g_fc) {
+        // read_out_proj.0 / .1 and fc_embed.0 have nothing between them: one folded contraction, then ReLU (w->prep_fold)
+        p = GemmProblem(); p.wts = w;
+        p.M = n_rows; p.N = FC; p.nseg = 1;
+        p.seg[0] = make_seg(read_out, 2 * L, w->prep_fold.w, 2 * L, 2 * L);
+        p.seg[0].gather32 = sel;
+        p.epi.bias = w->prep_fold.b; p.epi.relu = 1;
+        p.epi.c16_hi = f16_hi; p.epi.c16_lo = f16_lo; p.epi.ld16 = FC;
+        p.C = fch; p.ldc = FC;
+        SUBGC_TRY(launch_gemm(p, ws.cursor(), ws.remaining(), st));
+    } else {
     // read_out_proj: 2L -> AH -> 2L (no activation)
     p = GemmProblem(); p.wts = w;
     p.M = n_rows; p.N = AH; p.nseg = 1;
@@ -92,11 +113,14 @@ extern "C" int subgc_prepare_forward(const subgc_dims* d, const subgc_weights* w
     p.M = n_rows; p.N = FC; p.nseg = 1;
     p.seg[0] = make_seg(g_fc, 2 * L, w->fc_embed0.w, d->att_feat, d->att_feat);
     p.epi.bias = w->fc_embed0.b; p.epi.relu = 1;
+    p.epi.c16_hi = f16_hi; p.epi.c16_lo = f16_lo; p.epi.ld16 = FC;
     p.C = fch; p.ldc = FC;
     SUBGC_TRY(launch_gemm(p, ws.cursor(), ws.remaining(), st));
+    }
     p = GemmProblem(); p.wts = w;
     p.M = n_rows; p.N = H; p.nseg = 1;
     p.seg[0] = make_seg(fch, FC, w->fc_embed2.w, FC, FC);
+    if (f16_hi) { p.seg[0].A16_hi = f16_hi; p.seg[0].A16_lo = f16_lo; p.seg[0].lda16 = FC; }
     p.epi.bias = w->fc_embed2.b; p.epi.relu = 1;
     p.C = fc; p.ldc = H;
     SUBGC_TRY(launch_gemm(p, ws.cursor(), ws.remaining(), st));
@@ -107,12 +131,14 @@ extern "C" int subgc_prepare_forward(const subgc_dims* d, const subgc_weights* w
     p.seg[0].gather = node_row;
     p.epi.bias = w->att_embed.b; p.epi.relu = 1;
     p.epi.group = len_max; p.epi.group_len = row_len;
+    p.epi.c16_hi = a16_hi; p.epi.c16_lo = a16_lo; p.epi.ld16 = H;
     p.C = att; p.ldc = H;
     SUBGC_TRY(launch_gemm(p, ws.cursor(), ws.remaining(), st));
     // ctx2att on every row up to len_max (padded rows give the bias)
     p = GemmProblem(); p.wts = w;
     p.M = rows; p.N = AH; p.nseg = 1;
     p.seg[0] = make_seg(att, H, w->ctx2att.w, H, H);
+    if (a16_hi) { p.seg[0].A16_hi = a16_hi; p.seg[0].A16_lo = a16_lo; p.seg[0].lda16 = H; }
     p.epi.bias = w->ctx2att.b;
     p.C = p_att; p.ldc = AH;
     SUBGC_TRY(launch_gemm(p, ws.cursor(), ws.remaining(), st));

@@ -473,7 +473,7 @@ size_t tc_workspace_bytes(int M, int N, int Ktotal) {
     return align_up((size_t)M * Kpad * 4, 256) + 2 * TC_MAX_SEG * 256 + align_up((size_t)splits * M * N * 4, 256) + 1024;
 }
 
-void launch_splitk_reduce(const GemmProblem& p, const float* part, int splits, cudaStream_t stream);
+void launch_splitk_reduce(const GemmProblem& p, const float* part, int splits, cudaStream_t stream, bool write_c16 = false);
 
 // raw != nullptr: leave the split-K partials [splits][M][N] (no epilogue) for a fused consumer and report where they are
 int launch_gemm_tc(const GemmProblem& p, void* ws_, size_t ws_bytes, cudaStream_t stream, RawPartials* raw) {

@@ -47,6 +47,7 @@ class Weights(C.Structure):
         ("packs", C.POINTER(Packed)), ("n_packs", C.c_int32), ("h3_overflow", c_fp), ("lang_early_w", c_fp),
         ("mega", c_fp), ("mega_bytes", C.c_uint64), ("mega_ctas", C.c_int32),
         ("gcn_fold", (Linear * 2) * MAX_GCN_LAYERS), ("gcn_fold_scale", (C.c_float * 2) * MAX_GCN_LAYERS),
+        ("prep_fold", Linear),
     ]
 
 

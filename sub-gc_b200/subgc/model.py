@@ -156,6 +156,7 @@ class _DeviceState:
         self.ovf_dev = self.ovf_host = self.ovf_event = None
         self.early = self.early_key = None
         self.fold = self.fold_key = None
+        self.pfold = self.pfold_key = None
         self.mega = self.mega_key = None
         self.plans = {}
         self.tops = None
@@ -181,6 +182,8 @@ class TopDownModel(nn.Module):
     _early_key = _state_property("early_key")
     _fold = _state_property("fold")
     _fold_key = _state_property("fold_key")
+    _pfold = _state_property("pfold")
+    _pfold_key = _state_property("pfold_key")
     _mega = _state_property("mega")
     _mega_key = _state_property("mega_key")
     _plans = _state_property("plans")
@@ -354,6 +357,7 @@ class TopDownModel(nn.Module):
                 w.lang_early_w = None
                 self._plans.clear()
             w.mega, w.mega_bytes, w.mega_ctas = None, 0, 0
+            w.prep_fold = _lib.Linear(None, None)
             for l in range(self.dims.gcn_layers):   # folded GCN weights are an inference-only derived copy
                 for dr in range(2):
                     w.gcn_fold[l][dr] = _lib.Linear(None, None)
@@ -381,12 +385,34 @@ class TopDownModel(nn.Module):
         named["__lang_early"] = self._early
         w.lang_early_w = self._early.data_ptr()
         self._attach_gcn_fold(w, params, named)
+        self._attach_prep_fold(w, params, named)
         arr, cnt = self._packs.build(named, {"core.att_lstm.weight_ih": [H, 2 * H], "core.lang_lstm.weight_ih": [H], "__lang_early": [H]})
         if self._pack_key != self._packs.array_key or not w.n_packs:
             w.packs, w.n_packs = arr, cnt
             self._pack_key = self._packs.array_key
             self._plans.clear()  # captured graphs hold the old packed-copy addresses
         self._attach_mega(w, params, dev)
+
+    def _attach_prep_fold(self, w, params, named):
+        """read_out_proj.0 -> read_out_proj.1 -> fc_embed.0 are three Linears in a row (reference models/lib/gpn.py:35-36,
+        models/AttModel.py:109): folded in fp64 into one [FC, 2L] matrix for calls that do not need the intermediate `fc_feats`
+        (include/subgc_b200.h: subgc_weights.prep_fold)."""
+        if os.environ.get("SUBGC_PREP_FOLD", "1") == "0":
+            w.prep_fold = _lib.Linear(None, None)
+            return
+        names = ("gpn_layer.read_out_proj.0", "gpn_layer.read_out_proj.1", "fc_embed.0")
+        src = [params[n + k] for n in names for k in (".weight", ".bias")]
+        key = tuple((t.data_ptr(), t._version) for t in src)
+        if self._pfold_key != key:
+            with torch.no_grad():
+                w0, b0, w1, b1, w2, b2 = (t.double() for t in src)
+                wf = w2 @ w1 @ w0
+                bf = w2 @ (w1 @ b0 + b1) + b2
+                self._pfold = (wf.float().contiguous(), bf.float().contiguous())
+            self._pfold_key = key
+            self._plans.clear()
+        named["__prep_fold"] = self._pfold[0]
+        w.prep_fold = _lib.Linear(self._pfold[0].data_ptr(), self._pfold[1].data_ptr())
 
     def _attach_gcn_fold(self, w, params, named):
         """Folded GCN weights (include/subgc_b200.h: subgc_weights.gcn_fold): fc_rgt(fc_lft(.)) of a _Collection_Unit is linear
@@ -601,12 +627,16 @@ class TopDownModel(nn.Module):
             plan = self._plans[key] = _DecodePlan(dev, self.dims, n_rows, len_max)
         return plan
 
-    def _prepare(self, lay, n_rows, len_max, sel, x_obj, gpn_obj_ind, att_masks, read_out, plan=None):
+    def _prepare(self, lay, n_rows, len_max, sel, x_obj, gpn_obj_ind, att_masks, read_out, plan=None, want_g_fc=True):
+        """want_g_fc=False: the reference's intermediate `fc_feats` is not materialised (read_out_proj and fc_embed.0 as one folded
+        contraction, subgc_weights.prep_fold); the returned g_fc is then None."""
         dev = x_obj.device
         L, d, w, cd = lib(), self.dims, self._weights(), self._cdims
         if plan is None:
             plan = _DecodePlan(dev, d, n_rows, len_max)
         g_fc, fc, att, p_att, masks = plan.g_fc, plan.fc, plan.att, plan.p_att, plan.masks
+        if not want_g_fc and w.prep_fold.w:
+            g_fc = None
         ws = self._ws.get(L.subgc_prepare_workspace_bytes(C.byref(cd), n_rows, len_max), dev)
         check(L.subgc_prepare_forward(C.byref(cd), C.byref(w), C.byref(lay), n_rows, len_max, ptr(sel), ptr(x_obj), ptr(gpn_obj_ind),
                                       ptr(att_masks), ptr(read_out), ptr(g_fc), ptr(fc), ptr(att), ptr(p_att), ptr(masks), ptr(ws),
@@ -737,7 +767,7 @@ class TopDownModel(nn.Module):
         check(L.subgc_subgraph_nms(C.byref(cd), C.byref(lay), ptr(score), ptr(sub_len), ptr(gpn_obj_ind), ptr(att_masks), int(bool(g.use_nms)),
                                    float(g.iou_thres), int(g.max_subgraphs), ptr(sel), ptr(keep), ptr(stats), ptr(ws), ws.numel(),
                                    self._stream()), "subgc_subgraph_nms")
-        g_fc, fc, att, p_att, masks = self._prepare(lay, rows_cap, N, sel, x_obj, gpn_obj_ind, att_masks, read_out, plan)
+        g_fc, fc, att, p_att, masks = self._prepare(lay, rows_cap, N, sel, x_obj, gpn_obj_ind, att_masks, read_out, plan, want_g_fc=False)
         o = plan.out
         check(L.subgc_decode_sample_dyn(C.byref(cd), C.byref(w), rows_cap, N, ptr(stats), 1 if self.topk_sampling else 0, float(self.topk_temp),
                                         int(self.the_k), 0, 0, ptr(o["uniforms"]), ptr(fc), ptr(att), ptr(p_att), ptr(masks), ptr(o["seq"]),

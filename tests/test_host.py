@@ -45,7 +45,7 @@ def test_struct_layouts_match_the_header():
     n_linear = 3 + 2 * 4 * _lib.MAX_GCN_LAYERS + 5 + 6
     # + packs pointer, n_packs (padded), overflow flag pointer, lang_early_w, + mega pointer, mega_bytes, mega_ctas (padded)
     # + gcn_fold (2 linears per layer) and gcn_fold_scale (2 floats per layer)
-    assert ctypes.sizeof(_lib.Weights) == 16 * n_linear + 8 * (3 + 8) + 32 + 24 + _lib.MAX_GCN_LAYERS * (2 * 16 + 2 * 4)
+    assert ctypes.sizeof(_lib.Weights) == 16 * n_linear + 8 * (3 + 8) + 32 + 24 + _lib.MAX_GCN_LAYERS * (2 * 16 + 2 * 4) + 16
     assert ctypes.sizeof(_lib.Packed) == 3 * 8 + 8 * 4
     assert ctypes.sizeof(_lib.Layout) == 16
     assert ctypes.sizeof(_lib.DecoderTrainBufs) == 26 * 8 and ctypes.sizeof(_lib.DecoderGrads) == 14 * 8
