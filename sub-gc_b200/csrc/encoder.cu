@@ -160,20 +160,26 @@ __global__ void __launch_bounds__(256) gcn_node_update_kernel(const float* __res
 // (graph_conv_unit.py:29-35: collect = A (W src + b), collect / (rowsum(A) + 1e-7)), so the segment mean over the edges of a node is taken
 // BEFORE the contraction: agg_s[b,n] = sum_{k: s_k = n} p[b,k] / (c_s + 1e-7) (ascending edge order), likewise agg_o; the contraction then
 // runs over 37 node rows per image instead of 65 edge rows (-43 % FLOPs for the layer), and the bias enters as b * c / (c + 1e-7).
-__global__ void __launch_bounds__(256) gcn_edge_aggregate_kernel(const float* __restrict__ p, const long long* __restrict__ rel_ind, float* __restrict__ agg_s,
+// m2 != nullptr (p == nullptr): the edge stream is not materialised at all -- p[b,k] = 0.5 * (relu(Ma[b,s_k] * msc / (1+1e-7)) +
+// relu(Mb[b,o_k] * msc / (1+1e-7))) is evaluated on the fly from the node messages m2 [B*N, 2L] = [Ma | Mb] of the previous layer's
+// edge <- node direction (same summation order as gcn_edge_update_kernel followed by this kernel; the division by 1 + 1e-7 is a multiplication).
+__global__ void __launch_bounds__(256) gcn_edge_aggregate_kernel(const float* __restrict__ p, const float* __restrict__ m2, float msc,
+                                                                 const long long* __restrict__ rel_ind, float* __restrict__ agg_s,
                                                                  float* __restrict__ agg_o, float* __restrict__ ratio, unsigned short* __restrict__ s16_hi,
                                                                  unsigned short* __restrict__ s16_lo, unsigned short* __restrict__ o16_hi,
                                                                  unsigned short* __restrict__ o16_lo, int* __restrict__ overflow, int N, int K, int L) {
-    extern __shared__ int s_list[];  // [2][K] edge lists of this node (ascending)
+    extern __shared__ int s_list[];  // [2][K] edge lists of this node (ascending) | [2][K] the OTHER end node of those edges
     __shared__ int s_cnt[2];
     __shared__ int s_wcnt[2][8];
+    int* s_other = s_list + 2 * K;
     const int bn = blockIdx.x;
     const int b = bn / N, n = bn - b * N;
     // order-preserving compaction of the edges whose subject / object is this node: ballot + prefix counts (K <= 256)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int k = threadIdx.x;
-    const bool fs = k < K && (int)rel_ind[((size_t)b * K + k) * 2] == n;
-    const bool fo = k < K && (int)rel_ind[((size_t)b * K + k) * 2 + 1] == n;
+    const int ek_s = k < K ? (int)rel_ind[((size_t)b * K + k) * 2] : -1, ek_o = k < K ? (int)rel_ind[((size_t)b * K + k) * 2 + 1] : -1;
+    const bool fs = k < K && ek_s == n;
+    const bool fo = k < K && ek_o == n;
     const unsigned ms_ = __ballot_sync(0xffffffffu, fs), mo_ = __ballot_sync(0xffffffffu, fo);
     if (lane == 0) { s_wcnt[0][wid] = __popc(ms_); s_wcnt[1][wid] = __popc(mo_); }
     __syncthreads();
@@ -181,8 +187,8 @@ __global__ void __launch_bounds__(256) gcn_edge_aggregate_kernel(const float* __
         int off_s = 0, off_o = 0;
         for (int w2 = 0; w2 < wid; ++w2) { off_s += s_wcnt[0][w2]; off_o += s_wcnt[1][w2]; }
         const unsigned lt = (1u << lane) - 1u;
-        if (fs) s_list[off_s + __popc(ms_ & lt)] = k;
-        if (fo) s_list[K + off_o + __popc(mo_ & lt)] = k;
+        if (fs) { s_list[off_s + __popc(ms_ & lt)] = k; s_other[off_s + __popc(ms_ & lt)] = ek_o; }
+        if (fo) { s_list[K + off_o + __popc(mo_ & lt)] = k; s_other[K + off_o + __popc(mo_ & lt)] = ek_s; }
         if (threadIdx.x == 0) {
             int cs_ = 0, co_ = 0;
             for (int w2 = 0; w2 < 8; ++w2) { cs_ += s_wcnt[0][w2]; co_ += s_wcnt[1][w2]; }
@@ -193,19 +199,42 @@ __global__ void __launch_bounds__(256) gcn_edge_aggregate_kernel(const float* __
     const int cs = s_cnt[0], co = s_cnt[1];
     const float ds = (float)cs + 1e-7f, dob = (float)co + 1e-7f;
     if (threadIdx.x == 0) { ratio[2 * (size_t)bn] = (float)cs / ds; ratio[2 * (size_t)bn + 1] = (float)co / dob; }
-    const float* pb = p + (size_t)b * K * L;
+    const float* pb = p ? p + (size_t)b * K * L : nullptr;
+    const float* mb = m2 ? m2 + (size_t)b * N * 2 * L : nullptr;
+    // the unit's divisor for one source row is 1 + 1e-7 (= 1 + 2^-23 in fp32): folded with the power-of-two message scale into one factor
+    // (x * mf and (x * msc) / (1 + 2^-23) are both correctly rounded values of reals 2^-46 x apart)
+    const float mf = (float)((double)msc / (double)(1.f + 1e-7f));
     const int L4 = L >> 2;   // L % 4 == 0 (checked by the caller)
     for (int c4 = threadIdx.x; c4 < L4; c4 += blockDim.x) {
+        float4 own_a = make_float4(0.f, 0.f, 0.f, 0.f), own_b = own_a;   // relu(Ma[n] * msc / d1), relu(Mb[n] * msc / d1)
+        if (mb) {
+            const float4 ta = __ldg(reinterpret_cast<const float4*>(mb + (size_t)n * 2 * L) + c4), tb = __ldg(reinterpret_cast<const float4*>(mb + (size_t)n * 2 * L + L) + c4);
+            own_a = make_float4(fmaxf(ta.x * mf, 0.f), fmaxf(ta.y * mf, 0.f), fmaxf(ta.z * mf, 0.f), fmaxf(ta.w * mf, 0.f));
+            own_b = make_float4(fmaxf(tb.x * mf, 0.f), fmaxf(tb.y * mf, 0.f), fmaxf(tb.z * mf, 0.f), fmaxf(tb.w * mf, 0.f));
+        }
 #pragma unroll
         for (int which = 0; which < 2; ++which) {
             const int cnt = which ? co : cs;
             const int* lst = s_list + which * K;
+            const int* oth = s_other + which * K;
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int i = 0; i < cnt; i += 8) {   // eight independent 16-byte loads in flight, added in ascending edge order
                 float4 v[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    v[u] = (i + u < cnt) ? __ldg(reinterpret_cast<const float4*>(pb + (size_t)lst[i + u] * L) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int u = 0; u < 8; ++u) {
+                    if (i + u >= cnt) { v[u] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
+                    if (pb) v[u] = __ldg(reinterpret_cast<const float4*>(pb + (size_t)lst[i + u] * L) + c4);
+                    else    v[u] = __ldg(reinterpret_cast<const float4*>(mb + (size_t)oth[i + u] * 2 * L + (which ? 0 : L)) + c4);   // the other end's message
+                }
+                if (!pb) {   // edge value = 0.5 * (relu(Ma[s_k]) + relu(Mb[o_k])): this node is s_k (which = 0) or o_k (which = 1)
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (i + u >= cnt) continue;
+                        const float4 t = make_float4(fmaxf(v[u].x * mf, 0.f), fmaxf(v[u].y * mf, 0.f), fmaxf(v[u].z * mf, 0.f), fmaxf(v[u].w * mf, 0.f));
+                        const float4 sa = which ? t : own_a, sb = which ? own_b : t;
+                        v[u] = make_float4(0.5f * (sa.x + sb.x), 0.5f * (sa.y + sb.y), 0.5f * (sa.z + sb.z), 0.5f * (sa.w + sb.w));
+                    }
+                }
 #pragma unroll
                 for (int u = 0; u < 8; ++u)
                     if (i + u < cnt) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
@@ -423,6 +452,8 @@ extern "C" int subgc_gcn_forward(const subgc_dims* d, const subgc_weights* w, in
     unsigned short* n16_hi[2] = {fuse16 ? ws.take<unsigned short>((size_t)B * K * L) : nullptr, fuse16 ? ws.take<unsigned short>((size_t)B * K * L) : nullptr};
     unsigned short* n16_lo[2] = {fuse16 ? ws.take<unsigned short>((size_t)B * K * L) : nullptr, fuse16 ? ws.take<unsigned short>((size_t)B * K * L) : nullptr};
     const unsigned short *cur16_hi = nullptr, *cur16_lo = nullptr;   // split copy of the current edge stream p, if its producer wrote one
+    bool skip_edges = false;   // the previous layer left its edge stream un-materialised (node messages still in M2)
+    float skip_scale = 1.f;
     // aggregate-then-transform buffers (folded node <- edges direction)
     static const bool agg_off = getenv("SUBGC_GCN_AGG") != nullptr && getenv("SUBGC_GCN_AGG")[0] == '0';
     bool any_fold0 = false;
@@ -441,7 +472,7 @@ extern "C" int subgc_gcn_forward(const subgc_dims* d, const subgc_weights* w, in
     const long long* rel = reinterpret_cast<const long long*>(rel_ind);
     for (int l = 0; l < Ln; ++l) {
         const bool last = (l == Ln - 1), boundary = ((l + 1) % d->gcn_residual == 0);
-        bool next16 = false;
+        bool next16 = false, skip_next = false;
         float* x_next = nullptr;
         float* p_next = nullptr;
         if (need_x[l + 1]) x_next = last ? x_obj : ws.take<float>(xn);
@@ -465,10 +496,18 @@ extern "C" int subgc_gcn_forward(const subgc_dims* d, const subgc_weights* w, in
             }
             next16 = fuse16 && !last && need_x[l + 2];   // layer l+1 contracts this edge stream (its units 0, 1 produce x of layer l+2)
             if (agg && !last && w->gcn_fold[l + 1][0].w != nullptr && w->gcn_fold_scale[l + 1][0] > 0.f) next16 = false;   // ... unless it aggregates first
-            gcn_edge_update_kernel<<<B * K, 256, 0, st>>>(folded ? M2 : Ma, folded ? M2 + L : Mb, rel, boundary ? p_res : nullptr, p_next, B, N, K, L,
-                                                          next16 ? n16_hi[l & 1] : nullptr, next16 ? n16_lo[l & 1] : nullptr, L, w->h3_overflow,
-                                                          folded ? 2 * L : L, folded ? 1.f / w->gcn_fold_scale[l][1] : 1.f);
-            SUBGC_LAUNCH_CHECK();
+            // The edge stream p(l+1) need not exist when its only reader is the next (= last) layer's aggregation, which can evaluate an
+            // edge's value from the node messages in M2 itself: no residual at this layer, no x_pred output, no later residual anchor
+            static const bool noskip = getenv("SUBGC_GCN_KEEP_EDGES") != nullptr;
+            skip_next = folded && agg && !noskip && !boundary && x_pred == nullptr && l + 1 == Ln - 1 && need_x[l + 2] && !need_p[l + 2] &&
+                         w->gcn_fold[l + 1][0].w != nullptr && w->gcn_fold_scale[l + 1][0] > 0.f;
+            skip_scale = folded ? 1.f / w->gcn_fold_scale[l][1] : 1.f;
+            if (!skip_next) {
+                gcn_edge_update_kernel<<<B * K, 256, 0, st>>>(folded ? M2 : Ma, folded ? M2 + L : Mb, rel, boundary ? p_res : nullptr, p_next, B, N, K, L,
+                                                              next16 ? n16_hi[l & 1] : nullptr, next16 ? n16_lo[l & 1] : nullptr, L, w->h3_overflow,
+                                                              folded ? 2 * L : L, folded ? 1.f / w->gcn_fold_scale[l][1] : 1.f);
+                SUBGC_LAUNCH_CHECK();
+            }
         }
         if (x_next) {  // units 0,1: node <- edges (graph_conv.py:22-26)
             const subgc_linear& fold = w->gcn_fold[l][0];
@@ -496,7 +535,8 @@ extern "C" int subgc_gcn_forward(const subgc_dims* d, const subgc_weights* w, in
                     all16 = all16 && h3_eligible(gp[u]);   // the contraction will read the split copy only
                 }
                 SUBGC_CHECK_ARG(K <= 256, "subgc_gcn_forward: at most 256 edges per image");
-                gcn_edge_aggregate_kernel<<<B * N, 256, 2 * K * sizeof(int), st>>>(p, rel, all16 ? nullptr : agg_s, all16 ? nullptr : agg_o, agg_ratio, ag16[0],
+                gcn_edge_aggregate_kernel<<<B * N, 256, 4 * K * sizeof(int), st>>>(skip_edges ? nullptr : p, skip_edges ? M2 : nullptr, skip_scale, rel,
+                                                                                   all16 ? nullptr : agg_s, all16 ? nullptr : agg_o, agg_ratio, ag16[0],
                                                                                    ag16[1], ag16[2], ag16[3], w->h3_overflow, N, K, L);
                 SUBGC_LAUNCH_CHECK();
                 for (int u = 0; u < 2; ++u) SUBGC_TRY(launch_gemm(gp[u], ws.cursor(), ws.remaining(), st));
@@ -517,6 +557,7 @@ extern "C" int subgc_gcn_forward(const subgc_dims* d, const subgc_weights* w, in
             }
         }
         cur16_hi = next16 ? n16_hi[l & 1] : nullptr; cur16_lo = next16 ? n16_lo[l & 1] : nullptr;
+        skip_edges = skip_next;
         x = x_next; p = p_next;
         if (boundary) { x_res = x; p_res = p; }
     }
