@@ -131,3 +131,16 @@ def test_compact_batch_host_side():
     lean = compact.needed_only(*host)
     assert lean[0] is None and lean[8] is None and lean[10] is None and lean[11] is None and lean[12] is None and lean[1] is host[1]
     assert cb.nbytes() < sum(t.numel() * t.element_size() for t in host if t is not None) / 1.5
+    # packed(): every field a view into ONE buffer (the host->device transfer of a batch is a single copy)
+    pk = cb.packed()
+    assert pk._buf.dtype == torch.uint8 and pk._buf.numel() >= cb.nbytes()
+    for name in ("att_feats", "obj_cls", "pred_cls", "rel_ind", "sub_nodes", "sub_len"):
+        a, b = getattr(cb, name), getattr(pk, name)
+        assert torch.equal(a, b) and b.is_contiguous()
+        assert pk._buf.data_ptr() <= b.data_ptr() < pk._buf.data_ptr() + pk._buf.numel() and b.data_ptr() % 256 == pk._buf.data_ptr() % 256
+    dst = cb.packed(copy=False)
+    dst.copy_(pk)
+    assert torch.equal(dst._buf, pk._buf) and torch.equal(dst.sub_nodes, cb.sub_nodes)
+    dst2 = cb.empty_like("cpu")
+    dst2.copy_(pk)                         # field-wise path (no common buffer)
+    assert torch.equal(dst2.att_feats, cb.att_feats)
