@@ -29,6 +29,7 @@ namespace subgc {
 // ---- geometry ------------------------------------------------------------------------------------------------------------
 constexpr int MG_THREADS = 640;          // warps 0-3: W producer, X loader, MMA issuer, TMEM owner; warps 4-19: workers
 constexpr int MG_NW = 512;               // worker threads
+constexpr int MG_NSEL = 384;             // threads of the 12 selection warps of a row CTA (the other 4 worker warps drain A(t+1) meanwhile)
 constexpr int MG_WSLOTS = 3, MG_WSLOT_BYTES = 36864;   // weight ring: tiles of <= 144 rows x 64 k (hi | lo)
 constexpr int MG_XSLOTS = 3, MG_XTILE_BYTES = 32768;   // activation ring: [128 rows x 64 k] hi | lo
 constexpr int MG_SCR_BYTES = 16384;
@@ -54,7 +55,7 @@ struct MgTask { int n_blk, n_rows, x_src, x_kb0, acc_set, flags, rot, pad1; };  
 struct MgJob {
     int present, set, n_rows;
     int part_off;      // floats: A/C: this job's [col][128] tile; B/D: first column inside the plane
-    int plane;         // B/D: split index (plane of the row-major partials)
+    int plane;         // split index (B/D: plane of the row-major partials)
     int tile, n_split; // A/C: tile id (sync counter) and partials per tile
     int tile_u0, tile_units;   // A/C: hidden units of the tile
     int u_lo, u_n;     // A/C: this CTA's share of the tile's units in the cell
@@ -76,7 +77,7 @@ struct MgParams {
     const float* fc_pre; const float* att; const float* p_att; const float* masks;
     const float* h2att_b; const float* alpha_w; const float* alpha_b; const float* logit_b;
     const float* xt_table;       // [V1, H, 4] (gates i,f,g,o of a unit adjacent): W_ih[:, 2H:2H+E] relu(E[v]) for every token v (subgc_mega_pack)
-    const float* lang_b_ih; const float* lang_b_hh;
+    const float* lang_b;         // [H, 4]: b_ih + b_hh of the language LSTM, gates of a unit adjacent (built next to fc_pre at launch)
     uint8_t* x_ctx; uint8_t* x_hatt[2]; uint8_t* x_hlang[2];
     float* partA; float* partC; float* partB; float* partD;
     unsigned* sync;
@@ -110,6 +111,7 @@ __device__ __forceinline__ int ld_relaxed_s32(const int* p) {
     asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void st_relaxed_s32(int* p, int v) { asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void st_release_s32(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void red_release(unsigned* p, unsigned v) { asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async.global;" ::: "memory"); }   // generic <-> async proxy, global memory
@@ -121,6 +123,8 @@ __device__ __forceinline__ void bulk_load_hint(uint32_t dst, const void* src, ui
                  "r"(bytes), "r"(bar), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+__device__ __forceinline__ void sel_bar() { asm volatile("bar.sync 2, 384;" ::: "memory"); }     // the 12 selection warps
+__device__ __forceinline__ void drain_bar() { asm volatile("bar.sync 3, 128;" ::: "memory"); }   // the 4 drain warps
 #define MG_TMEM_LD16(R, ADDR)                                                                                                          \
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];" \
                  : "=r"(R[0]), "=r"(R[1]), "=r"(R[2]), "=r"(R[3]), "=r"(R[4]), "=r"(R[5]), "=r"(R[6]), "=r"(R[7]), "=r"(R[8]), "=r"(R[9]),  \
@@ -136,6 +140,7 @@ struct MgCtl {
     volatile int flag[4];   // worker broadcast of wait results (two per round, rounds alternate)
     int red_i[16];
     float red_f[16];
+    float red_s[16];
     float topv[16];
     int topi[16];
     MgCta cta;
@@ -147,13 +152,12 @@ static_assert(sizeof(MgCtl) <= 1024, "control block must fit its 1 KB");
 
 struct MgWait {
     MgCtl* ctl;
-    unsigned* sync;
+    const MgParams& p;
     unsigned long long t0;
-    unsigned long long timeout_ns;
     __device__ __forceinline__ bool expired(int site) {
-        if (ld_acquire(sync + MG_C_ABORT) != 0) { ctl->stop = 2; return true; }
-        if (globaltimer_ns() - t0 > timeout_ns) {
-            atomicCAS(sync + MG_C_ABORT, 0u, (unsigned)(site * 1000 + (int)blockIdx.x + 1));
+        if (ld_acquire(p.sync + MG_C_ABORT) != 0) { ctl->stop = 2; return true; }
+        if (globaltimer_ns() - t0 > p.timeout_ns) {
+            atomicCAS(p.sync + MG_C_ABORT, 0u, (unsigned)(site * 1000 + (int)blockIdx.x + 1));
             ctl->stop = 2;
             return true;
         }
@@ -210,25 +214,25 @@ __device__ __forceinline__ float mg_tanh_score(float x) {   // same form as deco
     return copysignf(__fdividef(1.f - e, 1.f + e), x);
 }
 
-// reductions over the 512 worker threads (wt = worker thread id); every worker must call
+// reductions over the 384 selection threads (wt < MG_NSEL); every selection thread must call
 __device__ __forceinline__ float workers_sum(float v, MgCtl* ctl, int wt) {
     v = warp_sum(v);
-    worker_bar();
+    sel_bar();
     if ((wt & 31) == 0) ctl->red_f[wt >> 5] = v;
-    worker_bar();
+    sel_bar();
     float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) t += ctl->red_f[i];
+    for (int i = 0; i < MG_NSEL / 32; ++i) t += ctl->red_f[i];
     return t;
 }
 __device__ __forceinline__ void workers_argmax(float& v, int& i, MgCtl* ctl, int wt) {
     warp_argmax(v, i);
-    worker_bar();
+    sel_bar();
     if ((wt & 31) == 0) { ctl->red_f[wt >> 5] = v; ctl->red_i[wt >> 5] = i; }
-    worker_bar();
+    sel_bar();
     v = ctl->red_f[0]; i = ctl->red_i[0];
 #pragma unroll
-    for (int w = 1; w < 16; ++w) argmax_combine(v, i, ctl->red_f[w], ctl->red_i[w]);
+    for (int w = 1; w < MG_NSEL / 32; ++w) argmax_combine(v, i, ctl->red_f[w], ctl->red_i[w]);
 }
 
 struct MgPhilox {
@@ -246,7 +250,9 @@ struct MgPhilox {
     }
 };
 
-constexpr int MG_SELVALS = 20;   // logit values per worker thread: V1 <= 10240
+constexpr int MG_SELQ = 7;        // logit column quads per selection thread: thread wt owns quads wt + i * MG_NSEL, V1 <= 10752
+constexpr int MG_SELVALS = 4 * MG_SELQ;
+#define MG_SELCOL(WT_, I_) (4 * ((WT_) + ((I_) >> 2) * MG_NSEL) + ((I_) & 3))   // column of value slot I_ of selection thread WT_
 constexpr int MG_ATT_ITEMS = 10; // (node, 32-quad slice) items per worker warp and pass
 
 __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid_constant__ MgParams p) {
@@ -283,10 +289,20 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = ctl->tmem_slot;
     const MgCta& cta = ctl->cta;
-    MgWait wt_{ctl, p.sync, globaltimer_ns(), p.timeout_ns};
+    MgWait wt_{ctl, p, globaltimer_ns()};
+#ifdef MG_LEAN
+#define MG_STAMP(T_, EV_) do { } while (0)
+#else
 #define MG_STAMP(T_, EV_) do { if (p.trace) p.trace[((size_t)cta_id * T + (T_)) * MG_TRACE_EVENTS + (EV_)] = globaltimer_ns(); } while (0)
+#endif
 
+    // The kernel launches with 96 registers per thread (640 threads = 61440).  The four single-thread roles need fewer: their warpgroup
+    // hands registers over to the 16 worker warps (4 warpgroups: 128 x 64 + 512 x 104 = 61440), whose selection phase keeps 56 partial
+    // values in flight.  A spill is expensive here: the 227 KB of shared memory leave almost no L1 behind local memory.
+#define MG_REG_DEC() asm volatile("setmaxnreg.dec.sync.aligned.u32 64;" ::: "memory")
+#define MG_REG_INC() asm volatile("setmaxnreg.inc.sync.aligned.u32 104;" ::: "memory")
     if (warp == 0) {
+        MG_REG_DEC();
         // ===================================================== weight stream producer =====================================================
         if (lane == 0) {
             uint64_t pol;
@@ -317,6 +333,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                     while (!mbar_try(smem_u32(&ctl->w_full[i % MG_WSLOTS]), (i / MG_WSLOTS) & 1u)) {}
         }
     } else if (warp == 1) {
+        MG_REG_DEC();
         // ===================================================== activation tile loader =====================================================
         if (lane == 0) {
             uint32_t cnt = 0;
@@ -369,6 +386,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
             }
         }
     } else if (warp == 2) {
+        MG_REG_DEC();
         // ===================================================== MMA issuer =====================================================
         if (lane == 0) {
             uint32_t wcnt = 0, xcnt = 0, jobs[2] = {0, 0};
@@ -426,27 +444,30 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                 for (uint32_t it = 0; it < (1u << 24) && !mbar_try(smem_u32(&ctl->mma_done), 0); ++it) {}
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp == 3) {
+        MG_REG_DEC();
+    } else {
+        MG_REG_INC();
         // ===================================================== workers =====================================================
         const int wt = tid - 128, ww = wt >> 5;
-        uint32_t epis[2] = {0, 0};
-        uint32_t nwait = 0;
+        // parities in one register: bit 0 worker-wide waits, bit 1 drain-group waits, bits 2 / 3 epilogues done on accumulator set 0 / 1
+        uint32_t par = 0;
         bool alive = true;
         const bool has_row = cta_id < S;
         const int row = cta_id;
         // broadcast wait helpers: worker thread 0 waits, everybody learns the outcome
         auto w_mbar = [&](unsigned long long* bar, uint32_t parity, int site) -> bool {
-            if (wt == 0) ctl->flag[nwait & 1] = wt_.mbar(bar, parity, site) ? 1 : 0;
+            if (wt == 0) ctl->flag[par & 1] = wt_.mbar(bar, parity, site) ? 1 : 0;
             worker_bar();
-            const bool ok = ctl->flag[nwait & 1] != 0;
-            ++nwait;
+            const bool ok = ctl->flag[par & 1] != 0;
+            par ^= 1u;
             return ok;
         };
         auto w_counter = [&](const unsigned* c, unsigned target, int site) -> bool {
-            if (wt == 0) ctl->flag[nwait & 1] = wt_.counter(c, target, site) ? 1 : 0;
+            if (wt == 0) ctl->flag[par & 1] = wt_.counter(c, target, site) ? 1 : 0;
             worker_bar();
-            const bool ok = ctl->flag[nwait & 1] != 0;
-            ++nwait;
+            const bool ok = ctl->flag[par & 1] != 0;
+            par ^= 1u;
             return ok;
         };
         // everything this CTA's workers wrote becomes visible to whoever acquires the counter afterwards
@@ -455,19 +476,32 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
             worker_bar();
             if (wt == 0) red_release(c, inc);   // release at gpu scope: cumulative over what the barrier made visible to this thread
         };
-        // accumulator -> split-K partial.  col_major: [col][128 rows] (cells read rows of a column), else row-major plane [128][ld]
-        auto epilogue = [&](const MgJob& jb, float* dst, int ld, bool col_major, int t, int ev) -> bool {
+        // accumulator -> split-K partial.  col_major: LSTM tile as [unit][128 rows] float4 (i, f, g, o), else row-major plane [128][ld]
+        // sub: only the 4 drain warps (ww >= 12, one per lane quarter) call, while the other 12 run the token selection
+        // bias: added to the partial here (the plane-0 tiles of the logit contraction: the selection then sums planes only)
+        // add4 (LSTM tiles of split 0): float4 (i, f, g, o) per unit, added here so that the cell has nothing but the partials to sum:
+        // the language LSTM's bias (add_ld = 0: the same for every row) or the attention LSTM's fc_pre row (add_ld = H, rows < add_rows)
+        auto epilogue = [&](const MgJob& jb, float* dst, int ld, bool col_major, int t, int ev, bool sub = false, const float* bias = nullptr,
+                            int bias_n = 0, const float4* add4 = nullptr, int add_ld = 0, int add_rows = 0) -> bool {
             const int set = jb.set;
-            if (!w_mbar(&ctl->acc_full[set], epis[set] & 1u, 8)) return false;
-            ++epis[set];
-            if (wt == 0) MG_STAMP(t, ev);
+            if (!sub) {
+                if (!w_mbar(&ctl->acc_full[set], (par >> (2 + set)) & 1u, 8)) return false;
+            } else {
+                if (wt == MG_NSEL) ctl->flag[2 + ((par >> 1) & 1)] = wt_.mbar(&ctl->acc_full[set], (par >> (2 + set)) & 1u, 8) ? 1 : 0;
+                drain_bar();
+                const bool ok = ctl->flag[2 + ((par >> 1) & 1)] != 0;
+                par ^= 2u;
+                if (!ok) return false;
+            }
+            par ^= 4u << set;
+            if (wt == (sub ? MG_NSEL : 0)) MG_STAMP(t, ev);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int q = ww & 3, g = ww >> 2;
+            const int q = ww & 3, g = sub ? 0 : ww >> 2, gs = sub ? 1 : 4, ncc = sub ? 9 : 3;
             const int r = q * 32 + lane;
             const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)mg_set_col(set);
 #pragma unroll 1
-            for (int cc = 0; cc < 3; ++cc) {
-                const int chunk = g + 4 * cc;   // 16-column chunks, interleaved over the 4 warps of a lane quarter (<= 9 chunks)
+            for (int cc = 0; cc < ncc; ++cc) {
+                const int chunk = g + gs * cc;   // 16-column chunks, interleaved over the warps of a lane quarter (<= 9 chunks)
                 if (chunk * 16 >= jb.n_rows) break;
                 uint32_t ra[16], rb[16];
                 MG_TMEM_LD16(ra, tl + (uint32_t)(chunk * 16));
@@ -476,10 +510,23 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                 float v[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(rb[j]), kH3LoInv, __uint_as_float(ra[j]));
-                if (col_major) {
-                    float* o = dst + (size_t)(chunk * 16) * 128 + r;
+                if (bias) {   // the same address in every lane: one broadcast transaction per column
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) __stcg(o + (size_t)j * 128, v[j]);
+                    for (int j = 0; j < 16; ++j) v[j] += (chunk * 16 + j < bias_n) ? __ldg(bias + chunk * 16 + j) : 0.f;
+                }
+                if (col_major) {   // LSTM tile: columns are [unit][gate]; slot (unit, row) is one float4 of the four gates
+                    float4* o = reinterpret_cast<float4*>(dst) + (size_t)(chunk * 4) * 128 + r;
+                    if (add4 && r < add_rows) {
+                        const float4* ap = add4 + (size_t)r * add_ld + jb.tile_u0 + chunk * 4;
+#pragma unroll
+                        for (int uu = 0; uu < 4; ++uu) {
+                            if (jb.tile_u0 + chunk * 4 + uu >= H) continue;
+                            const float4 av = __ldg(ap + uu);
+                            v[4 * uu] += av.x; v[4 * uu + 1] += av.y; v[4 * uu + 2] += av.z; v[4 * uu + 3] += av.w;
+                        }
+                    }
+#pragma unroll
+                    for (int uu = 0; uu < 4; ++uu) __stcg(o + (size_t)uu * 128, make_float4(v[4 * uu], v[4 * uu + 1], v[4 * uu + 2], v[4 * uu + 3]));
                 } else {
                     // A lane holds 64 contiguous bytes of its row.  Lane pairs swap halves so that every store instruction writes
                     // 32 contiguous bytes per pair (full sectors) instead of 16 per lane (half sectors: measured ~1.5 us slower per tile)
@@ -505,7 +552,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&ctl->acc_free[set]));
+            if (lane == 0)
+                for (int i = 0; i < (sub ? 4 : 1); ++i) mbar_arrive(smem_u32(&ctl->acc_free[set]));   // the barrier counts 16 warps
             return true;
         };
 
@@ -539,6 +587,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
             const bool have_part = !is_att || t > 0;
             // nothing is requested before the polls: an acquire load is not served before the thread's earlier loads have landed
             // (measured: operands requested ahead of the wait delayed the poll by ~2 us)
+            // nothing is requested before the polls: an acquire load is not served before the thread's earlier loads have landed
+            // (measured: operands requested ahead of the wait delayed the poll by ~2 us)
             int tok[2] = {0, 0};
             if (is_att && t > 0) {
                 // Every thread spins on the token slot of its row (both of its elements belong to row wt & 127): the poll returns the
@@ -563,70 +613,38 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                 if (!w_counter(tile_cnt, (unsigned)jb.n_split * (unsigned)(t + 1), 9)) return false;
             }
             if (wt == 0) MG_STAMP(t, ev);
-            // fc_pre and xt_table keep the four gates of a unit adjacent: one 16-byte load per element, and the rows of this CTA's units
-            // are 16 x u_n contiguous bytes (gate-major rows cost a 32-byte sector per scalar: measured 7 us per cell)
+            // xt_table (and fc_pre, needed here at t = 0 only: later it arrives inside the partial of split 0, like the language LSTM's
+            // bias) and the partials keep the four gates of a unit adjacent: one 16-byte load per (element, split)
             float4 add[2], tab[2];
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const int e = wt + k * MG_NW;
                 const int r = e & 127, u = jb.tile_u0 + jb.u_lo + (e >> 7);
                 const bool live = is_att && e < nel && r < S;
-                add[k] = live ? __ldg(reinterpret_cast<const float4*>(p.fc_pre) + (size_t)r * H + u) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            float bi[2][4], bh[2][4];   // language LSTM: both biases, requested together with the partials
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const int e = wt + k * MG_NW;
-                const int u = jb.tile_u0 + jb.u_lo + (e >> 7);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    bi[k][q] = (!is_att && e < nel) ? __ldg(p.lang_b_ih + q * H + u) : 0.f;
-                    bh[k][q] = (!is_att && e < nel) ? __ldg(p.lang_b_hh + q * H + u) : 0.f;
-                }
-            }
-            // every partial of both elements of this thread is requested before the first one is used (one L2 round trip)
-            float acc2[2][4];
-            if (jb.n_split <= 4) {
-                float pz[2][4][4];
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const int e = wt + k * MG_NW;
-                    const int r = e & 127, ul = jb.u_lo + (e >> 7);
-                    const bool live = e < nel && r < S && have_part;
-                    const float* g = part + jb.part_tile_off + r;
-#pragma unroll
-                    for (int z = 0; z < 4; ++z) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            pz[k][z][q] = (live && z < jb.n_split) ? __ldcg(g + (size_t)z * 16384 + (size_t)(q * jb.tile_units + ul) * 128) : 0.f;
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) acc2[k][q] = ((pz[k][0][q] + pz[k][1][q]) + pz[k][2][q]) + pz[k][3][q];   // split order
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const int e = wt + k * MG_NW;
-                    const int r = e & 127, ul = jb.u_lo + (e >> 7);
-                    const bool live = e < nel && r < S && have_part;
-                    const float* g = part + jb.part_tile_off + r;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) acc2[k][q] = 0.f;
-                    for (int z = 0; z < jb.n_split; ++z) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) acc2[k][q] += live ? __ldcg(g + (size_t)z * 16384 + (size_t)(q * jb.tile_units + ul) * 128) : 0.f;
-                    }
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const int e = wt + k * MG_NW;
-                const int r = e & 127, u = jb.tile_u0 + jb.u_lo + (e >> 7);
-                const bool live = is_att && e < nel && r < S;
+                add[k] = (live && t == 0) ? __ldg(reinterpret_cast<const float4*>(p.fc_pre) + (size_t)r * H + u) : make_float4(0.f, 0.f, 0.f, 0.f);
                 tab[k] = live ? __ldg(reinterpret_cast<const float4*>(p.xt_table) + (size_t)tok[k] * H + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            // every partial of both elements of this thread is requested before the first one is used (one L2 round trip);
+            // slot (split z, unit ul, row r) is the float4 at z * 4096 + ul * 128 + r of the tile; n_split <= 4 (mega_plan)
+            float acc2[2][4];
+            {
+                const float4* g4 = reinterpret_cast<const float4*>(part + jb.part_tile_off);
+                float4 pz[2][4];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const int e = wt + k * MG_NW;
+                    const bool live = e < nel && (e & 127) < S && have_part;
+                    const float4* g = g4 + (size_t)(jb.u_lo + (e >> 7)) * 128 + (e & 127);
+#pragma unroll
+                    for (int z = 0; z < 4; ++z) pz[k][z] = (live && z < jb.n_split) ? __ldcg(g + (size_t)z * 4096) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {   // split order
+                    acc2[k][0] = ((pz[k][0].x + pz[k][1].x) + pz[k][2].x) + pz[k][3].x;
+                    acc2[k][1] = ((pz[k][0].y + pz[k][1].y) + pz[k][2].y) + pz[k][3].y;
+                    acc2[k][2] = ((pz[k][0].z + pz[k][1].z) + pz[k][2].z) + pz[k][3].z;
+                    acc2[k][3] = ((pz[k][0].w + pz[k][1].w) + pz[k][2].w) + pz[k][3].w;
+                }
             }
             if (p.trace && wt == 0) {   // the stamp must not be taken before the operands have landed
                 asm volatile("" ::"f"(acc2[0][0]), "f"(acc2[1][3]), "f"(tab[0].x), "f"(tab[1].w), "f"(add[0].x), "f"(add[1].w) : "memory");
@@ -644,9 +662,6 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                     const float a4[4] = {add[k].x, add[k].y, add[k].z, add[k].w}, t4[4] = {tab[k].x, tab[k].y, tab[k].z, tab[k].w};
 #pragma unroll
                     for (int q = 0; q < 4; ++q) acc[q] = (acc[q] + a4[q]) + t4[q];
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) acc[q] = (acc[q] + bi[k][q]) + bh[k][q];
                 }
                 const float c = mg_sigmoid(acc[1]) * cst[k] + mg_sigmoid(acc[0]) * mg_tanh(acc[2]);
                 cst[k] = c;
@@ -805,7 +820,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
             }
             // ---------------- language LSTM -> h_lang(t)
             if (jC.present) {
-                if (!epilogue(jC, p.partC + jC.part_off, 128, true, t, 9)) break;
+                if (!epilogue(jC, p.partC + jC.part_off, 128, true, t, 9, false, nullptr, 0,
+                              jC.plane == 0 ? reinterpret_cast<const float4*>(p.lang_b) : nullptr, 0, 128)) break;
                 w_signal(p.sync + MG_C_TILE_C + jC.tile);
                 MG_WSTAMP(10);
                 if (!cell(jC, p.partC, p.sync + MG_C_TILE_C + jC.tile, t, cC, false, p.x_hlang[t & 1], 11)) break;
@@ -814,48 +830,69 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
             }
             // ---------------- logit partial
             if (jD.present) {
-                if (!epilogue(jD, p.partD + (size_t)jD.plane * 128 * p.ldD + jD.part_off, p.ldD, false, t, 13)) break;
+                if (!epilogue(jD, p.partD + (size_t)jD.plane * 128 * p.ldD + jD.part_off, p.ldD, false, t, 13, false,
+                              jD.plane == 0 ? p.logit_b + jD.part_off : nullptr, p.V1 - jD.part_off)) break;
                 w_signal(p.sync + MG_C_D);
                 MG_WSTAMP(14);
             }
-            // ---------------- token selection of this CTA's row (AttModel.py:292-318) -> xt(t+1)
-            if (has_row) {
-                if (!w_counter(p.sync + MG_C_D, (unsigned)p.nD * (unsigned)(t + 1), 11)) break;
+            // ---------------- token selection of this CTA's row (AttModel.py:292-318) -> xt(t+1), on 12 of the 16 worker warps.
+            // The other 4 (one per tensor-memory lane quarter) drain the attention LSTM accumulator of the NEXT step meanwhile (its
+            // h_att(t) / h_lang(t) segments are contracted right after the logit tile): those partials are what cell A(t+1) would
+            // otherwise wait for after the token is out (measured: published ~2 us after the token when all 16 warps drained it afterwards).
+            const bool next_a = jA.present && t + 1 < T;
+            if (has_row && wt < MG_NSEL) {
+                if (wt == 0) ctl->flag[par & 1] = wt_.counter(p.sync + MG_C_D, (unsigned)p.nD * (unsigned)(t + 1), 11) ? 1 : 0;
+                sel_bar();
+                const bool seen = ctl->flag[par & 1] != 0;
+                if (seen) {
                 MG_WSTAMP(15);
+                // logit partials of this row: thread wt owns the column quads wt + i * MG_NSEL; both planes (zD <= 2: mega_plan) are
+                // requested together, 16 bytes per load.  Plane 0 carries the bias (added by its epilogue).
                 const int V1 = p.V1;
+                const float4* pl = reinterpret_cast<const float4*>(p.partD + (size_t)row * p.ldD);
+                const size_t plane = (size_t)32 * p.ldD;   // float4 units
+                const int nquad = p.ldD >> 2;   // ldD is a multiple of 16; columns V1 .. ldD - 1 are written (zero weights) but not selectable
                 float v[MG_SELVALS];
+                {
+                    float4 a0[MG_SELQ], a1[MG_SELQ];
 #pragma unroll
-                for (int i = 0; i < MG_SELVALS; ++i) v[i] = 0.f;
-                for (int z = 0; z < p.zD; z += 2) {   // split order; the loads of two planes are in flight together
-                    const float* pl = p.partD + ((size_t)z * 128 + row) * p.ldD;
-                    const float* pl1 = pl + (size_t)128 * p.ldD;
-                    const bool two = z + 1 < p.zD;
-                    float tmp[MG_SELVALS], tmp1[MG_SELVALS];
+                    for (int i = 0; i < MG_SELQ; ++i) a0[i] = (wt + i * MG_NSEL < nquad) ? __ldcg(pl + wt + i * MG_NSEL) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int i = 0; i < MG_SELVALS; ++i) tmp[i] = (wt + i * MG_NW < V1) ? __ldcg(pl + wt + i * MG_NW) : 0.f;
+                    for (int i = 0; i < MG_SELQ; ++i)
+                        a1[i] = (p.zD > 1 && wt + i * MG_NSEL < nquad) ? __ldcg(pl + plane + wt + i * MG_NSEL) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int i = 0; i < MG_SELVALS; ++i) tmp1[i] = (two && wt + i * MG_NW < V1) ? __ldcg(pl1 + wt + i * MG_NW) : 0.f;
-#pragma unroll
-                    for (int i = 0; i < MG_SELVALS; ++i) v[i] = (v[i] + tmp[i]) + tmp1[i];
+                    for (int i = 0; i < MG_SELQ; ++i) {   // split order; a1 = +0 with one plane
+                        v[4 * i] = a0[i].x + a1[i].x; v[4 * i + 1] = a0[i].y + a1[i].y; v[4 * i + 2] = a0[i].z + a1[i].z; v[4 * i + 3] = a0[i].w + a1[i].w;
+                    }
                 }
-#pragma unroll
-                for (int i = 0; i < MG_SELVALS; ++i)
-                    if (wt + i * MG_NW < V1) v[i] += __ldg(p.logit_b + wt + i * MG_NW);
                 MG_WSTAMP(45);
+                // arg-max and log-sum-exp in ONE block reduction: every thread sums exp(v - its own max), the partial sums are rescaled
+                // to the warp's and then to the row's maximum (the sum differs from the two-pass one by rounding only)
                 float bv = -INFINITY;
                 int bi = 0x7fffffff;
 #pragma unroll
                 for (int i = 0; i < MG_SELVALS; ++i) {
-                    const int j = wt + i * MG_NW;
+                    const int j = MG_SELCOL(wt, i);
                     if (j < V1 && (v[i] > bv || bi == 0x7fffffff)) { bv = v[i]; bi = j; }
                 }
-                workers_argmax(bv, bi, ctl, wt);
-                const float m = bv;
                 float s = 0.f;
 #pragma unroll
                 for (int i = 0; i < MG_SELVALS; ++i)
-                    if (wt + i * MG_NW < V1) s += expf(v[i] - m);
-                s = workers_sum(s, ctl, wt);
+                    if (MG_SELCOL(wt, i) < V1) s += __expf(v[i] - bv);
+                {
+                    const float own = bv;
+                    warp_argmax(bv, bi);
+                    s = warp_sum(bi == 0x7fffffff || own == -INFINITY ? 0.f : s * __expf(own - bv));
+                    if ((wt & 31) == 0) { ctl->red_f[wt >> 5] = bv; ctl->red_i[wt >> 5] = bi; ctl->red_s[wt >> 5] = s; }
+                    sel_bar();
+                    bv = ctl->red_f[0]; bi = ctl->red_i[0];
+#pragma unroll
+                    for (int w = 1; w < MG_NSEL / 32; ++w) argmax_combine(bv, bi, ctl->red_f[w], ctl->red_i[w]);
+                    s = 0.f;
+#pragma unroll
+                    for (int w = 0; w < MG_NSEL / 32; ++w) s += ctl->red_i[w] == 0x7fffffff ? 0.f : ctl->red_s[w] * __expf(ctl->red_f[w] - bv);
+                }
+                const float m = bv;
                 const float lz = logf(s);
                 MG_WSTAMP(46);
                 int tok;
@@ -863,7 +900,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                 if (p.mode == 0) {
                     tok = bi;
                     lp = (m - m) - lz;
-                } else {   // top-k sampling: q = log_softmax(logp / temp), keep the k best, Categorical over them (AttModel.py:296-303)
+                }
+#ifndef MG_LEAN
+                else {   // top-k sampling: q = log_softmax(logp / temp), keep the k best, Categorical over them (AttModel.py:296-303)
                     const float ym = ((m - m) - lz) / p.temp;
                     // the scaled log-probs are evaluated ONCE per element (one division each; the same expression as before, so the same
                     // bits): v[i] <- (logp / temp) - max, then <- q = that - log(sum) for the k selection rounds
@@ -871,7 +910,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
 #pragma unroll
                     for (int i = 0; i < MG_SELVALS; ++i) {
                         v[i] = ((v[i] - m) - lz) / p.temp - ym;
-                        if (wt + i * MG_NW < V1) s2 += expf(v[i]);
+                        if (MG_SELCOL(wt, i) < V1) s2 += expf(v[i]);
                     }
                     s2 = workers_sum(s2, ctl, wt);
                     const float lz2 = logf(s2);
@@ -883,16 +922,16 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                         int ci = 0x7fffffff;
 #pragma unroll
                         for (int i = 0; i < MG_SELVALS; ++i) {
-                            const int j = wt + i * MG_NW;
+                            const int j = MG_SELCOL(wt, i);
                             if (j >= V1 || ((taken >> i) & 1u)) continue;
                             const float qv = v[i];
                             if (qv > cv || ci == 0x7fffffff) { cv = qv; ci = j; }
                         }
                         workers_argmax(cv, ci, ctl, wt);
-                        if (ci != 0x7fffffff && (ci % MG_NW) == wt) taken |= 1u << (ci / MG_NW);
+                        if (ci != 0x7fffffff && ((ci >> 2) % MG_NSEL) == wt) taken |= 1u << ((((ci >> 2) / MG_NSEL) << 2) | (ci & 3));
                         if (wt == 0) { ctl->topv[c] = cv; ctl->topi[c] = ci; }
                     }
-                    worker_bar();
+                    sel_bar();
                     const int k = p.top_k;
                     const float u = p.uniforms ? p.uniforms[(size_t)t * p.S + row] : MgPhilox::uniform(p.seed, p.offset, (unsigned)t, (unsigned)row);
                     float den = 0.f;
@@ -907,13 +946,17 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                     tok = ctl->topi[pos];
                     lp = ctl->topv[pos];
                 }
+#else
+                else { tok = 0; lp = 0.f; }
+#endif
                 if (wt == 0) {
                     const int unf = (t == 0 ? 1 : unfinished) && (tok > 0);
                     unfinished = unf;
                     const long long it = unf ? tok : 0;
+                    // the cells of step t + 1 spin on this; the slot carries the token itself, nothing else has to be visible with it
+                    st_relaxed_s32(p.tok_slots + (size_t)t * 128 + row, (int)it + 1);
                     p.seq[(size_t)row * T + t] = it;
                     p.seq_lp[(size_t)row * T + t] = lp;
-                    st_release_s32(p.tok_slots + (size_t)t * 128 + row, (int)it + 1);   // the cells of step t + 1 spin on this
                 }
                 {   // the cells gather this token's xt_table row next: on its way into L2 while the token is published and polled for
                     const size_t row_bytes = (size_t)4 * H * sizeof(float);
@@ -921,12 +964,25 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                     if (wt == 32) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(tr), "r"((uint32_t)row_bytes) : "memory");
                 }
                 MG_WSTAMP(47);
-                w_signal(p.sync + MG_C_XT, false, 1u + (unfinished ? 0x10000u : 0u));   // only worker thread 0 uses the increment
+                sel_bar();
+                if (wt == 0) red_release(p.sync + MG_C_XT, 1u + (unfinished ? 0x10000u : 0u));
                 MG_WSTAMP(16);
+                } else if (wt == 0) ctl->fail = 1;
             }
-            // ---------------- attention LSTM of the NEXT step: the h_att(t) / h_lang(t) segments are contracted by now -> partial
-            if (jA.present && t + 1 < T) {
-                if (!epilogue(jA, p.partA + jA.part_off, 128, true, t, 1)) break;
+            if (has_row) {
+                if (wt >= MG_NSEL && next_a) {
+                    if (epilogue(jA, p.partA + jA.part_off, 128, true, t, 1, true, nullptr, 0,
+                                 jA.plane == 0 ? reinterpret_cast<const float4*>(p.fc_pre) : nullptr, H, S)) {
+                        drain_bar();
+                        if (wt == MG_NSEL) { red_release(p.sync + MG_C_TILE_A + jA.tile, 1u); MG_STAMP(t, 2); }
+                    } else if (wt == MG_NSEL) ctl->fail = 1;
+                } else if (next_a) par ^= 4u << jA.set;
+                par ^= 1u;
+                worker_bar();   // both groups meet again; a give-up of either ends the loop for all
+                if (ctl->fail) break;
+            } else if (next_a) {
+                if (!epilogue(jA, p.partA + jA.part_off, 128, true, t, 1, false, nullptr, 0,
+                              jA.plane == 0 ? reinterpret_cast<const float4*>(p.fc_pre) : nullptr, H, S)) break;
                 w_signal(p.sync + MG_C_TILE_A + jA.tile);
                 MG_WSTAMP(2);
             }
@@ -945,19 +1001,25 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
 }
 
 // [rows, 4H] gate-major (row q * H + u of an LSTM weight) -> [rows, H, 4]: the cell reads the four gates of a unit with one 16-byte load
-__global__ void __launch_bounds__(256) gate_interleave_kernel(const float* __restrict__ src, float4* __restrict__ dst, int rows, int H) {
-    const size_t n = (size_t)rows * H;
+// b_a / b_b (nullable): two gate-major bias vectors [4H]; their sum goes, interleaved the same way, to dst row `rows` (H more float4)
+__global__ void __launch_bounds__(256) gate_interleave_kernel(const float* __restrict__ src, float4* __restrict__ dst, int rows, int H,
+                                                              const float* __restrict__ b_a, const float* __restrict__ b_b) {
+    const size_t n = (size_t)rows * H + (b_a ? H : 0);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const size_t r = i / H;
         const int u = (int)(i - r * H);
-        const float* s = src + r * 4 * H + u;
-        dst[i] = make_float4(s[0], s[H], s[2 * (size_t)H], s[3 * (size_t)H]);
+        if (r < (size_t)rows) {
+            const float* s = src + r * 4 * H + u;
+            dst[i] = make_float4(s[0], s[H], s[2 * (size_t)H], s[3 * (size_t)H]);
+        } else {
+            dst[i] = make_float4(b_a[u] + b_b[u], b_a[H + u] + b_b[H + u], b_a[2 * H + u] + b_b[2 * H + u], b_a[3 * H + u] + b_b[3 * H + u]);
+        }
     }
 }
-static void launch_gate_interleave(const float* src, float* dst, int rows, int H, cudaStream_t st) {
-    const size_t n = (size_t)rows * H;
+static void launch_gate_interleave(const float* src, float* dst, int rows, int H, cudaStream_t st, const float* b_a = nullptr, const float* b_b = nullptr) {
+    const size_t n = (size_t)rows * H + (b_a ? H : 0);
     const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)kNumSMs * 8);
-    gate_interleave_kernel<<<blocks, 256, 0, st>>>(src, reinterpret_cast<float4*>(dst), rows, H);
+    gate_interleave_kernel<<<blocks, 256, 0, st>>>(src, reinterpret_cast<float4*>(dst), rows, H, b_a, b_b);
 }
 
 // ---- stream pack ---------------------------------------------------------------------------------------------------------------
@@ -965,7 +1027,7 @@ static void launch_gate_interleave(const float* src, float* dst, int rows, int H
 // 128 bytes, 16-byte chunks XOR-swizzled by (row & 7).  The blocks of a CTA follow each other in the order the CTA contracts them.
 struct MgBlockDesc {
     const float* src; int ld;
-    int gate;          // 1: rows are gate-grouped (row r = gate r / U, unit u0 + r % U -> source row gate * H + unit), 0: row r -> r0 + r
+    int gate;          // 1: LSTM tile, the four gates of a unit adjacent (row r = unit u0 + r / 4, gate r % 4 -> source row gate * H + unit), 0: row r -> r0 + r
     int r0, U, Hrows;  // plain: first source row and number of source rows; gate: first unit, units in the tile, H
     int n_rows;
     int col0, ncols;   // source columns [col0, col0 + ncols) are valid (the rest of the 64 is zero)
@@ -981,8 +1043,8 @@ __global__ void __launch_bounds__(256) mega_pack_kernel(const MgBlockDesc* __res
         long long srow;
         bool valid;
         if (d.gate) {
-            const int q = r / d.U, u = d.r0 + (r - q * d.U);
-            valid = q < 4 && u < d.Hrows;
+            const int q = r & 3, u = d.r0 + (r >> 2);
+            valid = (r >> 2) < d.U && u < d.Hrows;
             srow = (long long)q * d.Hrows + u;
         } else {
             valid = d.r0 + r < d.Hrows;
@@ -1022,7 +1084,7 @@ static void split_groups(int groups, int tiles, std::vector<int>& g0, std::vecto
 static MgPlan mega_plan(const subgc_dims* d, int n_cta) {
     MgPlan pl;
     const int H = d->rnn, E = d->enc, AH = d->att_hid, V1 = d->vocab1;
-    if (n_cta < 1 || n_cta > 1024 || H < 4 || (H & 3) || E < 1 || AH < 128 || (AH & 127) || AH > 512 || V1 < 2 || V1 > MG_SELVALS * MG_NW) return pl;
+    if (n_cta < 1 || n_cta > 1024 || H < 4 || (H & 3) || E < 1 || AH < 128 || (AH & 127) || AH > 512 || V1 < 2 || V1 > MG_SELVALS * MG_NSEL) return pl;
     if ((size_t)(2 * AH + 64 + 64 + 256 + 2 * H) * 4 > MG_SCR_BYTES) return pl;
     pl.n_cta = n_cta;
     const int kbH = (H + 63) / 64;
@@ -1030,7 +1092,7 @@ static MgPlan mega_plan(const subgc_dims* d, int n_cta) {
     // LSTM contractions: tiles of <= 7 groups of 4 hidden units (x 4 gates = <= 112 weight rows), zL k-splits per tile
     const int G = H / 4;
     int zL = 0, tilesL = 0;
-    for (int z = 8; z >= 1; z >>= 1) {
+    for (int z = 4; z >= 1; z >>= 1) {   // <= 4: the cell requests every partial of its elements in one round trip
         if (z > kbH) continue;
         const int tl = std::min(G, n_cta / z);
         if (tl < 1 || (G + tl - 1) / tl > 7) continue;
@@ -1052,7 +1114,7 @@ static MgPlan mega_plan(const subgc_dims* d, int n_cta) {
     // logit: tiles of <= 9 groups of 16 rows
     const int GD = (V1 + 15) / 16;
     int zD = 0, tilesD = 0;
-    for (int z = 4; z >= 1; z >>= 1) {
+    for (int z = 2; z >= 1; z >>= 1) {   // <= 2: the selection requests both planes of its row in one round trip
         if (z > kbH) continue;
         const int td = std::min(GD, n_cta / z);
         if (td < 1 || (GD + td - 1) / td > 9) continue;
@@ -1133,7 +1195,7 @@ static MgPlan mega_plan(const subgc_dims* d, int n_cta) {
             for (int which = 0; which < 2; ++which) {
                 MgJob& jb = ct.job[which == 0 ? MG_JOB_A : MG_JOB_C];
                 jb.present = 1; jb.set = which; jb.n_rows = nrL;
-                jb.part_off = (tileL * zL + zl) * 16384;
+                jb.part_off = (tileL * zL + zl) * 16384; jb.plane = zl;
                 jb.tile = tileL; jb.n_split = zL; jb.tile_u0 = u0; jb.tile_units = U;
                 jb.u_lo = zl * U / zL; jb.u_n = (zl + 1) * U / zL - jb.u_lo;
                 jb.part_tile_off = tileL * zL * 16384;
@@ -1170,7 +1232,7 @@ static size_t mega_scratch_bytes(const MgPlan& pl) {
     b += 5 * align_up((size_t)pl.kbH * MG_XTILE_BYTES, 1024) + MG_C_TOTAL * 4 + (size_t)pl.T * 128 * 4;
     b += 2 * align_up((size_t)pl.nL * 16384 * 4, 1024);
     b += align_up((size_t)pl.zB * 128 * pl.ldB * 4, 1024) + align_up((size_t)pl.zD * 128 * pl.ldD * 4, 1024);
-    b += align_up((size_t)128 * 4 * pl.H * 4, 1024);   // gate-interleaved copy of fc_pre
+    b += align_up((size_t)129 * 4 * pl.H * 4, 1024);   // gate-interleaved copy of fc_pre + the interleaved language-LSTM bias
     return b + 2048;
 }
 static bool mega_take_scratch(const MgPlan& pl, Workspace& ws, MgScratch& sc) {
@@ -1187,7 +1249,7 @@ static bool mega_take_scratch(const MgPlan& pl, Workspace& ws, MgScratch& sc) {
     sc.partC = ws.take<float>((size_t)pl.nL * 16384);
     sc.partB = ws.take<float>((size_t)pl.zB * 128 * pl.ldB);
     sc.partD = ws.take<float>((size_t)pl.zD * 128 * pl.ldD);
-    sc.fc_il = ws.take<float>((size_t)128 * 4 * pl.H);
+    sc.fc_il = ws.take<float>((size_t)129 * 4 * pl.H);
     return ws.ok();
 }
 
@@ -1257,12 +1319,13 @@ int launch_mega_decode(const subgc_dims* d, const subgc_weights* w, int S, int l
     p.wstream = mb + mega_table_bytes(pl);
     p.n_cta = pl.n_cta; p.S = S; p.T = d->seq_length; p.len_max = len_max; p.H = d->rnn; p.AH = d->att_hid; p.V1 = d->vocab1;
     p.kbH = pl.kbH; p.nL = pl.nL; p.nB = pl.nB; p.nD = pl.nD; p.zB = pl.zB; p.zD = pl.zD; p.ldB = pl.ldB; p.ldD = pl.ldD;
-    launch_gate_interleave(fc_pre, sc.fc_il, S, d->rnn, st);   // S is the row capacity when `counts` decides the real count
+    // S is the row capacity when `counts` decides the real count; row S of the copy is the language LSTM's bias (b_ih + b_hh)
+    launch_gate_interleave(fc_pre, sc.fc_il, S, d->rnn, st, w->lang_b_ih, w->lang_b_hh);
     SUBGC_LAUNCH_CHECK();
     p.fc_pre = sc.fc_il; p.att = att; p.p_att = p_att; p.masks = masks;
     p.h2att_b = w->h2att.b; p.alpha_w = w->alpha_net.w; p.alpha_b = w->alpha_net.b; p.logit_b = w->logit.b;
     p.xt_table = reinterpret_cast<const float*>(p.wstream + mega_table_off(pl));
-    p.lang_b_ih = w->lang_b_ih; p.lang_b_hh = w->lang_b_hh;
+    p.lang_b = sc.fc_il + (size_t)S * 4 * d->rnn;
     p.x_ctx = sc.x_ctx; p.x_hatt[0] = sc.x_hatt[0]; p.x_hatt[1] = sc.x_hatt[1]; p.x_hlang[0] = sc.x_hlang[0]; p.x_hlang[1] = sc.x_hlang[1];
     p.partA = sc.partA; p.partC = sc.partC; p.partB = sc.partB; p.partD = sc.partD; p.sync = sc.sync; p.tok_slots = sc.tok_slots;
     p.seq = reinterpret_cast<long long*>(seq); p.seq_lp = seq_lp; p.steps_done = steps_done; p.overflow = w->h3_overflow;

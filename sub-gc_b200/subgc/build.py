@@ -22,6 +22,7 @@ INCLUDE = os.path.join(ROOT, "include")
 OUT = os.path.join(HERE, "libsubgc_b200.so")
 STAMP = OUT + ".stamp"
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
+FLAGS += os.environ.get("SUBGC_NVCC_EXTRA", "").split()   # experiments only (e.g. -DMG_LEAN); part of the stamp
 
 
 def _sources():
