@@ -479,10 +479,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
         // accumulator -> split-K partial.  col_major: LSTM tile as [unit][128 rows] float4 (i, f, g, o), else row-major plane [128][ld]
         // sub: only the 4 drain warps (ww >= 12, one per lane quarter) call, while the other 12 run the token selection
         // bias: added to the partial here (the plane-0 tiles of the logit contraction: the selection then sums planes only)
-        // add4 (LSTM tiles of split 0): float4 (i, f, g, o) per unit, added here so that the cell has nothing but the partials to sum:
-        // the language LSTM's bias (add_ld = 0: the same for every row) or the attention LSTM's fc_pre row (add_ld = H, rows < add_rows)
         auto epilogue = [&](const MgJob& jb, float* dst, int ld, bool col_major, int t, int ev, bool sub = false, const float* bias = nullptr,
-                            int bias_n = 0, const float4* add4 = nullptr, int add_ld = 0, int add_rows = 0) -> bool {
+                            int bias_n = 0) -> bool {
             const int set = jb.set;
             if (!sub) {
                 if (!w_mbar(&ctl->acc_full[set], (par >> (2 + set)) & 1u, 8)) return false;
@@ -516,15 +514,6 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                 }
                 if (col_major) {   // LSTM tile: columns are [unit][gate]; slot (unit, row) is one float4 of the four gates
                     float4* o = reinterpret_cast<float4*>(dst) + (size_t)(chunk * 4) * 128 + r;
-                    if (add4 && r < add_rows) {
-                        const float4* ap = add4 + (size_t)r * add_ld + jb.tile_u0 + chunk * 4;
-#pragma unroll
-                        for (int uu = 0; uu < 4; ++uu) {
-                            if (jb.tile_u0 + chunk * 4 + uu >= H) continue;
-                            const float4 av = __ldg(ap + uu);
-                            v[4 * uu] += av.x; v[4 * uu + 1] += av.y; v[4 * uu + 2] += av.z; v[4 * uu + 3] += av.w;
-                        }
-                    }
 #pragma unroll
                     for (int uu = 0; uu < 4; ++uu) __stcg(o + (size_t)uu * 128, make_float4(v[4 * uu], v[4 * uu + 1], v[4 * uu + 2], v[4 * uu + 3]));
                 } else {
@@ -613,16 +602,17 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                 if (!w_counter(tile_cnt, (unsigned)jb.n_split * (unsigned)(t + 1), 9)) return false;
             }
             if (wt == 0) MG_STAMP(t, ev);
-            // xt_table (and fc_pre, needed here at t = 0 only: later it arrives inside the partial of split 0, like the language LSTM's
-            // bias) and the partials keep the four gates of a unit adjacent: one 16-byte load per (element, split)
+            // fc_pre (attention LSTM: fc segment + both biases), the language LSTM's bias (b_ih + b_hh), xt_table and the partials keep the
+            // four gates of a unit adjacent: one 16-byte load per element (and split)
             float4 add[2], tab[2];
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const int e = wt + k * MG_NW;
                 const int r = e & 127, u = jb.tile_u0 + jb.u_lo + (e >> 7);
-                const bool live = is_att && e < nel && r < S;
-                add[k] = (live && t == 0) ? __ldg(reinterpret_cast<const float4*>(p.fc_pre) + (size_t)r * H + u) : make_float4(0.f, 0.f, 0.f, 0.f);
-                tab[k] = live ? __ldg(reinterpret_cast<const float4*>(p.xt_table) + (size_t)tok[k] * H + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const bool live = e < nel && r < S;
+                const float4* ap = is_att ? reinterpret_cast<const float4*>(p.fc_pre) + (size_t)r * H + u : reinterpret_cast<const float4*>(p.lang_b) + u;
+                add[k] = live ? __ldg(ap) : make_float4(0.f, 0.f, 0.f, 0.f);
+                tab[k] = (live && is_att) ? __ldg(reinterpret_cast<const float4*>(p.xt_table) + (size_t)tok[k] * H + u) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             // every partial of both elements of this thread is requested before the first one is used (one L2 round trip);
             // slot (split z, unit ul, row r) is the float4 at z * 4096 + ul * 128 + r of the tile; n_split <= 4 (mega_plan)
@@ -657,12 +647,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                 const int r = e & 127, ul = jb.u_lo + (e >> 7), u = jb.tile_u0 + ul;
                 if (r >= S) continue;
                 float acc[4] = {acc2[k][0], acc2[k][1], acc2[k][2], acc2[k][3]};
-                if (is_att) {
+                const float a4[4] = {add[k].x, add[k].y, add[k].z, add[k].w}, t4[4] = {tab[k].x, tab[k].y, tab[k].z, tab[k].w};
 #pragma unroll
-                    const float a4[4] = {add[k].x, add[k].y, add[k].z, add[k].w}, t4[4] = {tab[k].x, tab[k].y, tab[k].z, tab[k].w};
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) acc[q] = (acc[q] + a4[q]) + t4[q];
-                }
+                for (int q = 0; q < 4; ++q) acc[q] = is_att ? (acc[q] + a4[q]) + t4[q] : acc[q] + a4[q];
                 const float c = mg_sigmoid(acc[1]) * cst[k] + mg_sigmoid(acc[0]) * mg_tanh(acc[2]);
                 cst[k] = c;
                 x_store(xout, r, u, mg_sigmoid(acc[3]) * mg_tanh(c), ovf);
@@ -820,8 +807,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
             }
             // ---------------- language LSTM -> h_lang(t)
             if (jC.present) {
-                if (!epilogue(jC, p.partC + jC.part_off, 128, true, t, 9, false, nullptr, 0,
-                              jC.plane == 0 ? reinterpret_cast<const float4*>(p.lang_b) : nullptr, 0, 128)) break;
+                if (!epilogue(jC, p.partC + jC.part_off, 128, true, t, 9)) break;
                 w_signal(p.sync + MG_C_TILE_C + jC.tile);
                 MG_WSTAMP(10);
                 if (!cell(jC, p.partC, p.sync + MG_C_TILE_C + jC.tile, t, cC, false, p.x_hlang[t & 1], 11)) break;
@@ -971,8 +957,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
             }
             if (has_row) {
                 if (wt >= MG_NSEL && next_a) {
-                    if (epilogue(jA, p.partA + jA.part_off, 128, true, t, 1, true, nullptr, 0,
-                                 jA.plane == 0 ? reinterpret_cast<const float4*>(p.fc_pre) : nullptr, H, S)) {
+                    if (epilogue(jA, p.partA + jA.part_off, 128, true, t, 1, true)) {
                         drain_bar();
                         if (wt == MG_NSEL) { red_release(p.sync + MG_C_TILE_A + jA.tile, 1u); MG_STAMP(t, 2); }
                     } else if (wt == MG_NSEL) ctl->fail = 1;
@@ -981,8 +966,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                 worker_bar();   // both groups meet again; a give-up of either ends the loop for all
                 if (ctl->fail) break;
             } else if (next_a) {
-                if (!epilogue(jA, p.partA + jA.part_off, 128, true, t, 1, false, nullptr, 0,
-                              jA.plane == 0 ? reinterpret_cast<const float4*>(p.fc_pre) : nullptr, H, S)) break;
+                if (!epilogue(jA, p.partA + jA.part_off, 128, true, t, 1)) break;
                 w_signal(p.sync + MG_C_TILE_A + jA.tile);
                 MG_WSTAMP(2);
             }
