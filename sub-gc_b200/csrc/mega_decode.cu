@@ -33,6 +33,7 @@ constexpr int MG_NSEL = 384;             // threads of the 12 selection warps of
 constexpr int MG_WSLOTS = 3, MG_WSLOT_BYTES = 36864;   // weight ring: tiles of <= 144 rows x 64 k (hi | lo)
 constexpr int MG_XSLOTS = 3, MG_XTILE_BYTES = 32768;   // activation ring: [128 rows x 64 k] hi | lo
 constexpr int MG_SCR_BYTES = 16384;
+constexpr int MG_TOK_STRIDE = 8;         // ints per token slot: one 32-byte sector each, so that the polls of a step spread over the L2 slices
 constexpr int MG_OFF_X = MG_WSLOTS * MG_WSLOT_BYTES;            // 110592
 constexpr int MG_OFF_SCR = MG_OFF_X + MG_XSLOTS * MG_XTILE_BYTES;   // 208896
 constexpr int MG_OFF_BAR = MG_OFF_SCR + MG_SCR_BYTES;           // 225280
@@ -81,7 +82,7 @@ struct MgParams {
     uint8_t* x_ctx; uint8_t* x_hatt[2]; uint8_t* x_hlang[2];
     float* partA; float* partC; float* partB; float* partD;
     unsigned* sync;
-    int* tok_slots;              // [T][128], zero at launch: token of (step, row) + 1 once selected (the cells of the next step spin on it)
+    int* tok_slots;              // [T][128][MG_TOK_STRIDE], zero at launch: token of (step, row) + 1 once selected (the cells of the next step spin on it)
     long long* seq; float* seq_lp; int* steps_done; int* overflow;
     int mode; float temp; int top_k; unsigned long long seed, offset; const float* uniforms;
     const int* counts;           // nullable DEVICE int32[2]: (rows, longest sub-graph) decided by the NMS kernel earlier in the stream; S / len_max
@@ -557,13 +558,14 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
         float cA[2] = {0.f, 0.f}, cC[2] = {0.f, 0.f};
         int unfinished = 1;   // worker thread 0 of a row CTA
         int ovf = 0;
-        // scratch: [AH] atth | [AH] alpha_net weight | [64] scores | [64] mask | [256] score partials | [2][H] context partials
+        // scratch: [AH] atth | [AH] alpha_net weight | [64] scores | [64] mask | [256] score partials | [2][H] context partials | [128] tokens
         float* s_h = scr;
         float* s_w = scr + p.AH;
         float* s_e = scr + 2 * p.AH;
         float* s_mask = s_e + 64;
         float* s_sp = s_mask + 64;
         float* s_c = s_sp + 256;
+        int* s_tok = reinterpret_cast<int*>(s_c + 2 * p.H);   // [128] tokens of the previous step, one poller per row
         if (has_row) {
             for (int j = wt; j < p.AH; j += MG_NW) s_w[j] = __ldg(p.alpha_w + j);
             if (wt < len_rt) s_mask[wt] = __ldg(p.masks + (size_t)row * p.len_stride + wt);
@@ -583,24 +585,25 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
             // (measured: operands requested ahead of the wait delayed the poll by ~2 us)
             int tok[2] = {0, 0};
             if (is_att && t > 0) {
-                // Every thread spins on the token slot of its row (both of its elements belong to row wt & 127): the poll returns the
-                // token itself, one L2 round trip instead of counter poll + barrier + token load.  Worker thread 0 polls the tile's
-                // partial counter in the same loop; the barrier below makes its result (and any give-up) common knowledge.
-                const int r = wt & 127;
-                const int* slot = p.tok_slots + (size_t)(t - 1) * 128 + r;
-                const bool want_tok = wt < nel && r < S;
-                const unsigned tile_target = (unsigned)jb.n_split * (unsigned)t;
-                int v = want_tok ? 0 : 1;
-                bool tile_ok = wt != 0;
-                for (uint32_t it = 1; v == 0 || !tile_ok; ++it) {
-                    if (v == 0) v = ld_relaxed_s32(slot);
-                    if (!tile_ok) tile_ok = ld_acquire(tile_cnt) >= tile_target;
-                    if (v != 0 && tile_ok) break;
-                    if (ctl->stop || ((it & 1023u) == 0 && wt_.expired(15))) { ctl->fail = 1; break; }
+                // One worker thread per row spins on that row's token slot (the poll returns the token itself) and hands it to the other
+                // threads through shared memory; worker thread 0 polls the tile's partial counter in the same loop.  (All 512 threads
+                // polling, 148 CTAs on the same few lines, kept one L2 slice busy for microseconds: measured as late releases.)
+                if (wt < 128) {
+                    const int* slot = p.tok_slots + ((size_t)(t - 1) * 128 + wt) * MG_TOK_STRIDE;
+                    const unsigned tile_target = (unsigned)jb.n_split * (unsigned)t;
+                    int v = wt < S ? 0 : 1;
+                    bool tile_ok = wt != 0;
+                    for (uint32_t it = 1; v == 0 || !tile_ok; ++it) {
+                        if (v == 0) v = ld_relaxed_s32(slot);
+                        if (!tile_ok) tile_ok = ld_acquire(tile_cnt) >= tile_target;
+                        if (v != 0 && tile_ok) break;
+                        if (ctl->stop || ((it & 1023u) == 0 && wt_.expired(15))) { ctl->fail = 1; break; }
+                    }
+                    s_tok[wt] = v - 1;
                 }
-                tok[0] = tok[1] = v - 1;
                 worker_bar();
                 if (ctl->fail) return false;
+                tok[0] = tok[1] = s_tok[wt & 127];
             } else if (!is_att) {
                 if (!w_counter(tile_cnt, (unsigned)jb.n_split * (unsigned)(t + 1), 9)) return false;
             }
@@ -948,14 +951,16 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                     unfinished = unf;
                     const long long it = unf ? tok : 0;
                     // the cells of step t + 1 spin on this; the slot carries the token itself, nothing else has to be visible with it
-                    st_relaxed_s32(p.tok_slots + (size_t)t * 128 + row, (int)it + 1);
+                    st_relaxed_s32(p.tok_slots + ((size_t)t * 128 + row) * MG_TOK_STRIDE, (int)it + 1);
                     p.seq[(size_t)row * T + t] = it;
                     p.seq_lp[(size_t)row * T + t] = lp;
                 }
                 {   // the cells gather this token's xt_table row next: on its way into L2 while the token is published and polled for
                     const size_t row_bytes = (size_t)4 * H * sizeof(float);
                     const char* tr = reinterpret_cast<const char*>(p.xt_table) + (size_t)tok * row_bytes;
+#ifndef MG_NO_XT_PREFETCH
                     if (wt == 32) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(tr), "r"((uint32_t)row_bytes) : "memory");
+#endif
                 }
                 MG_WSTAMP(47);
                 sel_bar();
@@ -1077,7 +1082,7 @@ static MgPlan mega_plan(const subgc_dims* d, int n_cta) {
     MgPlan pl;
     const int H = d->rnn, E = d->enc, AH = d->att_hid, V1 = d->vocab1;
     if (n_cta < 1 || n_cta > 1024 || H < 4 || (H & 3) || E < 1 || AH < 128 || (AH & 127) || AH > 512 || V1 < 2 || V1 > MG_SELVALS * MG_NSEL) return pl;
-    if ((size_t)(2 * AH + 64 + 64 + 256 + 2 * H) * 4 > MG_SCR_BYTES) return pl;
+    if ((size_t)(2 * AH + 64 + 64 + 256 + 2 * H + 128) * 4 > MG_SCR_BYTES) return pl;
     pl.n_cta = n_cta;
     const int kbH = (H + 63) / 64;
     pl.kbH = kbH; pl.H = H; pl.T = d->seq_length;
@@ -1221,7 +1226,7 @@ struct MgScratch {   // per-call device scratch (inside the decode workspace)
 };
 static size_t mega_scratch_bytes(const MgPlan& pl) {
     size_t b = 0;
-    b += 5 * align_up((size_t)pl.kbH * MG_XTILE_BYTES, 1024) + MG_C_TOTAL * 4 + (size_t)pl.T * 128 * 4;
+    b += 5 * align_up((size_t)pl.kbH * MG_XTILE_BYTES, 1024) + MG_C_TOTAL * 4 + (size_t)pl.T * 128 * MG_TOK_STRIDE * 4;
     b += 2 * align_up((size_t)pl.nL * 16384 * 4, 1024);
     b += align_up((size_t)pl.zB * 128 * pl.ldB * 4, 1024) + align_up((size_t)pl.zD * 128 * pl.ldD * 4, 1024);
     b += align_up((size_t)129 * 4 * pl.H * 4, 1024);   // gate-interleaved copy of fc_pre + the interleaved language-LSTM bias
@@ -1229,14 +1234,14 @@ static size_t mega_scratch_bytes(const MgPlan& pl) {
 }
 static bool mega_take_scratch(const MgPlan& pl, Workspace& ws, MgScratch& sc) {
     const size_t xh = align_up((size_t)pl.kbH * MG_XTILE_BYTES, 1024);
-    uint8_t* z = ws.take<uint8_t>(5 * xh + MG_C_TOTAL * 4 + (size_t)pl.T * 128 * 4 + 1024);
+    uint8_t* z = ws.take<uint8_t>(5 * xh + MG_C_TOTAL * 4 + (size_t)pl.T * 128 * MG_TOK_STRIDE * 4 + 1024);
     if (!z) return false;
     z = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(z), 1024));
     sc.x_ctx = z; sc.x_hatt[0] = sc.x_ctx + xh; sc.x_hatt[1] = sc.x_hatt[0] + xh; sc.x_hlang[0] = sc.x_hatt[1] + xh;
     sc.x_hlang[1] = sc.x_hlang[0] + xh;
     sc.sync = reinterpret_cast<unsigned*>(sc.x_hlang[1] + xh);
     sc.tok_slots = reinterpret_cast<int*>(sc.sync + MG_C_TOTAL);
-    sc.zero_bytes = 5 * xh + MG_C_TOTAL * 4 + (size_t)pl.T * 128 * 4;
+    sc.zero_bytes = 5 * xh + MG_C_TOTAL * 4 + (size_t)pl.T * 128 * MG_TOK_STRIDE * 4;
     sc.partA = ws.take<float>((size_t)pl.nL * 16384);
     sc.partC = ws.take<float>((size_t)pl.nL * 16384);
     sc.partB = ws.take<float>((size_t)pl.zB * 128 * pl.ldB);

@@ -58,3 +58,13 @@ for _, line in sorted(rows, key=lambda r: r[0]):
 per_step = (np.nanmax(a[:, 1:, 16], axis=0) - np.nanmax(a[:, :-1, 16], axis=0)) / 1e3
 print("step time (token published -> next token published), us:", np.array2string(per_step, precision=1))
 print("kernel span us:", (np.nanmax(a[:, T - 1, 16]) - np.nanmin(a[:, 0, 0])) / 1e3)
+if os.environ.get("MG_OUTLIERS"):
+    # which CTAs are late, per step: the hand-offs wait for the slowest one
+    for ev in [int(x) for x in os.environ.get('MG_OUTLIER_EVENTS', '2,16,14,10,4,12').split(',')]:
+        print(f"late CTAs for '{names[ev].strip()}' (step: cta +us over the median)")
+        for s in range(T):
+            v = (a[:, s, ev] - np.nanmedian(a[:, s, ev])) / 1e3
+            if np.all(np.isnan(v)):
+                continue
+            order = np.argsort(np.nan_to_num(v, nan=-1e9))[::-1][:3]
+            print(f"  {s:2d}: " + "  ".join(f"{int(c)} +{v[c]:.1f}" for c in order))
