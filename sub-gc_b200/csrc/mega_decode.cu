@@ -49,8 +49,10 @@ enum { MG_X_CTX = 1, MG_X_HATT = 2, MG_X_HLANG_PREV = 3, MG_X_HLANG = 4 };
 enum { MG_F_START = 1, MG_F_COMMIT = 2, MG_F_NEXT = 4 };
 enum { MG_JOB_A = 0, MG_JOB_B = 1, MG_JOB_C = 2, MG_JOB_D = 3 };
 // sync counters (uint32 indices into MgParams::sync)
+// (one 128-byte line per global counter, one 32-byte sector per tile counter: pollers of different counters do not meet on a line)
+constexpr int MG_TILE_STRIDE = 8;
 enum { MG_C_XT = 0, MG_C_HATT = 32, MG_C_HLANG = 64, MG_C_CTX = 96, MG_C_B = 128, MG_C_D = 160, MG_C_ABORT = 192, MG_C_TILE_A = 256,
-       MG_C_TILE_C = 256 + MG_MAX_TILES, MG_C_UNF = 256 + 2 * MG_MAX_TILES, MG_C_TOTAL = 1024 };
+       MG_C_TILE_C = 256 + MG_MAX_TILES * MG_TILE_STRIDE, MG_C_TOTAL = 256 + 2 * MG_MAX_TILES * MG_TILE_STRIDE };
 
 struct MgTask { int n_blk, n_rows, x_src, x_kb0, acc_set, flags, rot, pad1; };   // block b covers k-block x_kb0 + (b + rot) % n_blk
 struct MgJob {
@@ -669,7 +671,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
             MG_WSTAMP(0);
             // ---------------- attention LSTM: gates -> partial -> cell -> h_att(t)
             if (jA.present) {
-                if (!cell(jA, p.partA, p.sync + MG_C_TILE_A + jA.tile, t, cA, true, p.x_hatt[t & 1], 3)) break;
+                if (!cell(jA, p.partA, p.sync + MG_C_TILE_A + jA.tile * MG_TILE_STRIDE, t, cA, true, p.x_hatt[t & 1], 3)) break;
                 w_signal(p.sync + MG_C_HATT, true);
                 MG_WSTAMP(4);
             }
@@ -819,9 +821,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
             // ---------------- language LSTM -> h_lang(t)
             if (jC.present) {
                 if (!epilogue(jC, p.partC + jC.part_off, 128, true, t, 9)) break;
-                w_signal(p.sync + MG_C_TILE_C + jC.tile);
+                w_signal(p.sync + MG_C_TILE_C + jC.tile * MG_TILE_STRIDE);
                 MG_WSTAMP(10);
-                if (!cell(jC, p.partC, p.sync + MG_C_TILE_C + jC.tile, t, cC, false, p.x_hlang[t & 1], 11)) break;
+                if (!cell(jC, p.partC, p.sync + MG_C_TILE_C + jC.tile * MG_TILE_STRIDE, t, cC, false, p.x_hlang[t & 1], 11)) break;
                 w_signal(p.sync + MG_C_HLANG, true);
                 MG_WSTAMP(12);
             }
@@ -972,7 +974,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                 if (wt >= MG_NSEL && next_a) {
                     if (epilogue(jA, p.partA + jA.part_off, 128, true, t, 1, true)) {
                         drain_bar();
-                        if (wt == MG_NSEL) { red_release(p.sync + MG_C_TILE_A + jA.tile, 1u); MG_STAMP(t, 2); }
+                        if (wt == MG_NSEL) { red_release(p.sync + MG_C_TILE_A + jA.tile * MG_TILE_STRIDE, 1u); MG_STAMP(t, 2); }
                     } else if (wt == MG_NSEL) ctl->fail = 1;
                 } else if (next_a) par ^= 4u << jA.set;
                 par ^= 1u;
@@ -980,7 +982,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                 if (ctl->fail) break;
             } else if (next_a) {
                 if (!epilogue(jA, p.partA + jA.part_off, 128, true, t, 1)) break;
-                w_signal(p.sync + MG_C_TILE_A + jA.tile);
+                w_signal(p.sync + MG_C_TILE_A + jA.tile * MG_TILE_STRIDE);
                 MG_WSTAMP(2);
             }
         }
