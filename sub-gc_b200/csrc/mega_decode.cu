@@ -37,7 +37,7 @@ constexpr int MG_TOK_STRIDE = 8;         // ints per token slot: one 32-byte sec
 constexpr int MG_OFF_X = MG_WSLOTS * MG_WSLOT_BYTES;            // 110592
 constexpr int MG_OFF_SCR = MG_OFF_X + MG_XSLOTS * MG_XTILE_BYTES;   // 208896
 constexpr int MG_OFF_BAR = MG_OFF_SCR + MG_SCR_BYTES;           // 225280
-constexpr int MG_SMEM = MG_OFF_BAR + 1024 + 1024;               // + control block + alignment slack
+constexpr int MG_SMEM = MG_OFF_BAR + 2048 + 1024;               // + control block + alignment slack
 // TMEM columns of the two accumulator sets (set 0: tiles <= 112 wide, set 1: <= 144) and the offset of the cross-term accumulator
 __host__ __device__ constexpr int mg_set_col(int set) { return set ? 224 : 0; }
 __host__ __device__ constexpr int mg_set_cross(int set) { return set ? 144 : 112; }
@@ -144,11 +144,15 @@ struct MgCtl {
     int red_i[16];
     float red_f[16];
     float red_s[16];
+    float red_s2[16];       // top-k selection (k <= 3): per-warp sum and the two best elements other than the row maximum
+    float cand_v[2][16];
+    int cand_i[2][16];
     float topv[16];
     int topi[16];
     MgCta cta;
 };
-static_assert(sizeof(MgCtl) <= 1024, "control block must fit its 1 KB");
+static_assert(sizeof(MgCtl) <= 2048, "control block must fit its 2 KB");
+static_assert(MG_SMEM <= 232448, "shared memory of a CTA");
 
 // a wait longer than MgParams::timeout_ns aborts the kernel (guard: never hang the GPU).  Default 4 s; SUBGC_MEGA_TIMEOUT_S raises it
 // for runs under compute-sanitizer, where the kernel is ~100x slower.
@@ -911,6 +915,63 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                         v[i] = ((v[i] - m) - lz) / p.temp - ym;
                         if (MG_SELCOL(wt, i) < V1) s2 += expf(v[i]);
                     }
+                    if (p.top_k <= 3) {
+                        // The best of q is the row maximum found above (q is a monotone map of the logit; first index on ties): q = 0 - lz2.
+                        // The next two come from ONE more block reduction, shared with the sum: every thread keeps its two best other
+                        // elements, a warp merges them by shuffles, and every thread merges the 12 warps' pairs itself (comparisons
+                        // before or after the - lz2 shift are the same).  Was: a sum and three arg-max reductions, nine barriers.
+                        float c1v = -INFINITY, c2v = -INFINITY;
+                        int c1i = 0x7fffffff, c2i = 0x7fffffff;
+                        auto better = [](float av, int ai, float bv_, int bi_) { return av > bv_ || (av == bv_ && ai < bi_); };
+                        auto offer = [&](float xv, int xi) {   // insert into the sorted pair
+                            if (better(xv, xi, c1v, c1i)) { c2v = c1v; c2i = c1i; c1v = xv; c1i = xi; }
+                            else if (better(xv, xi, c2v, c2i)) { c2v = xv; c2i = xi; }
+                        };
+#pragma unroll
+                        for (int i = 0; i < MG_SELVALS; ++i) {
+                            const int j = MG_SELCOL(wt, i);
+                            if (j < V1 && j != bi) offer(v[i], j);
+                        }
+                        s2 = warp_sum(s2);
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            const float o1v = __shfl_xor_sync(0xffffffffu, c1v, o), o2v = __shfl_xor_sync(0xffffffffu, c2v, o);
+                            const int o1i = __shfl_xor_sync(0xffffffffu, c1i, o), o2i = __shfl_xor_sync(0xffffffffu, c2i, o);
+                            offer(o1v, o1i);
+                            offer(o2v, o2i);
+                        }
+                        if ((wt & 31) == 0) {
+                            const int w = wt >> 5;
+                            ctl->red_s2[w] = s2; ctl->cand_v[0][w] = c1v; ctl->cand_i[0][w] = c1i; ctl->cand_v[1][w] = c2v; ctl->cand_i[1][w] = c2i;
+                        }
+                        sel_bar();
+                        s2 = 0.f;
+#pragma unroll
+                        for (int w = 0; w < MG_NSEL / 32; ++w) s2 += ctl->red_s2[w];
+                        const float lz2 = logf(s2);
+                        c1v = c2v = -INFINITY; c1i = c2i = 0x7fffffff;
+#pragma unroll
+                        for (int w = 0; w < MG_NSEL / 32; ++w) { offer(ctl->cand_v[0][w], ctl->cand_i[0][w]); offer(ctl->cand_v[1][w], ctl->cand_i[1][w]); }
+                        const float tv[3] = {0.f - lz2, c1i == 0x7fffffff ? -INFINITY : c1v - lz2, c2i == 0x7fffffff ? -INFINITY : c2v - lz2};
+                        const int ti[3] = {bi, c1i, c2i};
+                        const int k = p.top_k;
+                        const float u = p.uniforms ? p.uniforms[(size_t)t * p.S + row] : MgPhilox::uniform(p.seed, p.offset, (unsigned)t, (unsigned)row);
+                        float den = 0.f;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) den += c < k ? expf(tv[c] - tv[0]) : 0.f;
+                        float cdf = 0.f;
+                        int pos = 0;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            if (c < k) {
+                                cdf += expf(tv[c] - tv[0]) / den;
+                                if (u >= cdf) pos = c + 1;
+                            }
+                        }
+                        if (pos > k - 1) pos = k - 1;
+                        tok = pos == 0 ? ti[0] : (pos == 1 ? ti[1] : ti[2]);
+                        lp = pos == 0 ? tv[0] : (pos == 1 ? tv[1] : tv[2]);
+                    } else {
                     s2 = workers_sum(s2, ctl, wt);
                     const float lz2 = logf(s2);
 #pragma unroll
@@ -944,6 +1005,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                     if (pos > k - 1) pos = k - 1;
                     tok = ctl->topi[pos];
                     lp = ctl->topv[pos];
+                    }
                 }
 #else
                 else { tok = 0; lp = 0.f; }

@@ -984,11 +984,21 @@ class TopDownModel(nn.Module):
             kind, alpha = {"wu": 1, "avg": 2}[name], float(a)
         o = plan.out
         if not o:
-            o["seq"] = torch.empty(n_sub, b, T, dtype=torch.int64, device=dev)
-            o["lps"] = torch.empty(n_sub, b, T, device=dev)
-            o["p"] = torch.empty(n_sub, b, dtype=torch.float64, device=dev)
-            o["up"] = torch.empty(n_sub, b, dtype=torch.float64, device=dev)
-            o["cnt"] = torch.empty(n_sub, dtype=torch.int32, device=dev)
+            # every result of the search in ONE device buffer (8-byte fields first), read back with one copy into pinned memory
+            n_seq, n_p, n_lps = n_sub * b * T * 8, n_sub * b * 8, n_sub * b * T * 4
+            o["pack"] = torch.empty(n_seq + 2 * n_p + n_lps + n_sub * 4, dtype=torch.uint8, device=dev)
+            o["host"] = torch.empty(o["pack"].numel(), dtype=torch.uint8).pin_memory()
+
+            def views(buf):
+                at = 0
+                out = []
+                for nbytes, dt, shape in ((n_seq, torch.int64, (n_sub, b, T)), (n_p, torch.float64, (n_sub, b)), (n_p, torch.float64, (n_sub, b)),
+                                          (n_lps, torch.float32, (n_sub, b, T)), (n_sub * 4, torch.int32, (n_sub,))):
+                    out.append(buf[at:at + nbytes].view(dt).view(shape))
+                    at += nbytes
+                return out
+            o["views"] = views
+            o["seq"], o["p"], o["up"], o["lps"], o["cnt"] = views(o["pack"])
             o["ws"] = torch.empty(L.subgc_beam_workspace_bytes(C.byref(cd), n_sub, b, len_max) + 256, dtype=torch.uint8, device=dev)
         st_args = (C.byref(cd), C.byref(w), n_sub, len_max, b, kind, alpha, int(opt.get("decoding_constraint", 0)), ptr(fc), ptr(att),
                    ptr(p_att), ptr(masks), ptr(o["seq"]), ptr(o["lps"]), ptr(o["p"]), ptr(o["up"]), ptr(o["cnt"]), ptr(o["ws"]),
@@ -1000,9 +1010,12 @@ class TopDownModel(nn.Module):
         plan.run(launch, self.use_graphs)
         self._mark("decode")
         self._arm_overflow_check()
-        # the reference hands back CPU tensors and python lists here (AttModel.py:212-213,229-231)
-        seq_h, lps_h, p_h, up_h, cnt_h = o["seq"].cpu(), o["lps"].cpu(), o["p"].cpu(), o["up"].cpu(), o["cnt"].cpu()
-        if self._ovf_event is not None:   # the copies above synchronised already
+        # the reference hands back CPU tensors and python lists here (AttModel.py:212-213,229-231): one copy, one synchronisation;
+        # the private copy of the host buffer belongs to this call's results (the pinned buffer is reused by the next call)
+        o["host"].copy_(o["pack"], non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        seq_h, p_h, up_h, lps_h, cnt_h = o["views"](o["host"].clone())
+        if self._ovf_event is not None:   # the synchronisation above covered it
             self._ovf_event.synchronize()
             self._ovf_event = None
             if int(self._ovf_host[0]) != 0:
@@ -1012,8 +1025,7 @@ class TopDownModel(nn.Module):
                 warnings.warn("subgc: an activation exceeded the fp16 range of the split-fp16 tensor-core path (|x| > 65504); "
                               "repeating the beam search on the fp32 (split-TF32) path, which this model keeps using from now on")
                 return None
-        self.done_beams = [[dict(seq=seq_h[k, j], logps=lps_h[k, j], unaug_p=float(up_h[k, j]), p=float(p_h[k, j]))
-                            for j in range(int(cnt_h[k]))] for k in range(n_sub)]
+        self.done_beams = _DoneBeams(seq_h, lps_h, up_h, p_h, cnt_h)
         return seq_h[:, 0].contiguous(), lps_h[:, 0].contiguous()
 
     def get_logprobs_state(self, it, fc_feats, att_feats, p_att_feats, att_masks, state, sg_emb=None, p_sg_emb=None, return_att=False):
@@ -1086,6 +1098,45 @@ def _forward_train(self, att_feats, seq, att_masks, obj_dist, rel_ind, gpn_obj_i
 
 
 TopDownModel._forward_train = _forward_train
+
+
+class _DoneBeams:
+    """`model.done_beams` after a beam search (reference models/AttModel.py:229-231: per sub-graph the list of finished beams, best
+    first, each a dict seq / logps / unaug_p / p).  Same indexing, length and iteration as the reference's list of lists; the 640 dicts
+    of a 128-image batch are built when somebody looks at them (eval_utils does for `verbose_beam` only), not on every call."""
+
+    def __init__(self, seq, logps, unaug_p, p, count):
+        self._seq, self._logps = seq, logps
+        self._unaug_p, self._p, self._count = unaug_p.tolist(), p.tolist(), count.tolist()
+        self._cache = {}
+
+    def __len__(self):
+        return len(self._count)
+
+    def _image(self, k):
+        got = self._cache.get(k)
+        if got is None:
+            seqs, lps = self._seq[k].unbind(0), self._logps[k].unbind(0)
+            got = [dict(seq=seqs[j], logps=lps[j], unaug_p=self._unaug_p[k][j], p=self._p[k][j]) for j in range(self._count[k])]
+            self._cache[k] = got
+        return got
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [self._image(i) for i in range(*k.indices(len(self)))]
+        n = len(self)
+        if k < -n or k >= n:
+            raise IndexError("done_beams index out of range")
+        return self._image(k % n)
+
+    def __iter__(self):
+        return (self._image(k) for k in range(len(self)))
+
+    def __eq__(self, other):
+        return list(self) == other
+
+    def __repr__(self):
+        return repr(list(self))
 
 
 class LanguageModelCriterion(nn.Module):
