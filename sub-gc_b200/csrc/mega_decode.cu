@@ -262,6 +262,9 @@ constexpr int MG_SELVALS = 4 * MG_SELQ;
 #define MG_SELCOL(WT_, I_) (4 * ((WT_) + ((I_) >> 2) * MG_NSEL) + ((I_) & 3))   // column of value slot I_ of selection thread WT_
 constexpr int MG_ATT_ITEMS = 10; // (node, 32-quad slice) items per worker warp and pass
 
+// kTrace: the instantiation with the time stamps (SUBGC_MEGA_TRACE=1); the production one carries none of that code (every step runs
+// through ~50 stamp sites once, and straight-line code that is executed once per step comes from a cold instruction cache)
+template <bool kTrace>
 __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid_constant__ MgParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
 #ifdef MG_LEAN
 #define MG_STAMP(T_, EV_) do { } while (0)
 #else
-#define MG_STAMP(T_, EV_) do { if (p.trace) p.trace[((size_t)cta_id * T + (T_)) * MG_TRACE_EVENTS + (EV_)] = globaltimer_ns(); } while (0)
+#define MG_STAMP(T_, EV_) do { if (kTrace && p.trace) p.trace[((size_t)cta_id * T + (T_)) * MG_TRACE_EVENTS + (EV_)] = globaltimer_ns(); } while (0)
 #endif
 
     // The kernel launches with 96 registers per thread (640 threads = 61440).  The four single-thread roles need fewer: their warpgroup
@@ -648,7 +651,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                     acc2[k][3] = ((pz[k][0].w + pz[k][1].w) + pz[k][2].w) + pz[k][3].w;
                 }
             }
-            if (p.trace && wt == 0) {   // the stamp must not be taken before the operands have landed
+            if (kTrace && p.trace && wt == 0) {   // the stamp must not be taken before the operands have landed
                 asm volatile("" ::"f"(acc2[0][0]), "f"(acc2[1][3]), "f"(tab[0].x), "f"(tab[1].w), "f"(add[0].x), "f"(add[1].w) : "memory");
                 MG_STAMP(t, is_att ? 36 : 37);
             }
@@ -844,6 +847,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
             // otherwise wait for after the token is out (measured: published ~2 us after the token when all 16 warps drained it afterwards).
             const bool next_a = jA.present && t + 1 < T;
             if (has_row && wt < MG_NSEL) {
+                // top-k: the uniform of (step, row) does not depend on the logits; every selection thread draws it ahead of the wait
+                float u_row = 0.f;
+                if (p.mode != 0) u_row = p.uniforms ? __ldg(p.uniforms + (size_t)t * p.S + row) : MgPhilox::uniform(p.seed, p.offset, (unsigned)t, (unsigned)row);
                 if (wt == 0) ctl->flag[par & 1] = wt_.counter(p.sync + MG_C_D, (unsigned)p.nD * (unsigned)(t + 1), 11) ? 1 : 0;
                 sel_bar();
                 const bool seen = ctl->flag[par & 1] != 0;
@@ -906,15 +912,19 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                 }
 #ifndef MG_LEAN
                 else {   // top-k sampling: q = log_softmax(logp / temp), keep the k best, Categorical over them (AttModel.py:296-303)
-                    const float ym = ((m - m) - lz) / p.temp;
-                    // the scaled log-probs are evaluated ONCE per element (one division each; the same expression as before, so the same
-                    // bits): v[i] <- (logp / temp) - max, then <- q = that - log(sum) for the k selection rounds
+                    // the scaled log-probs are evaluated ONCE per element: v[i] <- (logp / temp) - max, then q = that - log(sum).  The
+                    // division is a multiplication by 1 / temp and the exponential comes from the ex2 unit (<= 2 ulp each, far below
+                    // the 2e-5 bar): the IEEE division + libdevice expf were ~1000 instructions per thread and step, straight-line code
+                    // that ran from a cold instruction cache (measured 3.8 us for this loop)
+                    const float rtemp = 1.f / p.temp;
+                    const float ym = ((m - m) - lz) * rtemp;
                     float s2 = 0.f;
 #pragma unroll
                     for (int i = 0; i < MG_SELVALS; ++i) {
-                        v[i] = ((v[i] - m) - lz) / p.temp - ym;
-                        if (MG_SELCOL(wt, i) < V1) s2 += expf(v[i]);
+                        v[i] = ((v[i] - m) - lz) * rtemp - ym;
+                        if (MG_SELCOL(wt, i) < V1) s2 += __expf(v[i]);
                     }
+                    MG_WSTAMP(38);
                     if (p.top_k <= 3) {
                         // The best of q is the row maximum found above (q is a monotone map of the logit; first index on ties): q = 0 - lz2.
                         // The next two come from ONE more block reduction, shared with the sum: every thread keeps its two best other
@@ -945,6 +955,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                             ctl->red_s2[w] = s2; ctl->cand_v[0][w] = c1v; ctl->cand_i[0][w] = c1i; ctl->cand_v[1][w] = c2v; ctl->cand_i[1][w] = c2i;
                         }
                         sel_bar();
+                        MG_WSTAMP(39);
                         s2 = 0.f;
 #pragma unroll
                         for (int w = 0; w < MG_NSEL / 32; ++w) s2 += ctl->red_s2[w];
@@ -955,7 +966,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                         const float tv[3] = {0.f - lz2, c1i == 0x7fffffff ? -INFINITY : c1v - lz2, c2i == 0x7fffffff ? -INFINITY : c2v - lz2};
                         const int ti[3] = {bi, c1i, c2i};
                         const int k = p.top_k;
-                        const float u = p.uniforms ? p.uniforms[(size_t)t * p.S + row] : MgPhilox::uniform(p.seed, p.offset, (unsigned)t, (unsigned)row);
+                        const float u = u_row;
                         float den = 0.f;
 #pragma unroll
                         for (int c = 0; c < 3; ++c) den += c < k ? expf(tv[c] - tv[0]) : 0.f;
@@ -993,7 +1004,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                     }
                     sel_bar();
                     const int k = p.top_k;
-                    const float u = p.uniforms ? p.uniforms[(size_t)t * p.S + row] : MgPhilox::uniform(p.seed, p.offset, (unsigned)t, (unsigned)row);
+                    const float u = u_row;
                     float den = 0.f;
                     for (int c = 0; c < k; ++c) den += expf(ctl->topv[c] - ctl->topv[0]);
                     float cdf = 0.f;
@@ -1032,21 +1043,16 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                 MG_WSTAMP(16);
                 } else if (wt == 0) ctl->fail = 1;
             }
-            if (has_row) {
-                if (wt >= MG_NSEL && next_a) {
-                    if (epilogue(jA, p.partA + jA.part_off, 128, true, t, 1, true)) {
-                        drain_bar();
-                        if (wt == MG_NSEL) { red_release(p.sync + MG_C_TILE_A + jA.tile * MG_TILE_STRIDE, 1u); MG_STAMP(t, 2); }
-                    } else if (wt == MG_NSEL) ctl->fail = 1;
-                } else if (next_a) par ^= 4u << jA.set;
-                par ^= 1u;
-                worker_bar();   // both groups meet again; a give-up of either ends the loop for all
-                if (ctl->fail) break;
-            } else if (next_a) {
-                if (!epilogue(jA, p.partA + jA.part_off, 128, true, t, 1)) break;
-                w_signal(p.sync + MG_C_TILE_A + jA.tile * MG_TILE_STRIDE);
-                MG_WSTAMP(2);
-            }
+            // next-step accumulator: the 4 drain warps of a row CTA (beside the selection), all 16 worker warps elsewhere
+            if (next_a && (!has_row || wt >= MG_NSEL)) {
+                if (epilogue(jA, p.partA + jA.part_off, 128, true, t, 1, has_row)) {
+                    if (has_row) drain_bar(); else worker_bar();
+                    if (wt == (has_row ? MG_NSEL : 0)) { red_release(p.sync + MG_C_TILE_A + jA.tile * MG_TILE_STRIDE, 1u); MG_STAMP(t, 2); }
+                } else if (wt == (has_row ? MG_NSEL : 0)) ctl->fail = 1;
+            } else if (next_a) par ^= 4u << jA.set;
+            if (has_row) par ^= 1u;   // the selection group used flag[par & 1]
+            worker_bar();   // the groups meet again; a give-up of either ends the loop for all
+            if (ctl->fail) break;
         }
         if (ovf && p.overflow) atomicOr(p.overflow, 1);
     }
@@ -1400,7 +1406,10 @@ int launch_mega_decode(const subgc_dims* d, const subgc_weights* w, int S, int l
     }();
     p.timeout_ns = timeout_ns;
     static DeviceOnce once;
-    SUBGC_CUDA(once.run([]() { return cudaFuncSetAttribute(mega_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM); }));
+    SUBGC_CUDA(once.run([]() {
+        cudaError_t e = cudaFuncSetAttribute(mega_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM);
+        return e != cudaSuccess ? e : cudaFuncSetAttribute(mega_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM);
+    }));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(pl.n_cta); cfg.blockDim = dim3(MG_THREADS); cfg.dynamicSmemBytes = MG_SMEM; cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -1416,7 +1425,8 @@ int launch_mega_decode(const subgc_dims* d, const subgc_weights* w, int S, int l
         if (!tm.e0) { cudaEventCreate(&tm.e0); cudaEventCreate(&tm.e1); }
         cudaEventRecord(tm.e0, st);
     }
-    SUBGC_CUDA(cudaLaunchKernelEx(&cfg, mega_decode_kernel, p));
+    if (p.trace) SUBGC_CUDA(cudaLaunchKernelEx(&cfg, mega_decode_kernel<true>, p));
+    else SUBGC_CUDA(cudaLaunchKernelEx(&cfg, mega_decode_kernel<false>, p));
     if (timed) { cudaEventRecord(tm.e1, st); tm.pending = true; }
     SUBGC_LAUNCH_CHECK();
     return SUBGC_OK;

@@ -13,7 +13,7 @@ from subgc.model import setup
 n_images = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 step = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 d = Dims()
-m = setup(make_opt(d, test_LSTM=1, gpn_nms_thres=0.75, gpn_max_subg=1))
+m = setup(make_opt(d, test_LSTM=1, gpn_nms_thres=0.75, gpn_max_subg=1, use_topk_sampling=1 if os.environ.get("MG_TOPK") else 0))
 m.load_state_dict(synth.make_state_dict(d, 2019)); m.cuda().eval()
 data = synth.make_test_inputs(d, 2019, n_images=n_images, per_half=1, ragged=False, ragged_edges=False)
 args = [data[k].cuda() if data[k] is not None else None for k in synth.SAMPLE_ARG_ORDER]
@@ -32,7 +32,7 @@ names = {0: "step begins (workers)", 1: "acc A(t+1) complete", 2: "partial A(t+1
          10: "partial C published", 11: "tile C partials complete", 12: "h_lang published", 13: "acc D complete", 14: "partial D published",
          15: "all D partials seen (select)", 16: "token published", 40: "producer: step issued",
          36: "  cell A operands landed", 37: "  cell C operands landed", 17: "  cell A computed + stored", 19: "  cell C computed + stored", 41: "  atth reduced", 42: "  scores done", 43: "  softmax done",
-         44: "  ctx partials done", 18: "  ctx stored", 45: "  logits loaded", 46: "  argmax + lse done", 47: "  token chosen"}
+         38: "  top-k: scaled log-probs + exp done", 39: "  top-k: sum and candidates merged", 44: "  ctx partials done", 18: "  ctx stored", 45: "  logits loaded", 46: "  argmax + lse done", 47: "  token chosen"}
 tasks = ["C_hlang", "B", "C_hatt", "A_hatt+", "C_ctx", "D", "A_hlang+"]
 t0 = np.nanmin(a[:, step, 0])
 print(f"step {step} of {T}; us relative to the first CTA entering the step; min / median / max over CTAs")
