@@ -762,7 +762,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                     const int n = grp + 2 * i;
                     pre[i] = (tg < H4 && n < len_max) ? __ldg(reinterpret_cast<const float4*>(af + (size_t)n * H) + tg) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                if (ww == 0) {   // softmax, then mask, then renormalise: two-stage as the reference (AttModel.py:462-466)
+                if (ww == 0) {   // softmax, then mask, then renormalise: two-stage as the reference (AttModel.py:462-466); ex2 / rcp units
+                                 // (<= 2 ulp per weight; one warp runs this while fifteen wait: libdevice expf and IEEE divisions were 2 us)
                     float m = -INFINITY;
                     for (int n = lane; n < len_max; n += 32) m = fmaxf(m, s_e[n]);
                     m = warp_max(m);
@@ -771,20 +772,20 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
                         const int n = lane + 32 * i;
-                        if (n < len_max) { ex[i] = expf(s_e[n] - m); sum += ex[i]; }
+                        if (n < len_max) { ex[i] = __expf(s_e[n] - m); sum += ex[i]; }
                     }
                     sum = warp_sum(sum);
                     float msum = 0.f;
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
                         const int n = lane + 32 * i;
-                        if (n < len_max) { ex[i] = ex[i] / sum * s_mask[n]; msum += ex[i]; }
+                        if (n < len_max) { ex[i] = __fdividef(ex[i], sum) * s_mask[n]; msum += ex[i]; }
                     }
                     msum = warp_sum(msum);
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
                         const int n = lane + 32 * i;
-                        if (n < len_max) s_e[n] = ex[i] / msum;
+                        if (n < len_max) s_e[n] = __fdividef(ex[i], msum);
                     }
                 }
                 worker_bar();
