@@ -140,8 +140,10 @@ struct MgCtl {
     uint32_t tmem_slot;
     volatile int stop;      // 1: all rows finished (normal early exit), 2: aborted (time-out; MG_C_ABORT holds the site)
     volatile int fail;      // sticky: a worker thread gave up a spin wait (the kernel is stopping)
-    volatile int flag[4];   // worker broadcast of wait results (two per round, rounds alternate)
-    int red_i[16];
+    volatile int flag[4];   // worker broadcast of wait results (two per round, rounds alternate); [2], [3]: the drain group's
+    // 16-byte aligned: the compiler reads these arrays with 16-byte loads; unaligned, such a load also covered flag[3], which the drain
+    // group writes while the selection group reduces (compute-sanitizer racecheck: a WAR hazard on a value nobody uses)
+    alignas(16) int red_i[16];
     float red_f[16];
     float red_s[16];
     float red_s2[16];       // top-k selection (k <= 3): per-warp sum and the two best elements other than the row maximum
