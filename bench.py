@@ -520,7 +520,7 @@ def main():
             "prepare": {"ms": t_prep * 1e3, "executed_flops": prep_flops, "achieved": 3 * prep_flops / max(t_prep, 1e-9) / 1e12,
                         "frac": 3 * prep_flops / max(t_prep, 1e-9) / 1e12 / tf_peak},
             "note": "stage time includes the non-contraction kernels (splits, segment means, pooling); per-kernel tensor-pipe activity: "
-                    "profiles/r02c_ncu_encoder.md"}
+                    "profiles/r02d_ncu_encoder.md"}
     if not args.no_cpu_baseline:
         n_sample = 16 if args.mode == "beam" else IMAGES_PER_GPU
         ref = reference_arm(d, sd, data, args.mode, 1, 1, cores, n_sample, check_seq=out[0])
