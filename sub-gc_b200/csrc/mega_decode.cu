@@ -6,11 +6,13 @@
 // 7.0-7.3 TB/s next to an equally large L2-resident activation stream, as long as >= 96 KB per SM stay in flight, and that a grid-wide
 // hand-off costs 1.2-2.4 us.  So here one CTA per SM owns a fixed slice of every contraction of the step and
 //   * a producer thread streams that slice (its own contiguous, pre-swizzled region of the "stream pack", cp.async.bulk, L2 evict-first)
-//     into a 4-deep ring and never waits for anything but a free slot: the HBM pipe keeps running across phase hand-offs;
+//     into a 3-slot ring and never waits for anything but a free slot: the HBM pipe keeps running across phase hand-offs;
 //   * a second thread loads the activation tiles (split-fp16, pre-swizzled by their producers) once their dependency counter is up;
 //   * one thread issues the tcgen05.mma chains (split-fp16: main + cross accumulators in TMEM, two accumulator sets);
 //   * 16 worker warps drain accumulators (TMEM -> split-K partial in L2), and run the LSTM cells, the attention of "their" row and the
-//     token selection of "their" row, handing results over through global counters (release / acquire), not kernel boundaries.
+//     token selection of "their" row (12 warps; the other 4 drain the next step's attention-LSTM accumulator meanwhile), handing results
+//     over through global counters (release / acquire), not kernel boundaries.  A hand-off is polled by ONE thread per CTA (or one per
+//     row for the tokens) and every polled word has a 32-byte sector of its own: many pollers on one line keep an L2 slice busy.
 // Work that does not depend on the newest result (the h_att / h_lang segments of the NEXT contraction) is issued while a hand-off is
 // in flight.  The schedule (which CTA contracts which weight tile in which order) is a table built on the host (mega_plan).
 #include <cuda.h>
@@ -302,11 +304,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
     const uint32_t tmem = ctl->tmem_slot;
     const MgCta& cta = ctl->cta;
     MgWait wt_{ctl, p, globaltimer_ns()};
-#ifdef MG_LEAN
-#define MG_STAMP(T_, EV_) do { } while (0)
-#else
 #define MG_STAMP(T_, EV_) do { if (kTrace && p.trace) p.trace[((size_t)cta_id * T + (T_)) * MG_TRACE_EVENTS + (EV_)] = globaltimer_ns(); } while (0)
-#endif
 
     // The kernel launches with 96 registers per thread (640 threads = 61440).  The four single-thread roles need fewer: their warpgroup
     // hands registers over to the 16 worker warps (4 warpgroups: 128 x 64 + 512 x 104 = 61440), whose selection phase keeps 56 partial
@@ -747,14 +745,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                 if (!alive) break;
                 worker_bar();
                 MG_WSTAMP(42);
-                if (wt < len_max) {
-                    float e = 0.f;
-                    for (int q = 0; q < Q; ++q) e += s_sp[wt * Q + q];
-                    s_e[wt] = e + __ldg(p.alpha_b);
-                }
-                worker_bar();
                 // the att rows of the context sum do not depend on the weights: the first nodes of this thread's column quad are requested
-                // now and land while one warp finishes the softmax
+                // now and land during the softmax
                 constexpr int kPre = 12;
                 const float* af = p.att + (size_t)row * lst * H;
                 const int grp = wt >> 8, tg = wt & 255, H4 = H >> 2;
@@ -764,61 +756,67 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                     const int n = grp + 2 * i;
                     pre[i] = (tg < H4 && n < len_max) ? __ldg(reinterpret_cast<const float4*>(af + (size_t)n * H) + tg) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                if (ww == 0) {   // softmax, then mask, then renormalise: two-stage as the reference (AttModel.py:462-466); ex2 / rcp units
-                                 // (<= 2 ulp per weight; one warp runs this while fifteen wait: libdevice expf and IEEE divisions were 2 us)
-                    float m = -INFINITY;
-                    for (int n = lane; n < len_max; n += 32) m = fmaxf(m, s_e[n]);
-                    m = warp_max(m);
-                    float ex[2] = {0.f, 0.f};   // len_max <= 64: two elements per lane, exponentials evaluated once
-                    float sum = 0.f;
+                // Every warp runs the softmax itself (lane l owns nodes l and l + 32; len_max <= 64) and keeps the weights in registers:
+                // no barrier between scores and context, and no warp waits for another one's softmax (one warp ran it while fifteen
+                // waited: 2.3 us).  softmax, then mask, then renormalise: two-stage as the reference (AttModel.py:462-466); ex2 / rcp units.
+                float wgt[2];
+                {
+                    float e[2];
+                    const float ab = __ldg(p.alpha_b);
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
                         const int n = lane + 32 * i;
-                        if (n < len_max) { ex[i] = __expf(s_e[n] - m); sum += ex[i]; }
+                        float acc = 0.f;
+                        if (n < len_max)
+                            for (int q = 0; q < Q; ++q) acc += s_sp[n * Q + q];
+                        e[i] = acc + ab;
                     }
+                    float m = -INFINITY;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+                        if (lane + 32 * i < len_max) m = fmaxf(m, e[i]);
+                    m = warp_max(m);
+                    float ex[2] = {0.f, 0.f}, sum = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+                        if (lane + 32 * i < len_max) { ex[i] = __expf(e[i] - m); sum += ex[i]; }
                     sum = warp_sum(sum);
                     float msum = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const int n = lane + 32 * i;
-                        if (n < len_max) { ex[i] = __fdividef(ex[i], sum) * s_mask[n]; msum += ex[i]; }
-                    }
+                    for (int i = 0; i < 2; ++i)
+                        if (lane + 32 * i < len_max) { ex[i] = __fdividef(ex[i], sum) * s_mask[lane + 32 * i]; msum += ex[i]; }
                     msum = warp_sum(msum);
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const int n = lane + 32 * i;
-                        if (n < len_max) s_e[n] = __fdividef(ex[i], msum);
-                    }
+                    for (int i = 0; i < 2; ++i) wgt[i] = (lane + 32 * i < len_max) ? __fdividef(ex[i], msum) : 0.f;
                 }
-                worker_bar();
                 MG_WSTAMP(43);
-                {   // context: two thread groups take interleaved node subsets, partials combined in fixed order
-                    if (tg < H4) {
+                {   // context: two thread groups take interleaved node subsets, partials combined in fixed order.  The node index is the
+                    // same in every lane of a warp: its weight comes from the owning lane by shuffle (outside any lane-dependent branch)
+                    {
                         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                         for (int i = 0; i < kPre; ++i) {
-                            const int n = grp + 2 * i;
-                            if (n < len_max) {
-                                const float wv = s_e[n];
-                                a.x = fmaf(wv, pre[i].x, a.x); a.y = fmaf(wv, pre[i].y, a.y); a.z = fmaf(wv, pre[i].z, a.z); a.w = fmaf(wv, pre[i].w, a.w);
-                            }
+                            const int n = grp + 2 * i;   // < 32 + grp for every i < kPre <= 16
+                            const float wv = __shfl_sync(0xffffffffu, n < 32 ? wgt[0] : wgt[1], n & 31);
+                            if (n < len_max) { a.x = fmaf(wv, pre[i].x, a.x); a.y = fmaf(wv, pre[i].y, a.y); a.z = fmaf(wv, pre[i].z, a.z); a.w = fmaf(wv, pre[i].w, a.w); }
                         }
 #pragma unroll 12
                         for (int n = grp + 2 * kPre; n < len_max; n += 2) {
-                            const float4 v = __ldg(reinterpret_cast<const float4*>(af + (size_t)n * H) + tg);
-                            const float wv = s_e[n];
+                            const float wv = __shfl_sync(0xffffffffu, n < 32 ? wgt[0] : wgt[1], n & 31);
+                            const float4 v = tg < H4 ? __ldg(reinterpret_cast<const float4*>(af + (size_t)n * H) + tg) : make_float4(0.f, 0.f, 0.f, 0.f);
                             a.x = fmaf(wv, v.x, a.x); a.y = fmaf(wv, v.y, a.y); a.z = fmaf(wv, v.z, a.z); a.w = fmaf(wv, v.w, a.w);
                         }
-                        reinterpret_cast<float4*>(s_c + (size_t)grp * H)[tg] = a;
+                        if (tg < H4) reinterpret_cast<float4*>(s_c + (size_t)grp * H)[tg] = a;
                     }
-                    for (int j4 = tg + 256; j4 < H4; j4 += 256) {   // H > 1024 only
+                    for (int j4b = 256; j4b < H4; j4b += 256) {   // H > 1024 only
+                        const int j4 = j4b + tg;
                         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
                         for (int n = grp; n < len_max; n += 2) {
-                            const float4 v = __ldg(reinterpret_cast<const float4*>(af + (size_t)n * H) + j4);
-                            const float wv = s_e[n];
+                            const float wv = __shfl_sync(0xffffffffu, n < 32 ? wgt[0] : wgt[1], n & 31);
+                            const float4 v = j4 < H4 ? __ldg(reinterpret_cast<const float4*>(af + (size_t)n * H) + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
                             a.x = fmaf(wv, v.x, a.x); a.y = fmaf(wv, v.y, a.y); a.z = fmaf(wv, v.z, a.z); a.w = fmaf(wv, v.w, a.w);
                         }
-                        reinterpret_cast<float4*>(s_c + (size_t)grp * H)[j4] = a;
+                        if (j4 < H4) reinterpret_cast<float4*>(s_c + (size_t)grp * H)[j4] = a;
                     }
                     worker_bar();
                     MG_WSTAMP(44);
@@ -912,9 +910,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                 if (p.mode == 0) {
                     tok = bi;
                     lp = (m - m) - lz;
-                }
-#ifndef MG_LEAN
-                else {   // top-k sampling: q = log_softmax(logp / temp), keep the k best, Categorical over them (AttModel.py:296-303)
+                } else {   // top-k sampling: q = log_softmax(logp / temp), keep the k best, Categorical over them (AttModel.py:296-303)
                     // the scaled log-probs are evaluated ONCE per element: v[i] <- (logp / temp) - max, then q = that - log(sum).  The
                     // division is a multiplication by 1 / temp and the exponential comes from the ex2 unit (<= 2 ulp each, far below
                     // the 2e-5 bar): the IEEE division + libdevice expf were ~1000 instructions per thread and step, straight-line code
@@ -1021,9 +1017,6 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                     lp = ctl->topv[pos];
                     }
                 }
-#else
-                else { tok = 0; lp = 0.f; }
-#endif
                 if (wt == 0) {
                     const int unf = (t == 0 ? 1 : unfinished) && (tok > 0);
                     unfinished = unf;
@@ -1036,9 +1029,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_decode_kernel(const __grid
                 {   // the cells gather this token's xt_table row next: on its way into L2 while the token is published and polled for
                     const size_t row_bytes = (size_t)4 * H * sizeof(float);
                     const char* tr = reinterpret_cast<const char*>(p.xt_table) + (size_t)tok * row_bytes;
-#ifndef MG_NO_XT_PREFETCH
                     if (wt == 32) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(tr), "r"((uint32_t)row_bytes) : "memory");
-#endif
                 }
                 MG_WSTAMP(47);
                 sel_bar();

@@ -144,3 +144,28 @@ def test_compact_batch_host_side():
     dst2 = cb.empty_like("cpu")
     dst2.copy_(pk)                         # field-wise path (no common buffer)
     assert torch.equal(dst2.att_feats, cb.att_feats)
+
+
+def test_done_beams_is_a_lazy_list_of_lists():
+    """`model.done_beams` after a beam search (reference models/AttModel.py:229-231): per sub-graph the finished beams, best first, each a
+    dict seq / logps / unaug_p / p.  The product builds the dicts when they are looked at; indexing, length, iteration, slicing and
+    comparison must behave like the reference's list of lists."""
+    from subgc.model import _DoneBeams
+    g = torch.Generator().manual_seed(3)
+    n, b, T = 4, 3, 5
+    seq = torch.randint(0, 50, (n, b, T), generator=g)
+    lps = -torch.rand(n, b, T, generator=g)
+    up = -torch.rand(n, b, generator=g, dtype=torch.float64)
+    p = -torch.rand(n, b, generator=g, dtype=torch.float64)
+    cnt = torch.tensor([3, 2, 0, 1], dtype=torch.int32)
+    want = [[dict(seq=seq[k, j], logps=lps[k, j], unaug_p=float(up[k, j]), p=float(p[k, j])) for j in range(int(cnt[k]))] for k in range(n)]
+    got = _DoneBeams(seq, lps, up, p, cnt)
+    assert len(got) == n and [len(x) for x in got] == [3, 2, 0, 1]
+    for k, (beams, exp) in enumerate(zip(got, want)):
+        assert beams is got[k]            # built once
+        for a, e in zip(beams, exp):
+            assert torch.equal(a["seq"], e["seq"]) and torch.equal(a["logps"], e["logps"])
+            assert a["p"] == e["p"] and a["unaug_p"] == e["unaug_p"] and isinstance(a["p"], float)
+    assert got[-1] is got[n - 1] and got[1:3] == [got[1], got[2]]
+    with pytest.raises(IndexError):
+        got[n]
