@@ -1146,7 +1146,6 @@ __global__ void __maxnreg__(48) beam_topb_kernel(const BeamTopArgs a) {
     pdl_trigger();
     pdl_wait();
     __shared__ float redv[32];
-    __shared__ int redi[32];
     const int r = blockIdx.x, tid = threadIdx.x, q = r % a.b;
     if (a.t == 0 && q != 0) return;   // the <bos> step expands one row per sub-graph
     float v[kSelVals];
@@ -1194,6 +1193,13 @@ __global__ void __maxnreg__(48) beam_topb_kernel(const BeamTopArgs a) {
         if (j == a.V1 - 1) lp = lp - 1000.f;  // UNK suppression (CaptionModel.py:131)
         v[i] = lp;
     }
+    // top-b of the row, best first, first index on ties: every warp takes the b best of its own elements (b rounds of a shuffle
+    // arg-max, no block barrier), then warp 0 merges the sorted per-warp lists (each round the list heads compete, the winner's list
+    // moves up).  One barrier instead of three per round: the kernel is one block of 32 warps per row and was barrier-bound (78 us per
+    // step at 640 rows); a vocabulary index belongs to exactly one warp, so the result is the same list as b block-wide rounds.
+    __shared__ float cand_v[32][kMaxBeam];
+    __shared__ int cand_i[32][kMaxBeam];
+    const int lane = tid & 31, wid = tid >> 5;
     unsigned taken = 0;
     for (int c = 0; c < a.b; ++c) {
         float cv = -INFINITY;
@@ -1204,10 +1210,31 @@ __global__ void __maxnreg__(48) beam_topb_kernel(const BeamTopArgs a) {
             if (j >= a.V1 || ((taken >> i) & 1u)) continue;
             if (v[i] > cv || ci == 0x7fffffff) { cv = v[i]; ci = j; }
         }
-        block_argmax(cv, ci, redv, redi);
+        warp_argmax(cv, ci);
         if ((ci % kSelectThreads) == tid && ci != 0x7fffffff) taken |= 1u << (ci / kSelectThreads);
-        if (tid == 0) { a.ys[(size_t)r * kMaxBeam + c] = cv; a.ix[(size_t)r * kMaxBeam + c] = ci; }
-        __syncthreads();
+        if (lane == 0) { cand_v[wid][c] = cv; cand_i[wid][c] = ci; }
+    }
+    __syncthreads();
+    if (wid == 0) {
+        float lv[kMaxBeam];
+        int li[kMaxBeam];
+#pragma unroll
+        for (int c = 0; c < kMaxBeam; ++c) {
+            const bool have = c < a.b && lane < kSelectThreads / 32;
+            lv[c] = have ? cand_v[lane][c] : -INFINITY;
+            li[c] = have ? cand_i[lane][c] : 0x7fffffff;
+        }
+        for (int c = 0; c < a.b; ++c) {
+            float wv = lv[0];
+            int wi = li[0];
+            warp_argmax(wv, wi);
+            if (wi != 0x7fffffff && li[0] == wi) {   // this lane's head won: its list moves up
+#pragma unroll
+                for (int k = 0; k + 1 < kMaxBeam; ++k) { lv[k] = lv[k + 1]; li[k] = li[k + 1]; }
+                lv[kMaxBeam - 1] = -INFINITY; li[kMaxBeam - 1] = 0x7fffffff;
+            }
+            if (lane == 0) { a.ys[(size_t)r * kMaxBeam + c] = wv; a.ix[(size_t)r * kMaxBeam + c] = wi; }
+        }
     }
 }
 
