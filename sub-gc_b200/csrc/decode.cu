@@ -90,6 +90,7 @@ __device__ __forceinline__ float tanh_score(float x) {
     return copysignf(__fdividef(1.f - e, 1.f + e), x);
 }
 
+constexpr int kMaxBeamAtt = 8;    // beams per block of attention_beam_kernel (= kMaxBeam)
 constexpr int kAttThreads = 1024;  // one block per row; the row is latency-bound (28 MB of att / p_att per step over 128 rows), so every
                                    // warp slot of the SM is used to keep loads in flight
 
@@ -298,6 +299,152 @@ __global__ void __maxnreg__(48) attention_kernel(const float* __restrict__ atth_
     if (threadIdx.x == 0) trace_mark(trace, 1);   // scores done
     attention_tail(s_e, s_c, r, cr, att, masks, ctx, att_w, att_w_stride, len_max, H, c16_hi, c16_lo, Hp, trace, overflow, s_mask);
     trace_end(trace);
+}
+
+// ---- attention of a beam-search step: one block per SUB-GRAPH ------------------------------------------------------------------
+// The b beams of a sub-graph attend over the same p_att / att rows (rows_per_ctx = b).  attention_kernel runs one block per decode row
+// and reads them b times (640 blocks at beam 5: 68 us per step, L2- and latency-bound); here the block of a sub-graph reads every p_att
+// quad and every att row once and applies it to its b rows.  Per row the operations and their order are those of attention_kernel's fast
+// path (same split-K reduce, score partials per (node, slice) combined in slice order, the same one-warp softmax, four node groups
+// combined in the same fixed order), so the results are identical.
+constexpr int kBeamAttItems = 5;   // (node, 32-quad slice) items per warp: len_max * AH / 128 <= 160
+__global__ void __launch_bounds__(kAttThreads, 1) attention_beam_kernel(const float* __restrict__ atth_part, int splits, const float* __restrict__ h2att_b,
+                                                                       const float* __restrict__ p_att, const float* __restrict__ att,
+                                                                       const float* __restrict__ masks, const float* __restrict__ alpha_w,
+                                                                       const float* __restrict__ alpha_b, float* __restrict__ ctx, float* __restrict__ att_w,
+                                                                       int att_w_stride, int S, int len_max, int H, int AH, int b,
+                                                                       const int* __restrict__ active, unsigned short* __restrict__ c16_hi,
+                                                                       unsigned short* __restrict__ c16_lo, int Hp, int* overflow, int ld_part, int early_ok) {
+    pdl_trigger();
+    extern __shared__ float s_att[];   // [b][AH] atth | [AH] alpha_w | [b][64] e | [64] mask | [b][256] score partials | [4][b][H] context partials
+    float* s_h = s_att;
+    float* s_w = s_h + (size_t)b * AH;
+    float* s_e = s_w + AH;
+    float* s_mask = s_e + (size_t)b * 64;
+    float* s_sp = s_mask + 64;
+    float* s_c = s_sp + (size_t)b * 256;
+    const int cr = blockIdx.x, r0 = cr * b;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int AH4 = AH >> 2, Q = AH4 >> 5;
+    const int items = len_max * Q;
+    const float4* pa4 = reinterpret_cast<const float4*>(p_att + (size_t)cr * len_max * AH);
+    float4 pv[kBeamAttItems];
+    if (early_ok) {   // p_att / masks do not depend on this step (see attention_kernel)
+#pragma unroll
+        for (int k = 0; k < kBeamAttItems; ++k) {
+            const int item = wid + k * nw;
+            pv[k] = item < items ? __ldg(pa4 + (size_t)(item / Q) * AH4 + (item % Q) * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (threadIdx.x < len_max) s_mask[threadIdx.x] = __ldg(masks + (size_t)cr * len_max + threadIdx.x);
+    }
+    {
+        const char* af = reinterpret_cast<const char*>(att + (size_t)cr * len_max * H);
+        const size_t nb_a = (size_t)len_max * H * 4;
+        for (size_t o = (size_t)threadIdx.x * 128; o < nb_a; o += (size_t)blockDim.x * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(af + o));
+    }
+    for (int j = threadIdx.x; j < AH; j += blockDim.x) s_w[j] = __ldg(alpha_w + j);
+    pdl_wait();
+    if (active != nullptr && *active == 0) return;
+    if (!early_ok) {
+#pragma unroll
+        for (int k = 0; k < kBeamAttItems; ++k) {
+            const int item = wid + k * nw;
+            pv[k] = item < items ? pa4[(size_t)(item / Q) * AH4 + (item % Q) * 32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (threadIdx.x < len_max) s_mask[threadIdx.x] = masks[(size_t)cr * len_max + threadIdx.x];
+    }
+    for (int i = threadIdx.x; i < b * AH; i += blockDim.x) {
+        const int q = i / AH, j = i - q * AH;
+        float a = 0.f;
+        for (int z = 0; z < splits; ++z) a += atth_part[((size_t)z * S + r0 + q) * ld_part + j];
+        s_h[i] = a + __ldg(h2att_b + j);
+    }
+    __syncthreads();
+    {
+        const float4* w4 = reinterpret_cast<const float4*>(s_w);
+#pragma unroll
+        for (int k = 0; k < kBeamAttItems; ++k) {
+            const int item = wid + k * nw;
+            if (item >= items) continue;
+            const int j4 = (item % Q) * 32 + lane;
+            const float4 v = pv[k], ww = w4[j4];
+            for (int q = 0; q < b; ++q) {
+                const float4 hh = reinterpret_cast<const float4*>(s_h + (size_t)q * AH)[j4];
+                float a = ww.x * tanh_score(v.x + hh.x);
+                a = fmaf(ww.y, tanh_score(v.y + hh.y), a);
+                a = fmaf(ww.z, tanh_score(v.z + hh.z), a);
+                a = fmaf(ww.w, tanh_score(v.w + hh.w), a);
+                a = warp_sum(a);
+                if (lane == 0) s_sp[q * 256 + item] = a;
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < b * len_max; i += blockDim.x) {
+        const int q = i / len_max, n = i - q * len_max;
+        float e = 0.f;
+        for (int z = 0; z < Q; ++z) e += s_sp[q * 256 + n * Q + z];
+        s_e[q * 64 + n] = e + __ldg(alpha_b);
+    }
+    __syncthreads();
+    if (wid < b) {   // warp q: softmax / mask / renormalise of beam q (two-stage, as the reference; the sequence of attention_tail)
+        float* e = s_e + wid * 64;
+        float m = -INFINITY;
+        for (int n = lane; n < len_max; n += 32) m = fmaxf(m, e[n]);
+        m = warp_max(m);
+        float sum = 0.f;
+        for (int n = lane; n < len_max; n += 32) sum += expf(e[n] - m);
+        sum = warp_sum(sum);
+        float msum = 0.f;
+        for (int n = lane; n < len_max; n += 32) {
+            float wv = expf(e[n] - m) / sum;
+            wv = wv * s_mask[n];
+            e[n] = wv;
+            msum += wv;
+        }
+        msum = warp_sum(msum);
+        for (int n = lane; n < len_max; n += 32) {
+            const float wv = e[n] / msum;
+            e[n] = wv;
+            if (att_w) att_w[(size_t)(r0 + wid) * att_w_stride + n] = wv;
+        }
+    }
+    __syncthreads();
+    // context: four thread groups take interleaved node subsets (n = g, g + 4, ...); every att quad is loaded once for all beams
+    const float* af = att + (size_t)cr * len_max * H;
+    const int grp = threadIdx.x >> 8, tg = threadIdx.x & 255, H4 = H >> 2;
+    for (int j4 = tg; j4 < H4; j4 += 256) {
+        float4 acc[kMaxBeamAtt];
+#pragma unroll
+        for (int q = 0; q < kMaxBeamAtt; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 3
+        for (int n = grp; n < len_max; n += 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(af + (size_t)n * H) + j4);
+#pragma unroll
+            for (int q = 0; q < kMaxBeamAtt; ++q) {
+                if (q < b) {
+                    const float wv = s_e[q * 64 + n];
+                    acc[q].x = fmaf(wv, v.x, acc[q].x); acc[q].y = fmaf(wv, v.y, acc[q].y); acc[q].z = fmaf(wv, v.z, acc[q].z); acc[q].w = fmaf(wv, v.w, acc[q].w);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < kMaxBeamAtt; ++q)
+            if (q < b) reinterpret_cast<float4*>(s_c + ((size_t)grp * b + q) * H)[j4] = acc[q];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < b * H; i += blockDim.x) {
+        const int q = i / H, j = i - q * H;
+        const size_t gs = (size_t)b * H;
+        const float cv = ((s_c[(size_t)q * H + j] + s_c[gs + (size_t)q * H + j]) + s_c[2 * gs + (size_t)q * H + j]) + s_c[3 * gs + (size_t)q * H + j];
+        ctx[(size_t)(r0 + q) * H + j] = cv;
+        if (c16_hi) split_f16_store(cv, c16_hi, c16_lo, (size_t)(r0 + q) * Hp + j, overflow);
+    }
+}
+static size_t attention_beam_smem(int b, int AH, int H) { return (size_t)(b * AH + AH + b * 64 + 64 + b * 256 + 4 * b * H) * sizeof(float); }
+static bool attention_beam_ok(int S, int b, int len_max, int H, int AH) {
+    return b > 1 && b <= kMaxBeamAtt && S % b == 0 && (AH & 127) == 0 && (H & 3) == 0 && len_max <= 64 && len_max * (AH >> 7) <= kBeamAttItems * (kAttThreads / 32) &&
+           attention_beam_smem(b, AH, H) <= 200 * 1024;
 }
 
 // ---- fused attention phase of a decode step: one cluster kernel instead of cell + h2att GEMM + attention --------------------
@@ -1011,6 +1158,14 @@ static int launch_step(const subgc_dims* d, const subgc_weights* w, int S, int l
         p.active = active;
         if (!(skip & 4)) SUBGC_TRY(launch_gemm_raw(p, sc.gemm_ws, sc.gemm_ws_bytes, st, &rp));
         }
+        if (!(skip & 8) && attention_beam_ok(S, rows_per_ctx, len_max, H, AH) && !getenv("SUBGC_NO_BEAM_ATT")) {
+            static DeviceOnce once_ba;
+            SUBGC_CUDA(once_ba.run([]() { return cudaFuncSetAttribute(attention_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }));
+            launch_pdl(attention_beam_kernel, dim3(S / rows_per_ctx), dim3(kAttThreads), attention_beam_smem(rows_per_ctx, AH, H), st, rp.part, rp.splits, w->h2att.b,
+                       p_att, att, masks, w->alpha_net.w, w->alpha_net.b, sc.ctx, att_w, att_w_stride, S, len_max, H, AH, rows_per_ctx, active,
+                       out16 ? h16->ctx_hi : nullptr, out16 ? h16->ctx_lo : nullptr, out16 ? h16->Hp : 0, (int*)(out16 ? w->h3_overflow : nullptr),
+                       merged ? AH + 4 * H : AH, fc_pre != nullptr ? 1 : 0);
+        } else
         if (!(skip & 8)) launch_pdl(attention_kernel, dim3(S), dim3(kAttThreads), smem, st, rp.part, rp.splits, w->h2att.b, p_att, att, masks, w->alpha_net.w, w->alpha_net.b,
                                                                         sc.ctx, att_w, att_w_stride, S, len_max, H, AH, rows_per_ctx, active,
                                                                         out16 ? h16->ctx_hi : nullptr, out16 ? h16->ctx_lo : nullptr, out16 ? h16->Hp : 0, next_trace_slot(3),
