@@ -241,3 +241,27 @@ def test_other_baseline_configurations_match_oracle(mode, n_images):
     seq, lps = res[0].cpu(), res[1].cpu()
     assert torch.equal(seq, ref["seq"]), int((seq != ref["seq"]).sum())
     assert float((lps - ref["seqLogprobs"]).abs().max()) <= RTOL * max(1.0, float(ref["seqLogprobs"].abs().max()))
+
+
+def test_beam_attention_block_per_subgraph_equals_block_per_row(monkeypatch):
+    """Beam search runs the attention of the b rows that share a context in one block per sub-graph (attention_beam_kernel: p_att / att read
+    once); per row the operations are those of the block-per-row kernel, so sequences, log-probs and the finished-beam lists are identical."""
+    d = Dims()
+    sd = synth.make_state_dict(d, 41)
+    data = synth.make_test_inputs(d, 41, n_images=6, per_half=2, ragged=True, ragged_edges=True)
+    dev = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in data.items()}
+    args = [dev[k] for k in synth.SAMPLE_ARG_ORDER]
+    out = []
+    for off in (False, True):
+        if off:
+            monkeypatch.setenv("SUBGC_NO_BEAM_ATT", "1")
+        m = _model(d, sd, gpn_nms_thres=0.6, gpn_max_subg=3)
+        with torch.no_grad():
+            for _ in range(2):   # eager, then the captured graph
+                res = m(*args, opt={"beam_size": 5}, mode="sample")
+        out.append((res[0].clone(), res[1].clone(), [[(bm["seq"].clone(), bm["p"]) for bm in beams] for beams in m.done_beams]))
+    (s0, l0, b0), (s1, l1, b1) = out
+    assert torch.equal(s0, s1) and torch.equal(l0, l1)
+    assert len(b0) == len(b1)
+    for x, y in zip(b0, b1):
+        assert len(x) == len(y) and all(torch.equal(a[0], c[0]) and a[1] == c[1] for a, c in zip(x, y))
